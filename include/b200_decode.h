@@ -1,0 +1,120 @@
+/*
+ * b200_decode.h -- C ABI of the B200-native (sm_100a) quantised decode hot path:
+ *   paged MLA decode attention over a per-token-FP8 KV cache + block-scaled W8A8 FP8 GEMM.
+ *
+ * Drop-in boundary for meituan-longcat/SGLang-FluentLLM.  Each entry point names the reference interface it
+ * replaces (paths relative to the reference root).  Conventions:
+ *   - all pointers are DEVICE pointers unless stated; the caller owns every buffer (inputs, outputs, scratch), so
+ *     nothing is allocated here and every call is CUDA-graph capturable;
+ *   - `stream` is a cudaStream_t passed as void*;
+ *   - return value 0 = ok; non-zero = error, message via b200_last_error() (thread-local).  Nothing exits or aborts
+ *     the process (the reference's CHECK_CUDA does, csrc/kernels/ckv_fp8_per_token/utils.h:7-16);
+ *   - no global mutable state besides per-device attribute caches.
+ */
+#ifndef B200_DECODE_H_
+#define B200_DECODE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200_MLA_PAGE_SIZE 64              /* flashmla-fp8 csrc/kernels/ckv_fp8_per_token/config.h:6 */
+#define B200_MLA_BLOCK_M 64                /* config.h:5: q rows per CTA */
+#define B200_MLA_FIXED_OVERHEAD_BLOCKS 5   /* config.h:14 */
+#define B200_MLA_METADATA_INTS 8           /* params.h:72 TileSchedulerMetaDataSize */
+#define B200_MLA_HEAD_DIM_V 512
+#define B200_MLA_HEAD_DIM_ROPE 64
+
+/* Last error message of the calling thread ("" if none). */
+const char* b200_last_error(void);
+
+/* Number of SMs of the current device (148 on B200). */
+int b200_sm_count(void);
+
+/* num_sm_parts = sm_count / num_heads_k / ceil(num_heads_per_head_k / 64).
+ * Replaces the shape rule in 3rdparty/flashmla-fp8/csrc/flash_api.cpp:41-43. */
+int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_count);
+
+/* Tile-scheduler metadata.  Replaces flash_mla_fp8.get_mla_metadata
+ * (flash_mla_fp8/flash_mla_interface.py:8-23 -> csrc/flash_api.cpp:27-63 -> csrc/kernels/get_mla_metadata.cu:8-82).
+ *   cache_seqlens            int32 [batch]
+ *   tile_scheduler_metadata  int32 [num_sm_parts][8]  {begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, 0,0,0}
+ *   num_splits               int32 [batch + 1]        prefix sums of the per-request split counts */
+int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
+                          int32_t* num_splits, void* stream);
+
+/* Per-(token, head) FP8 quantiser for q.  Replaces flash_mla_fp8.quantize_ckv_per_token_head
+ * (csrc/flash_api.cpp:399-460, cache_kernels.cu:27-122).
+ *   q       bf16 [rows][576] contiguous      q_nope  e4m3 [rows][512]
+ *   q_scale f32  [rows]                      q_rope  bf16 [rows][64]  (divided by the same scale) */
+int b200_mla_quantize_q(const void* q, int64_t rows, int head_dim, int head_dim_v, void* q_nope, float* q_scale,
+                        void* q_rope, void* stream);
+
+/* Quantise new K tokens and scatter them into the paged pool.  Replaces flash_mla_fp8.quantize_and_cache_k
+ * (csrc/flash_api.cpp:462-532, cache_kernels.cu:140-250).
+ *   key bf16 [n][key_row_stride >= 576]; indices int32 [n] token slots;
+ *   pool: k_lora_cache e4m3 [slots][512], k_scale_cache f32 [slots], k_rope_cache bf16 [slots][64]
+ *   (the MLATokenToKVPool per_token_head layout, python/sglang/srt/mem_cache/memory_pool.py:635-649). */
+int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64_t n, int head_dim, int head_dim_v,
+                                  const int32_t* indices, void* k_lora_cache, float* k_scale_cache, void* k_rope_cache,
+                                  void* stream);
+
+/* Gather + de-quantise pool entries.  Replaces flash_mla_fp8.dequantize_ckv_fused_indexed
+ * (csrc/flash_api.cpp:534-632, cache_kernels.cu:274-423).  max_num_tokens > 0 fixes the grid for CUDA graphs.
+ *   k_lora_out bf16 [n][512], k_rope_out bf16 [n][64] */
+int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cache, const float* k_scale_cache,
+                                const int32_t* indices, int64_t n, int64_t max_num_tokens, void* k_lora_out,
+                                void* k_rope_out, void* stream);
+
+/* Scratch the decode call needs: o_accum f32 [(batch + num_sm_parts)][M][512] then lse_accum f32 [(..)][M]
+ * (same sizing as csrc/flash_api.cpp:365-368); M = s_q * h_q. */
+size_t b200_mla_workspace_bytes(int batch, int s_q, int h_q, int num_sm_parts);
+
+/* Paged MLA decode attention over the per-token-FP8 KV pool (split-KV + combine).
+ * Replaces flash_mla_fp8.flash_mla_ckv_fp8_per_token (flash_mla_interface.py:68-120 ->
+ * csrc/flash_api.cpp:216-397 -> ckv_fp8_per_token/splitkv_mla.cu:1147-1515 + mla_combine.cu:16-154).
+ *   q_nope e4m3 [b][s_q][h_q][512]   q_rope bf16 [b][s_q][h_q][64]   q_scale f32 [b][s_q][h_q]   (contiguous)
+ *   k_lora e4m3 [num_pages*64][512]  k_rope bf16 [num_pages*64][64]  k_scale f32 [num_pages*64]  (token-major pool)
+ *   block_table int32 [b][block_table_stride]   cache_seqlens int32 [b]
+ *   tile_scheduler_metadata / num_splits from b200_mla_get_metadata (num_sm_parts rows)
+ *   out bf16 [b][s_q][h_q][512]      lse f32 [b][h_q][s_q]
+ *   workspace >= b200_mla_workspace_bytes(...) */
+int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, const float* q_scale, const void* k_lora,
+                                      const void* k_rope, const float* k_scale, int64_t num_pages,
+                                      const int32_t* block_table, int64_t block_table_stride,
+                                      const int32_t* cache_seqlens, const int32_t* tile_scheduler_metadata,
+                                      const int32_t* num_splits, int num_sm_parts, int batch, int s_q, int h_q,
+                                      float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
+                                      size_t workspace_bytes, int use_pdl, void* stream);
+
+/* Split-KV combine (also run by the decode call).  Replaces ckv_fp8_per_token/mla_combine.cu:16-154. */
+int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
+                     int batch, int s_q, int h_q, int use_pdl, void* stream);
+
+/* 1x128 activation quantiser, column-major TMA-aligned scales.  Replaces sgl_per_token_group_quant_fp8
+ * (3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-520; python wrapper
+ * python/sglang/srt/layers/dense/gemms/fp8/fp8_kernel.py:430-463).
+ *   x bf16 [m][k]; q e4m3 [m][k]; scales f32 [k/128][scale_stride], scale_stride = m rounded up to 4. */
+int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* scales, int64_t scale_stride, float eps,
+                         void* stream);
+
+/* Block-scaled W8A8 FP8 GEMM, out[m][n] = bf16( sum_kb a_scales[kb][i] * b_scales[n/128][kb] * (A_kb . B_kb^T) ).
+ * Replaces deep_gemm.gemm_fp8_fp8_bf16_nt (3rdparty/deep_gemm/deep_gemm/jit_kernels/gemm.py:145-226 ->
+ * include/deep_gemm/fp8_gemm.cuh:60-399,409-827); same argument order as the JIT'd
+ * `launch(lhs, lhs_scales, rhs, rhs_scales, out, m, stream, ...)` C symbol (deep_gemm/jit/template.py:57-79).
+ *   a e4m3 [m][k]; a_scales f32 [k/128][a_scale_stride] (column-major, stride = m rounded up to 4);
+ *   b e4m3 [n][k]; b_scales f32 [ceil(n/128)][k/128]; out bf16 [m][n].  Requires n % 64 == 0, k % 128 == 0. */
+int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b, const float* b_scales,
+                     void* out, int m, int n, int k, int use_pdl, void* stream);
+
+/* Hardware self-test of the hand-built UMMA shared-memory / instruction descriptors (csrc/umma_lab.cu).
+ * Writes max|got-expected|/max|expected| of one operand-layout variant to *rel_err. */
+int b200_umma_selftest(int variant, int n, float* rel_err);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200_DECODE_H_ */

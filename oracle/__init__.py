@@ -1,0 +1,21 @@
+"""CPU oracle for the B200 quantised-decode hot path.
+
+TEST INFRASTRUCTURE ONLY.  Nothing under ``oracle/`` is imported by the product
+package (``sglang_fluentllm_b200``).  Only ``tests/``, ``__graft_entry__.smoke()``
+and the ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it,
+and there only as the checker / the reported CPU baseline.
+
+Every function is a plain numpy / torch-CPU restatement of the reference's
+algorithm and cites the reference file:line it follows (paths relative to
+``/root/reference``).
+
+Pinning status (see DESIGN.md "Oracle pinning"):
+  * quantiser fall-back, indexed dequant, block-table allocator, torch-native
+    SDPA decode, block-FP8 GEMM and 1x128 activation quantiser are pinned by
+    golden vectors generated from the reference's own Python (tests/golden/).
+  * the per-token-FP8 MLA decode kernel and the metadata scheduler exist in the
+    reference only as sm_90a CUDA (wgmma) that cannot execute on this box; their
+    restatements are pinned only through the semantic (dequantise -> fp32
+    attention) flavour and the reference's own 5e-2 test criterion:
+    PARITY UNPINNED for the bit-level behaviour of those two.
+"""

@@ -1,0 +1,69 @@
+"""ctypes binding of the in-tree C-ABI library (include/b200_decode.h).
+
+There is no CPU or eager fallback: if the library is missing or a call fails, a RuntimeError is raised.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "_C", "libb200decode.so")
+
+_P = c_void_p
+_SIGNATURES = {
+    "b200_last_error": (c_char_p, []),
+    "b200_sm_count": (c_int, []),
+    "b200_mla_num_sm_parts": (c_int, [c_int, c_int, c_int]),
+    "b200_mla_get_metadata": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "b200_mla_quantize_q": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P]),
+    "b200_mla_quantize_and_cache_k": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "b200_mla_dequantize_indexed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P]),
+    "b200_mla_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200_mla_decode_ckv_fp8_per_token": (
+        c_int,
+        [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P,
+         _P, c_size_t, c_int, _P],
+    ),
+    "b200_mla_combine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_act_quant_1x128": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),
+    "b200_fp8_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_umma_selftest": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
+}
+EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """Load (once) and return the library; raise loudly when it is absent."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "sglang_fluentllm_b200: %s not found -- run `python __graft_entry__.py` (nvcc, sm_100a) first; "
+                "there is no CPU fallback for this path" % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(handle, name)  # AttributeError if the symbol is missing
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def check(rc: int, what: str) -> None:
+    if rc != 0:
+        msg = lib().b200_last_error()
+        raise RuntimeError("%s failed (rc=%d): %s" % (what, rc, msg.decode() if msg else "?"))
+
+
+def ptr(t) -> int:
+    return t.data_ptr()
+
+
+def current_stream(device=None) -> int:
+    import torch
+
+    return torch.cuda.current_stream(device).cuda_stream

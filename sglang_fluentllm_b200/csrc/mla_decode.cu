@@ -1,0 +1,599 @@
+// Paged MLA decode attention over the per-token-FP8 KV pool, sm_100a (tcgen05 + TMEM + TMA).
+//
+// Replaces ckv_fp8_per_token::flash_fwd_splitkv_mla_kernel of the reference
+// (3rdparty/flashmla-fp8/csrc/kernels/ckv_fp8_per_token/splitkv_mla.cu:1147-1515, host side
+// csrc/flash_api.cpp:216-397).  Same split-KV work partition (tile-scheduler metadata), same arithmetic contract
+// (e4m3 x e4m3 -> f32 for the 512 "nope" dims + bf16 x bf16 -> same f32 accumulator for the 64 rope dims, logits
+// scaled by q_scale * k_scale, V-dequant scale folded into P, P re-quantised to e4m3 before P.V), different
+// machine mapping:
+//
+//   SwapAB everywhere: KV tokens sit on the UMMA M side (128 tokens = 2 pages per tile), the q rows of one request
+//   (HB = 16/32/64 per CTA) on the UMMA N side.
+//       S^T[128 tok, HB]  = K_nope[128, 512] . Qn^T  (16 x kind::f8f6f4, K-major SW128, straight from TMA)
+//                         + K_rope[128, 64]  . Qr^T  ( 4 x kind::f16 into the same TMEM accumulator)
+//       O^T[512 d, HB]   += V^T[512, 128 tok] . P[128 tok, HB]
+//   V^T is the *same* shared-memory bytes as K_nope, described MN-major to the tensor core -- the reference's
+//   LDSM/byte_perm/STSM transpose of V (ckv_fp8_per_token/utils.h:39-147) disappears.
+//   The four 128-byte k-chunks of the QK contraction are exactly the four 128-lane M tiles of the PV product.
+//
+//   Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = UMMA issuer, warps 2-5 = softmax /
+//   correction / epilogue (one thread per KV token = one TMEM lane).
+//   TMEM: S double-buffered (2 x HB columns) + O (4 x HB columns).
+//
+//   Online softmax keeps a per-q-row reference (m_ref, p_scale) in shared memory and only moves it -- and rescales
+//   O in TMEM -- when a tile's P would overflow e4m3 under the current reference ("lazy rescale").  The reference
+//   kernel re-derives p_scale = rowmax(P)/448 for every 64-token page and rescales O each time (splitkv_mla.cu:
+//   420-455); here the row sum L is kept per token-lane in registers and reduced once per request.
+#include <cuda_bf16.h>
+#include <math.h>
+#include <string.h>
+
+#include "b200_decode.h"
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kTileTokens = 128;
+static constexpr int kPage = B200_MLA_PAGE_SIZE;
+static constexpr int kStages = 2;
+static constexpr int kNopeChunkBytes = kTileTokens * 128;     // one 128-byte k-chunk of a tile: 16 KB
+static constexpr int kStageNopeBytes = 4 * kNopeChunkBytes;   // 64 KB
+static constexpr int kStageRopeBytes = kTileTokens * 128;     // 16 KB
+static constexpr int kStageBytes = kStageNopeBytes + kStageRopeBytes;
+static constexpr int kPageTxBytes = kPage * 512 + kPage * 128;
+static constexpr int kNumThreads = 192;
+static constexpr int kSoftmaxThreads = 128;
+static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
+static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
+static constexpr float kHeadroom = 8.0f;                      // lazy rescale: new reference leaves 2^3 of growth
+
+struct MlaParams {
+  CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;
+  const float* q_scale;
+  const float* k_scale;
+  const int32_t* block_table;
+  int64_t block_table_stride;
+  const int32_t* seqlens;
+  const int32_t* meta;
+  const int32_t* num_splits;
+  __nv_bfloat16* out;
+  float* lse;
+  float* o_accum;
+  float* lse_accum;
+  int batch, s_q, h_q, M;
+  float scale_log2;
+  int is_causal;
+};
+
+template <int HB>
+struct SmemLayout {
+  static constexpr int kQBytes = HB * 640;           // 4 nope chunks [HB x 128 B] + rope [HB x 128 B]
+  static constexpr int kPBytes = HB * kTileTokens;   // [HB/16 chunks][16 groups][8 tokens][16 q]
+  static constexpr int kOffKV = 0;
+  static constexpr int kOffQ = kStages * kStageBytes;
+  static constexpr int kOffP = kOffQ + kQBytes;
+  static constexpr int kOffSmall = kOffP + 2 * kPBytes;
+  static constexpr int kTotal = kOffSmall + 4096;
+};
+
+struct SmallSmem {
+  uint64_t kv_full[kStages], kv_empty[kStages];
+  uint64_t q_full, q_empty;
+  uint64_t s_full[2], p_full[2];
+  uint64_t pv_done, o_free;
+  uint32_t tmem_base;
+  uint32_t trig[3];
+  float f[64];        // q_scale * softmax_scale * log2(e)
+  float mref[64];     // reference max (log2 domain)
+  float ps[64];       // reference P scale
+  float mprime[64];   // mref + log2(ps)
+  float fac[64];      // rescale factor of the last reference move
+  float lsum[64];
+  int32_t lim[64];    // per q row: first masked token index
+  float red[4][64];
+};
+static_assert(sizeof(SmallSmem) <= 4096, "SmallSmem too large");
+
+// The work of one (sm part, request) pair.
+struct Segment {
+  int batch_idx, seqlen, start_block, end_block, n_tiles, valid_end, split_idx;
+  bool no_split;
+};
+
+__device__ __forceinline__ int mask_len(int s_q, int h_q, int M, int row) {  // splitkv_mla.cu:1136-1145
+  return row < M ? s_q - row / h_q - 1 : 0;
+}
+
+__device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_idx, int begin_idx, int begin_seqlen,
+                                                int end_idx, int end_seqlen, int begin_n_split, int q_row0, int hb) {
+  Segment s;
+  s.batch_idx = batch_idx;
+  s.seqlen = __ldg(p.seqlens + batch_idx);
+  s.start_block = batch_idx == begin_idx ? begin_seqlen / kPage : 0;
+  const int full_blocks = (s.seqlen + kPage - 1) / kPage;
+  int end_block = batch_idx == end_idx ? (end_seqlen + kPage - 1) / kPage : full_blocks;
+  s.no_split = (s.start_block == 0 && end_block == full_blocks);  // splitkv_mla.cu:1239
+  if (p.is_causal) {                                              // splitkv_mla.cu:1242-1266
+    const int last_row = min(q_row0 + hb, p.M) - 1;
+    int lim = s.seqlen - mask_len(p.s_q, p.h_q, p.M, last_row);
+    if (batch_idx == end_idx) lim = min(lim, end_seqlen);
+    end_block = (max(lim, 0) + kPage - 1) / kPage;
+  }
+  s.end_block = max(end_block, s.start_block);
+  s.n_tiles = (s.end_block - s.start_block + 1) / 2;
+  s.valid_end = min(s.seqlen, s.end_block * kPage);
+  const int n_split_idx = batch_idx == begin_idx ? begin_n_split : 0;
+  s.split_idx = __ldg(p.num_splits + batch_idx) + n_split_idx;  // splitkv_mla.cu:1490
+  return s;
+}
+
+template <int HB>
+__global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
+  using L = SmemLayout<HB>;
+  constexpr uint32_t kTmemCols = HB == 64 ? 512 : (HB == 32 ? 256 : 128);
+  constexpr uint32_t kColS = 0, kColO = 2 * HB;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_kv = smem + L::kOffKV;
+  uint8_t* s_q = smem + L::kOffQ;
+  uint8_t* s_p = smem + L::kOffP;
+  SmallSmem& sm = *reinterpret_cast<SmallSmem*>(smem + L::kOffSmall);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int q_block = blockIdx.x, part = blockIdx.z;
+  const int q_row0 = q_block * HB;
+  const int n_valid_q = min(HB, p.M - q_row0);
+
+  const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
+  const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
+            end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
+  if (begin_idx >= p.batch) return;  // splitkv_mla.cu:1226
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&sm.kv_full[i], 1);
+      mbar_init(&sm.kv_empty[i], 1);
+    }
+    mbar_init(&sm.q_full, 1);
+    mbar_init(&sm.q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.p_full[i], kSoftmaxThreads);
+    }
+    mbar_init(&sm.pv_done, 1);
+    mbar_init(&sm.o_free, kSoftmaxThreads);
+    sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_q_nope);
+    tma_prefetch_desc(&p.tm_q_rope);
+    tma_prefetch_desc(&p.tm_k_nope);
+    tma_prefetch_desc(&p.tm_k_rope);
+  }
+  if (warp == 1) tmem_alloc(&sm.tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      const uint64_t pol_kv = policy_evict_first();
+      const bool shared_kv = gridDim.x > 1;  // sibling q-block CTAs stream the same pages: let L2 keep them
+      uint32_t g = 0, seg_i = 0;
+      for (int b = begin_idx; b <= end_idx; ++b) {
+        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+        if (sg.n_tiles == 0) continue;
+        // Q tile of this request (rows beyond the request are masked by the consumers)
+        mbar_wait(&sm.q_empty, (seg_i & 1) ^ 1);
+        ++seg_i;
+        mbar_arrive_expect_tx(&sm.q_full, L::kQBytes);
+        const int qrow = b * p.M + q_row0;
+        for (int c = 0; c < 4; ++c) tma_load_2d(s_q + c * HB * 128, &p.tm_q_nope, &sm.q_full, c * 128, qrow);
+        tma_load_2d(s_q + 4 * HB * 128, &p.tm_q_rope, &sm.q_full, 0, qrow);
+        const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+          const uint32_t st = g % kStages;
+          mbar_wait(&sm.kv_empty[st], ((g / kStages) & 1) ^ 1);
+          const int blk0 = sg.start_block + 2 * t;
+          const int npages = min(2, sg.end_block - blk0);
+          mbar_arrive_expect_tx(&sm.kv_full[st], npages * kPageTxBytes);
+          uint8_t* stage = s_kv + st * kStageBytes;
+          for (int pg = 0; pg < npages; ++pg) {
+            const int tok0 = __ldg(bt + blk0 + pg) * kPage;
+            if (shared_kv) {
+              for (int c = 0; c < 4; ++c)
+                tma_load_2d(stage + c * kNopeChunkBytes + pg * (kPage * 128), &p.tm_k_nope, &sm.kv_full[st], c * 128,
+                            tok0);
+              tma_load_2d(stage + kStageNopeBytes + pg * (kPage * 128), &p.tm_k_rope, &sm.kv_full[st], 0, tok0);
+            } else {
+              for (int c = 0; c < 4; ++c)
+                tma_load_2d_hint(stage + c * kNopeChunkBytes + pg * (kPage * 128), &p.tm_k_nope, &sm.kv_full[st],
+                                 c * 128, tok0, pol_kv);
+              tma_load_2d_hint(stage + kStageNopeBytes + pg * (kPage * 128), &p.tm_k_rope, &sm.kv_full[st], 0, tok0,
+                               pol_kv);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== UMMA issuer ==============================
+    if (lane == 0) {
+      constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, HB);
+      constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, HB);
+      constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
+      const uint32_t kv_addr = smem_u32(s_kv), q_addr = smem_u32(s_q), p_addr = smem_u32(s_p);
+      uint32_t g = 0, o_seg = 0;
+      for (int b = begin_idx; b <= end_idx; ++b) {
+        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+        if (sg.n_tiles == 0) continue;
+        mbar_wait(&sm.q_full, o_seg & 1);
+        auto issue_qk = [&](uint32_t gi) {
+          const uint32_t st = gi % kStages;
+          mbar_wait(&sm.kv_full[st], (gi / kStages) & 1);
+          tc_fence_after();
+          const uint32_t stage = kv_addr + st * kStageBytes;
+          const uint32_t d = tmem + kColS + (gi & 1) * HB;
+#pragma unroll
+          for (int c = 0; c < 4; ++c)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_f8(d, make_smem_desc(stage + c * kNopeChunkBytes + s * 32, 0, 1024, SWZ_128B),
+                      make_smem_desc(q_addr + c * HB * 128 + s * 32, 0, 1024, SWZ_128B), idesc_qk8, (c | s) != 0);
+#pragma unroll
+          for (int s = 0; s < 4; ++s)
+            umma_f16(d, make_smem_desc(stage + kStageNopeBytes + s * 32, 0, 1024, SWZ_128B),
+                     make_smem_desc(q_addr + 4 * HB * 128 + s * 32, 0, 1024, SWZ_128B), idesc_qk16, 1);
+          umma_commit(&sm.s_full[gi & 1]);
+        };
+        issue_qk(g);
+        for (int t = 0; t < sg.n_tiles; ++t) {
+          const uint32_t gi = g + t;
+          if (t + 1 < sg.n_tiles) issue_qk(gi + 1);
+          else umma_commit(&sm.q_empty);  // all QK MMAs of this request issued: Q smem reusable once they finish
+          // ---- P.V for tile gi ----
+          mbar_wait(&sm.p_full[gi & 1], (gi >> 1) & 1);
+          if (t == 0 && o_seg > 0) mbar_wait(&sm.o_free, (o_seg - 1) & 1);
+          tc_fence_after();
+          const uint32_t st = gi % kStages;
+          const uint32_t stage = kv_addr + st * kStageBytes;
+          const int tile_start = (sg.start_block + 2 * t) * kPage;
+          const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
+          const uint32_t pbuf = p_addr + (gi & 1) * L::kPBytes;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            for (int s = 0; s < nk; ++s)
+              umma_f8(tmem + kColO + j * HB,
+                      make_smem_desc(stage + j * kNopeChunkBytes + s * 4096, 16384, 1024, SWZ_128B),
+                      make_smem_desc(pbuf + s * 512, 128, 2048, SWZ_NONE), idesc_pv, (t | s) != 0);
+          umma_commit(&sm.kv_empty[st]);
+          umma_commit(&sm.pv_done);
+        }
+        g += sg.n_tiles;
+        ++o_seg;
+      }
+    }
+  } else {
+    // ============================== softmax / correction / epilogue ==============================
+    const int st_id = tid - 64;                 // 0..127 within the softmax group
+    const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int tl = quad * 32 + lane;            // token lane within the tile
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    uint32_t g = 0, o_seg = 0;
+    float lt[HB];                               // per-lane partial row sums, units of 1/ps relative to mref
+
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+      // ---- per-request state ----
+      named_bar_sync(1, kSoftmaxThreads);  // previous request's readers of sm.* are done
+      if (st_id < HB) {
+        const int row = q_row0 + st_id;
+        const bool vq = st_id < n_valid_q;
+        sm.f[st_id] = vq ? __ldg(p.q_scale + (int64_t)b * p.M + row) * p.scale_log2 : 0.f;
+        sm.mref[st_id] = kMInit;
+        sm.ps[st_id] = 1.f;
+        sm.mprime[st_id] = kMInit;
+        sm.lsum[st_id] = 0.f;
+        int lim = 0;
+        if (vq) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, row), sg.end_block * kPage) : sg.valid_end;
+        sm.lim[st_id] = lim;
+      }
+      named_bar_sync(1, kSoftmaxThreads);
+#pragma unroll
+      for (int q = 0; q < HB; ++q) lt[q] = 0.f;
+      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+      const bool all_q_valid = n_valid_q == HB && !p.is_causal;
+
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        const uint32_t buf = g & 1;
+        const int tile_start = (sg.start_block + 2 * t) * kPage;
+        const int token = tile_start + tl;
+        const bool tok_valid = token < sg.valid_end;
+        float ks = 0.f;
+        if (tok_valid) {
+          const int page = __ldg(bt + sg.start_block + 2 * t + (tl >> 6));
+          ks = __ldg(p.k_scale + (int64_t)page * kPage + (tl & 63));
+        }
+        const bool full_tile = all_q_valid && (tile_start + kTileTokens <= sg.valid_end);
+        if (st_id == 0) sm.trig[(g + 1) % 3] = 0;
+
+        mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        float x[HB];
+        const uint32_t s_addr = tmem + kColS + buf * HB + lane_addr;
+        tmem_ld<HB>(s_addr, x);
+        tmem_wait_ld();
+
+        uint32_t pk[HB / 4];
+        bool trigger = (t == 0);
+        if (!trigger) {
+          // ---- fast path: reuse the current reference ----
+          float vmax = 0.f;
+#pragma unroll
+          for (int q = 0; q < HB; ++q) {
+            float arg = fmaf(x[q] * sm.f[q], ks, -sm.mprime[q]);
+            if (!full_tile && !(token < sm.lim[q])) arg = -INFINITY;
+            const float u = ex2_approx(arg);
+            x[q] = u;
+            vmax = fmaxf(vmax, u * ks);
+          }
+#pragma unroll
+          for (int q = 0; q < HB; q += 4)
+            pk[q / 4] = cvt_e4m3x4(x[q] * ks, x[q + 1] * ks, x[q + 2] * ks, x[q + 3] * ks);
+          const bool over = vmax > 448.f;
+          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[g % 3] = 1;
+          named_bar_sync(1, kSoftmaxThreads);
+          trigger = sm.trig[g % 3] != 0;
+          if (!trigger) {
+#pragma unroll
+            for (int q = 0; q < HB; ++q) lt[q] += x[q];
+          }
+        }
+        if (trigger) {
+          // ---- slow path: move the reference (m_ref, p_scale), rescale O and L ----
+          if (t != 0) {
+            tmem_ld<HB>(s_addr, x);
+            tmem_wait_ld();
+          }
+#pragma unroll
+          for (int q = 0; q < HB; ++q) {
+            float z = (x[q] * sm.f[q]) * ks;
+            if (!(token < sm.lim[q])) z = -INFINITY;
+            x[q] = z;
+            const float wm = warp_max_f32(z);
+            if ((q & 31) == lane) sm.red[quad][q] = wm;
+          }
+          named_bar_sync(1, kSoftmaxThreads);
+          float m_old = 0.f, m_new = 0.f;
+          if (st_id < HB) {
+            const float cm = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
+            m_old = sm.mref[st_id];
+            m_new = fmaxf(m_old, cm);
+            sm.mprime[st_id] = m_new;  // temporarily: plain new max, p_scale applied below
+          }
+          named_bar_sync(1, kSoftmaxThreads);
+#pragma unroll
+          for (int q = 0; q < HB; ++q) {
+            const float pp = ex2_approx(x[q] - sm.mprime[q]) * ks;
+            const float wm = warp_max_f32(pp);
+            if ((q & 31) == lane) sm.red[quad][q] = wm;
+          }
+          named_bar_sync(1, kSoftmaxThreads);
+          if (st_id < HB) {
+            float pmax = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
+            pmax = fmaxf(pmax, kPMin);
+            const float ps_new = pmax * (kHeadroom / 448.f);
+            const float ps_old = sm.ps[st_id];
+            sm.fac[st_id] = exp2f(m_old - m_new) * (ps_old / ps_new);
+            sm.mref[st_id] = m_new;
+            sm.ps[st_id] = ps_new;
+            sm.mprime[st_id] = m_new + log2f(ps_new);
+          }
+          named_bar_sync(1, kSoftmaxThreads);
+          if (t != 0) {
+            // all P.V up to the previous tile must have landed in O before it is rescaled
+            mbar_wait(&sm.pv_done, (g - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c0 = 0; c0 < HB; c0 += 16) {
+                float o[16];
+                const uint32_t a = tmem + kColO + j * HB + c0 + lane_addr;
+                tmem_ld<16>(a, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 16; ++k) o[k] *= sm.fac[c0 + k];
+                tmem_st<16>(a, o);
+              }
+            tmem_wait_st();
+#pragma unroll
+            for (int q = 0; q < HB; ++q) lt[q] *= sm.fac[q];
+          }
+#pragma unroll
+          for (int q = 0; q < HB; ++q) {
+            const float u = ex2_approx(x[q] - sm.mprime[q]);
+            lt[q] += u;
+            x[q] = u * ks;
+          }
+#pragma unroll
+          for (int q = 0; q < HB; q += 4) pk[q / 4] = cvt_e4m3x4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+        }
+
+        // ---- publish P (B operand of P.V: [token][q], MN-major, 8x16-byte core matrices) ----
+        uint8_t* pbuf = s_p + buf * L::kPBytes;
+#pragma unroll
+        for (int c = 0; c < HB / 16; ++c)
+          *reinterpret_cast<uint4*>(pbuf + c * 2048 + (tl >> 3) * 128 + (tl & 7) * 16) =
+              make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        // rows past the end of the sequence feed P.V with P = 0; make sure V there is finite (0 * NaN).
+        // Reference: fill_oob_V, splitkv_mla.cu:698-721.
+        if (!tok_valid) {
+          const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
+          if (tl < nk * 32) {
+            uint8_t* stage = s_kv + (g % kStages) * kStageBytes;
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              uint4* row = reinterpret_cast<uint4*>(stage + c * kNopeChunkBytes + tl * 128);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) row[k] = make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        mbar_arrive(&sm.p_full[buf]);
+      }
+
+      // ---- epilogue of this request: O^T / L -> out (or split partials) ----
+#pragma unroll
+      for (int q = 0; q < HB; ++q) {
+        float v = lt[q];
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) atomicAdd(&sm.lsum[q], v);
+      }
+      named_bar_sync(1, kSoftmaxThreads);
+      if (sg.n_tiles > 0) {
+        mbar_wait(&sm.pv_done, (g - 1) & 1);
+        tc_fence_after();
+      }
+      const int64_t out_row0 = (int64_t)b * p.M + q_row0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+#pragma unroll
+        for (int c0 = 0; c0 < HB; c0 += 16) {
+          float o[16];
+          if (sg.n_tiles > 0) {
+            tmem_ld<16>(tmem + kColO + j * HB + c0 + lane_addr, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) o[k] = 0.f;
+          }
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const int q = c0 + k;
+            if (q < n_valid_q) {
+              const float l = sm.lsum[q];
+              const float inv = (l == 0.f || l != l) ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
+              const float val = o[k] * inv;
+              const int d = j * 128 + tl;
+              if (sg.no_split) p.out[(out_row0 + q) * 512 + d] = __float2bfloat16_rn(val);
+              else p.o_accum[((int64_t)sg.split_idx * p.M + q_row0 + q) * 512 + d] = val;
+            }
+          }
+        }
+      }
+      if (st_id < n_valid_q) {
+        const int row = q_row0 + st_id;
+        const float l = sm.lsum[st_id];
+        const bool bad = (l == 0.f || l != l);
+        const float lse2 = log2f(l) + sm.mprime[st_id];
+        if (sg.no_split) {
+          const int s = row / p.h_q, h = row % p.h_q;
+          p.lse[((int64_t)b * p.h_q + h) * p.s_q + s] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
+        } else {
+          p.lse_accum[(int64_t)sg.split_idx * p.M + row] = bad ? -INFINITY : lse2;                    // :1506
+        }
+      }
+      if (sg.n_tiles > 0) {
+        tc_fence_before();
+        mbar_arrive(&sm.o_free);
+        ++o_seg;
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, kTmemCols);
+}
+
+template <int HB>
+static int launch_mla(const MlaParams& prm, int q_blocks, int num_sm_parts, cudaStream_t stream) {
+  const int smem = SmemLayout<HB>::kTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  mla_decode_kernel<HB><<<dim3(q_blocks, 1, num_sm_parts), kNumThreads, smem, stream>>>(prm);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+size_t b200_mla_workspace_bytes(int batch, int s_q, int h_q, int num_sm_parts) {
+  const size_t M = (size_t)s_q * h_q;
+  const size_t splits = (size_t)batch + num_sm_parts;
+  return splits * M * 512 * sizeof(float) + splits * M * sizeof(float);
+}
+
+int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, const float* q_scale, const void* k_lora,
+                                      const void* k_rope, const float* k_scale, int64_t num_pages,
+                                      const int32_t* block_table, int64_t block_table_stride,
+                                      const int32_t* cache_seqlens, const int32_t* tile_scheduler_metadata,
+                                      const int32_t* num_splits, int num_sm_parts, int batch, int s_q, int h_q,
+                                      float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
+                                      size_t workspace_bytes, int use_pdl, void* stream) {
+  B200_CHECK(q_nope && q_rope && q_scale && k_lora && k_rope && k_scale && block_table && cache_seqlens &&
+                 tile_scheduler_metadata && num_splits && out && lse && workspace,
+             "mla_decode: null pointer argument");
+  B200_CHECK(batch > 0 && s_q > 0 && h_q > 0 && num_pages > 0, "mla_decode: batch=%d s_q=%d h_q=%d num_pages=%lld", batch,
+             s_q, h_q, (long long)num_pages);
+  const int M = s_q * h_q;
+  const int q_blocks = (M + B200_MLA_BLOCK_M - 1) / B200_MLA_BLOCK_M;
+  B200_CHECK(num_sm_parts > 0, "mla_decode: num_sm_parts must be positive");
+  B200_CHECK(workspace_bytes >= b200_mla_workspace_bytes(batch, s_q, h_q, num_sm_parts),
+             "mla_decode: workspace too small (%zu < %zu)", workspace_bytes,
+             b200_mla_workspace_bytes(batch, s_q, h_q, num_sm_parts));
+  B200_CHECK((reinterpret_cast<uintptr_t>(k_lora) & 15) == 0 && (reinterpret_cast<uintptr_t>(k_rope) & 15) == 0 &&
+                 (reinterpret_cast<uintptr_t>(q_nope) & 15) == 0 && (reinterpret_cast<uintptr_t>(q_rope) & 15) == 0,
+             "mla_decode: q / k tensors must be 16-byte aligned");
+  if (s_q == 1) is_causal = 0;  // flash_api.cpp:279
+
+  const int HB = M <= 16 ? 16 : (M <= 32 ? 32 : 64);
+  MlaParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const uint64_t q_rows = (uint64_t)batch * M;
+  const uint64_t tokens = (uint64_t)num_pages * kPage;
+  if (make_tma_2d(&prm.tm_q_nope, q_nope, 1, 512, q_rows, 512, 128, HB, TmaSwizzle::B128)) return 1;
+  if (make_tma_2d(&prm.tm_q_rope, q_rope, 2, 64, q_rows, 128, 64, HB, TmaSwizzle::B128)) return 1;
+  if (make_tma_2d(&prm.tm_k_nope, k_lora, 1, 512, tokens, 512, 128, kPage, TmaSwizzle::B128)) return 1;
+  if (make_tma_2d(&prm.tm_k_rope, k_rope, 2, 64, tokens, 128, 64, kPage, TmaSwizzle::B128)) return 1;
+  prm.q_scale = q_scale;
+  prm.k_scale = k_scale;
+  prm.block_table = block_table;
+  prm.block_table_stride = block_table_stride;
+  prm.seqlens = cache_seqlens;
+  prm.meta = tile_scheduler_metadata;
+  prm.num_splits = num_splits;
+  prm.out = (__nv_bfloat16*)out;
+  prm.lse = lse;
+  const size_t splits = (size_t)batch + num_sm_parts;
+  prm.o_accum = (float*)workspace;
+  prm.lse_accum = (float*)workspace + splits * M * 512;
+  prm.batch = batch;
+  prm.s_q = s_q;
+  prm.h_q = h_q;
+  prm.M = M;
+  prm.scale_log2 = softmax_scale * 1.4426950408889634f;  // flash_api.cpp:324
+  prm.is_causal = is_causal;
+
+  int rc;
+  if (HB == 16) rc = launch_mla<16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else if (HB == 32) rc = launch_mla<32>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else rc = launch_mla<64>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  if (rc) return rc;
+  return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);
+}
+
+}  // extern "C"

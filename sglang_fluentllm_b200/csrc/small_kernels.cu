@@ -1,0 +1,388 @@
+// The HBM-bound helper kernels around the MLA decode / FP8 GEMM hot path:
+//   * tile-scheduler metadata (integer, bit-exact vs oracle/mla.py:get_mla_metadata)
+//   * per-(token,head) FP8 quantisers for q and for new K tokens (scatter into the paged pool)
+//   * indexed de-quantisation of the pool
+//   * split-KV combine
+//   * 1x128 activation quantiser for the block-scaled GEMM
+// All are byte/elementwise streaming kernels: 128-bit coalesced loads/stores, one warp per row, no shared-memory
+// staging needed (no reuse).  Arithmetic is IEEE fp32 (explicit _rn intrinsics, no FMA contraction) so e4m3 codes
+// and scale bits are bit-exact against the numpy oracle.
+#include <cuda_bf16.h>
+#include <cuda_fp8.h>
+#include <math.h>
+
+#include "b200_decode.h"
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr float FP8_MAX = 448.0f;
+
+// ------------------------------------------------------------------------------------------------
+// a-4  metadata.  Reference: 3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu:8-75 (one warp; the
+// assignment loop is inherently serial over sm parts, so a single lane runs it after a parallel block count).
+// ------------------------------------------------------------------------------------------------
+__global__ void mla_metadata_kernel(const int32_t* __restrict__ seqlens, int32_t* __restrict__ meta,
+                                    int32_t* __restrict__ num_splits, int batch, int block_n, int fixed_overhead,
+                                    int num_sm_parts) {
+  extern __shared__ int32_t s_blocks[];  // [batch]
+  int total = 0;
+  for (int i = threadIdx.x; i < batch; i += 32) {
+    int nb = (seqlens[i] + block_n - 1) / block_n;
+    s_blocks[i] = nb;
+    total += nb + fixed_overhead;
+  }
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  __syncwarp();
+  if (threadIdx.x != 0) return;
+  int payload = max((total + num_sm_parts - 1) / num_sm_parts + fixed_overhead, 2 * fixed_overhead);
+  int now_idx = 0, now_block = 0, now_split = 0, cum = 0;
+  num_splits[0] = 0;
+  for (int i = 0; i < num_sm_parts; ++i) {
+    int32_t* m = meta + i * 8;
+    m[0] = now_idx;
+    m[1] = now_block * block_n;
+    m[4] = now_split;
+    int remain = payload;
+    while (now_idx < batch) {
+      int nb = s_blocks[now_idx];
+      int left = nb - now_block;
+      if (remain >= left + fixed_overhead) {
+        cum += now_split + 1;
+        num_splits[now_idx + 1] = cum;
+        remain -= left + fixed_overhead;
+        ++now_idx;
+        now_block = 0;
+        now_split = 0;
+      } else {
+        if (remain - fixed_overhead > 0) {
+          now_block += remain - fixed_overhead;
+          ++now_split;
+          remain = 0;
+        }
+        break;
+      }
+    }
+    m[2] = now_block > 0 ? now_idx : now_idx - 1;
+    m[3] = now_block > 0 ? now_block * block_n : (now_idx >= 1 ? seqlens[now_idx - 1] : 0);
+    m[5] = 0;
+    m[6] = 0;
+    m[7] = 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-6 / a-7  per-row quantiser (one warp per row of 512 nope + 64 rope bf16 values).
+// Reference arithmetic: cache_kernels.cu:27-98 / :140-218.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void quantize_row_576(const __nv_bfloat16* __restrict__ in, uint8_t* __restrict__ nope_out,
+                                                 float* __restrict__ scale_out, __nv_bfloat16* __restrict__ rope_out,
+                                                 int lane) {
+  // 512 bf16 = 1024 B = 2 x (32 lanes x 16 B)
+  uint4 raw[2];
+  raw[0] = __ldg(reinterpret_cast<const uint4*>(in) + lane);
+  raw[1] = __ldg(reinterpret_cast<const uint4*>(in) + 32 + lane);
+  const uint32_t rope_raw = __ldg(reinterpret_cast<const uint32_t*>(in + 512) + lane);
+  float v[16];
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const uint32_t w[4] = {raw[i].x, raw[i].y, raw[i].z, raw[i].w};
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      v[i * 8 + j * 2] = __uint_as_float(w[j] << 16);
+      v[i * 8 + j * 2 + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 16; ++i) amax = fmaxf(amax, fabsf(v[i]));  // NaN-ignoring like __hmax
+  amax = warp_max_f32(amax);
+  float scale = __fdiv_rn(amax, FP8_MAX);
+  scale = __fadd_rn(scale, 1e-12f);
+  const float inv = __fdiv_rn(1.0f, scale);
+  if (lane == 0) *scale_out = scale;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    uint2 packed;
+    packed.x = cvt_e4m3x4(__fmul_rn(v[i * 8 + 0], inv), __fmul_rn(v[i * 8 + 1], inv), __fmul_rn(v[i * 8 + 2], inv),
+                          __fmul_rn(v[i * 8 + 3], inv));
+    packed.y = cvt_e4m3x4(__fmul_rn(v[i * 8 + 4], inv), __fmul_rn(v[i * 8 + 5], inv), __fmul_rn(v[i * 8 + 6], inv),
+                          __fmul_rn(v[i * 8 + 7], inv));
+    *reinterpret_cast<uint2*>(nope_out + (i * 32 + lane) * 8) = packed;
+  }
+  const float r0 = __fmul_rn(__uint_as_float(rope_raw << 16), inv);
+  const float r1 = __fmul_rn(__uint_as_float(rope_raw & 0xFFFF0000u), inv);
+  __nv_bfloat162 rr = __floats2bfloat162_rn(r0, r1);
+  *reinterpret_cast<__nv_bfloat162*>(rope_out + lane * 2) = rr;
+}
+
+__global__ void __launch_bounds__(256) quantize_q_kernel(const __nv_bfloat16* __restrict__ q, uint8_t* __restrict__ nope,
+                                                         float* __restrict__ scale, __nv_bfloat16* __restrict__ rope,
+                                                         int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  quantize_row_576(q + row * 576, nope + row * 512, scale + row, rope + row * 64, threadIdx.x & 31);
+}
+
+__global__ void __launch_bounds__(256)
+    quantize_cache_k_kernel(const __nv_bfloat16* __restrict__ key, int64_t key_row_stride,
+                            const int32_t* __restrict__ indices, uint8_t* __restrict__ lora_cache,
+                            float* __restrict__ scale_cache, __nv_bfloat16* __restrict__ rope_cache, int64_t n) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int64_t loc = indices[row];
+  quantize_row_576(key + row * key_row_stride, lora_cache + loc * 512, scale_cache + loc, rope_cache + loc * 64,
+                   threadIdx.x & 31);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-8  indexed de-quantisation.  Reference: cache_kernels.cu:274-369.  One warp per gathered token.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float e4m3_byte_to_float(uint32_t b) {
+  __half_raw h = __nv_cvt_fp8_to_halfraw(static_cast<__nv_fp8_storage_t>(b), __NV_E4M3);
+  return __half2float(__half(h));
+}
+
+__global__ void __launch_bounds__(256)
+    dequantize_indexed_kernel(const uint8_t* __restrict__ lora_cache, const __nv_bfloat16* __restrict__ rope_cache,
+                              const float* __restrict__ scale_cache, const int32_t* __restrict__ indices,
+                              __nv_bfloat16* __restrict__ lora_out, __nv_bfloat16* __restrict__ rope_out, int64_t n) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n; row += warps) {
+    const int64_t loc = indices[row];
+    const float s = __ldg(scale_cache + loc);
+    const uint4 raw = __ldg(reinterpret_cast<const uint4*>(lora_cache + loc * 512) + lane);  // 16 codes
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    uint32_t o[8];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float f0 = __fmul_rn(e4m3_byte_to_float(w[j] & 0xFF), s);
+      float f1 = __fmul_rn(e4m3_byte_to_float((w[j] >> 8) & 0xFF), s);
+      float f2 = __fmul_rn(e4m3_byte_to_float((w[j] >> 16) & 0xFF), s);
+      float f3 = __fmul_rn(e4m3_byte_to_float(w[j] >> 24), s);
+      __nv_bfloat162 a = __floats2bfloat162_rn(f0, f1), b = __floats2bfloat162_rn(f2, f3);
+      o[j * 2] = *reinterpret_cast<uint32_t*>(&a);
+      o[j * 2 + 1] = *reinterpret_cast<uint32_t*>(&b);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(lora_out + row * 512 + lane * 16);
+    dst[0] = make_uint4(o[0], o[1], o[2], o[3]);
+    dst[1] = make_uint4(o[4], o[5], o[6], o[7]);
+    const uint32_t rr = __ldg(reinterpret_cast<const uint32_t*>(rope_cache + loc * 64) + lane);
+    __nv_bfloat162 r = __floats2bfloat162_rn(__fmul_rn(__uint_as_float(rr << 16), s),
+                                             __fmul_rn(__uint_as_float(rr & 0xFFFF0000u), s));
+    *reinterpret_cast<__nv_bfloat162*>(rope_out + row * 64 + lane * 2) = r;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a-5  split-KV combine.  Reference: ckv_fp8_per_token/mla_combine.cu:16-154.
+// One warp per (request, q row): lse_g = log2(sum 2^lse_i), out = sum 2^(lse_i - lse_g) * oaccum_i.
+// o_accum: [total_splits][M][512] fp32, lse_accum: [total_splits][M] fp32 (log2 domain).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    mla_combine_kernel(const float* __restrict__ o_accum, const float* __restrict__ lse_accum,
+                       const int32_t* __restrict__ num_splits_ptr, __nv_bfloat16* __restrict__ out,
+                       float* __restrict__ lse_out, int batch, int M, int h_q, int s_q) {
+  pdl_wait_prior_grid();
+  const int b = blockIdx.x;
+  const int row = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= M) return;
+  const int s0 = num_splits_ptr[b], s1 = num_splits_ptr[b + 1];
+  const int n = s1 - s0;
+  if (n <= 1) return;  // the decode kernel wrote the final result itself
+  float max_lse = -INFINITY;
+  for (int i = lane; i < n; i += 32) max_lse = fmaxf(max_lse, lse_accum[(size_t)(s0 + i) * M + row]);
+  max_lse = warp_max_f32(max_lse);
+  if (max_lse == -INFINITY) max_lse = 0.f;
+  float sum = 0.f;
+  for (int i = lane; i < n; i += 32) sum += exp2f(lse_accum[(size_t)(s0 + i) * M + row] - max_lse);
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float global_lse = (sum == 0.f || sum != sum) ? INFINITY : log2f(sum) + max_lse;
+  if (lane == 0) {
+    // lse layout [b, h_q, s_q]; row = s * h_q + h
+    const int s = row / h_q, h = row % h_q;
+    lse_out[((size_t)b * h_q + h) * s_q + s] = global_lse * 0.6931471805599453f;
+  }
+  float acc[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) acc[j] = 0.f;
+  for (int i = 0; i < n; ++i) {
+    const float w = exp2f(lse_accum[(size_t)(s0 + i) * M + row] - global_lse);
+    if (w == 0.f || w != w) continue;  // empty split: partial may hold anything
+    const float4* src = reinterpret_cast<const float4*>(o_accum + ((size_t)(s0 + i) * M + row) * 512);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float4 v = __ldg(src + j * 32 + lane);
+      acc[j * 4 + 0] += w * v.x;
+      acc[j * 4 + 1] += w * v.y;
+      acc[j * 4 + 2] += w * v.z;
+      acc[j * 4 + 3] += w * v.w;
+    }
+  }
+  __nv_bfloat16* dst = out + ((size_t)b * M + row) * 512;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    __nv_bfloat162 a = __floats2bfloat162_rn(acc[j * 4], acc[j * 4 + 1]);
+    __nv_bfloat162 c = __floats2bfloat162_rn(acc[j * 4 + 2], acc[j * 4 + 3]);
+    uint2 pk = make_uint2(*reinterpret_cast<uint32_t*>(&a), *reinterpret_cast<uint32_t*>(&c));
+    *reinterpret_cast<uint2*>(dst + (j * 32 + lane) * 4) = pk;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// G-2  1x128 activation quantiser.  Reference: 3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-437 and
+// python/sglang/test/test_block_fp8.py:15-40.  16 lanes per 128-element group (8 bf16 = 16 B per lane).
+// scales are written column-major [k/128][scale_stride] (scale_stride = m padded to 4: TMA-aligned).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    act_quant_1x128_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scales,
+                           int64_t num_groups, int groups_per_row, int64_t scale_stride, float eps) {
+  const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
+  const int sub = threadIdx.x & 15;
+  if (g >= num_groups) return;
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + g * 128) + sub);
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  float v[8];
+  float amax = eps;
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    v[j * 2] = __uint_as_float(w[j] << 16);
+    v[j * 2 + 1] = __uint_as_float(w[j] & 0xFFFF0000u);
+    amax = fmaxf(amax, fmaxf(fabsf(v[j * 2]), fabsf(v[j * 2 + 1])));
+  }
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o, 16));
+  const float s = __fdiv_rn(amax, FP8_MAX);
+  if (sub == 0) {
+    const int64_t row = g / groups_per_row, col = g % groups_per_row;
+    scales[col * scale_stride + row] = s;
+  }
+  float qv[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) qv[j] = fminf(fmaxf(__fdiv_rn(v[j], s), -FP8_MAX), FP8_MAX);
+  uint2 pk;
+  pk.x = cvt_e4m3x4(qv[0], qv[1], qv[2], qv[3]);
+  pk.y = cvt_e4m3x4(qv[4], qv[5], qv[6], qv[7]);
+  *reinterpret_cast<uint2*>(q + g * 128 + sub * 8) = pk;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+extern "C" {
+
+const char* b200_last_error(void) { return get_last_error(); }
+
+int b200_sm_count(void) { return device_sm_count(); }
+
+int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_count) {
+  if (num_heads_per_head_k <= 0 || num_heads_k <= 0 || sm_count <= 0) return 0;
+  const int m_blocks = (num_heads_per_head_k + B200_MLA_BLOCK_M - 1) / B200_MLA_BLOCK_M;
+  return sm_count / num_heads_k / m_blocks;
+}
+
+int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
+                          int32_t* num_splits, void* stream) {
+  B200_CHECK(cache_seqlens && tile_scheduler_metadata && num_splits, "get_metadata: null pointer");
+  B200_CHECK(batch > 0 && num_sm_parts > 0, "get_metadata: batch=%d num_sm_parts=%d must be positive", batch,
+             num_sm_parts);
+  B200_CHECK(batch * 4 <= 200 * 1024, "get_metadata: batch %d too large", batch);
+  const size_t smem = (size_t)batch * 4;
+  if (smem > 48 * 1024)
+    B200_CUDA(cudaFuncSetAttribute(mla_metadata_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  mla_metadata_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cache_seqlens, tile_scheduler_metadata, num_splits, batch,
+                                                             B200_MLA_PAGE_SIZE, B200_MLA_FIXED_OVERHEAD_BLOCKS,
+                                                             num_sm_parts);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200_mla_quantize_q(const void* q, int64_t rows, int head_dim, int head_dim_v, void* q_nope, float* q_scale,
+                        void* q_rope, void* stream) {
+  B200_CHECK(head_dim == 576 && head_dim_v == 512, "quantize_q: only head_dim=576/head_dim_v=512 supported (got %d/%d)",
+             head_dim, head_dim_v);
+  B200_CHECK(q && q_nope && q_scale && q_rope, "quantize_q: null pointer");
+  if (rows == 0) return 0;
+  const int warps = 8;
+  quantize_q_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)q, (uint8_t*)q_nope, q_scale, (__nv_bfloat16*)q_rope, rows);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64_t n, int head_dim, int head_dim_v,
+                                  const int32_t* indices, void* k_lora_cache, float* k_scale_cache, void* k_rope_cache,
+                                  void* stream) {
+  B200_CHECK(head_dim == 576 && head_dim_v == 512,
+             "quantize_and_cache_k: only head_dim=576/head_dim_v=512 supported (got %d/%d)", head_dim, head_dim_v);
+  B200_CHECK(key && indices && k_lora_cache && k_scale_cache && k_rope_cache, "quantize_and_cache_k: null pointer");
+  B200_CHECK(key_row_stride >= 576 && key_row_stride % 8 == 0, "quantize_and_cache_k: key row stride %lld invalid",
+             (long long)key_row_stride);
+  if (n == 0) return 0;
+  const int warps = 8;
+  quantize_cache_k_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)key, key_row_stride, indices, (uint8_t*)k_lora_cache, k_scale_cache,
+      (__nv_bfloat16*)k_rope_cache, n);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cache, const float* k_scale_cache,
+                                const int32_t* indices, int64_t n, int64_t max_num_tokens, void* k_lora_out,
+                                void* k_rope_out, void* stream) {
+  B200_CHECK(k_lora_cache && k_rope_cache && k_scale_cache && k_lora_out && k_rope_out, "dequantize: null pointer");
+  if (n == 0) return 0;
+  B200_CHECK(indices, "dequantize: null indices");
+  // grid depends only on max_num_tokens when given, so CUDA-graph capture and replay agree
+  // (reference: cache_kernels.cu:372-423)
+  const int warps = 8;
+  int64_t sizing = max_num_tokens > 0 ? max_num_tokens : n;
+  int64_t blocks = (sizing + warps - 1) / warps;
+  if (blocks > 65535) blocks = 65535;
+  dequantize_indexed_kernel<<<(unsigned)blocks, warps * 32, 0, (cudaStream_t)stream>>>(
+      (const uint8_t*)k_lora_cache, (const __nv_bfloat16*)k_rope_cache, k_scale_cache, indices,
+      (__nv_bfloat16*)k_lora_out, (__nv_bfloat16*)k_rope_out, n);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
+                     int batch, int s_q, int h_q, int use_pdl, void* stream) {
+  B200_CHECK(o_accum && lse_accum && num_splits && out && lse, "combine: null pointer");
+  const int M = s_q * h_q;
+  const int warps = 8;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(batch, (M + warps - 1) / warps, 1);
+  cfg.blockDim = dim3(warps * 32, 1, 1);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, mla_combine_kernel, o_accum, lse_accum, num_splits, (__nv_bfloat16*)out, lse, batch,
+                               M, h_q, s_q));
+  return 0;
+}
+
+int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* scales, int64_t scale_stride, float eps,
+                         void* stream) {
+  B200_CHECK(x && q && scales, "act_quant: null pointer");
+  B200_CHECK(k % 128 == 0, "act_quant: k=%lld must be a multiple of 128", (long long)k);
+  B200_CHECK(scale_stride >= m, "act_quant: scale_stride %lld < m %lld", (long long)scale_stride, (long long)m);
+  if (m == 0) return 0;
+  const int64_t groups = m * (k / 128);
+  const int groups_per_block = 16;
+  act_quant_1x128_kernel<<<(unsigned)((groups + groups_per_block - 1) / groups_per_block), groups_per_block * 16, 0,
+                           (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (uint8_t*)q, scales, groups, (int)(k / 128),
+                                                   scale_stride, eps);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,244 @@
+// UMMA descriptor self-test ("lab"): runs one tcgen05.mma chain per operand-layout variant used by the MLA
+// decode and FP8 GEMM kernels and checks it against a host fp32 reference.  It exists because the smem /
+// instruction descriptor encodings are hand-built (no CUTLASS); each kernel's layout assumptions are pinned
+// here on real hardware before the big kernels rely on them.
+//
+// Variants (see b200_umma_selftest):
+//   0  fp8  A K-major SW128 (TMA)  x  B K-major SW128 (TMA)            -> q.k^T nope term, GEMM main loop
+//   1  bf16 A K-major SW128 (TMA)  x  B K-major SW128 (TMA)            -> q.k^T rope term
+//   2  fp8  A MN-major SW128 (TMA, the K-tile re-read as V^T)  x  B MN-major no-swizzle (thread-written P)
+//   3  as 2 with the LBO/SBO roles of B exchanged (diagnostic)
+//   4  fp8  A MN-major SW128 x B K-major SW128 thread-written (fallback layout for P)
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+struct LabParams {
+  CUtensorMap tm_a, tm_b;
+  const uint8_t* b_raw;  // logical [K][N] bytes for thread-written B
+  float* out;            // [128][N]
+  int n;
+  int kind;  // 0 = f8f6f4 (e4m3), 1 = f16 (bf16)
+  int a_mn_major, b_mn_major;
+  int num_k_steps;
+  int a_rows;  // TMA box rows for A
+  int b_mode;  // 0 = TMA K-major SW128; 1 = thread-written MN-major no-swizzle; 2 = thread-written K-major SW128
+  uint32_t a_layout, b_layout;
+  uint32_t a_lbo, a_sbo, b_lbo, b_sbo;
+  uint32_t a_kstep, b_kstep;  // bytes added to the start address per k-step
+  uint32_t b_chunk_stride, b_group_stride;
+  uint32_t k_total;  // K extent (tokens) for thread-written B
+};
+
+__global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant__ LabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_a = smem;           // 16 KB
+  uint8_t* s_b = smem + 16384;   // 32 KB
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (tid == 0) {
+    mbar_init(&bar_load, 1);
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (tid == 0) {
+    uint32_t bytes = p.a_rows * 128;
+    tma_load_2d(s_a, &p.tm_a, &bar_load, 0, 0);
+    if (p.b_mode == 0) {
+      tma_load_2d(s_b, &p.tm_b, &bar_load, 0, 0);
+      bytes += p.n * 128;
+    }
+    mbar_arrive_expect_tx(&bar_load, bytes);
+  }
+  if (p.b_mode == 1) {
+    // thread t = token (K index); writes its N bytes as 16-B chunks: core matrix (group g = t/8, chunk c)
+    const int t = tid;
+    if (t < (int)p.k_total) {
+      for (int c = 0; c < p.n / 16; ++c) {
+        uint4 v = *reinterpret_cast<const uint4*>(p.b_raw + (size_t)t * p.n + c * 16);
+        *reinterpret_cast<uint4*>(s_b + c * p.b_chunk_stride + (t >> 3) * p.b_group_stride + (t & 7) * 16) = v;
+      }
+    }
+    fence_proxy_async_smem();
+  } else if (p.b_mode == 2) {
+    // K-major SW128: row n holds K (tokens) contiguously; 16-B chunk index XOR (n & 7)
+    for (int idx = tid; idx < p.n * (int)p.k_total; idx += 128) {
+      int n = idx / p.k_total, k = idx % p.k_total;
+      uint32_t off = n * 128 + ((((k >> 4) ^ (n & 7)) & 7) << 4) + (k & 15);
+      s_b[off] = p.b_raw[(size_t)k * p.n + n];
+    }
+    fence_proxy_async_smem();
+  }
+  __syncthreads();
+
+  if (tid == 0) {
+    mbar_wait(&bar_load, 0);
+    tc_fence_after();
+    const uint32_t idesc = make_idesc(p.kind ? FMT_BF16 : FMT_E4M3, p.kind ? FMT_BF16 : FMT_E4M3, p.a_mn_major,
+                                      p.b_mn_major, 128, p.n);
+    for (int k = 0; k < p.num_k_steps; ++k) {
+      uint64_t da = make_smem_desc(smem_u32(s_a) + k * p.a_kstep, p.a_lbo, p.a_sbo, p.a_layout);
+      uint64_t db = make_smem_desc(smem_u32(s_b) + k * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
+      if (p.kind) umma_f16(tmem, da, db, idesc, k > 0);
+      else umma_f8(tmem, da, db, idesc, k > 0);
+    }
+    umma_commit(&bar_mma);
+  }
+  mbar_wait(&bar_mma, 0);
+  tc_fence_after();
+  {
+    const uint32_t lane_base = (warp & 3) * 32;
+    for (int c0 = 0; c0 < p.n; c0 += 16) {
+      float v[16];
+      tmem_ld<16>(tmem + (lane_base << 16) + c0, v);
+      tmem_wait_ld();
+      for (int j = 0; j < 16; ++j) p.out[(size_t)(lane_base + (tid & 31)) * p.n + c0 + j] = v[j];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tmem, 256);
+}
+
+static float e4m3_to_float(uint8_t c) {
+  int s = c >> 7, e = (c >> 3) & 0xF, m = c & 7;
+  float v;
+  if (e == 0xF && m == 7) v = NAN;
+  else if (e == 0) v = ldexpf((float)m / 8.f, -6);
+  else v = ldexpf(1.f + (float)m / 8.f, e - 7);
+  return s ? -v : v;
+}
+static float bf16_to_float(uint16_t b) {
+  uint32_t u = (uint32_t)b << 16;
+  float f;
+  memcpy(&f, &u, 4);
+  return f;
+}
+
+}  // namespace b200
+
+using namespace b200;
+
+// Runs one variant; writes max |got - expected| / max|expected| to *rel_err.  Returns 0 on success.
+extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
+  B200_CHECK(n % 16 == 0 && n >= 16 && n <= 256, "selftest: n must be a multiple of 16 in [16,256]");
+  LabParams p;
+  memset(&p, 0, sizeof(p));
+  p.n = n;
+  const int K_BYTES = 128;
+  std::vector<uint8_t> hA(128 * K_BYTES), hB((size_t)256 * K_BYTES);
+  srand(1234 + variant);
+  auto rnd_e4m3 = [] {
+    uint8_t c;
+    do c = rand() & 0xFF;
+    while ((c & 0x7F) >= 0x58);  // |v| < 16, no NaN
+    return c;
+  };
+  std::vector<float> expect((size_t)128 * n, 0.f);
+  uint8_t *dA = nullptr, *dB = nullptr;
+  float* dOut = nullptr;
+  B200_CUDA(cudaMalloc(&dA, hA.size()));
+  B200_CUDA(cudaMalloc(&dB, hB.size()));
+  B200_CUDA(cudaMalloc(&dOut, sizeof(float) * 128 * n));
+  B200_CUDA(cudaMemset(dOut, 0xFF, sizeof(float) * 128 * n));
+  int rc = 0;
+  if (variant == 0) {
+    for (auto& x : hA) x = rnd_e4m3();
+    for (auto& x : hB) x = rnd_e4m3();
+    for (int m = 0; m < 128; ++m)
+      for (int j = 0; j < n; ++j) {
+        float acc = 0;
+        for (int k = 0; k < 128; ++k) acc += e4m3_to_float(hA[m * 128 + k]) * e4m3_to_float(hB[j * 128 + k]);
+        expect[(size_t)m * n + j] = acc;
+      }
+    p.kind = 0; p.num_k_steps = 4; p.a_rows = 128; p.b_mode = 0;
+    p.a_layout = p.b_layout = SWZ_128B; p.a_sbo = p.b_sbo = 1024; p.a_kstep = p.b_kstep = 32;
+    rc |= make_tma_2d(&p.tm_a, dA, 1, 128, 128, 128, 128, 128, TmaSwizzle::B128);
+    rc |= make_tma_2d(&p.tm_b, dB, 1, 128, n, 128, 128, n, TmaSwizzle::B128);
+  } else if (variant == 1) {
+    uint16_t* a16 = reinterpret_cast<uint16_t*>(hA.data());
+    uint16_t* b16 = reinterpret_cast<uint16_t*>(hB.data());
+    for (int i = 0; i < 128 * 64; ++i) a16[i] = (uint16_t)(0x3C00 + (rand() & 0x3FF) + ((rand() & 1) << 15));
+    for (int i = 0; i < 256 * 64; ++i) b16[i] = (uint16_t)(0x3C00 + (rand() & 0x3FF) + ((rand() & 1) << 15));
+    for (int m = 0; m < 128; ++m)
+      for (int j = 0; j < n; ++j) {
+        float acc = 0;
+        for (int k = 0; k < 64; ++k) acc += bf16_to_float(a16[m * 64 + k]) * bf16_to_float(b16[j * 64 + k]);
+        expect[(size_t)m * n + j] = acc;
+      }
+    p.kind = 1; p.num_k_steps = 4; p.a_rows = 128; p.b_mode = 0;
+    p.a_layout = p.b_layout = SWZ_128B; p.a_sbo = p.b_sbo = 1024; p.a_kstep = p.b_kstep = 32;
+    rc |= make_tma_2d(&p.tm_a, dA, 2, 64, 128, 128, 64, 128, TmaSwizzle::B128);
+    rc |= make_tma_2d(&p.tm_b, dB, 2, 64, n, 128, 64, n, TmaSwizzle::B128);
+  } else if (variant >= 2 && variant <= 4) {
+    // A image = KV chunk [128 tokens][128 d bytes]; used MN-major: D[d][q] = sum_t A[t][d] * P[t][q]
+    for (auto& x : hA) x = rnd_e4m3();
+    for (size_t i = 0; i < (size_t)128 * n; ++i) hB[i] = rnd_e4m3();  // P logical [token][q]
+    for (int d = 0; d < 128; ++d)
+      for (int j = 0; j < n; ++j) {
+        float acc = 0;
+        for (int t = 0; t < 128; ++t) acc += e4m3_to_float(hA[t * 128 + d]) * e4m3_to_float(hB[(size_t)t * n + j]);
+        expect[(size_t)d * n + j] = acc;
+      }
+    p.kind = 0; p.num_k_steps = 4; p.a_rows = 128; p.k_total = 128;
+    p.a_mn_major = 1; p.a_layout = SWZ_128B; p.a_sbo = 1024; p.a_lbo = 16384; p.a_kstep = 32 * 128;
+    rc |= make_tma_2d(&p.tm_a, dA, 1, 128, 128, 128, 128, 128, TmaSwizzle::B128);
+    p.b_raw = dB;
+    if (variant == 4) {
+      p.b_mode = 2; p.b_mn_major = 0; p.b_layout = SWZ_128B; p.b_sbo = 1024; p.b_lbo = 0; p.b_kstep = 32;
+    } else {
+      p.b_mode = 1; p.b_mn_major = 1; p.b_layout = SWZ_NONE;
+      p.b_group_stride = 128;   // consecutive 8-token groups (K direction)
+      p.b_chunk_stride = 2048;  // next 16-q chunk (N direction): 16 groups * 128 B
+      p.b_kstep = 4 * 128;      // 32 tokens
+      if (variant == 2) { p.b_lbo = p.b_chunk_stride; p.b_sbo = p.b_group_stride; }
+      else              { p.b_lbo = p.b_group_stride; p.b_sbo = p.b_chunk_stride; }
+    }
+  } else {
+    set_last_error("selftest: unknown variant %d", variant);
+    rc = 1;
+  }
+  if (rc == 0) {
+    cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice);
+    cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice);
+    const int smem_bytes = 1024 + 16384 + 32768;
+    cudaFuncSetAttribute(umma_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    umma_lab_kernel<<<1, 128, smem_bytes>>>(p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_last_error("selftest variant %d: kernel failed: %s", variant, cudaGetErrorString(e));
+      rc = 2;
+    } else {
+      std::vector<float> got((size_t)128 * n);
+      cudaMemcpy(got.data(), dOut, sizeof(float) * got.size(), cudaMemcpyDeviceToHost);
+      float max_ref = 0, max_diff = 0;
+      for (size_t i = 0; i < got.size(); ++i) {
+        max_ref = fmaxf(max_ref, fabsf(expect[i]));
+        float d = fabsf(got[i] - expect[i]);
+        if (!(d == d)) d = INFINITY;
+        max_diff = fmaxf(max_diff, d);
+      }
+      *rel_err = max_diff / fmaxf(max_ref, 1e-20f);
+    }
+  }
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dOut);
+  return rc;
+}

@@ -1,0 +1,115 @@
+"""Drop-in for the reference's ``deep_gemm`` dense entry point (3rdparty/deep_gemm/deep_gemm/__init__.py,
+jit_kernels/gemm.py:145-226): ``gemm_fp8_fp8_bf16_nt(lhs, rhs, out, use_pdl)`` plus the layout helpers its callers use.
+Backed by the AOT sm_100a kernel behind ``b200_fp8_gemm_nt`` (no JIT: shapes are runtime arguments).
+"""
+from __future__ import annotations
+
+from typing import Tuple
+
+import torch
+
+from . import _lib
+
+_num_sms = None
+
+
+def ceil_div(x: int, y: int) -> int:
+    return (x + y - 1) // y
+
+
+def set_num_sms(num_sms: int) -> None:  # jit_kernels/utils.py: kept for API compatibility; grids are tile-shaped
+    global _num_sms
+    _num_sms = int(num_sms)
+
+
+def get_num_sms() -> int:
+    global _num_sms
+    if _num_sms is None:
+        _num_sms = _lib.lib().b200_sm_count()
+    return _num_sms
+
+
+def get_tma_aligned_size(x: int, element_size: int) -> int:
+    """jit_kernels/utils.py:55-75."""
+    alignment = 16 // element_size
+    return ceil_div(x, alignment) * alignment
+
+
+def get_col_major_tma_aligned_tensor(x: torch.Tensor) -> torch.Tensor:
+    """jit_kernels/utils.py:77-107: [m, k/128] scales -> same logical shape, column-major storage with the m stride
+    padded to 16 bytes."""
+    assert x.dim() in (2, 3)
+    remove_dim = False
+    origin_dim = x.dim()
+    if x.dim() == 2:
+        x, remove_dim = x.unsqueeze(0), True
+    b, m, n = x.shape
+    aligned_m = get_tma_aligned_size(m, x.element_size())
+    if (origin_dim == 2 or x.stride(0) == aligned_m * n) and x.stride(1) == 1 and x.stride(2) == aligned_m:
+        return x.squeeze(0) if remove_dim else x
+    aligned_x = torch.transpose(torch.empty((b, n, aligned_m), device=x.device, dtype=x.dtype), 1, 2)
+    aligned_x[:, :m, :] = x
+    aligned_x = aligned_x[:, :m, :]
+    return aligned_x.squeeze(0) if remove_dim else aligned_x
+
+
+def per_token_cast_to_fp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Test-side quantiser of the reference (3rdparty/deep_gemm/tests/test_core.py:9-14)."""
+    assert x.dim() == 2 and x.size(1) % 128 == 0
+    m, n = x.shape
+    x_view = x.view(m, -1, 128)
+    x_amax = x_view.abs().float().amax(dim=2).view(m, -1).clamp(1e-4)
+    return (x_view * (448.0 / x_amax.unsqueeze(2))).to(torch.float8_e4m3fn).view(m, n), (x_amax / 448.0).view(m, -1)
+
+
+def per_block_cast_to_fp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Test-side weight quantiser of the reference (tests/test_core.py:17-25)."""
+    assert x.dim() == 2
+    m, n = x.shape
+    x_padded = torch.zeros((ceil_div(m, 128) * 128, ceil_div(n, 128) * 128), dtype=x.dtype, device=x.device)
+    x_padded[:m, :n] = x
+    x_view = x_padded.view(-1, 128, x_padded.size(1) // 128, 128)
+    x_amax = x_view.abs().float().amax(dim=(1, 3), keepdim=True).clamp(1e-4)
+    x_scaled = (x_view * (448.0 / x_amax)).to(torch.float8_e4m3fn)
+    return x_scaled.view_as(x_padded)[:m, :n].contiguous(), (x_amax / 448.0).view(x_view.size(0), x_view.size(2))
+
+
+def calc_diff(x: torch.Tensor, y: torch.Tensor) -> float:
+    """deep_gemm/utils.py:140-144."""
+    x, y = x.double(), y.double()
+    denominator = (x * x + y * y).sum()
+    sim = 2 * (x * y).sum() / denominator
+    return float(1 - sim)
+
+
+def gemm_fp8_fp8_bf16_nt(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torch.Tensor, torch.Tensor],
+                         out: torch.Tensor, use_pdl: bool = False) -> None:
+    """out[m, n] (bf16) = lhs[m, k] @ rhs[n, k]^T with 1x128 LHS scales and 128x128 RHS scales, written in place.
+    Same checks as jit_kernels/gemm.py:159-177."""
+    lhs, lhs_scales = lhs
+    rhs, rhs_scales = rhs
+    m, k = lhs.shape
+    n, k_ = rhs.shape
+    m_, n_ = out.shape
+    assert n % 64 == 0 and k % 128 == 0
+    assert m == m_ and n == n_ and k == k_
+    assert n > 0 and k > 0
+    assert lhs_scales.shape == (m, (k + 127) // 128)
+    assert rhs_scales.shape == ((n + 127) // 128, (k + 127) // 128)
+    assert lhs.dtype == torch.float8_e4m3fn and lhs_scales.dtype == torch.float32
+    assert rhs.dtype == torch.float8_e4m3fn and rhs_scales.dtype == torch.float32
+    assert out.dtype == torch.bfloat16
+    assert lhs.is_contiguous() and rhs.is_contiguous() and out.is_contiguous()
+    lhs_scales = get_col_major_tma_aligned_tensor(lhs_scales)
+    assert rhs_scales.is_contiguous()
+    if m == 0:
+        return
+    if not lhs.is_cuda:
+        raise RuntimeError("gemm_fp8_fp8_bf16_nt: tensors must be on a CUDA device (no CPU fallback)")
+    with torch.cuda.device(lhs.device):
+        _lib.check(
+            _lib.lib().b200_fp8_gemm_nt(lhs.data_ptr(), lhs_scales.data_ptr(),
+                                        lhs_scales.stride(1) if lhs_scales.shape[1] > 1 else get_tma_aligned_size(m, 4),
+                                        rhs.data_ptr(),
+                                        rhs_scales.data_ptr(), out.data_ptr(), m, n, k, int(bool(use_pdl)),
+                                        _lib.current_stream()), "gemm_fp8_fp8_bf16_nt")

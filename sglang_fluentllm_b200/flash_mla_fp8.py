@@ -1,0 +1,229 @@
+"""Drop-in for the reference's ``flash_mla_fp8`` kernel module (3rdparty/flashmla-fp8/flash_mla_fp8/__init__.py:3-10,
+flash_mla_interface.py:8-185): same function names, argument order, shapes and error behaviour (RuntimeError on bad
+input), backed by the sm_100a C-ABI library instead of the sm_90a pybind extension ``flash_mla_fp8_cuda``.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib
+
+PAGE_BLOCK_SIZE = 64
+TILE_SCHEDULER_METADATA_SIZE = 8
+
+
+def _require(cond: bool, msg: str) -> None:
+    if not cond:
+        raise RuntimeError(msg)  # the reference raises RuntimeError through TORCH_CHECK
+
+
+def _cuda(t: torch.Tensor, name: str) -> None:
+    _require(t.is_cuda, "%s must be on CUDA device" % name)  # flash_api.cpp:23 CHECK_DEVICE
+
+
+def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
+                     num_heads_k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+    """flash_mla_interface.py:8-23 -> csrc/flash_api.cpp:27-63.
+    Returns (tile_scheduler_metadata int32 [num_sm_parts, 8], num_splits int32 [batch + 1])."""
+    _cuda(cache_seqlens, "seqlens_k")
+    _require(cache_seqlens.dtype == torch.int32, "seqlens_k must have dtype int32")
+    _require(cache_seqlens.is_contiguous(), "seqlens_k must be contiguous")
+    L = _lib.lib()
+    with torch.cuda.device(cache_seqlens.device):
+        num_sm_parts = L.b200_mla_num_sm_parts(num_heads_per_head_k, num_heads_k, L.b200_sm_count())
+        _require(num_sm_parts > 0, "get_mla_metadata: no SM parts for num_heads_per_head_k=%d" % num_heads_per_head_k)
+        batch = cache_seqlens.numel()
+        meta = torch.empty(num_sm_parts, TILE_SCHEDULER_METADATA_SIZE, dtype=torch.int32, device=cache_seqlens.device)
+        num_splits = torch.empty(batch + 1, dtype=torch.int32, device=cache_seqlens.device)
+        _lib.check(L.b200_mla_get_metadata(cache_seqlens.data_ptr(), batch, num_sm_parts, meta.data_ptr(),
+                                           num_splits.data_ptr(), _lib.current_stream()), "get_mla_metadata")
+    return meta, num_splits
+
+
+def flash_mla_ckv_fp8_per_token(
+    q_nope: torch.Tensor,
+    q_rope: torch.Tensor,
+    k_cache_lora: torch.Tensor,
+    k_cache_rope: torch.Tensor,
+    q_scale: torch.Tensor,
+    k_scale: torch.Tensor,
+    block_table: torch.Tensor,
+    cache_seqlens: torch.Tensor,
+    head_dim_v: int,
+    tile_scheduler_metadata: torch.Tensor,
+    num_splits: torch.Tensor,
+    softmax_scale: Optional[float] = None,
+    causal: bool = False,
+    out: Optional[torch.Tensor] = None,
+    lse: Optional[torch.Tensor] = None,
+    workspace: Optional[torch.Tensor] = None,
+    use_pdl: bool = True,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """flash_mla_interface.py:68-120 -> csrc/flash_api.cpp:216-397.
+
+    q_nope (b, s_q, h_q, 512) fp8/uint8; q_rope (b, s_q, h_q, 64) bf16; q_scale (b, s_q, h_q, 1) f32;
+    k_cache_lora (num_blocks, 64, 1, 512) fp8/uint8; k_cache_rope (num_blocks, 64, 1, 64) bf16;
+    k_scale (num_blocks, 64, 1, 1) f32; block_table (b, max_blocks) int32; cache_seqlens (b) int32.
+    Returns (out (b, s_q, h_q, 512) bf16, softmax_lse (b, h_q, s_q) f32).
+    ``out`` / ``lse`` / ``workspace`` may be passed in to keep the call allocation-free (CUDA graphs)."""
+    for t, n in ((q_nope, "q_nope"), (q_rope, "q_rope"), (k_cache_lora, "k_cache_lora"), (k_cache_rope, "k_cache_rope"),
+                 (q_scale, "q_scale"), (k_scale, "k_scale"), (block_table, "block_table"),
+                 (cache_seqlens, "seqlens_k"), (tile_scheduler_metadata, "tile_scheduler_metadata"),
+                 (num_splits, "num_splits")):
+        _cuda(t, n)
+    _require(q_nope.dim() == 4 and q_rope.dim() == 4, "q_nope / q_rope must be 4-D (b, s_q, h_q, d)")
+    b, s_q, h_q, dv = q_nope.shape
+    d_rope = q_rope.shape[-1]
+    _require(head_dim_v == 512 and dv == 512 and d_rope == 64,
+             "only head_dim_v=512 / rope=64 is supported")  # flash_api.cpp:252-255
+    _require(q_nope.element_size() == 1, "q_nope must be fp8 (e4m3) / uint8")
+    _require(k_cache_lora.element_size() == 1, "k_cache_lora must be fp8 (e4m3) / uint8")
+    _require(q_rope.dtype == torch.bfloat16 and k_cache_rope.dtype == torch.bfloat16,
+             "q_rope / k_cache_rope must be bfloat16")
+    _require(q_scale.dtype == torch.float32 and k_scale.dtype == torch.float32, "scales must be float32")
+    _require(block_table.dtype == torch.int32, "block_table must have dtype torch.int32")
+    _require(cache_seqlens.dtype == torch.int32, "seqlens_k must have dtype int32")
+    _require(block_table.stride(-1) == 1, "block_table must have contiguous last dimension")
+    _require(k_cache_lora.dim() == 4 and k_cache_lora.shape[1] == PAGE_BLOCK_SIZE and k_cache_lora.shape[2] == 1,
+             "k_cache_lora must be (num_blocks, 64, 1, 512)")
+    _require(tuple(q_rope.shape[:3]) == (b, s_q, h_q) and q_scale.numel() == b * s_q * h_q, "q shape mismatch")
+    num_blocks = k_cache_lora.shape[0]
+    _require(k_cache_rope.shape[0] == num_blocks and k_scale.numel() == num_blocks * PAGE_BLOCK_SIZE,
+             "k cache shape mismatch")
+    for t, n in ((q_nope, "q_nope"), (q_rope, "q_rope"), (q_scale, "q_scale"), (k_cache_lora, "k_cache_lora"),
+                 (k_cache_rope, "k_cache_rope"), (k_scale, "k_scale"), (cache_seqlens, "seqlens_k"),
+                 (tile_scheduler_metadata, "tile_scheduler_metadata"), (num_splits, "num_splits")):
+        _require(t.is_contiguous(), "%s must be contiguous" % n)
+    _require(block_table.shape[0] == b and cache_seqlens.numel() == b, "batch size mismatch")
+    _require(tile_scheduler_metadata.dtype == torch.int32 and tile_scheduler_metadata.dim() == 2
+             and tile_scheduler_metadata.shape[1] == TILE_SCHEDULER_METADATA_SIZE,
+             "tile_scheduler_metadata must be int32 (num_sm_parts, 8)")
+    _require(num_splits.dtype == torch.int32 and num_splits.numel() == b + 1, "num_splits must be int32 (batch + 1)")
+    if softmax_scale is None:
+        softmax_scale = (dv + d_rope) ** (-0.5)  # flash_mla_interface.py:100-101
+    num_sm_parts = tile_scheduler_metadata.shape[0]
+    L = _lib.lib()
+    dev = q_nope.device
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(b, s_q, h_q, dv, dtype=torch.bfloat16, device=dev)
+        if lse is None:
+            lse = torch.empty(b, h_q, s_q, dtype=torch.float32, device=dev)
+        ws_bytes = L.b200_mla_workspace_bytes(b, s_q, h_q, num_sm_parts)
+        if workspace is None:
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _require(workspace.numel() * workspace.element_size() >= ws_bytes, "workspace too small")
+        _lib.check(
+            L.b200_mla_decode_ckv_fp8_per_token(
+                q_nope.data_ptr(), q_rope.data_ptr(), q_scale.data_ptr(), k_cache_lora.data_ptr(),
+                k_cache_rope.data_ptr(), k_scale.data_ptr(), num_blocks, block_table.data_ptr(), block_table.stride(0),
+                cache_seqlens.data_ptr(), tile_scheduler_metadata.data_ptr(), num_splits.data_ptr(), num_sm_parts, b,
+                s_q, h_q, float(softmax_scale), int(bool(causal)), out.data_ptr(), lse.data_ptr(),
+                workspace.data_ptr(), workspace.numel() * workspace.element_size(), int(bool(use_pdl)),
+                _lib.current_stream()),
+            "flash_mla_ckv_fp8_per_token")
+    return out, lse
+
+
+def quantize_ckv_per_token_head(tensor: torch.Tensor,
+                                head_dim_v: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """flash_mla_interface.py:122-126 -> csrc/flash_api.cpp:399-460.
+    tensor [..., 576] bf16 contiguous -> (nope uint8 [..., 512], scale f32 [..., 1], rope bf16 [..., 64])."""
+    _cuda(tensor, "tensor")
+    _require(tensor.dim() >= 2, "tensor must have at least 2 dims")
+    _require(tensor.is_contiguous(), "tensor must be contiguous")
+    _require(tensor.dtype == torch.bfloat16, "Unsupported tensor dtype")
+    head_dim = tensor.shape[-1]
+    base = tuple(tensor.shape[:-1])
+    rows = tensor.numel() // head_dim
+    dev = tensor.device
+    nope = torch.empty(base + (head_dim_v,), dtype=torch.uint8, device=dev)
+    scale = torch.empty(base + (1,), dtype=torch.float32, device=dev)
+    rope = torch.empty(base + (head_dim - head_dim_v,), dtype=tensor.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(_lib.lib().b200_mla_quantize_q(tensor.data_ptr(), rows, head_dim, head_dim_v, nope.data_ptr(),
+                                                  scale.data_ptr(), rope.data_ptr(), _lib.current_stream()),
+                   "quantize_ckv_per_token_head")
+    return nope, scale, rope
+
+
+def quantize_and_cache_k(key: torch.Tensor, k_lora_cache: torch.Tensor, k_lora_scale_cache: torch.Tensor,
+                         k_rope_cache: torch.Tensor, indices: torch.Tensor,
+                         head_dim_v: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """flash_mla_interface.py:128-154 -> csrc/flash_api.cpp:462-532: quantise ``key`` rows and scatter them to the
+    token slots ``indices`` of the three pool tensors, in place."""
+    for t, n in ((key, "key"), (k_lora_cache, "k_lora_cache"), (k_lora_scale_cache, "k_lora_scale_cache"),
+                 (k_rope_cache, "k_rope_cache"), (indices, "indices")):
+        _cuda(t, n)
+        _require(t.is_contiguous(), "%s must be contiguous" % n)
+    _require(indices.dtype == torch.int32, "indices must have dtype int32")
+    _require(key.dtype == torch.bfloat16, "Unsupported key dtype")
+    head_dim = key.shape[-1]
+    n = key.numel() // head_dim
+    _require(indices.numel() == n, "indices size must match key batch size")
+    _require(k_lora_cache.element_size() == 1 and k_lora_cache.shape[-1] == head_dim_v, "k_lora_cache shape/dtype")
+    _require(k_lora_scale_cache.dtype == torch.float32, "k_lora_scale_cache must be float32")
+    _require(k_rope_cache.dtype == key.dtype and k_rope_cache.shape[-1] == head_dim - head_dim_v, "k_rope_cache shape")
+    with torch.cuda.device(key.device):
+        _lib.check(
+            _lib.lib().b200_mla_quantize_and_cache_k(key.data_ptr(), head_dim, n, head_dim, head_dim_v,
+                                                     indices.data_ptr(), k_lora_cache.data_ptr(),
+                                                     k_lora_scale_cache.data_ptr(), k_rope_cache.data_ptr(),
+                                                     _lib.current_stream()), "quantize_and_cache_k")
+    return k_lora_cache, k_lora_scale_cache, k_rope_cache
+
+
+def dequantize_ckv_fused_indexed(k_lora_cache: torch.Tensor, k_rope_cache: torch.Tensor, k_scale_cache: torch.Tensor,
+                                 indices: torch.Tensor, max_num_tokens: int = -1) -> Tuple[torch.Tensor, torch.Tensor]:
+    """flash_mla_interface.py:156-185 -> csrc/flash_api.cpp:534-632: gather ``indices`` and de-quantise to bf16.
+    Returns (k_lora_deq [n, 1, 512], k_rope_deq [n, 1, 64])."""
+    for t, n in ((k_lora_cache, "k_lora_cache"), (k_rope_cache, "k_rope_cache"), (k_scale_cache, "k_scale_cache"),
+                 (indices, "indices")):
+        _cuda(t, n)
+        _require(t.is_contiguous(), "%s must be contiguous" % n)
+    _require(indices.dtype == torch.int32, "indices must be int32")
+    _require(k_lora_cache.element_size() == 1, "k_lora_cache must be fp8 / uint8")
+    _require(k_rope_cache.dtype == torch.bfloat16, "k_rope_cache must be bfloat16")
+    _require(k_scale_cache.dtype == torch.float32, "k_scale_cache must be float32")
+    n = indices.shape[0]
+    dev = k_lora_cache.device
+    lora = torch.empty(n, 1, k_lora_cache.shape[-1], dtype=k_rope_cache.dtype, device=dev)
+    rope = torch.empty(n, 1, k_rope_cache.shape[-1], dtype=k_rope_cache.dtype, device=dev)
+    with torch.cuda.device(dev):
+        _lib.check(
+            _lib.lib().b200_mla_dequantize_indexed(k_lora_cache.data_ptr(), k_rope_cache.data_ptr(),
+                                                   k_scale_cache.data_ptr(), indices.data_ptr(), n,
+                                                   int(max_num_tokens), lora.data_ptr(), rope.data_ptr(),
+                                                   _lib.current_stream()), "dequantize_ckv_fused_indexed")
+    return lora, rope
+
+
+def flash_mla_with_kvcache(q: torch.Tensor, k_cache: torch.Tensor, block_table: torch.Tensor,
+                           cache_seqlens: torch.Tensor, head_dim_v: int, tile_scheduler_metadata: torch.Tensor,
+                           num_splits: torch.Tensor, softmax_scale: Optional[float] = None,
+                           causal: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16-KV entry point of the reference module (flash_mla_interface.py:26-66).  The B200 path is FP8-KV only: the
+    call quantises q and the referenced pages with the path's own quantisers and runs the FP8 kernel, so the result
+    carries per-token-FP8 rounding (documented deviation; the reference's FP8-KV mode never takes this entry,
+    python/sglang/srt/layers/attention/flashmla_backend.py:205-222)."""
+    _cuda(q, "q")
+    _require(q.dtype == torch.bfloat16 and k_cache.dtype == torch.bfloat16, "q / k_cache must be bfloat16")
+    _require(k_cache.dim() == 4 and k_cache.shape[1] == PAGE_BLOCK_SIZE and k_cache.shape[2] == 1,
+             "k_cache must be (num_blocks, 64, 1, d)")
+    if softmax_scale is None:
+        softmax_scale = q.shape[-1] ** (-0.5)
+    nb = k_cache.shape[0]
+    d = k_cache.shape[-1]
+    dev = q.device
+    k_lora = torch.empty(nb * PAGE_BLOCK_SIZE, 1, head_dim_v, dtype=torch.uint8, device=dev)
+    k_scale = torch.empty(nb * PAGE_BLOCK_SIZE, 1, 1, dtype=torch.float32, device=dev)
+    k_rope = torch.empty(nb * PAGE_BLOCK_SIZE, 1, d - head_dim_v, dtype=torch.bfloat16, device=dev)
+    idx = torch.arange(nb * PAGE_BLOCK_SIZE, dtype=torch.int32, device=dev)
+    quantize_and_cache_k(k_cache.contiguous().view(-1, 1, d), k_lora, k_scale, k_rope, idx, head_dim_v)
+    q_nope, q_scale, q_rope = quantize_ckv_per_token_head(q.contiguous(), head_dim_v)
+    return flash_mla_ckv_fp8_per_token(
+        q_nope, q_rope, k_lora.view(nb, PAGE_BLOCK_SIZE, 1, head_dim_v), k_rope.view(nb, PAGE_BLOCK_SIZE, 1, -1),
+        q_scale, k_scale.view(nb, PAGE_BLOCK_SIZE, 1, 1), block_table, cache_seqlens, head_dim_v,
+        tile_scheduler_metadata, num_splits, softmax_scale, causal)
