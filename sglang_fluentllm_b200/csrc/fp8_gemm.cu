@@ -6,11 +6,15 @@
 // k-blocks is an fp32 FMA with the product of the activation (1x128) and weight (128x128) scales (fp8_gemm.cuh:298-330).
 //
 // Machine mapping: weights always sit on the UMMA M side (128 weight rows per CTA = one 128x128 scale block, so the
-// weight scale is a CTA-uniform scalar per k-block) and tokens on the UMMA N side (BLOCK_T = 16..128 columns).  For
+// weight scale is a CTA-uniform scalar per k-block) and tokens on the UMMA N side (BT = 16..128 columns).  For
 // decode (m <= 128) that is the reference's SwapAB layout; for large m it is the same kernel with more token tiles.
-//   warp 0: TMA producer (weight tile 128x128 B, token tile BLOCK_Tx128 B, BLOCK_T activation scales per stage)
-//   warp 1: UMMA issuer (4 x kind::f8f6f4 M=128 N=BLOCK_T K=32 per k-block into one of two TMEM accumulators)
-//   warps 2-5: promotion + epilogue (tcgen05.ld the k-block partial, fp32 FMA with the scales, bf16 store)
+//   warp 0: TMA producer (weight tile 128x128 B, token tile BTx128 B, BT activation scales per stage)
+//   warp 1: UMMA issuer (4 x kind::f8f6f4 M=128 N=BT K=32 per k-block into one of two TMEM accumulators)
+//   warps 2..: promotion + epilogue, 4 lane quadrants x BT/CPT column slices: tcgen05.ld the k-block partial,
+//              packed-fp32x2 FMA with the scales, bf16 store.
+// Decode shapes stream weights (HBM-bound) but have few 128-row weight tiles (17..56): split-K over grid.z spreads
+// the stream over all SMs; partials meet in an fp32 workspace through red.global.add and the last CTA of a tile
+// converts to bf16 and re-zeroes the workspace (self-cleaning, one launch).
 #include <cuda_bf16.h>
 #include <string.h>
 
@@ -26,10 +30,10 @@ struct GemmParams {
   int64_t a_scale_stride;
   const float* b_scales;
   __nv_bfloat16* out;
-  int m, n, k;
+  float* ws;            // [m][n] fp32 split-K accumulator (zero between calls)
+  unsigned int* counters;  // [tiles] arrival counters (zero between calls)
+  int m, n, k, splits, kb_per_split;
 };
-
-static constexpr int kGemmThreads = 192;
 
 template <int BT>
 struct GemmSmem {
@@ -37,38 +41,41 @@ struct GemmSmem {
   static constexpr int kWBytes = 128 * 128;
   static constexpr int kABytes = BT * 128;
   static constexpr int kABytesPadded = (kABytes + 1023) / 1024 * 1024;
-  static constexpr int kSBytes = 512;  // up to 128 fp32 scales
-  static constexpr int kStageBytes = kWBytes + kABytesPadded + kSBytes + 512;  // keep stages 1024-aligned
-  static_assert(kStageBytes % 1024 == 0, "stage must stay 1024-byte aligned");
+  static constexpr int kStageBytes = kWBytes + kABytesPadded + 1024;  // + scales (<= 512 B), keeps 1024 alignment
   static constexpr int kTotal = kStages * kStageBytes + 1024;
 };
 
-template <int BT>
-__global__ void __launch_bounds__(kGemmThreads, 1) fp8_gemm_kernel(const __grid_constant__ GemmParams p) {
+template <int BT, int CPT>
+__global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmSmem<BT>;
   constexpr int kStages = S::kStages;
   constexpr uint32_t kTmemCols = 2 * BT < 32 ? 32 : 2 * BT;
+  constexpr int kCS = BT / CPT;
+  constexpr int kPromo = 128 * kCS;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   struct Bars {
     uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
+    uint32_t is_last;
   };
   Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * S::kStageBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * 128, m0 = blockIdx.y * BT;
-  const int num_kb = p.k / 128;
+  const int total_kb = p.k / 128;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int num_kb = min(p.kb_per_split, total_kb - kb0);
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars.full[i], 1);
-      mbar_init(&bars.empty[i], 1 + 128);  // UMMA commit + the 128 promotion threads (they read the scales)
+      mbar_init(&bars.empty[i], 1 + kPromo);  // UMMA commit + the promotion threads (they read the scales)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.acc_full[i], 1);
-      mbar_init(&bars.acc_empty[i], 128);
+      mbar_init(&bars.acc_empty[i], kPromo);
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
@@ -87,9 +94,10 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fp8_gemm_kernel(const __grid_
       const int rows_valid = min(BT, p.m - m0);
       // bulk copies need 16-byte granularity: a_scale_stride is a multiple of 4 floats, so rounding up stays in-row
       const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % kStages;
-        mbar_wait(&bars.empty[st], ((kb / kStages) & 1) ^ 1);
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb0 + i;
+        const int st = i % kStages;
+        mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
         uint8_t* stage = smem + st * S::kStageBytes;
         mbar_arrive_expect_tx(&bars.full[st], S::kWBytes + S::kABytes + scale_bytes);
         tma_load_2d_hint(stage, &p.tm_w, &bars.full[st], kb * 128, n0, pol_w);
@@ -101,58 +109,89 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fp8_gemm_kernel(const __grid_
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BT);
-      for (int kb = 0; kb < num_kb; ++kb) {
-        const int st = kb % kStages, buf = kb & 1;
-        mbar_wait(&bars.acc_empty[buf], ((kb >> 1) & 1) ^ 1);
-        mbar_wait(&bars.full[st], (kb / kStages) & 1);
+      const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages, buf = i & 1;
+        mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&bars.full[st], (i / kStages) & 1);
         tc_fence_after();
         const uint32_t w_addr = smem_u32(smem + st * S::kStageBytes);
         const uint32_t a_addr = w_addr + S::kWBytes;
 #pragma unroll
         for (int s = 0; s < 4; ++s)
-          umma_f8(tmem + buf * BT, make_smem_desc(w_addr + s * 32, 0, 1024, SWZ_128B),
-                  make_smem_desc(a_addr + s * 32, 0, 1024, SWZ_128B), idesc, s != 0);
+          umma_f8(tmem + buf * BT, dk | (uint64_t)(((w_addr + s * 32) >> 4) & 0x3FFF),
+                  dk | (uint64_t)(((a_addr + s * 32) >> 4) & 0x3FFF), idesc, s != 0);
         umma_commit(&bars.empty[st]);
         umma_commit(&bars.acc_full[buf]);
       }
     }
   } else {
     const int quad = warp & 3;
+    const int cs = (warp - 2) >> 2;
+    const int cb = cs * CPT;
     const int row = quad * 32 + lane;  // weight row within the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int nb = blockIdx.x;
-    float acc[BT];
+    float2 acc[CPT / 2];
 #pragma unroll
-    for (int j = 0; j < BT; ++j) acc[j] = 0.f;
-    for (int kb = 0; kb < num_kb; ++kb) {
-      const int st = kb % kStages, buf = kb & 1;
-      const float sb = __ldg(p.b_scales + (int64_t)nb * num_kb + kb);
-      mbar_wait(&bars.acc_full[buf], (kb >> 1) & 1);  // implies full[st] completed
+    for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % kStages, buf = i & 1;
+      const float sb = __ldg(p.b_scales + (int64_t)nb * total_kb + kb0 + i);
+      const float2 sb2 = make_float2(sb, sb);
+      mbar_wait(&bars.acc_full[buf], (i >> 1) & 1);  // implies full[st] completed
       tc_fence_after();
-      const float* sa = reinterpret_cast<const float*>(smem + st * S::kStageBytes + S::kWBytes + S::kABytesPadded);
+      const float* sa = reinterpret_cast<const float*>(smem + st * S::kStageBytes + S::kWBytes + S::kABytesPadded) + cb;
+      float v[CPT];
+      tmem_ld<CPT>(tmem + buf * BT + cb + lane_addr, v);
+      tmem_wait_ld();
 #pragma unroll
-      for (int c0 = 0; c0 < BT; c0 += 16) {
-        float v[16];
-        tmem_ld<16>(tmem + buf * BT + c0 + lane_addr, v);
-        tmem_wait_ld();
-#pragma unroll
-        for (int j = 0; j < 16; j += 4) {
-          const float4 s4 = *reinterpret_cast<const float4*>(sa + c0 + j);
-          acc[c0 + j + 0] = fmaf(v[j + 0], s4.x * sb, acc[c0 + j + 0]);
-          acc[c0 + j + 1] = fmaf(v[j + 1], s4.y * sb, acc[c0 + j + 1]);
-          acc[c0 + j + 2] = fmaf(v[j + 2], s4.z * sb, acc[c0 + j + 2]);
-          acc[c0 + j + 3] = fmaf(v[j + 3], s4.w * sb, acc[c0 + j + 3]);
-        }
+      for (int j = 0; j < CPT; j += 4) {
+        const float4 s4 = *reinterpret_cast<const float4*>(sa + j);
+        acc[j / 2] = fma2(make_float2(v[j], v[j + 1]), mul2(make_float2(s4.x, s4.y), sb2), acc[j / 2]);
+        acc[j / 2 + 1] = fma2(make_float2(v[j + 2], v[j + 3]), mul2(make_float2(s4.z, s4.w), sb2), acc[j / 2 + 1]);
       }
       tc_fence_before();
       mbar_arrive(&bars.acc_empty[buf]);
       mbar_arrive(&bars.empty[st]);
     }
     const int ncol = n0 + row;
-    if (ncol < p.n) {
+    if (p.splits == 1) {
+      if (ncol < p.n) {
 #pragma unroll
-      for (int j = 0; j < BT; ++j)
-        if (m0 + j < p.m) p.out[(int64_t)(m0 + j) * p.n + ncol] = __float2bfloat16_rn(acc[j]);
+        for (int j = 0; j < CPT; ++j)
+          if (m0 + cb + j < p.m)
+            p.out[(int64_t)(m0 + cb + j) * p.n + ncol] = __float2bfloat16_rn(j & 1 ? acc[j / 2].y : acc[j / 2].x);
+      }
+    } else {
+      // split-K: add the partial into the fp32 workspace; the last CTA of this tile converts and re-zeroes it
+      if (ncol < p.n) {
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+          if (m0 + cb + j < p.m)
+            atomicAdd(p.ws + (int64_t)(m0 + cb + j) * p.n + ncol, j & 1 ? acc[j / 2].y : acc[j / 2].x);
+      }
+      __threadfence();
+      named_bar_sync(1, kPromo);
+      if (tid == 64) {
+        const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned int prev = atomicAdd(p.counters + tile, 1u);
+        bars.is_last = (prev == (unsigned int)p.splits - 1) ? 1u : 0u;
+        if (bars.is_last) p.counters[tile] = 0;
+      }
+      named_bar_sync(1, kPromo);
+      if (bars.is_last) {
+        __threadfence();
+        if (ncol < p.n) {
+#pragma unroll
+          for (int j = 0; j < CPT; ++j)
+            if (m0 + cb + j < p.m) {
+              float* w = p.ws + (int64_t)(m0 + cb + j) * p.n + ncol;
+              p.out[(int64_t)(m0 + cb + j) * p.n + ncol] = __float2bfloat16_rn(__ldcg(w));
+              __stcg(w, 0.f);
+            }
+        }
+      }
     }
   }
   pdl_launch_dependents();
@@ -161,18 +200,18 @@ __global__ void __launch_bounds__(kGemmThreads, 1) fp8_gemm_kernel(const __grid_
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int BT>
+template <int BT, int CPT>
 static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmSmem<BT>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_kernel<BT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((prm.n + 127) / 128, (prm.m + BT - 1) / BT, 1);
-  cfg.blockDim = dim3(kGemmThreads, 1, 1);
+  cfg.gridDim = dim3((prm.n + 127) / 128, (prm.m + BT - 1) / BT, prm.splits);
+  cfg.blockDim = dim3(64 + 128 * (BT / CPT), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -180,16 +219,41 @@ static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) 
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_kernel<BT>, prm));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_kernel<BT, CPT>, prm));
   return 0;
+}
+
+static int pick_bt(int m) { return m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128)); }
+
+// split-K factor: fill the SMs when the (weight tile x token tile) grid is small; keep >= 4 k-blocks per split
+static int pick_splits(int m, int n, int k, int sm_count) {
+  const int bt = pick_bt(m);
+  const int tiles = ((n + 127) / 128) * ((m + bt - 1) / bt);
+  const int num_kb = k / 128;
+  if (tiles * 2 > sm_count) return 1;
+  int splits = sm_count / tiles;
+  if (splits > num_kb / 4) splits = num_kb / 4;
+  if (splits > 16) splits = 16;
+  return splits < 1 ? 1 : splits;
 }
 
 }  // namespace b200
 
 using namespace b200;
 
-extern "C" int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
-                                const float* b_scales, void* out, int m, int n, int k, int use_pdl, void* stream) {
+extern "C" {
+
+size_t b200_fp8_gemm_workspace_bytes(int m, int n, int k) {
+  const int sms = device_sm_count();
+  if (pick_splits(m, n, k, sms > 0 ? sms : 148) == 1) return 0;
+  const int bt = pick_bt(m);
+  const size_t tiles = (size_t)((n + 127) / 128) * ((m + bt - 1) / bt);
+  return (size_t)m * n * sizeof(float) + tiles * sizeof(unsigned int);
+}
+
+int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b, const float* b_scales,
+                     void* out, int m, int n, int k, void* workspace, size_t workspace_bytes, int use_pdl,
+                     void* stream) {
   B200_CHECK(a && a_scales && b && b_scales && out, "fp8_gemm: null pointer");
   // same shape contract as the reference: gemm.py:169 (n % 64 == 0, k % 128 == 0)
   B200_CHECK(n % 64 == 0 && k % 128 == 0 && n > 0 && k > 0, "fp8_gemm: need n %% 64 == 0 and k %% 128 == 0 (n=%d k=%d)", n,
@@ -204,7 +268,19 @@ extern "C" int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_
              "fp8_gemm: operands must be 16-byte aligned");
   GemmParams prm;
   memset(&prm, 0, sizeof(prm));
-  const int BT = m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128));
+  const int BT = pick_bt(m);
+  const int sms = device_sm_count();
+  int splits = pick_splits(m, n, k, sms > 0 ? sms : 148);
+  const size_t need = b200_fp8_gemm_workspace_bytes(m, n, k);
+  if (splits > 1 && (workspace == nullptr || workspace_bytes < need)) splits = 1;  // no workspace: plain tiling
+  const int num_kb = k / 128;
+  prm.splits = splits;
+  prm.kb_per_split = (num_kb + splits - 1) / splits;
+  prm.splits = (num_kb + prm.kb_per_split - 1) / prm.kb_per_split;
+  if (prm.splits > 1) {
+    prm.ws = (float*)workspace;
+    prm.counters = (unsigned int*)((char*)workspace + (size_t)m * n * sizeof(float));
+  }
   if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, 128, TmaSwizzle::B128)) return 1;
   if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)m, (uint64_t)k, 128, BT, TmaSwizzle::B128)) return 1;
   prm.a_scales = a_scales;
@@ -215,9 +291,11 @@ extern "C" int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_
   prm.n = n;
   prm.k = k;
   switch (BT) {
-    case 16: return launch_gemm<16>(prm, use_pdl, (cudaStream_t)stream);
-    case 32: return launch_gemm<32>(prm, use_pdl, (cudaStream_t)stream);
-    case 64: return launch_gemm<64>(prm, use_pdl, (cudaStream_t)stream);
-    default: return launch_gemm<128>(prm, use_pdl, (cudaStream_t)stream);
+    case 16: return launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
+    case 32: return launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
+    case 64: return launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
+    default: return launch_gemm<128, 32>(prm, use_pdl, (cudaStream_t)stream);
   }
 }
+
+}  // extern "C"

@@ -42,8 +42,6 @@ static constexpr int kStageNopeBytes = 4 * kNopeChunkBytes;   // 64 KB
 static constexpr int kStageRopeBytes = kTileTokens * 128;     // 16 KB
 static constexpr int kStageBytes = kStageNopeBytes + kStageRopeBytes;
 static constexpr int kPageTxBytes = kPage * 512 + kPage * 128;
-static constexpr int kNumThreads = 192;
-static constexpr int kSoftmaxThreads = 128;
 static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
 static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
 static constexpr float kHeadroom = 8.0f;                      // lazy rescale: new reference leaves 2^3 of growth
@@ -128,11 +126,17 @@ __device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_id
   return s;
 }
 
-template <int HB>
-__global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
+// HB  = q rows per CTA (UMMA N); CPT = S columns (q rows) each softmax thread owns.
+// The softmax group has 4 * HB/CPT warps: 4 TMEM lane quadrants x HB/CPT column slices, so the per-thread work per
+// tile is CPT elements and every SM sub-partition has HB/CPT warps to hide ALU / MUFU / TMEM-load latency.
+template <int HB, int CPT>
+__global__ void __launch_bounds__(64 + 128 * (HB / CPT), 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
   using L = SmemLayout<HB>;
   constexpr uint32_t kTmemCols = HB == 64 ? 512 : (HB == 32 ? 256 : 128);
   constexpr uint32_t kColS = 0, kColO = 2 * HB;
+  constexpr int kCS = HB / CPT;                 // column slices
+  constexpr int kSmThreads = 128 * kCS;         // softmax group size
+  static_assert(CPT == 8 || CPT == 16, "CPT must be 8 or 16");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -160,10 +164,10 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
     mbar_init(&sm.q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.s_full[i], 1);
-      mbar_init(&sm.p_full[i], kSoftmaxThreads);
+      mbar_init(&sm.p_full[i], kSmThreads);
     }
     mbar_init(&sm.pv_done, 1);
-    mbar_init(&sm.o_free, kSoftmaxThreads);
+    mbar_init(&sm.o_free, kSmThreads);
     sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_q_nope);
@@ -226,6 +230,11 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
       constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, HB);
       constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
       const uint32_t kv_addr = smem_u32(s_kv), q_addr = smem_u32(s_q), p_addr = smem_u32(s_p);
+      // descriptor templates: only the 14-bit start-address field changes per MMA
+      const uint64_t dk_sw128 = make_smem_desc(0, 0, 1024, SWZ_128B);        // K-major, 128-B swizzle
+      const uint64_t dv_sw128 = make_smem_desc(0, 16384, 1024, SWZ_128B);    // MN-major view of the same bytes
+      const uint64_t dp_none = make_smem_desc(0, 128, 2048, SWZ_NONE);       // P: 8x16-B core matrices
+      auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
       uint32_t g = 0, o_seg = 0;
       for (int b = begin_idx; b <= end_idx; ++b) {
         const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
@@ -241,12 +250,12 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
           for (int c = 0; c < 4; ++c)
 #pragma unroll
             for (int s = 0; s < 4; ++s)
-              umma_f8(d, make_smem_desc(stage + c * kNopeChunkBytes + s * 32, 0, 1024, SWZ_128B),
-                      make_smem_desc(q_addr + c * HB * 128 + s * 32, 0, 1024, SWZ_128B), idesc_qk8, (c | s) != 0);
+              umma_f8(d, with_addr(dk_sw128, stage + c * kNopeChunkBytes + s * 32),
+                      with_addr(dk_sw128, q_addr + c * HB * 128 + s * 32), idesc_qk8, (c | s) != 0);
 #pragma unroll
           for (int s = 0; s < 4; ++s)
-            umma_f16(d, make_smem_desc(stage + kStageNopeBytes + s * 32, 0, 1024, SWZ_128B),
-                     make_smem_desc(q_addr + 4 * HB * 128 + s * 32, 0, 1024, SWZ_128B), idesc_qk16, 1);
+            umma_f16(d, with_addr(dk_sw128, stage + kStageNopeBytes + s * 32),
+                     with_addr(dk_sw128, q_addr + 4 * HB * 128 + s * 32), idesc_qk16, 1);
           umma_commit(&sm.s_full[gi & 1]);
         };
         issue_qk(g);
@@ -266,9 +275,8 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
 #pragma unroll
           for (int j = 0; j < 4; ++j)
             for (int s = 0; s < nk; ++s)
-              umma_f8(tmem + kColO + j * HB,
-                      make_smem_desc(stage + j * kNopeChunkBytes + s * 4096, 16384, 1024, SWZ_128B),
-                      make_smem_desc(pbuf + s * 512, 128, 2048, SWZ_NONE), idesc_pv, (t | s) != 0);
+              umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
+                      with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
           umma_commit(&sm.kv_empty[st]);
           umma_commit(&sm.pv_done);
         }
@@ -278,17 +286,19 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
     }
   } else {
     // ============================== softmax / correction / epilogue ==============================
-    const int st_id = tid - 64;                 // 0..127 within the softmax group
+    const int st_id = tid - 64;                 // 0 .. kSmThreads-1 within the softmax group
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
+    const int cs = (warp - 2) >> 2;             // column slice
+    const int cb = cs * CPT;                    // first q column of this thread
     const int tl = quad * 32 + lane;            // token lane within the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t g = 0, o_seg = 0;
-    float lt[HB];                               // per-lane partial row sums, units of 1/ps relative to mref
+    float lt[CPT];                              // per-lane partial row sums, units of 1/ps relative to mref
 
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
       // ---- per-request state ----
-      named_bar_sync(1, kSoftmaxThreads);  // previous request's readers of sm.* are done
+      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.* are done
       if (st_id < HB) {
         const int row = q_row0 + st_id;
         const bool vq = st_id < n_valid_q;
@@ -301,9 +311,9 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
         if (vq) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, row), sg.end_block * kPage) : sg.valid_end;
         sm.lim[st_id] = lim;
       }
-      named_bar_sync(1, kSoftmaxThreads);
+      named_bar_sync(1, kSmThreads);
 #pragma unroll
-      for (int q = 0; q < HB; ++q) lt[q] = 0.f;
+      for (int q = 0; q < CPT; ++q) lt[q] = 0.f;
       const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
       const bool all_q_valid = n_valid_q == HB && !p.is_causal;
 
@@ -322,51 +332,51 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
 
         mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
         tc_fence_after();
-        float x[HB];
-        const uint32_t s_addr = tmem + kColS + buf * HB + lane_addr;
-        tmem_ld<HB>(s_addr, x);
+        float x[CPT];
+        const uint32_t s_addr = tmem + kColS + buf * HB + cb + lane_addr;
+        tmem_ld<CPT>(s_addr, x);
         tmem_wait_ld();
 
-        uint32_t pk[HB / 4];
+        uint32_t pk[CPT / 4];
         bool trigger = (t == 0);
         if (!trigger) {
           // ---- fast path: reuse the current reference ----
           float vmax = 0.f;
 #pragma unroll
-          for (int q = 0; q < HB; ++q) {
-            float arg = fmaf(x[q] * sm.f[q], ks, -sm.mprime[q]);
-            if (!full_tile && !(token < sm.lim[q])) arg = -INFINITY;
+          for (int q = 0; q < CPT; ++q) {
+            float arg = fmaf(x[q] * sm.f[cb + q], ks, -sm.mprime[cb + q]);
+            if (!full_tile && !(token < sm.lim[cb + q])) arg = -INFINITY;
             const float u = ex2_approx(arg);
             x[q] = u;
             vmax = fmaxf(vmax, u * ks);
           }
 #pragma unroll
-          for (int q = 0; q < HB; q += 4)
+          for (int q = 0; q < CPT; q += 4)
             pk[q / 4] = cvt_e4m3x4(x[q] * ks, x[q + 1] * ks, x[q + 2] * ks, x[q + 3] * ks);
           const bool over = vmax > 448.f;
           if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[g % 3] = 1;
-          named_bar_sync(1, kSoftmaxThreads);
+          named_bar_sync(1, kSmThreads);
           trigger = sm.trig[g % 3] != 0;
           if (!trigger) {
 #pragma unroll
-            for (int q = 0; q < HB; ++q) lt[q] += x[q];
+            for (int q = 0; q < CPT; ++q) lt[q] += x[q];
           }
         }
         if (trigger) {
           // ---- slow path: move the reference (m_ref, p_scale), rescale O and L ----
           if (t != 0) {
-            tmem_ld<HB>(s_addr, x);
+            tmem_ld<CPT>(s_addr, x);
             tmem_wait_ld();
           }
 #pragma unroll
-          for (int q = 0; q < HB; ++q) {
-            float z = (x[q] * sm.f[q]) * ks;
-            if (!(token < sm.lim[q])) z = -INFINITY;
+          for (int q = 0; q < CPT; ++q) {
+            float z = (x[q] * sm.f[cb + q]) * ks;
+            if (!(token < sm.lim[cb + q])) z = -INFINITY;
             x[q] = z;
             const float wm = warp_max_f32(z);
-            if ((q & 31) == lane) sm.red[quad][q] = wm;
+            if (((cb + q) & 31) == lane) sm.red[quad][cb + q] = wm;
           }
-          named_bar_sync(1, kSoftmaxThreads);
+          named_bar_sync(1, kSmThreads);
           float m_old = 0.f, m_new = 0.f;
           if (st_id < HB) {
             const float cm = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
@@ -374,14 +384,14 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
             m_new = fmaxf(m_old, cm);
             sm.mprime[st_id] = m_new;  // temporarily: plain new max, p_scale applied below
           }
-          named_bar_sync(1, kSoftmaxThreads);
+          named_bar_sync(1, kSmThreads);
 #pragma unroll
-          for (int q = 0; q < HB; ++q) {
-            const float pp = ex2_approx(x[q] - sm.mprime[q]) * ks;
+          for (int q = 0; q < CPT; ++q) {
+            const float pp = ex2_approx(x[q] - sm.mprime[cb + q]) * ks;
             const float wm = warp_max_f32(pp);
-            if ((q & 31) == lane) sm.red[quad][q] = wm;
+            if (((cb + q) & 31) == lane) sm.red[quad][cb + q] = wm;
           }
-          named_bar_sync(1, kSoftmaxThreads);
+          named_bar_sync(1, kSmThreads);
           if (st_id < HB) {
             float pmax = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
             pmax = fmaxf(pmax, kPMin);
@@ -392,46 +402,42 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
             sm.ps[st_id] = ps_new;
             sm.mprime[st_id] = m_new + log2f(ps_new);
           }
-          named_bar_sync(1, kSoftmaxThreads);
+          named_bar_sync(1, kSmThreads);
           if (t != 0) {
             // all P.V up to the previous tile must have landed in O before it is rescaled
             mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
+            for (int j = 0; j < 4; ++j) {
+              float o[CPT];
+              const uint32_t a = tmem + kColO + j * HB + cb + lane_addr;
+              tmem_ld<CPT>(a, o);
+              tmem_wait_ld();
 #pragma unroll
-              for (int c0 = 0; c0 < HB; c0 += 16) {
-                float o[16];
-                const uint32_t a = tmem + kColO + j * HB + c0 + lane_addr;
-                tmem_ld<16>(a, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 16; ++k) o[k] *= sm.fac[c0 + k];
-                tmem_st<16>(a, o);
-              }
+              for (int k = 0; k < CPT; ++k) o[k] *= sm.fac[cb + k];
+              tmem_st<CPT>(a, o);
+            }
             tmem_wait_st();
 #pragma unroll
-            for (int q = 0; q < HB; ++q) lt[q] *= sm.fac[q];
+            for (int q = 0; q < CPT; ++q) lt[q] *= sm.fac[cb + q];
           }
 #pragma unroll
-          for (int q = 0; q < HB; ++q) {
-            const float u = ex2_approx(x[q] - sm.mprime[q]);
+          for (int q = 0; q < CPT; ++q) {
+            const float u = ex2_approx(x[q] - sm.mprime[cb + q]);
             lt[q] += u;
             x[q] = u * ks;
           }
 #pragma unroll
-          for (int q = 0; q < HB; q += 4) pk[q / 4] = cvt_e4m3x4(x[q], x[q + 1], x[q + 2], x[q + 3]);
+          for (int q = 0; q < CPT; q += 4) pk[q / 4] = cvt_e4m3x4(x[q], x[q + 1], x[q + 2], x[q + 3]);
         }
 
         // ---- publish P (B operand of P.V: [token][q], MN-major, 8x16-byte core matrices) ----
-        uint8_t* pbuf = s_p + buf * L::kPBytes;
-#pragma unroll
-        for (int c = 0; c < HB / 16; ++c)
-          *reinterpret_cast<uint4*>(pbuf + c * 2048 + (tl >> 3) * 128 + (tl & 7) * 16) =
-              make_uint4(pk[c * 4], pk[c * 4 + 1], pk[c * 4 + 2], pk[c * 4 + 3]);
+        uint8_t* prow = s_p + buf * L::kPBytes + (cb >> 4) * 2048 + (tl >> 3) * 128 + (tl & 7) * 16 + (cb & 15);
+        if constexpr (CPT == 16) *reinterpret_cast<uint4*>(prow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+        else *reinterpret_cast<uint2*>(prow) = make_uint2(pk[0], pk[1]);
         // rows past the end of the sequence feed P.V with P = 0; make sure V there is finite (0 * NaN).
         // Reference: fill_oob_V, splitkv_mla.cu:698-721.
-        if (!tok_valid) {
+        if (!tok_valid && cs == 0) {
           const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
           if (tl < nk * 32) {
             uint8_t* stage = s_kv + (g % kStages) * kStageBytes;
@@ -450,40 +456,40 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
 
       // ---- epilogue of this request: O^T / L -> out (or split partials) ----
 #pragma unroll
-      for (int q = 0; q < HB; ++q) {
+      for (int q = 0; q < CPT; ++q) {
         float v = lt[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(&sm.lsum[q], v);
+        if (lane == 0) atomicAdd(&sm.lsum[cb + q], v);
       }
-      named_bar_sync(1, kSoftmaxThreads);
+      named_bar_sync(1, kSmThreads);
       if (sg.n_tiles > 0) {
         mbar_wait(&sm.pv_done, (g - 1) & 1);
         tc_fence_after();
       }
       const int64_t out_row0 = (int64_t)b * p.M + q_row0;
+      if (st_id < HB) {
+        const float l = sm.lsum[st_id];
+        sm.fac[st_id] = (l == 0.f || l != l) ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
+      }
+      named_bar_sync(1, kSmThreads);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
+        float o[CPT];
+        if (sg.n_tiles > 0) {
+          tmem_ld<CPT>(tmem + kColO + j * HB + cb + lane_addr, o);
+          tmem_wait_ld();
+        } else {
 #pragma unroll
-        for (int c0 = 0; c0 < HB; c0 += 16) {
-          float o[16];
-          if (sg.n_tiles > 0) {
-            tmem_ld<16>(tmem + kColO + j * HB + c0 + lane_addr, o);
-            tmem_wait_ld();
-          } else {
+          for (int k = 0; k < CPT; ++k) o[k] = 0.f;
+        }
+        const int d = j * 128 + tl;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) o[k] = 0.f;
-          }
-#pragma unroll
-          for (int k = 0; k < 16; ++k) {
-            const int q = c0 + k;
-            if (q < n_valid_q) {
-              const float l = sm.lsum[q];
-              const float inv = (l == 0.f || l != l) ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
-              const float val = o[k] * inv;
-              const int d = j * 128 + tl;
-              if (sg.no_split) p.out[(out_row0 + q) * 512 + d] = __float2bfloat16_rn(val);
-              else p.o_accum[((int64_t)sg.split_idx * p.M + q_row0 + q) * 512 + d] = val;
-            }
+        for (int k = 0; k < CPT; ++k) {
+          const int q = cb + k;
+          if (q < n_valid_q) {
+            const float val = o[k] * sm.fac[q];
+            if (sg.no_split) p.out[(out_row0 + q) * 512 + d] = __float2bfloat16_rn(val);
+            else p.o_accum[((int64_t)sg.split_idx * p.M + q_row0 + q) * 512 + d] = val;
           }
         }
       }
@@ -512,15 +518,15 @@ __global__ void __launch_bounds__(kNumThreads, 1) mla_decode_kernel(const __grid
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
-template <int HB>
+template <int HB, int CPT>
 static int launch_mla(const MlaParams& prm, int q_blocks, int num_sm_parts, cudaStream_t stream) {
   const int smem = SmemLayout<HB>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  mla_decode_kernel<HB><<<dim3(q_blocks, 1, num_sm_parts), kNumThreads, smem, stream>>>(prm);
+  mla_decode_kernel<HB, CPT><<<dim3(q_blocks, 1, num_sm_parts), 64 + 128 * (HB / CPT), smem, stream>>>(prm);
   B200_CUDA(cudaGetLastError());
   return 0;
 }
@@ -589,9 +595,9 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.is_causal = is_causal;
 
   int rc;
-  if (HB == 16) rc = launch_mla<16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else if (HB == 32) rc = launch_mla<32>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else rc = launch_mla<64>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else if (HB == 32) rc = launch_mla<32, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else rc = launch_mla<64, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;
   return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);
 }

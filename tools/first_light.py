@@ -47,7 +47,8 @@ def small():
 
 def gemm():
     torch.manual_seed(0)
-    for (m, n, k) in ((16, 128, 128), (32, 256, 512), (128, 7168, 2048), (128, 4096, 7168), (100, 192, 256), (300, 256, 384)):
+    for (m, n, k) in ((16, 128, 128), (32, 256, 512), (128, 7168, 2048), (128, 4096, 7168), (100, 192, 256), (300, 256, 384),
+                      (128, 2112, 7168), (64, 7168, 16384), (128, 24576, 1536), (7, 2112, 7168)):
         x = torch.randn(m, k, dtype=torch.bfloat16, device=dev)
         w = torch.randn(n, k, dtype=torch.bfloat16, device=dev)
         a8, a_s = dg.per_token_cast_to_fp8(x)

@@ -1,0 +1,114 @@
+"""Kernel microbenchmarks on one GPU (CUDA-graph replay, L2-cold by rotating over distinct buffers).
+Usage: python tools/microbench.py [mla] [gemm]"""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from sglang_fluentllm_b200 import flash_mla_fp8 as fm, deep_gemm as dg, _lib
+
+dev = torch.device("cuda:0")
+PEAK = 6555.8
+
+
+def time_graph(fn, n_rot, reps=3):
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        for i in range(min(n_rot, 2)):
+            fn(i)
+        s.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g, stream=s):
+            for i in range(n_rot):
+                fn(i)
+        g.replay()
+        s.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(s)
+        for _ in range(reps):
+            g.replay()
+        e1.record(s)
+        s.synchronize()
+    return e0.elapsed_time(e1) / (reps * n_rot) * 1e3  # us
+
+
+def bench_mla(b, seq, h, s_q=1, n_rot=None):
+    torch.manual_seed(0)
+    pages_per = (seq + 63) // 64 + 1
+    n_pages = b * pages_per + 1
+    kv_bytes = n_pages * 64 * 644
+    if n_rot is None:
+        n_rot = max(2, min(16, int(2.5e8 // kv_bytes) + 2))
+    pools = []
+    tmp = torch.empty(n_pages * 64, 1, 576, dtype=torch.bfloat16, device=dev)
+    idx = torch.arange(n_pages * 64, dtype=torch.int32, device=dev)
+    for _ in range(n_rot):
+        tmp.normal_()
+        kl = torch.empty(n_pages * 64, 1, 512, dtype=torch.uint8, device=dev)
+        ks = torch.empty(n_pages * 64, 1, 1, dtype=torch.float32, device=dev)
+        kr = torch.empty(n_pages * 64, 1, 64, dtype=torch.bfloat16, device=dev)
+        fm.quantize_and_cache_k(tmp, kl, ks, kr, idx, 512)
+        pools.append((kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), ks.view(n_pages, 64, 1, 1)))
+    del tmp
+    q = torch.randn(b, s_q, h, 576, dtype=torch.bfloat16, device=dev)
+    qn, qs, qr = fm.quantize_ckv_per_token_head(q, 512)
+    bt = (torch.randperm(n_pages - 1)[: b * pages_per].reshape(b, pages_per) + 1).to(torch.int32).to(dev)
+    sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    L = _lib.lib()
+    out = torch.empty(b, s_q, h, 512, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(b, h, s_q, dtype=torch.float32, device=dev)
+    ws = torch.empty(L.b200_mla_workspace_bytes(b, s_q, h, meta.shape[0]), dtype=torch.uint8, device=dev)
+
+    def fn(i):
+        kl, kr, ks = pools[i % n_rot]
+        fm.flash_mla_ckv_fp8_per_token(qn, qr, kl, kr, qs, ks, bt, sl, 512, meta, ns, causal=s_q > 1, out=out, lse=lse,
+                                       workspace=ws)
+
+    us = time_graph(fn, n_rot)
+    S, M = b * seq, h * s_q
+    bytes_ = S * 644 + b * M * 644 + b * M * 1024
+    flops = 2 * S * M * 1088
+    print("mla b=%d seq=%d h=%d s_q=%d: %.1f us  %.0f GB/s (%.1f%% of %.0f)  %.0f TFLOP/s" % (
+        b, seq, h, s_q, us, bytes_ / us / 1e3, 100 * bytes_ / us / 1e3 / PEAK, PEAK, flops / us / 1e6), flush=True)
+
+
+def bench_gemm(m, n, k, n_rot=None):
+    torch.manual_seed(0)
+    wbytes = n * k
+    if n_rot is None:
+        n_rot = max(2, min(24, int(3e8 // wbytes) + 2))
+    ws_ = []
+    for _ in range(n_rot):
+        w = torch.randn(n, k, dtype=torch.bfloat16, device=dev)
+        ws_.append(dg.per_block_cast_to_fp8(w))
+    x = torch.randn(m, k, dtype=torch.bfloat16, device=dev)
+    a8, a_s = dg.per_token_cast_to_fp8(x)
+    a_s = dg.get_col_major_tma_aligned_tensor(a_s)
+    out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
+
+    def fn(i):
+        dg.gemm_fp8_fp8_bf16_nt((a8, a_s), ws_[i % n_rot], out, True)
+
+    us = time_graph(fn, n_rot)
+    bytes_ = m * k + n * k + 2 * m * n + 4 * m * k // 128 + 4 * ((n + 127) // 128) * (k // 128)
+    print("gemm m=%d n=%d k=%d: %.2f us  %.0f GB/s (%.1f%%)  %.0f TFLOP/s" % (
+        m, n, k, us, bytes_ / us / 1e3, 100 * bytes_ / us / 1e3 / PEAK, 2.0 * m * n * k / us / 1e6), flush=True)
+
+
+what = sys.argv[1:] or ["mla", "gemm"]
+if "mla" in what:
+    bench_mla(128, 4096, 128)
+    bench_mla(128, 4096, 16)
+    bench_mla(128, 4096, 64)
+    bench_mla(128, 4096, 32)
+    bench_mla(64, 4096, 16, s_q=4)
+    bench_mla(256, 8192, 16, n_rot=2)
+if "gemm" in what:
+    for m in (16, 64, 128):
+        bench_gemm(m, 7168, 2048)
+        bench_gemm(m, 4096, 7168)
+    bench_gemm(128, 2112, 7168)
+    bench_gemm(128, 24576, 1536)
+    bench_gemm(128, 7168, 16384)
+    bench_gemm(4096, 7168, 2048)
+    bench_gemm(4096, 4096, 7168)
