@@ -118,6 +118,9 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
  * Writes max|got-expected|/max|expected| of one operand-layout variant to *rel_err. */
 int b200_umma_selftest(int variant, int n, float* rel_err);
 
+/* Issue-rate probe for the same operand layouts: average SM cycles per tcgen05.mma (M=128, N=n, K=32 B). */
+int b200_umma_rate(int variant, int n, int iters, float* cycles_per_mma);
+
 #ifdef __cplusplus
 }
 #endif

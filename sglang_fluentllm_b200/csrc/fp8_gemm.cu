@@ -200,6 +200,208 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// m > 64: tokens on the UMMA M side (128 rows), 256 weight rows on the N side.  Each CTA re-reads the activation tile
+// once per 256 weight rows (half the L2->SM traffic of the 128-row orientation), the activation scale is a per-thread
+// scalar (thread = token row), the weight scale a per-128-column scalar, so promotion is one packed FMA per pair, and
+// the epilogue writes 128 contiguous bytes per thread.
+// ------------------------------------------------------------------------------------------------------------------
+struct GemmTokMSmem {
+  static constexpr int kStages = 4;
+  static constexpr int kABytes = 128 * 128;   // token tile
+  static constexpr int kWBytes = 256 * 128;   // weight tile
+  static constexpr int kStageBytes = kABytes + kWBytes + 1024;  // + 128 activation scales
+  static constexpr int kTotal = kStages * kStageBytes + 1024;
+};
+
+__global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
+  using S = GemmTokMSmem;
+  constexpr int kStages = S::kStages;
+  constexpr int BN = 256, CPT = 64, kPromo = 512;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  struct Bars {
+    uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
+    uint32_t tmem_base;
+    uint32_t is_last;
+  };
+  Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * S::kStageBytes);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int total_kb = p.k / 128;
+  const int kb0 = blockIdx.z * p.kb_per_split;
+  const int num_kb = min(p.kb_per_split, total_kb - kb0);
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) {
+      mbar_init(&bars.full[i], 1);
+      mbar_init(&bars.empty[i], 1 + kPromo);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&bars.acc_full[i], 1);
+      mbar_init(&bars.acc_empty[i], kPromo);
+    }
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_w);
+    tma_prefetch_desc(&p.tm_a);
+  }
+  if (warp == 1) tmem_alloc(&bars.tmem_base, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = bars.tmem_base;
+  pdl_wait_prior_grid();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint64_t pol_w = policy_evict_first();
+      const int rows_valid = min(128, p.m - m0);
+      const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
+      for (int i = 0; i < num_kb; ++i) {
+        const int kb = kb0 + i;
+        const int st = i % kStages;
+        mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
+        uint8_t* stage = smem + st * S::kStageBytes;
+        mbar_arrive_expect_tx(&bars.full[st], S::kABytes + S::kWBytes + scale_bytes);
+        tma_load_2d(stage, &p.tm_a, &bars.full[st], kb * 128, m0);
+        tma_load_2d_hint(stage + S::kABytes, &p.tm_w, &bars.full[st], kb * 128, n0, pol_w);
+        bulk_load_1d(stage + S::kABytes + S::kWBytes, p.a_scales + (int64_t)kb * p.a_scale_stride + m0, scale_bytes,
+                     &bars.full[st]);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BN);
+      const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
+      for (int i = 0; i < num_kb; ++i) {
+        const int st = i % kStages, buf = i & 1;
+        mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
+        mbar_wait(&bars.full[st], (i / kStages) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + st * S::kStageBytes);
+        const uint32_t w_addr = a_addr + S::kABytes;
+#pragma unroll
+        for (int s = 0; s < 4; ++s)
+          umma_f8(tmem + buf * BN, dk | (uint64_t)(((a_addr + s * 32) >> 4) & 0x3FFF),
+                  dk | (uint64_t)(((w_addr + s * 32) >> 4) & 0x3FFF), idesc, s != 0);
+        umma_commit(&bars.empty[st]);
+        umma_commit(&bars.acc_full[buf]);
+      }
+    }
+  } else {
+    const int quad = warp & 3;
+    const int cs = (warp - 2) >> 2;             // 0..3: 64-column slice
+    const int cb = cs * CPT;
+    const int row = quad * 32 + lane;           // token row within the tile = TMEM lane
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const int nblk = (n0 + cb) / 128;           // weight scale block of this thread's columns
+    const bool blk_valid = (n0 + cb) < p.n;
+    float2 acc[CPT / 2];
+#pragma unroll
+    for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % kStages, buf = i & 1;
+      const float sb = blk_valid ? __ldg(p.b_scales + (int64_t)nblk * total_kb + kb0 + i) : 0.f;
+      mbar_wait(&bars.acc_full[buf], (i >> 1) & 1);
+      tc_fence_after();
+      const float sa = reinterpret_cast<const float*>(smem + st * S::kStageBytes + S::kABytes + S::kWBytes)[row];
+      const float sc = sa * sb;
+      const float2 s2 = make_float2(sc, sc);
+      float v[CPT];
+      tmem_ld<CPT>(tmem + buf * BN + cb + lane_addr, v);
+      tmem_wait_ld();
+#pragma unroll
+      for (int j = 0; j < CPT / 2; ++j) acc[j] = fma2(make_float2(v[2 * j], v[2 * j + 1]), s2, acc[j]);
+      tc_fence_before();
+      mbar_arrive(&bars.acc_empty[buf]);
+      mbar_arrive(&bars.empty[st]);
+    }
+    const int grow = m0 + row;
+    const bool row_ok = grow < p.m;
+    if (p.splits == 1) {
+      if (row_ok) {
+        __nv_bfloat16* dst = p.out + (int64_t)grow * p.n + n0 + cb;
+#pragma unroll
+        for (int j = 0; j < CPT; j += 8) {
+          if (n0 + cb + j < p.n) {
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j / 2].x, acc[j / 2].y);
+            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[j / 2 + 1].x, acc[j / 2 + 1].y);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[j / 2 + 2].x, acc[j / 2 + 2].y);
+            __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[j / 2 + 3].x, acc[j / 2 + 3].y);
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          }
+        }
+      }
+    } else {
+      if (row_ok) {
+        float* dst = p.ws + (int64_t)grow * p.n + n0 + cb;
+#pragma unroll
+        for (int j = 0; j < CPT; j += 4)
+          if (n0 + cb + j < p.n)
+            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(acc[j / 2].x), "f"(acc[j / 2].y),
+                         "f"(acc[j / 2 + 1].x), "f"(acc[j / 2 + 1].y)
+                         : "memory");
+      }
+      __threadfence();
+      named_bar_sync(1, kPromo);
+      if (tid == 64) {
+        const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
+        const unsigned int prev = atomicAdd(p.counters + tile, 1u);
+        bars.is_last = (prev == (unsigned int)p.splits - 1) ? 1u : 0u;
+        if (bars.is_last) p.counters[tile] = 0;
+      }
+      named_bar_sync(1, kPromo);
+      if (bars.is_last && row_ok) {
+        __threadfence();
+        float* src = p.ws + (int64_t)grow * p.n + n0 + cb;
+        __nv_bfloat16* dst = p.out + (int64_t)grow * p.n + n0 + cb;
+#pragma unroll
+        for (int j = 0; j < CPT; j += 8) {
+          if (n0 + cb + j < p.n) {
+            const float4 a = __ldcg(reinterpret_cast<const float4*>(src + j));
+            const float4 b = __ldcg(reinterpret_cast<const float4*>(src + j + 4));
+            __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+            __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+            *reinterpret_cast<uint4*>(dst + j) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            __stcg(reinterpret_cast<float4*>(src + j), make_float4(0.f, 0.f, 0.f, 0.f));
+            __stcg(reinterpret_cast<float4*>(src + j + 4), make_float4(0.f, 0.f, 0.f, 0.f));
+          }
+        }
+      }
+    }
+  }
+  pdl_launch_dependents();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
+  const int smem = GemmTokMSmem::kTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((prm.n + 255) / 256, (prm.m + 127) / 128, prm.splits);
+  cfg.blockDim = dim3(64 + 512, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel, prm));
+  return 0;
+}
+
 template <int BT, int CPT>
 static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmSmem<BT>::kTotal + 1024;
@@ -224,11 +426,16 @@ static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) 
 }
 
 static int pick_bt(int m) { return m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128)); }
+static bool tokens_on_m(int m) { return m > 64; }
+static int num_tiles(int m, int n) {
+  if (tokens_on_m(m)) return ((n + 255) / 256) * ((m + 127) / 128);
+  const int bt = pick_bt(m);
+  return ((n + 127) / 128) * ((m + bt - 1) / bt);
+}
 
 // split-K factor: fill the SMs when the (weight tile x token tile) grid is small; keep >= 4 k-blocks per split
 static int pick_splits(int m, int n, int k, int sm_count) {
-  const int bt = pick_bt(m);
-  const int tiles = ((n + 127) / 128) * ((m + bt - 1) / bt);
+  const int tiles = num_tiles(m, n);
   const int num_kb = k / 128;
   if (tiles * 2 > sm_count) return 1;
   int splits = sm_count / tiles;
@@ -246,8 +453,7 @@ extern "C" {
 size_t b200_fp8_gemm_workspace_bytes(int m, int n, int k) {
   const int sms = device_sm_count();
   if (pick_splits(m, n, k, sms > 0 ? sms : 148) == 1) return 0;
-  const int bt = pick_bt(m);
-  const size_t tiles = (size_t)((n + 127) / 128) * ((m + bt - 1) / bt);
+  const size_t tiles = (size_t)num_tiles(m, n);
   return (size_t)m * n * sizeof(float) + tiles * sizeof(unsigned int);
 }
 
@@ -281,8 +487,11 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
     prm.ws = (float*)workspace;
     prm.counters = (unsigned int*)((char*)workspace + (size_t)m * n * sizeof(float));
   }
-  if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, 128, TmaSwizzle::B128)) return 1;
-  if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)m, (uint64_t)k, 128, BT, TmaSwizzle::B128)) return 1;
+  const bool tokm = tokens_on_m(m);
+  if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, tokm ? 256 : 128, TmaSwizzle::B128))
+    return 1;
+  if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)m, (uint64_t)k, 128, tokm ? 128 : BT, TmaSwizzle::B128))
+    return 1;
   prm.a_scales = a_scales;
   prm.a_scale_stride = a_scale_stride;
   prm.b_scales = b_scales;
@@ -290,11 +499,12 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.m = m;
   prm.n = n;
   prm.k = k;
+  if (tokm) return launch_gemm_tokm(prm, use_pdl, (cudaStream_t)stream);
   switch (BT) {
     case 16: return launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
     case 32: return launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
     case 64: return launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
-    default: return launch_gemm<128, 32>(prm, use_pdl, (cudaStream_t)stream);
+    default: return launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
   }
 }
 

@@ -16,8 +16,9 @@
 //   LDSM/byte_perm/STSM transpose of V (ckv_fp8_per_token/utils.h:39-147) disappears.
 //   The four 128-byte k-chunks of the QK contraction are exactly the four 128-lane M tiles of the PV product.
 //
-//   Warp roles (192 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = UMMA issuer, warps 2-5 = softmax /
-//   correction / epilogue (one thread per KV token = one TMEM lane).
+//   Warp roles (1 CTA/SM): warp 0 = TMA producer, warp 1 = UMMA issuer for Q.K^T, warp 2 = UMMA issuer for P.V,
+//   warp 3 idle, warps 4.. = softmax / correction / epilogue (4 TMEM lane quadrants x HB/CPT column slices; one
+//   thread per (KV token, column slice)).
 //   TMEM: S double-buffered (2 x HB columns) + O (4 x HB columns).
 //
 //   Online softmax keeps a per-q-row reference (m_ref, p_scale) in shared memory and only moves it -- and rescales
@@ -130,7 +131,7 @@ __device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_id
 // The softmax group has 4 * HB/CPT warps: 4 TMEM lane quadrants x HB/CPT column slices, so the per-thread work per
 // tile is CPT elements and every SM sub-partition has HB/CPT warps to hide ALU / MUFU / TMEM-load latency.
 template <int HB, int CPT>
-__global__ void __launch_bounds__(64 + 128 * (HB / CPT), 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
+__global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
   using L = SmemLayout<HB>;
   constexpr uint32_t kTmemCols = HB == 64 ? 512 : (HB == 32 ? 256 : 128);
   constexpr uint32_t kColS = 0, kColO = 2 * HB;
@@ -181,71 +182,101 @@ __global__ void __launch_bounds__(64 + 128 * (HB / CPT), 1) mla_decode_kernel(co
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
 
+  // Issuer warps run warp-uniform code (every lane executes the loops and the barrier waits) and predicate only the
+  // TMA / MMA instructions with elect.sync: descriptors and coordinates then live in uniform registers.  Issuing from
+  // a divergent `if (lane == 0)` costs ~110 cycles per tcgen05.mma (R2UR traffic), measured with b200_umma_rate.
   if (warp == 0) {
     // ============================== TMA producer ==============================
-    if (lane == 0) {
-      const uint64_t pol_kv = policy_evict_first();
-      const bool shared_kv = gridDim.x > 1;  // sibling q-block CTAs stream the same pages: let L2 keep them
-      uint32_t g = 0, seg_i = 0;
-      for (int b = begin_idx; b <= end_idx; ++b) {
-        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
-        if (sg.n_tiles == 0) continue;
-        // Q tile of this request (rows beyond the request are masked by the consumers)
-        mbar_wait(&sm.q_empty, (seg_i & 1) ^ 1);
-        ++seg_i;
+    const uint64_t pol_kv = policy_evict_first();
+    const bool shared_kv = gridDim.x > 1;  // sibling q-block CTAs stream the same pages: let L2 keep them
+    uint32_t g = 0, seg_i = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+      if (sg.n_tiles == 0) continue;
+      // Q tile of this request (rows beyond the request are masked by the consumers)
+      mbar_wait(&sm.q_empty, (seg_i & 1) ^ 1);
+      ++seg_i;
+      const int qrow = b * p.M + q_row0;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&sm.q_full, L::kQBytes);
-        const int qrow = b * p.M + q_row0;
+#pragma unroll
         for (int c = 0; c < 4; ++c) tma_load_2d(s_q + c * HB * 128, &p.tm_q_nope, &sm.q_full, c * 128, qrow);
         tma_load_2d(s_q + 4 * HB * 128, &p.tm_q_rope, &sm.q_full, 0, qrow);
-        const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
-        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          const uint32_t st = g % kStages;
-          mbar_wait(&sm.kv_empty[st], ((g / kStages) & 1) ^ 1);
-          const int blk0 = sg.start_block + 2 * t;
-          const int npages = min(2, sg.end_block - blk0);
+      }
+      __syncwarp();
+      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        const uint32_t st = g % kStages;
+        mbar_wait(&sm.kv_empty[st], ((g / kStages) & 1) ^ 1);
+        const int blk0 = sg.start_block + 2 * t;
+        const int npages = min(2, sg.end_block - blk0);
+        uint8_t* stage = s_kv + st * kStageBytes;
+        const int tok0 = __ldg(bt + blk0) * kPage;
+        const int tok1 = npages > 1 ? __ldg(bt + blk0 + 1) * kPage : 0;
+        // warm L2 for the tile that will reuse this stage (two tiles ahead): HBM latency is then overlapped with
+        // the consumption of the current tiles instead of being paid after the stage is released
+        const int pf0 = blk0 + 2 * kStages < sg.end_block ? __ldg(bt + blk0 + 2 * kStages) * kPage : -1;
+        const int pf1 = blk0 + 2 * kStages + 1 < sg.end_block ? __ldg(bt + blk0 + 2 * kStages + 1) * kPage : -1;
+        if (elect_one()) {
           mbar_arrive_expect_tx(&sm.kv_full[st], npages * kPageTxBytes);
-          uint8_t* stage = s_kv + st * kStageBytes;
-          for (int pg = 0; pg < npages; ++pg) {
-            const int tok0 = __ldg(bt + blk0 + pg) * kPage;
-            if (shared_kv) {
+          if (shared_kv) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              tma_load_2d(stage + c * kNopeChunkBytes, &p.tm_k_nope, &sm.kv_full[st], c * 128, tok0);
+            tma_load_2d(stage + kStageNopeBytes, &p.tm_k_rope, &sm.kv_full[st], 0, tok0);
+            if (npages > 1) {
+#pragma unroll
               for (int c = 0; c < 4; ++c)
-                tma_load_2d(stage + c * kNopeChunkBytes + pg * (kPage * 128), &p.tm_k_nope, &sm.kv_full[st], c * 128,
-                            tok0);
-              tma_load_2d(stage + kStageNopeBytes + pg * (kPage * 128), &p.tm_k_rope, &sm.kv_full[st], 0, tok0);
-            } else {
+                tma_load_2d(stage + c * kNopeChunkBytes + kPage * 128, &p.tm_k_nope, &sm.kv_full[st], c * 128, tok1);
+              tma_load_2d(stage + kStageNopeBytes + kPage * 128, &p.tm_k_rope, &sm.kv_full[st], 0, tok1);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+              tma_load_2d_hint(stage + c * kNopeChunkBytes, &p.tm_k_nope, &sm.kv_full[st], c * 128, tok0, pol_kv);
+            tma_load_2d_hint(stage + kStageNopeBytes, &p.tm_k_rope, &sm.kv_full[st], 0, tok0, pol_kv);
+            if (npages > 1) {
+#pragma unroll
               for (int c = 0; c < 4; ++c)
-                tma_load_2d_hint(stage + c * kNopeChunkBytes + pg * (kPage * 128), &p.tm_k_nope, &sm.kv_full[st],
-                                 c * 128, tok0, pol_kv);
-              tma_load_2d_hint(stage + kStageNopeBytes + pg * (kPage * 128), &p.tm_k_rope, &sm.kv_full[st], 0, tok0,
-                               pol_kv);
+                tma_load_2d_hint(stage + c * kNopeChunkBytes + kPage * 128, &p.tm_k_nope, &sm.kv_full[st], c * 128,
+                                 tok1, pol_kv);
+              tma_load_2d_hint(stage + kStageNopeBytes + kPage * 128, &p.tm_k_rope, &sm.kv_full[st], 0, tok1, pol_kv);
             }
           }
+          if (pf0 >= 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, pf0);
+            tma_prefetch_2d(&p.tm_k_rope, 0, pf0);
+          }
+          if (pf1 >= 0) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, pf1);
+            tma_prefetch_2d(&p.tm_k_rope, 0, pf1);
+          }
         }
+        __syncwarp();
       }
     }
   } else if (warp == 1) {
-    // ============================== UMMA issuer ==============================
-    if (lane == 0) {
-      constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, HB);
-      constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, HB);
-      constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
-      const uint32_t kv_addr = smem_u32(s_kv), q_addr = smem_u32(s_q), p_addr = smem_u32(s_p);
-      // descriptor templates: only the 14-bit start-address field changes per MMA
-      const uint64_t dk_sw128 = make_smem_desc(0, 0, 1024, SWZ_128B);        // K-major, 128-B swizzle
-      const uint64_t dv_sw128 = make_smem_desc(0, 16384, 1024, SWZ_128B);    // MN-major view of the same bytes
-      const uint64_t dp_none = make_smem_desc(0, 128, 2048, SWZ_NONE);       // P: 8x16-B core matrices
-      auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
-      uint32_t g = 0, o_seg = 0;
-      for (int b = begin_idx; b <= end_idx; ++b) {
-        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
-        if (sg.n_tiles == 0) continue;
-        mbar_wait(&sm.q_full, o_seg & 1);
-        auto issue_qk = [&](uint32_t gi) {
-          const uint32_t st = gi % kStages;
-          mbar_wait(&sm.kv_full[st], (gi / kStages) & 1);
-          tc_fence_after();
-          const uint32_t stage = kv_addr + st * kStageBytes;
-          const uint32_t d = tmem + kColS + (gi & 1) * HB;
+    // ============================== UMMA issuer: S^T = K . Q^T ==============================
+    constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, HB);
+    constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, HB);
+    const uint32_t kv_addr = smem_u32(s_kv), q_addr = smem_u32(s_q);
+    const uint64_t dk_sw128 = make_smem_desc(0, 0, 1024, SWZ_128B);  // K-major, 128-B swizzle
+    auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
+    uint32_t g = 0, seg = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+      if (sg.n_tiles == 0) continue;
+      mbar_wait(&sm.q_full, seg & 1);
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        const uint32_t st = g % kStages, buf = g & 1;
+        mbar_wait(&sm.kv_full[st], (g / kStages) & 1);
+        mbar_wait(&sm.p_full[buf], ((g >> 1) & 1) ^ 1);  // S[buf] drained by the softmax of tile g-2
+        tc_fence_after();
+        const uint32_t stage = kv_addr + st * kStageBytes;
+        const uint32_t d = tmem + kColS + buf * HB;
+        if (elect_one()) {
 #pragma unroll
           for (int c = 0; c < 4; ++c)
 #pragma unroll
@@ -256,39 +287,54 @@ __global__ void __launch_bounds__(64 + 128 * (HB / CPT), 1) mla_decode_kernel(co
           for (int s = 0; s < 4; ++s)
             umma_f16(d, with_addr(dk_sw128, stage + kStageNopeBytes + s * 32),
                      with_addr(dk_sw128, q_addr + 4 * HB * 128 + s * 32), idesc_qk16, 1);
-          umma_commit(&sm.s_full[gi & 1]);
-        };
-        issue_qk(g);
-        for (int t = 0; t < sg.n_tiles; ++t) {
-          const uint32_t gi = g + t;
-          if (t + 1 < sg.n_tiles) issue_qk(gi + 1);
-          else umma_commit(&sm.q_empty);  // all QK MMAs of this request issued: Q smem reusable once they finish
-          // ---- P.V for tile gi ----
-          mbar_wait(&sm.p_full[gi & 1], (gi >> 1) & 1);
-          if (t == 0 && o_seg > 0) mbar_wait(&sm.o_free, (o_seg - 1) & 1);
-          tc_fence_after();
-          const uint32_t st = gi % kStages;
-          const uint32_t stage = kv_addr + st * kStageBytes;
-          const int tile_start = (sg.start_block + 2 * t) * kPage;
-          const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
-          const uint32_t pbuf = p_addr + (gi & 1) * L::kPBytes;
+          umma_commit(&sm.s_full[buf]);
+          // last Q.K^T of this request issued: Q smem is reusable once these MMAs retire
+          if (t == sg.n_tiles - 1) umma_commit(&sm.q_empty);
+        }
+        __syncwarp();
+      }
+      ++seg;
+    }
+  } else if (warp == 2) {
+    // ============================== UMMA issuer: O^T += V^T . P ==============================
+    constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
+    const uint32_t kv_addr = smem_u32(s_kv), p_addr = smem_u32(s_p);
+    const uint64_t dv_sw128 = make_smem_desc(0, 16384, 1024, SWZ_128B);  // MN-major view of the K tile bytes
+    const uint64_t dp_none = make_smem_desc(0, 128, 2048, SWZ_NONE);     // P: 8x16-B core matrices
+    auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
+    uint32_t g = 0, seg = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
+      if (sg.n_tiles == 0) continue;
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        const uint32_t st = g % kStages, buf = g & 1;
+        mbar_wait(&sm.p_full[buf], (g >> 1) & 1);
+        if (t == 0 && seg > 0) mbar_wait(&sm.o_free, (seg - 1) & 1);
+        tc_fence_after();
+        const uint32_t stage = kv_addr + st * kStageBytes;
+        const int tile_start = (sg.start_block + 2 * t) * kPage;
+        const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
+        const uint32_t pbuf = p_addr + buf * L::kPBytes;
+        if (elect_one()) {
 #pragma unroll
           for (int j = 0; j < 4; ++j)
-            for (int s = 0; s < nk; ++s)
-              umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
-                      with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              if (s < nk)
+                umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
+                        with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
           umma_commit(&sm.kv_empty[st]);
           umma_commit(&sm.pv_done);
         }
-        g += sg.n_tiles;
-        ++o_seg;
+        __syncwarp();
       }
+      ++seg;
     }
-  } else {
+  } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue ==============================
-    const int st_id = tid - 64;                 // 0 .. kSmThreads-1 within the softmax group
+    const int st_id = tid - 128;                // 0 .. kSmThreads-1 within the softmax group
     const int quad = warp & 3;                  // TMEM lane quadrant this warp may access
-    const int cs = (warp - 2) >> 2;             // column slice
+    const int cs = (warp - 4) >> 2;             // column slice
     const int cb = cs * CPT;                    // first q column of this thread
     const int tl = quad * 32 + lane;            // token lane within the tile
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
@@ -432,6 +478,8 @@ __global__ void __launch_bounds__(64 + 128 * (HB / CPT), 1) mla_decode_kernel(co
         }
 
         // ---- publish P (B operand of P.V: [token][q], MN-major, 8x16-byte core matrices) ----
+        // P[buf] (and this KV stage) were last read by P.V of tile g-2, issued by another warp: wait for it to retire
+        mbar_wait(&sm.kv_empty[g % kStages], ((g / kStages) & 1) ^ 1);
         uint8_t* prow = s_p + buf * L::kPBytes + (cb >> 4) * 2048 + (tl >> 3) * 128 + (tl & 7) * 16 + (cb & 15);
         if constexpr (CPT == 16) *reinterpret_cast<uint4*>(prow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
         else *reinterpret_cast<uint2*>(prow) = make_uint2(pk[0], pk[1]);
@@ -526,7 +574,7 @@ static int launch_mla(const MlaParams& prm, int q_blocks, int num_sm_parts, cuda
     B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  mla_decode_kernel<HB, CPT><<<dim3(q_blocks, 1, num_sm_parts), 64 + 128 * (HB / CPT), smem, stream>>>(prm);
+  mla_decode_kernel<HB, CPT><<<dim3(q_blocks, 1, num_sm_parts), 128 + 128 * (HB / CPT), smem, stream>>>(prm);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -117,6 +117,78 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
   if (warp == 1) tmem_dealloc(tmem, 256);
 }
 
+// Issue-rate probe: `iters` back-to-back MMAs of one operand-layout variant on resident (uninitialised) smem.
+//   variant 0: fp8 A K-major SW128 x B K-major SW128         (Q.K^T nope, GEMM)
+//   variant 1: bf16 A K-major SW128 x B K-major SW128        (Q.K^T rope)
+//   variant 2: fp8 A MN-major SW128 x B MN-major no-swizzle  (P.V as shipped)
+//   variant 3: fp8 A MN-major SW128 x B K-major SW128        (P.V with a K-major P)
+//   variant 4: fp8 A K-major SW128 x B MN-major no-swizzle
+__global__ void __launch_bounds__(128, 1) umma_rate_kernel(int variant, int n, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  for (int i = tid; i < (64 + 32) * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x38383838u;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  // Warp 0 issues from warp-uniform code: every lane runs the loop, only the MMA is predicated with elect.sync, so the
+  // descriptors stay in uniform registers (variant >= 8 selects the old divergent `if (tid == 0)` issue for contrast).
+  const bool divergent = variant >= 8;
+  variant &= 7;
+  if (warp == 0 && (!divergent || tid == 0)) {
+    const uint32_t a = smem_u32(smem), b = a + 64 * 1024;
+    const bool bf = variant == 1;
+    const uint32_t a_mn = (variant == 2 || variant == 3), b_mn = (variant == 2 || variant == 4);
+    const uint32_t idesc = make_idesc(bf ? FMT_BF16 : FMT_E4M3, bf ? FMT_BF16 : FMT_E4M3, a_mn, b_mn, 128, n);
+    const uint64_t da0 = a_mn ? make_smem_desc(0, 16384, 1024, SWZ_128B) : make_smem_desc(0, 0, 1024, SWZ_128B);
+    const uint64_t db0 = b_mn ? make_smem_desc(0, 128, 2048, SWZ_NONE) : make_smem_desc(0, 0, 1024, SWZ_128B);
+    const long long t0 = clock64();
+    if (divergent) {
+      for (int i = 0; i < iters; ++i) {
+        const uint32_t ka = a_mn ? (i & 3) * 4096 + ((i >> 2) & 3) * 16384 : (i & 3) * 32 + ((i >> 2) & 3) * 16384;
+        const uint32_t kb = b_mn ? (i & 3) * 512 : (i & 3) * 32;
+        const uint64_t da = da0 | (uint64_t)(((a + ka) >> 4) & 0x3FFF);
+        const uint64_t db = db0 | (uint64_t)(((b + kb) >> 4) & 0x3FFF);
+        if (bf) umma_f16(tmem + (i & 1) * 256, da, db, idesc, 1);
+        else umma_f8(tmem + (i & 1) * 256, da, db, idesc, 1);
+      }
+      umma_commit(&bar);
+    } else {
+      for (int i = 0; i < iters; i += 16) {
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const uint32_t ka = a_mn ? (j & 3) * 4096 + ((j >> 2) & 3) * 16384 : (j & 3) * 32 + ((j >> 2) & 3) * 16384;
+            const uint32_t kb = b_mn ? (j & 3) * 512 : (j & 3) * 32;
+            const uint64_t da = da0 | (uint64_t)(((a + ka) >> 4) & 0x3FFF);
+            const uint64_t db = db0 | (uint64_t)(((b + kb) >> 4) & 0x3FFF);
+            if (bf) umma_f16(tmem + (j & 1) * 256, da, db, idesc, 1);
+            else umma_f8(tmem + (j & 1) * 256, da, db, idesc, 1);
+          }
+        }
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&bar);
+      __syncwarp();
+    }
+    mbar_wait(&bar, 0);
+    if (lane_id() == 0) cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
 static float e4m3_to_float(uint8_t c) {
   int s = c >> 7, e = (c >> 3) & 0xF, m = c & 7;
   float v;
@@ -243,4 +315,24 @@ extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
   cudaFree(dB);
   cudaFree(dOut);
   return rc;
+}
+
+// Average SM cycles per tcgen05.mma (M=128, N=n, K=32 bytes) for one operand-layout variant; see umma_rate_kernel.
+extern "C" int b200_umma_rate(int variant, int n, int iters, float* cycles_per_mma) {
+  B200_CHECK(n % 16 == 0 && n >= 16 && n <= 256 && iters > 0 && iters % 16 == 0, "umma_rate: bad arguments");
+  long long* d = nullptr;
+  B200_CUDA(cudaMalloc(&d, sizeof(long long)));
+  const int smem_bytes = 1024 + (64 + 32) * 1024;
+  cudaFuncSetAttribute(umma_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  umma_rate_kernel<<<1, 128, smem_bytes>>>(variant, n, iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long h = 0;
+  if (e == cudaSuccess) cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_last_error("umma_rate: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  *cycles_per_mma = (float)h / iters;
+  return 0;
 }

@@ -1,0 +1,337 @@
+"""Attention plug-in for the quantised decode path: ``FlashMLABackend`` with the reference's method names, argument
+order and metadata handling (python/sglang/srt/layers/attention/flashmla_backend.py:49-408), an
+``AttentionBackend`` base with the reference's ``forward`` dispatch (base_attn_backend.py:15-127), and the two
+pool-side classes the backend reads -- ``MLATokenToKVPool`` in the per-token-FP8 layout
+(mem_cache/memory_pool.py:591-882) and ``KVAllocator`` (mem_cache/allocator.py:19-102).
+
+In the reference the backend is imported only when ``is_sm90_supported()`` (model_executor/attn_initializer.py:25-29)
+and inherits its prefill from FlashInferMLAAttnBackend.  Here the class is self-contained, duck-types ``model_runner``
+/ ``forward_batch`` / ``layer`` (so it can be registered in the reference's AttnInitializer -- see INTEGRATION.md -- or
+driven directly by tests and bench.py) and covers DECODE / IDLE / TARGET_VERIFY / DRAFT_EXTEND.  EXTEND (prefill) is
+outside the hot path and raises.
+"""
+from __future__ import annotations
+
+from abc import ABC, abstractmethod
+from enum import IntEnum, auto
+from typing import Optional
+
+import torch
+
+from . import flash_mla_fp8
+
+PAGE_SIZE = 64  # flashmla_backend.py:25
+
+
+class ForwardMode(IntEnum):
+    """model_executor/forward_batch_info.py:61-101 (same members and predicates)."""
+    EXTEND = auto()
+    DECODE = auto()
+    MIXED = auto()
+    IDLE = auto()
+    TARGET_VERIFY = auto()
+    DRAFT_EXTEND = auto()
+    DUMMY_FIRST = auto()
+
+    def is_extend(self):
+        return self in (ForwardMode.EXTEND, ForwardMode.MIXED, ForwardMode.DRAFT_EXTEND, ForwardMode.TARGET_VERIFY)
+
+    def is_decode(self):
+        return self == ForwardMode.DECODE
+
+    def is_idle(self):
+        return self == ForwardMode.IDLE
+
+    def is_decode_or_idle(self):
+        return self == ForwardMode.DECODE or self == ForwardMode.IDLE
+
+    def is_target_verify(self):
+        return self == ForwardMode.TARGET_VERIFY
+
+    def is_draft_extend(self):
+        return self == ForwardMode.DRAFT_EXTEND
+
+    def is_cuda_graph(self):
+        return self in (ForwardMode.DECODE, ForwardMode.TARGET_VERIFY, ForwardMode.IDLE)
+
+
+class AttentionBackend(ABC):
+    """base_attn_backend.py:15-127."""
+
+    @abstractmethod
+    def init_forward_metadata(self, forward_batch):
+        raise NotImplementedError()
+
+    def init_cuda_graph_state(self, max_bs: int):
+        raise NotImplementedError()
+
+    def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens, forward_mode,
+                                                 spec_info):
+        raise NotImplementedError()
+
+    def init_forward_metadata_replay_cuda_graph(self, bs, req_pool_indices, seq_lens, seq_lens_sum, forward_mode,
+                                                spec_info):
+        raise NotImplementedError()
+
+    def get_cuda_graph_seq_len_fill_value(self):
+        raise NotImplementedError()
+
+    def forward(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, **kwargs):
+        if forward_batch.forward_mode.is_decode():
+            return self.forward_decode(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache, **kwargs)
+        return self.forward_extend(q, k, v, layer, forward_batch, save_kv_cache=save_kv_cache, **kwargs)
+
+    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, **kwargs):
+        raise NotImplementedError()
+
+    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache: bool = True, **kwargs):
+        raise NotImplementedError()
+
+
+class KVAllocator:
+    """mem_cache/allocator.py:19-102,169-173: owns ``req_to_page`` (int32 [max_bs, ceil(ctx/page)]) and hands out
+    pages in increasing order from 1 (page 0 is the padding page)."""
+
+    def __init__(self, size: int, device, max_batch_size: int, max_context_len: int, page_size: int = PAGE_SIZE):
+        self.size, self.device, self.page_size = size, device, page_size
+        self.max_page_num = (max_context_len + page_size - 1) // page_size
+        self.req_to_page = torch.zeros((max_batch_size, self.max_page_num), dtype=torch.int32, device=device)
+        self.clear()
+
+    def clear(self):
+        self.free_slots = torch.arange(1, self.size // self.page_size, dtype=torch.int32)
+
+    def available_size(self):
+        return len(self.free_slots)
+
+    def alloc(self, req_pool_index: int, need_size: int, alloced_len: int):
+        ps = self.page_size
+        page_offset = alloced_len % ps
+        page_num = (alloced_len + ps - 1) // ps
+        last_page_remain = page_num * ps - alloced_len
+        last_page_id = int(self.req_to_page[req_pool_index, page_num - 1].item())
+        kv_loc = last_page_id * ps + page_offset + torch.arange(0, min(last_page_remain, need_size), dtype=torch.int32)
+        if last_page_remain >= need_size:
+            return kv_loc.to(self.device, non_blocking=True)
+        remain = need_size - last_page_remain
+        need_pages = (remain + ps - 1) // ps
+        if need_pages > len(self.free_slots) or page_num + need_pages > self.max_page_num:
+            return None
+        new_pages = self.free_slots[:need_pages]
+        self.free_slots = self.free_slots[need_pages:]
+        self.req_to_page[req_pool_index, page_num:page_num + need_pages] = new_pages.to(self.device)
+        kv_loc1 = (new_pages.unsqueeze(1) * ps + torch.arange(0, ps, dtype=torch.int32)).flatten()[:remain]
+        return torch.concat([kv_loc, kv_loc1]).to(self.device, non_blocking=True)
+
+
+class MLATokenToKVPool:
+    """Per-layer MLA KV pool in the ``per_token_head`` layout (mem_cache/memory_pool.py:635-649): for every layer a
+    tuple (k_lora uint8/e4m3 [size+page, 1, 512], k_scale f32 [size+page, 1, 1], k_rope bf16 [size+page, 1, 64]) --
+    644 bytes per token per layer; page 0 absorbs padded writes."""
+
+    def __init__(self, size: int, model_dtype: torch.dtype, kv_lora_rank: int, qk_rope_head_dim: int, layer_num: int,
+                 device, page_size: int = PAGE_SIZE):
+        assert model_dtype == torch.bfloat16 and kv_lora_rank == 512 and qk_rope_head_dim == 64
+        self.size, self.page_size, self.device = size, page_size, device
+        self.kv_lora_rank, self.qk_rope_head_dim, self.model_dtype = kv_lora_rank, qk_rope_head_dim, model_dtype
+        self.quant_method = "per_token_head"
+        self.dtype = torch.float8_e4m3fn
+        self.store_dtype = torch.uint8
+        n = size + page_size
+        self.kv_buffer = [(torch.zeros((n, 1, kv_lora_rank), dtype=torch.uint8, device=device),
+                           torch.zeros((n, 1, 1), dtype=torch.float32, device=device),
+                           torch.zeros((n, 1, qk_rope_head_dim), dtype=model_dtype, device=device))
+                          for _ in range(layer_num)]
+
+    def get_key_buffer(self, layer_id: int):
+        return self.kv_buffer[layer_id]  # memory_pool.py:810-811
+
+    def get_value_buffer(self, layer_id: int):
+        return self.kv_buffer[layer_id][:2]  # memory_pool.py:844-845
+
+    def set_kv_buffer(self, layer, loc: torch.Tensor, cache_k: torch.Tensor, cache_v=None):
+        """memory_pool.py:854-871 (sm90 branch): quantise + scatter in one kernel."""
+        k_lora, k_scale, k_rope = self.kv_buffer[layer.layer_id]
+        flash_mla_fp8.quantize_and_cache_k(key=cache_k.contiguous(), k_lora_cache=k_lora, k_lora_scale_cache=k_scale,
+                                           k_rope_cache=k_rope, indices=loc.to(torch.int32),
+                                           head_dim_v=self.kv_lora_rank)
+
+    def get_key_split_contiguous(self, layer_id: int, indices: torch.Tensor):
+        """memory_pool.py:817-824."""
+        k_lora, k_scale, k_rope = self.kv_buffer[layer_id]
+        return flash_mla_fp8.dequantize_ckv_fused_indexed(k_lora, k_rope, k_scale, indices.to(torch.int32))
+
+
+class FlashMLADecodeMetadata:
+    """flashmla_backend.py:32-46."""
+
+    def __init__(self, flashmla_metadata=None, num_splits=None, block_table=None):
+        self.flashmla_metadata = flashmla_metadata
+        self.num_splits = num_splits
+        self.block_table = block_table
+
+
+class FlashMLABackend(AttentionBackend):
+    """flashmla_backend.py:49-408.  Reads from ``model_runner``: model_config.{scaling, num_attention_heads,
+    kv_lora_rank, qk_nope_head_dim, qk_rope_head_dim, v_head_dim, context_len}, server_args.{speculative_algorithm,
+    speculative_num_draft_tokens}, kv_cache_dtype, kv_cache_quant_method, kv_allocator, dtype; the attention TP size
+    comes from ``attn_tp_size`` (reference: dp_attention.get_attention_tp_size())."""
+
+    def __init__(self, model_runner, skip_prefill: bool = False, kv_indptr_buf=None, q_indptr_decode_buf=None,
+                 multi_step_seqlen_incr: int = 0, attn_tp_size: int = 1):
+        cfg, sa = model_runner.model_config, model_runner.server_args
+        self.softmax_scale = cfg.scaling
+        self.draft_token_num = 0 if getattr(sa, "speculative_algorithm", None) is None else sa.speculative_num_draft_tokens
+        self.multi_step_seqlen_incr = multi_step_seqlen_incr
+        self.cache_dtype = model_runner.kv_cache_dtype
+        self.cache_quant_method = model_runner.kv_cache_quant_method
+        if self.cache_quant_method != "per_token_head":
+            raise RuntimeError("FlashMLABackend (B200): only --kv-cache-quant-method per_token_head is implemented; "
+                               "the reference's other FP8 branch is dead code (SURVEY.md 8a-2)")
+        self.num_q_heads = cfg.num_attention_heads // attn_tp_size
+        self.num_local_heads = self.num_q_heads
+        self.kv_allocator = model_runner.kv_allocator
+        self.forward_metadata: Optional[FlashMLADecodeMetadata] = None
+        self.kv_lora_rank = cfg.kv_lora_rank
+        self.qk_nope_head_dim = cfg.qk_nope_head_dim
+        self.qk_rope_head_dim = cfg.qk_rope_head_dim
+        self.v_head_dim = cfg.v_head_dim
+        self.scaling = cfg.scaling
+        self.q_data_type = model_runner.dtype
+        self.kv_cache_dim = self.kv_lora_rank + self.qk_rope_head_dim
+        self.max_context_len = cfg.context_len
+        self.device = getattr(model_runner, "device", "cuda")
+
+    def get_flash_mla_module(self, M):
+        """flashmla_backend.py:18-22,84-85.  One module on B200: the kernel is SwapAB *and* FP8 for every M."""
+        return flash_mla_fp8
+
+    # ------------------------------------------------------------------ attention calls
+    def _attend(self, q, layer, forward_batch, cache_seqlens):
+        bs = forward_batch.batch_size
+        k_cache = forward_batch.token_to_kv_pool.get_key_buffer(layer.layer_id)
+        assert layer.tp_q_head_num == self.num_q_heads, f"{layer.tp_q_head_num=} != {self.num_q_heads=}"
+        reshape_q = q.view(bs, -1, self.num_q_heads, layer.head_dim)
+        mod = self.get_flash_mla_module(reshape_q.shape[1] * reshape_q.shape[2])
+        q_nope, q_scale, q_rope = mod.quantize_ckv_per_token_head(reshape_q.contiguous(), self.kv_lora_rank)
+        k_cache_lora, k_scale, k_cache_rope = k_cache
+        o, _ = mod.flash_mla_ckv_fp8_per_token(
+            q_nope=q_nope, q_rope=q_rope,
+            k_cache_lora=k_cache_lora.view(-1, PAGE_SIZE, 1, self.kv_lora_rank),
+            k_cache_rope=k_cache_rope.view(-1, PAGE_SIZE, 1, self.qk_rope_head_dim),
+            q_scale=q_scale, k_scale=k_scale.view(-1, PAGE_SIZE, 1, 1),
+            block_table=self.forward_metadata.block_table[:bs],
+            cache_seqlens=cache_seqlens.to(torch.int32),
+            head_dim_v=self.kv_lora_rank,
+            tile_scheduler_metadata=self.forward_metadata.flashmla_metadata,
+            num_splits=self.forward_metadata.num_splits,
+            softmax_scale=layer.scaling, causal=True)
+        return o.view(-1, layer.tp_q_head_num * layer.v_head_dim)
+
+    def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache=True, **kwargs):
+        """flashmla_backend.py:178-256: write the new token's K (quantised) first, then attend over seq_lens."""
+        if k is not None:
+            assert v is not None
+            if save_kv_cache:
+                forward_batch.token_to_kv_pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+        return self._attend(q, layer, forward_batch, forward_batch.seq_lens + self.multi_step_seqlen_incr)
+
+    def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache=True, q_pe=None, k_pe=None, **kwargs):
+        """flashmla_backend.py:87-176: TARGET_VERIFY / DRAFT_EXTEND run the decode kernel with s_q = draft tokens."""
+        mode = forward_batch.forward_mode
+        if not (mode.is_target_verify() or mode.is_draft_extend()):
+            raise NotImplementedError("prefill (EXTEND) is outside the B200 decode hot path; the reference routes it to "
+                                      "FlashInferMLAAttnBackend (flashmla_backend.py:100-104)")
+        if k is not None:
+            assert v is not None
+            if save_kv_cache:
+                forward_batch.token_to_kv_pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
+        return self._attend(q, layer, forward_batch, forward_batch.seq_lens + self.draft_token_num)
+
+    # ------------------------------------------------------------------ metadata
+    def _metadata(self, seq_lens, forward_mode):
+        if forward_mode.is_decode_or_idle():
+            lens, m = seq_lens + self.multi_step_seqlen_incr, self.num_q_heads
+        elif forward_mode.is_target_verify() or forward_mode.is_draft_extend():
+            lens, m = seq_lens + self.draft_token_num, self.draft_token_num * self.num_q_heads
+        else:
+            raise RuntimeError(f"Not supported forward mode: {forward_mode}")
+        return self.get_flash_mla_module(m).get_mla_metadata(lens.to(torch.int32).contiguous(), m, 1)
+
+    def init_forward_metadata(self, forward_batch):
+        """flashmla_backend.py:258-290."""
+        block_table = self.kv_allocator.req_to_page[forward_batch.req_pool_indices]
+        mla_metadata, num_splits = self._metadata(forward_batch.seq_lens, forward_batch.forward_mode)
+        self.forward_metadata = FlashMLADecodeMetadata(mla_metadata, num_splits, block_table)
+
+    def init_cuda_graph_state(self, max_bs: int, block_kv_indices: Optional[torch.Tensor] = None):
+        """flashmla_backend.py:292-326: static block table filled with page 1 (4 pages reserved for speculation) and
+        static metadata sized for seq_len == 1 per padded row."""
+        if block_kv_indices is None:
+            max_context_len = self.max_context_len + PAGE_SIZE - 1
+            block_kv_indices = torch.full((max_bs, (max_context_len + 4 * PAGE_SIZE) // PAGE_SIZE), 1,
+                                          dtype=torch.int32, device=self.device)
+        m = (self.draft_token_num or 1) * self.num_q_heads
+        ones = torch.ones(max_bs, dtype=torch.int32, device=block_kv_indices.device)
+        self.cuda_graph_mla_metadata, self.cuda_graph_num_splits = self.get_flash_mla_module(m).get_mla_metadata(ones, m, 1)
+        self.cuda_graph_kv_indices = block_kv_indices
+
+    def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens, forward_mode,
+                                                 spec_info=None):
+        """flashmla_backend.py:328-364."""
+        block_table = self.kv_allocator.req_to_page[req_pool_indices]
+        mla_metadata, num_splits = self._metadata(seq_lens, forward_mode)
+        self.cuda_graph_mla_metadata.copy_(mla_metadata)
+        self.cuda_graph_num_splits[: bs + 1].copy_(num_splits)
+        self.cuda_graph_kv_indices[:bs, : block_table.shape[1]].copy_(block_table)
+        self.forward_metadata = FlashMLADecodeMetadata(self.cuda_graph_mla_metadata,
+                                                       self.cuda_graph_num_splits[: bs + 1],
+                                                       self.cuda_graph_kv_indices[:bs, :])
+
+    def init_forward_metadata_replay_cuda_graph(self, bs, req_pool_indices, seq_lens, seq_lens_sum, forward_mode,
+                                                spec_info=None, seq_lens_cpu=None):
+        """flashmla_backend.py:366-405: runs outside the graph; refreshes the static tensors in place."""
+        req_pool_indices = req_pool_indices[:bs]
+        block_table = self.kv_allocator.req_to_page[req_pool_indices]
+        mla_metadata, num_splits = self._metadata(seq_lens[:bs], forward_mode)
+        self.cuda_graph_mla_metadata.copy_(mla_metadata)
+        self.cuda_graph_num_splits[: bs + 1].copy_(num_splits)
+        self.cuda_graph_kv_indices[:bs, : block_table.shape[1]].copy_(block_table)
+        self.forward_metadata.flashmla_metadata = self.cuda_graph_mla_metadata
+        self.forward_metadata.num_splits = self.cuda_graph_num_splits[: bs + 1]
+        self.forward_metadata.block_table = self.cuda_graph_kv_indices[:bs]
+
+    def get_cuda_graph_seq_len_fill_value(self):
+        return 1  # flashmla_backend.py:407-408
+
+
+class FlashMLAMultiStepDecodeBackend:
+    """flashmla_backend.py:411-477: one FlashMLABackend per speculative draft step, step i attending over
+    seq_lens + i."""
+
+    def __init__(self, model_runner, topk: int, speculative_num_steps: int, attn_tp_size: int = 1):
+        if topk > 1:
+            raise ValueError("Currently FlashMLA only supports topk=1 for speculative decoding")
+        self.topk, self.speculative_num_steps = topk, speculative_num_steps
+        self.attn_backends = [FlashMLABackend(model_runner, skip_prefill=True, multi_step_seqlen_incr=i,
+                                              attn_tp_size=attn_tp_size) for i in range(speculative_num_steps)]
+
+    def init_forward_metadata(self, forward_batch):
+        for b in self.attn_backends[: self.speculative_num_steps - 1]:
+            b.init_forward_metadata(forward_batch)
+
+    def init_cuda_graph_state(self, max_bs: int):
+        for b in self.attn_backends:
+            b.init_cuda_graph_state(max_bs, block_kv_indices=None)
+
+    def init_forward_metadata_capture_cuda_graph(self, forward_batch):
+        for b in self.attn_backends[: self.speculative_num_steps]:
+            b.init_forward_metadata_capture_cuda_graph(forward_batch.batch_size, forward_batch.batch_size,
+                                                       forward_batch.req_pool_indices, forward_batch.seq_lens,
+                                                       ForwardMode.DECODE, forward_batch.spec_info)
+
+    def init_forward_metadata_replay_cuda_graph(self, forward_batch, bs):
+        for b in self.attn_backends[: self.speculative_num_steps]:
+            b.init_forward_metadata_replay_cuda_graph(bs, forward_batch.req_pool_indices, forward_batch.seq_lens,
+                                                      getattr(forward_batch, "seq_lens_sum", 0), ForwardMode.DECODE,
+                                                      forward_batch.spec_info, seq_lens_cpu=None)

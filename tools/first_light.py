@@ -131,7 +131,23 @@ def mla():
 
 for st in stages:
     try:
+        if st == "rate":
+            continue
         {"lab": lab, "small": small, "gemm": gemm, "mla": mla}[st]()
     except Exception:
         traceback.print_exc()
         print("STAGE %s FAILED" % st, flush=True)
+
+
+def rate():
+    L = _lib.lib()
+    names = {8: "fp8 K/K divergent issue", 0: "fp8 K/K", 1: "bf16 K/K", 2: "fp8 A-MN/B-MN(none)", 3: "fp8 A-MN/B-K", 4: "fp8 A-K/B-MN(none)"}
+    for variant in (0, 1, 2, 3, 4, 8):
+        for n in (16, 32, 64, 128, 256):
+            c = ctypes.c_float(-1)
+            rc = L.b200_umma_rate(variant, n, 2048, ctypes.byref(c))
+            print("rate %-22s n=%3d: %7.1f cycles/MMA %s" % (names[variant], n, c.value, "" if rc == 0 else L.b200_last_error().decode()), flush=True)
+
+
+if "rate" in stages:
+    rate()
