@@ -121,6 +121,9 @@ int b200_umma_selftest(int variant, int n, float* rel_err);
 /* Issue-rate probe for the same operand layouts: average SM cycles per tcgen05.mma (M=128, N=n, K=32 B). */
 int b200_umma_rate(int variant, int n, int iters, float* cycles_per_mma);
 
+/* CTA-pair (cta_group::2) lab: raw TMEM dump [2][128][256] of one M=128 MMA chain; host pointers (diagnostic). */
+int b200_umma_pair_lab(int b_mode, int n, const void* a, const void* b, float* out);
+
 #ifdef __cplusplus
 }
 #endif

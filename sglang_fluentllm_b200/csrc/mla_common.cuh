@@ -1,0 +1,74 @@
+// Shared between the two MLA decode kernels (mla_decode.cu: SwapAB single-CTA, M <= 64 q rows; mla_decode_pair.cu:
+// CTA-pair cta_group::2, 64 < M): launch parameters and the split-KV work partition
+// (reference: ckv_fp8_per_token/splitkv_mla.cu:1218-1269, params.h).
+#pragma once
+#include <cuda_bf16.h>
+#include <math.h>
+
+#include "b200_decode.h"
+#include "host_utils.h"
+#include "ptx.cuh"
+
+namespace b200 {
+
+static constexpr int kTileTokens = 128;
+static constexpr int kPage = B200_MLA_PAGE_SIZE;
+static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
+static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
+static constexpr float kHeadroom = 8.0f;                      // lazy rescale: new reference leaves 2^3 of growth
+
+struct MlaParams {
+  CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;
+  const float* q_scale;
+  const float* k_scale;
+  const int32_t* block_table;
+  int64_t block_table_stride;
+  const int32_t* seqlens;
+  const int32_t* meta;
+  const int32_t* num_splits;
+  __nv_bfloat16* out;
+  float* lse;
+  float* o_accum;
+  float* lse_accum;
+  int batch, s_q, h_q, M;
+  float scale_log2;
+  int is_causal;
+};
+
+// The work of one (sm part, request) pair.
+struct Segment {
+  int batch_idx, seqlen, start_block, end_block, n_tiles, valid_end, split_idx;
+  bool no_split;
+};
+
+__device__ __forceinline__ int mask_len(int s_q, int h_q, int M, int row) {  // splitkv_mla.cu:1136-1145
+  return row < M ? s_q - row / h_q - 1 : 0;
+}
+
+__device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_idx, int begin_idx, int begin_seqlen,
+                                                int end_idx, int end_seqlen, int begin_n_split, int q_row0, int hb) {
+  Segment s;
+  s.batch_idx = batch_idx;
+  s.seqlen = __ldg(p.seqlens + batch_idx);
+  s.start_block = batch_idx == begin_idx ? begin_seqlen / kPage : 0;
+  const int full_blocks = (s.seqlen + kPage - 1) / kPage;
+  int end_block = batch_idx == end_idx ? (end_seqlen + kPage - 1) / kPage : full_blocks;
+  s.no_split = (s.start_block == 0 && end_block == full_blocks);  // splitkv_mla.cu:1239
+  if (p.is_causal) {                                              // splitkv_mla.cu:1242-1266
+    const int last_row = min(q_row0 + hb, p.M) - 1;
+    int lim = s.seqlen - mask_len(p.s_q, p.h_q, p.M, last_row);
+    if (batch_idx == end_idx) lim = min(lim, end_seqlen);
+    end_block = (max(lim, 0) + kPage - 1) / kPage;
+  }
+  s.end_block = max(end_block, s.start_block);
+  s.n_tiles = (s.end_block - s.start_block + 1) / 2;
+  s.valid_end = min(s.seqlen, s.end_block * kPage);
+  const int n_split_idx = batch_idx == begin_idx ? begin_n_split : 0;
+  s.split_idx = __ldg(p.num_splits + batch_idx) + n_split_idx;  // splitkv_mla.cu:1490
+  return s;
+}
+
+// CTA-pair kernel for 64 < M (mla_decode_pair.cu); the Q tensor maps must use 64-row boxes.
+int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream);
+
+}  // namespace b200

@@ -25,45 +25,19 @@
 //   O in TMEM -- when a tile's P would overflow e4m3 under the current reference ("lazy rescale").  The reference
 //   kernel re-derives p_scale = rowmax(P)/448 for every 64-token page and rescales O each time (splitkv_mla.cu:
 //   420-455); here the row sum L is kept per token-lane in registers and reduced once per request.
-#include <cuda_bf16.h>
-#include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
-#include "b200_decode.h"
-#include "host_utils.h"
-#include "ptx.cuh"
+#include "mla_common.cuh"
 
 namespace b200 {
 
-static constexpr int kTileTokens = 128;
-static constexpr int kPage = B200_MLA_PAGE_SIZE;
 static constexpr int kStages = 2;
 static constexpr int kNopeChunkBytes = kTileTokens * 128;     // one 128-byte k-chunk of a tile: 16 KB
 static constexpr int kStageNopeBytes = 4 * kNopeChunkBytes;   // 64 KB
 static constexpr int kStageRopeBytes = kTileTokens * 128;     // 16 KB
 static constexpr int kStageBytes = kStageNopeBytes + kStageRopeBytes;
 static constexpr int kPageTxBytes = kPage * 512 + kPage * 128;
-static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
-static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
-static constexpr float kHeadroom = 8.0f;                      // lazy rescale: new reference leaves 2^3 of growth
-
-struct MlaParams {
-  CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;
-  const float* q_scale;
-  const float* k_scale;
-  const int32_t* block_table;
-  int64_t block_table_stride;
-  const int32_t* seqlens;
-  const int32_t* meta;
-  const int32_t* num_splits;
-  __nv_bfloat16* out;
-  float* lse;
-  float* o_accum;
-  float* lse_accum;
-  int batch, s_q, h_q, M;
-  float scale_log2;
-  int is_causal;
-};
 
 template <int HB>
 struct SmemLayout {
@@ -93,39 +67,6 @@ struct SmallSmem {
   float red[4][64];
 };
 static_assert(sizeof(SmallSmem) <= 4096, "SmallSmem too large");
-
-// The work of one (sm part, request) pair.
-struct Segment {
-  int batch_idx, seqlen, start_block, end_block, n_tiles, valid_end, split_idx;
-  bool no_split;
-};
-
-__device__ __forceinline__ int mask_len(int s_q, int h_q, int M, int row) {  // splitkv_mla.cu:1136-1145
-  return row < M ? s_q - row / h_q - 1 : 0;
-}
-
-__device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_idx, int begin_idx, int begin_seqlen,
-                                                int end_idx, int end_seqlen, int begin_n_split, int q_row0, int hb) {
-  Segment s;
-  s.batch_idx = batch_idx;
-  s.seqlen = __ldg(p.seqlens + batch_idx);
-  s.start_block = batch_idx == begin_idx ? begin_seqlen / kPage : 0;
-  const int full_blocks = (s.seqlen + kPage - 1) / kPage;
-  int end_block = batch_idx == end_idx ? (end_seqlen + kPage - 1) / kPage : full_blocks;
-  s.no_split = (s.start_block == 0 && end_block == full_blocks);  // splitkv_mla.cu:1239
-  if (p.is_causal) {                                              // splitkv_mla.cu:1242-1266
-    const int last_row = min(q_row0 + hb, p.M) - 1;
-    int lim = s.seqlen - mask_len(p.s_q, p.h_q, p.M, last_row);
-    if (batch_idx == end_idx) lim = min(lim, end_seqlen);
-    end_block = (max(lim, 0) + kPage - 1) / kPage;
-  }
-  s.end_block = max(end_block, s.start_block);
-  s.n_tiles = (s.end_block - s.start_block + 1) / 2;
-  s.valid_end = min(s.seqlen, s.end_block * kPage);
-  const int n_split_idx = batch_idx == begin_idx ? begin_n_split : 0;
-  s.split_idx = __ldg(p.num_splits + batch_idx) + n_split_idx;  // splitkv_mla.cu:1490
-  return s;
-}
 
 // HB  = q rows per CTA (UMMA N); CPT = S columns (q rows) each softmax thread owns.
 // The softmax group has 4 * HB/CPT warps: 4 TMEM lane quadrants x HB/CPT column slices, so the per-thread work per
@@ -643,7 +584,9 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.is_causal = is_causal;
 
   int rc;
-  if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
+  if (M > 64 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
+  else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 32) rc = launch_mla<32, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else rc = launch_mla<64, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;

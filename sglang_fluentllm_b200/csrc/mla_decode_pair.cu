@@ -1,0 +1,530 @@
+// Paged MLA decode attention over the per-token-FP8 KV pool for 64 < M = h_q * s_q: CTA-pair kernel (cluster of two
+// CTAs on one TPC, tcgen05 cta_group::2).
+//
+// Replaces ckv_fp8_per_token::flash_fwd_splitkv_mla_kernel of the reference for the shapes where it runs two 64-row
+// q blocks per request (3rdparty/flashmla-fp8/csrc/kernels/ckv_fp8_per_token/splitkv_mla.cu:1147-1515; the two
+// warpgroup "seesaw" of docs/20250422-new-kernel-deep-dive.md:27-50).  Same split-KV metadata, same arithmetic contract
+// as mla_decode.cu; the machine mapping is the non-swapped one:
+//
+//   A pair owns 128 q rows of one request (CTA r: rows 64r..64r+63) and walks its KV in 128-token tiles (2 pages).
+//       S[128 q, 128 tok]   = Qn[128, 512] . Kn^T   (16 x kind::f8f6f4, M=128 N=128)  + Qr[128, 64] . Kr^T (4 x kind::f16)
+//       O[128 q, 512 d]    += P[128 q, 128 tok] . V  ( 2 d-halves x 4 x kind::f8f6f4, M=128 N=256, V MN-major)
+//   cta_group::2 splits M across the pair (each CTA keeps its 64 rows of S and O in its own TMEM, as 128 lanes x N/2
+//   columns: lanes 0-63 hold the first half of the N columns, lanes 64-127 the second half -- measured with
+//   b200_umma_pair_lab) and splits the B operand's N between the two shared memories: for Q.K^T each CTA stages ONE
+//   page (64 tokens x 576 dims), for P.V each CTA stages 128 of every 256 output dims for all 128 tokens.  Per SM that
+//   is 72 KB of shared-memory fill per 128 tokens x 128 q rows instead of 160 KB for two independent 64-row CTAs, and
+//   every MMA reads at most 6 KB of operands per 64 tensor-core cycles, which is what lets the tensor pipe run near
+//   its issue rate (single-CTA SS MMAs at N <= 128 are operand-bandwidth bound, see b200_umma_rate).
+//
+//   Softmax threads own (q row, 32 token columns): the row maximum and sum are thread-local up to a 4-way exchange,
+//   q_scale is a register, k_scale a shared-memory broadcast.  Same lazy (m_ref, p_scale) reference as mla_decode.cu.
+//
+//   Warp roles per CTA (384 threads): warp 0 = TMA producer (K page -> leader barrier via cta_group::2 TMA, V halves +
+//   k scales -> local barrier), warp 1 = UMMA issuer (leader CTA only) + TMEM allocation, warps 4-11 = softmax /
+//   correction / epilogue (4 TMEM lane quadrants x 2 column halves).
+//   TMEM per CTA: S double-buffered (2 x 64 columns) + O (2 x 128 columns).
+#include <string.h>
+
+#include "mla_common.cuh"
+
+namespace b200 {
+namespace pairk {
+
+constexpr int kKStages = 2, kVStages = 2;
+constexpr int kQBytes = 64 * 640;          // 4 nope chunks [64 rows x 128 B] + rope [64 x 128 B]
+constexpr int kKStageBytes = 64 * 640;     // this CTA's page of the tile, same layout
+constexpr int kVStageBytes = 2 * 128 * 128;  // [2 d-halves][128 tokens][128 B]
+constexpr int kPBytes = 64 * 128;          // [64 q rows][128 tokens] e4m3, K-major SW128
+constexpr int kOffQ = 0;
+constexpr int kOffK = kOffQ + kQBytes;
+constexpr int kOffV = kOffK + kKStages * kKStageBytes;
+constexpr int kOffP = kOffV + kVStages * kVStageBytes;
+constexpr int kOffKs = kOffP + 2 * kPBytes;          // k scales of the tile: [kVStages][128] f32
+constexpr int kOffSmall = kOffKs + kVStages * 512;
+constexpr int kTotal = kOffSmall + 4096;
+constexpr int kSmThreads = 256;                      // softmax group
+constexpr uint32_t kColS = 0, kColO = 128, kTmemCols = 512;
+static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffKs % 1024 == 0, "swizzle alignment");
+
+struct Small {
+  uint64_t k_full[kKStages], k_empty[kKStages];
+  uint64_t v_land[kVStages], v_empty[kVStages];
+  uint64_t q_full, q_empty;
+  uint64_t s_full[2], p_full[2], p_free[2];
+  uint64_t pv_done, o_free;
+  uint32_t tmem_base;
+  uint32_t trig[3];
+  float red1[4][64], red2[4][64];
+  float lsum[64];
+};
+static_assert(sizeof(Small) <= 4096, "Small too large");
+
+struct PendingPv {
+  uint32_t g, seg, nk;
+  bool first, valid;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+    mla_decode_pair_kernel(const __grid_constant__ MlaParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_q = smem + kOffQ;
+  uint8_t* s_k = smem + kOffK;
+  uint8_t* s_v = smem + kOffV;
+  uint8_t* s_p = smem + kOffP;
+  float* s_ks = reinterpret_cast<float*>(smem + kOffKs);
+  Small& sm = *reinterpret_cast<Small*>(smem + kOffSmall);
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t rank = cluster_ctarank();
+  const int part = blockIdx.z;
+  const int pair_row0 = blockIdx.y * 128;
+  const int q_row0 = pair_row0 + 64 * (int)rank;
+  const int n_valid_q = max(0, min(64, p.M - q_row0));
+
+  const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
+  const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
+            end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
+  if (begin_idx >= p.batch) return;  // splitkv_mla.cu:1226 (both CTAs of the pair take the same exit)
+
+  if (tid == 0) {
+    for (int i = 0; i < kKStages; ++i) {
+      mbar_init(&sm.k_full[i], 2);  // one expect_tx arrival per CTA of the pair (leader's copy is the live one)
+      mbar_init(&sm.k_empty[i], 1);
+    }
+    for (int i = 0; i < kVStages; ++i) {
+      mbar_init(&sm.v_land[i], 1);
+      mbar_init(&sm.v_empty[i], 1);
+    }
+    mbar_init(&sm.q_full, 2);
+    mbar_init(&sm.q_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.p_full[i], 16);  // 8 softmax warps x 2 CTAs
+      mbar_init(&sm.p_free[i], 1);
+    }
+    mbar_init(&sm.pv_done, 1);
+    mbar_init(&sm.o_free, 16);
+    sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
+    fence_mbar_init();
+    tma_prefetch_desc(&p.tm_q_nope);
+    tma_prefetch_desc(&p.tm_q_rope);
+    tma_prefetch_desc(&p.tm_k_nope);
+    tma_prefetch_desc(&p.tm_k_rope);
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_pair(&sm.tmem_base, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // the peer's barriers are initialised before anything is credited to them
+  tc_fence_after();
+  const uint32_t tmem = sm.tmem_base;
+
+  if (warp == 0) {
+    // ============================== TMA producer (both CTAs) ==============================
+    const uint64_t pol_last_use = policy_evict_first();
+    const uint32_t q_full_l = mapa_u32(smem_u32(&sm.q_full), 0);
+    uint32_t k_full_l[kKStages];
+#pragma unroll
+    for (int i = 0; i < kKStages; ++i) k_full_l[i] = mapa_u32(smem_u32(&sm.k_full[i]), 0);
+
+    uint32_t g = 0, seg_i = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      if (sg.n_tiles == 0) continue;
+      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+
+      // this CTA's page of tile t -> K stage (credits the leader's barrier)
+      auto load_k = [&](int t, uint32_t gt) {
+        const uint32_t st = gt % kKStages;
+        mbar_wait(&sm.k_empty[st], ((gt / kKStages) & 1) ^ 1);
+        const int blk = sg.start_block + 2 * t + (int)rank;
+        const bool exists = blk < sg.end_block;
+        const int tok0 = exists ? __ldg(bt + blk) * kPage : 0;
+        const int blk_pf = blk + 2 * kKStages;
+        const int tok_pf = blk_pf < sg.end_block ? __ldg(bt + blk_pf) * kPage : -1;
+        uint8_t* stage = s_k + st * kKStageBytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx_cluster(k_full_l[st], exists ? (uint32_t)kKStageBytes : 0u);
+          if (exists) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_load_2d_pair(stage + c * 8192, &p.tm_k_nope, k_full_l[st], c * 128, tok0);
+            tma_load_2d_pair(stage + 32768, &p.tm_k_rope, k_full_l[st], 0, tok0);
+          }
+          if (tok_pf >= 0) {  // warm L2 for the page that will reuse this stage
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tok_pf);
+            tma_prefetch_2d(&p.tm_k_rope, 0, tok_pf);
+          }
+        }
+        __syncwarp();
+      };
+      // both pages of tile t, this CTA's two 128-dim output slices (+ the tile's k scales) -> V stage (local barrier);
+      // these bytes were just streamed through L2 as K by this CTA or its peer
+      auto load_v = [&](int t, uint32_t gt) {
+        const uint32_t st = gt % kVStages;
+        mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
+        const int blk0 = sg.start_block + 2 * t;
+        const int npages = min(2, sg.end_block - blk0);
+        const int tok0 = __ldg(bt + blk0) * kPage;
+        const int tok1 = npages > 1 ? __ldg(bt + blk0 + 1) * kPage : 0;
+        uint8_t* stage = s_v + st * kVStageBytes;
+        float* ks_dst = s_ks + st * 128;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192 + 256));
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d_hint(stage + j * 16384, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
+          bulk_load_1d(ks_dst, p.k_scale + tok0, 256, &sm.v_land[st]);
+          if (npages > 1) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_hint(stage + j * 16384 + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1,
+                               pol_last_use);
+            bulk_load_1d(ks_dst + 64, p.k_scale + tok1, 256, &sm.v_land[st]);
+          }
+        }
+        __syncwarp();
+      };
+
+      // Q rows of this CTA (rows past the request are masked by the consumers)
+      mbar_wait(&sm.q_empty, (seg_i & 1) ^ 1);
+      ++seg_i;
+      const int qrow = b * p.M + q_row0;
+      if (elect_one()) {
+        mbar_arrive_expect_tx_cluster(q_full_l, kQBytes);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) tma_load_2d_pair(s_q + c * 8192, &p.tm_q_nope, q_full_l, c * 128, qrow);
+        tma_load_2d_pair(s_q + 32768, &p.tm_q_rope, q_full_l, 0, qrow);
+      }
+      __syncwarp();
+      load_k(0, g);
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        if (t + 1 < sg.n_tiles) load_k(t + 1, g + 1);
+        load_v(t, g);
+      }
+    }
+  } else if (warp == 1) {
+    if (rank == 0) {
+      // ============================== UMMA issuer (leader CTA) ==============================
+      constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
+      constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
+      constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
+      const uint32_t q_addr = smem_u32(s_q), k_addr = smem_u32(s_k), v_addr = smem_u32(s_v), p_addr = smem_u32(s_p);
+      const uint64_t d_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);       // K-major, 128-B swizzle
+      const uint64_t d_vmn = make_smem_desc(0, 16384, 1024, SWZ_128B);    // V: MN-major view of the token rows
+      auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
+
+      auto issue_pv = [&](const PendingPv& pv) {
+        const uint32_t buf = pv.g & 1, vst = pv.g % kVStages;
+        mbar_wait_cluster(&sm.p_full[buf], (pv.g >> 1) & 1);  // P written and V landed in both CTAs
+        if (pv.first && pv.seg > 0) mbar_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
+        tc_fence_after();
+        if (elect_one()) {
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              if (s < (int)pv.nk)
+                umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
+                             with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
+                             !(pv.first && s == 0));
+          umma_commit_pair(&sm.v_empty[vst], 3);
+          umma_commit_pair(&sm.p_free[buf], 3);
+          umma_commit_pair(&sm.pv_done, 3);
+        }
+        __syncwarp();
+      };
+
+      uint32_t g = 0, seg = 0;
+      PendingPv pend;
+      pend.valid = false;
+      for (int b = begin_idx; b <= end_idx; ++b) {
+        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+        if (sg.n_tiles == 0) continue;
+        mbar_wait_cluster(&sm.q_full, seg & 1);
+        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+          const uint32_t kst = g % kKStages, buf = g & 1;
+          mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
+          tc_fence_after();
+          const uint32_t stage = k_addr + kst * kKStageBytes;
+          const uint32_t d = tmem + kColS + buf * 64;
+          if (elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                umma_f8_pair(d, with_addr(d_kmaj, q_addr + c * 8192 + s * 32), with_addr(d_kmaj, stage + c * 8192 + s * 32),
+                             idesc_qk8, (c | s) != 0);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_f16_pair(d, with_addr(d_kmaj, q_addr + 32768 + s * 32), with_addr(d_kmaj, stage + 32768 + s * 32),
+                            idesc_qk16, 1);
+            umma_commit_pair(&sm.s_full[buf], 3);
+            umma_commit_pair(&sm.k_empty[kst], 3);
+            if (t == sg.n_tiles - 1) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
+          }
+          __syncwarp();
+          // P.V of the previous tile goes behind this tile's Q.K^T: the softmax of tile g overlaps it
+          if (pend.valid) issue_pv(pend);
+          const int tile_start = (sg.start_block + 2 * t) * kPage;
+          pend.g = g;
+          pend.seg = seg;
+          pend.first = (t == 0);
+          pend.nk = (uint32_t)((min(kTileTokens, sg.valid_end - tile_start) + 31) / 32);
+          pend.valid = true;
+        }
+        ++seg;
+      }
+      if (pend.valid) issue_pv(pend);
+    }
+  } else if (warp >= 4) {
+    // ============================== softmax / correction / epilogue (both CTAs) ==============================
+    const int st_id = tid - 128;              // 0 .. 255 within the softmax group
+    const int quad = warp & 3;                // TMEM lane quadrant of this warp
+    const int ch = (warp - 4) >> 2;           // which 32 of the 64 S columns
+    const int tl = quad * 32 + lane;          // TMEM lane
+    const int row = tl & 63;                  // q row within this CTA
+    const int page = tl >> 6;                 // lanes 64-127 hold the second half of the N columns = the peer's page
+    const int col0 = ch * 32;
+    const int slot = page * 2 + ch;           // which quarter of the row this thread holds
+    const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
+    const uint32_t p_full_l[2] = {mapa_u32(smem_u32(&sm.p_full[0]), 0), mapa_u32(smem_u32(&sm.p_full[1]), 0)};
+    const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
+    const bool row_valid = row < n_valid_q;
+    const int grow = q_row0 + row;            // row within the request's M rows
+    uint32_t g = 0;
+
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      // ---- per-request state (identical in the four threads of a row) ----
+      const float f = row_valid ? __ldg(p.q_scale + (int64_t)b * p.M + grow) * p.scale_log2 : 0.f;
+      int lim = 0;
+      if (row_valid) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, grow), sg.end_block * kPage) : sg.valid_end;
+      float mref = kMInit, ps = 1.f, mprime = kMInit, lsum = 0.f;
+      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lsum are done
+      if (st_id < 64) sm.lsum[st_id] = 0.f;
+      named_bar_sync(1, kSmThreads);
+
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        const uint32_t buf = g & 1, vst = g % kVStages;
+        const int tile_start = (sg.start_block + 2 * t) * kPage;
+        const int tok_base = tile_start + page * 64 + col0;  // first token of this thread's 32 columns
+        const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
+        if (st_id == 0) sm.trig[(g + 1) % 3] = 0;
+
+        mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);  // k scales (and this CTA's V slices) have landed
+        float kf[32];                                     // k_scale, later f * k_scale
+        {
+          const float4* src = reinterpret_cast<const float4*>(s_ks + vst * 128 + page * 64 + col0);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 v4 = src[i];
+            kf[4 * i] = v4.x, kf[4 * i + 1] = v4.y, kf[4 * i + 2] = v4.z, kf[4 * i + 3] = v4.w;
+          }
+        }
+        if (need_mask) {
+#pragma unroll
+          for (int c = 0; c < 32; ++c)
+            if (!(tok_base + c < lim)) kf[c] = 0.f;
+        }
+        mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
+        tc_fence_after();
+        float x[32];
+        const uint32_t s_addr = tmem + kColS + buf * 64 + col0 + lane_addr;
+        tmem_ld<32>(s_addr, x);
+        tmem_wait_ld();
+
+        uint32_t pk[8];
+        bool trigger = (t == 0);
+        if (!trigger) {
+          // ---- fast path: reuse the current reference ----
+          float vmax = 0.f, acc = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float arg = fmaf(x[c], f * kf[c], -mprime);
+            if (need_mask && !(tok_base + c < lim)) arg = -INFINITY;
+            const float u = ex2_approx(arg);
+            acc += u;
+            x[c] = u * kf[c];
+            vmax = fmaxf(vmax, x[c]);
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+          const bool over = vmax > 448.f;
+          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[g % 3] = 1;
+          named_bar_sync(1, kSmThreads);
+          trigger = sm.trig[g % 3] != 0;
+          if (!trigger) lsum += acc;
+        }
+        if (trigger) {
+          // ---- slow path: move the reference (m_ref, p_scale), rescale O and L ----
+          if (t != 0) {
+            tmem_ld<32>(s_addr, x);
+            tmem_wait_ld();
+          }
+          float lmax = -INFINITY;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            float z = x[c] * (f * kf[c]);
+            if (!(tok_base + c < lim)) z = -INFINITY;
+            x[c] = z;
+            lmax = fmaxf(lmax, z);
+          }
+          sm.red1[slot][row] = lmax;
+          named_bar_sync(1, kSmThreads);
+          const float cm = fmaxf(fmaxf(sm.red1[0][row], sm.red1[1][row]), fmaxf(sm.red1[2][row], sm.red1[3][row]));
+          const float m_new = fmaxf(mref, cm);
+          float lp = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) lp = fmaxf(lp, ex2_approx(x[c] - m_new) * kf[c]);
+          sm.red2[slot][row] = lp;
+          named_bar_sync(1, kSmThreads);
+          float pmax = fmaxf(fmaxf(sm.red2[0][row], sm.red2[1][row]), fmaxf(sm.red2[2][row], sm.red2[3][row]));
+          pmax = fmaxf(pmax, kPMin);
+          const float ps_new = pmax * (kHeadroom / 448.f);
+          const float fac = exp2f(mref - m_new) * (ps / ps_new);
+          mref = m_new;
+          ps = ps_new;
+          mprime = m_new + log2f(ps_new);
+          if (t != 0) {
+            // every P.V up to the previous tile must have landed in O before it is rescaled
+            mbar_wait(&sm.pv_done, (g - 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int hh = 0; hh < 2; ++hh) {
+                float o[32];
+                const uint32_t a = tmem + kColO + j * 128 + ch * 64 + hh * 32 + lane_addr;
+                tmem_ld<32>(a, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 32; ++k) o[k] *= fac;
+                tmem_st<32>(a, o);
+              }
+            tmem_wait_st();
+            lsum *= fac;
+          }
+#pragma unroll
+          for (int c = 0; c < 32; ++c) {
+            const float u = ex2_approx(x[c] - mprime);
+            lsum += u;
+            x[c] = u * kf[c];
+          }
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+        }
+
+        // ---- publish P (A operand of P.V: [q row][token], K-major, 128-byte swizzle) ----
+        mbar_wait(&sm.p_free[buf], ((g >> 1) & 1) ^ 1);  // P.V of tile g-2 has retired
+        {
+          uint8_t* prow = s_p + buf * kPBytes + row * 128;
+          const int c16 = (page * 64 + col0) >> 4;  // first of this thread's two 16-byte chunks
+          *reinterpret_cast<uint4*>(prow + (((c16) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
+          *reinterpret_cast<uint4*>(prow + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
+        }
+        // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
+        // Reference: fill_oob_V, splitkv_mla.cu:698-721.
+        if (tile_start + kTileTokens > sg.valid_end && st_id < kTileTokens) {
+          const int valid_in_tile = sg.valid_end - tile_start;
+          const int nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
+          if (st_id >= valid_in_tile && st_id < nk * 32) {
+            uint8_t* stage = s_v + vst * kVStageBytes;
+#pragma unroll
+            for (int j = 0; j < 2; ++j) {
+              uint4* vr = reinterpret_cast<uint4*>(stage + j * 16384 + st_id * 128);
+#pragma unroll
+              for (int k = 0; k < 8; ++k) vr[k] = make_uint4(0, 0, 0, 0);
+            }
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(p_full_l[buf]);
+      }
+
+      // ---- epilogue of this request: O / L -> out (or split partials) ----
+      atomicAdd(&sm.lsum[row], lsum);
+      named_bar_sync(1, kSmThreads);
+      const float l = sm.lsum[row];
+      const bool bad = (l == 0.f || l != l);
+      const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
+      if (sg.n_tiles > 0) {
+        mbar_wait(&sm.pv_done, (g - 1) & 1);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int hh = 0; hh < 2; ++hh) {
+          float o[32];
+          if (sg.n_tiles > 0) {
+            tmem_ld<32>(tmem + kColO + j * 128 + ch * 64 + hh * 32 + lane_addr, o);
+            tmem_wait_ld();
+          } else {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) o[k] = 0.f;
+          }
+          const int d0 = 256 * j + 128 * page + ch * 64 + hh * 32;
+          if (row_valid) {
+            if (sg.no_split) {
+              uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)b * p.M + grow) * 512 + d0);
+#pragma unroll
+              for (int k = 0; k < 32; k += 8) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[k] * inv, o[k + 1] * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[k + 2] * inv, o[k + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[k + 4] * inv, o[k + 5] * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[k + 6] * inv, o[k + 7] * inv);
+                dst[k / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            } else {
+              float4* dst = reinterpret_cast<float4*>(p.o_accum + ((int64_t)sg.split_idx * p.M + grow) * 512 + d0);
+#pragma unroll
+              for (int k = 0; k < 32; k += 4)
+                dst[k / 4] = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+            }
+          }
+        }
+      if (row_valid && slot == 0) {
+        const float lse2 = log2f(l) + mprime;
+        if (sg.no_split) {
+          const int s = grow / p.h_q, h = grow % p.h_q;
+          p.lse[((int64_t)b * p.h_q + h) * p.s_q + s] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
+        } else {
+          p.lse_accum[(int64_t)sg.split_idx * p.M + grow] = bad ? -INFINITY : lse2;                    // :1506
+        }
+      }
+      if (sg.n_tiles > 0) {
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(o_free_l);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();  // no CTA frees TMEM or exits while its peer can still address its barriers / shared memory
+  if (warp == 1) tmem_dealloc_pair(tmem, kTmemCols);
+}
+
+}  // namespace pairk
+
+int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream) {
+  const int smem = pairk::kTotal + 1024;
+  static bool configured = false;
+  if (!configured) {
+    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    configured = true;
+  }
+  const int q_pairs = (prm.M + 127) / 128;
+  pairk::mla_decode_pair_kernel<<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace b200

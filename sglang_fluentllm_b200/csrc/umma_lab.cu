@@ -189,6 +189,96 @@ __global__ void __launch_bounds__(128, 1) umma_rate_kernel(int variant, int n, i
   if (warp == 1) tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair lab: one cta_group::2 MMA chain (M = 128 = 64 rows per CTA, N = n, K = 128 bytes) with operands staged by
+// cta_group::2 TMA loads that credit the leader's barrier, completion multicast to both CTAs, and a raw dump of each
+// CTA's TMEM (128 lanes x 256 columns).  The host side (tools/first_light.py pair) derives the D layout from the dump.
+//   b_mode 0: B K-major   SW128, global [n rows][128 B]; CTA r stages rows [r*n/2, (r+1)*n/2)          (Q.K^T form)
+//   b_mode 1: B MN-major  SW128, global [128 k rows][n B] (n = 256); CTA r stages bytes [128 r, 128 r + 128) of every
+//             row                                                                                        (P.V form)
+// ------------------------------------------------------------------------------------------------------------------
+struct PairLabParams {
+  CUtensorMap tm_a, tm_b;
+  float* out;  // [2][128][256]
+  int n, b_mode;
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_pair_lab_kernel(const __grid_constant__ PairLabParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* s_a = smem;          // 64 rows x 128 B = 8 KB
+  uint8_t* s_b = smem + 8192;   // <= 16 KB
+  __shared__ uint64_t bar_load, bar_mma;
+  __shared__ uint32_t tmem_base_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  if (tid == 0) {
+    mbar_init(&bar_load, 2);  // one expect_tx arrival per CTA
+    mbar_init(&bar_mma, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_pair(&tmem_base_slot, 256);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  {  // clear this CTA's TMEM window so untouched cells read back as a sentinel
+    float z[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) z[i] = -12345.f;
+    for (int c = 0; c < 256; c += 16) tmem_st<16>(tmem + ((uint32_t)(warp * 32) << 16) + c, z);
+    tmem_wait_st();
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+
+  const uint32_t leader_load = mapa_u32(smem_u32(&bar_load), 0);
+  if (warp == 0) {
+    if (elect_one()) {
+      const uint32_t b_bytes = p.b_mode == 0 ? (uint32_t)(p.n / 2) * 128u : 128u * 128u;
+      mbar_arrive_expect_tx_cluster(leader_load, 8192u + b_bytes);
+      tma_load_2d_pair(s_a, &p.tm_a, leader_load, 0, 64 * (int)rank);
+      if (p.b_mode == 0) tma_load_2d_pair(s_b, &p.tm_b, leader_load, 0, (p.n / 2) * (int)rank);
+      else tma_load_2d_pair(s_b, &p.tm_b, leader_load, 128 * (int)rank, 0);
+    }
+    __syncwarp();
+    if (rank == 0) {
+      mbar_wait_cluster(&bar_load, 0);
+      tc_fence_after();
+      const uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, p.b_mode == 1, 128, p.n);
+      const uint64_t da0 = make_smem_desc(0, 0, 1024, SWZ_128B);
+      const uint64_t db0 = p.b_mode == 1 ? make_smem_desc(0, 16384, 1024, SWZ_128B) : make_smem_desc(0, 0, 1024, SWZ_128B);
+      const uint32_t a = smem_u32(s_a), b = smem_u32(s_b);
+      if (elect_one()) {
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const uint32_t kb = p.b_mode == 1 ? k * 4096 : k * 32;
+          umma_f8_pair(tmem, da0 | (uint64_t)(((a + k * 32) >> 4) & 0x3FFF), db0 | (uint64_t)(((b + kb) >> 4) & 0x3FFF), idesc,
+                       k > 0);
+        }
+        umma_commit_pair(&bar_mma, 3);
+      }
+      __syncwarp();
+    }
+  }
+  mbar_wait_cluster(&bar_mma, 0);
+  tc_fence_after();
+  for (int c0 = 0; c0 < 256; c0 += 16) {
+    float v[16];
+    tmem_ld<16>(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    tmem_wait_ld();
+    for (int j = 0; j < 16; ++j) p.out[((size_t)rank * 128 + tid) * 256 + c0 + j] = v[j];
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem, 256);
+}
+
 static float e4m3_to_float(uint8_t c) {
   int s = c >> 7, e = (c >> 3) & 0xF, m = c & 7;
   float v;
@@ -335,4 +425,41 @@ extern "C" int b200_umma_rate(int variant, int n, int iters, float* cycles_per_m
   }
   *cycles_per_mma = (float)h / iters;
   return 0;
+}
+
+// CTA-pair lab (see umma_pair_lab_kernel).  a: host [128][128] e4m3 bytes; b: host, b_mode 0 -> [n][128], b_mode 1 ->
+// [128][n] (n must be 256); out: host float [2][128][256] raw TMEM dump of the two CTAs.
+extern "C" int b200_umma_pair_lab(int b_mode, int n, const void* a, const void* b, float* out) {
+  B200_CHECK(n % 32 == 0 && n >= 32 && n <= 256 && (b_mode == 0 || (b_mode == 1 && n == 256)), "pair_lab: bad arguments");
+  uint8_t *dA = nullptr, *dB = nullptr;
+  float* dOut = nullptr;
+  B200_CUDA(cudaMalloc(&dA, 128 * 128));
+  B200_CUDA(cudaMalloc(&dB, 256 * 128));
+  B200_CUDA(cudaMalloc(&dOut, sizeof(float) * 2 * 128 * 256));
+  cudaMemcpy(dA, a, 128 * 128, cudaMemcpyHostToDevice);
+  cudaMemcpy(dB, b, (size_t)n * 128, cudaMemcpyHostToDevice);
+  PairLabParams p;
+  memset(&p, 0, sizeof(p));
+  p.out = dOut;
+  p.n = n;
+  p.b_mode = b_mode;
+  int rc = make_tma_2d(&p.tm_a, dA, 1, 128, 128, 128, 128, 64, TmaSwizzle::B128);
+  if (b_mode == 0) rc |= make_tma_2d(&p.tm_b, dB, 1, 128, n, 128, 128, n / 2, TmaSwizzle::B128);
+  else rc |= make_tma_2d(&p.tm_b, dB, 1, 256, 128, 256, 128, 128, TmaSwizzle::B128);
+  if (rc == 0) {
+    const int smem_bytes = 1024 + 8192 + 16384;
+    cudaFuncSetAttribute(umma_pair_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+    umma_pair_lab_kernel<<<2, 128, smem_bytes>>>(p);
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+      set_last_error("pair_lab: kernel failed: %s", cudaGetErrorString(e));
+      rc = 2;
+    } else {
+      cudaMemcpy(out, dOut, sizeof(float) * 2 * 128 * 256, cudaMemcpyDeviceToHost);
+    }
+  }
+  cudaFree(dA);
+  cudaFree(dB);
+  cudaFree(dOut);
+  return rc;
 }

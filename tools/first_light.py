@@ -129,11 +129,24 @@ def mla():
     run_case("b128-s4096-h16", 128, 16, 1, [4096] * 128, faithful=False)
 
 
+def mla_pair():
+    """Shapes with M = h * s_q > 64: the CTA-pair kernel."""
+    run_case("pair-single-short", 1, 128, 1, [100])
+    run_case("pair-1page", 1, 128, 1, [64])
+    run_case("pair-ragged-h128", 3, 128, 1, [333, 1025, 1])
+    run_case("pair-h96", 2, 96, 1, [200, 77])
+    run_case("pair-h64-sq2-causal", 3, 64, 2, [300, 130, 64], causal=True)
+    run_case("pair-h128-sq2-causal", 2, 128, 2, [300, 129], causal=True)
+    run_case("pair-h32-sq4-causal", 2, 32, 4, [300, 65], causal=True)
+    run_case("pair-long-split-h128", 2, 128, 1, [20000, 9000], faithful=False)
+    run_case("pair-b64-s2048-h128", 64, 128, 1, [2048] * 64, faithful=False)
+
+
 for st in stages:
     try:
-        if st == "rate":
+        if st in ("rate", "pair"):
             continue
-        {"lab": lab, "small": small, "gemm": gemm, "mla": mla}[st]()
+        {"lab": lab, "small": small, "gemm": gemm, "mla": mla, "mla_pair": mla_pair}[st]()
     except Exception:
         traceback.print_exc()
         print("STAGE %s FAILED" % st, flush=True)
@@ -151,3 +164,61 @@ def rate():
 
 if "rate" in stages:
     rate()
+
+
+def pair():
+    """CTA-pair (cta_group::2) lab: derive the TMEM layout of D from a raw dump."""
+    import numpy as np
+    L = _lib.lib()
+    lut = np.array([_e4m3(i) for i in range(256)], dtype=np.float32)
+    rng = np.random.default_rng(5)
+
+    def rnd(shape):
+        c = rng.integers(0, 256, size=shape, dtype=np.uint8)
+        c[(c & 0x7F) >= 0x58] &= 0x47  # |v| < 16, no NaN
+        return c
+
+    for b_mode, n in ((0, 128), (0, 256), (0, 64), (1, 256)):
+        a = rnd((128, 128))
+        b = rnd((n, 128)) if b_mode == 0 else rnd((128, n))
+        out = np.zeros((2, 128, 256), dtype=np.float32)
+        rc = L.b200_umma_pair_lab(b_mode, n, a.ctypes.data, b.ctypes.data, out.ctypes.data)
+        if rc != 0:
+            print("pair b_mode=%d n=%d FAILED: %s" % (b_mode, n, L.b200_last_error().decode()), flush=True)
+            continue
+        af, bf = lut[a], lut[b]
+        d = af @ bf.T if b_mode == 0 else af @ bf  # [128][n]
+        print("pair b_mode=%d n=%d" % (b_mode, n), flush=True)
+        for cta in range(2):
+            for l0 in range(0, 128, 32):
+                desc = []
+                for lane in (l0, l0 + 31):
+                    x = out[cta, lane]
+                    written = np.nonzero(x != -12345.0)[0]
+                    if len(written) == 0:
+                        desc.append("lane %d: untouched" % lane)
+                        continue
+                    c_lo, c_hi = written.min(), written.max() + 1
+                    seg = x[c_lo:c_hi]
+                    best = None
+                    for row in range(128):
+                        for off in range(0, n - len(seg) + 1, 8):
+                            err = np.abs(d[row, off:off + len(seg)] - seg).max()
+                            if best is None or err < best[0]:
+                                best = (err, row, off)
+                    desc.append("lane %d: tmem cols [%d,%d) = D[row %d, cols %d..%d) err %.2g" % (
+                        lane, c_lo, c_hi, best[1], best[2], best[2] + len(seg), best[0]))
+                print("  cta %d  %s" % (cta, " | ".join(desc)), flush=True)
+
+
+def _e4m3(c):
+    import math
+    s, e, m = c >> 7, (c >> 3) & 0xF, c & 7
+    if e == 0xF and m == 7:
+        return float("nan")
+    v = math.ldexp(m / 8.0, -6) if e == 0 else math.ldexp(1 + m / 8.0, e - 7)
+    return -v if s else v
+
+
+if "pair" in stages:
+    pair()

@@ -96,6 +96,10 @@ def bench_gemm(m, n, k, n_rot=None):
 
 
 what = sys.argv[1:] or ["mla", "gemm"]
+if "mla128" in what:
+    bench_mla(128, 4096, 128)
+    bench_mla(64, 4096, 128, s_q=2)
+    bench_mla(128, 4096, 64, s_q=2)
 if "mla" in what:
     bench_mla(128, 4096, 128)
     bench_mla(128, 4096, 16)
