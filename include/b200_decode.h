@@ -124,6 +124,9 @@ int b200_umma_rate(int variant, int n, int iters, float* cycles_per_mma);
 /* CTA-pair (cta_group::2) lab: raw TMEM dump [2][128][256] of one M=128 MMA chain; host pointers (diagnostic). */
 int b200_umma_pair_lab(int b_mode, int n, const void* a, const void* b, float* out);
 
+/* Diagnostic: clock64 pipeline trace of the last CTA-pair MLA launch made with B200_MLA_TRACE set. */
+int b200_mla_read_trace(unsigned long long* out, int n);
+
 #ifdef __cplusplus
 }
 #endif

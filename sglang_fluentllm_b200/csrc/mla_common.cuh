@@ -33,6 +33,7 @@ struct MlaParams {
   int batch, s_q, h_q, M;
   float scale_log2;
   int is_causal;
+  int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)
 };
 
 // The work of one (sm part, request) pair.

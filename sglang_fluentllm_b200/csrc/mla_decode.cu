@@ -54,7 +54,7 @@ struct SmallSmem {
   uint64_t kv_full[kStages], kv_empty[kStages];
   uint64_t q_full, q_empty;
   uint64_t s_full[2], p_full[2];
-  uint64_t pv_done, o_free;
+  uint64_t pv_done, o_ready, o_free;
   uint32_t tmem_base;
   uint32_t trig[3];
   float f[64];        // q_scale * softmax_scale * log2(e)
@@ -109,6 +109,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
       mbar_init(&sm.p_full[i], kSmThreads);
     }
     mbar_init(&sm.pv_done, 1);
+    mbar_init(&sm.o_ready, 1);
     mbar_init(&sm.o_free, kSmThreads);
     sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
     fence_mbar_init();
@@ -266,6 +267,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
                         with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
           umma_commit(&sm.kv_empty[st]);
           umma_commit(&sm.pv_done);
+          if (t == sg.n_tiles - 1) umma_commit(&sm.o_ready);  // one completion per request: the epilogue's gate
         }
         __syncwarp();
       }
@@ -448,11 +450,15 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
       for (int q = 0; q < CPT; ++q) {
         float v = lt[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) atomicAdd(&sm.lsum[cb + q], v);
+        if (lane == 0) sm.red[quad][cb + q] = v;
       }
       named_bar_sync(1, kSmThreads);
+      // fixed summation order: results are bit-reproducible run to run
+      if (st_id < HB) sm.lsum[st_id] = (sm.red[0][st_id] + sm.red[1][st_id]) + (sm.red[2][st_id] + sm.red[3][st_id]);
+      named_bar_sync(1, kSmThreads);
       if (sg.n_tiles > 0) {
-        mbar_wait(&sm.pv_done, (g - 1) & 1);
+        // not pv_done: it completes once per tile and a parity wait from here could be two phases behind
+        mbar_wait(&sm.o_ready, o_seg & 1);
         tc_fence_after();
       }
       const int64_t out_row0 = (int64_t)b * p.M + q_row0;
@@ -582,6 +588,8 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.M = M;
   prm.scale_log2 = softmax_scale * 1.4426950408889634f;  // flash_api.cpp:324
   prm.is_causal = is_causal;
+  static const int trace = getenv("B200_MLA_TRACE") ? atoi(getenv("B200_MLA_TRACE")) : 0;  // diagnostic bit flags
+  prm.trace = trace;
 
   int rc;
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M

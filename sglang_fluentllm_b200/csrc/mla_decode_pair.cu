@@ -52,17 +52,24 @@ struct Small {
   uint64_t v_land[kVStages], v_empty[kVStages];
   uint64_t q_full, q_empty;
   uint64_t s_full[2], p_full[2], p_free[2];
-  uint64_t pv_done, o_free;
+  uint64_t pv_done, o_ready, o_free;
+  uint64_t p_relay[2], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
   uint32_t tmem_base;
   uint32_t trig[3];
-  float red1[4][64], red2[4][64];
-  float lsum[64];
+  float red1[4][64], red2[4][64], lred[4][64];
 };
 static_assert(sizeof(Small) <= 4096, "Small too large");
 
+// Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4][tile < 64][event < 4]
+constexpr int kTraceTiles = 64;
+__device__ unsigned long long g_trace[2 * 3 * kTraceTiles * 4];
+__device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
+  if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * 3 + role) * kTraceTiles + g) * 4 + ev] = clock64();
+}
+
 struct PendingPv {
   uint32_t g, seg, nk;
-  bool first, valid;
+  bool first, last, valid;
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
@@ -82,6 +89,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const int pair_row0 = blockIdx.y * 128;
   const int q_row0 = pair_row0 + 64 * (int)rank;
   const int n_valid_q = max(0, min(64, p.M - q_row0));
+  const bool tr = (p.trace & 1) && part == 0 && blockIdx.y == 0 && lane == 0;
 
   const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
   const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
@@ -101,11 +109,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     mbar_init(&sm.q_empty, 1);
     for (int i = 0; i < 2; ++i) {
       mbar_init(&sm.s_full[i], 1);
-      mbar_init(&sm.p_full[i], 16);  // 8 softmax warps x 2 CTAs
+      mbar_init(&sm.p_full[i], 9);   // the leader's 8 softmax warps + the peer's relay
+      mbar_init(&sm.p_relay[i], 8);
       mbar_init(&sm.p_free[i], 1);
     }
     mbar_init(&sm.pv_done, 1);
-    mbar_init(&sm.o_free, 16);
+    mbar_init(&sm.o_ready, 1);
+    mbar_init(&sm.o_free, 9);
+    mbar_init(&sm.o_relay, 8);
     sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_q_nope);
@@ -142,9 +153,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const int blk = sg.start_block + 2 * t + (int)rank;
         const bool exists = blk < sg.end_block;
         const int tok0 = exists ? __ldg(bt + blk) * kPage : 0;
-        const int blk_pf = blk + 2 * kKStages;
-        const int tok_pf = blk_pf < sg.end_block ? __ldg(bt + blk_pf) * kPage : -1;
+        const int blk_pf = blk + 2 * kKStages + ((p.trace & 4) ? 2 : 0);
+        const int tok_pf = (blk_pf < sg.end_block && !(p.trace & 2)) ? __ldg(bt + blk_pf) * kPage : -1;
         uint8_t* stage = s_k + st * kKStageBytes;
+        trace(tr, rank, 0, gt, 0);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(k_full_l[st], exists ? (uint32_t)kKStageBytes : 0u);
           if (exists) {
@@ -164,7 +176,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       // these bytes were just streamed through L2 as K by this CTA or its peer
       auto load_v = [&](int t, uint32_t gt) {
         const uint32_t st = gt % kVStages;
+        trace(tr, rank, 0, gt, 1);
         mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
+        trace(tr, rank, 0, gt, 2);
         const int blk0 = sg.start_block + 2 * t;
         const int npages = min(2, sg.end_block - blk0);
         const int tok0 = __ldg(bt + blk0) * kPage;
@@ -218,6 +232,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
       auto issue_pv = [&](const PendingPv& pv) {
         const uint32_t buf = pv.g & 1, vst = pv.g % kVStages;
+        trace(tr, rank, 1, pv.g, 2);
         mbar_wait_cluster(&sm.p_full[buf], (pv.g >> 1) & 1);  // P written and V landed in both CTAs
         if (pv.first && pv.seg > 0) mbar_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
         tc_fence_after();
@@ -233,8 +248,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           umma_commit_pair(&sm.v_empty[vst], 3);
           umma_commit_pair(&sm.p_free[buf], 3);
           umma_commit_pair(&sm.pv_done, 3);
+          if (pv.last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
         }
         __syncwarp();
+        trace(tr, rank, 1, pv.g, 3);
       };
 
       uint32_t g = 0, seg = 0;
@@ -246,6 +263,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait_cluster(&sm.q_full, seg & 1);
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
           const uint32_t kst = g % kKStages, buf = g & 1;
+          trace(tr, rank, 1, g, 0);
           mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
           tc_fence_after();
           const uint32_t stage = k_addr + kst * kKStageBytes;
@@ -266,18 +284,42 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             if (t == sg.n_tiles - 1) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
           }
           __syncwarp();
+          trace(tr, rank, 1, g, 1);
           // P.V of the previous tile goes behind this tile's Q.K^T: the softmax of tile g overlaps it
           if (pend.valid) issue_pv(pend);
           const int tile_start = (sg.start_block + 2 * t) * kPage;
           pend.g = g;
           pend.seg = seg;
           pend.first = (t == 0);
+          pend.last = (t == sg.n_tiles - 1);
           pend.nk = (uint32_t)((min(kTileTokens, sg.valid_end - tile_start) + 31) / 32);
           pend.valid = true;
         }
         ++seg;
       }
       if (pend.valid) issue_pv(pend);
+    } else {
+      // ============================== relay (non-leader CTA) ==============================
+      // This CTA's softmax warps hand P / O over on LOCAL barriers (ordered with their shared-memory stores); once a
+      // phase completes here -- the stores are then performed in this SM's shared memory -- one remote arrive tells the
+      // leader.  A direct remote arrive from the softmax warps would need a cluster-scope release (a cluster-wide
+      // membar per tile, measured at a third of their time); with CTA-scope release the arrive overtakes the stores.
+      const uint32_t p_full_l[2] = {mapa_u32(smem_u32(&sm.p_full[0]), 0), mapa_u32(smem_u32(&sm.p_full[1]), 0)};
+      const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
+      uint32_t g = 0, seg = 0;
+      for (int b = begin_idx; b <= end_idx; ++b) {
+        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+        if (sg.n_tiles == 0) continue;
+        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+          mbar_wait(&sm.p_relay[g & 1], (g >> 1) & 1);
+          if (elect_one()) mbar_arrive_cluster(p_full_l[g & 1]);
+          __syncwarp();
+        }
+        mbar_wait(&sm.o_relay, seg & 1);
+        if (elect_one()) mbar_arrive_cluster(o_free_l);
+        __syncwarp();
+        ++seg;
+      }
     }
   } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue (both CTAs) ==============================
@@ -290,11 +332,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const int col0 = ch * 32;
     const int slot = page * 2 + ch;           // which quarter of the row this thread holds
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
-    const uint32_t p_full_l[2] = {mapa_u32(smem_u32(&sm.p_full[0]), 0), mapa_u32(smem_u32(&sm.p_full[1]), 0)};
-    const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
     const bool row_valid = row < n_valid_q;
     const int grow = q_row0 + row;            // row within the request's M rows
-    uint32_t g = 0;
+    uint32_t g = 0, o_seg = 0;
 
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
@@ -303,9 +343,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       int lim = 0;
       if (row_valid) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, grow), sg.end_block * kPage) : sg.valid_end;
       float mref = kMInit, ps = 1.f, mprime = kMInit, lsum = 0.f;
-      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lsum are done
-      if (st_id < 64) sm.lsum[st_id] = 0.f;
-      named_bar_sync(1, kSmThreads);
+      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lred are done
 
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
         const uint32_t buf = g & 1, vst = g % kVStages;
@@ -329,7 +367,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           for (int c = 0; c < 32; ++c)
             if (!(tok_base + c < lim)) kf[c] = 0.f;
         }
+        trace(tr && warp == 4, rank, 2, g, 0);
         mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
+        trace(tr && warp == 4, rank, 2, g, 1);
         tc_fence_after();
         float x[32];
         const uint32_t s_addr = tmem + kColS + buf * 64 + col0 + lane_addr;
@@ -341,14 +381,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         if (!trigger) {
           // ---- fast path: reuse the current reference ----
           float vmax = 0.f, acc = 0.f;
+          if (!need_mask) {
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float arg = fmaf(x[c], f * kf[c], -mprime);
-            if (need_mask && !(tok_base + c < lim)) arg = -INFINITY;
-            const float u = ex2_approx(arg);
-            acc += u;
-            x[c] = u * kf[c];
-            vmax = fmaxf(vmax, x[c]);
+            for (int c = 0; c < 32; ++c) {
+              const float u = ex2_approx(fmaf(x[c], f * kf[c], -mprime));
+              acc += u;
+              x[c] = u * kf[c];
+              vmax = fmaxf(vmax, x[c]);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float arg = fmaf(x[c], f * kf[c], -mprime);
+              if (!(tok_base + c < lim)) arg = -INFINITY;
+              const float u = ex2_approx(arg);
+              acc += u;
+              x[c] = u * kf[c];
+              vmax = fmaxf(vmax, x[c]);
+            }
           }
 #pragma unroll
           for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
@@ -417,6 +467,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
         }
 
+        trace(tr && warp == 4, rank, 2, g, 2);
         // ---- publish P (A operand of P.V: [q row][token], K-major, 128-byte swizzle) ----
         mbar_wait(&sm.p_free[buf], ((g >> 1) & 1) ^ 1);  // P.V of tile g-2 has retired
         {
@@ -443,17 +494,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(p_full_l[buf]);
+        if (lane == 0) mbar_arrive(rank == 0 ? &sm.p_full[buf] : &sm.p_relay[buf]);
+        trace(tr && warp == 4, rank, 2, g, 3);
       }
 
       // ---- epilogue of this request: O / L -> out (or split partials) ----
-      atomicAdd(&sm.lsum[row], lsum);
+      sm.lred[slot][row] = lsum;
       named_bar_sync(1, kSmThreads);
-      const float l = sm.lsum[row];
+      const float l = (sm.lred[0][row] + sm.lred[1][row]) + (sm.lred[2][row] + sm.lred[3][row]);  // fixed order
       const bool bad = (l == 0.f || l != l);
       const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
       if (sg.n_tiles > 0) {
-        mbar_wait(&sm.pv_done, (g - 1) & 1);
+        // pv_done completes once per tile and this thread has not waited on it since its last rescale: a parity wait
+        // on it could be two phases behind.  o_ready completes once per request.
+        mbar_wait(&sm.o_ready, o_seg & 1);
+        ++o_seg;
         tc_fence_after();
       }
 #pragma unroll
@@ -501,7 +556,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       if (sg.n_tiles > 0) {
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive_cluster(o_free_l);
+        if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
       }
     }
   }
@@ -528,3 +583,10 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream)
 }
 
 }  // namespace b200
+
+// Diagnostic: copy the pipeline trace of the last traced pair-kernel launch (see g_trace) to host memory.
+extern "C" int b200_mla_read_trace(unsigned long long* out, int n) {
+  const int total = 2 * 3 * b200::pairk::kTraceTiles * 4;
+  B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_trace, sizeof(unsigned long long) * (n < total ? n : total)));
+  return 0;
+}

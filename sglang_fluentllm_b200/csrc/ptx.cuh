@@ -278,12 +278,14 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
-// arrive on a barrier that may live in the peer CTA (cluster address from mapa_u32)
+// arrive on a barrier that may live in the peer CTA (cluster address from mapa_u32).  Default semantics (release at
+// CTA scope): what is handed over is this CTA's own shared memory / TMEM, consumed by its own tensor core; a
+// .release.cluster here costs a cluster-wide membar per arrival (measured: a third of the softmax warps' time).
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar_addr) {
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar_addr) : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx_cluster(uint32_t cluster_bar_addr, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.release.cluster.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar_addr),
+  asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], %1;" ::"r"(cluster_bar_addr),
                "r"(bytes)
                : "memory");
 }
