@@ -58,27 +58,60 @@ def parse():
 # clocks
 # ----------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock / throttle reasons sampled DURING the timed region (NVML, ~2 ms period; nvidia-smi as a fallback)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index: int):
         self.index = index
-        self.samples = []
+        self.sm, self.power = [], []
+        self.sm_max = None
+        self.reasons = set()
         self._stop = threading.Event()
         self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self._nvml = pynvml
+            self.sm_max = int(pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self._nvml = None
+
+    def _sample_nvml(self):
+        n = self._nvml
+        self.sm.append(int(n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)))
+        try:
+            self.power.append(n.nvmlDeviceGetPowerUsage(self._h) / 1000.0)
+        except Exception:
+            pass
+        r = int(n.nvmlDeviceGetCurrentClocksEventReasons(self._h)) if hasattr(n, "nvmlDeviceGetCurrentClocksEventReasons") \
+            else int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self._h))
+        for name, bit in (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+                          ("sw_power_cap", 0x4)):
+            if r & bit:
+                self.reasons.add(name)
+
+    def _sample_smi(self):
+        out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                              "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [p.strip() for p in out.strip().split(",")]
+        if len(parts) >= 7:
+            self.sm.append(int(float(parts[0])))
+            self.sm_max = int(float(parts[1]))
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), parts[3:7]):
+                if v.lower().startswith("active"):
+                    self.reasons.add(name)
 
     def _run(self):
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
-                parts = [p.strip() for p in out.strip().split(",")]
-                if len(parts) >= 7:
-                    self.samples.append(parts)
+                self._sample_nvml() if self._nvml else self._sample_smi()
             except Exception:
                 pass
-            self._stop.wait(0.1)
+            self._stop.wait(0.002)
 
     def start(self):
         self._t = threading.Thread(target=self._run, daemon=True)
@@ -88,15 +121,10 @@ class ClockSampler:
         self._stop.set()
         if self._t:
             self._t.join(timeout=6)
-        sm = sorted(int(float(s[0])) for s in self.samples if s[0].replace(".", "").isdigit())
-        mx = [int(float(s[1])) for s in self.samples if s[1].replace(".", "").isdigit()]
-        reasons = set()
-        for s in self.samples:
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), s[3:7]):
-                if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.samples)}
+        sm = sorted(self.sm)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_min_mhz": sm[0] if sm else None,
+                "sm_max_mhz": self.sm_max, "power_w_max": round(max(self.power), 1) if self.power else None,
+                "reasons": sorted(self.reasons), "samples": len(sm)}
 
 
 # ----------------------------------------------------------------------------------------------------------------

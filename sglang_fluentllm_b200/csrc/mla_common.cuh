@@ -33,6 +33,7 @@ struct MlaParams {
   int batch, s_q, h_q, M;
   float scale_log2;
   int is_causal;
+  int pf_tiles;  // pair kernel: L2 prefetch distance of the K pages, in 128-token tiles (>= 2)
   int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)
 };
 

@@ -590,6 +590,8 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.is_causal = is_causal;
   static const int trace = getenv("B200_MLA_TRACE") ? atoi(getenv("B200_MLA_TRACE")) : 0;  // diagnostic bit flags
   prm.trace = trace;
+  static const int pf_tiles = getenv("B200_MLA_PF") ? atoi(getenv("B200_MLA_PF")) : 4;  // tuning knob, see DESIGN.md
+  prm.pf_tiles = pf_tiles < 2 ? 2 : pf_tiles;
 
   int rc;
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M

@@ -32,6 +32,7 @@ namespace b200 {
 namespace pairk {
 
 constexpr int kKStages = 2, kVStages = 2;
+constexpr int kKsStages = 8, kKsAhead = 6;  // k-scale ring: 512 B per tile, loaded kKsAhead tiles ahead of the softmax
 constexpr int kQBytes = 64 * 640;          // 4 nope chunks [64 rows x 128 B] + rope [64 x 128 B]
 constexpr int kKStageBytes = 64 * 640;     // this CTA's page of the tile, same layout
 constexpr int kVStageBytes = 2 * 128 * 128;  // [2 d-halves][128 tokens][128 B]
@@ -40,8 +41,9 @@ constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kQBytes;
 constexpr int kOffV = kOffK + kKStages * kKStageBytes;
 constexpr int kOffP = kOffV + kVStages * kVStageBytes;
-constexpr int kOffKs = kOffP + 2 * kPBytes;          // k scales of the tile: [kVStages][128] f32
-constexpr int kOffSmall = kOffKs + kVStages * 512;
+constexpr int kStageExtra = 16384;                   // epilogue staging tile = the two P buffers + this (32 KB)
+constexpr int kOffKs = kOffP + 2 * kPBytes + kStageExtra;  // k scales of the tile: [kVStages][128] f32
+constexpr int kOffSmall = kOffKs + kKsStages * 512;
 constexpr int kTotal = kOffSmall + 4096;
 constexpr int kSmThreads = 256;                      // softmax group
 constexpr uint32_t kColS = 0, kColO = 128, kTmemCols = 512;
@@ -50,6 +52,7 @@ static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOf
 struct Small {
   uint64_t k_full[kKStages], k_empty[kKStages];
   uint64_t v_land[kVStages], v_empty[kVStages];
+  uint64_t ks_full[kKsStages], ks_empty[kKsStages];
   uint64_t q_full, q_empty;
   uint64_t s_full[2], p_full[2], p_free[2];
   uint64_t pv_done, o_ready, o_free;
@@ -60,12 +63,41 @@ struct Small {
 };
 static_assert(sizeof(Small) <= 4096, "Small too large");
 
-// Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4][tile < 64][event < 4]
+// Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4, 3 epilogue (indexed by
+// request)][tile < 64][event < 4]
 constexpr int kTraceTiles = 64;
-__device__ unsigned long long g_trace[2 * 3 * kTraceTiles * 4];
+constexpr int kTraceRoles = 4;
+__device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
-  if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * 3 + role) * kTraceTiles + g) * 4 + ev] = clock64();
+  if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
 }
+
+// Register-resident window of one block-table row for the producer warp (warp-uniform use): lane l holds entries
+// base + l and base + 32 + l.  With ~230 KB of shared memory per CTA there is no L1 left, so every __ldg of the block
+// table is an L2 round trip (300-600 cycles under load); three of them per tile in the producer's dependency chain were
+// the pipeline's critical path.  Entries are fetched 16+ tiles ahead instead and read with a shuffle.
+struct BtWindow {
+  const int32_t* row;
+  int base, limit, cur, nxt;
+  __device__ __forceinline__ void init(const int32_t* r, int first, int lim, int lane) {
+    row = r, base = first, limit = lim;
+    cur = (base + lane < limit) ? __ldg(row + base + lane) : 0;
+    nxt = (base + 32 + lane < limit) ? __ldg(row + base + 32 + lane) : 0;
+  }
+  // call with the lowest block index still needed; keeps [lowest, lowest + 32) inside the window
+  __device__ __forceinline__ void advance_to(int lowest, int lane) {
+    while (lowest >= base + 32) {
+      cur = nxt;
+      base += 32;
+      nxt = (base + 32 + lane < limit) ? __ldg(row + base + 32 + lane) : 0;
+    }
+  }
+  __device__ __forceinline__ int get(int blk) const {
+    const int i = blk - base;
+    const int a = __shfl_sync(0xffffffffu, cur, i & 31), c = __shfl_sync(0xffffffffu, nxt, i & 31);
+    return i < 32 ? a : c;
+  }
+};
 
 struct PendingPv {
   uint32_t g, seg, nk;
@@ -105,6 +137,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       mbar_init(&sm.v_land[i], 1);
       mbar_init(&sm.v_empty[i], 1);
     }
+    for (int i = 0; i < kKsStages; ++i) {
+      mbar_init(&sm.ks_full[i], 1);
+      mbar_init(&sm.ks_empty[i], 8);  // the eight softmax warps
+    }
     mbar_init(&sm.q_full, 2);
     mbar_init(&sm.q_empty, 1);
     for (int i = 0; i < 2; ++i) {
@@ -141,10 +177,22 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     for (int i = 0; i < kKStages; ++i) k_full_l[i] = mapa_u32(smem_u32(&sm.k_full[i]), 0);
 
     uint32_t g = 0, seg_i = 0;
+    const int pf = min(p.pf_tiles, 14);  // the block-table window holds 32 entries past the current tile
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
       if (sg.n_tiles == 0) continue;
       const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+      // the request after this one (same part): its first pages and its Q are prefetched into L2 while this one runs
+      const int32_t* bt_next = nullptr;
+      int nxt_blocks = 0;
+      if (b < end_idx) {
+        const int nsl = (b + 1 == end_idx) ? min(end_seqlen, __ldg(p.seqlens + b + 1)) : __ldg(p.seqlens + b + 1);
+        nxt_blocks = (nsl + kPage - 1) / kPage;
+        bt_next = p.block_table + (int64_t)(b + 1) * p.block_table_stride;
+      }
+      BtWindow bw;
+      bw.init(bt, sg.start_block, sg.end_block, lane);
+      const int nxt_req = (bt_next != nullptr && lane < nxt_blocks) ? __ldg(bt_next + lane) : 0;  // its first 16 tiles
 
       // this CTA's page of tile t -> K stage (credits the leader's barrier)
       auto load_k = [&](int t, uint32_t gt) {
@@ -152,9 +200,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait(&sm.k_empty[st], ((gt / kKStages) & 1) ^ 1);
         const int blk = sg.start_block + 2 * t + (int)rank;
         const bool exists = blk < sg.end_block;
-        const int tok0 = exists ? __ldg(bt + blk) * kPage : 0;
-        const int blk_pf = blk + 2 * kKStages + ((p.trace & 4) ? 2 : 0);
-        const int tok_pf = (blk_pf < sg.end_block && !(p.trace & 2)) ? __ldg(bt + blk_pf) * kPage : -1;
+        const int tok0 = exists ? bw.get(blk) * kPage : 0;
+        // L2 prefetch `pf` tiles ahead (past the end of this request: the first tiles of the next one)
+        int tok_pf = -1;
+        {
+          const int tp = t + pf;
+          if (tp < sg.n_tiles) {
+            const int bp = sg.start_block + 2 * tp + (int)rank;
+            if (bp < sg.end_block) tok_pf = bw.get(bp) * kPage;
+          } else if (bt_next != nullptr) {
+            const int bp = 2 * (tp - sg.n_tiles) + (int)rank;
+            if (bp < nxt_blocks && bp < 32) tok_pf = __shfl_sync(0xffffffffu, nxt_req, bp) * kPage;
+          }
+        }
         uint8_t* stage = s_k + st * kKStageBytes;
         trace(tr, rank, 0, gt, 0);
         if (elect_one()) {
@@ -181,23 +239,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         trace(tr, rank, 0, gt, 2);
         const int blk0 = sg.start_block + 2 * t;
         const int npages = min(2, sg.end_block - blk0);
-        const int tok0 = __ldg(bt + blk0) * kPage;
-        const int tok1 = npages > 1 ? __ldg(bt + blk0 + 1) * kPage : 0;
+        const int tok0 = bw.get(blk0) * kPage;
+        const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
         uint8_t* stage = s_v + st * kVStageBytes;
-        float* ks_dst = s_ks + st * 128;
         if (elect_one()) {
-          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192 + 256));
+          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192));
 #pragma unroll
           for (int j = 0; j < 2; ++j)
             tma_load_2d_hint(stage + j * 16384, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
-          bulk_load_1d(ks_dst, p.k_scale + tok0, 256, &sm.v_land[st]);
           if (npages > 1) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
               tma_load_2d_hint(stage + j * 16384 + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1,
                                pol_last_use);
-            bulk_load_1d(ks_dst + 64, p.k_scale + tok1, 256, &sm.v_land[st]);
           }
+        }
+        __syncwarp();
+      };
+      // k scales of both pages of tile t -> scale ring.  Their HBM latency (a separate array: no L2 warm-up by the K
+      // stream) is paid kKsAhead tiles before the softmax needs them.
+      auto load_ks = [&](int t, uint32_t gt) {
+        const uint32_t st = gt % kKsStages;
+        mbar_wait(&sm.ks_empty[st], ((gt / kKsStages) & 1) ^ 1);
+        const int blk0 = sg.start_block + 2 * t;
+        const int npages = min(2, sg.end_block - blk0);
+        const int tok0 = bw.get(blk0) * kPage;
+        const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
+        float* ks_dst = s_ks + st * 128;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sm.ks_full[st], (uint32_t)npages * 256);
+          bulk_load_1d(ks_dst, p.k_scale + tok0, 256, &sm.ks_full[st]);
+          if (npages > 1) bulk_load_1d(ks_dst + 64, p.k_scale + tok1, 256, &sm.ks_full[st]);
         }
         __syncwarp();
       };
@@ -211,11 +283,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 #pragma unroll
         for (int c = 0; c < 4; ++c) tma_load_2d_pair(s_q + c * 8192, &p.tm_q_nope, q_full_l, c * 128, qrow);
         tma_load_2d_pair(s_q + 32768, &p.tm_q_rope, q_full_l, 0, qrow);
+        if (b < end_idx) {  // next request's Q rows of this CTA
+#pragma unroll
+          for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_q_nope, c * 128, qrow + p.M);
+          tma_prefetch_2d(&p.tm_q_rope, 0, qrow + p.M);
+        }
       }
       __syncwarp();
+      if (seg_i == 1) {  // first request of this part: tiles the steady-state prefetch (t + pf) will not reach
+        for (int tp = kKStages; tp < pf && tp < sg.n_tiles; ++tp) {
+          const int bp = sg.start_block + 2 * tp + (int)rank;
+          if (bp < sg.end_block) {
+            const int tk = bw.get(bp) * kPage;
+            if (elect_one()) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tk);
+              tma_prefetch_2d(&p.tm_k_rope, 0, tk);
+            }
+            __syncwarp();
+          }
+        }
+      }
+      __syncwarp();
+      for (int t = 0; t < kKsAhead && t < sg.n_tiles; ++t) load_ks(t, g + t);
       load_k(0, g);
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        bw.advance_to(sg.start_block + 2 * t, lane);
         if (t + 1 < sg.n_tiles) load_k(t + 1, g + 1);
+        if (t + kKsAhead < sg.n_tiles) load_ks(t + kKsAhead, g + kKsAhead);
         load_v(t, g);
       }
     }
@@ -352,16 +447,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
         if (st_id == 0) sm.trig[(g + 1) % 3] = 0;
 
-        mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);  // k scales (and this CTA's V slices) have landed
-        float kf[32];                                     // k_scale, later f * k_scale
+        if (g == 0 || t == 0) trace(tr && warp == 4, rank, 3, o_seg, 3);
+        const uint32_t kst = g % kKsStages;
+        mbar_wait(&sm.ks_full[kst], (g / kKsStages) & 1);  // k scales of the tile (loaded kKsAhead tiles ago)
+        float kf[32];                                       // k_scale, later f * k_scale
         {
-          const float4* src = reinterpret_cast<const float4*>(s_ks + vst * 128 + page * 64 + col0);
+          const float4* src = reinterpret_cast<const float4*>(s_ks + kst * 128 + page * 64 + col0);
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             const float4 v4 = src[i];
             kf[4 * i] = v4.x, kf[4 * i + 1] = v4.y, kf[4 * i + 2] = v4.z, kf[4 * i + 3] = v4.w;
           }
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
         if (need_mask) {
 #pragma unroll
           for (int c = 0; c < 32; ++c)
@@ -470,6 +569,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         trace(tr && warp == 4, rank, 2, g, 2);
         // ---- publish P (A operand of P.V: [q row][token], K-major, 128-byte swizzle) ----
         mbar_wait(&sm.p_free[buf], ((g >> 1) & 1) ^ 1);  // P.V of tile g-2 has retired
+        mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);  // this CTA's V slices have landed (p_full vouches for them)
         {
           uint8_t* prow = s_p + buf * kPBytes + row * 128;
           const int c16 = (page * 64 + col0) >> 4;  // first of this thread's two 16-byte chunks
@@ -499,6 +599,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       }
 
       // ---- epilogue of this request: O / L -> out (or split partials) ----
+      trace(tr && warp == 4, rank, 3, o_seg, 0);
       sm.lred[slot][row] = lsum;
       named_bar_sync(1, kSmThreads);
       const float l = (sm.lred[0][row] + sm.lred[1][row]) + (sm.lred[2][row] + sm.lred[3][row]);  // fixed order
@@ -508,42 +609,81 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         // pv_done completes once per tile and this thread has not waited on it since its last rescale: a parity wait
         // on it could be two phases behind.  o_ready completes once per request.
         mbar_wait(&sm.o_ready, o_seg & 1);
+        trace(tr && warp == 4, rank, 3, o_seg, 1);
         ++o_seg;
         tc_fence_after();
       }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int hh = 0; hh < 2; ++hh) {
+      // O -> global through a shared-memory staging tile, so that every global store instruction writes whole
+      // 128-byte lines: a TMEM lane is a q row, and storing straight from the tcgen05.ld registers would scatter
+      // 16-byte pieces over 32 rows per instruction (measured: ~10k cycles per request, now ~2k).
+      // Staging tile (the two P buffers -- every P.V of this request has retired -- + 16 KB): [64 rows][4 slots][32
+      // values], 16-byte chunks XOR-swizzled with (row & 7); one round per (d half j, 32-column group hh).
+      {
+        uint8_t* stage = s_p;
+        const int wq = warp - 4;
+        const int64_t grow0 = (int64_t)b * p.M + q_row0;
+#pragma unroll 1
+        for (int r4 = 0; r4 < 4; ++r4) {
+          const int j = r4 >> 1, hh = r4 & 1;
           float o[32];
           if (sg.n_tiles > 0) {
             tmem_ld<32>(tmem + kColO + j * 128 + ch * 64 + hh * 32 + lane_addr, o);
             tmem_wait_ld();
+            if (r4 == 3) {  // O is in registers / shared memory: the next request's P.V may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
+            }
           } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) o[k] = 0.f;
           }
-          const int d0 = 256 * j + 128 * page + ch * 64 + hh * 32;
-          if (row_valid) {
-            if (sg.no_split) {
-              uint4* dst = reinterpret_cast<uint4*>(p.out + ((int64_t)b * p.M + grow) * 512 + d0);
+          if (sg.no_split) {
+            uint8_t* srow = stage + row * 256;
 #pragma unroll
-              for (int k = 0; k < 32; k += 8) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[k] * inv, o[k + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[k + 2] * inv, o[k + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[k + 4] * inv, o[k + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[k + 6] * inv, o[k + 7] * inv);
-                dst[k / 8] = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-              }
-            } else {
-              float4* dst = reinterpret_cast<float4*>(p.o_accum + ((int64_t)sg.split_idx * p.M + grow) * 512 + d0);
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
+              *reinterpret_cast<uint4*>(srow + (((slot * 4 + k) ^ (row & 7)) << 4)) =
+                  make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+            }
+          } else {
+            uint8_t* srow = stage + row * 512;
 #pragma unroll
-              for (int k = 0; k < 32; k += 4)
-                dst[k / 4] = make_float4(o[k] * inv, o[k + 1] * inv, o[k + 2] * inv, o[k + 3] * inv);
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(srow + (((slot * 8 + k) ^ (row & 7)) << 4)) =
+                  make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
+          }
+          named_bar_sync(1, kSmThreads);
+          if (sg.no_split) {
+            // 16 lanes x 16 B per row, two rows per instruction
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = wq * 8 + it * 2 + (lane >> 4), c = lane & 15;
+              const int sl = c >> 2, k = c & 3;
+              const int d0 = 256 * j + 128 * (sl >> 1) + 64 * (sl & 1) + 32 * hh + 8 * k;
+              const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 256 + ((c ^ (r & 7)) << 4));
+              if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d0) = v;
+            }
+          } else {
+            // 32 lanes x 16 B = one row's four 128-byte segments per instruction
+            float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
+            const int sl = lane >> 3, k = lane & 7;
+            const int d0 = 256 * j + 128 * (sl >> 1) + 64 * (sl & 1) + 32 * hh + 4 * k;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = wq * 8 + it;
+              const float4 v = *reinterpret_cast<const float4*>(stage + r * 512 + ((lane ^ (r & 7)) << 4));
+              if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d0) = v;
             }
           }
+          named_bar_sync(1, kSmThreads);  // the staging tile is rewritten by the next round / the next request's P
         }
+      }
+      if (sg.n_tiles > 0) trace(tr && warp == 4, rank, 3, o_seg - 1, 2);
       if (row_valid && slot == 0) {
         const float lse2 = log2f(l) + mprime;
         if (sg.no_split) {
@@ -552,11 +692,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         } else {
           p.lse_accum[(int64_t)sg.split_idx * p.M + grow] = bad ? -INFINITY : lse2;                    // :1506
         }
-      }
-      if (sg.n_tiles > 0) {
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
       }
     }
   }
@@ -586,7 +721,7 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream)
 
 // Diagnostic: copy the pipeline trace of the last traced pair-kernel launch (see g_trace) to host memory.
 extern "C" int b200_mla_read_trace(unsigned long long* out, int n) {
-  const int total = 2 * 3 * b200::pairk::kTraceTiles * 4;
+  const int total = 2 * b200::pairk::kTraceRoles * b200::pairk::kTraceTiles * 4;
   B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_trace, sizeof(unsigned long long) * (n < total ? n : total)));
   return 0;
 }

@@ -334,8 +334,8 @@ int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64
 int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cache, const float* k_scale_cache,
                                 const int32_t* indices, int64_t n, int64_t max_num_tokens, void* k_lora_out,
                                 void* k_rope_out, void* stream) {
+  if (n == 0) return 0;  // empty request: the (empty) output tensors have no storage
   B200_CHECK(k_lora_cache && k_rope_cache && k_scale_cache && k_lora_out && k_rope_out, "dequantize: null pointer");
-  if (n == 0) return 0;
   B200_CHECK(indices, "dequantize: null indices");
   // grid depends only on max_num_tokens when given, so CUDA-graph capture and replay agree
   // (reference: cache_kernels.cu:372-423)

@@ -279,6 +279,77 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1) umma_pair_la
   if (warp == 1) tmem_dealloc_pair(tmem, 256);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// CTA-pair issue-rate probe: `iters` back-to-back cta_group::2 MMAs (M = 128 over the pair) on resident smem.
+//   mode 0: fp8  A K-major SW128 x B K-major SW128, N = n              (pair Q.K^T nope)
+//   mode 1: fp8  A K-major SW128 x B MN-major SW128, N = n (256)       (pair P.V)
+//   mode 2: bf16 A K-major SW128 x B K-major SW128, N = n              (pair Q.K^T rope)
+//   mode 3: the MLA tile mix: 16 x mode 0 (N=128) + 4 x mode 2 (N=128) + 8 x mode 1 (N=256); cycles per 28-MMA tile / 28
+// ------------------------------------------------------------------------------------------------------------------
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128, 1)
+    umma_pair_rate_kernel(int mode, int n, int iters, long long* cycles) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  __shared__ uint64_t bar;
+  __shared__ uint32_t slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const uint32_t rank = cluster_ctarank();
+  for (int i = tid; i < 128 * 1024 / 4; i += 128) reinterpret_cast<uint32_t*>(smem)[i] = 0x38383838u;
+  fence_proxy_async_smem();
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncwarp();
+  if (warp == 1) tmem_alloc_pair(&slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem = slot;
+  if (warp == 0 && rank == 0) {
+    const uint32_t a = smem_u32(smem), b = a + 40 * 1024;
+    const uint32_t id_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, mode == 3 ? 128 : n);
+    const uint32_t id_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, mode == 3 ? 128 : n);
+    const uint32_t id_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, mode == 3 ? 256 : n);
+    const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
+    const uint64_t dv = make_smem_desc(0, 16384, 1024, SWZ_128B);
+    auto wa = [](uint64_t d, uint32_t x) { return d | (uint64_t)((x >> 4) & 0x3FFF); };
+    const long long t0 = clock64();
+    for (int i = 0; i < iters; ++i) {
+      if (elect_one()) {
+        if (mode == 0 || mode == 3) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            umma_f8_pair(tmem + (i & 1) * 64, wa(dk, a + (j >> 2) * 8192 + (j & 3) * 32), wa(dk, b + (j >> 2) * 8192 + (j & 3) * 32),
+                         id_qk8, 1);
+        }
+        if (mode == 2 || mode == 3) {
+#pragma unroll
+          for (int j = 0; j < (16 >> (mode == 3 ? 2 : 0)); ++j)
+            umma_f16_pair(tmem + (i & 1) * 64, wa(dk, a + 32768 + (j & 3) * 32), wa(dk, b + 32768 + (j & 3) * 32), id_qk16, 1);
+        }
+        if (mode == 1 || mode == 3) {
+#pragma unroll
+          for (int j = 0; j < (mode == 3 ? 8 : 16); ++j)
+            umma_f8_pair(tmem + 128 + (j & 1) * 128, wa(dk, a + (j & 3) * 32), wa(dv, b + 40960 + (j & 1) * 16384 + ((j >> 1) & 3) * 4096),
+                         id_pv, 1);
+        }
+      }
+      __syncwarp();
+    }
+    if (elect_one()) umma_commit_pair(&bar, 1);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    if (lane_id() == 0) cycles[0] = clock64() - t0;
+  }
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();
+  if (warp == 1) tmem_dealloc_pair(tmem, 512);
+}
+
 static float e4m3_to_float(uint8_t c) {
   int s = c >> 7, e = (c >> 3) & 0xF, m = c & 7;
   float v;
@@ -462,4 +533,25 @@ extern "C" int b200_umma_pair_lab(int b_mode, int n, const void* a, const void* 
   cudaFree(dB);
   cudaFree(dOut);
   return rc;
+}
+
+// Average SM cycles per cta_group::2 tcgen05.mma for one operand form; see umma_pair_rate_kernel.
+extern "C" int b200_umma_pair_rate(int mode, int n, int iters, float* cycles_per_mma) {
+  B200_CHECK(mode >= 0 && mode <= 3 && n % 16 == 0 && n >= 32 && n <= 256 && iters > 0, "umma_pair_rate: bad arguments");
+  long long* d = nullptr;
+  B200_CUDA(cudaMalloc(&d, sizeof(long long)));
+  const int smem_bytes = 130 * 1024;
+  cudaFuncSetAttribute(umma_pair_rate_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+  umma_pair_rate_kernel<<<2, 128, smem_bytes>>>(mode, n, iters, d);
+  cudaError_t e = cudaDeviceSynchronize();
+  long long c = 0;
+  if (e == cudaSuccess) e = cudaMemcpy(&c, d, sizeof(c), cudaMemcpyDeviceToHost);
+  cudaFree(d);
+  if (e != cudaSuccess) {
+    set_last_error("umma_pair_rate: %s", cudaGetErrorString(e));
+    return 2;
+  }
+  const int per_iter = mode == 3 ? 28 : 16;
+  *cycles_per_mma = (float)c / ((float)iters * per_iter);
+  return 0;
 }

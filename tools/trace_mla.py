@@ -43,9 +43,9 @@ for i in range(1, len(outs)):
             bb, min(hs), max(hs), len(hs), half, quads, float(dm), float(ld), blocks))
 L = _lib.lib()
 T = 64
-buf = np.zeros(2 * 3 * T * 4, dtype=np.uint64)
+buf = np.zeros(2 * 4 * T * 4, dtype=np.uint64)
 _lib.check(L.b200_mla_read_trace(buf.ctypes.data, buf.size), "read_trace")
-tr = buf.reshape(2, 3, T, 4).astype(np.int64)
+tr = buf.reshape(2, 4, T, 4).astype(np.int64)
 for rank in range(2):
     t0 = tr[rank, 1, 0, 0] if rank == 0 else tr[rank, 0, 0, 0]
     print("rank %d (cycles relative to first event; d = delta to previous tile)" % rank)
@@ -60,3 +60,8 @@ for rank in range(2):
         prev = ref
         print(" %4d | %7d %7d %7d | %7d %7d %7d %7d | %7d %7d %7d %7d | %s" % (
             g, r[0, 0], r[0, 1], r[0, 2], r[1, 0], r[1, 1], r[1, 2], r[1, 3], r[2, 0], r[2, 1], r[2, 2], r[2, 3], per))
+
+    print(" request | epilogue: start  o_ready  stored | next request's first tile top (previous row's request)")
+    for sgi in range(4):
+        e = tr[rank, 3, sgi, :] - t0
+        print(" %7d | %9d %8d %8d | %8d" % (sgi, e[0], e[1], e[2], e[3]))
