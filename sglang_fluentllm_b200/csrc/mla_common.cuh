@@ -15,7 +15,7 @@ static constexpr int kTileTokens = 128;
 static constexpr int kPage = B200_MLA_PAGE_SIZE;
 static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
 static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
-static constexpr float kHeadroom = 8.0f;                      // lazy rescale: new reference leaves 2^3 of growth
+static constexpr float kHeadroom = 16.0f;                     // lazy rescale: a new reference leaves 2^4 of growth before e4m3 saturates
 
 struct MlaParams {
   CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;
@@ -33,6 +33,9 @@ struct MlaParams {
   int batch, s_q, h_q, M;
   float scale_log2;
   int is_causal;
+  const uint8_t* k_lora_base;  // raw pool pointers (bulk L2 prefetch)
+  const uint8_t* k_rope_base;
+  int pf_mode;   // diagnostic: 0 tensor-map prefetch, 1 none, 2 bulk prefetch
   int pf_tiles;  // pair kernel: L2 prefetch distance of the K pages, in 128-token tiles (>= 2)
   int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)
 };

@@ -41,12 +41,16 @@ constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kQBytes;
 constexpr int kOffV = kOffK + kKStages * kKStageBytes;
 constexpr int kOffP = kOffV + kVStages * kVStageBytes;
-constexpr int kStageExtra = 16384;                   // epilogue staging tile = the two P buffers + this (32 KB)
-constexpr int kOffKs = kOffP + 2 * kPBytes + kStageExtra;  // k scales of the tile: [kVStages][128] f32
+constexpr int kPBufs = 4;                            // P tiles: a softmax group writes tile g+2 while P.V of tile g is pending
+constexpr int kOffKs = kOffP + kPBufs * kPBytes;     // k-scale ring: [kKsStages][128] f32; the four P tiles (32 KB) double
+                                                     // as the epilogue's staging tile
 constexpr int kOffSmall = kOffKs + kKsStages * 512;
-constexpr int kTotal = kOffSmall + 4096;
+constexpr int kTotal = kOffSmall + 5120;
 constexpr int kSmThreads = 256;                      // softmax group
-constexpr uint32_t kColS = 0, kColO = 128, kTmemCols = 512;
+constexpr int kSBufs = 4;                            // S tiles in TMEM: Q.K^T may run kSBufs - 1 tiles ahead of P.V
+constexpr uint32_t kColS = 0, kColO = kSBufs * 64, kTmemCols = 512;
+static_assert(kColO + 256 <= kTmemCols, "TMEM budget");
+static_assert(kPBufs == kSBufs, "s_full(g) stands in for p_free of P tile g % kPBufs");
 static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffKs % 1024 == 0, "swizzle alignment");
 
 struct Small {
@@ -54,19 +58,24 @@ struct Small {
   uint64_t v_land[kVStages], v_empty[kVStages];
   uint64_t ks_full[kKsStages], ks_empty[kKsStages];
   uint64_t q_full, q_empty;
-  uint64_t s_full[2], p_full[2], p_free[2];
+  uint64_t s_full[kSBufs], p_full[kPBufs], p_free[kPBufs];
   uint64_t pv_done, o_ready, o_free;
-  uint64_t p_relay[2], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
+  uint64_t p_relay[kPBufs], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
+  uint64_t fin[2];               // tile g (buffer g & 1) is final: published, reference moves done
   uint32_t tmem_base;
-  uint32_t trig[3];
-  float red1[4][64], red2[4][64], lred[4][64];
+  uint32_t version;              // bumped by every reference move
+  uint32_t k_issued;             // tiles whose K page this CTA's producer has issued (orders the V re-read behind it)
+  uint32_t trig[2][3];
+  float st_mref[64], st_ps[64], st_mprime[64];  // per-row lazy reference: max (log2 domain), P scale, mref + log2(ps)
+  float red1[2][2][64], red2[2][2][64], lred[4][64];
 };
-static_assert(sizeof(Small) <= 4096, "Small too large");
+static_assert(sizeof(Small) <= 5120, "Small too large");
+static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
 
 // Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4, 3 epilogue (indexed by
 // request)][tile < 64][event < 4]
 constexpr int kTraceTiles = 64;
-constexpr int kTraceRoles = 4;
+constexpr int kTraceRoles = 5;
 __device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
   if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
@@ -99,15 +108,12 @@ struct BtWindow {
   }
 };
 
-struct PendingPv {
-  uint32_t g, seg, nk;
-  bool first, last, valid;
-};
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     mla_decode_pair_kernel(const __grid_constant__ MlaParams p) {
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // round up to 1024 B by pointer arithmetic (an integer round trip would demote every access to generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_q = smem + kOffQ;
   uint8_t* s_k = smem + kOffK;
   uint8_t* s_v = smem + kOffV;
@@ -139,21 +145,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
     for (int i = 0; i < kKsStages; ++i) {
       mbar_init(&sm.ks_full[i], 1);
-      mbar_init(&sm.ks_empty[i], 8);  // the eight softmax warps
+      mbar_init(&sm.ks_empty[i], 4);  // the four warps of the softmax group that serves the tile
     }
     mbar_init(&sm.q_full, 2);
     mbar_init(&sm.q_empty, 1);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&sm.s_full[i], 1);
-      mbar_init(&sm.p_full[i], 9);   // the leader's 8 softmax warps + the peer's relay
-      mbar_init(&sm.p_relay[i], 8);
+    for (int i = 0; i < kSBufs; ++i) mbar_init(&sm.s_full[i], 1);
+    for (int i = 0; i < kPBufs; ++i) {
+      mbar_init(&sm.p_full[i], 5);   // the four warps of the leader's softmax group + the peer's relay
+      mbar_init(&sm.p_relay[i], 4);
       mbar_init(&sm.p_free[i], 1);
     }
+    for (int i = 0; i < 2; ++i) mbar_init(&sm.fin[i], 4);
     mbar_init(&sm.pv_done, 1);
     mbar_init(&sm.o_ready, 1);
     mbar_init(&sm.o_free, 9);
     mbar_init(&sm.o_relay, 8);
-    sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
+    for (int i = 0; i < 3; ++i) sm.trig[0][i] = sm.trig[1][i] = 0;
+    sm.version = 0;
+    sm.k_issued = 0;
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_q_nope);
     tma_prefetch_desc(&p.tm_q_rope);
@@ -170,7 +179,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
   if (warp == 0) {
     // ============================== TMA producer (both CTAs) ==============================
-    const uint64_t pol_last_use = policy_evict_first();
     const uint32_t q_full_l = mapa_u32(smem_u32(&sm.q_full), 0);
     uint32_t k_full_l[kKStages];
 #pragma unroll
@@ -222,39 +230,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             for (int c = 0; c < 4; ++c) tma_load_2d_pair(stage + c * 8192, &p.tm_k_nope, k_full_l[st], c * 128, tok0);
             tma_load_2d_pair(stage + 32768, &p.tm_k_rope, k_full_l[st], 0, tok0);
           }
-          if (tok_pf >= 0) {  // warm L2 for the page that will reuse this stage
+          if (tok_pf >= 0) {  // warm L2 for a page `pf` tiles ahead
+            if (p.pf_mode == 0) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tok_pf);
-            tma_prefetch_2d(&p.tm_k_rope, 0, tok_pf);
+              for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tok_pf);
+              tma_prefetch_2d(&p.tm_k_rope, 0, tok_pf);
+            } else if (p.pf_mode == 2) {  // the page's 32 KB of latent and 8 KB of rope are contiguous: two bulk prefetches
+              bulk_prefetch_l2(p.k_lora_base + (int64_t)tok_pf * 512, 64 * 512);
+              bulk_prefetch_l2(p.k_rope_base + (int64_t)tok_pf * 128, 64 * 128);
+            }
           }
         }
         __syncwarp();
-      };
-      // both pages of tile t, this CTA's two 128-dim output slices (+ the tile's k scales) -> V stage (local barrier);
-      // these bytes were just streamed through L2 as K by this CTA or its peer
-      auto load_v = [&](int t, uint32_t gt) {
-        const uint32_t st = gt % kVStages;
-        trace(tr, rank, 0, gt, 1);
-        mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
-        trace(tr, rank, 0, gt, 2);
-        const int blk0 = sg.start_block + 2 * t;
-        const int npages = min(2, sg.end_block - blk0);
-        const int tok0 = bw.get(blk0) * kPage;
-        const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
-        uint8_t* stage = s_v + st * kVStageBytes;
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192));
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d_hint(stage + j * 16384, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
-          if (npages > 1) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_2d_hint(stage + j * 16384 + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1,
-                               pol_last_use);
-          }
-        }
-        __syncwarp();
+        if (lane == 0) st_shared_volatile_u32(&sm.k_issued, gt + 1);
       };
       // k scales of both pages of tile t -> scale ring.  Their HBM latency (a separate array: no L2 warm-up by the K
       // stream) is paid kKsAhead tiles before the softmax needs them.
@@ -283,14 +271,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 #pragma unroll
         for (int c = 0; c < 4; ++c) tma_load_2d_pair(s_q + c * 8192, &p.tm_q_nope, q_full_l, c * 128, qrow);
         tma_load_2d_pair(s_q + 32768, &p.tm_q_rope, q_full_l, 0, qrow);
-        if (b < end_idx) {  // next request's Q rows of this CTA
-#pragma unroll
-          for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_q_nope, c * 128, qrow + p.M);
-          tma_prefetch_2d(&p.tm_q_rope, 0, qrow + p.M);
-        }
       }
       __syncwarp();
-      if (seg_i == 1) {  // first request of this part: tiles the steady-state prefetch (t + pf) will not reach
+      if (seg_i == 1 && p.pf_mode == 0) {  // first request of this part: tiles the steady-state prefetch (t + pf) will not reach
         for (int tp = kKStages; tp < pf && tp < sg.n_tiles; ++tp) {
           const int bp = sg.start_block + 2 * tp + (int)rank;
           if (bp < sg.end_block) {
@@ -305,18 +288,79 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
       }
       __syncwarp();
-      for (int t = 0; t < kKsAhead && t < sg.n_tiles; ++t) load_ks(t, g + t);
-      load_k(0, g);
+      load_k(0, g);  // Q and the first K page (+ its scales) are what the first Q.K^T waits for: they go first
+      load_ks(0, g);
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
         bw.advance_to(sg.start_block + 2 * t, lane);
         if (t + 1 < sg.n_tiles) load_k(t + 1, g + 1);
+        if (t == 0)
+          for (int i = 1; i < kKsAhead && i < sg.n_tiles; ++i) load_ks(i, g + i);
+        if (b < end_idx && t == (sg.n_tiles > 4 ? 4 : 0)) {  // next request's Q rows of this CTA -> L2, off the start-up path
+          if (elect_one()) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_q_nope, c * 128, qrow + p.M);
+            tma_prefetch_2d(&p.tm_q_rope, 0, qrow + p.M);
+          }
+          __syncwarp();
+        }
         if (t + kKsAhead < sg.n_tiles) load_ks(t + kKsAhead, g + kKsAhead);
+      }
+    }
+  } else if (warp == 2) {
+    // ============================== V producer (both CTAs) ==============================
+    // Its own warp: the V stage of tile t frees when P.V of tile t-2 retires, which must not hold back the K stream
+    // (Q.K^T runs ahead of P.V).
+    const uint64_t pol_last_use = policy_evict_first();
+    uint32_t g = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      if (sg.n_tiles == 0) continue;
+      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
+      BtWindow bw;
+      bw.init(bt, sg.start_block, sg.end_block, lane);
+      // both pages of tile t, this CTA's two 128-dim output slices (+ the tile's k scales) -> V stage (local barrier);
+      // these bytes were just streamed through L2 as K by this CTA or its peer
+      auto load_v = [&](int t, uint32_t gt) {
+        const uint32_t st = gt % kVStages;
+        trace(tr, rank, 0, gt, 1);
+        mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
+        // behind this tile's K issue: the same bytes then come out of L2 (or merge with the K fetch in flight) instead
+        // of competing with the K and Q loads for HBM at a request's start
+        for (uint32_t spins = 0; ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
+          if (spins > B200_WAIT_SPIN_LIMIT) __trap();
+          __nanosleep(64);
+        }
+        trace(tr, rank, 0, gt, 2);
+        const int blk0 = sg.start_block + 2 * t;
+        const int npages = min(2, sg.end_block - blk0);
+        const int tok0 = bw.get(blk0) * kPage;
+        const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
+        uint8_t* stage = s_v + st * kVStageBytes;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192));
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            tma_load_2d_hint(stage + j * 16384, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
+          if (npages > 1) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tma_load_2d_hint(stage + j * 16384 + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1,
+                               pol_last_use);
+          }
+        }
+        __syncwarp();
+      };
+      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+        bw.advance_to(sg.start_block + 2 * t, lane);
         load_v(t, g);
       }
     }
   } else if (warp == 1) {
     if (rank == 0) {
       // ============================== UMMA issuer (leader CTA) ==============================
+      // Two cursors walk the part's tiles: Q.K^T runs ahead of P.V by up to kSBufs - 1 tiles (S is kSBufs-buffered in
+      // TMEM), so the next tiles' scores are ready the moment a softmax group publishes P; whichever of the two has
+      // its operands ready is issued, P.V first.
       constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
       constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
       constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
@@ -325,89 +369,132 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       const uint64_t d_vmn = make_smem_desc(0, 16384, 1024, SWZ_128B);    // V: MN-major view of the token rows
       auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
 
-      auto issue_pv = [&](const PendingPv& pv) {
-        const uint32_t buf = pv.g & 1, vst = pv.g % kVStages;
-        trace(tr, rank, 1, pv.g, 2);
-        mbar_wait_cluster(&sm.p_full[buf], (pv.g >> 1) & 1);  // P written and V landed in both CTAs
-        if (pv.first && pv.seg > 0) mbar_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
-        tc_fence_after();
-        if (elect_one()) {
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-              if (s < (int)pv.nk)
-                umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
-                             with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
-                             !(pv.first && s == 0));
-          umma_commit_pair(&sm.v_empty[vst], 3);
-          umma_commit_pair(&sm.p_free[buf], 3);
-          umma_commit_pair(&sm.pv_done, 3);
-          if (pv.last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
-        }
-        __syncwarp();
-        trace(tr, rank, 1, pv.g, 3);
+      struct Cursor {
+        int b, t;
+        uint32_t g, seg;
+        Segment sg;
+        bool active;
       };
+      auto seek = [&](Cursor& c) {  // position on the next request of the part that has tiles
+        c.t = 0;
+        for (; c.b <= end_idx; ++c.b) {
+          c.sg = make_segment(p, c.b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+          if (c.sg.n_tiles > 0) return;
+        }
+        c.active = false;
+      };
+      auto advance = [&](Cursor& c) {
+        ++c.g;
+        if (++c.t == c.sg.n_tiles) {
+          ++c.seg;
+          ++c.b;
+          seek(c);
+        }
+      };
+      Cursor qk, pv;
+      qk.b = pv.b = begin_idx;
+      qk.g = pv.g = 0;
+      qk.seg = pv.seg = 0;
+      qk.active = pv.active = true;
+      seek(qk);
+      seek(pv);
 
-      uint32_t g = 0, seg = 0;
-      PendingPv pend;
-      pend.valid = false;
-      for (int b = begin_idx; b <= end_idx; ++b) {
-        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
-        if (sg.n_tiles == 0) continue;
-        mbar_wait_cluster(&sm.q_full, seg & 1);
-        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          const uint32_t kst = g % kKStages, buf = g & 1;
-          trace(tr, rank, 1, g, 0);
-          mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
-          tc_fence_after();
-          const uint32_t stage = k_addr + kst * kKStageBytes;
-          const uint32_t d = tmem + kColS + buf * 64;
-          if (elect_one()) {
+      uint32_t idle = 0, k_seen = 0xffffffffu;
+      while (pv.active) {
+        bool did = false;
+        // ---- P.V of the oldest unpublished tile ----
+        {
+          const uint32_t buf = pv.g % kPBufs, vst = pv.g % kVStages;
+          bool ready = mbar_test_wait_cluster(&sm.p_full[buf], (pv.g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
+          if (ready) ready = mbar_test_wait(&sm.v_land[vst], (pv.g / kVStages) & 1);          // V landed here
+          if (ready && pv.t == 0 && pv.seg > 0) ready = mbar_test_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
+          if (ready) {
+            tc_fence_after();
+            const int tile_start = (pv.sg.start_block + 2 * pv.t) * kPage;
+            const int nk = (min(kTileTokens, pv.sg.valid_end - tile_start) + 31) / 32;
+            const bool first = pv.t == 0, last = pv.t == pv.sg.n_tiles - 1;
+            if (elect_one()) {
 #pragma unroll
-            for (int c = 0; c < 4; ++c)
+              for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                  if (s < nk)
+                    umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
+                                 with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
+                                 !(first && s == 0));
+              umma_commit_pair(&sm.v_empty[vst], 3);
+              umma_commit_pair(&sm.p_free[buf], 3);
+              umma_commit_pair(&sm.pv_done, 3);
+              if (last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
+            }
+            __syncwarp();
+            trace(tr, rank, 1, pv.g, 3);
+            advance(pv);
+            did = true;
+          }
+        }
+        // ---- Q.K^T of the next tile, while an S buffer is free ----
+        if (!did && qk.active && qk.g < pv.g + kSBufs) {
+          const uint32_t kst = qk.g % kKStages, sb = qk.g % kSBufs;
+          bool ready = mbar_test_wait_cluster(&sm.k_full[kst], (qk.g / kKStages) & 1);
+          if (ready && k_seen != qk.g) {
+            k_seen = qk.g;
+            trace(tr, rank, 1, qk.g, 2);  // first sight of the landed K page
+          }
+          if (ready) ready = mbar_test_wait(&sm.ks_full[qk.g % kKsStages], (qk.g / kKsStages) & 1);  // s_full vouches for it
+          if (ready && qk.t == 0) ready = mbar_test_wait_cluster(&sm.q_full, qk.seg & 1);
+          if (ready) {
+            trace(tr, rank, 1, qk.g, 0);
+            tc_fence_after();
+            const uint32_t stage = k_addr + kst * kKStageBytes;
+            const uint32_t d = tmem + kColS + sb * 64;
+            const bool last = qk.t == qk.sg.n_tiles - 1;
+            if (elect_one()) {
+#pragma unroll
+              for (int c = 0; c < 4; ++c)
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                  umma_f8_pair(d, with_addr(d_kmaj, q_addr + c * 8192 + s * 32), with_addr(d_kmaj, stage + c * 8192 + s * 32),
+                               idesc_qk8, (c | s) != 0);
 #pragma unroll
               for (int s = 0; s < 4; ++s)
-                umma_f8_pair(d, with_addr(d_kmaj, q_addr + c * 8192 + s * 32), with_addr(d_kmaj, stage + c * 8192 + s * 32),
-                             idesc_qk8, (c | s) != 0);
-#pragma unroll
-            for (int s = 0; s < 4; ++s)
-              umma_f16_pair(d, with_addr(d_kmaj, q_addr + 32768 + s * 32), with_addr(d_kmaj, stage + 32768 + s * 32),
-                            idesc_qk16, 1);
-            umma_commit_pair(&sm.s_full[buf], 3);
-            umma_commit_pair(&sm.k_empty[kst], 3);
-            if (t == sg.n_tiles - 1) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
+                umma_f16_pair(d, with_addr(d_kmaj, q_addr + 32768 + s * 32), with_addr(d_kmaj, stage + 32768 + s * 32),
+                              idesc_qk16, 1);
+              umma_commit_pair(&sm.s_full[sb], 3);
+              umma_commit_pair(&sm.k_empty[kst], 3);
+              if (last) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
+            }
+            __syncwarp();
+            trace(tr, rank, 1, qk.g, 1);
+            advance(qk);
+            did = true;
           }
-          __syncwarp();
-          trace(tr, rank, 1, g, 1);
-          // P.V of the previous tile goes behind this tile's Q.K^T: the softmax of tile g overlaps it
-          if (pend.valid) issue_pv(pend);
-          const int tile_start = (sg.start_block + 2 * t) * kPage;
-          pend.g = g;
-          pend.seg = seg;
-          pend.first = (t == 0);
-          pend.last = (t == sg.n_tiles - 1);
-          pend.nk = (uint32_t)((min(kTileTokens, sg.valid_end - tile_start) + 31) / 32);
-          pend.valid = true;
         }
-        ++seg;
+        if (did) {
+          idle = 0;
+        } else {
+          if (++idle > B200_WAIT_SPIN_LIMIT) __trap();
+          __nanosleep(32);
+        }
       }
-      if (pend.valid) issue_pv(pend);
     } else {
       // ============================== relay (non-leader CTA) ==============================
       // This CTA's softmax warps hand P / O over on LOCAL barriers (ordered with their shared-memory stores); once a
       // phase completes here -- the stores are then performed in this SM's shared memory -- one remote arrive tells the
       // leader.  A direct remote arrive from the softmax warps would need a cluster-scope release (a cluster-wide
       // membar per tile, measured at a third of their time); with CTA-scope release the arrive overtakes the stores.
-      const uint32_t p_full_l[2] = {mapa_u32(smem_u32(&sm.p_full[0]), 0), mapa_u32(smem_u32(&sm.p_full[1]), 0)};
+      uint32_t p_full_l[kPBufs];
+#pragma unroll
+      for (int i = 0; i < kPBufs; ++i) p_full_l[i] = mapa_u32(smem_u32(&sm.p_full[i]), 0);
       const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
       uint32_t g = 0, seg = 0;
       for (int b = begin_idx; b <= end_idx; ++b) {
         const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
         if (sg.n_tiles == 0) continue;
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          mbar_wait(&sm.p_relay[g & 1], (g >> 1) & 1);
-          if (elect_one()) mbar_arrive_cluster(p_full_l[g & 1]);
+          mbar_wait(&sm.p_relay[g % kPBufs], (g / kPBufs) & 1);
+          mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);  // the forwarded arrival also vouches for this CTA's V
+          if (elect_one()) mbar_arrive_cluster(p_full_l[g % kPBufs]);
           __syncwarp();
         }
         mbar_wait(&sm.o_relay, seg & 1);
@@ -418,174 +505,262 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
   } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue (both CTAs) ==============================
-    const int st_id = tid - 128;              // 0 .. 255 within the softmax group
+    // Two groups of four warps ping-pong over the tiles: group 0 (warps 4-7) serves the tiles whose S / P buffer is 0,
+    // group 1 (warps 8-11) buffer 1.  A group's per-tile chain (barrier waits, TMEM load, vote, publish) then overlaps
+    // the other group's exponentials instead of idling the SM.  Under the lazy reference a tile's P does not depend
+    // on its predecessor unless a reference move ("trigger") happens, so the groups only meet at a per-tile hand-off
+    // (sm.fin) that orders the moves: tile g is published after tile g-1 is final, and a group that computed under a
+    // reference which has since moved (sm.version) recomputes.
+    const int st_id = tid - 128;              // 0 .. 255 over both groups
+    const int grp = (warp - 4) >> 2;          // S / P buffer (tile parity) this warp serves
+    const int gtid = st_id & 127;             // thread within the group
+    const uint32_t gbar = 2 + grp;            // the group's named barrier (128 threads)
     const int quad = warp & 3;                // TMEM lane quadrant of this warp
-    const int ch = (warp - 4) >> 2;           // which 32 of the 64 S columns
     const int tl = quad * 32 + lane;          // TMEM lane
     const int row = tl & 63;                  // q row within this CTA
     const int page = tl >> 6;                 // lanes 64-127 hold the second half of the N columns = the peer's page
-    const int col0 = ch * 32;
-    const int slot = page * 2 + ch;           // which quarter of the row this thread holds
+    const int ch = grp;                       // epilogue only: which 64 of the 128 O columns of each d half
+    const int slot = page * 2 + ch;           // epilogue only: which quarter of the staged row this thread fills
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const bool row_valid = row < n_valid_q;
     const int grow = q_row0 + row;            // row within the request's M rows
-    uint32_t g = 0, o_seg = 0;
+    uint32_t g0 = 0, o_seg = 0;               // g0: global index of the request's first tile
+    uint32_t n_mine = 0;                      // tiles this group has served (trigger-flag ring)
 
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
-      // ---- per-request state (identical in the four threads of a row) ----
+      // ---- per-request state ----
       const float f = row_valid ? __ldg(p.q_scale + (int64_t)b * p.M + grow) * p.scale_log2 : 0.f;
       int lim = 0;
       if (row_valid) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, grow), sg.end_block * kPage) : sg.valid_end;
-      float mref = kMInit, ps = 1.f, mprime = kMInit, lsum = 0.f;
-      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lred are done
+      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lred / the row state are done
+      if (grp == 0 && page == 0) {
+        sm.st_mref[row] = kMInit;
+        sm.st_ps[row] = 1.f;
+        sm.st_mprime[row] = kMInit;
+      }
+      named_bar_sync(1, kSmThreads);
+      float mprime = kMInit, lsum = 0.f;  // this thread's view of the row reference; lsum is in units of 2^-mprime
+      uint32_t ver = ld_shared_volatile_u32(&sm.version);
 
-      for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-        const uint32_t buf = g & 1, vst = g % kVStages;
-        const int tile_start = (sg.start_block + 2 * t) * kPage;
-        const int tok_base = tile_start + page * 64 + col0;  // first token of this thread's 32 columns
-        const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
-        if (st_id == 0) sm.trig[(g + 1) % 3] = 0;
-
-        if (g == 0 || t == 0) trace(tr && warp == 4, rank, 3, o_seg, 3);
-        const uint32_t kst = g % kKsStages;
-        mbar_wait(&sm.ks_full[kst], (g / kKsStages) & 1);  // k scales of the tile (loaded kKsAhead tiles ago)
-        float kf[32];                                       // k_scale, later f * k_scale
-        {
-          const float4* src = reinterpret_cast<const float4*>(s_ks + kst * 128 + page * 64 + col0);
+      // This lane's 64 S columns under the reference `mp`, 16 columns at a time (a compact, not unrolled loop: the
+      // kernel's hot code stays inside the instruction cache): P' = exp2(s f k - mp) k -> e4m3 straight into the P
+      // tile (K-major, 128-byte swizzle; nobody reads it before this group arrives on p_full), row-sum and overflow
+      // contributions.  Packed fp32x2 arithmetic: per element pair 4 FMA-pipe instructions, 2 MUFU.EX2, 1 F2FP.
+      auto tile_pass = [&](uint32_t s_addr, const float* ks_tile, int tile_start, bool need_mask, float mp, uint8_t* prow,
+                           float& acc, float& vmax) {
+        const float2 f2 = make_float2(f, f), nmp2 = make_float2(-mp, -mp), one2 = make_float2(1.f, 1.f);
+        float2 acc2 = make_float2(0.f, 0.f);
+        const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
+        const int nvalid = lim - (tile_start + page * 64);  // columns of this lane below the mask border
+        auto chunk = [&](float* x, int c16) {
+          float kf[16];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 v4 = src[i];
+          for (int i = 0; i < 4; ++i) {
+            const float4 v4 = ksrc[c16 * 4 + i];
             kf[4 * i] = v4.x, kf[4 * i + 1] = v4.y, kf[4 * i + 2] = v4.z, kf[4 * i + 3] = v4.w;
           }
-        }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
-        if (need_mask) {
-#pragma unroll
-          for (int c = 0; c < 32; ++c)
-            if (!(tok_base + c < lim)) kf[c] = 0.f;
-        }
-        trace(tr && warp == 4, rank, 2, g, 0);
-        mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
-        trace(tr && warp == 4, rank, 2, g, 1);
-        tc_fence_after();
-        float x[32];
-        const uint32_t s_addr = tmem + kColS + buf * 64 + col0 + lane_addr;
-        tmem_ld<32>(s_addr, x);
-        tmem_wait_ld();
-
-        uint32_t pk[8];
-        bool trigger = (t == 0);
-        if (!trigger) {
-          // ---- fast path: reuse the current reference ----
-          float vmax = 0.f, acc = 0.f;
           if (!need_mask) {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              const float u = ex2_approx(fmaf(x[c], f * kf[c], -mprime));
-              acc += u;
-              x[c] = u * kf[c];
-              vmax = fmaxf(vmax, x[c]);
+            for (int c = 0; c < 16; c += 2) {
+              const float2 k2 = make_float2(kf[c], kf[c + 1]);
+              const float2 a2 = fma2(make_float2(x[c], x[c + 1]), mul2(f2, k2), nmp2);
+              const float2 u2 = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
+              acc2 = fma2(u2, one2, acc2);
+              const float2 p2 = mul2(u2, k2);
+              x[c] = p2.x, x[c + 1] = p2.y;
+              vmax = fmaxf(vmax, fmaxf(p2.x, p2.y));
             }
           } else {
 #pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              float arg = fmaf(x[c], f * kf[c], -mprime);
-              if (!(tok_base + c < lim)) arg = -INFINITY;
+            for (int c = 0; c < 16; ++c) {
+              const bool ok = c16 * 16 + c < nvalid;
+              const float kc = ok ? kf[c] : 0.f;
+              const float arg = ok ? fmaf(x[c], f * kc, -mp) : -INFINITY;
               const float u = ex2_approx(arg);
-              acc += u;
-              x[c] = u * kf[c];
+              acc2.x += u;
+              x[c] = u * kc;
               vmax = fmaxf(vmax, x[c]);
             }
           }
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
-          const bool over = vmax > 448.f;
-          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[g % 3] = 1;
-          named_bar_sync(1, kSmThreads);
-          trigger = sm.trig[g % 3] != 0;
-          if (!trigger) lsum += acc;
+          *reinterpret_cast<uint4*>(prow + (((page * 4 + c16) ^ (row & 7)) << 4)) =
+              make_uint4(cvt_e4m3x4(x[0], x[1], x[2], x[3]), cvt_e4m3x4(x[4], x[5], x[6], x[7]),
+                         cvt_e4m3x4(x[8], x[9], x[10], x[11]), cvt_e4m3x4(x[12], x[13], x[14], x[15]));
+        };
+        // two register sets: the TMEM load of the next 16 columns is in flight while this one is processed
+        float xa[16], xb[16];
+        tmem_ld16(s_addr, reinterpret_cast<uint32_t*>(xa));
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; c16 += 2) {
+          tmem_wait_ld();
+          tmem_ld16(s_addr + (c16 + 1) * 16, reinterpret_cast<uint32_t*>(xb));
+          chunk(xa, c16);
+          tmem_wait_ld();
+          if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
+          chunk(xb, c16 + 1);
         }
-        if (trigger) {
-          // ---- slow path: move the reference (m_ref, p_scale), rescale O and L ----
-          if (t != 0) {
-            tmem_ld<32>(s_addr, x);
-            tmem_wait_ld();
-          }
-          float lmax = -INFINITY;
+        acc += acc2.x + acc2.y;
+      };
+      // max over this lane's 64 columns of the scaled logits z = s f k, and of the k scales of its unmasked columns
+      auto tile_max = [&](uint32_t s_addr, const float* ks_tile, int tile_start, float& ksmax) {
+        const float* ksrc = ks_tile + page * 64;
+        const int nvalid = lim - (tile_start + page * 64);
+        float r = -INFINITY;
+        ksmax = 0.f;
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; ++c16) {
+          float x[16];
+          tmem_ld16(s_addr + c16 * 16, reinterpret_cast<uint32_t*>(x));
+          tmem_wait_ld();
 #pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            float z = x[c] * (f * kf[c]);
-            if (!(tok_base + c < lim)) z = -INFINITY;
-            x[c] = z;
-            lmax = fmaxf(lmax, z);
+          for (int c = 0; c < 16; ++c) {
+            const float kfc = ksrc[c16 * 16 + c];
+            if (c16 * 16 + c < nvalid) {
+              r = fmaxf(r, x[c] * (f * kfc));
+              ksmax = fmaxf(ksmax, kfc);
+            }
           }
-          sm.red1[slot][row] = lmax;
-          named_bar_sync(1, kSmThreads);
-          const float cm = fmaxf(fmaxf(sm.red1[0][row], sm.red1[1][row]), fmaxf(sm.red1[2][row], sm.red1[3][row]));
-          const float m_new = fmaxf(mref, cm);
-          float lp = 0.f;
-#pragma unroll
-          for (int c = 0; c < 32; ++c) lp = fmaxf(lp, ex2_approx(x[c] - m_new) * kf[c]);
-          sm.red2[slot][row] = lp;
-          named_bar_sync(1, kSmThreads);
-          float pmax = fmaxf(fmaxf(sm.red2[0][row], sm.red2[1][row]), fmaxf(sm.red2[2][row], sm.red2[3][row]));
-          pmax = fmaxf(pmax, kPMin);
+        }
+        return r;
+      };
+
+      const int t_first = (int)((grp ^ g0) & 1u);  // this group's first tile of the request
+      for (int t = t_first; t < sg.n_tiles; t += 2, ++n_mine) {
+        const uint32_t g = g0 + (uint32_t)t;
+        const uint32_t buf = g % kPBufs, vst = g % kVStages, kst = g % kKsStages;
+        const int tile_start = (sg.start_block + 2 * t) * kPage;
+        const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
+        const bool tr_w = tr && quad == 0;
+        if (gtid == 0) sm.trig[grp][(n_mine + 1) % 3] = 0;
+        if (t <= 1) trace(tr_w, rank, 3, o_seg, 3);
+        trace(tr_w, rank, 4, g, 3);
+
+        // No wait on ks_full: the UMMA issuer saw the tile's k scales land before it issued this tile's Q.K^T, so
+        // s_full vouches for them too.
+        const float* ks_tile = s_ks + kst * 128;
+        const uint32_t sb = g % kSBufs;
+        const uint32_t s_addr = tmem + kColS + sb * 64 + lane_addr;
+        uint8_t* prow = s_p + buf * kPBytes + row * 128;
+        // the first two tiles of a request always see a reference move: wait for the predecessor before computing
+        bool fin_waited = false;
+        if (t <= 1 && g > 0) {
+          mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          fin_waited = true;
+        }
+        // No wait on p_free either: Q.K^T of tile g is issued after P.V of tile g - kSBufs and the tensor pipe retires
+        // in order, so s_full(g) implies that P tile g % kPBufs (kPBufs == kSBufs) is no longer being read.
+        trace(tr_w, rank, 2, g, 0);
+        mbar_wait(&sm.s_full[sb], (g / kSBufs) & 1);
+        trace(tr_w, rank, 2, g, 1);
+        tc_fence_after();
+
+        float acc = 0.f;
+        bool trigger = (t == 0);
+        while (!trigger) {
+          // ---- fast path: the current reference ----
+          const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
+          if (v_now != ver) {  // the reference moved since this thread last looked: re-base the running sum
+            const float mp_new = ld_shared_volatile_f32(&sm.st_mprime[row]);
+            lsum *= exp2f(mprime - mp_new);
+            mprime = mp_new;
+            ver = v_now;
+          }
+          float vmax = 0.f;
+          acc = 0.f;
+          tile_pass(s_addr, ks_tile, tile_start, need_mask, mprime, prow, acc, vmax);
+          trace(tr_w, rank, 4, g, 0);
+          if (!fin_waited) {
+            if (g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);  // tile g-1 is final
+            fin_waited = true;
+          }
+          trace(tr_w, rank, 4, g, 1);
+          if (ld_shared_volatile_u32(&sm.version) != ver) continue;  // computed under a reference that has moved
+          const bool over = vmax > 448.f;
+          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[grp][n_mine % 3] = 1;
+          named_bar_sync(gbar, 128);
+          trigger = sm.trig[grp][n_mine % 3] != 0;
+          break;
+        }
+        if (!trigger) {
+          lsum += acc;
+        } else {
+          // ---- slow path: move the reference (m_ref, p_scale) of every row, rescale O and the running sums ----
+          if (!fin_waited && g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          {
+            const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
+            if (v_now != ver) {
+              const float mp_new = ld_shared_volatile_f32(&sm.st_mprime[row]);
+              lsum *= exp2f(mprime - mp_new);
+              mprime = mp_new;
+              ver = v_now;
+            }
+          }
+          // New reference: m_new = the row's running maximum of the scaled logits; p_scale from an upper bound of
+          // P' = exp2(z - m_new) * k_scale <= max k_scale of the row's unmasked tokens in this tile (one pass over S
+          // instead of two; the bound costs at most the k-scale spread of the tile in e4m3 headroom).
+          float ksmax;
+          sm.red1[grp][page][row] = tile_max(s_addr, ks_tile, tile_start, ksmax);
+          sm.red2[grp][page][row] = ksmax;
+          named_bar_sync(gbar, 128);
+          const float m_old = ld_shared_volatile_f32(&sm.st_mref[row]), ps_old = ld_shared_volatile_f32(&sm.st_ps[row]);
+          const float m_new = fmaxf(m_old, fmaxf(sm.red1[grp][0][row], sm.red1[grp][1][row]));
+          const float pmax = fmaxf(fmaxf(sm.red2[grp][0][row], sm.red2[grp][1][row]), kPMin);
           const float ps_new = pmax * (kHeadroom / 448.f);
-          const float fac = exp2f(mref - m_new) * (ps / ps_new);
-          mref = m_new;
-          ps = ps_new;
-          mprime = m_new + log2f(ps_new);
+          const float fac = exp2f(m_old - m_new) * (ps_old / ps_new);
+          const float mp_new = m_new + log2f(ps_new);
           if (t != 0) {
-            // every P.V up to the previous tile must have landed in O before it is rescaled
+            // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
+            // last one issued: tile g is not published yet).  pv_done completes once per tile and Q.K^T runs ahead of
+            // P.V: first make sure P.V of tile g-2 has retired (its p_free, at most one phase behind), so that the
+            // parity wait on pv_done cannot alias the phase before it.
+            if (g >= 2) mbar_wait(&sm.p_free[(g - 2) % kPBufs], ((g - 2) / kPBufs) & 1);
             mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
+#pragma unroll 1
+            for (int c8 = 0; c8 < 8; ++c8) {
+              float o[32];
+              const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
+              tmem_ld<32>(a, o);
+              tmem_wait_ld();
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
-#pragma unroll
-              for (int hh = 0; hh < 2; ++hh) {
-                float o[32];
-                const uint32_t a = tmem + kColO + j * 128 + ch * 64 + hh * 32 + lane_addr;
-                tmem_ld<32>(a, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) o[k] *= fac;
-                tmem_st<32>(a, o);
-              }
+              for (int k = 0; k < 32; ++k) o[k] *= fac;
+              tmem_st<32>(a, o);
+            }
             tmem_wait_st();
             lsum *= fac;
           }
-#pragma unroll
-          for (int c = 0; c < 32; ++c) {
-            const float u = ex2_approx(x[c] - mprime);
-            lsum += u;
-            x[c] = u * kf[c];
+          mprime = mp_new;
+          if (page == 0) {
+            sm.st_mref[row] = m_new;
+            sm.st_ps[row] = ps_new;
+            sm.st_mprime[row] = mp_new;
           }
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) pk[c / 4] = cvt_e4m3x4(x[c], x[c + 1], x[c + 2], x[c + 3]);
+          tc_fence_before();
+          named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
+          ver += 1;
+          if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
+          float vmax = 0.f;
+          acc = 0.f;
+          tile_pass(s_addr, ks_tile, tile_start, true, mprime, prow, acc, vmax);
+          lsum += acc;
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
 
-        trace(tr && warp == 4, rank, 2, g, 2);
-        // ---- publish P (A operand of P.V: [q row][token], K-major, 128-byte swizzle) ----
-        mbar_wait(&sm.p_free[buf], ((g >> 1) & 1) ^ 1);  // P.V of tile g-2 has retired
-        mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);  // this CTA's V slices have landed (p_full vouches for them)
-        {
-          uint8_t* prow = s_p + buf * kPBytes + row * 128;
-          const int c16 = (page * 64 + col0) >> 4;  // first of this thread's two 16-byte chunks
-          *reinterpret_cast<uint4*>(prow + (((c16) ^ (row & 7)) << 4)) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-          *reinterpret_cast<uint4*>(prow + (((c16 + 1) ^ (row & 7)) << 4)) = make_uint4(pk[4], pk[5], pk[6], pk[7]);
-        }
+        trace(tr_w, rank, 2, g, 2);
+        // ---- publish P ----
+        trace(tr_w, rank, 4, g, 2);
         // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
         // Reference: fill_oob_V, splitkv_mla.cu:698-721.
-        if (tile_start + kTileTokens > sg.valid_end && st_id < kTileTokens) {
+        if (tile_start + kTileTokens > sg.valid_end) {
+          mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);
           const int valid_in_tile = sg.valid_end - tile_start;
           const int nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
-          if (st_id >= valid_in_tile && st_id < nk * 32) {
+          if (gtid >= valid_in_tile && gtid < nk * 32) {
             uint8_t* stage = s_v + vst * kVStageBytes;
 #pragma unroll
             for (int j = 0; j < 2; ++j) {
-              uint4* vr = reinterpret_cast<uint4*>(stage + j * 16384 + st_id * 128);
+              uint4* vr = reinterpret_cast<uint4*>(stage + j * 16384 + gtid * 128);
 #pragma unroll
               for (int k = 0; k < 8; ++k) vr[k] = make_uint4(0, 0, 0, 0);
             }
@@ -594,10 +769,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(rank == 0 ? &sm.p_full[buf] : &sm.p_relay[buf]);
-        trace(tr && warp == 4, rank, 2, g, 3);
+        if (lane == 0) {
+          mbar_arrive(rank == 0 ? &sm.p_full[buf] : &sm.p_relay[buf]);
+          mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the other group may publish tile g+1
+        }
+        trace(tr_w, rank, 2, g, 3);
       }
+      g0 += (uint32_t)sg.n_tiles;
 
+      // both groups have published their last tile: bring every thread's running sum to the request's final reference
+      named_bar_sync(1, kSmThreads);
+      {
+        const float mp_fin = ld_shared_volatile_f32(&sm.st_mprime[row]);
+        lsum *= exp2f(mprime - mp_fin);
+        mprime = mp_fin;
+      }
       // ---- epilogue of this request: O / L -> out (or split partials) ----
       trace(tr && warp == 4, rank, 3, o_seg, 0);
       sm.lred[slot][row] = lsum;

@@ -81,6 +81,22 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
 
+// shared-memory accesses the compiler must not cache or reorder (state polled across warp groups); shared-window
+// addressing, unlike a volatile generic pointer, which compiles to generic LD / ST
+__device__ __forceinline__ uint32_t ld_shared_volatile_u32(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.volatile.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ float ld_shared_volatile_f32(const float* p) {
+  float v;
+  asm volatile("ld.volatile.shared::cta.f32 %0, [%1];" : "=f"(v) : "r"(smem_u32(p)) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_shared_volatile_u32(uint32_t* p, uint32_t v) {
+  asm volatile("st.volatile.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -119,6 +135,10 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
           smem_u32(smem_dst)),
       "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
+}
+// L2 prefetch of a contiguous byte range (bytes multiple of 16, address 16-B aligned)
+__device__ __forceinline__ void bulk_prefetch_l2(const void* gsrc, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gsrc), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ uint64_t policy_evict_first() {
   uint64_t p;
@@ -295,6 +315,18 @@ __device__ __forceinline__ bool mbar_try_wait_cluster(uint64_t* bar, uint32_t pa
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// non-blocking probe with cluster-scope acquire
+__device__ __forceinline__ bool mbar_test_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
       : "r"(smem_u32(bar)), "r"(parity)

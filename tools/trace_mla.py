@@ -43,9 +43,9 @@ for i in range(1, len(outs)):
             bb, min(hs), max(hs), len(hs), half, quads, float(dm), float(ld), blocks))
 L = _lib.lib()
 T = 64
-buf = np.zeros(2 * 4 * T * 4, dtype=np.uint64)
+buf = np.zeros(2 * 5 * T * 4, dtype=np.uint64)
 _lib.check(L.b200_mla_read_trace(buf.ctypes.data, buf.size), "read_trace")
-tr = buf.reshape(2, 4, T, 4).astype(np.int64)
+tr = buf.reshape(2, 5, T, 4).astype(np.int64)
 for rank in range(2):
     t0 = tr[rank, 1, 0, 0] if rank == 0 else tr[rank, 0, 0, 0]
     print("rank %d (cycles relative to first event; d = delta to previous tile)" % rank)
@@ -61,6 +61,14 @@ for rank in range(2):
         print(" %4d | %7d %7d %7d | %7d %7d %7d %7d | %7d %7d %7d %7d | %s" % (
             g, r[0, 0], r[0, 1], r[0, 2], r[1, 0], r[1, 1], r[1, 2], r[1, 3], r[2, 0], r[2, 1], r[2, 2], r[2, 3], per))
 
+    print(" softmax detail (deltas): tile | top->swait  swait->Srdy  Srdy->pass  pass->fin  fin->voted(computed)  computed->vland  vland->arrived")
+    for g in range(8, 24):
+        a = tr[rank, 2, g, :]; d = tr[rank, 4, g, :]
+        print("   %3d | %6d %6d %6d %6d %6d %6d %6d" % (g, a[0] - d[3], a[1] - a[0], d[0] - a[1], d[1] - d[0], a[2] - d[1], d[2] - a[2], a[3] - d[2]))
+    print(" K / MMA detail: tile | Kissue->Kseen  Kseen->QKstart  QKstart->QKissued  QKissued->Srdy(softmax)  PVissued - P arrived(this CTA)")
+    for g in range(8, 24):
+        pr = tr[rank, 0, g, :]; m = tr[rank, 1, g, :]; a = tr[rank, 2, g, :]
+        print("   %3d | %6d %6d %6d %6d %6d" % (g, m[2] - pr[0], m[0] - m[2], m[1] - m[0], a[1] - m[1], m[3] - a[3]))
     print(" request | epilogue: start  o_ready  stored | next request's first tile top (previous row's request)")
     for sgi in range(4):
         e = tr[rank, 3, sgi, :] - t0
