@@ -130,6 +130,8 @@ int b200_umma_pair_rate(int mode, int n, int iters, float* cycles_per_mma);
 
 /* Diagnostic: clock64 pipeline trace of the last CTA-pair MLA launch made with B200_MLA_TRACE set. */
 int b200_mla_read_trace(unsigned long long* out, int n);
+/* Diagnostic: per (part, CTA rank) globaltimer ns at entry / at the end of the softmax warps' work, same launch. */
+int b200_mla_read_part_times(unsigned long long* out, int n);
 
 #ifdef __cplusplus
 }

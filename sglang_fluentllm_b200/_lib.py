@@ -35,6 +35,7 @@ _SIGNATURES = {
     "b200_umma_pair_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
     "b200_umma_pair_lab": (c_int, [c_int, c_int, _P, _P, _P]),
     "b200_mla_read_trace": (c_int, [_P, c_int]),
+    "b200_mla_read_part_times": (c_int, [_P, c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
 

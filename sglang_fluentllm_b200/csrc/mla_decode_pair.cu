@@ -17,13 +17,19 @@
 //   every MMA reads at most 6 KB of operands per 64 tensor-core cycles, which is what lets the tensor pipe run near
 //   its issue rate (single-CTA SS MMAs at N <= 128 are operand-bandwidth bound, see b200_umma_rate).
 //
-//   Softmax threads own (q row, 32 token columns): the row maximum and sum are thread-local up to a 4-way exchange,
-//   q_scale is a register, k_scale a shared-memory broadcast.  Same lazy (m_ref, p_scale) reference as mla_decode.cu.
+//   Softmax: a thread owns (q row, 64 token columns = one page).  Two groups of four warps ping-pong over the tiles
+//   (group = tile parity); under the lazy (m_ref, p_scale) reference of mla_decode.cu a tile's P does not depend on
+//   its predecessor unless the reference moves, so the groups only meet at a per-tile hand-off (fin) and a version
+//   counter; a group that computed under a reference that has since moved recomputes.  The pass over S is a compact
+//   16-column loop (TMEM load double-buffered, packed fp32x2 arithmetic, e4m3 codes written straight into the P tile).
 //
-//   Warp roles per CTA (384 threads): warp 0 = TMA producer (K page -> leader barrier via cta_group::2 TMA, V halves +
-//   k scales -> local barrier), warp 1 = UMMA issuer (leader CTA only) + TMEM allocation, warps 4-11 = softmax /
-//   correction / epilogue (4 TMEM lane quadrants x 2 column halves).
-//   TMEM per CTA: S double-buffered (2 x 64 columns) + O (2 x 128 columns).
+//   Warp roles per CTA (384 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
+//   and the k-scale ring; warp 1 = UMMA issuer (leader CTA; static order ... P.V(g-1), Q.K^T(g+2), P.V(g) ..., i.e.
+//   Q.K^T runs three tiles ahead) or relay of the local P / O hand-offs (other CTA) + TMEM allocation; warp 2 = V
+//   producer; warp 3 idle; warps 4-11 = softmax / correction / epilogue.
+//   TMEM per CTA: 4 S tiles (4 x 64 columns) + O (2 x 128 columns) = 512 columns.
+//   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, 2 V stages x 32 KB, 4 P tiles x 8 KB (also the
+//   epilogue's staging tile), k-scale ring 4 KB, barriers / row state 5 KB.
 #include <string.h>
 
 #include "mla_common.cuh"
@@ -77,6 +83,7 @@ static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
 constexpr int kTraceTiles = 64;
 constexpr int kTraceRoles = 5;
 __device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
+__device__ unsigned long long g_part_cycles[2 * 128 * 2];  // [part < 128][rank]{globaltimer at entry, at exit} (ns)
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
   if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
 }
@@ -128,6 +135,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const int q_row0 = pair_row0 + 64 * (int)rank;
   const int n_valid_q = max(0, min(64, p.M - q_row0));
   const bool tr = (p.trace & 1) && part == 0 && blockIdx.y == 0 && lane == 0;
+  if ((p.trace & 1) && tid == 0 && part < 128 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_part_cycles[(part * 2 + rank) * 2] = t;
+  }
 
   const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
   const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
@@ -306,6 +318,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         if (t + kKsAhead < sg.n_tiles) load_ks(t + kKsAhead, g + kKsAhead);
       }
     }
+  } else if (warp == 3 && rank == 0 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
+    // diagnostic: when each K stage actually lands (first 60 tiles of part 0; the part has at least that many)
+    for (uint32_t g = 0; g < 40; ++g) {
+      mbar_wait_cluster(&sm.k_full[g % kKStages], (g / kKStages) & 1);
+      trace(lane == 0, rank, 0, g, 3);
+    }
+  } else if (warp == 3 && rank == 1 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
+    // diagnostic: when each V stage lands in the non-leader CTA
+    for (uint32_t g = 0; g < 40; ++g) {
+      mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);
+      trace(lane == 0, rank, 0, g, 3);
+    }
   } else if (warp == 2) {
     // ============================== V producer (both CTAs) ==============================
     // Its own warp: the V stage of tile t frees when P.V of tile t-2 retires, which must not hold back the K stream
@@ -326,7 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
         // behind this tile's K issue: the same bytes then come out of L2 (or merge with the K fetch in flight) instead
         // of competing with the K and Q loads for HBM at a request's start
-        for (uint32_t spins = 0; ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
+        for (uint32_t spins = 0; !(p.trace & 32) && ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
           if (spins > B200_WAIT_SPIN_LIMIT) __trap();
           __nanosleep(64);
         }
@@ -336,6 +360,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const int tok0 = bw.get(blk0) * kPage;
         const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
         uint8_t* stage = s_v + st * kVStageBytes;
+        if (p.trace & 8) {  // diagnostic (wrong results): no V traffic at all
+          if (elect_one()) mbar_arrive(&sm.v_land[st]);
+          __syncwarp();
+          return;
+        }
         if (elect_one()) {
           mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192));
 #pragma unroll
@@ -399,82 +428,71 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       seek(qk);
       seek(pv);
 
-      uint32_t idle = 0, k_seen = 0xffffffffu;
+      // Static issue order with blocking waits (polling several barriers from this warp cost more than it bought):
+      // Q.K^T runs kQkLead tiles ahead of P.V, i.e. ... P.V(g-1), Q.K^T(g+2), P.V(g), Q.K^T(g+3) ...; the scores of
+      // tile g+2 are issued when tile g-1 is published, about half a softmax-group period before the group that
+      // publishes tile g needs them.  At a request boundary the old request's P.V go first (the new request's Q and
+      // K stream would hold them, and with them the epilogue, back).
+      constexpr uint32_t kQkLead = 3;
+      static_assert(kQkLead < kSBufs, "S tile g + kQkLead must not overwrite one that is still being read");
       while (pv.active) {
-        bool did = false;
-        // ---- P.V of the oldest unpublished tile ----
-        {
-          const uint32_t buf = pv.g % kPBufs, vst = pv.g % kVStages;
-          bool ready = mbar_test_wait_cluster(&sm.p_full[buf], (pv.g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
-          if (ready) ready = mbar_test_wait(&sm.v_land[vst], (pv.g / kVStages) & 1);          // V landed here
-          if (ready && pv.t == 0 && pv.seg > 0) ready = mbar_test_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
-          if (ready) {
-            tc_fence_after();
-            const int tile_start = (pv.sg.start_block + 2 * pv.t) * kPage;
-            const int nk = (min(kTileTokens, pv.sg.valid_end - tile_start) + 31) / 32;
-            const bool first = pv.t == 0, last = pv.t == pv.sg.n_tiles - 1;
-            if (elect_one()) {
-#pragma unroll
-              for (int j = 0; j < 2; ++j)
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                  if (s < nk)
-                    umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
-                                 with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
-                                 !(first && s == 0));
-              umma_commit_pair(&sm.v_empty[vst], 3);
-              umma_commit_pair(&sm.p_free[buf], 3);
-              umma_commit_pair(&sm.pv_done, 3);
-              if (last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
-            }
-            __syncwarp();
-            trace(tr, rank, 1, pv.g, 3);
-            advance(pv);
-            did = true;
-          }
-        }
-        // ---- Q.K^T of the next tile, while an S buffer is free ----
-        if (!did && qk.active && qk.g < pv.g + kSBufs) {
+        const uint32_t lead = (p.trace & 16) ? 2u : kQkLead;
+        const bool qk_turn = qk.active && qk.g < pv.g + lead && !(qk.t == 0 && qk.seg > pv.seg);
+        if (qk_turn) {
           const uint32_t kst = qk.g % kKStages, sb = qk.g % kSBufs;
-          bool ready = mbar_test_wait_cluster(&sm.k_full[kst], (qk.g / kKStages) & 1);
-          if (ready && k_seen != qk.g) {
-            k_seen = qk.g;
-            trace(tr, rank, 1, qk.g, 2);  // first sight of the landed K page
-          }
-          if (ready) ready = mbar_test_wait(&sm.ks_full[qk.g % kKsStages], (qk.g / kKsStages) & 1);  // s_full vouches for it
-          if (ready && qk.t == 0) ready = mbar_test_wait_cluster(&sm.q_full, qk.seg & 1);
-          if (ready) {
-            trace(tr, rank, 1, qk.g, 0);
-            tc_fence_after();
-            const uint32_t stage = k_addr + kst * kKStageBytes;
-            const uint32_t d = tmem + kColS + sb * 64;
-            const bool last = qk.t == qk.sg.n_tiles - 1;
-            if (elect_one()) {
+          if (qk.t == 0) mbar_wait_cluster(&sm.q_full, qk.seg & 1);
+          mbar_wait(&sm.ks_full[qk.g % kKsStages], (qk.g / kKsStages) & 1);  // s_full then vouches for the k scales too
+          mbar_wait_cluster(&sm.k_full[kst], (qk.g / kKStages) & 1);
+          trace(tr, rank, 1, qk.g, 0);
+          tc_fence_after();
+          const uint32_t stage = k_addr + kst * kKStageBytes;
+          const uint32_t d = tmem + kColS + sb * 64;
+          const bool last = qk.t == qk.sg.n_tiles - 1;
+          if (elect_one()) {
 #pragma unroll
-              for (int c = 0; c < 4; ++c)
-#pragma unroll
-                for (int s = 0; s < 4; ++s)
-                  umma_f8_pair(d, with_addr(d_kmaj, q_addr + c * 8192 + s * 32), with_addr(d_kmaj, stage + c * 8192 + s * 32),
-                               idesc_qk8, (c | s) != 0);
+            for (int c = 0; c < 4; ++c)
 #pragma unroll
               for (int s = 0; s < 4; ++s)
-                umma_f16_pair(d, with_addr(d_kmaj, q_addr + 32768 + s * 32), with_addr(d_kmaj, stage + 32768 + s * 32),
-                              idesc_qk16, 1);
-              umma_commit_pair(&sm.s_full[sb], 3);
-              umma_commit_pair(&sm.k_empty[kst], 3);
-              if (last) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
-            }
-            __syncwarp();
-            trace(tr, rank, 1, qk.g, 1);
-            advance(qk);
-            did = true;
+                umma_f8_pair(d, with_addr(d_kmaj, q_addr + c * 8192 + s * 32), with_addr(d_kmaj, stage + c * 8192 + s * 32),
+                             idesc_qk8, (c | s) != 0);
+#pragma unroll
+            for (int s = 0; s < 4; ++s)
+              umma_f16_pair(d, with_addr(d_kmaj, q_addr + 32768 + s * 32), with_addr(d_kmaj, stage + 32768 + s * 32),
+                            idesc_qk16, 1);
+            umma_commit_pair(&sm.s_full[sb], 3);
+            umma_commit_pair(&sm.k_empty[kst], 3);
+            if (last) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
           }
-        }
-        if (did) {
-          idle = 0;
+          __syncwarp();
+          trace(tr, rank, 1, qk.g, 1);
+          advance(qk);
         } else {
-          if (++idle > B200_WAIT_SPIN_LIMIT) __trap();
-          __nanosleep(32);
+          const uint32_t buf = pv.g % kPBufs, vst = pv.g % kVStages;
+          mbar_wait_cluster(&sm.p_full[buf], (pv.g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
+          mbar_wait(&sm.v_land[vst], (pv.g / kVStages) & 1);        // V landed here
+          if (pv.t == 0 && pv.seg > 0) mbar_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
+          trace(tr, rank, 1, pv.g, 2);
+          tc_fence_after();
+          const int tile_start = (pv.sg.start_block + 2 * pv.t) * kPage;
+          const int nk = (min(kTileTokens, pv.sg.valid_end - tile_start) + 31) / 32;
+          const bool first = pv.t == 0, last = pv.t == pv.sg.n_tiles - 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                if (s < nk)
+                  umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
+                               with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
+                               !(first && s == 0));
+            umma_commit_pair(&sm.v_empty[vst], 3);
+            umma_commit_pair(&sm.p_free[buf], 3);
+            umma_commit_pair(&sm.pv_done, 3);
+            if (last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
+          }
+          __syncwarp();
+          trace(tr, rank, 1, pv.g, 3);
+          advance(pv);
         }
       }
     } else {
@@ -882,6 +900,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
   }
 
+  if ((p.trace & 1) && tid == 128 && part < 128 && blockIdx.y == 0) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_part_cycles[(part * 2 + rank) * 2 + 1] = t;
+  }
   tc_fence_before();
   __syncthreads();
   cluster_sync_all();  // no CTA frees TMEM or exits while its peer can still address its barriers / shared memory
@@ -906,6 +929,11 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream)
 }  // namespace b200
 
 // Diagnostic: copy the pipeline trace of the last traced pair-kernel launch (see g_trace) to host memory.
+extern "C" int b200_mla_read_part_times(unsigned long long* out, int n) {
+  const int total = 2 * 128 * 2;
+  B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_part_cycles, sizeof(unsigned long long) * (n < total ? n : total)));
+  return 0;
+}
 extern "C" int b200_mla_read_trace(unsigned long long* out, int n) {
   const int total = 2 * b200::pairk::kTraceRoles * b200::pairk::kTraceTiles * 4;
   B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_trace, sizeof(unsigned long long) * (n < total ? n : total)));

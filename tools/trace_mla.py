@@ -17,6 +17,9 @@ fm.quantize_and_cache_k(kv, kl, ks, kr, torch.arange(n_pages * 64, dtype=torch.i
 q = torch.randn(b, 1, h, 576, dtype=torch.bfloat16, device=dev)
 qn, qs, qr = fm.quantize_ckv_per_token_head(q, 512)
 bt = (torch.randperm(n_pages - 1)[: b * pp].reshape(b, pp) + 1).to(torch.int32).to(dev)
+if os.environ.get("SHARED_PAGES"):  # diagnostic: every request walks the same few pages -> the KV stream is L2-resident
+    n_sh = int(os.environ["SHARED_PAGES"])
+    bt = ((torch.arange(b * pp).reshape(b, pp) % n_sh) + 1).to(torch.int32).to(dev)
 sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
 meta, ns = fm.get_mla_metadata(sl, h, 1)
 outs = []
@@ -65,11 +68,26 @@ for rank in range(2):
     for g in range(8, 24):
         a = tr[rank, 2, g, :]; d = tr[rank, 4, g, :]
         print("   %3d | %6d %6d %6d %6d %6d %6d %6d" % (g, a[0] - d[3], a[1] - a[0], d[0] - a[1], d[1] - d[0], a[2] - d[1], d[2] - a[2], a[3] - d[2]))
-    print(" K / MMA detail: tile | Kissue->Kseen  Kseen->QKstart  QKstart->QKissued  QKissued->Srdy(softmax)  PVissued - P arrived(this CTA)")
-    for g in range(8, 24):
+    print(" K / MMA detail: tile | Kissue->landed  landed->QKstart  QKstart->QKissued  QKissued->Srdy | P arrived(this CTA)->PVstart  PVstart->PVissued | PVissued(g-4)->QKstart(g)  QKissued(g)->Kissue(g+2)")
+    for g in range(8, 28):
         pr = tr[rank, 0, g, :]; m = tr[rank, 1, g, :]; a = tr[rank, 2, g, :]
-        print("   %3d | %6d %6d %6d %6d %6d" % (g, m[2] - pr[0], m[0] - m[2], m[1] - m[0], a[1] - m[1], m[3] - a[3]))
+        print("   %3d | %6d %6d %6d %6d | %6d %6d | %6d %6d" % (g, pr[3] - pr[0], m[0] - pr[3], m[1] - m[0], a[1] - m[1], m[2] - a[3], m[3] - m[2], m[0] - tr[rank, 1, g - 4, 3], tr[rank, 0, g + 2, 0] - m[1]))
+    if rank == 1:
+        print(" V detail (non-leader CTA): tile | Vwait(start)->Vissue   Vissue->landed   landed->P arrived(this CTA)")
+        for g in range(8, 24):
+            pr = tr[rank, 0, g, :]; a = tr[rank, 2, g, :]
+            print("   %3d | %6d %6d %6d" % (g, pr[2] - pr[1], pr[3] - pr[2], a[3] - pr[3]))
     print(" request | epilogue: start  o_ready  stored | next request's first tile top (previous row's request)")
     for sgi in range(4):
         e = tr[rank, 3, sgi, :] - t0
         print(" %7d | %9d %8d %8d | %8d" % (sgi, e[0], e[1], e[2], e[3]))
+
+pt = np.zeros(2 * 128 * 2, dtype=np.uint64)
+_lib.check(L.b200_mla_read_part_times(pt.ctypes.data, pt.size), "read_part_times")
+pt = pt.reshape(128, 2, 2).astype(np.int64)
+nparts = meta.shape[0]
+t_first = pt[:nparts, :, 0].min()
+print("per-part timeline (us relative to the first CTA's entry): part | entry r0 r1 | softmax end r0 r1 | busy")
+for part in range(nparts):
+    e = (pt[part, :, 0] - t_first) / 1e3; x = (pt[part, :, 1] - t_first) / 1e3
+    print("  %3d | %6.1f %6.1f | %6.1f %6.1f | %6.1f   meta %s" % (part, e[0], e[1], x[0], x[1], max(x) - min(e), meta[part, :5].tolist()))
