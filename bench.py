@@ -138,10 +138,14 @@ class HotPath:
 
         from sglang_fluentllm_b200 import deep_gemm as dg
         self.torch, self.dg, self.args, self.dev, self.world = torch, dg, args, dev, world
+        from sglang_fluentllm_b200 import tp as tpmod
+        self.tpmod = tpmod
         tp = world if args.parallelism == "tp" else 1
         self.tp = tp
         b, seq, L = args.batch, args.seq, args.layers
-        self.h = args.heads // tp
+        # heads / column-parallel q_b_proj rows / row-parallel o_proj columns of this rank (sglang_fluentllm_b200/tp.py)
+        self.plan = tpmod.TpPlan(rank if tp > 1 else 0, tp, args.heads, NOPE_HEAD + ROPE, V_HEAD)
+        self.h = self.plan.heads_per_rank
         h = self.h
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
@@ -234,7 +238,7 @@ class HotPath:
         attn_o = out[..., :V_HEAD].reshape(b, h * V_HEAD)  # stand-in for the w_vc bmm output
         y = self.linear(attn_o, self.w_o[l])
         if self.tp > 1:
-            torch.distributed.all_reduce(y)
+            self.tpmod.all_reduce_sum(y)  # the path's single exchange: row-parallel partial sums over NVLink
         return y
 
     def step(self, x):
@@ -320,12 +324,7 @@ def run_b200(args):
             e1.record(stream)
             stream.synchronize()
             barrier()
-            ms = e0.elapsed_time(e1)
-            if world > 1:
-                t = torch.tensor([ms], device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                ms = float(t.item())
-            return ms
+            return hp.tpmod.max_over_ranks_ms(e0.elapsed_time(e1), dev)
 
         for _ in range(max(args.warmup, 3)):
             run_step()

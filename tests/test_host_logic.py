@@ -67,3 +67,42 @@ def test_calc_diff():
     x = torch.randn(100)
     assert dg.calc_diff(x, x) < 1e-12
     assert dg.calc_diff(x, -x) > 1.9
+
+
+def test_fp8_config_and_linear_method_mirror_reference_rules():
+    from sglang_fluentllm_b200 import fp8_linear as fl
+    cfg = fl.Fp8Config.from_config({"quant_method": "fp8", "activation_scheme": "dynamic", "weight_block_size": [128, 128]})
+    assert cfg.get_name() == "fp8" and cfg.is_checkpoint_fp8_serialized and cfg.weight_block_size == [128, 128]
+    with pytest.raises(ValueError, match="Unsupported activation scheme"):
+        fl.Fp8Config(activation_scheme="sometimes")
+    with pytest.raises(ValueError, match="fp8-serialized"):
+        fl.Fp8Config(is_checkpoint_fp8_serialized=False, weight_block_size=[128, 128])
+    with pytest.raises(ValueError, match="dynamic activation scheme"):
+        fl.Fp8Config(True, "static", None, [128, 128])
+    cfg2 = fl.Fp8Config(True, "dynamic", ["lm_head"], [128, 128])
+    assert cfg2.get_quant_method(torch.nn.Module(), prefix="lm_head") is None
+    method = cfg2.get_quant_method(torch.nn.Module(), prefix="model.layers.0.self_attn.o_proj")
+    assert isinstance(method, fl.Fp8LinearMethod) and method.block_quant
+
+
+def test_fp8_linear_method_weights_and_checks():
+    from sglang_fluentllm_b200 import fp8_linear as fl
+    cfg = fl.Fp8Config(True, "dynamic", None, [128, 128])
+    method = fl.Fp8LinearMethod(cfg, tp_size=2)
+    layer = torch.nn.Module()
+    method.create_weights(layer, 256, [384], 512, 384, torch.bfloat16)   # row parallel: K split over 2 ranks
+    assert layer.weight.shape == (384, 256) and layer.weight.dtype == torch.float8_e4m3fn
+    assert layer.weight_scale_inv.shape == (3, 2) and layer.input_scale is None
+    with pytest.raises(ValueError, match="block_k"):
+        method.create_weights(torch.nn.Module(), 192, [384], 384, 384, torch.bfloat16)
+    with pytest.raises(ValueError, match="block_n"):
+        method.create_weights(torch.nn.Module(), 256, [192, 64], 256, 256, torch.bfloat16)
+    method.process_weights_after_loading(layer)
+    # apply: non-bf16 output and unsupported shapes raise instead of falling back; CPU tensors never reach a kernel
+    x = torch.zeros(4, 256, dtype=torch.bfloat16)
+    with pytest.raises(RuntimeError, match="no fallback"):
+        method.apply(layer, x, output_dtype=torch.float16)
+    with pytest.raises(RuntimeError):
+        method.apply(layer, x)
+    with pytest.raises(NotImplementedError):
+        fl.Fp8LinearMethod(fl.Fp8Config())
