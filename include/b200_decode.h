@@ -107,8 +107,8 @@ int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* sc
  * `launch(lhs, lhs_scales, rhs, rhs_scales, out, m, stream, ...)` C symbol (deep_gemm/jit/template.py:57-79).
  *   a e4m3 [m][k]; a_scales f32 [k/128][a_scale_stride] (column-major, stride = m rounded up to 4);
  *   b e4m3 [n][k]; b_scales f32 [ceil(n/128)][k/128]; out bf16 [m][n].  Requires n % 64 == 0, k % 128 == 0.
- *   workspace: optional split-K scratch of b200_fp8_gemm_workspace_bytes(m, n, k) bytes that must be ZERO on first
- *   use; the kernel leaves it zero again, so one buffer serves every call on a stream.  NULL = no split-K. */
+ *   workspace: optional split-K scratch of b200_fp8_gemm_workspace_bytes(m, n, k) bytes (fp32 partial slabs, one per
+ *   split; no initialisation needed, one buffer serves every call on a stream).  NULL = no split-K. */
 size_t b200_fp8_gemm_workspace_bytes(int m, int n, int k);
 int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b, const float* b_scales,
                      void* out, int m, int n, int k, void* workspace, size_t workspace_bytes, int use_pdl,

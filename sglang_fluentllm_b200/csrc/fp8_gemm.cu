@@ -12,9 +12,9 @@
 //   warp 1: UMMA issuer (4 x kind::f8f6f4 M=128 N=BT K=32 per k-block into one of two TMEM accumulators)
 //   warps 2..: promotion + epilogue, 4 lane quadrants x BT/CPT column slices: tcgen05.ld the k-block partial,
 //              packed-fp32x2 FMA with the scales, bf16 store.
-// Decode shapes stream weights (HBM-bound) but have few 128-row weight tiles (17..56): split-K over grid.z spreads
-// the stream over all SMs; partials meet in an fp32 workspace through red.global.add and the last CTA of a tile
-// converts to bf16 and re-zeroes the workspace (self-cleaning, one launch).
+// Decode shapes stream weights (HBM-bound) but have few weight tiles (9..56): split-K over grid.z spreads the stream
+// over all SMs; each split stores its fp32 partial to its own workspace slab with plain coalesced stores and a small
+// PDL-chained kernel sums the slabs in split order (deterministic; 17 MB of red.global.add cost 30 us per call).
 #include <cuda_bf16.h>
 #include <string.h>
 
@@ -30,8 +30,7 @@ struct GemmParams {
   int64_t a_scale_stride;
   const float* b_scales;
   __nv_bfloat16* out;
-  float* ws;            // [m][n] fp32 split-K accumulator (zero between calls)
-  unsigned int* counters;  // [tiles] arrival counters (zero between calls)
+  float* ws;            // [splits][m][n] fp32 split-K partial slabs
   int m, n, k, splits, kb_per_split;
 };
 
@@ -58,7 +57,6 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   struct Bars {
     uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    uint32_t is_last;
   };
   Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * S::kStageBytes);
 
@@ -164,33 +162,13 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
             p.out[(int64_t)(m0 + cb + j) * p.n + ncol] = __float2bfloat16_rn(j & 1 ? acc[j / 2].y : acc[j / 2].x);
       }
     } else {
-      // split-K: add the partial into the fp32 workspace; the last CTA of this tile converts and re-zeroes it
+      // split-K: this split's fp32 partial -> its own slab of the workspace (plain coalesced stores: a warp covers 32
+      // consecutive weight rows = 128 contiguous bytes per token); splitk_reduce_kernel sums the slabs in split order
       if (ncol < p.n) {
+        float* slab = p.ws + (int64_t)blockIdx.z * p.m * p.n;
 #pragma unroll
         for (int j = 0; j < CPT; ++j)
-          if (m0 + cb + j < p.m)
-            atomicAdd(p.ws + (int64_t)(m0 + cb + j) * p.n + ncol, j & 1 ? acc[j / 2].y : acc[j / 2].x);
-      }
-      __threadfence();
-      named_bar_sync(1, kPromo);
-      if (tid == 64) {
-        const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned int prev = atomicAdd(p.counters + tile, 1u);
-        bars.is_last = (prev == (unsigned int)p.splits - 1) ? 1u : 0u;
-        if (bars.is_last) p.counters[tile] = 0;
-      }
-      named_bar_sync(1, kPromo);
-      if (bars.is_last) {
-        __threadfence();
-        if (ncol < p.n) {
-#pragma unroll
-          for (int j = 0; j < CPT; ++j)
-            if (m0 + cb + j < p.m) {
-              float* w = p.ws + (int64_t)(m0 + cb + j) * p.n + ncol;
-              p.out[(int64_t)(m0 + cb + j) * p.n + ncol] = __float2bfloat16_rn(__ldcg(w));
-              __stcg(w, 0.f);
-            }
-        }
+          if (m0 + cb + j < p.m) slab[(int64_t)(m0 + cb + j) * p.n + ncol] = j & 1 ? acc[j / 2].y : acc[j / 2].x;
       }
     }
   }
@@ -224,7 +202,6 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
   struct Bars {
     uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
-    uint32_t is_last;
   };
   Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * S::kStageBytes);
 
@@ -336,41 +313,13 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
         }
       }
     } else {
+      // split-K: fp32 partial of this split -> its slab of the workspace; splitk_reduce_kernel sums in split order
       if (row_ok) {
-        float* dst = p.ws + (int64_t)grow * p.n + n0 + cb;
+        float* dst = p.ws + ((int64_t)blockIdx.z * p.m + grow) * p.n + n0 + cb;
 #pragma unroll
         for (int j = 0; j < CPT; j += 4)
           if (n0 + cb + j < p.n)
-            asm volatile("red.global.add.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(dst + j), "f"(acc[j / 2].x), "f"(acc[j / 2].y),
-                         "f"(acc[j / 2 + 1].x), "f"(acc[j / 2 + 1].y)
-                         : "memory");
-      }
-      __threadfence();
-      named_bar_sync(1, kPromo);
-      if (tid == 64) {
-        const unsigned int tile = blockIdx.y * gridDim.x + blockIdx.x;
-        const unsigned int prev = atomicAdd(p.counters + tile, 1u);
-        bars.is_last = (prev == (unsigned int)p.splits - 1) ? 1u : 0u;
-        if (bars.is_last) p.counters[tile] = 0;
-      }
-      named_bar_sync(1, kPromo);
-      if (bars.is_last && row_ok) {
-        __threadfence();
-        float* src = p.ws + (int64_t)grow * p.n + n0 + cb;
-        __nv_bfloat16* dst = p.out + (int64_t)grow * p.n + n0 + cb;
-#pragma unroll
-        for (int j = 0; j < CPT; j += 8) {
-          if (n0 + cb + j < p.n) {
-            const float4 a = __ldcg(reinterpret_cast<const float4*>(src + j));
-            const float4 b = __ldcg(reinterpret_cast<const float4*>(src + j + 4));
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-            __stcg(reinterpret_cast<float4*>(src + j), make_float4(0.f, 0.f, 0.f, 0.f));
-            __stcg(reinterpret_cast<float4*>(src + j + 4), make_float4(0.f, 0.f, 0.f, 0.f));
-          }
-        }
+            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j / 2].x, acc[j / 2].y, acc[j / 2 + 1].x, acc[j / 2 + 1].y);
       }
     }
   }
@@ -378,6 +327,42 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, 512);
+}
+
+// out[m][n] = bf16( sum over splits, in split order, of the fp32 slabs ): deterministic, no atomics.  8 outputs per thread.
+__global__ void __launch_bounds__(256) splitk_reduce_kernel(const float* __restrict__ ws, __nv_bfloat16* __restrict__ out,
+                                                            int64_t mn, int splits) {
+  pdl_wait_prior_grid();
+  const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 8;
+  if (i >= mn) return;
+  float4 a = __ldcg(reinterpret_cast<const float4*>(ws + i)), b = __ldcg(reinterpret_cast<const float4*>(ws + i + 4));
+  for (int s = 1; s < splits; ++s) {
+    const float4 c = __ldcg(reinterpret_cast<const float4*>(ws + s * mn + i));
+    const float4 d = __ldcg(reinterpret_cast<const float4*>(ws + s * mn + i + 4));
+    a.x += c.x, a.y += c.y, a.z += c.z, a.w += c.w;
+    b.x += d.x, b.y += d.y, b.z += d.z, b.w += d.w;
+  }
+  __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+  __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+  *reinterpret_cast<uint4*>(out + i) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                                                  *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+  pdl_launch_dependents();
+}
+
+static int launch_splitk_reduce(const GemmParams& prm, cudaStream_t stream) {
+  const int64_t mn = (int64_t)prm.m * prm.n;  // n % 64 == 0: a multiple of 8
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3((unsigned)((mn / 8 + 255) / 256), 1, 1);
+  cfg.blockDim = dim3(256, 1, 1);
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;  // its prologue overlaps the GEMM's tail; griddepcontrol.wait orders the reads
+  B200_CUDA(cudaLaunchKernelEx(&cfg, splitk_reduce_kernel, (const float*)prm.ws, prm.out, mn, prm.splits));
+  return 0;
 }
 
 static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
@@ -439,9 +424,11 @@ static int pick_splits(int m, int n, int k, int sm_count) {
   const int num_kb = k / 128;
   if (tiles * 2 > sm_count) return 1;
   int splits = sm_count / tiles;
-  if (splits > num_kb / 4) splits = num_kb / 4;
-  if (splits > 16) splits = 16;
-  return splits < 1 ? 1 : splits;
+  if (splits > num_kb / 2) splits = num_kb / 2;
+  if (splits > 32) splits = 32;
+  if (splits < 1) splits = 1;
+  const int kb_per = (num_kb + splits - 1) / splits;  // the split count the launch will really use
+  return (num_kb + kb_per - 1) / kb_per;
 }
 
 }  // namespace b200
@@ -453,8 +440,7 @@ extern "C" {
 size_t b200_fp8_gemm_workspace_bytes(int m, int n, int k) {
   const int sms = device_sm_count();
   if (pick_splits(m, n, k, sms > 0 ? sms : 148) == 1) return 0;
-  const size_t tiles = (size_t)num_tiles(m, n);
-  return (size_t)m * n * sizeof(float) + tiles * sizeof(unsigned int);
+  return (size_t)pick_splits(m, n, k, sms > 0 ? sms : 148) * m * n * sizeof(float);
 }
 
 int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b, const float* b_scales,
@@ -483,10 +469,7 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.splits = splits;
   prm.kb_per_split = (num_kb + splits - 1) / splits;
   prm.splits = (num_kb + prm.kb_per_split - 1) / prm.kb_per_split;
-  if (prm.splits > 1) {
-    prm.ws = (float*)workspace;
-    prm.counters = (unsigned int*)((char*)workspace + (size_t)m * n * sizeof(float));
-  }
+  if (prm.splits > 1) prm.ws = (float*)workspace;
   const bool tokm = tokens_on_m(m);
   if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, tokm ? 256 : 128, TmaSwizzle::B128))
     return 1;
@@ -499,13 +482,13 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.m = m;
   prm.n = n;
   prm.k = k;
-  if (tokm) return launch_gemm_tokm(prm, use_pdl, (cudaStream_t)stream);
-  switch (BT) {
-    case 16: return launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
-    case 32: return launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
-    case 64: return launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
-    default: return launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
-  }
+  int rc;
+  if (tokm) rc = launch_gemm_tokm(prm, use_pdl, (cudaStream_t)stream);
+  else if (BT == 16) rc = launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
+  else if (BT == 32) rc = launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
+  else rc = launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
+  if (rc == 0 && prm.splits > 1) rc = launch_splitk_reduce(prm, (cudaStream_t)stream);
+  return rc;
 }
 
 }  // extern "C"

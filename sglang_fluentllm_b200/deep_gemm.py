@@ -11,11 +11,11 @@ import torch
 from . import _lib
 
 _num_sms = None
-_workspaces = {}  # device index -> zero-initialised split-K scratch (the kernel leaves it zero after every call)
+_workspaces = {}  # device index -> split-K scratch (fp32 partial slabs; stream-ordered reuse, no initialisation)
 
 
 def _workspace(device: torch.device, nbytes: int):
-    """Per-device split-K scratch.  Grown (and zeroed) on demand; growth is not allowed while a CUDA graph is being
+    """Per-device split-K scratch.  Grown on demand; growth is not allowed while a CUDA graph is being
     captured -- the runner's warm-up calls before capture size it (reference: JIT compile happens in warm-up too,
     python/sglang/srt/model_executor/cuda_graph_runner.py:423-427)."""
     if nbytes == 0:
@@ -24,7 +24,7 @@ def _workspace(device: torch.device, nbytes: int):
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
             return None  # fall back to plain tiling for this call rather than allocate inside a capture
-        ws = torch.zeros(max(nbytes, 32 << 20), dtype=torch.uint8, device=device)
+        ws = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=device)
         _workspaces[device.index] = ws
     return ws
 
