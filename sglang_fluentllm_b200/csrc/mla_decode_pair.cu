@@ -24,9 +24,10 @@
 //   16-column loop (TMEM load double-buffered, packed fp32x2 arithmetic, e4m3 codes written straight into the P tile).
 //
 //   Warp roles per CTA (384 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
-//   and the k-scale ring; warp 1 = UMMA issuer (leader CTA; static order ... P.V(g-1), Q.K^T(g+2), P.V(g) ..., i.e.
-//   Q.K^T runs three tiles ahead) or relay of the local P / O hand-offs (other CTA) + TMEM allocation; warp 2 = V
-//   producer; warp 3 idle; warps 4-11 = softmax / correction / epilogue.
+//   and the k-scale ring; warp 2 = V producer; leader CTA: warp 1 issues every Q.K^T and warp 3 every P.V (two
+//   independent instruction streams into the in-order tensor pipe; Q.K^T runs up to four tiles ahead), other CTA:
+//   warp 1 relays the local P / O hand-offs to the leader; warp 1 also owns the TMEM allocation; warps 4-11 =
+//   softmax / correction / epilogue.
 //   TMEM per CTA: 4 S tiles (4 x 64 columns) + O (2 x 128 columns) = 512 columns.
 //   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, 2 V stages x 32 KB, 4 P tiles x 8 KB (also the
 //   epilogue's staging tile), k-scale ring 4 KB, barriers / row state 5 KB.
@@ -318,12 +319,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         if (t + kKsAhead < sg.n_tiles) load_ks(t + kKsAhead, g + kKsAhead);
       }
     }
-  } else if (warp == 3 && rank == 0 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
-    // diagnostic: when each K stage actually lands (first 60 tiles of part 0; the part has at least that many)
-    for (uint32_t g = 0; g < 40; ++g) {
-      mbar_wait_cluster(&sm.k_full[g % kKStages], (g / kKStages) & 1);
-      trace(lane == 0, rank, 0, g, 3);
-    }
   } else if (warp == 3 && rank == 1 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
     // diagnostic: when each V stage lands in the non-leader CTA
     for (uint32_t g = 0; g < 40; ++g) {
@@ -384,70 +379,35 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         load_v(t, g);
       }
     }
-  } else if (warp == 1) {
-    if (rank == 0) {
-      // ============================== UMMA issuer (leader CTA) ==============================
-      // Two cursors walk the part's tiles: Q.K^T runs ahead of P.V by up to kSBufs - 1 tiles (S is kSBufs-buffered in
-      // TMEM), so the next tiles' scores are ready the moment a softmax group publishes P; whichever of the two has
-      // its operands ready is issued, P.V first.
-      constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
-      constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
-      constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
-      const uint32_t q_addr = smem_u32(s_q), k_addr = smem_u32(s_k), v_addr = smem_u32(s_v), p_addr = smem_u32(s_p);
-      const uint64_t d_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);       // K-major, 128-B swizzle
-      const uint64_t d_vmn = make_smem_desc(0, 16384, 1024, SWZ_128B);    // V: MN-major view of the token rows
-      auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
-
-      struct Cursor {
-        int b, t;
-        uint32_t g, seg;
-        Segment sg;
-        bool active;
-      };
-      auto seek = [&](Cursor& c) {  // position on the next request of the part that has tiles
-        c.t = 0;
-        for (; c.b <= end_idx; ++c.b) {
-          c.sg = make_segment(p, c.b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
-          if (c.sg.n_tiles > 0) return;
-        }
-        c.active = false;
-      };
-      auto advance = [&](Cursor& c) {
-        ++c.g;
-        if (++c.t == c.sg.n_tiles) {
-          ++c.seg;
-          ++c.b;
-          seek(c);
-        }
-      };
-      Cursor qk, pv;
-      qk.b = pv.b = begin_idx;
-      qk.g = pv.g = 0;
-      qk.seg = pv.seg = 0;
-      qk.active = pv.active = true;
-      seek(qk);
-      seek(pv);
-
-      // Static issue order with blocking waits (polling several barriers from this warp cost more than it bought):
-      // Q.K^T runs kQkLead tiles ahead of P.V, i.e. ... P.V(g-1), Q.K^T(g+2), P.V(g), Q.K^T(g+3) ...; the scores of
-      // tile g+2 are issued when tile g-1 is published, about half a softmax-group period before the group that
-      // publishes tile g needs them.  At a request boundary the old request's P.V go first (the new request's Q and
-      // K stream would hold them, and with them the epilogue, back).
-      constexpr uint32_t kQkLead = 3;
-      static_assert(kQkLead < kSBufs, "S tile g + kQkLead must not overwrite one that is still being read");
-      while (pv.active) {
-        const uint32_t lead = (p.trace & 16) ? 2u : kQkLead;
-        const bool qk_turn = qk.active && qk.g < pv.g + lead && !(qk.t == 0 && qk.seg > pv.seg);
-        if (qk_turn) {
-          const uint32_t kst = qk.g % kKStages, sb = qk.g % kSBufs;
-          if (qk.t == 0) mbar_wait_cluster(&sm.q_full, qk.seg & 1);
-          mbar_wait(&sm.ks_full[qk.g % kKsStages], (qk.g / kKsStages) & 1);  // s_full then vouches for the k scales too
-          mbar_wait_cluster(&sm.k_full[kst], (qk.g / kKStages) & 1);
-          trace(tr, rank, 1, qk.g, 0);
+  } else if ((warp == 1 || warp == 3) && rank == 0) {
+    // ============================== UMMA issuers (leader CTA) ==============================
+    // warp 1 issues every Q.K^T, warp 3 every P.V: two independent instruction streams into the one in-order tensor
+    // pipe, so a Q.K^T waiting for its K page never holds back a P.V whose P is published (and vice versa; a single
+    // issuer needs either a fixed interleave or polling, and both cost throughput).  Q.K^T of tile g waits for P.V of
+    // tile g - kSBufs to retire (p_free): S tile g % kSBufs has then been read, P tile g % kPBufs is free, and -- the
+    // pipe being in order -- s_full(g) vouches for both to the softmax warps.
+    constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
+    constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
+    constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
+    const uint32_t q_addr = smem_u32(s_q), k_addr = smem_u32(s_k), v_addr = smem_u32(s_v), p_addr = smem_u32(s_p);
+    const uint64_t d_kmaj = make_smem_desc(0, 0, 1024, SWZ_128B);       // K-major, 128-B swizzle
+    const uint64_t d_vmn = make_smem_desc(0, 16384, 1024, SWZ_128B);    // V: MN-major view of the token rows
+    auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
+    uint32_t g = 0, seg = 0;
+    for (int b = begin_idx; b <= end_idx; ++b) {
+      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      if (sg.n_tiles == 0) continue;
+      if (warp == 1) {
+        mbar_wait_cluster(&sm.q_full, seg & 1);
+        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+          const uint32_t kst = g % kKStages, sb = g % kSBufs;
+          if (g >= (uint32_t)kSBufs) mbar_wait(&sm.p_free[sb], ((g / kSBufs) & 1) ^ 1);  // P.V of tile g - kSBufs retired
+          mbar_wait(&sm.ks_full[g % kKsStages], (g / kKsStages) & 1);  // s_full then vouches for the k scales too
+          mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
+          trace(tr, rank, 1, g, 0);
           tc_fence_after();
           const uint32_t stage = k_addr + kst * kKStageBytes;
           const uint32_t d = tmem + kColS + sb * 64;
-          const bool last = qk.t == qk.sg.n_tiles - 1;
           if (elect_one()) {
 #pragma unroll
             for (int c = 0; c < 4; ++c)
@@ -461,21 +421,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                             idesc_qk16, 1);
             umma_commit_pair(&sm.s_full[sb], 3);
             umma_commit_pair(&sm.k_empty[kst], 3);
-            if (last) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
+            if (t == sg.n_tiles - 1) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
           }
           __syncwarp();
-          trace(tr, rank, 1, qk.g, 1);
-          advance(qk);
-        } else {
-          const uint32_t buf = pv.g % kPBufs, vst = pv.g % kVStages;
-          mbar_wait_cluster(&sm.p_full[buf], (pv.g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
-          mbar_wait(&sm.v_land[vst], (pv.g / kVStages) & 1);        // V landed here
-          if (pv.t == 0 && pv.seg > 0) mbar_wait_cluster(&sm.o_free, (pv.seg - 1) & 1);
-          trace(tr, rank, 1, pv.g, 2);
+          trace(tr, rank, 1, g, 1);
+        }
+      } else {
+        for (int t = 0; t < sg.n_tiles; ++t, ++g) {
+          const uint32_t buf = g % kPBufs, vst = g % kVStages;
+          mbar_wait_cluster(&sm.p_full[buf], (g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
+          mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);        // V landed here
+          if (t == 0 && seg > 0) mbar_wait_cluster(&sm.o_free, (seg - 1) & 1);
+          trace(tr, rank, 1, g, 2);
           tc_fence_after();
-          const int tile_start = (pv.sg.start_block + 2 * pv.t) * kPage;
-          const int nk = (min(kTileTokens, pv.sg.valid_end - tile_start) + 31) / 32;
-          const bool first = pv.t == 0, last = pv.t == pv.sg.n_tiles - 1;
+          const int tile_start = (sg.start_block + 2 * t) * kPage;
+          const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
           if (elect_one()) {
 #pragma unroll
             for (int j = 0; j < 2; ++j)
@@ -484,18 +444,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
                 if (s < nk)
                   umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
                                with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
-                               !(first && s == 0));
+                               !(t == 0 && s == 0));
             umma_commit_pair(&sm.v_empty[vst], 3);
             umma_commit_pair(&sm.p_free[buf], 3);
             umma_commit_pair(&sm.pv_done, 3);
-            if (last) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
+            if (t == sg.n_tiles - 1) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
           }
           __syncwarp();
-          trace(tr, rank, 1, pv.g, 3);
-          advance(pv);
+          trace(tr, rank, 1, g, 3);
         }
       }
-    } else {
+      ++seg;
+    }
+  } else if (warp == 1) {
+    {
       // ============================== relay (non-leader CTA) ==============================
       // This CTA's softmax warps hand P / O over on LOCAL barriers (ordered with their shared-memory stores); once a
       // phase completes here -- the stores are then performed in this SM's shared memory -- one remote arrive tells the
