@@ -12,9 +12,12 @@ tokens/s = batch / step time.  `value` is timed with inputs resident in HBM (CUD
 `e2e` adds, inside the timed region, the pinned-host -> device copy of the step inputs (hidden states, block table,
 sequence lengths), the per-step metadata kernel and a device -> host read of the step output.
 
-Multi-GPU (torchrun, one rank per GPU): tensor-parallel over attention heads / column-parallel weights, one NCCL
-all-reduce per layer on the row-parallel o_proj output; the batch is replicated (strong scaling), as BASELINE.json's
-TP configs do.  `--parallelism dp` runs N independent replicas instead (weak scaling, no collective).
+Multi-GPU (torchrun, one rank per GPU).  Default `--parallelism dp`: one replica of the path per GPU with the per-GPU
+batch fixed at 128 (weak scaling, no data-path collective) -- MLA has a single latent KV head, so under head tensor
+parallelism every rank streams the whole KV pool and attention time does not shrink; sharding the
+requests is what the reference's DP-attention does to this block.  The same run then measures strict head-TP
+(`--parallelism tp`: heads / column-parallel q_b_proj / row-parallel o_proj over the GPUs, global batch fixed, ONE NCCL
+all-reduce per layer on the row-parallel output over NVLink) and reports it under "tp_strong".
 
 `--impl reference` times the reference's CPU path (torch-native SDPA decode loop + native block-FP8 matmul,
 oracle/native_cpu.py -- a port, the reference package is not installable) on a bounded sample of the same workload.
@@ -47,7 +50,12 @@ def parse():
     ap.add_argument("--seq", type=int, default=4096)
     ap.add_argument("--layers", type=int, default=LAYERS)
     ap.add_argument("--heads", type=int, default=HEADS)
-    ap.add_argument("--parallelism", default="tp", choices=["tp", "dp"])
+    ap.add_argument("--parallelism", default=None, choices=["tp", "dp"],
+                    help="N > 1: dp (default) = one replica of the path per GPU, per-GPU batch fixed (weak scaling, no "
+                         "data-path collective; what the reference's DP-attention does to this block); tp = heads / "
+                         "column- and row-parallel weights over the GPUs with one all-reduce per layer (strong scaling; "
+                         "MLA's single latent KV head makes every rank stream the whole KV pool).  The dp run also "
+                         "reports a short tp measurement under \"tp_strong\".")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="time only the MLA decode kernel per layer")
@@ -264,6 +272,14 @@ def mla_bytes_flops(b, seq, h, s_q=1):
     return S * 644 + b * M * 644 + b * M * 1024, 2 * S * M * (576 + 512)
 
 
+def log(msg):
+    if os.environ.get("BENCH_VERBOSE"):
+        print("[bench rank %s %.1fs] %s" % (os.environ.get("RANK", "0"), time.time() - _T0, msg), file=sys.stderr, flush=True)
+
+
+_T0 = time.time()
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -275,7 +291,11 @@ def run_b200(args):
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    log("process group up")
+    if args.parallelism is None:
+        args.parallelism = "dp" if world > 1 else "tp"
     hp = HotPath(args, rank, world, dev)
+    log("state built")
     stream = torch.cuda.Stream(device=dev)
     peaks = {}
     try:
@@ -294,12 +314,14 @@ def run_b200(args):
         for _ in range(2):
             hp.step(hp.hidden_in)
         stream.synchronize()
+        log("eager warm-up done")
         graph = None
         if not args.no_graph:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph, stream=stream):
                 hp.x_out = hp.step(hp.hidden_in)
         launches = hp.launches_per_step
+        log("graph captured")
 
         def run_step():
             if graph is not None:
@@ -328,13 +350,16 @@ def run_b200(args):
 
         for _ in range(max(args.warmup, 3)):
             run_step()
+        log("warm-up replays done")
         sampler = ClockSampler(local_rank)
         sampler.start()
         ms = timed(run_step, args.steps)
         clocks = sampler.stop()
+        log("timed region done")
         for _ in range(2):
             run_e2e_step()
         ms_e2e = timed(run_e2e_step, args.steps)
+        log("e2e region done")
 
         # dominant kernel: MLA decode (+combine), timed alone per layer (each layer's KV is distinct and the set of
         # layers is far larger than L2, so every launch is L2-cold)
@@ -386,12 +411,54 @@ def run_b200(args):
                      "kernel": "mla_decode_kernel (+combine), per layer, L2-cold", "kernel_ms": round(attn_ms, 4),
                      "algorithmic_bytes": bytes_, "tflops": round(flops / (attn_ms * 1e-3) / 1e12, 1)},
     }
+    tp_strong = None
+    if world > 1 and args.parallelism == "dp":
+        # the same step under strict head tensor parallelism (global batch fixed, one NCCL all-reduce per layer)
+        graph = attn_graph = hp = None
+        torch.cuda.empty_cache()
+        import copy
+        targs = copy.copy(args)
+        targs.parallelism = "tp"
+        hp_tp = HotPath(targs, rank, world, dev)
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                hp_tp.step(hp_tp.hidden_in)
+            stream.synchronize()
+            g_tp = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_tp, stream=stream):
+                hp_tp.x_out = hp_tp.step(hp_tp.hidden_in)
+            for _ in range(3):
+                g_tp.replay()
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record(stream)
+            for _ in range(args.steps):
+                g_tp.replay()
+            e1.record(stream)
+            stream.synchronize()
+            barrier()
+            ms_tp = hp_tp.tpmod.max_over_ranks_ms(e0.elapsed_time(e1), dev) / args.steps
+        tp_strong = {"value": round(args.batch / (ms_tp * 1e-3), 2), "unit": "tokens/s", "ms_per_step": round(ms_tp, 4),
+                     "global_batch": args.batch, "heads_per_gpu": hp_tp.h, "scaling": "strong",
+                     "collective": "1 NCCL all-reduce [b, 7168] bf16 per layer on the row-parallel o_proj output"}
+        g_tp = hp_tp = None
+        log("tp_strong done")
+    if tp_strong is not None:
+        line["tp_strong"] = tp_strong
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         line["cpu_baseline"] = cpu_baseline(args, budget_s=20.0)
     if rank == 0:
         print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        # Tearing the NCCL communicator down while captured graphs still reference it hangs (seen with torch 2.11 /
+        # NCCL 2.28 at N = 2): drop the graphs, drain the device, meet the other ranks, then leave without the
+        # communicator teardown.
+        graph = attn_graph = None
+        torch.cuda.synchronize()
+        dist.barrier()
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
 
 
 # ----------------------------------------------------------------------------------------------------------------
@@ -432,7 +499,8 @@ def run_reference(args):
     base["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.batch / v * 1e3, 3),
-            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16/f32 (CPU)",
+            "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "strong", "vs_baseline": None,
+            "dtype": "bf16/f32 (CPU)",
             "data": "synthetic", "config": {"workload": "same step as the b200 arm, reference CPU path (port)",
                                             "global_batch": args.batch, "seq_len": args.seq},
             "cpu_baseline": base,
