@@ -231,11 +231,11 @@ class HotPath:
         torch, fm = self.torch, self.fm
         b, h = self.args.batch, self.h
         y_a = self.linear(x, self.w_qkv_a[l])
-        k_new = y_a[:, Q_LORA:].contiguous().view(b, 1, KV_LORA + ROPE)
+        k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
         fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
         q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
         # absorbed q [b, 1, h, 576]: the w_kc bmm is outside the path; reuse q_full's leading columns as the data source
-        q_abs = self.q_abs + q_full[:, : h * 64].view(b, 1, h, 64).repeat(1, 1, 1, 9)
+        q_abs = (self.q_abs.view(b, 1, h, 9, 64) + q_full[:, : h * 64].view(b, 1, h, 1, 64)).view(b, 1, h, KV_LORA + ROPE)
         q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
         n_pages = self.n_pages
         out, _ = fm.flash_mla_ckv_fp8_per_token(

@@ -41,8 +41,10 @@ struct GemmSmem {
   static constexpr int kABytes = BT * 128;
   static constexpr int kABytesPadded = (kABytes + 1023) / 1024 * 1024;
   static constexpr int kStageBytes = kWBytes + kABytesPadded + 1024;  // + scales (<= 512 B), keeps 1024 alignment
-  static constexpr int kTotal = kStages * kStageBytes + 1024;
+  static constexpr int kOffWScale = kStages * kStageBytes + 1024;  // weight scales of this CTA's k range, <= 256 floats
+  static constexpr int kTotal = kOffWScale + 1024;
 };
+static constexpr int kMaxWScaleKb = 256;
 
 template <int BT, int CPT>
 __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(const __grid_constant__ GemmParams p) {
@@ -53,7 +55,7 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   constexpr int kPromo = 128 * kCS;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   struct Bars {
     uint64_t full[8], empty[8], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -69,11 +71,11 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars.full[i], 1);
-      mbar_init(&bars.empty[i], 1 + kPromo);  // UMMA commit + the promotion threads (they read the scales)
+      mbar_init(&bars.empty[i], 1 + kPromo / 32);  // UMMA commit + one arrival per promotion warp (they read the scales)
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.acc_full[i], 1);
-      mbar_init(&bars.acc_empty[i], kPromo);
+      mbar_init(&bars.acc_empty[i], kPromo / 32);  // one arrival per promotion warp: 512 arrivals on one word serialise
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
@@ -86,35 +88,38 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   const uint32_t tmem = bars.tmem_base;
   pdl_wait_prior_grid();
 
+  // Issuer warps run warp-uniform code and predicate only the TMA / MMA instructions with elect.sync (descriptors and
+  // coordinates stay in uniform registers; a divergent `if (lane == 0)` costs ~110 cycles per tcgen05.mma).
   if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol_w = policy_evict_first();  // weights are streamed once per token tile
-      const int rows_valid = min(BT, p.m - m0);
-      // bulk copies need 16-byte granularity: a_scale_stride is a multiple of 4 floats, so rounding up stays in-row
-      const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
-      for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb0 + i;
-        const int st = i % kStages;
-        mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
-        uint8_t* stage = smem + st * S::kStageBytes;
+    const uint64_t pol_w = policy_evict_first();  // weights are streamed once per token tile
+    const int rows_valid = min(BT, p.m - m0);
+    // bulk copies need 16-byte granularity: a_scale_stride is a multiple of 4 floats, so rounding up stays in-row
+    const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
+    for (int i = 0; i < num_kb; ++i) {
+      const int kb = kb0 + i;
+      const int st = i % kStages;
+      mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
+      uint8_t* stage = smem + st * S::kStageBytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars.full[st], S::kWBytes + S::kABytes + scale_bytes);
         tma_load_2d_hint(stage, &p.tm_w, &bars.full[st], kb * 128, n0, pol_w);
         tma_load_2d(stage + S::kWBytes, &p.tm_a, &bars.full[st], kb * 128, m0);
         bulk_load_1d(stage + S::kWBytes + S::kABytesPadded, p.a_scales + (int64_t)kb * p.a_scale_stride + m0,
                      scale_bytes, &bars.full[st]);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BT);
-      const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
-      for (int i = 0; i < num_kb; ++i) {
-        const int st = i % kStages, buf = i & 1;
-        mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
-        mbar_wait(&bars.full[st], (i / kStages) & 1);
-        tc_fence_after();
-        const uint32_t w_addr = smem_u32(smem + st * S::kStageBytes);
-        const uint32_t a_addr = w_addr + S::kWBytes;
+    constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BT);
+    const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % kStages, buf = i & 1;
+      mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&bars.full[st], (i / kStages) & 1);
+      tc_fence_after();
+      const uint32_t w_addr = smem_u32(smem + st * S::kStageBytes);
+      const uint32_t a_addr = w_addr + S::kWBytes;
+      if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < 4; ++s)
           umma_f8(tmem + buf * BT, dk | (uint64_t)(((w_addr + s * 32) >> 4) & 0x3FFF),
@@ -122,6 +127,7 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
         umma_commit(&bars.empty[st]);
         umma_commit(&bars.acc_full[buf]);
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -130,12 +136,20 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
     const int row = quad * 32 + lane;  // weight row within the tile = TMEM lane
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int nb = blockIdx.x;
+    // weight scales of this CTA's k range -> shared memory once (a per-k-block __ldg is an L2 round trip on the
+    // promotion's critical path: there is no L1 left beside 200 KB of stages)
+    float* s_wscale = reinterpret_cast<float*>(smem + S::kOffWScale);
+    const bool ws_smem = num_kb <= kMaxWScaleKb;
+    if (ws_smem) {
+      for (int i = tid - 64; i < num_kb; i += kPromo) s_wscale[i] = __ldg(p.b_scales + (int64_t)nb * total_kb + kb0 + i);
+      named_bar_sync(1, kPromo);
+    }
     float2 acc[CPT / 2];
 #pragma unroll
     for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
     for (int i = 0; i < num_kb; ++i) {
       const int st = i % kStages, buf = i & 1;
-      const float sb = __ldg(p.b_scales + (int64_t)nb * total_kb + kb0 + i);
+      const float sb = ws_smem ? s_wscale[i] : __ldg(p.b_scales + (int64_t)nb * total_kb + kb0 + i);
       const float2 sb2 = make_float2(sb, sb);
       mbar_wait(&bars.acc_full[buf], (i >> 1) & 1);  // implies full[st] completed
       tc_fence_after();
@@ -150,8 +164,11 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
         acc[j / 2 + 1] = fma2(make_float2(v[j + 2], v[j + 3]), mul2(make_float2(s4.z, s4.w), sb2), acc[j / 2 + 1]);
       }
       tc_fence_before();
-      mbar_arrive(&bars.acc_empty[buf]);
-      mbar_arrive(&bars.empty[st]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars.acc_empty[buf]);
+        mbar_arrive(&bars.empty[st]);
+      }
     }
     const int ncol = n0 + row;
     if (p.splits == 1) {
@@ -189,7 +206,8 @@ struct GemmTokMSmem {
   static constexpr int kABytes = 128 * 128;   // token tile
   static constexpr int kWBytes = 256 * 128;   // weight tile
   static constexpr int kStageBytes = kABytes + kWBytes + 1024;  // + 128 activation scales
-  static constexpr int kTotal = kStages * kStageBytes + 1024;
+  static constexpr int kOffWScale = kStages * kStageBytes + 1024;  // [2 weight blocks][<= 128 k-blocks] floats
+  static constexpr int kTotal = kOffWScale + 1024;
 };
 
 __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
@@ -198,7 +216,7 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
   constexpr int BN = 256, CPT = 64, kPromo = 512;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
   struct Bars {
     uint64_t full[kStages], empty[kStages], acc_full[2], acc_empty[2];
     uint32_t tmem_base;
@@ -214,11 +232,11 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&bars.full[i], 1);
-      mbar_init(&bars.empty[i], 1 + kPromo);
+      mbar_init(&bars.empty[i], 1 + kPromo / 32);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&bars.acc_full[i], 1);
-      mbar_init(&bars.acc_empty[i], kPromo);
+      mbar_init(&bars.acc_empty[i], kPromo / 32);  // one arrival per promotion warp: 512 arrivals on one word serialise
     }
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_w);
@@ -232,33 +250,34 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
   pdl_wait_prior_grid();
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint64_t pol_w = policy_evict_first();
-      const int rows_valid = min(128, p.m - m0);
-      const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
-      for (int i = 0; i < num_kb; ++i) {
-        const int kb = kb0 + i;
-        const int st = i % kStages;
-        mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
-        uint8_t* stage = smem + st * S::kStageBytes;
+    const uint64_t pol_w = policy_evict_first();
+    const int rows_valid = min(128, p.m - m0);
+    const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
+    for (int i = 0; i < num_kb; ++i) {
+      const int kb = kb0 + i;
+      const int st = i % kStages;
+      mbar_wait(&bars.empty[st], ((i / kStages) & 1) ^ 1);
+      uint8_t* stage = smem + st * S::kStageBytes;
+      if (elect_one()) {
         mbar_arrive_expect_tx(&bars.full[st], S::kABytes + S::kWBytes + scale_bytes);
         tma_load_2d(stage, &p.tm_a, &bars.full[st], kb * 128, m0);
         tma_load_2d_hint(stage + S::kABytes, &p.tm_w, &bars.full[st], kb * 128, n0, pol_w);
         bulk_load_1d(stage + S::kABytes + S::kWBytes, p.a_scales + (int64_t)kb * p.a_scale_stride + m0, scale_bytes,
                      &bars.full[st]);
       }
+      __syncwarp();
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BN);
-      const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
-      for (int i = 0; i < num_kb; ++i) {
-        const int st = i % kStages, buf = i & 1;
-        mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
-        mbar_wait(&bars.full[st], (i / kStages) & 1);
-        tc_fence_after();
-        const uint32_t a_addr = smem_u32(smem + st * S::kStageBytes);
-        const uint32_t w_addr = a_addr + S::kABytes;
+    constexpr uint32_t idesc = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, BN);
+    const uint64_t dk = make_smem_desc(0, 0, 1024, SWZ_128B);
+    for (int i = 0; i < num_kb; ++i) {
+      const int st = i % kStages, buf = i & 1;
+      mbar_wait(&bars.acc_empty[buf], ((i >> 1) & 1) ^ 1);
+      mbar_wait(&bars.full[st], (i / kStages) & 1);
+      tc_fence_after();
+      const uint32_t a_addr = smem_u32(smem + st * S::kStageBytes);
+      const uint32_t w_addr = a_addr + S::kABytes;
+      if (elect_one()) {
 #pragma unroll
         for (int s = 0; s < 4; ++s)
           umma_f8(tmem + buf * BN, dk | (uint64_t)(((a_addr + s * 32) >> 4) & 0x3FFF),
@@ -266,6 +285,7 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
         umma_commit(&bars.empty[st]);
         umma_commit(&bars.acc_full[buf]);
       }
+      __syncwarp();
     }
   } else {
     const int quad = warp & 3;
@@ -275,12 +295,23 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int nblk = (n0 + cb) / 128;           // weight scale block of this thread's columns
     const bool blk_valid = (n0 + cb) < p.n;
+    // weight scales of this CTA's two 128-row blocks over its k range -> shared memory once (see fp8_gemm_kernel)
+    float* s_wscale = reinterpret_cast<float*>(smem + S::kOffWScale);
+    const bool ws_smem = num_kb <= 128;
+    if (ws_smem) {
+      for (int i = tid - 64; i < 2 * num_kb; i += kPromo) {
+        const int blk = n0 / 128 + i / num_kb;
+        s_wscale[i] = blk * 128 < p.n ? __ldg(p.b_scales + (int64_t)blk * total_kb + kb0 + i % num_kb) : 0.f;
+      }
+      named_bar_sync(1, kPromo);
+    }
+    const float* my_wscale = s_wscale + (cb / 128) * num_kb;
     float2 acc[CPT / 2];
 #pragma unroll
     for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
     for (int i = 0; i < num_kb; ++i) {
       const int st = i % kStages, buf = i & 1;
-      const float sb = blk_valid ? __ldg(p.b_scales + (int64_t)nblk * total_kb + kb0 + i) : 0.f;
+      const float sb = ws_smem ? my_wscale[i] : (blk_valid ? __ldg(p.b_scales + (int64_t)nblk * total_kb + kb0 + i) : 0.f);
       mbar_wait(&bars.acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
       const float sa = reinterpret_cast<const float*>(smem + st * S::kStageBytes + S::kABytes + S::kWBytes)[row];
@@ -292,8 +323,11 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
 #pragma unroll
       for (int j = 0; j < CPT / 2; ++j) acc[j] = fma2(make_float2(v[2 * j], v[2 * j + 1]), s2, acc[j]);
       tc_fence_before();
-      mbar_arrive(&bars.acc_empty[buf]);
-      mbar_arrive(&bars.empty[st]);
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&bars.acc_empty[buf]);
+        mbar_arrive(&bars.empty[st]);
+      }
     }
     const int grow = m0 + row;
     const bool row_ok = grow < p.m;

@@ -154,7 +154,8 @@ def quantize_and_cache_k(key: torch.Tensor, k_lora_cache: torch.Tensor, k_lora_s
                          head_dim_v: int) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
     """flash_mla_interface.py:128-154 -> csrc/flash_api.cpp:462-532: quantise ``key`` rows and scatter them to the
     token slots ``indices`` of the three pool tensors, in place."""
-    for t, n in ((key, "key"), (k_lora_cache, "k_lora_cache"), (k_lora_scale_cache, "k_lora_scale_cache"),
+    _cuda(key, "key")
+    for t, n in ((k_lora_cache, "k_lora_cache"), (k_lora_scale_cache, "k_lora_scale_cache"),
                  (k_rope_cache, "k_rope_cache"), (indices, "indices")):
         _cuda(t, n)
         _require(t.is_contiguous(), "%s must be contiguous" % n)
@@ -162,13 +163,18 @@ def quantize_and_cache_k(key: torch.Tensor, k_lora_cache: torch.Tensor, k_lora_s
     _require(key.dtype == torch.bfloat16, "Unsupported key dtype")
     head_dim = key.shape[-1]
     n = key.numel() // head_dim
+    # rows may be a strided view (e.g. the kv columns of the fused qkv_a projection output): [n, (1,) head_dim] with a
+    # contiguous last dimension and one row stride
+    _require(key.stride(-1) == 1 and key.dim() in (2, 3) and (key.dim() == 2 or key.shape[1] == 1),
+             "key must be [n, head_dim] or [n, 1, head_dim] with a contiguous last dimension")
+    key_row_stride = key.stride(0) if n > 1 else head_dim
     _require(indices.numel() == n, "indices size must match key batch size")
     _require(k_lora_cache.element_size() == 1 and k_lora_cache.shape[-1] == head_dim_v, "k_lora_cache shape/dtype")
     _require(k_lora_scale_cache.dtype == torch.float32, "k_lora_scale_cache must be float32")
     _require(k_rope_cache.dtype == key.dtype and k_rope_cache.shape[-1] == head_dim - head_dim_v, "k_rope_cache shape")
     with torch.cuda.device(key.device):
         _lib.check(
-            _lib.lib().b200_mla_quantize_and_cache_k(key.data_ptr(), head_dim, n, head_dim, head_dim_v,
+            _lib.lib().b200_mla_quantize_and_cache_k(key.data_ptr(), key_row_stride, n, head_dim, head_dim_v,
                                                      indices.data_ptr(), k_lora_cache.data_ptr(),
                                                      k_lora_scale_cache.data_ptr(), k_rope_cache.data_ptr(),
                                                      _lib.current_stream()), "quantize_and_cache_k")

@@ -100,6 +100,25 @@ def test_quantize_and_cache_k_and_dequant_bit_exact(mods):
     assert dl.shape == (0, 1, 512) and dr.shape == (0, 1, 64)
 
 
+def test_quantize_and_cache_k_strided_rows(mods):
+    """key rows as a strided view (the kv columns of the fused qkv_a projection output): same bytes as a contiguous copy."""
+    fm = mods[1]
+    torch.manual_seed(2)
+    wide = (torch.randn(33, 2112, device=DEV) * 2).to(torch.bfloat16)
+    key = wide[:, 1536:].unsqueeze(1)
+    assert not key.is_contiguous()
+    loc = (torch.randperm(64 * 3)[:33] + 64).to(torch.int32).to(DEV)
+    outs = []
+    for k in (key, key.contiguous()):
+        kl = torch.zeros(64 * 4, 1, 512, dtype=torch.uint8, device=DEV)
+        ks = torch.zeros(64 * 4, 1, 1, dtype=torch.float32, device=DEV)
+        kr = torch.zeros(64 * 4, 1, 64, dtype=torch.bfloat16, device=DEV)
+        fm.quantize_and_cache_k(k, kl, ks, kr, loc, 512)
+        outs.append((kl, ks, kr))
+    for a, b in zip(*outs):
+        assert torch.equal(a, b)
+
+
 def test_quantiser_matches_reference_fallback_golden(mods, golden_dir):
     """CUDA quantiser vs the reference's own torch fall-back output (tests/golden/pool_per_token_head.npz)."""
     import os
