@@ -81,7 +81,8 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
   static_assert(CPT == 8 || CPT == 16, "CPT must be 8 or 16");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // round up to 1024 B by pointer arithmetic (an integer round trip would demote every access to generic LD / ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* s_kv = smem + L::kOffKV;
   uint8_t* s_q = smem + L::kOffQ;
   uint8_t* s_p = smem + L::kOffP;
