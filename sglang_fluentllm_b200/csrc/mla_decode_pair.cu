@@ -84,7 +84,7 @@ static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
 constexpr int kTraceTiles = 64;
 constexpr int kTraceRoles = 5;
 __device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
-__device__ unsigned long long g_part_cycles[2 * 128 * 2];  // [part < 128][rank]{globaltimer at entry, at exit} (ns)
+__device__ unsigned long long g_part_cycles[2 * 128 * 4];  // [part < 128][rank]{globaltimer ns at entry, at exit, clock64 at entry, at exit}
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
   if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
 }
@@ -139,7 +139,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   if ((p.trace & 1) && tid == 0 && part < 128 && blockIdx.y == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_part_cycles[(part * 2 + rank) * 2] = t;
+    g_part_cycles[(part * 2 + rank) * 4] = t;
+    g_part_cycles[(part * 2 + rank) * 4 + 2] = clock64();
   }
 
   const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
@@ -865,7 +866,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   if ((p.trace & 1) && tid == 128 && part < 128 && blockIdx.y == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    g_part_cycles[(part * 2 + rank) * 2 + 1] = t;
+    g_part_cycles[(part * 2 + rank) * 4 + 1] = t;
+    g_part_cycles[(part * 2 + rank) * 4 + 3] = clock64();
   }
   tc_fence_before();
   __syncthreads();
@@ -892,7 +894,7 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream)
 
 // Diagnostic: copy the pipeline trace of the last traced pair-kernel launch (see g_trace) to host memory.
 extern "C" int b200_mla_read_part_times(unsigned long long* out, int n) {
-  const int total = 2 * 128 * 2;
+  const int total = 2 * 128 * 4;
   B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_part_cycles, sizeof(unsigned long long) * (n < total ? n : total)));
   return 0;
 }

@@ -251,6 +251,12 @@ MLA_CASES = [
     ("sq4-causal-h16", 2, 16, 4, [300, 65], True),
     ("sq2-causal-h64", 2, 64, 2, [257, 64], True),
     ("sq2-noncausal", 2, 16, 2, [200, 90], False),
+    # M > 64: the CTA-pair kernel (two softmax groups, four S / P tiles, per-request epilogue staging)
+    ("pair-ragged-b5", 5, 128, 1, [1, 64, 129, 2000, 700], False),
+    ("pair-m96", 2, 96, 1, [500, 130], False),                 # second CTA of the pair has 32 valid q rows
+    ("pair-sq2-causal-h128", 2, 128, 2, [300, 65], True),      # M = 256: two pairs per request
+    ("pair-sq4-causal-h32", 2, 32, 4, [300, 200], True),       # M = 128 from s_q = 4
+    ("pair-sq2-m192", 2, 96, 2, [260, 131], True),             # M = 192: a full pair and a half pair
 ]
 
 
@@ -280,6 +286,78 @@ def test_mla_decode_split_long_sequences(mods):
     so, sl = omla.flash_mla_ckv_fp8_semantic(*args)
     assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
     assert rel(out, so) < 5e-2
+
+
+def test_mla_pair_split_long_sequences(mods):
+    """h = 128: 74 scheduler parts over two long requests -> every part boundary falls inside a request (fp32 partials +
+    combine), several tiles per part (steady-state ping-pong of the two softmax groups)."""
+    fm = mods[1]
+    c = make_case(fm, 2, 128, 1, [9000, 4100])
+    out, lse, args, meta, ns = run_mla(fm, c, 128, 1, False)
+    assert (np.diff(ns) > 8).all(), "expected both requests to be split over many parts"
+    so, sl = omla.flash_mla_ckv_fp8_semantic(*args)
+    assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
+    assert rel(out, so) < 5e-2
+    row_err = np.linalg.norm(out - so, axis=-1) / np.maximum(np.linalg.norm(so, axis=-1), 1e-20)
+    assert row_err.max() < 0.2
+
+
+@pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])
+def test_mla_reference_moves_under_growing_logits(mods, h, s_q):
+    """Keys whose norm grows along the sequence make the row maximum (and k_scale) climb tile after tile, so the lazy
+    (m_ref, p_scale) reference has to move again and again: exercises the slow path, the O rescale in TMEM and, in
+    the pair kernel, the version / hand-off protocol between the two softmax groups."""
+    fm = mods[1]
+    torch.manual_seed(5)
+    b, seq = 2, 1536
+    c = make_case(fm, b, h, s_q, [seq, seq - 200], nan_pad=False)
+    n_pages = c["kl"].shape[0]
+    kv = torch.randn(n_pages * 64, 1, 576, device=DEV)
+    # token t of request i lives at page bt[i, t // 64], row t % 64: scale it by 2^(t / 96) (+16 octaves over the sequence)
+    scale = torch.ones(n_pages, 64, device=DEV)
+    for i in range(b):
+        t = torch.arange(seq, device=DEV)
+        pages = c["bt"][i].to(DEV).long()[t // 64]
+        scale[pages, t % 64] = torch.exp2(t.float() / 96.0)
+    kv = (kv * scale.view(-1, 1, 1) * 0.05).to(torch.bfloat16)
+    fm.quantize_and_cache_k(kv, c["kl"].view(-1, 1, 512), c["ks"].view(-1, 1, 1), c["kr"].view(-1, 1, 64),
+                            torch.arange(n_pages * 64, dtype=torch.int32, device=DEV), 512)
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, False)
+    so, sl = omla.flash_mla_ckv_fp8_semantic(*args)
+    assert np.isfinite(out).all() and np.isfinite(lse).all()
+    assert np.allclose(lse, sl, rtol=1e-3, atol=2e-3)
+    assert rel(out, so) < 5e-2
+    # twice the same launch: bit-identical (the recompute-on-stale-reference path must not depend on timing)
+    out2, lse2, _, _, _ = run_mla(fm, c, h, s_q, False)
+    assert np.array_equal(out, out2) and np.array_equal(lse, lse2)
+
+
+def test_mla_pair_full_size_properties(mods):
+    """Metric shape (b = 128, seq = 4096, h = 128): page-permutation invariance, bit for bit, and lse against torch on
+    the de-quantised cache for a sample of requests."""
+    fm = mods[1]
+    b, h, seq = 128, 128, 4096
+    c = make_case(fm, b, h, 1, [seq] * b, nan_pad=False)
+    out1, lse1, _, _, _ = run_mla(fm, c, h, 1, False)
+    n_pages = c["kl"].shape[0]
+    perm = torch.randperm(n_pages - 1) + 1
+    inv = torch.zeros(n_pages, dtype=torch.int64)
+    inv[perm] = torch.arange(1, n_pages)
+    c2 = dict(c)
+    src = torch.cat([torch.zeros(1, dtype=torch.int64), inv[1:]]).to(DEV)
+    c2["kl"], c2["kr"], c2["ks"] = c["kl"][src].contiguous(), c["kr"][src].contiguous(), c["ks"][src].contiguous()
+    c2["bt"] = perm[c["bt"].long() - 1].to(torch.int32)
+    out2, lse2, _, _, _ = run_mla(fm, c2, h, 1, False)
+    assert np.array_equal(out1, out2) and np.array_equal(lse1, lse2)
+    for i in (0, 77):
+        pages = c["bt"][i, : seq // 64].long().to(DEV)
+        kn = c["kl"][pages].view(-1, 512).view(torch.float8_e4m3fn).float() * c["ks"][pages].view(-1, 1)
+        kr = c["kr"][pages].view(-1, 64).float() * c["ks"][pages].view(-1, 1)
+        qn = c["qn"][i, 0].view(torch.float8_e4m3fn).float() * c["qs"][i, 0]
+        qr = c["qr"][i, 0].float() * c["qs"][i, 0]
+        logits = (qn @ kn.t() + qr @ kr.t()) * 576 ** -0.5
+        assert np.allclose(lse1[i, :, 0], torch.logsumexp(logits, dim=-1).cpu().numpy(), rtol=1e-3, atol=1e-3)
+        assert rel(out1[i, 0], (torch.softmax(logits, -1) @ kn).cpu().numpy()) < 5e-2
 
 
 def test_mla_decode_low_noise_input_is_tight(mods):

@@ -82,9 +82,13 @@ for rank in range(2):
         e = tr[rank, 3, sgi, :] - t0
         print(" %7d | %9d %8d %8d | %8d" % (sgi, e[0], e[1], e[2], e[3]))
 
-pt = np.zeros(2 * 128 * 2, dtype=np.uint64)
+pt = np.zeros(2 * 128 * 4, dtype=np.uint64)
 _lib.check(L.b200_mla_read_part_times(pt.ctypes.data, pt.size), "read_part_times")
-pt = pt.reshape(128, 2, 2).astype(np.int64)
+pt = pt.reshape(128, 2, 4).astype(np.int64)
+clk = (pt[:, 0, 3] - pt[:, 0, 2]) / np.maximum(pt[:, 0, 1] - pt[:, 0, 0], 1)  # SM cycles per ns, leader CTA of each part
+print("SM clock during the kernel (clock64 / globaltimer, per part): median %.3f GHz, min %.3f, max %.3f; busy time median %.1f us" % (
+    np.median(clk[:meta.shape[0] - 1]), clk[:meta.shape[0] - 1].min(), clk[:meta.shape[0] - 1].max(),
+    np.median(pt[:meta.shape[0] - 1, 0, 1] - pt[:meta.shape[0] - 1, 0, 0]) / 1e3))
 nparts = meta.shape[0]
 t_first = pt[:nparts, :, 0].min()
 print("per-part timeline (us relative to the first CTA's entry): part | entry r0 r1 | softmax end r0 r1 | busy")
