@@ -329,31 +329,50 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
         mbar_arrive(&bars.empty[st]);
       }
     }
-    const int grow = m0 + row;
-    const bool row_ok = grow < p.m;
+    // Epilogue through shared memory: a thread owns one token row x 64 columns, so storing from registers scatters
+    // 16-byte pieces over 32 rows per instruction (a quarter of the kernel's stall samples at m = 128).  The pipeline
+    // stages are free now (every MMA has retired and every promotion thread is past its last scale read after the
+    // barrier): stage the tile as [128 rows][256 columns], 16-byte chunks XOR-swizzled with (row & 7), then each warp
+    // writes whole rows -- 512 B (bf16) or 2 x 512 B (fp32 split-K partial) of contiguous global memory per instruction.
+    named_bar_sync(1, kPromo);
+    const int pw = warp - 2;  // promotion warp 0 .. 15
     if (p.splits == 1) {
-      if (row_ok) {
-        __nv_bfloat16* dst = p.out + (int64_t)grow * p.n + n0 + cb;
+      uint8_t* srow = smem + row * 512;
 #pragma unroll
-        for (int j = 0; j < CPT; j += 8) {
-          if (n0 + cb + j < p.n) {
-            __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j / 2].x, acc[j / 2].y);
-            __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[j / 2 + 1].x, acc[j / 2 + 1].y);
-            __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[j / 2 + 2].x, acc[j / 2 + 2].y);
-            __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[j / 2 + 3].x, acc[j / 2 + 3].y);
-            *reinterpret_cast<uint4*>(dst + j) = make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                                                            *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-          }
-        }
+      for (int j = 0; j < CPT; j += 8) {
+        __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j / 2].x, acc[j / 2].y);
+        __nv_bfloat162 h1 = __floats2bfloat162_rn(acc[j / 2 + 1].x, acc[j / 2 + 1].y);
+        __nv_bfloat162 h2 = __floats2bfloat162_rn(acc[j / 2 + 2].x, acc[j / 2 + 2].y);
+        __nv_bfloat162 h3 = __floats2bfloat162_rn(acc[j / 2 + 3].x, acc[j / 2 + 3].y);
+        *reinterpret_cast<uint4*>(srow + ((((cb + j) >> 3) ^ (row & 7)) << 4)) =
+            make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                       *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+      }
+      named_bar_sync(1, kPromo);
+      const bool col_ok = n0 + lane * 8 < p.n;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = pw * 8 + it;
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + r * 512 + ((lane ^ (r & 7)) << 4));
+        if (m0 + r < p.m && col_ok) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + lane * 8) = v;
       }
     } else {
-      // split-K: fp32 partial of this split -> its slab of the workspace; splitk_reduce_kernel sums in split order
-      if (row_ok) {
-        float* dst = p.ws + ((int64_t)blockIdx.z * p.m + grow) * p.n + n0 + cb;
+      uint8_t* srow = smem + row * 1024;
 #pragma unroll
-        for (int j = 0; j < CPT; j += 4)
-          if (n0 + cb + j < p.n)
-            *reinterpret_cast<float4*>(dst + j) = make_float4(acc[j / 2].x, acc[j / 2].y, acc[j / 2 + 1].x, acc[j / 2 + 1].y);
+      for (int j = 0; j < CPT; j += 4)
+        *reinterpret_cast<float4*>(srow + ((((cb + j) >> 2) ^ (row & 7)) << 4)) =
+            make_float4(acc[j / 2].x, acc[j / 2].y, acc[j / 2 + 1].x, acc[j / 2 + 1].y);
+      named_bar_sync(1, kPromo);
+      float* slab = p.ws + ((int64_t)blockIdx.z * p.m + m0) * p.n + n0;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = pw * 8 + it;
+#pragma unroll
+        for (int hf = 0; hf < 2; ++hf) {
+          const int c = hf * 32 + lane;  // 16-byte chunk of the 1 KB row
+          const float4 v = *reinterpret_cast<const float4*>(smem + r * 1024 + ((c ^ (r & 7)) << 4));
+          if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
+        }
       }
     }
   }

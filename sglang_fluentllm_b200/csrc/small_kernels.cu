@@ -240,6 +240,9 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     act_quant_1x128_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scales,
                            int64_t num_groups, int groups_per_row, int64_t scale_stride, float eps) {
+  // the GEMM behind this kernel is launched with programmatic stream serialization: let its CTAs start their prologue
+  // (barrier init, TMEM allocation, descriptor prefetch) now; its griddepcontrol.wait still orders the data
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
   const int sub = threadIdx.x & 15;
   if (g >= num_groups) return;
