@@ -50,11 +50,14 @@ __device__ __forceinline__ int mask_len(int s_q, int h_q, int M, int row) {  // 
   return row < M ? s_q - row / h_q - 1 : 0;
 }
 
-__device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_idx, int begin_idx, int begin_seqlen,
-                                                int end_idx, int end_seqlen, int begin_n_split, int q_row0, int hb) {
+// seqlen / num_splits_b: cache_seqlens[batch_idx] and num_splits[batch_idx], loaded by the caller (so that they can be
+// fetched ahead of time: without an L1 every __ldg is an L2 round trip)
+__device__ __forceinline__ Segment make_segment_from(const MlaParams& p, int batch_idx, int seqlen, int num_splits_b,
+                                                     int begin_idx, int begin_seqlen, int end_idx, int end_seqlen,
+                                                     int begin_n_split, int q_row0, int hb) {
   Segment s;
   s.batch_idx = batch_idx;
-  s.seqlen = __ldg(p.seqlens + batch_idx);
+  s.seqlen = seqlen;
   s.start_block = batch_idx == begin_idx ? begin_seqlen / kPage : 0;
   const int full_blocks = (s.seqlen + kPage - 1) / kPage;
   int end_block = batch_idx == end_idx ? (end_seqlen + kPage - 1) / kPage : full_blocks;
@@ -69,8 +72,14 @@ __device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_id
   s.n_tiles = (s.end_block - s.start_block + 1) / 2;
   s.valid_end = min(s.seqlen, s.end_block * kPage);
   const int n_split_idx = batch_idx == begin_idx ? begin_n_split : 0;
-  s.split_idx = __ldg(p.num_splits + batch_idx) + n_split_idx;  // splitkv_mla.cu:1490
+  s.split_idx = num_splits_b + n_split_idx;  // splitkv_mla.cu:1490
   return s;
+}
+
+__device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_idx, int begin_idx, int begin_seqlen,
+                                                int end_idx, int end_seqlen, int begin_n_split, int q_row0, int hb) {
+  return make_segment_from(p, batch_idx, __ldg(p.seqlens + batch_idx), __ldg(p.num_splits + batch_idx), begin_idx,
+                           begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, hb);
 }
 
 // CTA-pair kernel for 64 < M (mla_decode_pair.cu); the Q tensor maps must use 64-row boxes.

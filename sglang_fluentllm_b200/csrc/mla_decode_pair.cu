@@ -507,11 +507,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const int grow = q_row0 + row;            // row within the request's M rows
     uint32_t g0 = 0, o_seg = 0;               // g0: global index of the request's first tile
     uint32_t n_mine = 0;                      // tiles this group has served (trigger-flag ring)
+    // per-request scalars, fetched one request ahead (three dependent L2 round trips otherwise sit between a request's
+    // epilogue and the next request's first tile)
+    int cur_seqlen = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);
+    float cur_qs = row_valid ? __ldg(p.q_scale + (int64_t)begin_idx * p.M + grow) : 0.f;
 
     for (int b = begin_idx; b <= end_idx; ++b) {
-      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      const Segment sg = make_segment_from(p, b, cur_seqlen, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                           begin_n_split, pair_row0, 128);
       // ---- per-request state ----
-      const float f = row_valid ? __ldg(p.q_scale + (int64_t)b * p.M + grow) * p.scale_log2 : 0.f;
+      const float f = cur_qs * p.scale_log2;
+      if (b < end_idx) {  // next request's scalars: in flight while this request runs
+        cur_seqlen = __ldg(p.seqlens + b + 1);
+        cur_ns = __ldg(p.num_splits + b + 1);
+        cur_qs = row_valid ? __ldg(p.q_scale + (int64_t)(b + 1) * p.M + grow) : 0.f;
+      }
       int lim = 0;
       if (row_valid) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, grow), sg.end_block * kPage) : sg.valid_end;
       named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lred / the row state are done
