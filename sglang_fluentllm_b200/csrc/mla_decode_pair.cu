@@ -52,7 +52,7 @@ constexpr int kPBufs = 4;                            // P tiles: a softmax group
 constexpr int kOffKs = kOffP + kPBufs * kPBytes;     // k-scale ring: [kKsStages][128] f32; the four P tiles (32 KB) double
                                                      // as the epilogue's staging tile
 constexpr int kOffSmall = kOffKs + kKsStages * 512;
-constexpr int kTotal = kOffSmall + 5120;
+constexpr int kTotal = kOffSmall + 6144;
 constexpr int kSmThreads = 256;                      // softmax group
 constexpr int kSBufs = 4;                            // S tiles in TMEM: Q.K^T may run kSBufs - 1 tiles ahead of P.V
 constexpr uint32_t kColS = 0, kColO = kSBufs * 64, kTmemCols = 512;
@@ -74,9 +74,9 @@ struct Small {
   uint32_t k_issued;             // tiles whose K page this CTA's producer has issued (orders the V re-read behind it)
   uint32_t trig[2][3];
   float st_mref[64], st_ps[64], st_mprime[64];  // per-row lazy reference: max (log2 domain), P scale, mref + log2(ps)
-  float red1[2][2][64], red2[2][2][64], lred[4][64];
+  float red1[2][2][64], red2[2][2][64], lred[2][4][64];  // lred: row-sum exchange, double-buffered by request parity
 };
-static_assert(sizeof(Small) <= 5120, "Small too large");
+static_assert(sizeof(Small) <= 6144, "Small too large");
 static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
 
 // Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4, 3 epilogue (indexed by
@@ -172,8 +172,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     for (int i = 0; i < 2; ++i) mbar_init(&sm.fin[i], 4);
     mbar_init(&sm.pv_done, 1);
     mbar_init(&sm.o_ready, 1);
-    mbar_init(&sm.o_free, 9);
-    mbar_init(&sm.o_relay, 8);
+    mbar_init(&sm.o_free, 5);   // the four warps of the leader's epilogue group + the peer's relay
+    mbar_init(&sm.o_relay, 4);
     for (int i = 0; i < 3; ++i) sm.trig[0][i] = sm.trig[1][i] = 0;
     sm.version = 0;
     sm.k_issued = 0;
@@ -511,8 +511,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     // epilogue and the next request's first tile)
     int cur_seqlen = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);
     float cur_qs = row_valid ? __ldg(p.q_scale + (int64_t)begin_idx * p.M + grow) : 0.f;
+    if (grp == 0 && page == 0) {
+      sm.st_mref[row] = kMInit;
+      sm.st_ps[row] = 1.f;
+      sm.st_mprime[row] = kMInit;
+    }
+    named_bar_sync(1, kSmThreads);
+    uint32_t rq = 0;  // requests of this part seen so far (parity selects the row-sum exchange buffer)
 
-    for (int b = begin_idx; b <= end_idx; ++b) {
+    for (int b = begin_idx; b <= end_idx; ++b, ++rq) {
       const Segment sg = make_segment_from(p, b, cur_seqlen, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
                                            begin_n_split, pair_row0, 128);
       // ---- per-request state ----
@@ -524,15 +531,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       }
       int lim = 0;
       if (row_valid) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, grow), sg.end_block * kPage) : sg.valid_end;
-      named_bar_sync(1, kSmThreads);  // previous request's readers of sm.lred / the row state are done
-      if (grp == 0 && page == 0) {
-        sm.st_mref[row] = kMInit;
-        sm.st_ps[row] = 1.f;
-        sm.st_mprime[row] = kMInit;
-      }
-      named_bar_sync(1, kSmThreads);
+      // The row state of this request was reset before the first request (below) or by the group that owns this
+      // request's first tile, right after the previous request's last hand-off.  A thread's view starts invalid, so
+      // its first tile loads the state (the other group may already have moved the reference).
       float mprime = kMInit, lsum = 0.f;  // this thread's view of the row reference; lsum is in units of 2^-mprime
-      uint32_t ver = ld_shared_volatile_u32(&sm.version);
+      uint32_t ver = 0xffffffffu;
 
       // This lane's 64 S columns under the reference `mp`, 16 columns at a time (a compact, not unrolled loop: the
       // kernel's hot code stays inside the instruction cache): P' = exp2(s f k - mp) k -> e4m3 straight into the P
@@ -776,37 +779,50 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mprime = mp_fin;
       }
       // ---- epilogue of this request: O / L -> out (or split partials) ----
-      trace(tr && warp == 4, rank, 3, o_seg, 0);
-      sm.lred[slot][row] = lsum;
+      // One group writes the request out while the other starts the next request (its first tile always moves the
+      // reference, ~3k cycles, and the fp32 partial stores drain at ~28 B/clk per SM, ~4.6k cycles): the epilogue group
+      // is the one that does NOT own the next request's first tile (global index g0 now).
+      const int egrp = b < end_idx ? (int)((g0 & 1u) ^ 1u) : 1;
+      sm.lred[rq & 1][slot][row] = lsum;
       named_bar_sync(1, kSmThreads);
-      const float l = (sm.lred[0][row] + sm.lred[1][row]) + (sm.lred[2][row] + sm.lred[3][row]);  // fixed order
-      const bool bad = (l == 0.f || l != l);
-      const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
-      if (sg.n_tiles > 0) {
-        // pv_done completes once per tile and this thread has not waited on it since its last rescale: a parity wait
-        // on it could be two phases behind.  o_ready completes once per request.
-        mbar_wait(&sm.o_ready, o_seg & 1);
-        trace(tr && warp == 4, rank, 3, o_seg, 1);
-        ++o_seg;
-        tc_fence_after();
-      }
-      // O -> global through a shared-memory staging tile, so that every global store instruction writes whole
-      // 128-byte lines: a TMEM lane is a q row, and storing straight from the tcgen05.ld registers would scatter
-      // 16-byte pieces over 32 rows per instruction (measured: ~10k cycles per request, now ~2k).
-      // Staging tile (the two P buffers -- every P.V of this request has retired -- + 16 KB): [64 rows][4 slots][32
-      // values], 16-byte chunks XOR-swizzled with (row & 7); one round per (d half j, 32-column group hh).
-      {
-        uint8_t* stage = s_p;
-        const int wq = warp - 4;
+      const bool had_tiles = sg.n_tiles > 0;
+      if (grp != egrp) {
+        if (b < end_idx) {  // reset the row state for the next request; nobody reads the old one any more
+          if (page == 0) {
+            sm.st_mref[row] = kMInit;
+            sm.st_ps[row] = 1.f;
+            sm.st_mprime[row] = kMInit;
+          }
+          named_bar_sync(gbar, 128);
+        }
+      } else {
+        const bool tr_e = tr && quad == 0;
+        trace(tr_e, rank, 3, o_seg, 0);
+        const float l = (sm.lred[rq & 1][0][row] + sm.lred[rq & 1][1][row]) + (sm.lred[rq & 1][2][row] + sm.lred[rq & 1][3][row]);
+        const bool bad = (l == 0.f || l != l);
+        const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
+        if (had_tiles) {
+          // (not pv_done: it completes once per tile and a parity wait from here could be phases behind)
+          mbar_wait(&sm.o_ready, o_seg & 1);
+          trace(tr_e, rank, 3, o_seg, 1);
+          tc_fence_after();
+        }
+        // O -> global through shared memory, so that every global store instruction writes whole 64 / 128-byte
+        // segments (a TMEM lane is a q row: storing straight from the tcgen05.ld registers scatters 16-byte pieces
+        // over 32 rows per instruction).  Staging = this group's own two P tiles (its next tiles' buffers: every P.V of
+        // this request has retired, and the other group only writes the other two): one 8 KB half per TMEM lane half
+        // (= 128-column block of d), [64 rows][32 values], 16-byte chunks XOR-swizzled; eight rounds of 32 columns.
+        uint8_t* stage_mine = s_p + (egrp + 2 * page) * kPBytes;
         const int64_t grow0 = (int64_t)b * p.M + q_row0;
+        const int gw = warp & 3;  // warp within the group
 #pragma unroll 1
-        for (int r4 = 0; r4 < 4; ++r4) {
-          const int j = r4 >> 1, hh = r4 & 1;
+        for (int r8 = 0; r8 < 8; ++r8) {
+          const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3);  // + 128 * page
           float o[32];
-          if (sg.n_tiles > 0) {
-            tmem_ld<32>(tmem + kColO + j * 128 + ch * 64 + hh * 32 + lane_addr, o);
+          if (had_tiles) {
+            tmem_ld<32>(tmem + kColO + r8 * 32 + lane_addr, o);
             tmem_wait_ld();
-            if (r4 == 3) {  // O is in registers / shared memory: the next request's P.V may overwrite it
+            if (r8 == 7) {  // O is in registers / shared memory: the next request's P.V may overwrite it
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
@@ -816,60 +832,61 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             for (int k = 0; k < 32; ++k) o[k] = 0.f;
           }
           if (sg.no_split) {
-            uint8_t* srow = stage + row * 256;
+            uint8_t* srow = stage_mine + row * 64;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
               __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
               __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
               __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
-              *reinterpret_cast<uint4*>(srow + (((slot * 4 + k) ^ (row & 7)) << 4)) =
+              *reinterpret_cast<uint4*>(srow + ((k ^ ((row >> 1) & 3)) << 4)) =
                   make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
                              *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
           } else {
-            uint8_t* srow = stage + row * 512;
+            uint8_t* srow = stage_mine + row * 128;
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-              *reinterpret_cast<float4*>(srow + (((slot * 8 + k) ^ (row & 7)) << 4)) =
+              *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
                   make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
           }
-          named_bar_sync(1, kSmThreads);
+          named_bar_sync(gbar, 128);
           if (sg.no_split) {
-            // 16 lanes x 16 B per row, two rows per instruction
+            // per instruction: 4 rows x 2 lane halves x 64 B
+            const int k = lane & 3, pg = (lane >> 2) & 1, rr = lane >> 3;
+            const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
 #pragma unroll
             for (int it = 0; it < 4; ++it) {
-              const int r = wq * 8 + it * 2 + (lane >> 4), c = lane & 15;
-              const int sl = c >> 2, k = c & 3;
-              const int d0 = 256 * j + 128 * (sl >> 1) + 64 * (sl & 1) + 32 * hh + 8 * k;
-              const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 256 + ((c ^ (r & 7)) << 4));
-              if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d0) = v;
+              const int r = gw * 16 + it * 4 + rr;
+              const uint4 v = *reinterpret_cast<const uint4*>(src + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+              if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d_base + 128 * pg + 8 * k) = v;
             }
           } else {
-            // 32 lanes x 16 B = one row's four 128-byte segments per instruction
+            // per instruction: 2 rows x 2 lane halves x 128 B
+            const int k = lane & 7, pg = (lane >> 3) & 1, rr = lane >> 4;
+            const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
             float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
-            const int sl = lane >> 3, k = lane & 7;
-            const int d0 = 256 * j + 128 * (sl >> 1) + 64 * (sl & 1) + 32 * hh + 4 * k;
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
-              const int r = wq * 8 + it;
-              const float4 v = *reinterpret_cast<const float4*>(stage + r * 512 + ((lane ^ (r & 7)) << 4));
-              if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d0) = v;
+              const int r = gw * 16 + it * 2 + rr;
+              const float4 v = *reinterpret_cast<const float4*>(src + r * 128 + ((k ^ (r & 7)) << 4));
+              if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d_base + 128 * pg + 4 * k) = v;
             }
           }
-          named_bar_sync(1, kSmThreads);  // the staging tile is rewritten by the next round / the next request's P
+          named_bar_sync(gbar, 128);  // the staging halves are rewritten by the next round / this group's next P tile
+        }
+        if (had_tiles) trace(tr_e, rank, 3, o_seg, 2);
+        if (row_valid && page == 0) {
+          const float lse2 = log2f(l) + mprime;
+          if (sg.no_split) {
+            const int sq = grow / p.h_q, hh = grow % p.h_q;
+            p.lse[((int64_t)b * p.h_q + hh) * p.s_q + sq] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
+          } else {
+            p.lse_accum[(int64_t)sg.split_idx * p.M + grow] = bad ? -INFINITY : lse2;                    // :1506
+          }
         }
       }
-      if (sg.n_tiles > 0) trace(tr && warp == 4, rank, 3, o_seg - 1, 2);
-      if (row_valid && slot == 0) {
-        const float lse2 = log2f(l) + mprime;
-        if (sg.no_split) {
-          const int s = grow / p.h_q, h = grow % p.h_q;
-          p.lse[((int64_t)b * p.h_q + h) * p.s_q + s] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
-        } else {
-          p.lse_accum[(int64_t)sg.split_idx * p.M + grow] = bad ? -INFINITY : lse2;                    // :1506
-        }
-      }
+      if (had_tiles) ++o_seg;
     }
   }
 
