@@ -146,6 +146,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
   const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
             end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
+  // the split-KV combine kernel behind this one is launched with programmatic stream serialization: its CTAs may be
+  // scheduled as soon as SMs drain (its griddepcontrol.wait orders the reads of the partials)
+  pdl_launch_dependents();
   if (begin_idx >= p.batch) return;  // splitkv_mla.cu:1226 (both CTAs of the pair take the same exit)
 
   if (tid == 0) {
