@@ -234,8 +234,10 @@ class HotPath:
         k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
         fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
         q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
-        # absorbed q [b, 1, h, 576]: the w_kc bmm is outside the path; reuse q_full's leading columns as the data source
-        q_abs = (self.q_abs.view(b, 1, h, 9, 64) + q_full[:, : h * 64].view(b, 1, h, 1, 64)).view(b, 1, h, KV_LORA + ROPE)
+        # absorbed q [b, 1, h, 576]: the w_kc bmm + rope are outside the path; their stand-in refreshes 64 of the 576
+        # columns of a resident random q from this step's q_b_proj output
+        q_abs = self.q_abs
+        q_abs[..., :64].copy_(q_full[:, : h * 64].view(b, 1, h, 64))  # one small strided copy, not a 19 MB broadcast add
         q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
         n_pages = self.n_pages
         out, _ = fm.flash_mla_ckv_fp8_per_token(
