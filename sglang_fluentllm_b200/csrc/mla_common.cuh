@@ -35,7 +35,7 @@ struct MlaParams {
   int is_causal;
   const uint8_t* k_lora_base;  // raw pool pointers (bulk L2 prefetch)
   const uint8_t* k_rope_base;
-  int pf_mode;   // diagnostic: 0 tensor-map prefetch, 1 none, 2 bulk prefetch
+  int pf_mode;   // pair kernel's L2 prefetch of upcoming K pages: 0 tensor-map prefetch, 1 none, 2 bulk prefetch (default)
   int pf_tiles;  // pair kernel: L2 prefetch distance of the K pages, in 128-token tiles (>= 2)
   int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)
 };
