@@ -90,6 +90,18 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
                                       float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
                                       size_t workspace_bytes, int use_pdl, void* stream);
 
+/* Paged MLA decode attention over a bf16 KV cache (split-KV + combine), no quantisation anywhere.
+ * Replaces flash_mla_fp8.flash_mla_with_kvcache / flash_mla_swap.flash_mla_with_kvcache
+ * (flash_mla_fp8/flash_mla_interface.py:26-66 -> csrc/flash_api.cpp:65-214 -> csrc/kernels/splitkv_mla.cu), the call
+ * the backend makes when the pool is not per-token FP8 (python/sglang/srt/layers/attention/flashmla_backend.py:240-256).
+ *   q bf16 [b][s_q][h_q][576] contiguous   k_cache bf16 [num_pages*64][576] (token-major; V = first 512 dims)
+ *   other arguments, outputs and workspace as b200_mla_decode_ckv_fp8_per_token. */
+int b200_mla_decode_bf16(const void* q, const void* k_cache, int64_t num_pages, const int32_t* block_table,
+                         int64_t block_table_stride, const int32_t* cache_seqlens,
+                         const int32_t* tile_scheduler_metadata, const int32_t* num_splits, int num_sm_parts,
+                         int batch, int s_q, int h_q, float softmax_scale, int is_causal, void* out, float* lse,
+                         void* workspace, size_t workspace_bytes, int use_pdl, void* stream);
+
 /* Split-KV combine (also run by the decode call).  Replaces ckv_fp8_per_token/mla_combine.cu:16-154. */
 int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
                      int batch, int s_q, int h_q, int use_pdl, void* stream);

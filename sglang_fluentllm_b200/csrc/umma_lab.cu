@@ -9,6 +9,8 @@
 //   2  fp8  A MN-major SW128 (TMA, the K-tile re-read as V^T)  x  B MN-major no-swizzle (thread-written P)
 //   3  as 2 with the LBO/SBO roles of B exchanged (diagnostic)
 //   4  fp8  A MN-major SW128 x B K-major SW128 thread-written (fallback layout for P)
+//   5  bf16 A MN-major SW128, M = 128 dims = two 64-dim chunks (LBO = chunk stride)  x  B K-major SW128 thread-written
+//      bf16 P[q][tok], two 64-token chunks                              -> P.V of the bf16-KV kernel (mla_decode_bf16.cu)
 #include <math.h>
 #include <stdlib.h>
 #include <string.h>
@@ -35,13 +37,15 @@ struct LabParams {
   uint32_t a_kstep, b_kstep;  // bytes added to the start address per k-step
   uint32_t b_chunk_stride, b_group_stride;
   uint32_t k_total;  // K extent (tokens) for thread-written B
+  int a_chunks;      // > 1: A is loaded as a_chunks boxes of 64 bf16 columns, 16 KB apart
+  uint32_t b_kstep_hi;  // != 0: B start address advances b_kstep per k-step within groups of 4 and b_kstep_hi per group
 };
 
 __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant__ LabParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* s_a = smem;           // 16 KB
-  uint8_t* s_b = smem + 16384;   // 32 KB
+  uint8_t* s_a = smem;           // 32 KB
+  uint8_t* s_b = smem + 32768;   // 32 KB
   __shared__ uint64_t bar_load, bar_mma;
   __shared__ uint32_t tmem_base_slot;
 
@@ -59,8 +63,9 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
   const uint32_t tmem = tmem_base_slot;
 
   if (tid == 0) {
-    uint32_t bytes = p.a_rows * 128;
+    uint32_t bytes = p.a_rows * 128 * (p.a_chunks > 1 ? p.a_chunks : 1);
     tma_load_2d(s_a, &p.tm_a, &bar_load, 0, 0);
+    for (int c = 1; c < p.a_chunks; ++c) tma_load_2d(s_a + c * 16384, &p.tm_a, &bar_load, c * 64, 0);
     if (p.b_mode == 0) {
       tma_load_2d(s_b, &p.tm_b, &bar_load, 0, 0);
       bytes += p.n * 128;
@@ -85,6 +90,18 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
       s_b[off] = p.b_raw[(size_t)k * p.n + n];
     }
     fence_proxy_async_smem();
+  } else if (p.b_mode == 3) {
+    // bf16 P[q][tok], K-major SW128, 64-token chunks n * 128 B apart: thread t = token writes its n values
+    const uint16_t* raw = reinterpret_cast<const uint16_t*>(p.b_raw);  // logical [K tokens][N]
+    const int t = tid;
+    if (t < (int)p.k_total) {
+      for (int q = 0; q < p.n; ++q) {
+        const uint32_t off = (t >> 6) * p.n * 128 + (q >> 3) * 1024 + (q & 7) * 128 +
+                             (((((t & 63) >> 3) ^ (q & 7)) & 7) << 4) + (t & 7) * 2;
+        *reinterpret_cast<uint16_t*>(s_b + off) = raw[(size_t)t * p.n + q];
+      }
+    }
+    fence_proxy_async_smem();
   }
   __syncthreads();
 
@@ -95,7 +112,8 @@ __global__ void __launch_bounds__(128, 1) umma_lab_kernel(const __grid_constant_
                                       p.b_mn_major, 128, p.n);
     for (int k = 0; k < p.num_k_steps; ++k) {
       uint64_t da = make_smem_desc(smem_u32(s_a) + k * p.a_kstep, p.a_lbo, p.a_sbo, p.a_layout);
-      uint64_t db = make_smem_desc(smem_u32(s_b) + k * p.b_kstep, p.b_lbo, p.b_sbo, p.b_layout);
+      const uint32_t b_off = p.b_kstep_hi ? (k & 3) * p.b_kstep + (k >> 2) * p.b_kstep_hi : k * p.b_kstep;
+      uint64_t db = make_smem_desc(smem_u32(s_b) + b_off, p.b_lbo, p.b_sbo, p.b_layout);
       if (p.kind) umma_f16(tmem, da, db, idesc, k > 0);
       else umma_f8(tmem, da, db, idesc, k > 0);
     }
@@ -376,7 +394,7 @@ extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
   memset(&p, 0, sizeof(p));
   p.n = n;
   const int K_BYTES = 128;
-  std::vector<uint8_t> hA(128 * K_BYTES), hB((size_t)256 * K_BYTES);
+  std::vector<uint8_t> hA(128 * K_BYTES * 2), hB((size_t)256 * K_BYTES);  // A: room for the two-chunk bf16 image
   srand(1234 + variant);
   auto rnd_e4m3 = [] {
     uint8_t c;
@@ -445,6 +463,25 @@ extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
       if (variant == 2) { p.b_lbo = p.b_chunk_stride; p.b_sbo = p.b_group_stride; }
       else              { p.b_lbo = p.b_group_stride; p.b_sbo = p.b_chunk_stride; }
     }
+  } else if (variant == 5) {
+    // A image = bf16 KV tile [128 tokens][128 dims]; used MN-major: D[d][q] = sum_t A[t][d] * P[t][q]
+    B200_CHECK(n <= 64, "selftest variant 5: n <= 64");
+    uint16_t* a16 = reinterpret_cast<uint16_t*>(hA.data());
+    uint16_t* b16 = reinterpret_cast<uint16_t*>(hB.data());
+    for (int i = 0; i < 128 * 128; ++i) a16[i] = (uint16_t)(0x3C00 + (rand() & 0x3FF) + ((rand() & 1) << 15));
+    for (int i = 0; i < 128 * n; ++i) b16[i] = (uint16_t)(0x3C00 + (rand() & 0x3FF) + ((rand() & 1) << 15));
+    for (int d = 0; d < 128; ++d)
+      for (int j = 0; j < n; ++j) {
+        float acc = 0;
+        for (int t = 0; t < 128; ++t) acc += bf16_to_float(a16[t * 128 + d]) * bf16_to_float(b16[(size_t)t * n + j]);
+        expect[(size_t)d * n + j] = acc;
+      }
+    p.kind = 1; p.num_k_steps = 8; p.a_rows = 128; p.k_total = 128; p.a_chunks = 2;
+    p.a_mn_major = 1; p.a_layout = SWZ_128B; p.a_sbo = 1024; p.a_lbo = 16384; p.a_kstep = 16 * 128;
+    rc |= make_tma_2d(&p.tm_a, dA, 2, 128, 128, 256, 64, 128, TmaSwizzle::B128);
+    p.b_raw = dB;
+    p.b_mode = 3; p.b_mn_major = 0; p.b_layout = SWZ_128B; p.b_sbo = 1024; p.b_lbo = 0; p.b_kstep = 32;
+    p.b_kstep_hi = n * 128;
   } else {
     set_last_error("selftest: unknown variant %d", variant);
     rc = 1;
@@ -452,7 +489,7 @@ extern "C" int b200_umma_selftest(int variant, int n, float* rel_err) {
   if (rc == 0) {
     cudaMemcpy(dA, hA.data(), hA.size(), cudaMemcpyHostToDevice);
     cudaMemcpy(dB, hB.data(), hB.size(), cudaMemcpyHostToDevice);
-    const int smem_bytes = 1024 + 16384 + 32768;
+    const int smem_bytes = 1024 + 32768 + 32768;
     cudaFuncSetAttribute(umma_lab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     umma_lab_kernel<<<1, 128, smem_bytes>>>(p);
     cudaError_t e = cudaDeviceSynchronize();

@@ -208,28 +208,60 @@ def dequantize_ckv_fused_indexed(k_lora_cache: torch.Tensor, k_rope_cache: torch
 
 def flash_mla_with_kvcache(q: torch.Tensor, k_cache: torch.Tensor, block_table: torch.Tensor,
                            cache_seqlens: torch.Tensor, head_dim_v: int, tile_scheduler_metadata: torch.Tensor,
-                           num_splits: torch.Tensor, softmax_scale: Optional[float] = None,
-                           causal: bool = False) -> Tuple[torch.Tensor, torch.Tensor]:
-    """bf16-KV entry point of the reference module (flash_mla_interface.py:26-66).  The B200 path is FP8-KV only: the
-    call quantises q and the referenced pages with the path's own quantisers and runs the FP8 kernel, so the result
-    carries per-token-FP8 rounding (documented deviation; the reference's FP8-KV mode never takes this entry,
-    python/sglang/srt/layers/attention/flashmla_backend.py:205-222)."""
-    _cuda(q, "q")
-    _require(q.dtype == torch.bfloat16 and k_cache.dtype == torch.bfloat16, "q / k_cache must be bfloat16")
-    _require(k_cache.dim() == 4 and k_cache.shape[1] == PAGE_BLOCK_SIZE and k_cache.shape[2] == 1,
-             "k_cache must be (num_blocks, 64, 1, d)")
+                           num_splits: torch.Tensor, softmax_scale: Optional[float] = None, causal: bool = False,
+                           out: Optional[torch.Tensor] = None, lse: Optional[torch.Tensor] = None,
+                           workspace: Optional[torch.Tensor] = None,
+                           use_pdl: bool = True) -> Tuple[torch.Tensor, torch.Tensor]:
+    """bf16-KV entry point of the reference module (flash_mla_interface.py:26-66 -> csrc/flash_api.cpp:65-214), also the
+    API of ``flash_mla_swap`` (flashmla-swap/flash_mla_swap/flash_mla_interface.py:26-66).
+
+    q (b, s_q, h_q, 576) bf16; k_cache (num_blocks, 64, 1, 576) bf16; block_table (b, max_blocks) int32;
+    cache_seqlens (b) int32.  Returns (out (b, s_q, h_q, head_dim_v) bf16, softmax_lse (b, h_q, s_q) f32).
+    Runs the bf16 kernel (csrc/mla_decode_bf16.cu): nothing is quantised on this entry."""
+    for t, n in ((q, "q"), (k_cache, "k_cache"), (block_table, "block_table"), (cache_seqlens, "seqlens_k"),
+                 (tile_scheduler_metadata, "tile_scheduler_metadata"), (num_splits, "num_splits")):
+        _cuda(t, n)
+    _require(q.dtype == torch.bfloat16, "q must be bfloat16")  # flash_api.cpp:84
+    _require(k_cache.dtype == q.dtype, "query and key must have the same dtype")
+    _require(q.dim() == 4, "q must be 4-D (b, s_q, h_q, d)")
+    b, s_q, h_q, d = q.shape
+    _require(head_dim_v == 512 and d == 576, "only head_dim=576 / head_dim_v=512 is supported")  # flash_api.cpp:103-105
+    _require(k_cache.dim() == 4 and k_cache.shape[1] == PAGE_BLOCK_SIZE and k_cache.shape[2] == 1
+             and k_cache.shape[3] == d, "k_cache must be (num_blocks, 64, 1, 576)")
+    _require(q.stride(-1) == 1 and k_cache.stride(-1) == 1, "q / k_cache must have contiguous last dimension")
+    _require(block_table.dtype == torch.int32, "block_table must have dtype torch.int32")
+    _require(block_table.stride(-1) == 1, "block_table must have contiguous last dimension")
+    _require(cache_seqlens.dtype == torch.int32, "seqlens_k must have dtype int32")
+    _require(block_table.shape[0] == b and cache_seqlens.numel() == b, "batch size mismatch")
+    for t, n in ((cache_seqlens, "seqlens_k"), (tile_scheduler_metadata, "tile_scheduler_metadata"),
+                 (num_splits, "num_splits")):
+        _require(t.is_contiguous(), "%s must be contiguous" % n)
+    _require(tile_scheduler_metadata.dtype == torch.int32 and tile_scheduler_metadata.dim() == 2
+             and tile_scheduler_metadata.shape[1] == TILE_SCHEDULER_METADATA_SIZE,
+             "tile_scheduler_metadata must be int32 (num_sm_parts, 8)")
+    _require(num_splits.dtype == torch.int32 and num_splits.numel() == b + 1, "num_splits must be int32 (batch + 1)")
     if softmax_scale is None:
-        softmax_scale = q.shape[-1] ** (-0.5)
-    nb = k_cache.shape[0]
-    d = k_cache.shape[-1]
+        softmax_scale = d ** (-0.5)  # flash_mla_interface.py:52-53
+    q = q.contiguous()
+    k_cache = k_cache.contiguous()
+    num_blocks = k_cache.shape[0]
+    num_sm_parts = tile_scheduler_metadata.shape[0]
+    L = _lib.lib()
     dev = q.device
-    k_lora = torch.empty(nb * PAGE_BLOCK_SIZE, 1, head_dim_v, dtype=torch.uint8, device=dev)
-    k_scale = torch.empty(nb * PAGE_BLOCK_SIZE, 1, 1, dtype=torch.float32, device=dev)
-    k_rope = torch.empty(nb * PAGE_BLOCK_SIZE, 1, d - head_dim_v, dtype=torch.bfloat16, device=dev)
-    idx = torch.arange(nb * PAGE_BLOCK_SIZE, dtype=torch.int32, device=dev)
-    quantize_and_cache_k(k_cache.contiguous().view(-1, 1, d), k_lora, k_scale, k_rope, idx, head_dim_v)
-    q_nope, q_scale, q_rope = quantize_ckv_per_token_head(q.contiguous(), head_dim_v)
-    return flash_mla_ckv_fp8_per_token(
-        q_nope, q_rope, k_lora.view(nb, PAGE_BLOCK_SIZE, 1, head_dim_v), k_rope.view(nb, PAGE_BLOCK_SIZE, 1, -1),
-        q_scale, k_scale.view(nb, PAGE_BLOCK_SIZE, 1, 1), block_table, cache_seqlens, head_dim_v,
-        tile_scheduler_metadata, num_splits, softmax_scale, causal)
+    with torch.cuda.device(dev):
+        if out is None:
+            out = torch.empty(b, s_q, h_q, head_dim_v, dtype=torch.bfloat16, device=dev)
+        if lse is None:
+            lse = torch.empty(b, h_q, s_q, dtype=torch.float32, device=dev)
+        ws_bytes = L.b200_mla_workspace_bytes(b, s_q, h_q, num_sm_parts)
+        if workspace is None:
+            workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+        _require(workspace.numel() * workspace.element_size() >= ws_bytes, "workspace too small")
+        _lib.check(
+            L.b200_mla_decode_bf16(q.data_ptr(), k_cache.data_ptr(), num_blocks, block_table.data_ptr(),
+                                   block_table.stride(0), cache_seqlens.data_ptr(), tile_scheduler_metadata.data_ptr(),
+                                   num_splits.data_ptr(), num_sm_parts, b, s_q, h_q, float(softmax_scale),
+                                   int(bool(causal)), out.data_ptr(), lse.data_ptr(), workspace.data_ptr(),
+                                   workspace.numel() * workspace.element_size(), int(bool(use_pdl)),
+                                   _lib.current_stream()), "flash_mla_with_kvcache")
+    return out, lse

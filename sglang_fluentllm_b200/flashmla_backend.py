@@ -125,41 +125,62 @@ class KVAllocator:
 
 
 class MLATokenToKVPool:
-    """Per-layer MLA KV pool in the ``per_token_head`` layout (mem_cache/memory_pool.py:635-649): for every layer a
-    tuple (k_lora uint8/e4m3 [size+page, 1, 512], k_scale f32 [size+page, 1, 1], k_rope bf16 [size+page, 1, 64]) --
-    644 bytes per token per layer; page 0 absorbs padded writes."""
+    """Per-layer MLA KV pool (mem_cache/memory_pool.py:604-880), both layouts the FlashMLA backend reads:
+
+    * ``quant_method="per_token_head"`` (memory_pool.py:635-649): for every layer a tuple (k_lora uint8/e4m3
+      [size+page, 1, 512], k_scale f32 [size+page, 1, 1], k_rope bf16 [size+page, 1, 64]) -- 644 bytes per token per
+      layer;
+    * ``quant_method="none"`` (memory_pool.py:650-660): one bf16 tensor [size+page, 1, 576] per layer -- 1152 bytes
+      per token per layer.
+
+    Page 0 absorbs padded writes."""
 
     def __init__(self, size: int, model_dtype: torch.dtype, kv_lora_rank: int, qk_rope_head_dim: int, layer_num: int,
-                 device, page_size: int = PAGE_SIZE):
+                 device, page_size: int = PAGE_SIZE, quant_method: str = "per_token_head"):
         assert model_dtype == torch.bfloat16 and kv_lora_rank == 512 and qk_rope_head_dim == 64
+        if quant_method not in ("per_token_head", "none"):
+            raise ValueError("unknown kv cache quant method %r" % (quant_method,))
         self.size, self.page_size, self.device = size, page_size, device
         self.kv_lora_rank, self.qk_rope_head_dim, self.model_dtype = kv_lora_rank, qk_rope_head_dim, model_dtype
-        self.quant_method = "per_token_head"
-        self.dtype = torch.float8_e4m3fn
-        self.store_dtype = torch.uint8
+        self.quant_method = quant_method
         n = size + page_size
-        self.kv_buffer = [(torch.zeros((n, 1, kv_lora_rank), dtype=torch.uint8, device=device),
-                           torch.zeros((n, 1, 1), dtype=torch.float32, device=device),
-                           torch.zeros((n, 1, qk_rope_head_dim), dtype=model_dtype, device=device))
-                          for _ in range(layer_num)]
+        if quant_method == "per_token_head":
+            self.dtype = torch.float8_e4m3fn
+            self.store_dtype = torch.uint8
+            self.kv_buffer = [(torch.zeros((n, 1, kv_lora_rank), dtype=torch.uint8, device=device),
+                               torch.zeros((n, 1, 1), dtype=torch.float32, device=device),
+                               torch.zeros((n, 1, qk_rope_head_dim), dtype=model_dtype, device=device))
+                              for _ in range(layer_num)]
+        else:
+            self.dtype = self.store_dtype = model_dtype
+            self.kv_buffer = [torch.zeros((n, 1, kv_lora_rank + qk_rope_head_dim), dtype=model_dtype, device=device)
+                              for _ in range(layer_num)]
 
     def get_key_buffer(self, layer_id: int):
         return self.kv_buffer[layer_id]  # memory_pool.py:810-811
 
     def get_value_buffer(self, layer_id: int):
-        return self.kv_buffer[layer_id][:2]  # memory_pool.py:844-845
+        if self.quant_method == "per_token_head":
+            return self.kv_buffer[layer_id][:2]  # memory_pool.py:844-845
+        return self.kv_buffer[layer_id][..., : self.kv_lora_rank]  # memory_pool.py:846-849
 
     def set_kv_buffer(self, layer, loc: torch.Tensor, cache_k: torch.Tensor, cache_v=None):
-        """memory_pool.py:854-871 (sm90 branch): quantise + scatter in one kernel."""
-        k_lora, k_scale, k_rope = self.kv_buffer[layer.layer_id]
-        flash_mla_fp8.quantize_and_cache_k(key=cache_k.contiguous(), k_lora_cache=k_lora, k_lora_scale_cache=k_scale,
-                                           k_rope_cache=k_rope, indices=loc.to(torch.int32),
-                                           head_dim_v=self.kv_lora_rank)
+        """memory_pool.py:854-871: quantise + scatter in one kernel (per-token FP8) or a plain indexed store."""
+        if self.quant_method == "per_token_head":
+            k_lora, k_scale, k_rope = self.kv_buffer[layer.layer_id]
+            flash_mla_fp8.quantize_and_cache_k(key=cache_k.contiguous(), k_lora_cache=k_lora,
+                                               k_lora_scale_cache=k_scale, k_rope_cache=k_rope,
+                                               indices=loc.to(torch.int32), head_dim_v=self.kv_lora_rank)
+        else:
+            self.kv_buffer[layer.layer_id][loc] = cache_k.view(-1, 1, cache_k.shape[-1]).to(self.model_dtype)
 
     def get_key_split_contiguous(self, layer_id: int, indices: torch.Tensor):
         """memory_pool.py:817-824."""
-        k_lora, k_scale, k_rope = self.kv_buffer[layer_id]
-        return flash_mla_fp8.dequantize_ckv_fused_indexed(k_lora, k_rope, k_scale, indices.to(torch.int32))
+        if self.quant_method == "per_token_head":
+            k_lora, k_scale, k_rope = self.kv_buffer[layer_id]
+            return flash_mla_fp8.dequantize_ckv_fused_indexed(k_lora, k_rope, k_scale, indices.to(torch.int32))
+        rows = self.kv_buffer[layer_id][indices.long()]
+        return rows[..., : self.kv_lora_rank].contiguous(), rows[..., self.kv_lora_rank:].contiguous()
 
 
 class FlashMLADecodeMetadata:
@@ -185,8 +206,9 @@ class FlashMLABackend(AttentionBackend):
         self.multi_step_seqlen_incr = multi_step_seqlen_incr
         self.cache_dtype = model_runner.kv_cache_dtype
         self.cache_quant_method = model_runner.kv_cache_quant_method
-        if self.cache_quant_method != "per_token_head":
-            raise RuntimeError("FlashMLABackend (B200): only --kv-cache-quant-method per_token_head is implemented; "
+        if self.cache_quant_method != "per_token_head" and self.cache_dtype == torch.float8_e4m3fn:
+            # flashmla_backend.py:225-239 passes descale_q / descale_k that neither shipped kernel module accepts
+            raise RuntimeError("FlashMLABackend (B200): an FP8 KV cache needs --kv-cache-quant-method per_token_head; "
                                "the reference's other FP8 branch is dead code (SURVEY.md 8a-2)")
         self.num_q_heads = cfg.num_attention_heads // attn_tp_size
         self.num_local_heads = self.num_q_heads
@@ -203,7 +225,8 @@ class FlashMLABackend(AttentionBackend):
         self.device = getattr(model_runner, "device", "cuda")
 
     def get_flash_mla_module(self, M):
-        """flashmla_backend.py:18-22,84-85.  One module on B200: the kernel is SwapAB *and* FP8 for every M."""
+        """flashmla_backend.py:18-22,84-85.  One module on B200: it serves every M (SwapAB below 64 q rows, CTA pairs
+        above) for the per-token-FP8 pool and carries the bf16 kernel of both reference forks."""
         return flash_mla_fp8
 
     # ------------------------------------------------------------------ attention calls
@@ -213,6 +236,17 @@ class FlashMLABackend(AttentionBackend):
         assert layer.tp_q_head_num == self.num_q_heads, f"{layer.tp_q_head_num=} != {self.num_q_heads=}"
         reshape_q = q.view(bs, -1, self.num_q_heads, layer.head_dim)
         mod = self.get_flash_mla_module(reshape_q.shape[1] * reshape_q.shape[2])
+        if self.cache_quant_method != "per_token_head":
+            # bf16 pool (flashmla_backend.py:240-256): the bf16 kernel, nothing quantised
+            o, _ = mod.flash_mla_with_kvcache(
+                q=reshape_q, k_cache=k_cache.view(-1, PAGE_SIZE, 1, self.kv_cache_dim),
+                block_table=self.forward_metadata.block_table[:bs],
+                cache_seqlens=cache_seqlens.to(torch.int32),
+                head_dim_v=self.kv_lora_rank,
+                tile_scheduler_metadata=self.forward_metadata.flashmla_metadata,
+                num_splits=self.forward_metadata.num_splits,
+                softmax_scale=layer.scaling, causal=True)
+            return o.view(-1, layer.tp_q_head_num * layer.v_head_dim)
         q_nope, q_scale, q_rope = mod.quantize_ckv_per_token_head(reshape_q.contiguous(), self.kv_lora_rank)
         k_cache_lora, k_scale, k_cache_rope = k_cache
         o, _ = mod.flash_mla_ckv_fp8_per_token(

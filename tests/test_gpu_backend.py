@@ -16,16 +16,18 @@ DEV = "cuda:0"
 SCALING = 192 ** -0.5  # DeepSeek-V2/V3 MLA: (qk_nope 128 + rope 64) ** -0.5
 
 
-def _runner(heads, draft_tokens=0, max_bs=8, context_len=2048):
+def _runner(heads, draft_tokens=0, max_bs=8, context_len=2048, quant_method="per_token_head"):
     from sglang_fluentllm_b200 import flashmla_backend as fb
     alloc = fb.KVAllocator(size=64 * 256, device=DEV, max_batch_size=max_bs, max_context_len=context_len)
     pool = fb.MLATokenToKVPool(size=64 * 256, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
-                               layer_num=2, device=DEV)
+                               layer_num=2, device=DEV, quant_method=quant_method)
     cfg = SimpleNamespace(scaling=SCALING, num_attention_heads=heads, kv_lora_rank=512, qk_nope_head_dim=128,
                           qk_rope_head_dim=64, v_head_dim=512, context_len=context_len)
     sa = SimpleNamespace(speculative_algorithm="EAGLE" if draft_tokens else None, speculative_num_draft_tokens=draft_tokens)
-    mr = SimpleNamespace(model_config=cfg, server_args=sa, kv_cache_dtype=torch.float8_e4m3fn,
-                         kv_cache_quant_method="per_token_head", kv_allocator=alloc, dtype=torch.bfloat16, device=DEV)
+    fp8_kv = quant_method == "per_token_head"
+    mr = SimpleNamespace(model_config=cfg, server_args=sa,
+                         kv_cache_dtype=torch.float8_e4m3fn if fp8_kv else torch.bfloat16,
+                         kv_cache_quant_method=quant_method, kv_allocator=alloc, dtype=torch.bfloat16, device=DEV)
     layer = SimpleNamespace(layer_id=1, tp_q_head_num=heads, head_dim=576, v_head_dim=512, scaling=SCALING)
     return fb, mr, alloc, pool, layer
 
@@ -85,6 +87,31 @@ def test_backend_forward_decode_eager(heads):
     assert _rel(out.view(bs, 1, heads, 512), ref) < 5e-2
     # the block table the kernel walked is the allocator's gather, bit for bit
     assert torch.equal(backend.forward_metadata.block_table, alloc.req_to_page[fbatch.req_pool_indices])
+
+
+@pytest.mark.parametrize("heads,draft", [(16, 0), (128, 0), (16, 4)])
+def test_backend_bf16_pool(heads, draft):
+    """--kv-cache-quant-method none: bf16 pool, the backend's third branch (flashmla_backend.py:240-256) -> the bf16
+    kernel.  Decode and speculative target-verify, against fp32 attention over the pool rows (bf16 tolerance)."""
+    fb, mr, alloc, pool, layer = _runner(heads, draft_tokens=draft, quant_method="none")
+    ctx = [130, 64, 700, 1]
+    bs, n_q = len(ctx), max(draft, 1)
+    ctx_locs = _fill_context(alloc, pool, layer, ctx)
+    backend = fb.FlashMLABackend(mr)
+    new_loc = torch.cat([alloc.alloc(i, n_q, n) for i, n in enumerate(ctx)])
+    mode = fb.ForwardMode.TARGET_VERIFY if draft else fb.ForwardMode.DECODE
+    seq_lens = torch.tensor(ctx if draft else [n + 1 for n in ctx], device=DEV)
+    fbatch = SimpleNamespace(batch_size=bs, seq_lens=seq_lens, req_pool_indices=torch.arange(bs, device=DEV),
+                             out_cache_loc=new_loc, token_to_kv_pool=pool, forward_mode=mode)
+    backend.init_forward_metadata(fbatch)
+    torch.manual_seed(1)
+    q = torch.randn(bs * n_q, heads * 576, dtype=torch.bfloat16, device=DEV)
+    k_new = torch.randn(bs * n_q, 1, 576, dtype=torch.bfloat16, device=DEV)
+    out = backend.forward(q, k_new, k_new[..., :512], layer, fbatch)
+    assert out.shape == (bs * n_q, heads * 512) and out.dtype == torch.bfloat16
+    all_locs = [torch.cat([ctx_locs[i], new_loc[i * n_q:(i + 1) * n_q]]) for i in range(bs)]
+    ref = _reference(pool, layer, q.view(bs, n_q, heads, 576), all_locs, n_q, bool(draft))
+    assert _rel(out.view(bs, n_q, heads, 512), ref) < 4e-3
 
 
 def test_backend_cuda_graph_capture_and_replay():

@@ -72,6 +72,34 @@ def bench_mla(b, seq, h, s_q=1, n_rot=None):
         b, seq, h, s_q, us, bytes_ / us / 1e3, 100 * bytes_ / us / 1e3 / PEAK, PEAK, flops / us / 1e6), flush=True)
 
 
+def bench_mla_bf16(b, seq, h, s_q=1):
+    """bf16-KV kernel (a-2): 1152 B per KV token."""
+    torch.manual_seed(0)
+    pages_per = (seq + 63) // 64 + 1
+    n_pages = b * pages_per + 1
+    n_rot = max(2, min(8, int(2.5e8 // (n_pages * 64 * 1152)) + 2))
+    pools = [torch.randn(n_pages, 64, 1, 576, dtype=torch.bfloat16, device=dev) for _ in range(n_rot)]
+    q = torch.randn(b, s_q, h, 576, dtype=torch.bfloat16, device=dev)
+    bt = (torch.randperm(n_pages - 1)[: b * pages_per].reshape(b, pages_per) + 1).to(torch.int32).to(dev)
+    sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    L = _lib.lib()
+    out = torch.empty(b, s_q, h, 512, dtype=torch.bfloat16, device=dev)
+    lse = torch.empty(b, h, s_q, dtype=torch.float32, device=dev)
+    ws = torch.empty(L.b200_mla_workspace_bytes(b, s_q, h, meta.shape[0]), dtype=torch.uint8, device=dev)
+
+    def fn(i):
+        fm.flash_mla_with_kvcache(q, pools[i % n_rot], bt, sl, 512, meta, ns, causal=s_q > 1, out=out, lse=lse,
+                                  workspace=ws)
+
+    us = time_graph(fn, n_rot)
+    S, M = b * seq, h * s_q
+    bytes_ = S * 1152 + b * M * 1152 + b * M * 1024
+    print("mla-bf16 b=%d seq=%d h=%d s_q=%d: %.1f us  %.0f GB/s (%.1f%% of %.0f)  %.0f TFLOP/s" % (
+        b, seq, h, s_q, us, bytes_ / us / 1e3, 100 * bytes_ / us / 1e3 / PEAK, PEAK, 2 * S * M * 1088 / us / 1e6),
+        flush=True)
+
+
 def bench_gemm(m, n, k, n_rot=None):
     torch.manual_seed(0)
     wbytes = n * k
@@ -107,6 +135,10 @@ if "mla" in what:
     bench_mla(128, 4096, 32)
     bench_mla(64, 4096, 16, s_q=4)
     bench_mla(256, 8192, 16, n_rot=2)
+if "bf16" in what:
+    bench_mla_bf16(128, 4096, 16)
+    bench_mla_bf16(128, 4096, 128)
+    bench_mla_bf16(64, 4096, 16, s_q=4)
 if "gemm" in what:
     for m in (16, 64, 128):
         bench_gemm(m, 7168, 2048)
