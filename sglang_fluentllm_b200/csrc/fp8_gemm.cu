@@ -16,6 +16,7 @@
 // over all SMs; each split stores its fp32 partial to its own workspace slab with plain coalesced stores and a small
 // PDL-chained kernel sums the slabs in split order (deterministic; 17 MB of red.global.add cost 30 us per call).
 #include <cuda_bf16.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "b200_decode.h"
@@ -201,19 +202,27 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
 // scalar (thread = token row), the weight scale a per-128-column scalar, so promotion is one packed FMA per pair, and
 // the epilogue writes 128 contiguous bytes per thread.
 // ------------------------------------------------------------------------------------------------------------------
+template <int BN>
 struct GemmTokMSmem {
-  static constexpr int kStages = 4;
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
   static constexpr int kABytes = 128 * 128;   // token tile
-  static constexpr int kWBytes = 256 * 128;   // weight tile
+  static constexpr int kWBytes = BN * 128;    // weight tile
   static constexpr int kStageBytes = kABytes + kWBytes + 1024;  // + 128 activation scales
-  static constexpr int kOffWScale = kStages * kStageBytes + 1024;  // [2 weight blocks][<= 128 k-blocks] floats
+  static constexpr int kWBlocks = BN > 128 ? BN / 128 : 1;      // 128-row weight scale blocks a tile touches
+  static constexpr int kOffWScale = kStages * kStageBytes + 1024;  // [kWBlocks][<= 128 k-blocks] floats
   static constexpr int kTotal = kOffWScale + 1024;
+  static_assert(kStages * kStageBytes >= 128 * BN * 4, "the epilogue stages the fp32 tile in the pipeline buffers");
 };
 
-__global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
-  using S = GemmTokMSmem;
+// BN = weight rows per CTA (UMMA N): 256 for large m (least activation re-read per weight row), 128 / 64 for decode
+// shapes, where narrower tiles fill the SMs without split-K (no fp32 partial round trip, no reduce launch).
+template <int BN>
+__global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
+  using S = GemmTokMSmem<BN>;
   constexpr int kStages = S::kStages;
-  constexpr int BN = 256, CPT = 64, kPromo = 512;
+  constexpr int CPT = 64, kPromo = 2 * BN;  // 4 lane quadrants x BN / 64 column slices
+  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr int kWBlocks = S::kWBlocks;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);  // keeps the shared address space
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
     tma_prefetch_desc(&p.tm_w);
     tma_prefetch_desc(&p.tm_a);
   }
-  if (warp == 1) tmem_alloc(&bars.tmem_base, 512);
+  if (warp == 1) tmem_alloc(&bars.tmem_base, kTmemCols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -295,11 +304,11 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const int nblk = (n0 + cb) / 128;           // weight scale block of this thread's columns
     const bool blk_valid = (n0 + cb) < p.n;
-    // weight scales of this CTA's two 128-row blocks over its k range -> shared memory once (see fp8_gemm_kernel)
+    // weight scales of this CTA's 128-row block(s) over its k range -> shared memory once (see fp8_gemm_kernel)
     float* s_wscale = reinterpret_cast<float*>(smem + S::kOffWScale);
-    const bool ws_smem = num_kb <= 128;
+    const bool ws_smem = kWBlocks * num_kb <= 256;
     if (ws_smem) {
-      for (int i = tid - 64; i < 2 * num_kb; i += kPromo) {
+      for (int i = tid - 64; i < kWBlocks * num_kb; i += kPromo) {
         const int blk = n0 / 128 + i / num_kb;
         s_wscale[i] = blk * 128 < p.n ? __ldg(p.b_scales + (int64_t)blk * total_kb + kb0 + i % num_kb) : 0.f;
       }
@@ -335,9 +344,11 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
     // barrier): stage the tile as [128 rows][256 columns], 16-byte chunks XOR-swizzled with (row & 7), then each warp
     // writes whole rows -- 512 B (bf16) or 2 x 512 B (fp32 split-K partial) of contiguous global memory per instruction.
     named_bar_sync(1, kPromo);
-    const int pw = warp - 2;  // promotion warp 0 .. 15
+    const int pw = warp - 2;                           // promotion warp
+    constexpr int kRowsPerWarp = 128 / (kPromo / 32);  // rows each warp writes out
     if (p.splits == 1) {
-      uint8_t* srow = smem + row * 512;
+      constexpr int kChunks = BN / 8;  // 16-byte chunks per bf16 row
+      uint8_t* srow = smem + row * (BN * 2);
 #pragma unroll
       for (int j = 0; j < CPT; j += 8) {
         __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[j / 2].x, acc[j / 2].y);
@@ -349,15 +360,16 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
                        *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
       }
       named_bar_sync(1, kPromo);
-      const bool col_ok = n0 + lane * 8 < p.n;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = pw * 8 + it;
-        const uint4 v = *reinterpret_cast<const uint4*>(smem + r * 512 + ((lane ^ (r & 7)) << 4));
-        if (m0 + r < p.m && col_ok) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + lane * 8) = v;
+      for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
+        const uint4 v = *reinterpret_cast<const uint4*>(smem + r * (BN * 2) + ((c ^ (r & 7)) << 4));
+        if (m0 + r < p.m && n0 + c * 8 < p.n) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
       }
     } else {
-      uint8_t* srow = smem + row * 1024;
+      constexpr int kChunks = BN / 4;  // 16-byte chunks per fp32 row
+      uint8_t* srow = smem + row * (BN * 4);
 #pragma unroll
       for (int j = 0; j < CPT; j += 4)
         *reinterpret_cast<float4*>(srow + ((((cb + j) >> 2) ^ (row & 7)) << 4)) =
@@ -365,21 +377,18 @@ __global__ void __launch_bounds__(64 + 512, 1) fp8_gemm_tokm_kernel(const __grid
       named_bar_sync(1, kPromo);
       float* slab = p.ws + ((int64_t)blockIdx.z * p.m + m0) * p.n + n0;
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int r = pw * 8 + it;
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const int c = hf * 32 + lane;  // 16-byte chunk of the 1 KB row
-          const float4 v = *reinterpret_cast<const float4*>(smem + r * 1024 + ((c ^ (r & 7)) << 4));
-          if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
-        }
+      for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
+        const int idx = it * 32 + lane;
+        const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
+        const float4 v = *reinterpret_cast<const float4*>(smem + r * (BN * 4) + ((c ^ (r & 7)) << 4));
+        if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
       }
     }
   }
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) tmem_dealloc(tmem, 512);
+  if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
 // out[m][n] = bf16( sum over splits, in split order, of the fp32 slabs ): deterministic, no atomics.  8 outputs per thread.
@@ -418,17 +427,18 @@ static int launch_splitk_reduce(const GemmParams& prm, cudaStream_t stream) {
   return 0;
 }
 
+template <int BN>
 static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
-  const int smem = GemmTokMSmem::kTotal + 1024;
+  const int smem = GemmTokMSmem<BN>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((prm.n + 255) / 256, (prm.m + 127) / 128, prm.splits);
-  cfg.blockDim = dim3(64 + 512, 1, 1);
+  cfg.gridDim = dim3((prm.n + BN - 1) / BN, (prm.m + 127) / 128, prm.splits);
+  cfg.blockDim = dim3(64 + 2 * BN, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -436,7 +446,7 @@ static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t str
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel, prm));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel<BN>, prm));
   return 0;
 }
 
@@ -465,15 +475,9 @@ static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) 
 
 static int pick_bt(int m) { return m <= 16 ? 16 : (m <= 32 ? 32 : (m <= 64 ? 64 : 128)); }
 static bool tokens_on_m(int m) { return m > 64; }
-static int num_tiles(int m, int n) {
-  if (tokens_on_m(m)) return ((n + 255) / 256) * ((m + 127) / 128);
-  const int bt = pick_bt(m);
-  return ((n + 127) / 128) * ((m + bt - 1) / bt);
-}
 
-// split-K factor: fill the SMs when the (weight tile x token tile) grid is small; keep >= 4 k-blocks per split
-static int pick_splits(int m, int n, int k, int sm_count) {
-  const int tiles = num_tiles(m, n);
+// split-K factor: fill the SMs when the tile grid is small; keep >= 2 k-blocks per split
+static int splits_for(int tiles, int k, int sm_count) {
   const int num_kb = k / 128;
   if (tiles * 2 > sm_count) return 1;
   int splits = sm_count / tiles;
@@ -484,6 +488,39 @@ static int pick_splits(int m, int n, int k, int sm_count) {
   return (num_kb + kb_per - 1) / kb_per;
 }
 
+struct GemmConfig {
+  int bn;      // weight rows per CTA (tokens-on-M kernel) or 128 (weights-on-M kernel)
+  int splits;
+};
+
+// Tokens-on-M kernel: weight rows per CTA and split-K factor from a per-SM traffic model (bytes through one SM on the
+// critical path): waves x k-blocks x (activation tile + weight tile), plus the fp32 partial round trip and the extra
+// launch when K is split.  B200_GEMM_BN / B200_GEMM_SPLITS override (tuning).
+static GemmConfig pick_config(int m, int n, int k, int sm_count) {
+  if (!tokens_on_m(m)) {
+    const int bt = pick_bt(m);
+    return {128, splits_for(((n + 127) / 128) * ((m + bt - 1) / bt), k, sm_count)};
+  }
+  static const int force_bn = getenv("B200_GEMM_BN") ? atoi(getenv("B200_GEMM_BN")) : 0;
+  static const int force_splits = getenv("B200_GEMM_SPLITS") ? atoi(getenv("B200_GEMM_SPLITS")) : 0;
+  const int num_kb = k / 128;
+  GemmConfig best = {256, 1};
+  double best_cost = 1e30;
+  for (int bn = 256; bn >= 64; bn >>= 1) {
+    if (force_bn && bn != force_bn) continue;
+    const int tiles = ((n + bn - 1) / bn) * ((m + 127) / 128);
+    int splits = force_splits ? force_splits : splits_for(tiles, k, sm_count);
+    if (splits > num_kb) splits = num_kb;
+    const int kb_per = (num_kb + splits - 1) / splits;
+    splits = (num_kb + kb_per - 1) / kb_per;
+    const int waves = (tiles * splits + sm_count - 1) / sm_count;
+    double cost = (double)waves * (kb_per * (16384.0 + bn * 128.0) + 128.0 * bn * (splits > 1 ? 4 : 2) * 2.0);
+    if (splits > 1) cost += (double)splits * m * n * 4.0 / sm_count + 150e3;
+    if (cost < best_cost) best_cost = cost, best = {bn, splits};
+  }
+  return best;
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -491,9 +528,10 @@ using namespace b200;
 extern "C" {
 
 size_t b200_fp8_gemm_workspace_bytes(int m, int n, int k) {
+  if (m <= 0 || n <= 0 || k < 128) return 0;
   const int sms = device_sm_count();
-  if (pick_splits(m, n, k, sms > 0 ? sms : 148) == 1) return 0;
-  return (size_t)pick_splits(m, n, k, sms > 0 ? sms : 148) * m * n * sizeof(float);
+  const GemmConfig c = pick_config(m, n, k, sms > 0 ? sms : 148);
+  return c.splits == 1 ? 0 : (size_t)c.splits * m * n * sizeof(float);
 }
 
 int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b, const float* b_scales,
@@ -515,8 +553,9 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   memset(&prm, 0, sizeof(prm));
   const int BT = pick_bt(m);
   const int sms = device_sm_count();
-  int splits = pick_splits(m, n, k, sms > 0 ? sms : 148);
-  const size_t need = b200_fp8_gemm_workspace_bytes(m, n, k);
+  const GemmConfig gc = pick_config(m, n, k, sms > 0 ? sms : 148);
+  int splits = gc.splits;
+  const size_t need = (size_t)splits * m * n * sizeof(float);
   if (splits > 1 && (workspace == nullptr || workspace_bytes < need)) splits = 1;  // no workspace: plain tiling
   const int num_kb = k / 128;
   prm.splits = splits;
@@ -524,7 +563,7 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.splits = (num_kb + prm.kb_per_split - 1) / prm.kb_per_split;
   if (prm.splits > 1) prm.ws = (float*)workspace;
   const bool tokm = tokens_on_m(m);
-  if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, tokm ? 256 : 128, TmaSwizzle::B128))
+  if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)n, (uint64_t)k, 128, tokm ? gc.bn : 128, TmaSwizzle::B128))
     return 1;
   if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)m, (uint64_t)k, 128, tokm ? 128 : BT, TmaSwizzle::B128))
     return 1;
@@ -536,7 +575,9 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.n = n;
   prm.k = k;
   int rc;
-  if (tokm) rc = launch_gemm_tokm(prm, use_pdl, (cudaStream_t)stream);
+  if (tokm && gc.bn == 256) rc = launch_gemm_tokm<256>(prm, use_pdl, (cudaStream_t)stream);
+  else if (tokm && gc.bn == 128) rc = launch_gemm_tokm<128>(prm, use_pdl, (cudaStream_t)stream);
+  else if (tokm) rc = launch_gemm_tokm<64>(prm, use_pdl, (cudaStream_t)stream);
   else if (BT == 16) rc = launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
   else if (BT == 32) rc = launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
   else rc = launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);

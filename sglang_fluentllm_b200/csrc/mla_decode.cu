@@ -601,6 +601,11 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.k_lora_base = (const uint8_t*)k_lora;
   prm.k_rope_base = (const uint8_t*)k_rope;
 
+  static const int epi_mode = getenv("B200_MLA_EPI") ? atoi(getenv("B200_MLA_EPI")) : 1;  // pair kernel epilogue staging (A/B knob)
+  prm.epi_mode = epi_mode;
+  static const int ks_ahead = getenv("B200_MLA_KSAHEAD") ? atoi(getenv("B200_MLA_KSAHEAD")) : 6;
+  prm.ks_ahead = ks_ahead < 1 ? 1 : (ks_ahead > 6 ? 6 : ks_ahead);
+
   int rc;
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
   if (M > 64 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);

@@ -101,6 +101,10 @@ struct BtWindow {
     cur = (base + lane < limit) ? __ldg(row + base + lane) : 0;
     nxt = (base + 32 + lane < limit) ? __ldg(row + base + 32 + lane) : 0;
   }
+  // window [0, 64) of a row whose entries were fetched while the previous request ran
+  __device__ __forceinline__ void adopt(const int32_t* r, int lim, int c, int n) {
+    row = r, base = 0, limit = lim, cur = c, nxt = n;
+  }
   // call with the lowest block index still needed; keeps [lowest, lowest + 32) inside the window
   __device__ __forceinline__ void advance_to(int lowest, int lane) {
     while (lowest >= base + 32) {
@@ -203,21 +207,34 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
     uint32_t g = 0, seg_i = 0;
     const int pf = min(p.pf_tiles, 14);  // the block-table window holds 32 entries past the current tile
+    const int ks_ahead = p.ks_ahead;
+    // Everything a request's first loads depend on is fetched while the previous request runs (its lengths, its split
+    // index, the first 64 entries of its block-table row): with no L1, the four dependent L2 round trips otherwise sit
+    // between the last K page of one request and the first of the next.
+    int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);
+    int pre_cur = 0, pre_nxt = 0;
+    bool have_pre = false;
+    int ks_done = 0;  // tiles of this request whose k scales were already issued from the previous request's tail
     for (int b = begin_idx; b <= end_idx; ++b) {
-      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
-      if (sg.n_tiles == 0) continue;
-      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
-      // the request after this one (same part): its first pages and its Q are prefetched into L2 while this one runs
-      const int32_t* bt_next = nullptr;
-      int nxt_blocks = 0;
+      const Segment sg = make_segment_from(p, b, cur_sl, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                           begin_n_split, pair_row0, 128);
+      int nxt_sl = 0, nxt_ns = 0;
       if (b < end_idx) {
-        const int nsl = (b + 1 == end_idx) ? min(end_seqlen, __ldg(p.seqlens + b + 1)) : __ldg(p.seqlens + b + 1);
-        nxt_blocks = (nsl + kPage - 1) / kPage;
-        bt_next = p.block_table + (int64_t)(b + 1) * p.block_table_stride;
+        nxt_sl = __ldg(p.seqlens + b + 1);
+        nxt_ns = __ldg(p.num_splits + b + 1);
       }
+      if (sg.n_tiles == 0) {
+        cur_sl = nxt_sl, cur_ns = nxt_ns, have_pre = false, ks_done = 0;
+        continue;
+      }
+      const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
       BtWindow bw;
-      bw.init(bt, sg.start_block, sg.end_block, lane);
-      const int nxt_req = (bt_next != nullptr && lane < nxt_blocks) ? __ldg(bt_next + lane) : 0;  // its first 16 tiles
+      if (have_pre) bw.adopt(bt, sg.end_block, pre_cur, pre_nxt);
+      else bw.init(bt, sg.start_block, sg.end_block, lane);
+      // the request after this one (same part, so it starts at block 0): filled in below, once this request's first
+      // loads are out
+      const int32_t* bt_next = nullptr;
+      int nxt_blocks = 0, nxt_tiles = 0, nxt_req = 0, nxt_req2 = 0;
 
       // this CTA's page of tile t -> K stage (credits the leader's barrier)
       auto load_k = [&](int t, uint32_t gt) {
@@ -278,7 +295,31 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
         __syncwarp();
       };
+      // the same for tile tn of the NEXT request: the scale ring runs across the request boundary, so the first tiles of a
+      // request do not wait for an HBM round trip that starts at the boundary
+      auto load_ks_next = [&](int tn, uint32_t gt) {
+        const uint32_t st = gt % kKsStages;
+        mbar_wait(&sm.ks_empty[st], ((gt / kKsStages) & 1) ^ 1);
+        const int blk0 = 2 * tn;
+        const int npages = min(2, nxt_blocks - blk0);
+        const int e0 = __shfl_sync(0xffffffffu, nxt_req, blk0 & 31), e1 = __shfl_sync(0xffffffffu, nxt_req, (blk0 + 1) & 31);
+        float* ks_dst = s_ks + st * 128;
+        if (elect_one()) {
+          mbar_arrive_expect_tx(&sm.ks_full[st], (uint32_t)npages * 256);
+          bulk_load_1d(ks_dst, p.k_scale + e0 * kPage, 256, &sm.ks_full[st]);
+          if (npages > 1) bulk_load_1d(ks_dst + 64, p.k_scale + e1 * kPage, 256, &sm.ks_full[st]);
+        }
+        __syncwarp();
+      };
 
+      // The first K page (+ its scales) and Q are what the first Q.K^T waits for.  K goes first: its stage frees one
+      // tile before the previous request's last Q.K^T retires (q_empty), and at a request boundary the K page comes from
+      // HBM while Q was prefetched into L2.
+      load_k(0, g);
+      if (ks_done == 0) {
+        load_ks(0, g);
+        ks_done = 1;
+      }
       // Q rows of this CTA (rows past the request are masked by the consumers)
       mbar_wait(&sm.q_empty, (seg_i & 1) ^ 1);
       ++seg_i;
@@ -290,28 +331,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tma_load_2d_pair(s_q + 32768, &p.tm_q_rope, q_full_l, 0, qrow);
       }
       __syncwarp();
-      if (seg_i == 1 && p.pf_mode == 0) {  // first request of this part: tiles the steady-state prefetch (t + pf) will not reach
-        for (int tp = kKStages; tp < pf && tp < sg.n_tiles; ++tp) {
-          const int bp = sg.start_block + 2 * tp + (int)rank;
-          if (bp < sg.end_block) {
-            const int tk = bw.get(bp) * kPage;
-            if (elect_one()) {
-#pragma unroll
-              for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tk);
-              tma_prefetch_2d(&p.tm_k_rope, 0, tk);
-            }
-            __syncwarp();
-          }
-        }
+      if (b < end_idx) {
+        const Segment sgn = make_segment_from(p, b + 1, nxt_sl, nxt_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                              begin_n_split, pair_row0, 128);
+        nxt_blocks = sgn.end_block;
+        nxt_tiles = sgn.n_tiles;
+        bt_next = p.block_table + (int64_t)(b + 1) * p.block_table_stride;
+        nxt_req = lane < nxt_blocks ? __ldg(bt_next + lane) : 0;  // its first 16 tiles
+        nxt_req2 = 32 + lane < nxt_blocks ? __ldg(bt_next + 32 + lane) : 0;
       }
-      __syncwarp();
-      load_k(0, g);  // Q and the first K page (+ its scales) are what the first Q.K^T waits for: they go first
-      load_ks(0, g);
+      int ks_next = 0;  // k-scale tiles of the next request issued so far
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
         bw.advance_to(sg.start_block + 2 * t, lane);
         if (t + 1 < sg.n_tiles) load_k(t + 1, g + 1);
+        if (t == 0 && seg_i == 1 && p.pf_mode != 1) {  // first request of this part: tiles the steady-state prefetch (t + pf)
+                                                      // will not reach, behind the demand loads of tiles 0 and 1
+          for (int tp = kKStages; tp < pf && tp < sg.n_tiles; ++tp) {
+            const int bp = sg.start_block + 2 * tp + (int)rank;
+            if (bp < sg.end_block) {
+              const int tk = bw.get(bp) * kPage;
+              if (elect_one()) {
+                if (p.pf_mode == 0) {
+#pragma unroll
+                  for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_k_nope, c * 128, tk);
+                  tma_prefetch_2d(&p.tm_k_rope, 0, tk);
+                } else {
+                  bulk_prefetch_l2(p.k_lora_base + (int64_t)tk * 512, 64 * 512);
+                  bulk_prefetch_l2(p.k_rope_base + (int64_t)tk * 128, 64 * 128);
+                }
+              }
+              __syncwarp();
+            }
+          }
+        }
         if (t == 0)
-          for (int i = 1; i < kKsAhead && i < sg.n_tiles; ++i) load_ks(i, g + i);
+          for (int i = ks_done; i < ks_ahead && i < sg.n_tiles; ++i) load_ks(i, g + i);
         if (b < end_idx && t == (sg.n_tiles > 4 ? 4 : 0)) {  // next request's Q rows of this CTA -> L2, off the start-up path
           if (elect_one()) {
 #pragma unroll
@@ -320,8 +374,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           }
           __syncwarp();
         }
-        if (t + kKsAhead < sg.n_tiles) load_ks(t + kKsAhead, g + kKsAhead);
+        if (t + ks_ahead < sg.n_tiles) load_ks(t + ks_ahead, g + ks_ahead);
+        // scales of the next request's first tiles, kKsAhead tiles ahead as well (in tile order: behind this request's)
+        while (ks_next < nxt_tiles && ks_next < 16 && ks_next <= t + ks_ahead - sg.n_tiles) {
+          load_ks_next(ks_next, g + (uint32_t)(sg.n_tiles - t + ks_next));
+          ++ks_next;
+        }
       }
+      cur_sl = nxt_sl, cur_ns = nxt_ns;
+      pre_cur = nxt_req, pre_nxt = nxt_req2, have_pre = bt_next != nullptr;
+      ks_done = ks_next;
     }
   } else if (warp == 3 && rank == 1 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
     // diagnostic: when each V stage lands in the non-leader CTA
@@ -335,8 +397,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     // (Q.K^T runs ahead of P.V).
     const uint64_t pol_last_use = policy_evict_first();
     uint32_t g = 0;
+    int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
     for (int b = begin_idx; b <= end_idx; ++b) {
-      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      const Segment sg = make_segment_from(p, b, cur_sl, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                           begin_n_split, pair_row0, 128);
+      if (b < end_idx) {
+        cur_sl = __ldg(p.seqlens + b + 1);
+        cur_ns = __ldg(p.num_splits + b + 1);
+      }
       if (sg.n_tiles == 0) continue;
       const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
       BtWindow bw;
@@ -398,8 +466,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     const uint64_t d_vmn = make_smem_desc(0, 16384, 1024, SWZ_128B);    // V: MN-major view of the token rows
     auto with_addr = [](uint64_t d, uint32_t a) { return d | (uint64_t)((a >> 4) & 0x3FFF); };
     uint32_t g = 0, seg = 0;
+    int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
     for (int b = begin_idx; b <= end_idx; ++b) {
-      const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+      const Segment sg = make_segment_from(p, b, cur_sl, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                           begin_n_split, pair_row0, 128);
+      if (b < end_idx) {
+        cur_sl = __ldg(p.seqlens + b + 1);
+        cur_ns = __ldg(p.num_splits + b + 1);
+      }
       if (sg.n_tiles == 0) continue;
       if (warp == 1) {
         mbar_wait_cluster(&sm.q_full, seg & 1);
@@ -472,8 +546,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       for (int i = 0; i < kPBufs; ++i) p_full_l[i] = mapa_u32(smem_u32(&sm.p_full[i]), 0);
       const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
       uint32_t g = 0, seg = 0;
+      int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
       for (int b = begin_idx; b <= end_idx; ++b) {
-        const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, pair_row0, 128);
+        const Segment sg = make_segment_from(p, b, cur_sl, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
+                                             begin_n_split, pair_row0, 128);
+        if (b < end_idx) {
+          cur_sl = __ldg(p.seqlens + b + 1);
+          cur_ns = __ldg(p.num_splits + b + 1);
+        }
         if (sg.n_tiles == 0) continue;
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
           mbar_wait(&sm.p_relay[g % kPBufs], (g / kPBufs) & 1);
@@ -599,25 +679,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         acc += acc2.x + acc2.y;
       };
       // max over this lane's 64 columns of the scaled logits z = s f k, and of the k scales of its unmasked columns
-      auto tile_max = [&](uint32_t s_addr, const float* ks_tile, int tile_start, float& ksmax) {
-        const float* ksrc = ks_tile + page * 64;
-        const int nvalid = lim - (tile_start + page * 64);
-        float r = -INFINITY;
-        ksmax = 0.f;
-#pragma unroll 1
-        for (int c16 = 0; c16 < 4; ++c16) {
-          float x[16];
-          tmem_ld16(s_addr + c16 * 16, reinterpret_cast<uint32_t*>(x));
-          tmem_wait_ld();
+      // (TMEM loads double-buffered, k scales read as float4)
+      auto tile_max = [&](uint32_t s_addr, const float* ks_tile, int tile_start, bool need_mask, float& ksmax) {
+        const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
+        const int nvalid = need_mask ? lim - (tile_start + page * 64) : 64;
+        float r = -INFINITY, km = 0.f;
+        auto chunk = [&](const float* x, int c16) {
 #pragma unroll
-          for (int c = 0; c < 16; ++c) {
-            const float kfc = ksrc[c16 * 16 + c];
-            if (c16 * 16 + c < nvalid) {
-              r = fmaxf(r, x[c] * (f * kfc));
-              ksmax = fmaxf(ksmax, kfc);
+          for (int i = 0; i < 4; ++i) {
+            const float4 k4 = ksrc[c16 * 4 + i];
+            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              if (c16 * 16 + 4 * i + j < nvalid) {
+                r = fmaxf(r, x[4 * i + j] * (f * kk[j]));
+                km = fmaxf(km, kk[j]);
+              }
             }
           }
+        };
+        float xa[16], xb[16];
+        tmem_ld16(s_addr, reinterpret_cast<uint32_t*>(xa));
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; c16 += 2) {
+          tmem_wait_ld();
+          tmem_ld16(s_addr + (c16 + 1) * 16, reinterpret_cast<uint32_t*>(xb));
+          chunk(xa, c16);
+          tmem_wait_ld();
+          if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
+          chunk(xb, c16 + 1);
         }
+        ksmax = km;
         return r;
       };
 
@@ -696,7 +788,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           // P' = exp2(z - m_new) * k_scale <= max k_scale of the row's unmasked tokens in this tile (one pass over S
           // instead of two; the bound costs at most the k-scale spread of the tile in e4m3 headroom).
           float ksmax;
-          sm.red1[grp][page][row] = tile_max(s_addr, ks_tile, tile_start, ksmax);
+          sm.red1[grp][page][row] = tile_max(s_addr, ks_tile, tile_start, need_mask, ksmax);
           sm.red2[grp][page][row] = ksmax;
           named_bar_sync(gbar, 128);
           const float m_old = ld_shared_volatile_f32(&sm.st_mref[row]), ps_old = ld_shared_volatile_f32(&sm.st_ps[row]);
@@ -738,7 +830,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
           float vmax = 0.f;
           acc = 0.f;
-          tile_pass(s_addr, ks_tile, tile_start, true, mprime, prow, acc, vmax);
+          tile_pass(s_addr, ks_tile, tile_start, need_mask, mprime, prow, acc, vmax);
           lsum += acc;
         }
         __syncwarp();
@@ -818,65 +910,141 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         uint8_t* stage_mine = s_p + (egrp + 2 * page) * kPBytes;
         const int64_t grow0 = (int64_t)b * p.M + q_row0;
         const int gw = warp & 3;  // warp within the group
-#pragma unroll 1
-        for (int r8 = 0; r8 < 8; ++r8) {
-          const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3);  // + 128 * page
-          float o[32];
-          if (had_tiles) {
-            tmem_ld<32>(tmem + kColO + r8 * 32 + lane_addr, o);
-            tmem_wait_ld();
-            if (r8 == 7) {  // O is in registers / shared memory: the next request's P.V may overwrite it
-              tc_fence_before();
+        if (p.epi_mode) {
+          // Warp-local staging: a warp's 32 lanes are 32 q rows of one TMEM lane half; it stages its [32 rows][32
+          // columns] block in a private 4 KB slice of the group's P tiles and reads it back row-major, so every global
+          // store instruction still writes whole 64 / 128-byte row segments but nothing but __syncwarp orders the
+          // round: the four warps run independently and hide each other's TMEM / shared / store latencies (the
+          // group-wide staging below spends ~900 cycles per round on two 128-thread barriers).
+          uint8_t* wst = stage_mine + (row >> 5) * 4096;
+          const int wrow0 = row & 32;  // first of this warp's 32 rows within the CTA's 64
+          auto flush = [&](const float* o, int r8) {
+            const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3) + 128 * page;
+            if (sg.no_split) {
+              uint8_t* srow = wst + lane * 64;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
+                *reinterpret_cast<uint4*>(srow + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
               __syncwarp();
-              if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
+              const int k = lane & 3, rr = lane >> 2;  // per instruction: 8 rows x 64 B
+#pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r = it * 8 + rr;
+                const uint4 v = *reinterpret_cast<const uint4*>(wst + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+                if (wrow0 + r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + wrow0 + r) * 512 + d_base + 8 * k) = v;
+              }
+            } else {
+              uint8_t* srow = wst + lane * 128;
+#pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(srow + ((k ^ (lane & 7)) << 4)) =
+                    make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
+              __syncwarp();
+              const int k = lane & 7, rr = lane >> 3;  // per instruction: 4 rows x 128 B
+              float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0 + wrow0) * 512 + d_base + 4 * k;
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rr;
+                const float4 v = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
+                if (wrow0 + r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512) = v;
+              }
+            }
+            __syncwarp();  // the slice is rewritten by the next round / this group's next P tile
+          };
+          float oa[32], ob[32];
+          if (had_tiles) {
+            const uint32_t o_addr = tmem + kColO + lane_addr;
+            tmem_ld<32>(o_addr, oa);
+#pragma unroll 1
+            for (int r8 = 0; r8 < 8; r8 += 2) {
+              tmem_wait_ld();
+              tmem_ld<32>(o_addr + (r8 + 1) * 32, ob);
+              flush(oa, r8);
+              tmem_wait_ld();
+              if (r8 + 2 < 8) {
+                tmem_ld<32>(o_addr + (r8 + 2) * 32, oa);
+              } else {  // O has left TMEM: the next request's P.V may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
+              }
+              flush(ob, r8 + 1);
             }
           } else {
 #pragma unroll
-            for (int k = 0; k < 32; ++k) o[k] = 0.f;
+            for (int k = 0; k < 32; ++k) oa[k] = 0.f;
+#pragma unroll 1
+            for (int r8 = 0; r8 < 8; ++r8) flush(oa, r8);
           }
-          if (sg.no_split) {
-            uint8_t* srow = stage_mine + row * 64;
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
-              __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
-              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
-              __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
-              *reinterpret_cast<uint4*>(srow + ((k ^ ((row >> 1) & 3)) << 4)) =
-                  make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+          named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
+        } else {
+  #pragma unroll 1
+          for (int r8 = 0; r8 < 8; ++r8) {
+            const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3);  // + 128 * page
+            float o[32];
+            if (had_tiles) {
+              tmem_ld<32>(tmem + kColO + r8 * 32 + lane_addr, o);
+              tmem_wait_ld();
+              if (r8 == 7) {  // O is in registers / shared memory: the next request's P.V may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
+              }
+            } else {
+  #pragma unroll
+              for (int k = 0; k < 32; ++k) o[k] = 0.f;
             }
-          } else {
-            uint8_t* srow = stage_mine + row * 128;
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-              *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
-                  make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
+            if (sg.no_split) {
+              uint8_t* srow = stage_mine + row * 64;
+  #pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
+                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
+                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
+                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
+                *reinterpret_cast<uint4*>(srow + ((k ^ ((row >> 1) & 3)) << 4)) =
+                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+              }
+            } else {
+              uint8_t* srow = stage_mine + row * 128;
+  #pragma unroll
+              for (int k = 0; k < 8; ++k)
+                *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
+                    make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
+            }
+            named_bar_sync(gbar, 128);
+            if (sg.no_split) {
+              // per instruction: 4 rows x 2 lane halves x 64 B
+              const int k = lane & 3, pg = (lane >> 2) & 1, rr = lane >> 3;
+              const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
+  #pragma unroll
+              for (int it = 0; it < 4; ++it) {
+                const int r = gw * 16 + it * 4 + rr;
+                const uint4 v = *reinterpret_cast<const uint4*>(src + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+                if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d_base + 128 * pg + 8 * k) = v;
+              }
+            } else {
+              // per instruction: 2 rows x 2 lane halves x 128 B
+              const int k = lane & 7, pg = (lane >> 3) & 1, rr = lane >> 4;
+              const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
+              float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
+  #pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = gw * 16 + it * 2 + rr;
+                const float4 v = *reinterpret_cast<const float4*>(src + r * 128 + ((k ^ (r & 7)) << 4));
+                if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d_base + 128 * pg + 4 * k) = v;
+              }
+            }
+            named_bar_sync(gbar, 128);  // the staging halves are rewritten by the next round / this group's next P tile
           }
-          named_bar_sync(gbar, 128);
-          if (sg.no_split) {
-            // per instruction: 4 rows x 2 lane halves x 64 B
-            const int k = lane & 3, pg = (lane >> 2) & 1, rr = lane >> 3;
-            const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
-#pragma unroll
-            for (int it = 0; it < 4; ++it) {
-              const int r = gw * 16 + it * 4 + rr;
-              const uint4 v = *reinterpret_cast<const uint4*>(src + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
-              if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d_base + 128 * pg + 8 * k) = v;
-            }
-          } else {
-            // per instruction: 2 rows x 2 lane halves x 128 B
-            const int k = lane & 7, pg = (lane >> 3) & 1, rr = lane >> 4;
-            const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
-            float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
-#pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = gw * 16 + it * 2 + rr;
-              const float4 v = *reinterpret_cast<const float4*>(src + r * 128 + ((k ^ (r & 7)) << 4));
-              if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d_base + 128 * pg + 4 * k) = v;
-            }
-          }
-          named_bar_sync(gbar, 128);  // the staging halves are rewritten by the next round / this group's next P tile
         }
         if (had_tiles) trace(tr_e, rank, 3, o_seg, 2);
         if (row_valid && page == 0) {
