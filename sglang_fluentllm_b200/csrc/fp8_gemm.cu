@@ -216,7 +216,13 @@ struct GemmTokMSmem {
 
 // BN = weight rows per CTA (UMMA N): 256 for large m (least activation re-read per weight row), 128 / 64 for decode
 // shapes, where narrower tiles fill the SMs without split-K (no fp32 partial round trip, no reduce launch).
-template <int BN>
+//
+// KC (split-K in a cluster): the `splits` CTAs that share an output tile form one thread-block cluster along grid.z.
+// Each stages its fp32 partial tile in its own shared memory; after a cluster barrier CTA z sums rows z, z + splits, ...
+// of all the partials over distributed shared memory, in split order (deterministic, bit-identical to the slab + reduce
+// kernel path), and writes bf16.  No fp32 round trip through global memory (a 128 x 256 partial drains at ~28 B/clk per
+// SM: ~2.9 us) and no second launch.
+template <int BN, bool KC>
 __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmTokMSmem<BN>;
   constexpr int kStages = S::kStages;
@@ -374,20 +380,56 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
       for (int j = 0; j < CPT; j += 4)
         *reinterpret_cast<float4*>(srow + ((((cb + j) >> 2) ^ (row & 7)) << 4)) =
             make_float4(acc[j / 2].x, acc[j / 2].y, acc[j / 2 + 1].x, acc[j / 2 + 1].y);
-      named_bar_sync(1, kPromo);
-      float* slab = p.ws + ((int64_t)blockIdx.z * p.m + m0) * p.n + n0;
+      if constexpr (!KC) {  // (KC: the staged tile is summed across the cluster below)
+        named_bar_sync(1, kPromo);
+        float* slab = p.ws + ((int64_t)blockIdx.z * p.m + m0) * p.n + n0;
 #pragma unroll
-      for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
-        const int idx = it * 32 + lane;
-        const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
-        const float4 v = *reinterpret_cast<const float4*>(smem + r * (BN * 4) + ((c ^ (r & 7)) << 4));
-        if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
+        for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
+          const int idx = it * 32 + lane;
+          const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
+          const float4 v = *reinterpret_cast<const float4*>(smem + r * (BN * 4) + ((c ^ (r & 7)) << 4));
+          if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
+        }
+      }
+    }
+  }
+  if constexpr (KC) {
+    // every partial tile of the cluster is staged ([128 rows][BN] fp32, 16-byte chunks XOR-swizzled with row & 7)
+    __syncthreads();
+    cluster_sync_all();
+    if (warp >= 2) {
+      const uint32_t nsplit = (uint32_t)p.splits, zr = cluster_ctarank();
+      uint32_t peer[8];
+#pragma unroll
+      for (uint32_t s = 0; s < 8; ++s) peer[s] = mapa_u32(smem_u32(smem), s < nsplit ? s : 0);
+      constexpr int kUnits = BN / 8;  // 8 output columns (two fp32 chunks in, one bf16 chunk out) per thread and step
+      for (int u = tid - 64;; u += kPromo) {
+        const int r = (int)zr + (u / kUnits) * (int)nsplit, c8 = u % kUnits;
+        if (r >= 128) break;
+        const uint32_t off0 = r * (BN * 4) + (((2 * c8) ^ (r & 7)) << 4), off1 = r * (BN * 4) + (((2 * c8 + 1) ^ (r & 7)) << 4);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+#pragma unroll
+        for (uint32_t s = 0; s < 8; ++s) {
+          if (s < nsplit) {
+            const float4 x = ld_cluster_f32x4(peer[s] + off0), y = ld_cluster_f32x4(peer[s] + off1);
+            if (s == 0) a = x, b = y;
+            else a.x += x.x, a.y += x.y, a.z += x.z, a.w += x.w, b.x += y.x, b.y += y.y, b.z += y.z, b.w += y.w;
+          }
+        }
+        if (m0 + r < p.m && n0 + c8 * 8 < p.n) {
+          __nv_bfloat162 h0 = __floats2bfloat162_rn(a.x, a.y), h1 = __floats2bfloat162_rn(a.z, a.w);
+          __nv_bfloat162 h2 = __floats2bfloat162_rn(b.x, b.y), h3 = __floats2bfloat162_rn(b.z, b.w);
+          *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c8 * 8) =
+              make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                         *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
+        }
       }
     }
   }
   pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
+  if constexpr (KC) cluster_sync_all();  // no CTA frees its shared memory while a peer still reads its partial
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
 }
 
@@ -427,12 +469,14 @@ static int launch_splitk_reduce(const GemmParams& prm, cudaStream_t stream) {
   return 0;
 }
 
-template <int BN>
+// KC: cluster of prm.splits CTAs along grid.z, reduction over distributed shared memory (2 <= splits <= 8).
+// Returns -1 (without launching) when the device cannot keep every cluster of the grid resident at once.
+template <int BN, bool KC>
 static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmTokMSmem<BN>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
@@ -441,12 +485,33 @@ static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t str
   cfg.blockDim = dim3(64 + 2 * BN, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (KC) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = 1;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = prm.splits;
+    ++na;
+    static int max_clusters[9] = {0};  // per cluster size, for this tile shape
+    if (max_clusters[prm.splits] == 0) {
+      cfg.attrs = attr;
+      cfg.numAttrs = na;
+      int nc = 0;
+      if (cudaOccupancyMaxActiveClusters(&nc, fp8_gemm_tokm_kernel<BN, KC>, &cfg) != cudaSuccess) nc = -1;
+      (void)cudaGetLastError();
+      max_clusters[prm.splits] = nc > 0 ? nc : -1;
+    }
+    if (max_clusters[prm.splits] < (int)(cfg.gridDim.x * cfg.gridDim.y)) return -1;
+  }
+  if (use_pdl) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
   cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel<BN>, prm));
+  cfg.numAttrs = na;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel<BN, KC>, prm));
   return 0;
 }
 
@@ -515,7 +580,7 @@ static GemmConfig pick_config(int m, int n, int k, int sm_count) {
     splits = (num_kb + kb_per - 1) / kb_per;
     const int waves = (tiles * splits + sm_count - 1) / sm_count;
     double cost = (double)waves * (kb_per * (16384.0 + bn * 128.0) + 128.0 * bn * (splits > 1 ? 4 : 2) * 2.0);
-    if (splits > 1) cost += (double)splits * m * n * 4.0 / sm_count + 150e3;
+    if (splits > 1) cost += 3.5 * splits * m * n * 4.0 / sm_count + 150e3;  // slab round trip through the reduce kernel + its launch
     if (cost < best_cost) best_cost = cost, best = {bn, splits};
   }
   return best;
@@ -574,14 +639,28 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   prm.m = m;
   prm.n = n;
   prm.k = k;
-  int rc;
-  if (tokm && gc.bn == 256) rc = launch_gemm_tokm<256>(prm, use_pdl, (cudaStream_t)stream);
-  else if (tokm && gc.bn == 128) rc = launch_gemm_tokm<128>(prm, use_pdl, (cudaStream_t)stream);
-  else if (tokm) rc = launch_gemm_tokm<64>(prm, use_pdl, (cudaStream_t)stream);
+  int rc = 0;
+  bool reduced_in_cluster = false;
+  if (tokm) {
+    const cudaStream_t st = (cudaStream_t)stream;
+    static const bool no_kc = getenv("B200_GEMM_NO_KC") != nullptr;  // A/B knob: always reduce through global slabs
+    rc = -1;
+    if (prm.splits >= 2 && prm.splits <= 8 && !no_kc) {
+      if (gc.bn == 256) rc = launch_gemm_tokm<256, true>(prm, use_pdl, st);
+      else if (gc.bn == 128) rc = launch_gemm_tokm<128, true>(prm, use_pdl, st);
+      else rc = launch_gemm_tokm<64, true>(prm, use_pdl, st);
+      reduced_in_cluster = rc == 0;
+    }
+    if (rc == -1) {  // no split, more than 8 splits, or the clusters do not all fit at once
+      if (gc.bn == 256) rc = launch_gemm_tokm<256, false>(prm, use_pdl, st);
+      else if (gc.bn == 128) rc = launch_gemm_tokm<128, false>(prm, use_pdl, st);
+      else rc = launch_gemm_tokm<64, false>(prm, use_pdl, st);
+    }
+  }
   else if (BT == 16) rc = launch_gemm<16, 8>(prm, use_pdl, (cudaStream_t)stream);
   else if (BT == 32) rc = launch_gemm<32, 8>(prm, use_pdl, (cudaStream_t)stream);
   else rc = launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
-  if (rc == 0 && prm.splits > 1) rc = launch_splitk_reduce(prm, (cudaStream_t)stream);
+  if (rc == 0 && prm.splits > 1 && !reduced_in_cluster) rc = launch_splitk_reduce(prm, (cudaStream_t)stream);
   return rc;
 }
 

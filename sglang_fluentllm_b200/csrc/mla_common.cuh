@@ -37,6 +37,7 @@ struct MlaParams {
   const uint8_t* k_rope_base;
   int pf_mode;   // pair kernel's L2 prefetch of upcoming K pages: 0 tensor-map prefetch, 1 none, 2 bulk prefetch (default)
   int pf_tiles;  // pair kernel: L2 prefetch distance of the K pages, in 128-token tiles (>= 2)
+  int q_pf_tiles;  // pair kernel: the next request's Q is prefetched into L2 this many tiles before the current one ends
   int ks_ahead;  // pair kernel: k scales are loaded this many tiles ahead of the softmax (1 .. kKsAhead)
   int epi_mode;  // pair kernel epilogue staging: 1 = warp-local (default), 0 = group-wide with 128-thread barriers
   int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)

@@ -603,6 +603,8 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
 
   static const int epi_mode = getenv("B200_MLA_EPI") ? atoi(getenv("B200_MLA_EPI")) : 1;  // pair kernel epilogue staging (A/B knob)
   prm.epi_mode = epi_mode;
+  static const int q_pf = getenv("B200_MLA_QPF") ? atoi(getenv("B200_MLA_QPF")) : 6;
+  prm.q_pf_tiles = q_pf < 1 ? 1 : q_pf;
   static const int ks_ahead = getenv("B200_MLA_KSAHEAD") ? atoi(getenv("B200_MLA_KSAHEAD")) : 6;
   prm.ks_ahead = ks_ahead < 1 ? 1 : (ks_ahead > 6 ? 6 : ks_ahead);
 

@@ -366,7 +366,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
         if (t == 0)
           for (int i = ks_done; i < ks_ahead && i < sg.n_tiles; ++i) load_ks(i, g + i);
-        if (b < end_idx && t == (sg.n_tiles > 4 ? 4 : 0)) {  // next request's Q rows of this CTA -> L2, off the start-up path
+        // next request's Q rows of this CTA -> L2, a few tiles before they are loaded: any earlier and the KV stream
+        // (about 4 MB per tile time chip-wide) has pushed them out of L2 again by the time the request starts
+        if (b < end_idx && t == (sg.n_tiles > p.q_pf_tiles ? sg.n_tiles - p.q_pf_tiles : 0)) {
           if (elect_one()) {
 #pragma unroll
             for (int c = 0; c < 4; ++c) tma_prefetch_2d(&p.tm_q_nope, c * 128, qrow + p.M);

@@ -312,6 +312,15 @@ __device__ __forceinline__ uint32_t mapa_u32(uint32_t local_smem_addr, uint32_t 
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
   return r;
 }
+// 16-byte load from the shared memory of any CTA of the cluster (address from mapa_u32)
+__device__ __forceinline__ float4 ld_cluster_f32x4(uint32_t cluster_addr) {
+  float4 v;
+  asm volatile("ld.shared::cluster.v4.f32 {%0, %1, %2, %3}, [%4];"
+               : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+               : "r"(cluster_addr)
+               : "memory");
+  return v;
+}
 // arrive on a barrier that may live in the peer CTA (cluster address from mapa_u32).  Default semantics (release at
 // CTA scope): what is handed over is this CTA's own shared memory / TMEM, consumed by its own tensor core; a
 // .release.cluster here costs a cluster-wide membar per arrival (measured: a third of the softmax warps' time).
