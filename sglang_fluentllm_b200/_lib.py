@@ -9,7 +9,7 @@ import os
 from ctypes import c_char_p, c_float, c_int, c_int64, c_size_t, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_C", "libb200decode.so")
+LIB_PATH = os.environ.get("B200_DECODE_LIB") or os.path.join(_HERE, "_C", "libb200decode.so")  # override: A/B of two builds
 
 _P = c_void_p
 _SIGNATURES = {

@@ -88,6 +88,7 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
   pdl_wait_prior_grid();
+  pdl_launch_dependents();  // the kernel behind this one (split-K reduce / next quantiser) waits for this grid to complete anyway
 
   // Issuer warps run warp-uniform code and predicate only the TMA / MMA instructions with elect.sync (descriptors and
   // coordinates stay in uniform registers; a divergent `if (lane == 0)` costs ~110 cycles per tcgen05.mma).
@@ -190,7 +191,6 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
       }
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tmem, kTmemCols);
@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
   tc_fence_after();
   const uint32_t tmem = bars.tmem_base;
   pdl_wait_prior_grid();
+  pdl_launch_dependents();  // see fp8_gemm_kernel
 
   if (warp == 0) {
     const uint64_t pol_w = policy_evict_first();
@@ -426,7 +427,6 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
       }
     }
   }
-  pdl_launch_dependents();
   tc_fence_before();
   __syncthreads();
   if constexpr (KC) cluster_sync_all();  // no CTA frees its shared memory while a peer still reads its partial

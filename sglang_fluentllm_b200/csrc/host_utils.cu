@@ -1,6 +1,7 @@
 #include "host_utils.h"
 
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -62,6 +63,11 @@ int make_tma_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t col
              (unsigned long long)cols, (unsigned long long)rows, (unsigned long long)pitch_bytes, box_cols, box_rows,
              elem_bytes);
   return 0;
+}
+
+bool pdl_default() {
+  static const bool on = getenv("B200_NO_PDL") == nullptr;
+  return on;
 }
 
 int device_sm_count() {

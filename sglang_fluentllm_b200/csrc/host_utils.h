@@ -37,4 +37,26 @@ int make_tma_2d(CUtensorMap* out, const void* gptr, int elem_bytes, uint64_t col
 
 int device_sm_count();
 
+// Programmatic dependent launch for the path's small kernels (quantisers): on unless B200_NO_PDL is set.
+bool pdl_default();
+
+// Launch with (optionally) the programmatic-stream-serialization attribute: the kernel may be scheduled while its
+// predecessor in the stream drains; it must execute griddepcontrol.wait before touching the predecessor's outputs.
+template <class... KArgs, class... Args>
+int launch_kernel(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, bool pdl,
+                  Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
+  return 0;
+}
+
 }  // namespace b200

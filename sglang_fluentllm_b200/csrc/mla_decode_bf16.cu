@@ -78,6 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) mla_decode_bf16_kernel(const __gr
   const int q_row0 = q_block * HB;
   const int n_valid_q = min(HB, p.M - q_row0);
 
+  pdl_wait_prior_grid();  // launched as a programmatic dependent of the kernel that produced q / the new K rows
   const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
   const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
             end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
@@ -442,7 +443,8 @@ extern "C" int b200_mla_decode_bf16(const void* q, const void* k_cache, int64_t 
     B200_CUDA(cudaFuncSetAttribute(bf16kv::mla_decode_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
-  bf16kv::mla_decode_bf16_kernel<<<dim3(q_blocks, 1, num_sm_parts), bf16kv::kThreads, smem, (cudaStream_t)stream>>>(prm);
-  B200_CUDA(cudaGetLastError());
+  if (int rc = launch_kernel(bf16kv::mla_decode_bf16_kernel, dim3(q_blocks, 1, num_sm_parts), dim3(bf16kv::kThreads), smem,
+                             (cudaStream_t)stream, use_pdl != 0, prm))
+    return rc;
   return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);
 }

@@ -120,6 +120,10 @@ __device__ __forceinline__ void quantize_row_576(const __nv_bfloat16* __restrict
 __global__ void __launch_bounds__(256) quantize_q_kernel(const __nv_bfloat16* __restrict__ q, uint8_t* __restrict__ nope,
                                                          float* __restrict__ scale, __nv_bfloat16* __restrict__ rope,
                                                          int64_t rows) {
+  // launched with programmatic stream serialization: the kernel behind this one may start its prologue now, and this
+  // one may have been scheduled while its predecessor drained -- griddepcontrol.wait orders the data
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
   quantize_row_576(q + row * 576, nope + row * 512, scale + row, rope + row * 64, threadIdx.x & 31);
@@ -129,6 +133,8 @@ __global__ void __launch_bounds__(256)
     quantize_cache_k_kernel(const __nv_bfloat16* __restrict__ key, int64_t key_row_stride,
                             const int32_t* __restrict__ indices, uint8_t* __restrict__ lora_cache,
                             float* __restrict__ scale_cache, __nv_bfloat16* __restrict__ rope_cache, int64_t n) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int64_t loc = indices[row];
@@ -243,6 +249,7 @@ __global__ void __launch_bounds__(256)
   // the GEMM behind this kernel is launched with programmatic stream serialization: let its CTAs start their prologue
   // (barrier init, TMEM allocation, descriptor prefetch) now; its griddepcontrol.wait still orders the data
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_wait_prior_grid();  // this kernel is itself launched as a programmatic dependent of its producer
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
   const int sub = threadIdx.x & 15;
   if (g >= num_groups) return;
@@ -311,10 +318,9 @@ int b200_mla_quantize_q(const void* q, int64_t rows, int head_dim, int head_dim_
   B200_CHECK(q && q_nope && q_scale && q_rope, "quantize_q: null pointer");
   if (rows == 0) return 0;
   const int warps = 8;
-  quantize_q_kernel<<<(unsigned)((rows + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)q, (uint8_t*)q_nope, q_scale, (__nv_bfloat16*)q_rope, rows);
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_kernel(quantize_q_kernel, dim3((unsigned)((rows + warps - 1) / warps)), dim3(warps * 32), 0,
+                       (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)q, (uint8_t*)q_nope, q_scale,
+                       (__nv_bfloat16*)q_rope, rows);
 }
 
 int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64_t n, int head_dim, int head_dim_v,
@@ -327,11 +333,9 @@ int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64
              (long long)key_row_stride);
   if (n == 0) return 0;
   const int warps = 8;
-  quantize_cache_k_kernel<<<(unsigned)((n + warps - 1) / warps), warps * 32, 0, (cudaStream_t)stream>>>(
-      (const __nv_bfloat16*)key, key_row_stride, indices, (uint8_t*)k_lora_cache, k_scale_cache,
-      (__nv_bfloat16*)k_rope_cache, n);
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_kernel(quantize_cache_k_kernel, dim3((unsigned)((n + warps - 1) / warps)), dim3(warps * 32), 0,
+                       (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)key, key_row_stride, indices,
+                       (uint8_t*)k_lora_cache, k_scale_cache, (__nv_bfloat16*)k_rope_cache, n);
 }
 
 int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cache, const float* k_scale_cache,
@@ -381,11 +385,9 @@ int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* sc
   if (m == 0) return 0;
   const int64_t groups = m * (k / 128);
   const int groups_per_block = 16;
-  act_quant_1x128_kernel<<<(unsigned)((groups + groups_per_block - 1) / groups_per_block), groups_per_block * 16, 0,
-                           (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (uint8_t*)q, scales, groups, (int)(k / 128),
-                                                   scale_stride, eps);
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  return launch_kernel(act_quant_1x128_kernel, dim3((unsigned)((groups + groups_per_block - 1) / groups_per_block)),
+                       dim3(groups_per_block * 16), 0, (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)x,
+                       (uint8_t*)q, scales, groups, (int)(k / 128), scale_stride, eps);
 }
 
 }  // extern "C"
