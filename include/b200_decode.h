@@ -126,6 +126,18 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
                      void* out, int m, int n, int k, void* workspace, size_t workspace_bytes, int use_pdl,
                      void* stream);
 
+/* Grouped block-scaled FP8 GEMMs (MoE expert GEMMs).  Replaces deep_gemm.m_grouped_gemm_fp8_fp8_bf16_nt_contiguous /
+ * _masked (3rdparty/deep_gemm/deep_gemm/jit_kernels/m_grouped_gemm.py:55-127 / :130-215).
+ *   b e4m3 [num_groups][n][k]; b_scales f32 [num_groups][ceil(n/128)][k/128]; n % 128 == 0.
+ *   mode 1 (contiguous): a e4m3 [m][k], out bf16 [m][n], m % 128 == 0, group_layout = m_indices int32 [m]: every
+ *     128-row block carries one group id, -1 skips the block; a_scales f32 [k/128][a_scale_stride] as b200_fp8_gemm_nt.
+ *   mode 2 (masked): a e4m3 [num_groups][m][k], out bf16 [num_groups][m][n] (m = rows per group, a multiple of 128 when
+ *     num_groups > 1), group_layout = masked_m int32 [num_groups]: rows of each group that are computed; a_scales f32
+ *     [num_groups][k/128][a_scale_stride], transposed per group. */
+int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
+                             const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
+                             int m, int n, int k, int use_pdl, void* stream);
+
 /* Hardware self-test of the hand-built UMMA shared-memory / instruction descriptors (csrc/umma_lab.cu).
  * Writes max|got-expected|/max|expected| of one operand-layout variant to *rel_err. */
 int b200_umma_selftest(int variant, int n, float* rel_err);

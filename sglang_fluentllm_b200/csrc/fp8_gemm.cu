@@ -33,6 +33,10 @@ struct GemmParams {
   __nv_bfloat16* out;
   float* ws;            // [splits][m][n] fp32 split-K partial slabs
   int m, n, k, splits, kb_per_split;
+  // grouped GEMMs (tokens-on-M kernel): 0 plain, 1 contiguous (group_layout = m_indices [m], one group per 128-row
+  // block, -1 skips the block), 2 masked (group_layout = masked_m [groups]; A / out are [groups][m_max] rows)
+  const int32_t* group_layout;
+  int group_mode, num_groups, m_max;
 };
 
 template <int BT>
@@ -239,7 +243,34 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
   Bars& bars = *reinterpret_cast<Bars*>(smem + kStages * S::kStageBytes);
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int n0 = blockIdx.x * BN, m0 = blockIdx.y * 128;
+  const int n0 = blockIdx.x * BN;
+  int m0 = blockIdx.y * 128;           // first A / out row of this tile
+  int m_end = p.m;                     // rows from here on are not stored
+  int a_scale_row = m0;                // row index into the (per group, for masked) activation scale columns
+  int w_row0 = n0;                     // first row of the weight tile in the [groups * n] weight matrix
+  const float* a_scales = p.a_scales;
+  const float* b_scales = p.b_scales;
+  if (p.group_mode != 0) {
+    // m_grouped_gemm_fp8_fp8_bf16_nt_{contiguous, masked} (deep_gemm/jit_kernels/m_grouped_gemm.py:55-215): the row tile
+    // picks its expert's weights; tiles without work leave before anything is allocated
+    pdl_wait_prior_grid();  // the layout may come from the kernel right before this one
+    int g;
+    if (p.group_mode == 1) {
+      g = __ldg(p.group_layout + m0);
+      if (g < 0) return;
+    } else {
+      const int tiles_m = (p.m_max + 127) / 128;
+      g = blockIdx.y / tiles_m;
+      const int ml = (blockIdx.y % tiles_m) * 128, mm = __ldg(p.group_layout + g);
+      if (ml >= mm) return;
+      m0 = g * p.m_max + ml;
+      m_end = g * p.m_max + min(mm, p.m_max);
+      a_scale_row = ml;
+      a_scales += (int64_t)g * (p.k / 128) * p.a_scale_stride;
+    }
+    w_row0 = g * p.n + n0;
+    b_scales += (int64_t)g * ((p.n + 127) / 128) * (p.k / 128);
+  }
   const int total_kb = p.k / 128;
   const int kb0 = blockIdx.z * p.kb_per_split;
   const int num_kb = min(p.kb_per_split, total_kb - kb0);
@@ -267,7 +298,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
 
   if (warp == 0) {
     const uint64_t pol_w = policy_evict_first();
-    const int rows_valid = min(128, p.m - m0);
+    const int rows_valid = min(128, m_end - m0);
     const uint32_t scale_bytes = (uint32_t)((rows_valid + 3) / 4 * 4) * 4;
     for (int i = 0; i < num_kb; ++i) {
       const int kb = kb0 + i;
@@ -277,8 +308,8 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
       if (elect_one()) {
         mbar_arrive_expect_tx(&bars.full[st], S::kABytes + S::kWBytes + scale_bytes);
         tma_load_2d(stage, &p.tm_a, &bars.full[st], kb * 128, m0);
-        tma_load_2d_hint(stage + S::kABytes, &p.tm_w, &bars.full[st], kb * 128, n0, pol_w);
-        bulk_load_1d(stage + S::kABytes + S::kWBytes, p.a_scales + (int64_t)kb * p.a_scale_stride + m0, scale_bytes,
+        tma_load_2d_hint(stage + S::kABytes, &p.tm_w, &bars.full[st], kb * 128, w_row0, pol_w);
+        bulk_load_1d(stage + S::kABytes + S::kWBytes, a_scales + (int64_t)kb * p.a_scale_stride + a_scale_row, scale_bytes,
                      &bars.full[st]);
       }
       __syncwarp();
@@ -317,7 +348,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
     if (ws_smem) {
       for (int i = tid - 64; i < kWBlocks * num_kb; i += kPromo) {
         const int blk = n0 / 128 + i / num_kb;
-        s_wscale[i] = blk * 128 < p.n ? __ldg(p.b_scales + (int64_t)blk * total_kb + kb0 + i % num_kb) : 0.f;
+        s_wscale[i] = blk * 128 < p.n ? __ldg(b_scales + (int64_t)blk * total_kb + kb0 + i % num_kb) : 0.f;
       }
       named_bar_sync(1, kPromo);
     }
@@ -327,7 +358,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
     for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
     for (int i = 0; i < num_kb; ++i) {
       const int st = i % kStages, buf = i & 1;
-      const float sb = ws_smem ? my_wscale[i] : (blk_valid ? __ldg(p.b_scales + (int64_t)nblk * total_kb + kb0 + i) : 0.f);
+      const float sb = ws_smem ? my_wscale[i] : (blk_valid ? __ldg(b_scales + (int64_t)nblk * total_kb + kb0 + i) : 0.f);
       mbar_wait(&bars.acc_full[buf], (i >> 1) & 1);
       tc_fence_after();
       const float sa = reinterpret_cast<const float*>(smem + st * S::kStageBytes + S::kABytes + S::kWBytes)[row];
@@ -372,7 +403,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
         const int idx = it * 32 + lane;
         const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
         const uint4 v = *reinterpret_cast<const uint4*>(smem + r * (BN * 2) + ((c ^ (r & 7)) << 4));
-        if (m0 + r < p.m && n0 + c * 8 < p.n) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
+        if (m0 + r < m_end && n0 + c * 8 < p.n) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
       }
     } else {
       constexpr int kChunks = BN / 4;  // 16-byte chunks per fp32 row
@@ -662,6 +693,47 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   else rc = launch_gemm<64, 16>(prm, use_pdl, (cudaStream_t)stream);
   if (rc == 0 && prm.splits > 1 && !reduced_in_cluster) rc = launch_splitk_reduce(prm, (cudaStream_t)stream);
   return rc;
+}
+
+/* Grouped GEMMs on the tokens-on-M kernel: each 128-row tile multiplies its group's weights. */
+int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
+                             const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
+                             int m, int n, int k, int use_pdl, void* stream) {
+  B200_CHECK(a && a_scales && b && b_scales && out && group_layout, "fp8_gemm_grouped: null pointer");
+  B200_CHECK(mode == 1 || mode == 2, "fp8_gemm_grouped: mode must be 1 (contiguous) or 2 (masked)");
+  B200_CHECK(n % 128 == 0 && k % 128 == 0 && n > 0 && k > 0 && num_groups > 0,
+             "fp8_gemm_grouped: need n %% 128 == 0, k %% 128 == 0 (n=%d k=%d groups=%d)", n, k, num_groups);
+  B200_CHECK(m >= 0, "fp8_gemm_grouped: negative m");
+  if (m == 0) return 0;
+  // contiguous: m = m_sum, a multiple of the 128-row alignment (get_m_alignment_for_contiguous_layout);
+  // masked: m = m_max rows per group
+  B200_CHECK(mode == 2 || m % 128 == 0, "fp8_gemm_grouped: contiguous layout needs m %% 128 == 0 (m=%d)", m);
+  B200_CHECK(a_scale_stride >= (mode == 1 ? m : m) && a_scale_stride % 4 == 0,
+             "fp8_gemm_grouped: activation scales must be column-major with the row count padded to 4");
+  GemmParams prm;
+  memset(&prm, 0, sizeof(prm));
+  const int bn = n % 256 == 0 ? 256 : 128;
+  const int64_t rows = mode == 1 ? m : (int64_t)num_groups * m;
+  if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)num_groups * n, (uint64_t)k, 128, bn, TmaSwizzle::B128)) return 1;
+  if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)rows, (uint64_t)k, 128, 128, TmaSwizzle::B128)) return 1;
+  prm.a_scales = a_scales;
+  prm.a_scale_stride = a_scale_stride;
+  prm.b_scales = b_scales;
+  prm.out = (__nv_bfloat16*)out;
+  prm.m = (int)rows;
+  prm.n = n;
+  prm.k = k;
+  prm.splits = 1;
+  prm.kb_per_split = k / 128;
+  prm.group_layout = group_layout;
+  prm.group_mode = mode;
+  prm.num_groups = num_groups;
+  prm.m_max = m;
+  // launch_gemm_tokm sizes grid.y from prm.m: [groups * m_max] rows only tile per group when m_max is a multiple of 128
+  B200_CHECK(mode == 1 || m % 128 == 0 || num_groups == 1,
+             "fp8_gemm_grouped: masked layout needs m_max %% 128 == 0 for more than one group (m_max=%d)", m);
+  return bn == 256 ? launch_gemm_tokm<256, false>(prm, use_pdl, (cudaStream_t)stream)
+                   : launch_gemm_tokm<128, false>(prm, use_pdl, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -131,3 +131,77 @@ def gemm_fp8_fp8_bf16_nt(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torc
                                rhs.data_ptr(), rhs_scales.data_ptr(), out.data_ptr(), m, n, k,
                                ws.data_ptr() if ws is not None else None, ws.numel() if ws is not None else 0,
                                int(bool(use_pdl)), _lib.current_stream()), "gemm_fp8_fp8_bf16_nt")
+
+
+def get_m_alignment_for_contiguous_layout() -> int:
+    """jit_kernels/utils.py: the row alignment of every group in the contiguous layout (one group per 128-row tile)."""
+    return 128
+
+
+def m_grouped_gemm_fp8_fp8_bf16_nt_contiguous(lhs: Tuple[torch.Tensor, torch.Tensor],
+                                              rhs: Tuple[torch.Tensor, torch.Tensor], out: torch.Tensor,
+                                              m_indices: torch.Tensor, use_pdl: bool = False) -> None:
+    """Grouped GEMM, contiguous layout (jit_kernels/m_grouped_gemm.py:55-127): lhs [m_sum, k] e4m3 with 1x128 scales
+    [m_sum, k/128]; rhs [groups, n, k] e4m3 with 128x128 scales [groups, n/128, k/128]; out [m_sum, n] bf16;
+    m_indices int32 [m_sum]: group of every row, constant over each 128-row block, -1 = skip the block."""
+    lhs, lhs_scales = lhs
+    rhs, rhs_scales = rhs
+    m, k = lhs.shape
+    num_groups, n, k_ = rhs.shape
+    m_, n_ = out.shape
+    assert m == m_ == m_indices.numel() and k == k_ and n == n_
+    assert lhs_scales.shape == (m, (k + 127) // 128)
+    assert rhs_scales.shape == (num_groups, (n + 127) // 128, (k + 127) // 128)
+    assert lhs.dtype == torch.float8_e4m3fn and lhs_scales.dtype == torch.float32
+    assert rhs.dtype == torch.float8_e4m3fn and rhs_scales.dtype == torch.float32
+    assert out.dtype == torch.bfloat16 and m_indices.dtype == torch.int32
+    assert lhs.is_contiguous() and rhs.is_contiguous() and out.is_contiguous() and m_indices.is_contiguous()
+    assert m % get_m_alignment_for_contiguous_layout() == 0 and n % 128 == 0 and k % 128 == 0
+    lhs_scales = get_col_major_tma_aligned_tensor(lhs_scales)
+    assert rhs_scales.is_contiguous()
+    if m == 0:
+        return
+    if not lhs.is_cuda:
+        raise RuntimeError("m_grouped_gemm_fp8_fp8_bf16_nt_contiguous: tensors must be on a CUDA device (no CPU fallback)")
+    with torch.cuda.device(lhs.device):
+        _lib.check(
+            _lib.lib().b200_fp8_gemm_grouped_nt(
+                lhs.data_ptr(), lhs_scales.data_ptr(),
+                lhs_scales.stride(1) if lhs_scales.shape[1] > 1 else get_tma_aligned_size(m, 4), rhs.data_ptr(),
+                rhs_scales.data_ptr(), out.data_ptr(), m_indices.data_ptr(), 1, num_groups, m, n, k, int(bool(use_pdl)),
+                _lib.current_stream()), "m_grouped_gemm_fp8_fp8_bf16_nt_contiguous")
+
+
+def m_grouped_gemm_fp8_fp8_bf16_nt_masked(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torch.Tensor, torch.Tensor],
+                                          out: torch.Tensor, masked_m: torch.Tensor, expected_m: int,
+                                          use_pdl: bool = False) -> None:
+    """Grouped GEMM, masked layout (jit_kernels/m_grouped_gemm.py:130-215): lhs [groups, m_max, k] e4m3 with scales
+    [groups, m_max, k/128]; rhs / scales as above; out [groups, m_max, n] bf16; masked_m int32 [groups]: rows of each
+    group that are computed (rows past it are left untouched).  expected_m is the reference's tuning hint."""
+    lhs, lhs_scales = lhs
+    rhs, rhs_scales = rhs
+    num_groups, m, k = lhs.shape
+    num_groups_, n, k_ = rhs.shape
+    num_groups__, m_, n_ = out.shape
+    assert num_groups == num_groups_ == num_groups__ == masked_m.numel()
+    assert m == m_ and n == n_ and k == k_
+    assert expected_m > 0 and m > 0 and n > 0 and k > 0 and num_groups > 0
+    assert lhs_scales.shape == (num_groups, m, (k + 127) // 128)
+    assert rhs_scales.shape == (num_groups, (n + 127) // 128, (k + 127) // 128)
+    assert lhs.dtype == torch.float8_e4m3fn and lhs_scales.dtype == torch.float32
+    assert rhs.dtype == torch.float8_e4m3fn and rhs_scales.dtype == torch.float32
+    assert out.dtype == torch.bfloat16 and masked_m.dtype == torch.int32
+    assert lhs.is_contiguous() and rhs.is_contiguous() and out.is_contiguous() and masked_m.is_contiguous()
+    assert n % 128 == 0 and k % 128 == 0
+    assert num_groups == 1 or m % 128 == 0, "masked layout: m_max must be a multiple of the 128-row tile"
+    lhs_scales = get_col_major_tma_aligned_tensor(lhs_scales)  # transposed per group
+    assert rhs_scales.is_contiguous()
+    if not lhs.is_cuda:
+        raise RuntimeError("m_grouped_gemm_fp8_fp8_bf16_nt_masked: tensors must be on a CUDA device (no CPU fallback)")
+    with torch.cuda.device(lhs.device):
+        _lib.check(
+            _lib.lib().b200_fp8_gemm_grouped_nt(
+                lhs.data_ptr(), lhs_scales.data_ptr(),
+                lhs_scales.stride(2) if lhs_scales.shape[2] > 1 else get_tma_aligned_size(m, 4), rhs.data_ptr(),
+                rhs_scales.data_ptr(), out.data_ptr(), masked_m.data_ptr(), 2, num_groups, m, n, k, int(bool(use_pdl)),
+                _lib.current_stream()), "m_grouped_gemm_fp8_fp8_bf16_nt_masked")
