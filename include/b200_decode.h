@@ -62,6 +62,28 @@ int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64
                                   const int32_t* indices, void* k_lora_cache, float* k_scale_cache, void* k_rope_cache,
                                   void* stream);
 
+/* Decode prologue in one launch: rotary embedding of q_pe and of the new key's rope dims, the
+ * per-(token, head) FP8 quantiser of the absorbed q, and quantise + scatter of the new key into the paged pool.
+ * Replaces the sequence the reference runs per layer: apply_rope_with_cos_sin_cache_inplace
+ * (python/sglang/srt/layers/rotary_embedding.py:198-213 with output_q_rope / fused_set_kv_buffer_arg as wired in
+ * python/sglang/srt/models/deepseek_v2.py:843-857; kernel 3rdparty/flashinfer/include/flashinfer/pos_enc.cuh:190-208),
+ * MLATokenToKVPool.set_kv_buffer -> quantize_and_cache_k (mem_cache/memory_pool.py:854-871) and
+ * quantize_ckv_per_token_head (layers/attention/flashmla_backend.py:205-206).  Bit-identical to that sequence with
+ * the rotation evaluated as in DeepseekScalingRotaryEmbedding.forward_native (rotary_embedding.py:804-846).
+ *   q_nope bf16 [tokens][heads][512] and q_pe bf16 [tokens][heads][64] (before rotation): element strides given,
+ *     last dimension contiguous, q_nope rows 16-byte aligned;
+ *   kv bf16 [tokens][576] = normed latent | k_pe before rotation, row stride kv_stride_t;
+ *   positions int64 [tokens]; cos_sin_cache f32 [max_position][64] = cos[32] | sin[32]; rotary_dim must be 64;
+ *   is_neox 0: rotation pairs (2i, 2i+1) (DeepSeek), 1: pairs (i, i+32) (LongCat);
+ *   outputs as b200_mla_quantize_q (contiguous [tokens][heads][...]) and, when cache_loc != NULL, the pool tensors of
+ *   b200_mla_quantize_and_cache_k written at slots cache_loc int32 [tokens]. */
+int b200_mla_rope_quantize_fused(const void* q_nope, int64_t q_nope_stride_t, int64_t q_nope_stride_h, const void* q_pe,
+                                 int64_t q_pe_stride_t, int64_t q_pe_stride_h, const void* kv, int64_t kv_stride_t,
+                                 const int64_t* positions, const float* cos_sin_cache, int rotary_dim, int is_neox,
+                                 int64_t tokens, int heads, void* q_nope_out, float* q_scale_out, void* q_rope_out,
+                                 const int32_t* cache_loc, void* k_lora_cache, float* k_scale_cache, void* k_rope_cache,
+                                 void* stream);
+
 /* Gather + de-quantise pool entries.  Replaces flash_mla_fp8.dequantize_ckv_fused_indexed
  * (csrc/flash_api.cpp:534-632, cache_kernels.cu:274-423).  max_num_tokens > 0 fixes the grid for CUDA graphs.
  *   k_lora_out bf16 [n][512], k_rope_out bf16 [n][64] */

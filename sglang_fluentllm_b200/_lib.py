@@ -19,6 +19,11 @@ _SIGNATURES = {
     "b200_mla_get_metadata": (c_int, [_P, c_int, c_int, _P, _P, _P]),
     "b200_mla_quantize_q": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "b200_mla_quantize_and_cache_k": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
+    "b200_mla_rope_quantize_fused": (
+        c_int,
+        [_P, c_int64, c_int64, _P, c_int64, c_int64, _P, c_int64, _P, _P, c_int, c_int, c_int64, c_int, _P, _P, _P, _P,
+         _P, _P, _P, _P],
+    ),
     "b200_mla_dequantize_indexed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "b200_mla_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
     "b200_mla_decode_ckv_fp8_per_token": (

@@ -76,14 +76,14 @@ __global__ void mla_metadata_kernel(const int32_t* __restrict__ seqlens, int32_t
 // a-6 / a-7  per-row quantiser (one warp per row of 512 nope + 64 rope bf16 values).
 // Reference arithmetic: cache_kernels.cu:27-98 / :140-218.
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void quantize_row_576(const __nv_bfloat16* __restrict__ in, uint8_t* __restrict__ nope_out,
-                                                 float* __restrict__ scale_out, __nv_bfloat16* __restrict__ rope_out,
-                                                 int lane) {
+// nope_in: 512 bf16 latent dims; rope_raw: this lane's two rope dims (2*lane, 2*lane+1) as packed bf16 bits.
+__device__ __forceinline__ void quantize_row_parts(const __nv_bfloat16* __restrict__ nope_in, uint32_t rope_raw,
+                                                   uint8_t* __restrict__ nope_out, float* __restrict__ scale_out,
+                                                   __nv_bfloat16* __restrict__ rope_out, int lane) {
   // 512 bf16 = 1024 B = 2 x (32 lanes x 16 B)
   uint4 raw[2];
-  raw[0] = __ldg(reinterpret_cast<const uint4*>(in) + lane);
-  raw[1] = __ldg(reinterpret_cast<const uint4*>(in) + 32 + lane);
-  const uint32_t rope_raw = __ldg(reinterpret_cast<const uint32_t*>(in + 512) + lane);
+  raw[0] = __ldg(reinterpret_cast<const uint4*>(nope_in) + lane);
+  raw[1] = __ldg(reinterpret_cast<const uint4*>(nope_in) + 32 + lane);
   float v[16];
   float amax = 0.f;
 #pragma unroll
@@ -115,6 +115,88 @@ __device__ __forceinline__ void quantize_row_576(const __nv_bfloat16* __restrict
   const float r1 = __fmul_rn(__uint_as_float(rope_raw & 0xFFFF0000u), inv);
   __nv_bfloat162 rr = __floats2bfloat162_rn(r0, r1);
   *reinterpret_cast<__nv_bfloat162*>(rope_out + lane * 2) = rr;
+}
+
+__device__ __forceinline__ void quantize_row_576(const __nv_bfloat16* __restrict__ in, uint8_t* __restrict__ nope_out,
+                                                 float* __restrict__ scale_out, __nv_bfloat16* __restrict__ rope_out,
+                                                 int lane) {
+  quantize_row_parts(in, __ldg(reinterpret_cast<const uint32_t*>(in + 512) + lane), nope_out, scale_out, rope_out, lane);
+}
+
+// ------------------------------------------------------------------------------------------------
+// the decode prologue in one launch.  For every token: rotary embedding of the 64 rope dims of each
+// q head and of the new key (cos/sin from the model's cos_sin_cache row of the token's position), then the a-6 / a-7
+// quantisers on the rotated rows -- q rows to (e4m3, scale, rope/scale), the key row scattered into the paged pool.
+// Replaces apply_rope_with_cos_sin_cache_inplace (python/sglang/srt/layers/rotary_embedding.py:198-213, kernel
+// 3rdparty/flashinfer/include/flashinfer/pos_enc.cuh:190-208) + MLATokenToKVPool.set_kv_buffer + the
+// quantize_ckv_per_token_head call of the backend.  The rotation is x*cos + rot(x)*sin in fp32 with every operation
+// rounded (the reference's DeepseekScalingRotaryEmbedding.forward_native, rotary_embedding.py:804-846, which the oracle
+// is pinned against), the result is rounded to bf16 exactly where the unfused sequence stores bf16 -- so the outputs
+// are bit-identical to rope -> bf16 -> quantiser.
+// A lane owns rope dims (2*lane, 2*lane+1): one rotation pair when interleaved (GPT-J style, DeepSeek); for NeoX style
+// (LongCat) the partner dims d +- 32 live in lane ^ 16.
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t rope_pair(uint32_t raw, const float* __restrict__ cos_sin, bool neox, int lane) {
+  const float x0 = __uint_as_float(raw << 16), x1 = __uint_as_float(raw & 0xFFFF0000u);
+  float o0, o1;
+  if (!neox) {
+    const float c = __ldg(cos_sin + lane), s = __ldg(cos_sin + 32 + lane);
+    o0 = __fadd_rn(__fmul_rn(x0, c), __fmul_rn(-x1, s));
+    o1 = __fadd_rn(__fmul_rn(x1, c), __fmul_rn(x0, s));
+  } else {
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, raw, 16);
+    const float y0 = __uint_as_float(other << 16), y1 = __uint_as_float(other & 0xFFFF0000u);
+    const int j = (2 * lane) & 31;  // cos/sin index of dim 2*lane (dims d and d+32 share one angle)
+    const float2 c = __ldg(reinterpret_cast<const float2*>(cos_sin + j));
+    const float2 s = __ldg(reinterpret_cast<const float2*>(cos_sin + 32 + j));
+    const bool first_half = lane < 16;
+    o0 = __fadd_rn(__fmul_rn(x0, c.x), __fmul_rn(first_half ? -y0 : y0, s.x));
+    o1 = __fadd_rn(__fmul_rn(x1, c.y), __fmul_rn(first_half ? -y1 : y1, s.y));
+  }
+  const __nv_bfloat162 r = __floats2bfloat162_rn(o0, o1);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+struct RopeQuantParams {
+  const __nv_bfloat16* q_nope;   // [tokens][heads][512], element strides below
+  const __nv_bfloat16* q_pe;     // [tokens][heads][64], before rotation
+  const __nv_bfloat16* kv;       // [tokens][576]: normed latent | k_pe before rotation
+  int64_t q_nope_stride_t, q_nope_stride_h, q_pe_stride_t, q_pe_stride_h, kv_stride_t;
+  const int64_t* positions;      // [tokens]
+  const float* cos_sin_cache;    // [max_position][64]: cos[32] | sin[32]
+  const int32_t* cache_loc;      // [tokens] pool slots; null: no key rows
+  uint8_t* q_nope_out;           // [tokens][heads][512]
+  float* q_scale_out;            // [tokens][heads]
+  __nv_bfloat16* q_rope_out;     // [tokens][heads][64]
+  uint8_t* k_lora_cache;
+  float* k_scale_cache;
+  __nv_bfloat16* k_rope_cache;
+  int64_t tokens;
+  int heads, neox;
+};
+
+__global__ void __launch_bounds__(256) rope_quantize_fused_kernel(const __grid_constant__ RopeQuantParams p) {
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int64_t q_rows = p.tokens * p.heads;
+  if (row < q_rows) {
+    const int64_t t = row / p.heads;
+    const int h = (int)(row - t * p.heads);
+    const float* cs = p.cos_sin_cache + __ldg(p.positions + t) * 64;
+    const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(p.q_pe + t * p.q_pe_stride_t + h * p.q_pe_stride_h) + lane);
+    quantize_row_parts(p.q_nope + t * p.q_nope_stride_t + h * p.q_nope_stride_h, rope_pair(raw, cs, p.neox != 0, lane),
+                       p.q_nope_out + row * 512, p.q_scale_out + row, p.q_rope_out + row * 64, lane);
+  } else if (row < q_rows + (p.cache_loc ? p.tokens : 0)) {
+    const int64_t t = row - q_rows;
+    const float* cs = p.cos_sin_cache + __ldg(p.positions + t) * 64;
+    const __nv_bfloat16* in = p.kv + t * p.kv_stride_t;
+    const uint32_t raw = __ldg(reinterpret_cast<const uint32_t*>(in + 512) + lane);
+    const int64_t loc = __ldg(p.cache_loc + t);
+    quantize_row_parts(in, rope_pair(raw, cs, p.neox != 0, lane), p.k_lora_cache + loc * 512, p.k_scale_cache + loc,
+                       p.k_rope_cache + loc * 64, lane);
+  }
 }
 
 __global__ void __launch_bounds__(256) quantize_q_kernel(const __nv_bfloat16* __restrict__ q, uint8_t* __restrict__ nope,
@@ -336,6 +418,57 @@ int b200_mla_quantize_and_cache_k(const void* key, int64_t key_row_stride, int64
   return launch_kernel(quantize_cache_k_kernel, dim3((unsigned)((n + warps - 1) / warps)), dim3(warps * 32), 0,
                        (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)key, key_row_stride, indices,
                        (uint8_t*)k_lora_cache, k_scale_cache, (__nv_bfloat16*)k_rope_cache, n);
+}
+
+int b200_mla_rope_quantize_fused(const void* q_nope, int64_t q_nope_stride_t, int64_t q_nope_stride_h, const void* q_pe,
+                                 int64_t q_pe_stride_t, int64_t q_pe_stride_h, const void* kv, int64_t kv_stride_t,
+                                 const int64_t* positions, const float* cos_sin_cache, int rotary_dim, int is_neox,
+                                 int64_t tokens, int heads, void* q_nope_out, float* q_scale_out, void* q_rope_out,
+                                 const int32_t* cache_loc, void* k_lora_cache, float* k_scale_cache, void* k_rope_cache,
+                                 void* stream) {
+  B200_CHECK(rotary_dim == 64, "rope_quantize_fused: only rotary_dim=64 supported (got %d)", rotary_dim);
+  B200_CHECK(q_nope && q_pe && positions && cos_sin_cache && q_nope_out && q_scale_out && q_rope_out,
+             "rope_quantize_fused: null pointer");
+  B200_CHECK(tokens >= 0 && heads > 0, "rope_quantize_fused: tokens=%lld heads=%d", (long long)tokens, heads);
+  B200_CHECK(q_nope_stride_t % 8 == 0 && q_nope_stride_h % 8 == 0 && q_nope_stride_h >= 512 &&
+                 ((uintptr_t)q_nope & 15) == 0,
+             "rope_quantize_fused: q_nope rows must be 16-byte aligned (strides %lld, %lld)",
+             (long long)q_nope_stride_t, (long long)q_nope_stride_h);
+  B200_CHECK(q_pe_stride_t % 2 == 0 && q_pe_stride_h % 2 == 0 && q_pe_stride_h >= 64 && ((uintptr_t)q_pe & 3) == 0,
+             "rope_quantize_fused: q_pe rows must be 4-byte aligned (strides %lld, %lld)", (long long)q_pe_stride_t,
+             (long long)q_pe_stride_h);
+  B200_CHECK(((uintptr_t)cos_sin_cache & 7) == 0, "rope_quantize_fused: cos_sin_cache must be 8-byte aligned");
+  if (cache_loc) {
+    B200_CHECK(kv && k_lora_cache && k_scale_cache && k_rope_cache, "rope_quantize_fused: null key / pool pointer");
+    B200_CHECK(kv_stride_t >= 576 && kv_stride_t % 8 == 0 && ((uintptr_t)kv & 15) == 0,
+               "rope_quantize_fused: kv row stride %lld invalid", (long long)kv_stride_t);
+  }
+  if (tokens == 0) return 0;
+  RopeQuantParams prm;
+  prm.q_nope = (const __nv_bfloat16*)q_nope;
+  prm.q_pe = (const __nv_bfloat16*)q_pe;
+  prm.kv = (const __nv_bfloat16*)kv;
+  prm.q_nope_stride_t = q_nope_stride_t;
+  prm.q_nope_stride_h = q_nope_stride_h;
+  prm.q_pe_stride_t = q_pe_stride_t;
+  prm.q_pe_stride_h = q_pe_stride_h;
+  prm.kv_stride_t = kv_stride_t;
+  prm.positions = positions;
+  prm.cos_sin_cache = cos_sin_cache;
+  prm.cache_loc = cache_loc;
+  prm.q_nope_out = (uint8_t*)q_nope_out;
+  prm.q_scale_out = q_scale_out;
+  prm.q_rope_out = (__nv_bfloat16*)q_rope_out;
+  prm.k_lora_cache = (uint8_t*)k_lora_cache;
+  prm.k_scale_cache = k_scale_cache;
+  prm.k_rope_cache = (__nv_bfloat16*)k_rope_cache;
+  prm.tokens = tokens;
+  prm.heads = heads;
+  prm.neox = is_neox;
+  const int warps = 8;
+  const int64_t rows = tokens * heads + (cache_loc ? tokens : 0);
+  return launch_kernel(rope_quantize_fused_kernel, dim3((unsigned)((rows + warps - 1) / warps)), dim3(warps * 32), 0,
+                       (cudaStream_t)stream, pdl_default(), prm);
 }
 
 int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cache, const float* k_scale_cache,

@@ -248,7 +248,16 @@ class FlashMLABackend(AttentionBackend):
                 softmax_scale=layer.scaling, causal=True)
             return o.view(-1, layer.tp_q_head_num * layer.v_head_dim)
         q_nope, q_scale, q_rope = mod.quantize_ckv_per_token_head(reshape_q.contiguous(), self.kv_lora_rank)
-        k_cache_lora, k_scale, k_cache_rope = k_cache
+        return self._attend_quantized(q_nope, q_scale, q_rope, layer, forward_batch, cache_seqlens)
+
+    def _attend_quantized(self, q_nope, q_scale, q_rope, layer, forward_batch, cache_seqlens):
+        """The attention call on an already quantised Q (flashmla_backend.py:207-224)."""
+        bs = forward_batch.batch_size
+        mod = self.get_flash_mla_module(q_nope.numel() // (bs * self.kv_lora_rank))
+        k_cache_lora, k_scale, k_cache_rope = forward_batch.token_to_kv_pool.get_key_buffer(layer.layer_id)
+        q_nope = q_nope.view(bs, -1, self.num_q_heads, self.kv_lora_rank)
+        q_rope = q_rope.view(bs, -1, self.num_q_heads, self.qk_rope_head_dim)
+        q_scale = q_scale.view(bs, -1, self.num_q_heads, 1)
         o, _ = mod.flash_mla_ckv_fp8_per_token(
             q_nope=q_nope, q_rope=q_rope,
             k_cache_lora=k_cache_lora.view(-1, PAGE_SIZE, 1, self.kv_lora_rank),
@@ -263,12 +272,19 @@ class FlashMLABackend(AttentionBackend):
         return o.view(-1, layer.tp_q_head_num * layer.v_head_dim)
 
     def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache=True, **kwargs):
-        """flashmla_backend.py:178-256: write the new token's K (quantised) first, then attend over seq_lens."""
+        """flashmla_backend.py:178-256: write the new token's K (quantised) first, then attend over seq_lens.
+        ``q`` may also be the (q_nope, q_scale, q_rope) triple of ``rope.fused_rope_quantize_set_kv`` -- the fused
+        prologue has then rotated, quantised and cached already (call with k = v = None or save_kv_cache=False)."""
         if k is not None:
             assert v is not None
             if save_kv_cache:
                 forward_batch.token_to_kv_pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
-        return self._attend(q, layer, forward_batch, forward_batch.seq_lens + self.multi_step_seqlen_incr)
+        cache_seqlens = forward_batch.seq_lens + self.multi_step_seqlen_incr
+        if isinstance(q, (tuple, list)):
+            if self.cache_quant_method != "per_token_head":
+                raise RuntimeError("a pre-quantised q needs the per_token_head KV pool")
+            return self._attend_quantized(*q, layer, forward_batch, cache_seqlens)
+        return self._attend(q, layer, forward_batch, cache_seqlens)
 
     def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache=True, q_pe=None, k_pe=None, **kwargs):
         """flashmla_backend.py:87-176: TARGET_VERIFY / DRAFT_EXTEND run the decode kernel with s_q = draft tokens."""

@@ -11,6 +11,8 @@ What can be pinned this way:
   * native_per_token_group_quant_fp8 / native_w8a8_block_fp8_matmul (python/sglang/test/test_block_fp8.py:15-40,
     89-141) -- the file itself does not import (stale names), so the two functions are extracted by AST;
   * per_token_cast_to_fp8 / per_block_cast_to_fp8 (3rdparty/deep_gemm/tests/test_core.py:9-25), same extraction.
+  * DeepseekScalingRotaryEmbedding.forward_native (python/sglang/srt/layers/rotary_embedding.py:804-846), both pairings
+    (`python tests/golden/make_golden.py rope` regenerates only this one).
 The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
 """
 import ast
@@ -67,9 +69,37 @@ def extract_functions(path, names):
     return [ns[n] for n in names]
 
 
+def make_rope():
+    """Rotary embedding of the MLA rope dims through the reference's own classes on CPU
+    (python/sglang/srt/layers/rotary_embedding.py: DeepseekScalingRotaryEmbedding.forward_native :804-846 with the
+    DeepSeek-V3 yarn parameters, interleaved pairs; the same class with is_neox_style=True for the LongCat pairing)."""
+    from sglang.srt.layers.rotary_embedding import DeepseekScalingRotaryEmbedding
+    torch.manual_seed(1)
+    tokens, heads = 24, 5
+    positions = torch.cat([torch.tensor([0, 1, 2, 63, 64, 4095, 4096, 16383]), torch.randint(0, 16384, (tokens - 8,))])
+    q_pe = (torch.randn(tokens, heads, 64) * 3).to(torch.bfloat16)
+    k_pe = (torch.randn(tokens, 1, 64) * 3).to(torch.bfloat16)
+    out = {"positions": positions.numpy(), "q_pe": q_pe.float().numpy(), "k_pe": k_pe.float().numpy()}
+    for name, neox in (("gptj", False), ("neox", True)):
+        rope = DeepseekScalingRotaryEmbedding(64, 64, 4096, 10000, neox, 40.0, torch.float32, beta_fast=32, beta_slow=1,
+                                              mscale=1.0, mscale_all_dim=1.0, device="cpu")
+        cache = rope.cos_sin_cache.float()
+        q_out, k_out = rope.forward_native(positions, q_pe.clone(), k_pe.clone())
+        assert q_out.dtype == torch.bfloat16
+        out["cos_sin_rows_" + name] = cache[positions].numpy()   # the rows the vectors use (the full table is 40 MB)
+        out["cache_shape_" + name] = np.array(cache.shape)
+        # the NeoX branch assumes [batch, seq] positions and returns a leading 1 (rotary_embedding.py:826-830)
+        out["q_out_" + name] = q_out.float().numpy().reshape(q_pe.shape)
+        out["k_out_" + name] = k_out.float().numpy().reshape(k_pe.shape)
+    np.savez_compressed(os.path.join(HERE, "rope.npz"), **out)
+
+
 def main():
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, os.path.join(REF, "python"))
+    if sys.argv[1:] == ["rope"]:  # regenerate only this fixture (the others stay byte-identical in git)
+        make_rope()
+        return
     torch.manual_seed(0)
 
     # ---- pool fall-back quantiser / de-quantiser ----
@@ -144,6 +174,7 @@ def main():
     np.savez_compressed(os.path.join(HERE, "block_fp8.npz"), x=x.float().numpy(), xq=xq.view(torch.uint8).numpy(),
                         xs=xs.numpy(), w=w.float().numpy(), wq=wq.view(torch.uint8).numpy(), ws=ws.numpy(),
                         c=c.numpy(), xq_cast=xq2.view(torch.uint8).numpy(), xs_cast=xs2.numpy())
+    make_rope()
     print("golden fixtures written to", HERE)
 
 

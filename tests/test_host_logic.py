@@ -1,5 +1,7 @@
 """CPU: host-side logic of the Python mirrors (layout helpers, argument checking) -- no GPU needed."""
 import numpy as np
+import types
+
 import pytest
 import torch
 
@@ -61,6 +63,20 @@ def test_mla_entry_points_reject_cpu_tensors():
         fm.quantize_ckv_per_token_head(torch.zeros(2, 576, dtype=torch.bfloat16), 512)
     with pytest.raises(RuntimeError):
         fk.sglang_per_token_group_quant_fp8(torch.zeros(2, 256, dtype=torch.bfloat16), 128)
+
+
+def test_fused_prologue_rejects_cpu_tensors_and_bad_caches():
+    from sglang_fluentllm_b200 import rope
+    q_nope = torch.zeros(2, 4, 512, dtype=torch.bfloat16)
+    q_pe = torch.zeros(2, 4, 64, dtype=torch.bfloat16)
+    k_pe = torch.zeros(2, 64, dtype=torch.bfloat16)
+    cache = torch.zeros(16, 64)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        rope.fused_rope_quantize_set_kv(torch.zeros(2, dtype=torch.int64), q_nope, q_pe, k_pe, cache, False)
+    pool = types.SimpleNamespace(quant_method="none")
+    with pytest.raises(ValueError, match="per_token_head"):
+        rope.create_fused_set_kv_buffer_arg(q_nope, types.SimpleNamespace(layer_id=0),
+                                            types.SimpleNamespace(token_to_kv_pool=pool, out_cache_loc=None))
 
 
 def test_calc_diff():

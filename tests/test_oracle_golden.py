@@ -152,3 +152,40 @@ def test_metadata_invariants():
                 covered[bi] += hi - lo
         assert np.array_equal(covered, -(-seqlens.astype(np.int64) // 64))
         assert ns[0] == 0 and np.all(np.diff(ns) >= 1)
+
+
+def test_rope_oracle_matches_reference_forward_native(golden_dir):
+    """oracle/rope.py::apply_rope vs DeepseekScalingRotaryEmbedding.forward_native of the reference
+    (python/sglang/srt/layers/rotary_embedding.py:804-846; V3 yarn cache, both pairings): bit-exact bf16 outputs."""
+    from oracle import rope as orope
+    g = _load(golden_dir, "rope.npz")
+    assert tuple(g["cache_shape_gptj"]) == (163840, 64)          # [max_position * factor, rotary_dim] = cos | sin
+    for name, neox in (("gptj", False), ("neox", True)):
+        rows = g["cos_sin_rows_" + name]                          # the cache rows of the vectors' positions
+        ids = np.arange(len(rows))
+        assert np.array_equal(orope.apply_rope(g["q_pe"], ids, rows, neox), g["q_out_" + name])
+        assert np.array_equal(orope.apply_rope(g["k_pe"], ids, rows, neox), g["k_out_" + name])
+    assert not np.array_equal(g["q_out_gptj"], g["q_out_neox"])  # the two pairings are different rotations
+
+
+def test_fused_prologue_oracle_is_the_unfused_sequence(golden_dir):
+    """rope_quantize_fused == rope -> quantize_ckv_per_token_head / quantize_and_cache_k, and a rotation preserves the
+    pair norms (size-independent property), so scales computed from the latent only are untouched by it."""
+    from oracle import rope as orope
+    g = _load(golden_dir, "rope.npz")
+    rng = np.random.default_rng(5)
+    t, h = g["q_pe"].shape[:2]
+    q_nope = ofp8.round_to_bf16(rng.standard_normal((t, h, 512)).astype(np.float32))
+    kv = ofp8.round_to_bf16(rng.standard_normal((t, 576)).astype(np.float32))
+    kv[:, 512:] = g["k_pe"][:, 0]
+    rows, ids = g["cos_sin_rows_gptj"], np.arange(t)
+    kl, ks, kr = np.zeros((64, 1, 512), np.uint8), np.zeros((64, 1, 1), np.float32), np.zeros((64, 1, 64), np.float32)
+    loc = rng.permutation(64)[:t]
+    n8, sc, qr = orope.rope_quantize_fused(q_nope, g["q_pe"], kv, ids, rows, False, loc, kl, ks, kr)
+    q = np.concatenate([q_nope, g["q_out_gptj"]], -1)
+    n8_u, sc_u, qr_u = omla.quantize_ckv_per_token_head(q)
+    assert np.array_equal(n8, n8_u) and np.array_equal(sc, sc_u) and np.array_equal(qr, qr_u)
+    deq_l, deq_r = omla.dequantize_ckv_fused_indexed(kl, kr, ks, loc)
+    assert np.allclose(deq_r[:, 0], g["k_out_gptj"][:, 0], rtol=2 ** -7, atol=1e-6)
+    x, y = g["q_pe"], g["q_out_gptj"]
+    assert np.allclose(x[..., 0::2] ** 2 + x[..., 1::2] ** 2, y[..., 0::2] ** 2 + y[..., 1::2] ** 2, rtol=3e-2, atol=1e-3)
