@@ -149,13 +149,16 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
                      void* stream);
 
 /* Grouped block-scaled FP8 GEMMs (MoE expert GEMMs).  Replaces deep_gemm.m_grouped_gemm_fp8_fp8_bf16_nt_contiguous /
- * _masked (3rdparty/deep_gemm/deep_gemm/jit_kernels/m_grouped_gemm.py:55-127 / :130-215).
+ * _masked / _offset (3rdparty/deep_gemm/deep_gemm/jit_kernels/m_grouped_gemm.py:55-127 / :130-215 / :225-310).
  *   b e4m3 [num_groups][n][k]; b_scales f32 [num_groups][ceil(n/128)][k/128]; n % 128 == 0.
  *   mode 1 (contiguous): a e4m3 [m][k], out bf16 [m][n], m % 128 == 0, group_layout = m_indices int32 [m]: every
  *     128-row block carries one group id, -1 skips the block; a_scales f32 [k/128][a_scale_stride] as b200_fp8_gemm_nt.
  *   mode 2 (masked): a e4m3 [num_groups][m][k], out bf16 [num_groups][m][n] (m = rows per group, a multiple of 128 when
  *     num_groups > 1), group_layout = masked_m int32 [num_groups]: rows of each group that are computed; a_scales f32
- *     [num_groups][k/128][a_scale_stride], transposed per group. */
+ *     [num_groups][k/128][a_scale_stride], transposed per group.
+ *   mode 3 (offset): a e4m3 [m][k], out bf16 [m][n], any m, group_layout = m_offset int32 [num_groups + 1]
+ *     (non-decreasing, m_offset[num_groups] <= m): group g owns rows [m_offset[g], m_offset[g + 1]); rows no group
+ *     owns are left untouched; a_scales as mode 1. */
 int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
                              const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
                              int m, int n, int k, int use_pdl, void* stream);

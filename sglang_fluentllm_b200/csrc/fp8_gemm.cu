@@ -34,9 +34,11 @@ struct GemmParams {
   float* ws;            // [splits][m][n] fp32 split-K partial slabs
   int m, n, k, splits, kb_per_split;
   // grouped GEMMs (tokens-on-M kernel): 0 plain, 1 contiguous (group_layout = m_indices [m], one group per 128-row
-  // block, -1 skips the block), 2 masked (group_layout = masked_m [groups]; A / out are [groups][m_max] rows)
+  // block, -1 skips the block), 2 masked (group_layout = masked_m [groups]; A / out are [groups][m_max] rows),
+  // 3 offset (group_layout = m_offset [groups + 1]: group g owns rows [m_offset[g], m_offset[g + 1]) of A / out)
   const int32_t* group_layout;
   int group_mode, num_groups, m_max;
+  int tiles_y;          // grid.y when it is not ceil(m / 128) (offset layout: an upper bound on the row tiles)
 };
 
 template <int BT>
@@ -226,7 +228,7 @@ struct GemmTokMSmem {
 // of all the partials over distributed shared memory, in split order (deterministic, bit-identical to the slab + reduce
 // kernel path), and writes bf16.  No fp32 round trip through global memory (a 128 x 256 partial drains at ~28 B/clk per
 // SM: ~2.9 us) and no second launch.
-template <int BN, bool KC>
+template <int BN, bool KC, bool GROUPED = false>
 __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __grid_constant__ GemmParams p) {
   using S = GemmTokMSmem<BN>;
   constexpr int kStages = S::kStages;
@@ -245,12 +247,13 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int n0 = blockIdx.x * BN;
   int m0 = blockIdx.y * 128;           // first A / out row of this tile
+  int m_begin = 0;                     // rows before this one are not stored (offset layout: the previous group's)
   int m_end = p.m;                     // rows from here on are not stored
   int a_scale_row = m0;                // row index into the (per group, for masked) activation scale columns
   int w_row0 = n0;                     // first row of the weight tile in the [groups * n] weight matrix
   const float* a_scales = p.a_scales;
   const float* b_scales = p.b_scales;
-  if (p.group_mode != 0) {
+  if constexpr (GROUPED) {  // its own instantiation: the dense kernel's register allocation is not touched
     // m_grouped_gemm_fp8_fp8_bf16_nt_{contiguous, masked} (deep_gemm/jit_kernels/m_grouped_gemm.py:55-215): the row tile
     // picks its expert's weights; tiles without work leave before anything is allocated
     pdl_wait_prior_grid();  // the layout may come from the kernel right before this one
@@ -258,6 +261,24 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
     if (p.group_mode == 1) {
       g = __ldg(p.group_layout + m0);
       if (g < 0) return;
+    } else if (p.group_mode == 3) {
+      // m_grouped_gemm_fp8_fp8_bf16_nt_offset (m_grouped_gemm.py:225-310): groups start at arbitrary rows.  A group's
+      // tiles start at its first row rounded down to 4 (the activation-scale columns are fetched in 16-byte pieces);
+      // rows of a tile outside [m_offset[g], m_offset[g + 1]) are computed and dropped.  blockIdx.y counts tiles over
+      // the groups in order; the grid holds an upper bound, surplus CTAs leave.
+      int ty = blockIdx.y, lo = 0, hi = 0;
+      for (g = 0; g < p.num_groups; ++g) {
+        lo = __ldg(p.group_layout + g);
+        hi = __ldg(p.group_layout + g + 1);
+        const int nt = hi > lo ? (hi - (lo & ~3) + 127) / 128 : 0;
+        if (ty < nt) break;
+        ty -= nt;
+      }
+      if (g == p.num_groups) return;
+      m0 = (lo & ~3) + ty * 128;
+      m_begin = lo;
+      m_end = hi;
+      a_scale_row = m0;
     } else {
       const int tiles_m = (p.m_max + 127) / 128;
       g = blockIdx.y / tiles_m;
@@ -403,7 +424,8 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
         const int idx = it * 32 + lane;
         const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
         const uint4 v = *reinterpret_cast<const uint4*>(smem + r * (BN * 2) + ((c ^ (r & 7)) << 4));
-        if (m0 + r < m_end && n0 + c * 8 < p.n) *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
+        if (m0 + r >= m_begin && m0 + r < m_end && n0 + c * 8 < p.n)
+          *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
       }
     } else {
       constexpr int kChunks = BN / 4;  // 16-byte chunks per fp32 row
@@ -502,17 +524,17 @@ static int launch_splitk_reduce(const GemmParams& prm, cudaStream_t stream) {
 
 // KC: cluster of prm.splits CTAs along grid.z, reduction over distributed shared memory (2 <= splits <= 8).
 // Returns -1 (without launching) when the device cannot keep every cluster of the grid resident at once.
-template <int BN, bool KC>
+template <int BN, bool KC, bool GROUPED = false>
 static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmTokMSmem<BN>::kTotal + 1024;
   static bool configured = false;
   if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN, KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN, KC, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     configured = true;
   }
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3((prm.n + BN - 1) / BN, (prm.m + 127) / 128, prm.splits);
+  cfg.gridDim = dim3((prm.n + BN - 1) / BN, prm.tiles_y ? prm.tiles_y : (prm.m + 127) / 128, prm.splits);
   cfg.blockDim = dim3(64 + 2 * BN, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
@@ -529,7 +551,7 @@ static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t str
       cfg.attrs = attr;
       cfg.numAttrs = na;
       int nc = 0;
-      if (cudaOccupancyMaxActiveClusters(&nc, fp8_gemm_tokm_kernel<BN, KC>, &cfg) != cudaSuccess) nc = -1;
+      if (cudaOccupancyMaxActiveClusters(&nc, fp8_gemm_tokm_kernel<BN, KC, GROUPED>, &cfg) != cudaSuccess) nc = -1;
       (void)cudaGetLastError();
       max_clusters[prm.splits] = nc > 0 ? nc : -1;
     }
@@ -542,7 +564,7 @@ static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t str
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel<BN, KC>, prm));
+  B200_CUDA(cudaLaunchKernelEx(&cfg, fp8_gemm_tokm_kernel<BN, KC, GROUPED>, prm));
   return 0;
 }
 
@@ -700,20 +722,20 @@ int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_sca
                              const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
                              int m, int n, int k, int use_pdl, void* stream) {
   B200_CHECK(a && a_scales && b && b_scales && out && group_layout, "fp8_gemm_grouped: null pointer");
-  B200_CHECK(mode == 1 || mode == 2, "fp8_gemm_grouped: mode must be 1 (contiguous) or 2 (masked)");
+  B200_CHECK(mode >= 1 && mode <= 3, "fp8_gemm_grouped: mode must be 1 (contiguous), 2 (masked) or 3 (offset)");
   B200_CHECK(n % 128 == 0 && k % 128 == 0 && n > 0 && k > 0 && num_groups > 0,
              "fp8_gemm_grouped: need n %% 128 == 0, k %% 128 == 0 (n=%d k=%d groups=%d)", n, k, num_groups);
   B200_CHECK(m >= 0, "fp8_gemm_grouped: negative m");
   if (m == 0) return 0;
   // contiguous: m = m_sum, a multiple of the 128-row alignment (get_m_alignment_for_contiguous_layout);
-  // masked: m = m_max rows per group
-  B200_CHECK(mode == 2 || m % 128 == 0, "fp8_gemm_grouped: contiguous layout needs m %% 128 == 0 (m=%d)", m);
-  B200_CHECK(a_scale_stride >= (mode == 1 ? m : m) && a_scale_stride % 4 == 0,
+  // masked: m = m_max rows per group; offset: m = m_sum, any value
+  B200_CHECK(mode != 1 || m % 128 == 0, "fp8_gemm_grouped: contiguous layout needs m %% 128 == 0 (m=%d)", m);
+  B200_CHECK(a_scale_stride >= m && a_scale_stride % 4 == 0,
              "fp8_gemm_grouped: activation scales must be column-major with the row count padded to 4");
   GemmParams prm;
   memset(&prm, 0, sizeof(prm));
   const int bn = n % 256 == 0 ? 256 : 128;
-  const int64_t rows = mode == 1 ? m : (int64_t)num_groups * m;
+  const int64_t rows = mode == 2 ? (int64_t)num_groups * m : m;
   if (make_tma_2d(&prm.tm_w, b, 1, (uint64_t)k, (uint64_t)num_groups * n, (uint64_t)k, 128, bn, TmaSwizzle::B128)) return 1;
   if (make_tma_2d(&prm.tm_a, a, 1, (uint64_t)k, (uint64_t)rows, (uint64_t)k, 128, 128, TmaSwizzle::B128)) return 1;
   prm.a_scales = a_scales;
@@ -730,10 +752,12 @@ int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_sca
   prm.num_groups = num_groups;
   prm.m_max = m;
   // launch_gemm_tokm sizes grid.y from prm.m: [groups * m_max] rows only tile per group when m_max is a multiple of 128
-  B200_CHECK(mode == 1 || m % 128 == 0 || num_groups == 1,
+  B200_CHECK(mode != 2 || m % 128 == 0 || num_groups == 1,
              "fp8_gemm_grouped: masked layout needs m_max %% 128 == 0 for more than one group (m_max=%d)", m);
-  return bn == 256 ? launch_gemm_tokm<256, false>(prm, use_pdl, (cudaStream_t)stream)
-                   : launch_gemm_tokm<128, false>(prm, use_pdl, (cudaStream_t)stream);
+  // offset: a group of len rows starting up to 3 rows into its first tile has ceil((len + 3) / 128) <= len / 128 + 2 tiles
+  if (mode == 3) prm.tiles_y = m / 128 + 2 * num_groups;
+  return bn == 256 ? launch_gemm_tokm<256, false, true>(prm, use_pdl, (cudaStream_t)stream)
+                   : launch_gemm_tokm<128, false, true>(prm, use_pdl, (cudaStream_t)stream);
 }
 
 }  // extern "C"

@@ -205,3 +205,36 @@ def m_grouped_gemm_fp8_fp8_bf16_nt_masked(lhs: Tuple[torch.Tensor, torch.Tensor]
                 lhs_scales.stride(2) if lhs_scales.shape[2] > 1 else get_tma_aligned_size(m, 4), rhs.data_ptr(),
                 rhs_scales.data_ptr(), out.data_ptr(), masked_m.data_ptr(), 2, num_groups, m, n, k, int(bool(use_pdl)),
                 _lib.current_stream()), "m_grouped_gemm_fp8_fp8_bf16_nt_masked")
+
+
+def m_grouped_gemm_fp8_fp8_bf16_nt_offset(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torch.Tensor, torch.Tensor],
+                                          out: torch.Tensor, m_offset: torch.Tensor, use_pdl: bool = False) -> None:
+    """Grouped GEMM, offset layout (jit_kernels/m_grouped_gemm.py:225-310): lhs [m_sum, k] e4m3 with scales
+    [m_sum, k/128]; rhs [groups, n, k] / scales [groups, n/128, k/128]; out [m_sum, n] bf16; m_offset int32
+    [groups + 1]: group g owns rows [m_offset[g], m_offset[g + 1]) -- any row counts, no alignment padding."""
+    lhs, lhs_scales = lhs
+    rhs, rhs_scales = rhs
+    m, k = lhs.shape
+    num_groups, n, k_ = rhs.shape
+    m_, n_ = out.shape
+    assert m == m_ and m_offset.numel() - 1 == num_groups and k == k_ and n == n_
+    assert lhs_scales.shape == (m, (k + 127) // 128)
+    assert rhs_scales.shape == (num_groups, (n + 127) // 128, (k + 127) // 128)
+    assert lhs.dtype == torch.float8_e4m3fn and lhs_scales.dtype == torch.float32
+    assert rhs.dtype == torch.float8_e4m3fn and rhs_scales.dtype == torch.float32
+    assert out.dtype == torch.bfloat16 and m_offset.dtype == torch.int32
+    assert lhs.is_contiguous() and rhs.is_contiguous() and out.is_contiguous() and m_offset.is_contiguous()
+    assert n % 128 == 0 and k % 128 == 0
+    lhs_scales = get_col_major_tma_aligned_tensor(lhs_scales)
+    assert rhs_scales.is_contiguous()
+    if m == 0:
+        return
+    if not lhs.is_cuda:
+        raise RuntimeError("m_grouped_gemm_fp8_fp8_bf16_nt_offset: tensors must be on a CUDA device (no CPU fallback)")
+    with torch.cuda.device(lhs.device):
+        _lib.check(
+            _lib.lib().b200_fp8_gemm_grouped_nt(
+                lhs.data_ptr(), lhs_scales.data_ptr(),
+                lhs_scales.stride(1) if lhs_scales.shape[1] > 1 else get_tma_aligned_size(m, 4), rhs.data_ptr(),
+                rhs_scales.data_ptr(), out.data_ptr(), m_offset.data_ptr(), 3, num_groups, m, n, k, int(bool(use_pdl)),
+                _lib.current_stream()), "m_grouped_gemm_fp8_fp8_bf16_nt_offset")
