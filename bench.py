@@ -2,11 +2,14 @@
 """bench.py -- decode tokens/s of the quantised decode hot path (DeepSeek-V3 MLA, per-token-FP8 KV, bs=128, seq=4K).
 
 One "step" = one decode step of the hot path through all 61 layers for one batch: per layer
-  act-quant + FP8 GEMM (fused_qkv_a_proj shape) -> quantize_and_cache_k (new token) -> act-quant + FP8 GEMM (q_b_proj)
-  -> quantize q -> paged MLA decode over the FP8 KV pool (+ split-KV combine) -> act-quant + FP8 GEMM (o_proj,
-  row-parallel) -> [all-reduce when tp > 1].
-The bf16 absorb bmm's (w_kc / w_vc), rope and norms are outside the path and are not run; the
-attention q and the o_proj input are taken from the producing GEMM / attention outputs by slicing.
+  act-quant + FP8 GEMM (fused_qkv_a_proj shape) -> act-quant + FP8 GEMM (q_b_proj) -> fused prologue (rotary embedding
+  of q_pe / k_pe, q quantiser, quantise-and-cache of the new token's K: one launch) -> paged MLA decode over the FP8 KV
+  pool (+ split-KV combine) -> act-quant + FP8 GEMM (o_proj, row-parallel) -> [all-reduce when tp > 1].
+`--unfused-prologue` runs the reference's sequence instead (quantize_and_cache_k, a copy standing in for rope's write of
+Q's rope columns, quantize_ckv_per_token_head: three launches).
+The bf16 absorb bmm's (w_kc / w_vc) and norms are outside the path and are not run; the latent
+part of the absorbed q is a resident random tensor, its rope part and the o_proj input are taken from the producing
+GEMM / attention outputs by slicing.
 
 tokens/s = batch / step time.  `value` is timed with inputs resident in HBM (CUDA-graph replay of the step);
 `e2e` adds, inside the timed region, the pinned-host -> device copy of the step inputs (hidden states, block table,
@@ -56,6 +59,9 @@ def parse():
                          "column- and row-parallel weights over the GPUs with one all-reduce per layer (strong scaling; "
                          "MLA's single latent KV head makes every rank stream the whole KV pool).  The dp run also "
                          "reports a short tp measurement under \"tp_strong\".")
+    ap.add_argument("--unfused-prologue", action="store_true",
+                    help="run quantize_and_cache_k / rope stand-in copy / quantize_ckv_per_token_head as separate "
+                         "launches instead of the fused prologue kernel (A/B)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="time only the MLA decode kernel per layer")
@@ -182,6 +188,14 @@ class HotPath:
         self.seqlens = self.seqlens_host.to(dev)
         last = seq - 1
         self.out_cache_loc = (self.block_table[:, last // PAGE].to(torch.int64) * PAGE + last % PAGE).to(torch.int32)
+        # rotary embedding inputs of the fused prologue: the new token's position, a cos | sin table of the model's layout
+        # (python/sglang/srt/layers/rotary_embedding.py:791-802)
+        self.positions = torch.full((b,), last, dtype=torch.int64, device=dev)
+        inv_freq = 1.0 / (10000.0 ** (torch.arange(0, ROPE, 2, dtype=torch.float32) / ROPE))
+        freqs = torch.arange(seq, dtype=torch.float32)[:, None] * inv_freq[None, :]
+        self.cos_sin_cache = torch.cat([freqs.cos(), freqs.sin()], dim=-1).contiguous().to(dev)
+        from sglang_fluentllm_b200 import rope as rope_mod
+        self.rope_mod = rope_mod
 
         def weight(n, k):
             w = (torch.randn(n, k, dtype=torch.bfloat16, device=dev, generator=g) * (k ** -0.5)).contiguous()
@@ -231,20 +245,33 @@ class HotPath:
         torch, fm = self.torch, self.fm
         b, h = self.args.batch, self.h
         y_a = self.linear(x, self.w_qkv_a[l])
-        k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
-        fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
-        q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
-        # absorbed q [b, 1, h, 576]: the w_kc bmm + rope are outside the path; their stand-in refreshes 64 of the 576
-        # columns of a resident random q from this step's q_b_proj output
-        q_abs = self.q_abs
-        q_abs[..., :64].copy_(q_full[:, : h * 64].view(b, 1, h, 64))  # one small strided copy, not a 19 MB broadcast add
-        q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
+        q_abs = self.q_abs  # absorbed q [b, 1, h, 576]: its latent 512 columns stand in for the w_kc bmm output
+        if self.args.unfused_prologue:
+            k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
+            fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
+            q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
+            # stand-in for rope's write of Q's rope columns: one small strided copy from this step's q_b_proj output
+            q_abs[..., KV_LORA:].copy_(q_full.view(b, 1, h, NOPE_HEAD + ROPE)[..., NOPE_HEAD:])
+            q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
+            self.launches_per_step += 2
+        else:
+            q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
+            slots = self.n_pages * PAGE
+            arg = self.rope_mod.FusedSetKVBufferArg(
+                value=y_a[:, Q_LORA:Q_LORA + KV_LORA], k_buffer=self.k_rope[l].view(slots, ROPE),
+                v_buffer=self.k_lora[l].view(slots, KV_LORA), scale_buffer=self.k_scale[l].view(slots),
+                cache_loc=self.out_cache_loc)
+            q_nope, q_scale, q_rope = self.rope_mod.fused_rope_quantize_set_kv(
+                self.positions, q_abs[:, 0, :, :KV_LORA], q_full.view(b, h, NOPE_HEAD + ROPE)[..., NOPE_HEAD:],
+                y_a[:, Q_LORA + KV_LORA:], self.cos_sin_cache, False, arg)
+            q_nope, q_scale, q_rope = (q_nope.view(b, 1, h, KV_LORA), q_scale.view(b, 1, h, 1), q_rope.view(b, 1, h, ROPE))
+            self.launches_per_step += 1
         n_pages = self.n_pages
         out, _ = fm.flash_mla_ckv_fp8_per_token(
             q_nope, q_rope, self.k_lora[l].view(n_pages, PAGE, 1, KV_LORA), self.k_rope[l].view(n_pages, PAGE, 1, ROPE),
             q_scale, self.k_scale[l].view(n_pages, PAGE, 1, 1), self.block_table, self.seqlens, KV_LORA, self.meta,
             self.num_splits, out=self.attn_out, lse=self.lse, workspace=self.workspace)
-        self.launches_per_step += 4
+        self.launches_per_step += 2  # decode + combine
         attn_o = out[..., :V_HEAD].reshape(b, h * V_HEAD)  # stand-in for the w_vc bmm output
         y = self.linear(attn_o, self.w_o[l])
         if self.tp > 1:
@@ -408,6 +435,7 @@ def run_b200(args):
                    "global_batch": args.batch * n_repl, "seq_len": args.seq, "heads_per_gpu": hp.h,
                    "parallelism": "%s%d" % (args.parallelism, world), "page_size": PAGE,
                    "cuda_graph": graph is not None,
+                   "prologue": "unfused (3 launches)" if args.unfused_prologue else "fused rope + q quantiser + K cache",
                    "l2": "inputs larger than L2: %.1f GB of distinct KV + weights streamed per step" % (
                        args.layers * (bytes_ + 0) / 1e9)},
         "e2e": {"value": round(e2e_tokens_per_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d,

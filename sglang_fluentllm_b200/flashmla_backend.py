@@ -174,6 +174,41 @@ class MLATokenToKVPool:
         else:
             self.kv_buffer[layer.layer_id][loc] = cache_k.view(-1, 1, cache_k.shape[-1]).to(self.model_dtype)
 
+    # ---- the formats either side of the path: PD-disaggregation transfer descriptors and the
+    # radix cache's slot moves see the three tensors per layer, grouped by tensor kind
+    def get_kv_size_bytes(self) -> int:
+        """memory_pool.py:779-784."""
+        total = 0
+        for kv in self.kv_buffer:
+            total += sum(t.nbytes for t in kv) if isinstance(kv, tuple) else kv.nbytes
+        return total
+
+    def get_contiguous_buf_infos(self):
+        """memory_pool.py:787-800: (data_ptrs, data_lens, item_lens) of every transferable buffer; an item is one page.
+        per_token_head: all layers' latent tensors, then all scale tensors, then all rope tensors."""
+        if self.quant_method == "per_token_head":
+            bufs = [kv[i] for i in range(3) for kv in self.kv_buffer]
+        else:
+            bufs = list(self.kv_buffer)
+        return ([b.data_ptr() for b in bufs], [b.nbytes for b in bufs], [b[0].nbytes * self.page_size for b in bufs])
+
+    def get_layerwise_buf_info_offsets(self, start_idx: int = 0):
+        """memory_pool.py:802-806: for each layer, the indices of its buffers in get_contiguous_buf_infos()."""
+        layer_num = len(self.kv_buffer)
+        if self.quant_method == "per_token_head":
+            return [[start_idx + i * layer_num + layer_id for i in range(3)] for layer_id in range(layer_num)]
+        return [[start_idx + layer_id] for layer_id in range(layer_num)]
+
+    def move_kv_cache(self, tgt_loc: torch.Tensor, src_loc: torch.Tensor):
+        """memory_pool.py:747-764 (the native path): copy token slots src_loc -> tgt_loc in every layer, all three
+        tensors -- codes, scales and pre-divided rope move together, so a moved token dequantises identically."""
+        if tgt_loc.numel() == 0:
+            return
+        tgt, src = tgt_loc.view(-1).long(), src_loc.view(-1).long()
+        for kv in self.kv_buffer:
+            for buf in (kv if isinstance(kv, tuple) else (kv,)):
+                buf[tgt] = buf[src]
+
     def get_key_split_contiguous(self, layer_id: int, indices: torch.Tensor):
         """memory_pool.py:817-824."""
         if self.quant_method == "per_token_head":

@@ -12,7 +12,9 @@ What can be pinned this way:
     89-141) -- the file itself does not import (stale names), so the two functions are extracted by AST;
   * per_token_cast_to_fp8 / per_block_cast_to_fp8 (3rdparty/deep_gemm/tests/test_core.py:9-25), same extraction.
   * DeepseekScalingRotaryEmbedding.forward_native (python/sglang/srt/layers/rotary_embedding.py:804-846), both pairings
-    (`python tests/golden/make_golden.py rope` regenerates only this one).
+    (`python tests/golden/make_golden.py rope` regenerates only this one);
+  * MLATokenToKVPool.get_contiguous_buf_infos / get_layerwise_buf_info_offsets / move_kv_cache
+    (mem_cache/memory_pool.py:747-806), both pool layouts.
 The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
 """
 import ast
@@ -69,6 +71,42 @@ def extract_functions(path, names):
     return [ns[n] for n in names]
 
 
+def make_pool_disagg():
+    """PD-disaggregation descriptors and slot moves of the per_token_head pool through the reference's own class on CPU
+    (python/sglang/srt/mem_cache/memory_pool.py:747-806)."""
+    from sglang.srt.mem_cache.memory_pool import MLATokenToKVPool
+    torch.manual_seed(2)
+    out = {}
+    for qm, dtype in (("per_token_head", torch.float8_e4m3fn), ("none", torch.bfloat16)):
+        pool = MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, dtype=dtype, quant_method=qm, kv_lora_rank=512,
+                                qk_rope_head_dim=64, layer_num=3, device="cpu", enable_memory_saver=False,
+                                max_batch_size=4, max_context_len=256, page_size=64, rank=0, enable_alt_stream=False)
+        ptrs, lens, item_lens = pool.get_contiguous_buf_infos()
+        bufs = [t for kv in pool.kv_buffer for t in (kv if isinstance(kv, tuple) else (kv,))]
+        order = [[b.data_ptr() for b in bufs].index(p) for p in ptrs]   # which tensor (layer-major flat index) each is
+        out["lens_" + qm], out["item_lens_" + qm], out["order_" + qm] = np.array(lens), np.array(item_lens), np.array(order)
+        out["offsets_" + qm] = np.array(pool.get_layerwise_buf_info_offsets(5))
+        try:
+            out["size_bytes_" + qm] = np.array(pool.get_kv_size_bytes())
+        except AttributeError:   # :779-784 calls get_tensor_size_bytes on the per-layer tuple of the FP8 layout and raises
+            out["size_bytes_" + qm] = np.array(-1)
+        if qm == "per_token_head":
+            for kv in pool.kv_buffer:
+                kv[0].copy_(torch.randint(0, 255, kv[0].shape, dtype=torch.uint8).view(kv[0].dtype))
+                kv[1].copy_(torch.rand(kv[1].shape))
+                kv[2].copy_(torch.randn(kv[2].shape).to(torch.bfloat16))
+            before = [[t.clone() for t in kv] for kv in pool.kv_buffer]
+            src, tgt = torch.tensor([64, 65, 70, 200]), torch.tensor([130, 131, 64, 319])
+            pool._kv_copy_config = None   # the native path (:748-764); the Triton tiled copy needs a GPU
+            pool.move_kv_cache(tgt, src)
+            out["move_src"], out["move_tgt"] = src.numpy(), tgt.numpy()
+            for l, kv in enumerate(pool.kv_buffer):
+                for i, name in enumerate(("lora", "scale", "rope")):
+                    out["before_%s_%d" % (name, l)] = before[l][i].view(torch.uint8).numpy() if i == 0 else before[l][i].float().numpy()
+                    out["after_%s_%d" % (name, l)] = kv[i].view(torch.uint8).numpy() if i == 0 else kv[i].float().numpy()
+    np.savez_compressed(os.path.join(HERE, "pool_disagg.npz"), **out)
+
+
 def make_rope():
     """Rotary embedding of the MLA rope dims through the reference's own classes on CPU
     (python/sglang/srt/layers/rotary_embedding.py: DeepseekScalingRotaryEmbedding.forward_native :804-846 with the
@@ -97,8 +135,9 @@ def make_rope():
 def main():
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, os.path.join(REF, "python"))
-    if sys.argv[1:] == ["rope"]:  # regenerate only this fixture (the others stay byte-identical in git)
-        make_rope()
+    if sys.argv[1:] and set(sys.argv[1:]) <= {"rope", "pool_disagg"}:  # regenerate only these fixtures
+        for name in sys.argv[1:]:
+            {"rope": make_rope, "pool_disagg": make_pool_disagg}[name]()
         return
     torch.manual_seed(0)
 
@@ -175,6 +214,7 @@ def main():
                         xs=xs.numpy(), w=w.float().numpy(), wq=wq.view(torch.uint8).numpy(), ws=ws.numpy(),
                         c=c.numpy(), xq_cast=xq2.view(torch.uint8).numpy(), xs_cast=xs2.numpy())
     make_rope()
+    make_pool_disagg()
     print("golden fixtures written to", HERE)
 
 

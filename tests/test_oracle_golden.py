@@ -189,3 +189,42 @@ def test_fused_prologue_oracle_is_the_unfused_sequence(golden_dir):
     assert np.allclose(deq_r[:, 0], g["k_out_gptj"][:, 0], rtol=2 ** -7, atol=1e-6)
     x, y = g["q_pe"], g["q_out_gptj"]
     assert np.allclose(x[..., 0::2] ** 2 + x[..., 1::2] ** 2, y[..., 0::2] ** 2 + y[..., 1::2] ** 2, rtol=3e-2, atol=1e-3)
+
+
+def test_pool_disagg_descriptors_and_moves_match_reference(golden_dir):
+    """The host mirror of MLATokenToKVPool (sglang_fluentllm_b200/flashmla_backend.py) against the reference class run on
+    CPU (mem_cache/memory_pool.py:747-806): transfer descriptors of both layouts (order, byte lengths, page item
+    lengths, per-layer offsets) and move_kv_cache on the three-tensor layout, bit for bit."""
+    torch = pytest.importorskip("torch")
+    from sglang_fluentllm_b200 import flashmla_backend as fb
+    g = _load(golden_dir, "pool_disagg.npz")
+    for qm in ("per_token_head", "none"):
+        pool = fb.MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
+                                   layer_num=3, device="cpu", quant_method=qm)
+        ptrs, lens, item_lens = pool.get_contiguous_buf_infos()
+        bufs = [t for kv in pool.kv_buffer for t in (kv if isinstance(kv, tuple) else (kv,))]
+        order = [[b.data_ptr() for b in bufs].index(p) for p in ptrs]
+        assert order == g["order_" + qm].tolist()
+        assert lens == g["lens_" + qm].tolist() and item_lens == g["item_lens_" + qm].tolist()
+        assert pool.get_layerwise_buf_info_offsets(5) == g["offsets_" + qm].tolist()
+        if int(g["size_bytes_" + qm]) >= 0:   # the reference's own method raises on the tuple layout (:779-784)
+            assert pool.get_kv_size_bytes() == int(g["size_bytes_" + qm])
+        else:
+            assert pool.get_kv_size_bytes() == sum(lens)
+    pool = fb.MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
+                               layer_num=3, device="cpu", quant_method="per_token_head")
+    for l, kv in enumerate(pool.kv_buffer):
+        kv[0].copy_(torch.from_numpy(g["before_lora_%d" % l]))
+        kv[1].copy_(torch.from_numpy(g["before_scale_%d" % l]))
+        kv[2].copy_(torch.from_numpy(g["before_rope_%d" % l]).to(torch.bfloat16))
+    pool.move_kv_cache(torch.from_numpy(g["move_tgt"]), torch.from_numpy(g["move_src"]))
+    for l, kv in enumerate(pool.kv_buffer):
+        assert np.array_equal(kv[0].numpy(), g["after_lora_%d" % l])
+        assert np.array_equal(kv[1].numpy(), g["after_scale_%d" % l])
+        assert np.array_equal(kv[2].float().numpy(), g["after_rope_%d" % l])
+    # a moved token de-quantises to the same values (codes, scale and pre-divided rope travel together)
+    src, tgt = g["move_src"], g["move_tgt"]
+    a = opool.pool_fallback_dequantize(g["after_lora_0"], g["after_scale_0"], g["after_rope_0"], tgt[[0, 1, 3]])
+    b = opool.pool_fallback_dequantize(g["before_lora_0"], g["before_scale_0"], g["before_rope_0"], src[[0, 1, 3]])
+    for x, y in zip(a, b):
+        assert np.array_equal(x, y, equal_nan=True)
