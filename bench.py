@@ -8,8 +8,8 @@ One "step" = one decode step of the hot path through all 61 layers for one batch
 `--unfused-prologue` runs the reference's sequence instead (quantize_and_cache_k, a copy standing in for rope's write of
 Q's rope columns, quantize_ckv_per_token_head: three launches).
 The bf16 absorb bmm's (w_kc / w_vc) and norms are outside the path and are not run; the latent
-part of the absorbed q is a resident random tensor, its rope part and the o_proj input are taken from the producing
-GEMM / attention outputs by slicing.
+part of the absorbed q is a resident random tensor, its rope part and the o_proj input are slices of the producing
+GEMM / attention outputs, read in place by the strided activation quantiser (no torch copy kernels in the step).
 
 tokens/s = batch / step time.  `value` is timed with inputs resident in HBM (CUDA-graph replay of the step);
 `e2e` adds, inside the timed region, the pinned-host -> device copy of the step inputs (hidden states, block table,
@@ -62,6 +62,8 @@ def parse():
     ap.add_argument("--unfused-prologue", action="store_true",
                     help="run quantize_and_cache_k / rope stand-in copy / quantize_ckv_per_token_head as separate "
                          "launches instead of the fused prologue kernel (A/B)")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="run ONE eager step between cudaProfilerStart/Stop and exit (for an ncu launch list of the step)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--kernel-only", action="store_true", help="time only the MLA decode kernel per layer")
@@ -234,8 +236,11 @@ class HotPath:
                                                  self._lib.current_stream()), "get_mla_metadata")
 
     def linear(self, x, w):
-        from sglang_fluentllm_b200.fp8_kernel import sglang_per_token_group_quant_fp8 as quant
-        xq, xs = quant(x, 128, column_major_scales=True, scale_tma_aligned=True)
+        from sglang_fluentllm_b200 import fp8_kernel as fk
+        if x.dim() == 2 and x.is_contiguous():
+            xq, xs = fk.sglang_per_token_group_quant_fp8(x, 128, column_major_scales=True, scale_tma_aligned=True)
+        else:  # a slice of the producer's output, quantised in place (no .contiguous() copy)
+            xq, xs = fk.per_token_group_quant_fp8_strided(x)
         out = self.torch.empty(x.shape[0], w[0].shape[0], dtype=self.torch.bfloat16, device=self.dev)
         self.dg.gemm_fp8_fp8_bf16_nt((xq, xs), w, out, True)
         self.launches_per_step += 2
@@ -249,13 +254,13 @@ class HotPath:
         if self.args.unfused_prologue:
             k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
             fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
-            q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
+            q_full = self.linear(y_a[:, :Q_LORA], self.w_q_b[l])
             # stand-in for rope's write of Q's rope columns: one small strided copy from this step's q_b_proj output
             q_abs[..., KV_LORA:].copy_(q_full.view(b, 1, h, NOPE_HEAD + ROPE)[..., NOPE_HEAD:])
             q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
             self.launches_per_step += 2
         else:
-            q_full = self.linear(y_a[:, :Q_LORA].contiguous(), self.w_q_b[l])
+            q_full = self.linear(y_a[:, :Q_LORA], self.w_q_b[l])
             slots = self.n_pages * PAGE
             arg = self.rope_mod.FusedSetKVBufferArg(
                 value=y_a[:, Q_LORA:Q_LORA + KV_LORA], k_buffer=self.k_rope[l].view(slots, ROPE),
@@ -272,7 +277,7 @@ class HotPath:
             q_scale, self.k_scale[l].view(n_pages, PAGE, 1, 1), self.block_table, self.seqlens, KV_LORA, self.meta,
             self.num_splits, out=self.attn_out, lse=self.lse, workspace=self.workspace)
         self.launches_per_step += 2  # decode + combine
-        attn_o = out[..., :V_HEAD].reshape(b, h * V_HEAD)  # stand-in for the w_vc bmm output
+        attn_o = out[:, 0, :, :V_HEAD]  # [b, h, 128] view standing in for the w_vc bmm output, quantised in place
         y = self.linear(attn_o, self.w_o[l])
         if self.tp > 1:
             self.tpmod.all_reduce_sum(y)  # the path's single exchange: row-parallel partial sums over NVLink
@@ -344,6 +349,15 @@ def run_b200(args):
             hp.step(hp.hidden_in)
         stream.synchronize()
         log("eager warm-up done")
+        if args.profile_step:
+            # launch list of exactly one step: run under
+            #   ncu --profile-from-start off --metrics gpu__time_duration.sum --clock-control none --csv --log-file ...
+            torch.cuda.profiler.start()
+            hp.step(hp.hidden_in)
+            stream.synchronize()
+            torch.cuda.profiler.stop()
+            print(json.dumps({"profile_step": True, "gpu_launches": hp.launches_per_step}))
+            return
         graph = None
         if not args.no_graph:
             graph = torch.cuda.CUDAGraph()

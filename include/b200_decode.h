@@ -134,6 +134,13 @@ int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t
  *   x bf16 [m][k]; q e4m3 [m][k]; scales f32 [k/128][scale_stride], scale_stride = m rounded up to 4. */
 int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* scales, int64_t scale_stride, float eps,
                          void* stream);
+/* Same quantiser reading its input in place from a strided producer output: group (i, g) of the logical [m][k] input
+ * is the 128 contiguous bf16 values at x + i * x_row_stride + g * x_group_stride (elements; both multiples of 8).
+ * Covers a column slice of a wider row (row stride > k, group stride 128: the q_a columns of the fused qkv_a projection,
+ * python/sglang/srt/models/deepseek_v2.py:796-807) and a per-head slice [m][heads][128] of wider heads (group stride =
+ * head stride).  q is written contiguous [m][k]. */
+int b200_act_quant_1x128_strided(const void* x, int64_t x_row_stride, int64_t x_group_stride, int64_t m, int64_t k,
+                                 void* q, float* scales, int64_t scale_stride, float eps, void* stream);
 
 /* Block-scaled W8A8 FP8 GEMM, out[m][n] = bf16( sum_kb a_scales[kb][i] * b_scales[n/128][kb] * (A_kb . B_kb^T) ).
  * Replaces deep_gemm.gemm_fp8_fp8_bf16_nt (3rdparty/deep_gemm/deep_gemm/jit_kernels/gemm.py:145-226 ->

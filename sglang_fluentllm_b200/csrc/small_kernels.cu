@@ -326,8 +326,9 @@ __global__ void __launch_bounds__(256)
 // scales are written column-major [k/128][scale_stride] (scale_stride = m padded to 4: TMA-aligned).
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-    act_quant_1x128_kernel(const __nv_bfloat16* __restrict__ x, uint8_t* __restrict__ q, float* __restrict__ scales,
-                           int64_t num_groups, int groups_per_row, int64_t scale_stride, float eps) {
+    act_quant_1x128_kernel(const __nv_bfloat16* __restrict__ x, int64_t x_row_stride, int64_t x_group_stride,
+                           uint8_t* __restrict__ q, float* __restrict__ scales, int64_t num_groups, int groups_per_row,
+                           int64_t scale_stride, float eps) {
   // the GEMM behind this kernel is launched with programmatic stream serialization: let its CTAs start their prologue
   // (barrier init, TMEM allocation, descriptor prefetch) now; its griddepcontrol.wait still orders the data
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
@@ -335,7 +336,11 @@ __global__ void __launch_bounds__(256)
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
   const int sub = threadIdx.x & 15;
   if (g >= num_groups) return;
-  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + g * 128) + sub);
+  // group (row, col) of the input sits at x + row * x_row_stride + col * x_group_stride (contiguous: k and 128): the
+  // producer's output is read in place when it is a column slice ([m, k] of a wider row) or a per-head slice
+  // ([m, heads, 128] of wider heads) -- no .contiguous() copy in front of the quantiser
+  const int64_t row = g / groups_per_row, col = g % groups_per_row;
+  const uint4 raw = __ldg(reinterpret_cast<const uint4*>(x + row * x_row_stride + col * x_group_stride) + sub);
   const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
   float v[8];
   float amax = eps;
@@ -348,10 +353,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
   for (int o = 8; o > 0; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, o, 16));
   const float s = __fdiv_rn(amax, FP8_MAX);
-  if (sub == 0) {
-    const int64_t row = g / groups_per_row, col = g % groups_per_row;
-    scales[col * scale_stride + row] = s;
-  }
+  if (sub == 0) scales[col * scale_stride + row] = s;
   float qv[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) qv[j] = fminf(fmaxf(__fdiv_rn(v[j], s), -FP8_MAX), FP8_MAX);
@@ -512,15 +514,23 @@ int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t
 
 int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* scales, int64_t scale_stride, float eps,
                          void* stream) {
+  return b200_act_quant_1x128_strided(x, k, 128, m, k, q, scales, scale_stride, eps, stream);
+}
+
+int b200_act_quant_1x128_strided(const void* x, int64_t x_row_stride, int64_t x_group_stride, int64_t m, int64_t k,
+                                 void* q, float* scales, int64_t scale_stride, float eps, void* stream) {
   B200_CHECK(x && q && scales, "act_quant: null pointer");
   B200_CHECK(k % 128 == 0, "act_quant: k=%lld must be a multiple of 128", (long long)k);
   B200_CHECK(scale_stride >= m, "act_quant: scale_stride %lld < m %lld", (long long)scale_stride, (long long)m);
+  B200_CHECK(x_row_stride % 8 == 0 && x_group_stride % 8 == 0 && x_group_stride >= 128 && ((uintptr_t)x & 15) == 0,
+             "act_quant: input groups must be 16-byte aligned (row stride %lld, group stride %lld)",
+             (long long)x_row_stride, (long long)x_group_stride);
   if (m == 0) return 0;
   const int64_t groups = m * (k / 128);
   const int groups_per_block = 16;
   return launch_kernel(act_quant_1x128_kernel, dim3((unsigned)((groups + groups_per_block - 1) / groups_per_block)),
                        dim3(groups_per_block * 16), 0, (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)x,
-                       (uint8_t*)q, scales, groups, (int)(k / 128), scale_stride, eps);
+                       x_row_stride, x_group_stride, (uint8_t*)q, scales, groups, (int)(k / 128), scale_stride, eps);
 }
 
 }  // extern "C"

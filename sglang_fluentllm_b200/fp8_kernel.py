@@ -57,3 +57,35 @@ def sglang_per_token_group_quant_fp8(x: torch.Tensor, group_size: int, eps: floa
         _lib.check(_lib.lib().b200_act_quant_1x128(x.data_ptr(), m, k, x_q.data_ptr(), tmp.data_ptr(), m, float(eps),
                                                    _lib.current_stream()), "per_token_group_quant_fp8")
     return x_q, tmp.t().contiguous().view(tuple(x.shape[:-1]) + (k // group_size,))
+
+
+def per_token_group_quant_fp8_strided(x: torch.Tensor, eps: float = 1e-10) -> Tuple[torch.Tensor, torch.Tensor]:
+    """The DeepGEMM-layout quantiser (group 128, column-major TMA-aligned scales) on a producer's output read in place:
+    x bf16 ``[m, k]`` with any row stride (a column slice of a wider projection output) or ``[m, heads, 128]`` with any
+    row / head strides (a per-head slice).  Returns (x_q e4m3 ``[m, k]`` contiguous, x_s f32 ``[m, k/128]``) -- the same
+    bits ``sglang_per_token_group_quant_fp8(x.contiguous(), 128, column_major_scales=True, scale_tma_aligned=True)``
+    gives, without the copy."""
+    if not x.is_cuda:
+        raise RuntimeError("per_token_group_quant_fp8_strided: CUDA tensor required (no CPU fallback)")
+    if x.dtype != torch.bfloat16 or x.dim() not in (2, 3) or x.stride(-1) != 1:
+        raise RuntimeError("per_token_group_quant_fp8_strided: bf16 [m, k] or [m, heads, 128] with a contiguous last "
+                           "dimension expected")
+    m = x.shape[0]
+    if x.dim() == 3:
+        if x.shape[2] != 128:
+            raise RuntimeError("per_token_group_quant_fp8_strided: 3-D input must be [m, heads, 128]")
+        k = x.shape[1] * 128
+        group_stride = x.stride(1) if x.shape[1] > 1 else 128
+        row_stride = x.stride(0) if m > 1 else x.shape[1] * group_stride
+    else:
+        k = x.shape[1]
+        assert k % 128 == 0, "the last dimension of `x` cannot be divisible by `group_size`"
+        group_stride, row_stride = 128, (x.stride(0) if m > 1 else k)
+    x_q = torch.empty((m, k), dtype=fp8_dtype, device=x.device)
+    x_s = create_per_token_group_quant_fp8_output_scale((m, k), x.device, 128, True, True)
+    stride = x_s.stride(1) if x_s.shape[1] > 1 else (m + 3) // 4 * 4
+    with torch.cuda.device(x.device):
+        _lib.check(_lib.lib().b200_act_quant_1x128_strided(x.data_ptr(), row_stride, group_stride, m, k, x_q.data_ptr(),
+                                                           x_s.data_ptr(), stride, float(eps), _lib.current_stream()),
+                   "per_token_group_quant_fp8_strided")
+    return x_q, x_s
