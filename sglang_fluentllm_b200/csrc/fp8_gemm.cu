@@ -260,7 +260,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
     int g;
     if (p.group_mode == 1) {
       g = __ldg(p.group_layout + m0);
-      if (g < 0) return;
+      if (g < 0 || g >= p.num_groups) return;  // -1: skipped block; anything else out of range is not dereferenced
     } else if (p.group_mode == 3) {
       // m_grouped_gemm_fp8_fp8_bf16_nt_offset (m_grouped_gemm.py:225-310): groups start at arbitrary rows.  A group's
       // tiles start at its first row rounded down to 4 (the activation-scale columns are fetched in 16-byte pieces);
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
         if (ty < nt) break;
         ty -= nt;
       }
-      if (g == p.num_groups) return;
+      if (g == p.num_groups || lo < 0 || hi > p.m) return;  // surplus CTA, or offsets outside the row range
       m0 = (lo & ~3) + ty * 128;
       m_begin = lo;
       m_end = hi;
@@ -754,8 +754,9 @@ int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_sca
   // launch_gemm_tokm sizes grid.y from prm.m: [groups * m_max] rows only tile per group when m_max is a multiple of 128
   B200_CHECK(mode != 2 || m % 128 == 0 || num_groups == 1,
              "fp8_gemm_grouped: masked layout needs m_max %% 128 == 0 for more than one group (m_max=%d)", m);
-  // offset: a group of len rows starting up to 3 rows into its first tile has ceil((len + 3) / 128) <= len / 128 + 2 tiles
-  if (mode == 3) prm.tiles_y = m / 128 + 2 * num_groups;
+  // offset: a non-empty group of len rows starting up to 3 rows into its first tile has ceil((len + 3) / 128) <=
+  // (len + 130) / 128 tiles, so all groups together have at most floor((m + 130 * groups) / 128)
+  if (mode == 3) prm.tiles_y = (int)(((int64_t)m + 130 * (int64_t)num_groups) / 128);
   return bn == 256 ? launch_gemm_tokm<256, false, true>(prm, use_pdl, (cudaStream_t)stream)
                    : launch_gemm_tokm<128, false, true>(prm, use_pdl, (cudaStream_t)stream);
 }

@@ -15,6 +15,7 @@ dev = torch.device("cuda:0")
 
 
 def time_graph(fn, n_rot, reps=5):
+    torch.cuda.synchronize()  # inputs were produced on the default stream
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for i in range(min(n_rot, 2)):
