@@ -166,6 +166,7 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
  *   mode 3 (offset): a e4m3 [m][k], out bf16 [m][n], any m, group_layout = m_offset int32 [num_groups + 1]
  *     (non-decreasing, m_offset[num_groups] <= m): group g owns rows [m_offset[g], m_offset[g + 1]); rows no group
  *     owns are left untouched; a_scales as mode 1. */
+int b200_fp8_gemm_grouped_row_tiles(int mode, int num_groups, int m); /* grid.y of the launch (host-only helper) */
 int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
                              const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
                              int m, int n, int k, int use_pdl, void* stream);

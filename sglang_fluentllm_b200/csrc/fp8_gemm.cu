@@ -717,6 +717,17 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
   return rc;
 }
 
+/* Row tiles (grid.y) a grouped launch carries.  Offset layout: a non-empty group of len rows starting up to 3 rows into
+ * its first tile has ceil((len + 3) / 128) <= (len + 130) / 128 tiles, so all groups together have at most
+ * floor((m + 130 * groups) / 128); surplus CTAs leave at once. */
+int b200_fp8_gemm_grouped_row_tiles(int mode, int num_groups, int m) {
+  if (num_groups <= 0 || m < 0) return 0;
+  if (mode == 1) return (m + 127) / 128;
+  if (mode == 2) return (int)(((int64_t)num_groups * m + 127) / 128);
+  if (mode == 3) return (int)(((int64_t)m + 130 * (int64_t)num_groups) / 128);
+  return 0;
+}
+
 /* Grouped GEMMs on the tokens-on-M kernel: each 128-row tile multiplies its group's weights. */
 int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_scale_stride, const void* b,
                              const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
@@ -754,9 +765,7 @@ int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_sca
   // launch_gemm_tokm sizes grid.y from prm.m: [groups * m_max] rows only tile per group when m_max is a multiple of 128
   B200_CHECK(mode != 2 || m % 128 == 0 || num_groups == 1,
              "fp8_gemm_grouped: masked layout needs m_max %% 128 == 0 for more than one group (m_max=%d)", m);
-  // offset: a non-empty group of len rows starting up to 3 rows into its first tile has ceil((len + 3) / 128) <=
-  // (len + 130) / 128 tiles, so all groups together have at most floor((m + 130 * groups) / 128)
-  if (mode == 3) prm.tiles_y = (int)(((int64_t)m + 130 * (int64_t)num_groups) / 128);
+  if (mode == 3) prm.tiles_y = b200_fp8_gemm_grouped_row_tiles(mode, num_groups, m);
   return bn == 256 ? launch_gemm_tokm<256, false, true>(prm, use_pdl, (cudaStream_t)stream)
                    : launch_gemm_tokm<128, false, true>(prm, use_pdl, (cudaStream_t)stream);
 }

@@ -54,6 +54,28 @@ def test_pure_host_entry_points(built_lib):
     assert L.b200_last_error() is not None
 
 
+def test_grouped_offset_layout_tile_bound(built_lib):
+    """The offset-layout grouped GEMM launches b200_fp8_gemm_grouped_row_tiles(3, groups, m) row tiles; a group's tiles
+    start at its first row rounded down to 4 (csrc/fp8_gemm.cu, GROUPED mode 3).  The grid must hold every tile the
+    kernel's own enumeration produces, for any m_offset."""
+    import random
+    from sglang_fluentllm_b200 import _lib
+    L = _lib.lib()
+    rnd = random.Random(0)
+    edge = [0, 0, 1, 2, 3, 4, 5, 125, 126, 127, 128, 129, 130, 253, 254, 255, 256]
+    for _ in range(20000):
+        groups = rnd.randint(1, 12)
+        lens = [rnd.choice(edge + [rnd.randint(0, 600)]) for _ in range(groups)]
+        off = [0]
+        for n in lens:
+            off.append(off[-1] + n)
+        m = off[-1] + rnd.choice([0, 0, 1, 9, 200])
+        need = sum((off[g + 1] - (off[g] & ~3) + 127) // 128 for g in range(groups) if off[g + 1] > off[g])
+        assert need <= L.b200_fp8_gemm_grouped_row_tiles(3, groups, m), (lens, m)
+    assert L.b200_fp8_gemm_grouped_row_tiles(1, 4, 1152) == 9
+    assert L.b200_fp8_gemm_grouped_row_tiles(2, 4, 256) == 8
+
+
 def test_sass_uses_blackwell_tensor_and_tma_paths(built_lib):
     """The product kernels must be tcgen05 / TMA code, not legacy mma.sync."""
     import subprocess
