@@ -330,6 +330,7 @@ def run_b200(args):
         args.parallelism = "dp" if world > 1 else "tp"
     hp = HotPath(args, rank, world, dev)
     log("state built")
+    torch.cuda.synchronize()  # the state was built on the default stream; the step runs on its own stream
     stream = torch.cuda.Stream(device=dev)
     peaks = {}
     try:
@@ -470,6 +471,7 @@ def run_b200(args):
         targs = copy.copy(args)
         targs.parallelism = "tp"
         hp_tp = HotPath(targs, rank, world, dev)
+        torch.cuda.synchronize()
         with torch.cuda.stream(stream):
             for _ in range(2):
                 hp_tp.step(hp_tp.hidden_in)

@@ -331,7 +331,12 @@ class FlashMLABackend(AttentionBackend):
             assert v is not None
             if save_kv_cache:
                 forward_batch.token_to_kv_pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
-        return self._attend(q, layer, forward_batch, forward_batch.seq_lens + self.draft_token_num)
+        cache_seqlens = forward_batch.seq_lens + self.draft_token_num
+        if isinstance(q, (tuple, list)):  # the fused prologue's (q_nope, q_scale, q_rope), as in forward_decode
+            if self.cache_quant_method != "per_token_head":
+                raise RuntimeError("a pre-quantised q needs the per_token_head KV pool")
+            return self._attend_quantized(*q, layer, forward_batch, cache_seqlens)
+        return self._attend(q, layer, forward_batch, cache_seqlens)
 
     # ------------------------------------------------------------------ metadata
     def _metadata(self, seq_lens, forward_mode):

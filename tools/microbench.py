@@ -11,6 +11,7 @@ PEAK = 6555.8
 
 
 def time_graph(fn, n_rot, reps=3):
+    torch.cuda.synchronize()  # inputs were produced on the default stream
     s = torch.cuda.Stream()
     with torch.cuda.stream(s):
         for i in range(min(n_rot, 2)):
