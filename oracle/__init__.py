@@ -13,6 +13,11 @@ Pinning status (see DESIGN.md "Oracle pinning"):
   * quantiser fall-back, indexed dequant, block-table allocator, torch-native
     SDPA decode, block-FP8 GEMM and 1x128 activation quantiser are pinned by
     golden vectors generated from the reference's own Python (tests/golden/).
+  * rotary embedding (oracle/rope.py) is pinned bit-for-bit by the reference's
+    DeepseekScalingRotaryEmbedding.forward_native (tests/golden/rope.npz).
+  * the attention restatements (bf16, semantic FP8, page-wise faithful FP8) pass the
+    reference's own kernel test -- its inputs, its fp32 ref_mla outputs and its
+    relative_L1 < 5e-2 criterion (tests/golden/mla_test_reference.npz).
   * the per-token-FP8 MLA decode kernel and the metadata scheduler exist in the
     reference only as sm_90a CUDA (wgmma) that cannot execute on this box; their
     restatements are pinned only through the semantic (dequantise -> fp32

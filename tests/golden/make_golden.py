@@ -13,6 +13,8 @@ What can be pinned this way:
   * per_token_cast_to_fp8 / per_block_cast_to_fp8 (3rdparty/deep_gemm/tests/test_core.py:9-25), same extraction.
   * DeepseekScalingRotaryEmbedding.forward_native (python/sglang/srt/layers/rotary_embedding.py:804-846), both pairings
     (`python tests/golden/make_golden.py rope` regenerates only this one);
+  * the reference's own attention test up to the kernel call: inputs, test-side quantisation and the fp32 `ref_mla`
+    outputs its kernel is compared with (3rdparty/flashmla-fp8/tests/test_flash_mla_ckv_fp8_per_token.py:12-101);
   * MLATokenToKVPool.get_contiguous_buf_infos / get_layerwise_buf_info_offsets / move_kv_cache
     (mem_cache/memory_pool.py:747-806), both pool layouts.
 The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
@@ -107,6 +109,75 @@ def make_pool_disagg():
     np.savez_compressed(os.path.join(HERE, "pool_disagg.npz"), **out)
 
 
+def make_mla_test_reference():
+    """The reference's own attention test re-run on CPU up to the kernel call
+    (3rdparty/flashmla-fp8/tests/test_flash_mla_ckv_fp8_per_token.py): its input construction (:48-69, NaN-poisoned
+    padding), its fp32 reference `ref_mla` / `scaled_dot_product_attention` (:12-30, :75-92, extracted by AST) and its
+    test-side per-token quantisation of q and of the paged K (:94-101).  The expected outputs are what the reference
+    compares its kernel against with relative_L1 < 5e-2 (:33-40)."""
+    import math
+    import random
+    path = os.path.join(REF, "3rdparty/flashmla-fp8/tests/test_flash_mla_ckv_fp8_per_token.py")
+    tree = ast.parse(open(path).read())
+    ns = {"torch": torch, "math": math}
+    for node in tree.body:
+        if isinstance(node, ast.FunctionDef) and node.name == "scaled_dot_product_attention":
+            exec(compile(ast.Module([node], []), path, "exec"), ns)
+    sdpa = ns["scaled_dot_product_attention"]
+    torch.manual_seed(0)
+    random.seed(0)
+    old_dtype = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)   # main(torch.bfloat16), :141-146
+    out = {}
+    try:
+        for tag, (b, s_q, mean_sk, h_q, causal, varlen) in {"decode": (3, 1, 120, 16, False, True),
+                                                             "verify": (2, 2, 100, 8, True, True)}.items():
+            h_kv, d, dv, block_size = 1, 576, 512, 64
+            cache_seqlens = torch.full((b,), mean_sk, dtype=torch.int32)
+            if varlen:
+                for i in range(b):
+                    cache_seqlens[i] = max(random.normalvariate(mean_sk, mean_sk / 2), s_q)
+            max_seqlen = cache_seqlens.max().item()
+            max_seqlen_pad = -(-max_seqlen // (block_size * 4)) * block_size * 4
+            q = torch.randn(b, s_q, h_q, d)
+            block_table = torch.arange(b * max_seqlen_pad // block_size, dtype=torch.int32).view(b, max_seqlen_pad // block_size)
+            blocked_k = torch.randn(block_table.numel(), block_size, h_kv, d)
+            for i in range(b):
+                blocked_k.view(b, max_seqlen_pad, h_kv, d)[i, cache_seqlens[i].item():] = float("nan")
+            blocked_v = blocked_k[..., :dv]
+            o_ref = torch.empty(b, s_q, h_q, dv, dtype=torch.float32)
+            lse_ref = torch.empty(b, h_q, s_q, dtype=torch.float32)
+            for i in range(b):
+                begin = i * max_seqlen_pad
+                end = begin + cache_seqlens[i]
+                O, LSE = sdpa(q[i].transpose(0, 1), blocked_k.view(-1, h_kv, d)[begin:end].transpose(0, 1),
+                              blocked_v.view(-1, h_kv, dv)[begin:end].transpose(0, 1), h_q=h_q, h_kv=h_kv, is_causal=causal)
+                o_ref[i] = O.transpose(0, 1)
+                lse_ref[i] = LSE
+            q_nope = q[..., :dv]
+            q_scale = q_nope.float().abs().amax(dim=-1, keepdim=True) / 448.0
+            q_rope = (q[..., dv:].float() / q_scale).to(q.dtype)
+            q_nope_fp8 = (q_nope.float() / q_scale).to(torch.float8_e4m3fn)
+            k_lora = blocked_k[..., :dv]
+            k_scale = k_lora.float().abs().amax(dim=-1, keepdim=True) / 448.0
+            k_rope = (blocked_k[..., dv:].float() / k_scale).to(q.dtype)
+            k_lora_fp8 = (k_lora.float() / k_scale).to(torch.float8_e4m3fn)
+            # bf16 tensors are stored as their bit patterns (uint16) to keep the fixture small
+            for name, t in (("q_bf16bits", q.view(torch.int16)), ("blocked_k_bf16bits", blocked_k.view(torch.int16)),
+                            ("cache_seqlens", cache_seqlens),
+                            ("block_table", block_table), ("out", o_ref), ("lse", lse_ref),
+                            # of the test-side quantisation only the scales are stored (the e4m3 / bf16 tensors follow from
+                            # them by the three lines at :94-101, which the consuming test restates); a checksum pins the codes
+                            ("q_scale", q_scale), ("k_scale", k_scale),
+                            ("q_nope_fp8_sum", q_nope_fp8.view(torch.uint8).long().sum()),
+                            ("k_lora_fp8_sum", k_lora_fp8.view(torch.uint8).long().sum())):
+                out["%s_%s" % (tag, name)] = t.numpy()
+            out["%s_causal" % tag] = np.array(causal)
+    finally:
+        torch.set_default_dtype(old_dtype)
+    np.savez_compressed(os.path.join(HERE, "mla_test_reference.npz"), **out)
+
+
 def make_rope():
     """Rotary embedding of the MLA rope dims through the reference's own classes on CPU
     (python/sglang/srt/layers/rotary_embedding.py: DeepseekScalingRotaryEmbedding.forward_native :804-846 with the
@@ -135,9 +206,10 @@ def make_rope():
 def main():
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, os.path.join(REF, "python"))
-    if sys.argv[1:] and set(sys.argv[1:]) <= {"rope", "pool_disagg"}:  # regenerate only these fixtures
+    only = {"rope": make_rope, "pool_disagg": make_pool_disagg, "mla_test_reference": make_mla_test_reference}
+    if sys.argv[1:] and set(sys.argv[1:]) <= set(only):  # regenerate only these fixtures
         for name in sys.argv[1:]:
-            {"rope": make_rope, "pool_disagg": make_pool_disagg}[name]()
+            only[name]()
         return
     torch.manual_seed(0)
 
@@ -215,6 +287,7 @@ def main():
                         c=c.numpy(), xq_cast=xq2.view(torch.uint8).numpy(), xs_cast=xs2.numpy())
     make_rope()
     make_pool_disagg()
+    make_mla_test_reference()
     print("golden fixtures written to", HERE)
 
 
