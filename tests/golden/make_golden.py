@@ -15,6 +15,8 @@ What can be pinned this way:
     (`python tests/golden/make_golden.py rope` regenerates only this one);
   * the reference's own attention test up to the kernel call: inputs, test-side quantisation and the fp32 `ref_mla`
     outputs its kernel is compared with (3rdparty/flashmla-fp8/tests/test_flash_mla_ckv_fp8_per_token.py:12-101);
+  * the reference's own quantiser test up to the kernel calls: generator, torch reference outputs
+    (3rdparty/flashmla-fp8/tests/test_cache_kernels.py:11-103);
   * MLATokenToKVPool.get_contiguous_buf_infos / get_layerwise_buf_info_offsets / move_kv_cache
     (mem_cache/memory_pool.py:747-806), both pool layouts.
 The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
@@ -178,6 +180,40 @@ def make_mla_test_reference():
     np.savez_compressed(os.path.join(HERE, "mla_test_reference.npz"), **out)
 
 
+def make_cache_kernel_test_reference():
+    """The reference's own quantiser test re-run on CPU up to the kernel calls
+    (3rdparty/flashmla-fp8/tests/test_cache_kernels.py): its input generator (:11-57, extracted by AST; rows with
+    different ranges and offsets) and its torch reference `ref_quant_and_cache` (:88-103).  The reference demands
+    relative_L1 < 1e-3 between these and its CUDA quantisers for all six outputs (:59-67, :141-146)."""
+    path = os.path.join(REF, "3rdparty/flashmla-fp8/tests/test_cache_kernels.py")
+    (gen,) = extract_functions(path, ["generate_random_tensor_with_varying_ranges"])
+    old_dtype = torch.get_default_dtype()
+    torch.set_default_dtype(torch.bfloat16)   # main(torch.bfloat16), :153-158
+    try:
+        b, s_q, h_q, d, dv = 4, 2, 16, 576, 512
+        block_num = b * s_q * 4
+        query = gen(num_vectors=b * s_q * h_q, vector_length=d).reshape(b, s_q, h_q, d)
+        key = gen(num_vectors=b * s_q, vector_length=d).reshape(b, s_q, 1, d)
+        assert query.dtype == torch.bfloat16
+        loc = torch.randperm(block_num * 64, dtype=torch.int32)[: b * s_q]
+        q_nope, q_rope = query[..., :dv].clone(), query[..., dv:].clone()
+        q_scale = q_nope.float().abs().amax(dim=-1, keepdim=True) / 448.0
+        q_nope = (q_nope.float() / q_scale).to(torch.float8_e4m3fn).view(torch.uint8)
+        q_rope = (q_rope.float() / q_scale).to(query.dtype)
+        k_lora, k_rope = key[..., :dv], key[..., dv:]
+        k_scale = k_lora.float().abs().amax(dim=-1, keepdim=True) / 448.0
+        k_lora = (k_lora.float() / k_scale).to(torch.float8_e4m3fn).view(torch.uint8)
+        k_rope = (k_rope.float() / k_scale).to(query.dtype)
+        np.savez_compressed(
+            os.path.join(HERE, "cache_kernel_test_reference.npz"),
+            query_bf16bits=query.view(torch.int16).numpy(), key_bf16bits=key.view(torch.int16).numpy(), loc=loc.numpy(),
+            q_nope=q_nope.numpy(), q_scale=q_scale.float().numpy(), q_rope=q_rope.float().numpy(),
+            k_lora=k_lora.reshape(-1, 1, dv).numpy(), k_scale=k_scale.float().reshape(-1, 1, 1).numpy(),
+            k_rope=k_rope.float().reshape(-1, 1, d - dv).numpy(), num_slots=np.array(block_num * 64))
+    finally:
+        torch.set_default_dtype(old_dtype)
+
+
 def make_rope():
     """Rotary embedding of the MLA rope dims through the reference's own classes on CPU
     (python/sglang/srt/layers/rotary_embedding.py: DeepseekScalingRotaryEmbedding.forward_native :804-846 with the
@@ -206,7 +242,8 @@ def make_rope():
 def main():
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, os.path.join(REF, "python"))
-    only = {"rope": make_rope, "pool_disagg": make_pool_disagg, "mla_test_reference": make_mla_test_reference}
+    only = {"rope": make_rope, "pool_disagg": make_pool_disagg, "mla_test_reference": make_mla_test_reference,
+            "cache_kernel_test_reference": make_cache_kernel_test_reference}
     if sys.argv[1:] and set(sys.argv[1:]) <= set(only):  # regenerate only these fixtures
         for name in sys.argv[1:]:
             only[name]()
@@ -288,6 +325,7 @@ def main():
     make_rope()
     make_pool_disagg()
     make_mla_test_reference()
+    make_cache_kernel_test_reference()
     print("golden fixtures written to", HERE)
 
 

@@ -273,3 +273,45 @@ def test_attention_oracles_pass_the_references_own_test(golden_dir):
         fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=causal)
         assert rel_l1(fo, want_o) < 5e-2 and rel_l1(fl, want_lse) < 5e-2
         assert not np.isnan(fo).any()
+
+
+def test_quantiser_oracles_against_the_references_own_test(golden_dir):
+    """3rdparty/flashmla-fp8/tests/test_cache_kernels.py compares the CUDA quantisers with a torch reference on rows of
+    varying range and offset (relative_L1 < 1e-3, :59-67, :88-146).  The fixture holds that test's inputs and torch
+    reference outputs, produced by its own generator on CPU.  The restatements the CUDA kernels are bit-exact with
+    (oracle/mla.py) give identical scales, identical rope values and identical cached-key scales/rope; the e4m3 codes
+    differ from the torch reference on < 0.1 % of the elements, by one code, and only where x / scale sits on a rounding
+    midpoint: the torch reference divides by the scale (:91-92), the CUDA kernel multiplies by a rounded reciprocal
+    (csrc/kernels/ckv_fp8_per_token/cache_kernels.cu:79,84), so exact ties (common with bf16 inputs) break differently.
+    That alone is relative_L1 = 2.5e-3 on this sample -- the reference kernel's own arithmetic does not meet the test's
+    1e-3 on it either; stated here instead of hidden."""
+    torch = pytest.importorskip("torch")
+    g = _load(golden_dir, "cache_kernel_test_reference.npz")
+
+    def rel_l1(x, y):
+        x, y = np.asarray(x, np.float64), np.asarray(y, np.float64)
+        return float(np.linalg.norm(x - y) / np.linalg.norm(y))
+
+    def check_codes(codes, want, x, scale):
+        got_v, want_v = ofp8.e4m3_to_f32(codes).astype(np.float64), ofp8.e4m3_to_f32(want).astype(np.float64)
+        diff = codes != want
+        assert diff.mean() < 1e-3 and rel_l1(got_v, want_v) < 5e-3
+        # every differing element: adjacent codes, and the exact quotient lies (to fp32 resolution) on their midpoint
+        exact = (x.astype(np.float64) / scale.astype(np.float64))[diff]
+        mid = (got_v[diff] + want_v[diff]) / 2
+        assert np.all(np.abs(codes[diff].astype(np.int16) - want[diff].astype(np.int16)) == 1)
+        assert np.all(np.abs(exact - mid) <= np.abs(mid) * 2.0 ** -22)
+
+    query = torch.from_numpy(g["query_bf16bits"]).view(torch.bfloat16).float().numpy()
+    key = torch.from_numpy(g["key_bf16bits"]).view(torch.bfloat16).float().numpy()
+    codes, scale, rope = omla.quantize_ckv_per_token_head(query)
+    assert np.array_equal(scale, g["q_scale"]) and np.array_equal(rope, g["q_rope"])
+    check_codes(codes, g["q_nope"], query[..., :512], scale)
+    slots, loc = int(g["num_slots"]), g["loc"]
+    kl, ks, kr = np.zeros((slots, 1, 512), np.uint8), np.zeros((slots, 1, 1), np.float32), np.zeros((slots, 1, 64), np.float32)
+    omla.quantize_and_cache_k(key.reshape(-1, 1, 576), kl, ks, kr, loc)
+    assert rel_l1(ks[loc], g["k_scale"]) < 1e-3 and rel_l1(kr[loc], g["k_rope"]) < 1e-3
+    check_codes(kl[loc], g["k_lora"], key.reshape(-1, 1, 576)[..., :512], ks[loc])
+    untouched = np.ones(slots, bool)
+    untouched[loc] = False
+    assert not kl[untouched].any() and not ks[untouched].any()   # only the addressed slots are written
