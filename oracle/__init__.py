@@ -18,9 +18,12 @@ Pinning status (see DESIGN.md "Oracle pinning"):
   * the attention restatements (bf16, semantic FP8, page-wise faithful FP8) pass the
     reference's own kernel test -- its inputs, its fp32 ref_mla outputs and its
     relative_L1 < 5e-2 criterion (tests/golden/mla_test_reference.npz).
-  * the per-token-FP8 MLA decode kernel and the metadata scheduler exist in the
-    reference only as sm_90a CUDA (wgmma) that cannot execute on this box; their
-    restatements are pinned only through the semantic (dequantise -> fp32
-    attention) flavour and the reference's own 5e-2 test criterion:
-    PARITY UNPINNED for the bit-level behaviour of those two.
+  * the metadata scheduler and the three quantiser kernels are pinned BIT FOR BIT by
+    the reference's own CUDA sources compiled for the host and run on CPU threads
+    (oracle/ref_build/ -> oracle/_ref/libflashmla_ref_cpu.so, oracle/ref_cpu.py;
+    fixture tests/golden/ref_kernels_cpu.npz).
+  * the per-token-FP8 MLA decode kernel exists in the reference only as sm_90a CUDA
+    (wgmma / TMA / CuTe) that can neither execute on this box nor be compiled for the
+    host: PARITY UNPINNED for its bit-level behaviour; its restatements are pinned at
+    the reference's own test criterion (above).
 """

@@ -19,7 +19,9 @@ What can be pinned this way:
     (3rdparty/flashmla-fp8/tests/test_cache_kernels.py:11-103);
   * MLATokenToKVPool.get_contiguous_buf_infos / get_layerwise_buf_info_offsets / move_kv_cache
     (mem_cache/memory_pool.py:747-806), both pool layouts.
-The sm_90a CUDA kernels (attention, metadata, CUDA quantisers) cannot run here: no fixture for them.
+  * the reference's metadata / quantiser / de-quantiser CUDA kernels themselves, compiled for the host from their sources
+    and run on CPU threads (oracle/ref_build/build_ref.py -> oracle/_ref/libflashmla_ref_cpu.so): ref_kernels_cpu.npz.
+The sm_90a attention kernel (wgmma, TMA, CuTe) cannot run here: no fixture of its own outputs.
 """
 import ast
 import importlib.abc
@@ -214,6 +216,44 @@ def make_cache_kernel_test_reference():
         torch.set_default_dtype(old_dtype)
 
 
+def make_ref_kernels_cpu():
+    """Outputs of the reference's own metadata / quantiser / de-quantiser kernels, compiled for the host from their
+    sources by oracle/ref_build/build_ref.py and executed on CPU threads (oracle/ref_cpu.py).  The fixture lets the
+    bit-exact pin run where oracle/_ref is absent."""
+    sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+    from oracle.ref_build import build_ref
+    build_ref.build(REF)
+    from oracle import ref_cpu
+    rng = np.random.default_rng(2024)
+    out = {}
+    cases = [(148, 16, 1), (148, 16, 128), (148, 128, 128), (148, 64, 37), (132, 64, 200), (74, 128, 5), (8, 16, 3)]
+    for i, (sm, hpk, b) in enumerate(cases):
+        seqlens = rng.integers(1, 9000, size=b).astype(np.int32) if i % 2 else np.full(b, 4096, np.int32)
+        meta, ns = ref_cpu.get_mla_metadata(seqlens, hpk, 1, sm)
+        out["meta_case_%d" % i] = np.array([sm, hpk, b])
+        out["meta_seqlens_%d" % i], out["meta_out_%d" % i], out["meta_num_splits_%d" % i] = seqlens, meta, ns
+    out["meta_cases"] = np.array(len(cases))
+    f32 = (rng.standard_normal((48, 4, 576)) * rng.uniform(0.001, 40, (48, 4, 1))).astype(np.float32)
+    f32[3] = 0                       # all-zero rows: scale = 1e-12
+    f32[4, 0, :512] = 7.0            # constant row: every element on the e4m3 maximum
+    q_bits = torch.from_numpy(f32).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    out["q_bits"] = q_bits
+    out["q_nope"], out["q_scale"], out["q_rope_bits"] = ref_cpu.quantize_ckv_per_token_head(q_bits)
+    slots, n = 64 * 5, 40
+    key = (rng.standard_normal((n, 1, 576)) * rng.uniform(0.001, 40, (n, 1, 1))).astype(np.float32)
+    k_bits = torch.from_numpy(key).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    loc = rng.permutation(slots)[:n].astype(np.int32)
+    kl, ks, kr = ref_cpu.pool_arrays(slots)
+    ref_cpu.quantize_and_cache_k(k_bits, kl, ks, kr, loc)
+    idx = rng.choice(loc, size=29).astype(np.int32)
+    lo, ro = ref_cpu.dequantize_ckv_fused_indexed(kl, kr, ks, idx)
+    lo2, ro2 = ref_cpu.dequantize_ckv_fused_indexed(kl, kr, ks, idx, max_num_tokens=6)
+    assert np.array_equal(lo, lo2) and np.array_equal(ro, ro2)
+    out.update(k_bits=k_bits, k_loc=loc, k_slots=np.array(slots), k_lora=kl.copy(), k_scale=ks.copy(), k_rope_bits=kr.copy(),
+               deq_idx=idx, deq_lora_bits=lo, deq_rope_bits=ro)
+    np.savez_compressed(os.path.join(HERE, "ref_kernels_cpu.npz"), **out)
+
+
 def make_rope():
     """Rotary embedding of the MLA rope dims through the reference's own classes on CPU
     (python/sglang/srt/layers/rotary_embedding.py: DeepseekScalingRotaryEmbedding.forward_native :804-846 with the
@@ -243,7 +283,7 @@ def main():
     sys.meta_path.insert(0, _Finder())
     sys.path.insert(0, os.path.join(REF, "python"))
     only = {"rope": make_rope, "pool_disagg": make_pool_disagg, "mla_test_reference": make_mla_test_reference,
-            "cache_kernel_test_reference": make_cache_kernel_test_reference}
+            "cache_kernel_test_reference": make_cache_kernel_test_reference, "ref_kernels_cpu": make_ref_kernels_cpu}
     if sys.argv[1:] and set(sys.argv[1:]) <= set(only):  # regenerate only these fixtures
         for name in sys.argv[1:]:
             only[name]()
@@ -326,6 +366,7 @@ def main():
     make_pool_disagg()
     make_mla_test_reference()
     make_cache_kernel_test_reference()
+    make_ref_kernels_cpu()
     print("golden fixtures written to", HERE)
 
 

@@ -315,3 +315,54 @@ def test_quantiser_oracles_against_the_references_own_test(golden_dir):
     untouched = np.ones(slots, bool)
     untouched[loc] = False
     assert not kl[untouched].any() and not ks[untouched].any()   # only the addressed slots are written
+
+
+def test_oracle_bit_exact_vs_reference_kernels_fixture(golden_dir):
+    """The restatements the CUDA kernels are checked against (oracle/mla.py: get_mla_metadata, quantize_ckv_per_token_head,
+    quantize_and_cache_k, dequantize_ckv_fused_indexed) against the outputs of the reference's OWN kernel sources
+    (3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu, ckv_fp8_per_token/cache_kernels.cu) compiled for the host
+    and executed on CPU (oracle/ref_build/): every int32, e4m3 code, fp32 scale bit and bf16 bit identical."""
+    g = _load(golden_dir, "ref_kernels_cpu.npz")
+    for i in range(int(g["meta_cases"])):
+        sm, hpk, b = (int(v) for v in g["meta_case_%d" % i])
+        meta, ns = omla.get_mla_metadata(g["meta_seqlens_%d" % i], hpk, 1, sm)
+        want = g["meta_out_%d" % i]
+        assert meta.shape == want.shape
+        assert np.array_equal(meta[:, :5], want[:, :5])          # columns 5-7 are never written by the reference kernel
+        assert np.array_equal(ns, g["meta_num_splits_%d" % i])
+    bits = lambda a: ofp8.f32_to_bf16_bits(a)
+    q = ofp8.bf16_bits_to_f32(g["q_bits"])
+    codes, scale, rope = omla.quantize_ckv_per_token_head(q)
+    assert np.array_equal(codes, g["q_nope"]) and np.array_equal(scale.view(np.uint32), g["q_scale"].view(np.uint32))
+    assert np.array_equal(bits(rope), g["q_rope_bits"])
+    slots = int(g["k_slots"])
+    kl, ks, kr = np.zeros((slots, 1, 512), np.uint8), np.zeros((slots, 1, 1), np.float32), np.zeros((slots, 1, 64), np.float32)
+    omla.quantize_and_cache_k(ofp8.bf16_bits_to_f32(g["k_bits"]), kl, ks, kr, g["k_loc"])
+    assert np.array_equal(kl, g["k_lora"]) and np.array_equal(ks.view(np.uint32), g["k_scale"].view(np.uint32))
+    assert np.array_equal(bits(kr), g["k_rope_bits"])
+    dl, dr = omla.dequantize_ckv_fused_indexed(kl, kr, ks, g["deq_idx"])
+    assert np.array_equal(bits(dl), g["deq_lora_bits"]) and np.array_equal(bits(dr), g["deq_rope_bits"])
+
+
+def test_oracle_bit_exact_vs_reference_kernels_live():
+    """Same pin, live: random sweeps against oracle/_ref/libflashmla_ref_cpu.so when it has been built (it is built by
+    __graft_entry__.build() wherever /root/reference exists, and travels to the GPU box)."""
+    from oracle import ref_cpu
+    if not ref_cpu.available():
+        pytest.skip("oracle/_ref not built (no reference tree on this machine)")
+    rng = np.random.default_rng(7)
+    for sm, hpk in ((148, 16), (148, 128), (148, 256), (132, 64), (8, 16)):
+        for b in (1, 2, 37, 128, 300):
+            seqlens = rng.integers(1, 20000, size=b).astype(np.int32)
+            if b == 2:
+                seqlens[:] = 1
+            want, want_ns = ref_cpu.get_mla_metadata(seqlens, hpk, 1, sm)
+            meta, ns = omla.get_mla_metadata(seqlens, hpk, 1, sm)
+            assert np.array_equal(meta[:, :5], want[:, :5]) and np.array_equal(ns, want_ns), (sm, hpk, b)
+    x = (rng.standard_normal((96, 2, 576)) * rng.uniform(1e-4, 60, (96, 2, 1))).astype(np.float32)
+    x[0] = 0
+    xb = ofp8.f32_to_bf16_bits(x)
+    c, sc, r = ref_cpu.quantize_ckv_per_token_head(xb)
+    oc, osc, orr = omla.quantize_ckv_per_token_head(ofp8.bf16_bits_to_f32(xb))
+    assert np.array_equal(c, oc) and np.array_equal(sc.view(np.uint32), osc.view(np.uint32))
+    assert np.array_equal(r, ofp8.f32_to_bf16_bits(orr))
