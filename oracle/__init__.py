@@ -18,7 +18,8 @@ Pinning status (see DESIGN.md "Oracle pinning"):
   * the attention restatements (bf16, semantic FP8, page-wise faithful FP8) pass the
     reference's own kernel test -- its inputs, its fp32 ref_mla outputs and its
     relative_L1 < 5e-2 criterion (tests/golden/mla_test_reference.npz).
-  * the metadata scheduler and the three quantiser kernels are pinned BIT FOR BIT by
+  * the metadata scheduler, the three KV/q quantiser kernels and the 1x128 activation
+    quantiser kernel are pinned BIT FOR BIT by
     the reference's own CUDA sources compiled for the host and run on CPU threads
     (oracle/ref_build/ -> oracle/_ref/libflashmla_ref_cpu.so, oracle/ref_cpu.py;
     fixture tests/golden/ref_kernels_cpu.npz).

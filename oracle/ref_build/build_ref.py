@@ -7,6 +7,7 @@ compiler.
   3rdparty/flashmla-fp8/csrc/kernels/ckv_fp8_per_token/cache_kernels.cu  quantize_single_kernel           (a-6)
                                                                           quant_and_save_cache_k_kernel    (a-7)
                                                                           dequantize_fused_indexed_kernel  (a-8)
+  3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu                       per_token_group_quant_8bit_kernel (G-2)
 
 The `__global__` functions are compiled unmodified by g++ against shim/ref_shim.h (threads, warp shuffles and barriers
 on std::thread; NVIDIA's host implementations of bf16 / e4m3 from the CUDA toolkit headers).  The one thing the stream
@@ -36,7 +37,7 @@ def strip_host_launchers(text: str) -> str:
                 i += 1
             i += 1
             continue
-        if re.match(r"void (invoke_|run_)\w+\(", ln):      # a launcher: drop it up to its closing brace
+        if re.match(r"void (invoke_|run_|sgl_)\w+\(", ln):  # a launcher: drop it up to its closing brace
             if out and out[-1].startswith("template <typename T>"):
                 out.pop()
             while lines[i] != "}":
@@ -52,9 +53,11 @@ def strip_host_launchers(text: str) -> str:
 
 def build(ref_root: str = "/root/reference", force: bool = False) -> str:
     kdir = os.path.join(ref_root, KERNELS)
-    srcs = [os.path.join(kdir, "get_mla_metadata.cu"), os.path.join(kdir, "ckv_fp8_per_token", "cache_kernels.cu")]
-    mine = [os.path.join(HERE, "driver.cpp"), os.path.join(HERE, "shim", "ref_shim.h"), os.path.join(HERE, "shim", "utils.h"),
-            os.path.join(HERE, "shim", "cutlass", "fast_math.h"), os.path.abspath(__file__)]
+    srcs = [os.path.join(kdir, "get_mla_metadata.cu"), os.path.join(kdir, "ckv_fp8_per_token", "cache_kernels.cu"),
+            os.path.join(ref_root, "3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu")]
+    mine = [os.path.join(HERE, "driver.cpp"), os.path.abspath(__file__)]
+    for dirpath, _, files in os.walk(os.path.join(HERE, "shim")):
+        mine += [os.path.join(dirpath, f) for f in files]
     for s in srcs:
         if not os.path.exists(s):
             raise FileNotFoundError(s)
@@ -68,6 +71,9 @@ def build(ref_root: str = "/root/reference", force: bool = False) -> str:
         # cache_kernels.cu: `__shared__ int cache_idx` is one variable per block
         "#undef __shared__", "#define __shared__ static",
         '#line 1 "%s"' % srcs[1], strip_host_launchers(open(srcs[1]).read()),
+        # sgl_fp8_quantization.cu: its one shared array is declared `static __shared__`
+        "#undef __shared__", "#define __shared__",
+        '#line 1 "%s"' % srcs[2], strip_host_launchers(open(srcs[2]).read()),
         '#include "%s"' % os.path.join(HERE, "driver.cpp"), ""])
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-x", "c++", "-",

@@ -3,6 +3,7 @@
 //   get_mla_metadata.cu:82-86  <<<1, 32, (2 * batch + 1) ints>>>
 //   cache_kernels.cu:111-121, 235-249  4 warps per block, one row per warp
 //   cache_kernels.cu:388-423  4 warps per block, one query per block (queries_per_block when the grid is capped)
+//   sgl_fp8_quantization.cu:452-491  16 threads per 128-element group, up to 16 groups per block
 thread_local refshim::Block* refshim::cur = nullptr;
 thread_local refshim::Idx threadIdx, blockIdx, blockDim, gridDim;
 
@@ -19,6 +20,9 @@ void refshim::run_grid(unsigned grid_x, unsigned block_x, const std::function<vo
         blockDim.x = block_x;
         gridDim.x = grid_x;
         kernel();
+        // a thread that has left the kernel no longer takes part in barriers (half-warp groups may leave early)
+        blk.warp_bar[t / 32]->arrive_and_drop();
+        blk.block_bar.arrive_and_drop();
       });
     for (auto& th : ts) th.join();
   }
@@ -86,6 +90,24 @@ int ref_dequantize_fused_indexed(const uint8_t* k_lora, const uint16_t* k_rope_b
                                                    reinterpret_cast<__nv_bfloat16*>(lora_out_bf16),
                                                    reinterpret_cast<__nv_bfloat16*>(rope_out_bf16), num_queries,
                                                    lora_stride, scale_stride, rope_stride, 512, 64, queries_per_block);
+  });
+  return 0;
+}
+
+int ref_per_token_group_quant_fp8(const uint16_t* x_bf16, int64_t m, int64_t k, uint8_t* q, float* scales,
+                                  int64_t scale_stride, float eps) {
+  // sgl_fp8_quantization.cu:452-491 (group 128, column-major float scales)
+  const int group_size = 128;
+  const int64_t num_groups = m * k / group_size;
+  int groups_per_block = 1;
+  if (num_groups % 16 == 0) groups_per_block = 16;
+  else if (num_groups % 8 == 0) groups_per_block = 8;
+  else if (num_groups % 4 == 0) groups_per_block = 4;
+  else if (num_groups % 2 == 0) groups_per_block = 2;
+  refshim::run_grid((unsigned)(num_groups / groups_per_block), (unsigned)(groups_per_block * 16), [&] {
+    per_token_group_quant_8bit_kernel<__nv_bfloat16, __nv_fp8_e4m3, true, false>(
+        reinterpret_cast<const __nv_bfloat16*>(x_bf16), q, scales, group_size, (int)num_groups, groups_per_block, eps,
+        -448.0f, 448.0f, (int)(k / group_size), (int)scale_stride);
   });
   return 0;
 }

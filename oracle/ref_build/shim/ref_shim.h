@@ -80,5 +80,12 @@ inline void __syncthreads() { refshim::cur->block_bar.arrive_and_wait(); }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+// bit casts and the two atomics the (uninstantiated-here) per-tensor kernels of sgl_fp8_quantization.cu name
+inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }
+inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); return f; }
+inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
+template <class T> inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }  // blocks run one at a time;
+template <class T> inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }  // not used by the built kernels
 using std::max;
 using std::min;

@@ -86,3 +86,16 @@ def dequantize_ckv_fused_indexed(k_lora, k_rope_bits, k_scale, indices, max_num_
     assert lib().ref_dequantize_fused_indexed(_p(k_lora), _p(k_rope_bits), _p(k_scale), _p(idx), _p(lo), _p(ro), n,
                                               int(max_num_tokens), 512, 1, 64) == 0
     return lo.copy(), ro.copy()
+
+
+def per_token_group_quant_fp8(x_bf16_bits, eps=1e-10):
+    """3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-437 (group 128, column-major TMA-aligned float scales, the
+    layout deep_geem.py:86-93 asks for) on uint16 bf16 bits [m, k] -> (codes u8 [m, k], scales f32 [m, k/128])."""
+    x = _aligned(np.shape(x_bf16_bits), np.uint16)
+    x[...] = x_bf16_bits
+    m, k = x.shape
+    stride = (m + 3) // 4 * 4
+    q = _aligned((m, k), np.uint8)
+    sc = np.zeros((k // 128, stride), np.float32)
+    assert lib().ref_per_token_group_quant_fp8(_p(x), m, k, _p(q), _p(sc), stride, ctypes.c_float(eps)) == 0
+    return q.copy(), sc[:, :m].T.copy()

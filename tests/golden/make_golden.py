@@ -217,7 +217,7 @@ def make_cache_kernel_test_reference():
 
 
 def make_ref_kernels_cpu():
-    """Outputs of the reference's own metadata / quantiser / de-quantiser kernels, compiled for the host from their
+    """Outputs of the reference's own metadata / quantiser / de-quantiser / activation-quantiser kernels, compiled for the host from their
     sources by oracle/ref_build/build_ref.py and executed on CPU threads (oracle/ref_cpu.py).  The fixture lets the
     bit-exact pin run where oracle/_ref is absent."""
     sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
@@ -251,6 +251,12 @@ def make_ref_kernels_cpu():
     assert np.array_equal(lo, lo2) and np.array_equal(ro, ro2)
     out.update(k_bits=k_bits, k_loc=loc, k_slots=np.array(slots), k_lora=kl.copy(), k_scale=ks.copy(), k_rope_bits=kr.copy(),
                deq_idx=idx, deq_lora_bits=lo, deq_rope_bits=ro)
+    # G-2: the 1x128 activation quantiser kernel (3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-437)
+    xa = (rng.standard_normal((37, 1536)) * rng.uniform(0.001, 50, (37, 1))).astype(np.float32)
+    xa[0, :128] = 0                 # an all-zero group: scale = eps / 448
+    a_bits = torch.from_numpy(xa).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
+    aq, a_s = ref_cpu.per_token_group_quant_fp8(a_bits)
+    out.update(act_bits=a_bits, act_q=aq, act_scales=a_s)
     np.savez_compressed(os.path.join(HERE, "ref_kernels_cpu.npz"), **out)
 
 

@@ -320,8 +320,9 @@ def test_quantiser_oracles_against_the_references_own_test(golden_dir):
 def test_oracle_bit_exact_vs_reference_kernels_fixture(golden_dir):
     """The restatements the CUDA kernels are checked against (oracle/mla.py: get_mla_metadata, quantize_ckv_per_token_head,
     quantize_and_cache_k, dequantize_ckv_fused_indexed) against the outputs of the reference's OWN kernel sources
-    (3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu, ckv_fp8_per_token/cache_kernels.cu) compiled for the host
-    and executed on CPU (oracle/ref_build/): every int32, e4m3 code, fp32 scale bit and bf16 bit identical."""
+    (3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu, ckv_fp8_per_token/cache_kernels.cu,
+    3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu) compiled for the host and executed on CPU (oracle/ref_build/):
+    every int32, e4m3 code, fp32 scale bit and bf16 bit identical."""
     g = _load(golden_dir, "ref_kernels_cpu.npz")
     for i in range(int(g["meta_cases"])):
         sm, hpk, b = (int(v) for v in g["meta_case_%d" % i])
@@ -342,6 +343,9 @@ def test_oracle_bit_exact_vs_reference_kernels_fixture(golden_dir):
     assert np.array_equal(bits(kr), g["k_rope_bits"])
     dl, dr = omla.dequantize_ckv_fused_indexed(kl, kr, ks, g["deq_idx"])
     assert np.array_equal(bits(dl), g["deq_lora_bits"]) and np.array_equal(bits(dr), g["deq_rope_bits"])
+    # G-2: 1x128 activation quantiser (3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-437)
+    aq, a_s = ogemm.per_token_group_quant_fp8(ofp8.bf16_bits_to_f32(g["act_bits"]))
+    assert np.array_equal(aq, g["act_q"]) and np.array_equal(a_s.view(np.uint32), g["act_scales"].view(np.uint32))
 
 
 def test_oracle_bit_exact_vs_reference_kernels_live():
@@ -366,3 +370,9 @@ def test_oracle_bit_exact_vs_reference_kernels_live():
     oc, osc, orr = omla.quantize_ckv_per_token_head(ofp8.bf16_bits_to_f32(xb))
     assert np.array_equal(c, oc) and np.array_equal(sc.view(np.uint32), osc.view(np.uint32))
     assert np.array_equal(r, ofp8.f32_to_bf16_bits(orr))
+    for m, k in ((1, 128), (5, 512), (37, 1536), (3, 7168)):
+        xa = (rng.standard_normal((m, k)) * rng.uniform(1e-3, 50, (m, 1))).astype(np.float32)
+        ab = ofp8.f32_to_bf16_bits(xa)
+        q_ref, s_ref = ref_cpu.per_token_group_quant_fp8(ab)
+        q_o, s_o = ogemm.per_token_group_quant_fp8(ofp8.bf16_bits_to_f32(ab))
+        assert np.array_equal(q_ref, q_o) and np.array_equal(s_ref.view(np.uint32), s_o.view(np.uint32))
