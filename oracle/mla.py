@@ -222,6 +222,34 @@ def _partial_attention(qn, qr, qs, kn_pages, kr_pages, ks_pages, block_ids, firs
     return O, L, m, p
 
 
+def combine_partials(o_accum, lse_accum, num_splits, out, lse):
+    """a-5, ckv_fp8_per_token/mla_combine.cu:16-154: merge the split-KV partials of every request that has more than one
+    split.  o_accum f32 [splits, M, dv]; lse_accum f32 [splits, M] (log2 domain); num_splits i32 [b + 1]; writes
+    out f32 [b, M, dv] (bf16 values) and lse f32 [b, M] (natural log) in place; single-split requests are untouched (:31-33).
+    Pinned against the reference kernel's source run on CPU (tests/golden/ref_kernels_cpu.npz)."""
+    b, M, dv = out.shape
+    for batch_idx in range(b):
+        s0, s1 = int(num_splits[batch_idx]), int(num_splits[batch_idx + 1])
+        if s1 - s0 == 1:
+            continue                                             # :31-33
+        lse_i = lse_accum[s0:s1]                                 # [n, M] (log2 domain)
+        max_lse = np.max(lse_i, axis=0)
+        max_lse = np.where(np.isneginf(max_lse), np.float32(0.0), max_lse)       # :92
+        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
+            sum_lse = np.sum(_exp2(lse_i - max_lse[None, :]), axis=0, dtype=np.float32)
+            bad = (sum_lse == 0.0) | np.isnan(sum_lse)
+            global_lse = np.where(bad, np.float32(np.inf), np.log2(sum_lse).astype(np.float32) + max_lse)  # :101
+            lse[batch_idx] = (global_lse / LOG2E).astype(np.float32)              # :103
+            w = _exp2(lse_i - global_lse[None, :])                                # :108
+        acc = np.zeros((M, dv), dtype=np.float32)
+        for i in range(s1 - s0):                                                  # :128-137
+            wi = w[i]
+            with np.errstate(invalid="ignore"):
+                contrib = np.where((wi != 0.0)[:, None], wi[:, None] * o_accum[s0 + i], np.float32(0.0))  # :131 skip w==0
+            acc = (acc + contrib).astype(np.float32)
+        out[batch_idx] = round_to_bf16(acc)
+
+
 def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_scale, k_scale,
                                 block_table, cache_seqlens, tile_scheduler_metadata, num_splits,
                                 softmax_scale=None, causal=False, block_m: int = BLOCK_SIZE_M,
@@ -311,26 +339,7 @@ def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_sc
                             (np.log2((L * p).astype(np.float32)) + m).astype(np.float32))          # :1506
 
     # ---- combine (mla_combine.cu:16-154) ----
-    for batch_idx in range(b):
-        s0, s1 = int(num_splits[batch_idx]), int(num_splits[batch_idx + 1])
-        if s1 - s0 == 1:
-            continue                                             # :31-33
-        lse_i = lse_accum[s0:s1]                                 # [n, M] (log2 domain)
-        max_lse = np.max(lse_i, axis=0)
-        max_lse = np.where(np.isneginf(max_lse), np.float32(0.0), max_lse)       # :92
-        with np.errstate(divide="ignore", invalid="ignore", over="ignore"):
-            sum_lse = np.sum(_exp2(lse_i - max_lse[None, :]), axis=0, dtype=np.float32)
-            bad = (sum_lse == 0.0) | np.isnan(sum_lse)
-            global_lse = np.where(bad, np.float32(np.inf), np.log2(sum_lse).astype(np.float32) + max_lse)  # :101
-            lse[batch_idx] = (global_lse / LOG2E).astype(np.float32)              # :103
-            w = _exp2(lse_i - global_lse[None, :])                                # :108
-        acc = np.zeros((M, dv), dtype=np.float32)
-        for i in range(s1 - s0):                                                  # :128-137
-            wi = w[i]
-            with np.errstate(invalid="ignore"):
-                contrib = np.where((wi != 0.0)[:, None], wi[:, None] * o_accum[s0 + i], np.float32(0.0))  # :131 skip w==0
-            acc = (acc + contrib).astype(np.float32)
-        out[batch_idx] = round_to_bf16(acc)
+    combine_partials(o_accum, lse_accum, num_splits, out, lse)
 
     out = out.reshape(b, s_q, h_q, dv)
     lse = lse.reshape(b, s_q, h_q).transpose(0, 2, 1).copy()     # flash_api.cpp:392-394

@@ -51,7 +51,7 @@ struct Block {
   std::vector<uint64_t> xch;
 };
 extern thread_local Block* cur;
-void run_grid(unsigned grid_x, unsigned block_x, const std::function<void()>& kernel);
+void run_grid(unsigned grid_x, unsigned block_x, const std::function<void()>& kernel, unsigned grid_y = 1);
 }  // namespace refshim
 
 extern thread_local refshim::Idx threadIdx, blockIdx, blockDim, gridDim;
@@ -87,5 +87,8 @@ inline float __uint_as_float(unsigned v) { float f; std::memcpy(&f, &v, 4); retu
 inline unsigned __float_as_uint(float f) { unsigned v; std::memcpy(&v, &f, 4); return v; }
 template <class T> inline T atomicMax(T* p, T v) { T o = *p; *p = std::max(o, v); return o; }  // blocks run one at a time;
 template <class T> inline T atomicMin(T* p, T v) { T o = *p; *p = std::min(o, v); return o; }  // not used by the built kernels
+// programmatic dependent launch has no meaning when kernels run one after the other
+#define cudaGridDependencySynchronize() ((void)0)
+#define cudaTriggerProgrammaticLaunchCompletion() ((void)0)
 using std::max;
 using std::min;

@@ -99,3 +99,16 @@ def per_token_group_quant_fp8(x_bf16_bits, eps=1e-10):
     sc = np.zeros((k // 128, stride), np.float32)
     assert lib().ref_per_token_group_quant_fp8(_p(x), m, k, _p(q), _p(sc), stride, ctypes.c_float(eps)) == 0
     return q.copy(), sc[:, :m].T.copy()
+
+
+def mla_combine(o_accum, lse_accum, num_splits, batch, s_q, h_q, num_sm_parts):
+    """ckv_fp8_per_token/mla_combine.cu:16-154 on fp32 partials [splits, M, 512] / [splits, M] (log2 domain).  Returns
+    (out bf16 bits u16 [b, M, 512], lse f32 [b, M]); requests with a single split are left untouched (zeros), :31-33."""
+    M = s_q * h_q
+    oa = np.ascontiguousarray(o_accum, np.float32)
+    la = np.ascontiguousarray(lse_accum, np.float32)
+    ns = np.ascontiguousarray(num_splits, np.int32)
+    out = _aligned((batch, M, 512), np.uint16)
+    lse = np.zeros((batch, M), np.float32)
+    assert lib().ref_mla_combine(_p(oa), _p(la), _p(ns), _p(out), _p(lse), batch, s_q, h_q, num_sm_parts) == 0
+    return out.copy(), lse

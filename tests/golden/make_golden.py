@@ -257,6 +257,16 @@ def make_ref_kernels_cpu():
     a_bits = torch.from_numpy(xa).to(torch.bfloat16).view(torch.int16).numpy().view(np.uint16)
     aq, a_s = ref_cpu.per_token_group_quant_fp8(a_bits)
     out.update(act_bits=a_bits, act_q=aq, act_scales=a_s)
+    # a-5: the split-KV combine kernel (ckv_fp8_per_token/mla_combine.cu:16-154) on fp32 partials in the layout the
+    # attention kernel leaves them in (o_accum [splits, M, 512], lse_accum [splits, M] in the log2 domain)
+    cb, cM, parts = 3, 4, 8
+    c_ns = np.array([0, 2, 3, 8], np.int32)                       # 2, 1 and 5 splits
+    c_oacc = rng.standard_normal((cb + parts, cM, 512)).astype(np.float32)
+    c_lacc = (rng.standard_normal((cb + parts, cM)) * 3 + 5).astype(np.float32)
+    c_lacc[3, 1] = -np.inf                                         # a split that saw no key for this row
+    c_lacc[4:8, 2] = -np.inf                                       # all but one
+    c_out, c_lse = ref_cpu.mla_combine(c_oacc, c_lacc, c_ns, cb, 1, cM, parts)
+    out.update(comb_o_accum=c_oacc, comb_lse_accum=c_lacc, comb_num_splits=c_ns, comb_out_bits=c_out, comb_lse=c_lse)
     np.savez_compressed(os.path.join(HERE, "ref_kernels_cpu.npz"), **out)
 
 

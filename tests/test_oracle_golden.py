@@ -346,6 +346,18 @@ def test_oracle_bit_exact_vs_reference_kernels_fixture(golden_dir):
     # G-2: 1x128 activation quantiser (3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-437)
     aq, a_s = ogemm.per_token_group_quant_fp8(ofp8.bf16_bits_to_f32(g["act_bits"]))
     assert np.array_equal(aq, g["act_q"]) and np.array_equal(a_s.view(np.uint32), g["act_scales"].view(np.uint32))
+    # a-5: split-KV combine (mla_combine.cu:16-154).  exp2f / log2f and the order of the 32-lane sums differ between libm +
+    # butterfly and numpy, so this one is pinned to fp32 rounding, not to the bit: lse within 2 ulp, out within one bf16 ulp
+    # on a handful of elements; -inf partials and single-split requests handled identically.
+    ns = g["comb_num_splits"]
+    b, M = len(ns) - 1, g["comb_lse_accum"].shape[1]
+    out, lse = np.zeros((b, M, 512), np.float32), np.zeros((b, M), np.float32)
+    omla.combine_partials(g["comb_o_accum"], g["comb_lse_accum"], ns, out, lse)
+    want_bits, want_lse = g["comb_out_bits"], g["comb_lse"]
+    assert np.allclose(lse, want_lse, rtol=3e-7, atol=0) and not want_bits[1].any() and not out[1].any()
+    got_bits = bits(out).astype(np.int32)
+    ulp = np.abs(got_bits - want_bits.astype(np.int32))
+    assert ulp.max() <= 1 and (ulp != 0).mean() < 5e-3
 
 
 def test_oracle_bit_exact_vs_reference_kernels_live():
