@@ -4,32 +4,7 @@
 //   cache_kernels.cu:111-121, 235-249  4 warps per block, one row per warp
 //   cache_kernels.cu:388-423  4 warps per block, one query per block (queries_per_block when the grid is capped)
 //   sgl_fp8_quantization.cu:452-491  16 threads per 128-element group, up to 16 groups per block
-thread_local refshim::Block* refshim::cur = nullptr;
-thread_local refshim::Idx threadIdx, blockIdx, blockDim, gridDim;
-
-void refshim::run_grid(unsigned grid_x, unsigned block_x, const std::function<void()>& kernel, unsigned grid_y) {
-  for (unsigned by = 0; by < grid_y; ++by)
-    for (unsigned b = 0; b < grid_x; ++b) {
-      Block blk((int)block_x);
-      std::vector<std::thread> ts;
-      ts.reserve(block_x);
-      for (unsigned t = 0; t < block_x; ++t)
-        ts.emplace_back([&, t, b, by] {
-          cur = &blk;
-          threadIdx.x = t;
-          blockIdx.x = b;
-          blockIdx.y = by;
-          blockDim.x = block_x;
-          gridDim.x = grid_x;
-          gridDim.y = grid_y;
-          kernel();
-          // a thread that has left the kernel no longer takes part in barriers (warps / half-warp groups leave early)
-          blk.warp_bar[t / 32]->arrive_and_drop();
-          blk.block_bar.arrive_and_drop();
-        });
-      for (auto& th : ts) th.join();
-    }
-}
+#include "shim/ref_shim_impl.inc"
 
 int shared_mem[1 << 20];  // get_mla_metadata_kernel's dynamic shared memory (extern __shared__ int shared_mem[])
 

@@ -80,6 +80,10 @@ inline void __syncthreads() { refshim::cur->block_bar.arrive_and_wait(); }
 template <class T>
 inline T __ldg(const T* p) { return *p; }
 inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
+// IEEE single-precision operations with round-to-nearest (the host build is compiled with -ffp-contract=off)
+inline float __fmul_rn(float a, float b) { return a * b; }
+inline float __fadd_rn(float a, float b) { return a + b; }
+inline float __fdiv_rn(float a, float b) { return a / b; }
 // bit casts and the two atomics the (uninstantiated-here) per-tensor kernels of sgl_fp8_quantization.cu name
 inline float __int_as_float(int v) { float f; std::memcpy(&f, &v, 4); return f; }
 inline int __float_as_int(float f) { int v; std::memcpy(&v, &f, 4); return v; }

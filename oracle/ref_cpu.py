@@ -21,6 +21,17 @@ def lib():
     global _lib
     if _lib is None:
         _lib = ctypes.CDLL(LIB_PATH)
+        P, I, L, F = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_float
+        for name, args in {
+            "ref_get_mla_metadata": [P, I, I, I, I, P, P],
+            "ref_quantize_ckv_per_token_head": [P, I, I, I, P, P, P],
+            "ref_quantize_and_cache_k": [P, P, P, P, P, I, I, I, I, I, I],
+            "ref_dequantize_fused_indexed": [P, P, P, P, P, P, I, I, I, I, I],
+            "ref_per_token_group_quant_fp8": [P, L, L, P, P, L, F],
+            "ref_mla_combine": [P, P, P, P, P, I, I, I, I],
+        }.items():
+            getattr(_lib, name).argtypes = args
+            getattr(_lib, name).restype = I
     return _lib
 
 
@@ -97,7 +108,7 @@ def per_token_group_quant_fp8(x_bf16_bits, eps=1e-10):
     stride = (m + 3) // 4 * 4
     q = _aligned((m, k), np.uint8)
     sc = np.zeros((k // 128, stride), np.float32)
-    assert lib().ref_per_token_group_quant_fp8(_p(x), m, k, _p(q), _p(sc), stride, ctypes.c_float(eps)) == 0
+    assert lib().ref_per_token_group_quant_fp8(_p(x), m, k, _p(q), _p(sc), stride, float(eps)) == 0
     return q.copy(), sc[:, :m].T.copy()
 
 

@@ -331,7 +331,7 @@ __global__ void __launch_bounds__(256)
                            int64_t scale_stride, float eps) {
   // the GEMM behind this kernel is launched with programmatic stream serialization: let its CTAs start their prologue
   // (barrier init, TMEM allocation, descriptor prefetch) now; its griddepcontrol.wait still orders the data
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  pdl_launch_dependents();
   pdl_wait_prior_grid();  // this kernel is itself launched as a programmatic dependent of its producer
   const int64_t g = (int64_t)blockIdx.x * (blockDim.x >> 4) + (threadIdx.x >> 4);
   const int sub = threadIdx.x & 15;
