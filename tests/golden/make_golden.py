@@ -84,9 +84,9 @@ def make_pool_disagg():
     torch.manual_seed(2)
     out = {}
     for qm, dtype in (("per_token_head", torch.float8_e4m3fn), ("none", torch.bfloat16)):
-        pool = MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, dtype=dtype, quant_method=qm, kv_lora_rank=512,
+        pool = MLATokenToKVPool(size=64, model_dtype=torch.bfloat16, dtype=dtype, quant_method=qm, kv_lora_rank=512,
                                 qk_rope_head_dim=64, layer_num=3, device="cpu", enable_memory_saver=False,
-                                max_batch_size=4, max_context_len=256, page_size=64, rank=0, enable_alt_stream=False)
+                                max_batch_size=4, max_context_len=64, page_size=64, rank=0, enable_alt_stream=False)
         ptrs, lens, item_lens = pool.get_contiguous_buf_infos()
         bufs = [t for kv in pool.kv_buffer for t in (kv if isinstance(kv, tuple) else (kv,))]
         order = [[b.data_ptr() for b in bufs].index(p) for p in ptrs]   # which tensor (layer-major flat index) each is
@@ -102,7 +102,7 @@ def make_pool_disagg():
                 kv[1].copy_(torch.rand(kv[1].shape))
                 kv[2].copy_(torch.randn(kv[2].shape).to(torch.bfloat16))
             before = [[t.clone() for t in kv] for kv in pool.kv_buffer]
-            src, tgt = torch.tensor([64, 65, 70, 200]), torch.tensor([130, 131, 64, 319])
+            src, tgt = torch.tensor([64, 65, 70, 100]), torch.tensor([90, 91, 64, 127])
             pool._kv_copy_config = None   # the native path (:748-764); the Triton tiled copy needs a GPU
             pool.move_kv_cache(tgt, src)
             out["move_src"], out["move_tgt"] = src.numpy(), tgt.numpy()

@@ -199,7 +199,7 @@ def test_pool_disagg_descriptors_and_moves_match_reference(golden_dir):
     from sglang_fluentllm_b200 import flashmla_backend as fb
     g = _load(golden_dir, "pool_disagg.npz")
     for qm in ("per_token_head", "none"):
-        pool = fb.MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
+        pool = fb.MLATokenToKVPool(size=64, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
                                    layer_num=3, device="cpu", quant_method=qm)
         ptrs, lens, item_lens = pool.get_contiguous_buf_infos()
         bufs = [t for kv in pool.kv_buffer for t in (kv if isinstance(kv, tuple) else (kv,))]
@@ -211,7 +211,7 @@ def test_pool_disagg_descriptors_and_moves_match_reference(golden_dir):
             assert pool.get_kv_size_bytes() == int(g["size_bytes_" + qm])
         else:
             assert pool.get_kv_size_bytes() == sum(lens)
-    pool = fb.MLATokenToKVPool(size=256, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
+    pool = fb.MLATokenToKVPool(size=64, model_dtype=torch.bfloat16, kv_lora_rank=512, qk_rope_head_dim=64,
                                layer_num=3, device="cpu", quant_method="per_token_head")
     for l, kv in enumerate(pool.kv_buffer):
         kv[0].copy_(torch.from_numpy(g["before_lora_%d" % l]))
