@@ -1,0 +1,53 @@
+"""The redirections of INTEGRATION.md as code: make the reference's own import statements land on the B200 modules.
+
+``install()`` registers the mirrors under the names the reference imports its kernel packages by
+(python/sglang/srt/layers/attention/flashmla_backend.py:14-15 ``flash_mla_fp8`` / ``flash_mla_swap``;
+python/sglang/srt/mem_cache/memory_pool.py:43-45; python/sglang/srt/layers/dense/gemms/fp8/deep_geem.py:6 ``deep_gemm``)
+and must run before ``sglang.srt`` is imported.  ``patch_attention_initializer(module)`` puts the backend classes where
+python/sglang/srt/model_executor/attn_initializer.py:25-29 would have imported the sm_90 ones from.  Nothing here
+touches a GPU; a missing library still fails at the first kernel call (``_lib.lib()``)."""
+from __future__ import annotations
+
+import sys
+from types import ModuleType
+from typing import Dict
+
+_ALIASES = ("flash_mla_fp8", "flash_mla_swap", "deep_gemm")
+_saved: Dict[str, ModuleType] = {}
+
+
+def install(force: bool = False) -> Dict[str, ModuleType]:
+    """Register the mirrors in ``sys.modules``.  An already imported foreign module of the same name is replaced only
+    with ``force=True`` (otherwise a RuntimeError says which one is in the way)."""
+    from . import deep_gemm, flash_mla_fp8
+
+    targets = {"flash_mla_fp8": flash_mla_fp8, "flash_mla_swap": flash_mla_fp8, "deep_gemm": deep_gemm}
+    for name, mod in targets.items():
+        cur = sys.modules.get(name)
+        if cur is not None and cur is not mod:
+            if not force:
+                raise RuntimeError("sglang_fluentllm_b200.install: module %r is already imported from %s" % (
+                    name, getattr(cur, "__file__", "?")))
+            _saved[name] = cur
+        sys.modules[name] = mod
+    return targets
+
+
+def uninstall() -> None:
+    """Undo ``install()`` (tests)."""
+    from . import deep_gemm, flash_mla_fp8
+
+    for name in _ALIASES:
+        if sys.modules.get(name) in (flash_mla_fp8, deep_gemm):
+            del sys.modules[name]
+        if name in _saved:
+            sys.modules[name] = _saved.pop(name)
+
+
+def patch_attention_initializer(attn_initializer: ModuleType) -> None:
+    """``attn_initializer`` = the imported ``sglang.srt.model_executor.attn_initializer``: define the two names its
+    ``--attention-backend flashmla`` branch constructs (:394-395), which the reference only imports on sm_90 (:25-29)."""
+    from .flashmla_backend import FlashMLABackend, FlashMLAMultiStepDecodeBackend
+
+    attn_initializer.FlashMLABackend = FlashMLABackend
+    attn_initializer.FlashMLAMultiStepDecodeBackend = FlashMLAMultiStepDecodeBackend

@@ -122,3 +122,41 @@ def test_fp8_linear_method_weights_and_checks():
         method.apply(layer, x)
     with pytest.raises(NotImplementedError):
         fl.Fp8LinearMethod(fl.Fp8Config())
+
+
+def test_install_redirects_the_references_imports():
+    """INTEGRATION.md section 2 as code: after install() the reference's `import flash_mla_fp8` / `import deep_gemm`
+    resolve to the B200 mirrors; uninstall() restores the interpreter."""
+    import importlib
+    import sys
+    from sglang_fluentllm_b200 import install as inst
+    for name in ("flash_mla_fp8", "flash_mla_swap", "deep_gemm"):
+        assert name not in sys.modules
+    inst.install()
+    try:
+        import deep_gemm as ref_name_dg
+        import flash_mla_fp8 as ref_name_fm
+        assert ref_name_fm is fm and ref_name_dg is dg
+        swap = importlib.import_module("flash_mla_swap")
+        assert swap.flash_mla_with_kvcache is fm.flash_mla_with_kvcache
+        for attr in ("get_mla_metadata", "flash_mla_with_kvcache", "flash_mla_ckv_fp8_per_token",
+                     "quantize_ckv_per_token_head", "dequantize_ckv_fused_indexed", "quantize_and_cache_k"):
+            assert callable(getattr(ref_name_fm, attr))       # flash_mla_fp8/__init__.py:3-10
+        for attr in ("gemm_fp8_fp8_bf16_nt", "m_grouped_gemm_fp8_fp8_bf16_nt_contiguous",
+                     "m_grouped_gemm_fp8_fp8_bf16_nt_masked", "m_grouped_gemm_fp8_fp8_bf16_nt_offset",
+                     "get_col_major_tma_aligned_tensor", "get_m_alignment_for_contiguous_layout"):
+            assert callable(getattr(ref_name_dg, attr))
+        sys.modules["deep_gemm"] = types.ModuleType("deep_gemm")   # a foreign module in the way
+        with pytest.raises(RuntimeError, match="already imported"):
+            inst.install()
+        inst.install(force=True)
+        assert sys.modules["deep_gemm"] is dg
+    finally:
+        inst.uninstall()
+        sys.modules.pop("deep_gemm", None)
+    assert "flash_mla_fp8" not in sys.modules and "flash_mla_swap" not in sys.modules
+    fake = types.ModuleType("attn_initializer")
+    inst.patch_attention_initializer(fake)
+    from sglang_fluentllm_b200 import flashmla_backend as fb
+    assert fake.FlashMLABackend is fb.FlashMLABackend
+    assert fake.FlashMLAMultiStepDecodeBackend is fb.FlashMLAMultiStepDecodeBackend
