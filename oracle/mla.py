@@ -222,13 +222,15 @@ def _partial_attention(qn, qr, qs, kn_pages, kr_pages, ks_pages, block_ids, firs
     return O, L, m, p
 
 
-def combine_partials(o_accum, lse_accum, num_splits, out, lse):
+def combine_partials(o_accum, lse_accum, num_splits, out, lse, only_requests=None):
     """a-5, ckv_fp8_per_token/mla_combine.cu:16-154: merge the split-KV partials of every request that has more than one
     split.  o_accum f32 [splits, M, dv]; lse_accum f32 [splits, M] (log2 domain); num_splits i32 [b + 1]; writes
     out f32 [b, M, dv] (bf16 values) and lse f32 [b, M] (natural log) in place; single-split requests are untouched (:31-33).
     Pinned against the reference kernel's source run on CPU (tests/golden/ref_kernels_cpu.npz)."""
     b, M, dv = out.shape
     for batch_idx in range(b):
+        if only_requests is not None and batch_idx not in only_requests:
+            continue
         s0, s1 = int(num_splits[batch_idx]), int(num_splits[batch_idx + 1])
         if s1 - s0 == 1:
             continue                                             # :31-33
@@ -253,7 +255,7 @@ def combine_partials(o_accum, lse_accum, num_splits, out, lse):
 def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_scale, k_scale,
                                 block_table, cache_seqlens, tile_scheduler_metadata, num_splits,
                                 softmax_scale=None, causal=False, block_m: int = BLOCK_SIZE_M,
-                                return_partials: bool = False):
+                                return_partials: bool = False, only_requests=None):
     """Faithful restatement of ``flash_mla_ckv_fp8_per_token``
     (flash_mla_fp8/flash_mla_interface.py:68-120 -> csrc/flash_api.cpp:216-397 ->
     splitkv_mla.cu:1147-1515 + mla_combine.cu:16-154).
@@ -263,6 +265,8 @@ def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_sc
     [pages,64,1,64]; k_scale f32 [pages,64,1,1]; block_table i32 [b,max_pages];
     cache_seqlens i32 [b]; metadata from get_mla_metadata.
     Returns (out f32 [b,s_q,h,512] holding bf16 values, lse f32 [b,h,s_q]).
+    only_requests: optional set of batch indices to evaluate (full-size tests sample a few requests; the others' rows of
+    the result are meaningless).
     """
     q_nope = np.asarray(q_nope)
     b, s_q, h_q, dv = q_nope.shape
@@ -297,6 +301,8 @@ def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_sc
         if begin_idx >= b:
             continue                                            # splitkv_mla.cu:1226
         for batch_idx in range(begin_idx, end_idx + 1):
+            if only_requests is not None and batch_idx not in only_requests:
+                continue
             n_split_idx = begin_n_split_idx if batch_idx == begin_idx else 0
             seqlen_k = int(cache_seqlens[batch_idx])
             start_block_idx = begin_seqlen // PAGE_BLOCK_SIZE if batch_idx == begin_idx else 0
@@ -339,7 +345,7 @@ def flash_mla_ckv_fp8_per_token(q_nope, q_rope, k_cache_lora, k_cache_rope, q_sc
                             (np.log2((L * p).astype(np.float32)) + m).astype(np.float32))          # :1506
 
     # ---- combine (mla_combine.cu:16-154) ----
-    combine_partials(o_accum, lse_accum, num_splits, out, lse)
+    combine_partials(o_accum, lse_accum, num_splits, out, lse, only_requests)
 
     out = out.reshape(b, s_q, h_q, dv)
     lse = lse.reshape(b, s_q, h_q).transpose(0, 2, 1).copy()     # flash_api.cpp:392-394

@@ -14,8 +14,8 @@ namespace b200 {
 static constexpr int kTileTokens = 128;
 static constexpr int kPage = B200_MLA_PAGE_SIZE;
 static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
-static constexpr float kPMin = 1e-26f;                        // splitkv_mla.cu:18 (MAX_INIT_VAL_P)
-static constexpr float kHeadroom = 16.0f;                     // lazy rescale: a new reference leaves 2^4 of growth before e4m3 saturates
+static constexpr float kLog2Fp8Max = 8.807354922057604f;      // log2(448): a page's largest P' maps to the e4m3 maximum (splitkv_mla.cu:433)
+static constexpr float kRefHeadroom = 4.0f;                   // log2: a moved row reference leaves 2^4 of growth before the next move
 
 struct MlaParams {
   CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;

@@ -19,12 +19,10 @@
 //   Warp roles (1 CTA/SM): warp 0 = TMA producer, warp 1 = UMMA issuer for Q.K^T, warp 2 = UMMA issuer for P.V,
 //   warp 3 idle, warps 4.. = softmax / correction / epilogue (4 TMEM lane quadrants x HB/CPT column slices; one
 //   thread per (KV token, column slice)).
-//   TMEM: S double-buffered (2 x HB columns) + O (4 x HB columns).
+//   TMEM: S double-buffered (2 x HB columns) + O (4 x HB columns).  P.V is issued twice per tile (hi and lo term of P).
 //
-//   Online softmax keeps a per-q-row reference (m_ref, p_scale) in shared memory and only moves it -- and rescales
-//   O in TMEM -- when a tile's P would overflow e4m3 under the current reference ("lazy rescale").  The reference
-//   kernel re-derives p_scale = rowmax(P)/448 for every 64-token page and rescales O each time (splitkv_mla.cu:
-//   420-455); here the row sum L is kept per token-lane in registers and reduced once per request.
+//   Softmax: the reference's page-wise FP8 codes of P under a lazily moved per-row reference (see the comment above
+//   mla_decode_kernel); the row sum L is kept per token-lane in registers and reduced once per request.
 #include <stdlib.h>
 #include <string.h>
 
@@ -43,10 +41,13 @@ template <int HB>
 struct SmemLayout {
   static constexpr int kQBytes = HB * 640;           // 4 nope chunks [HB x 128 B] + rope [HB x 128 B]
   static constexpr int kPBytes = HB * kTileTokens;   // [HB/16 chunks][16 groups][8 tokens][16 q]
+  // P buffers: (hi, lo) pairs.  Two pairs (tile parity) when they fit; HB = 64 has room for one pair, and the softmax
+  // of tile g then writes P once P.V of tile g-1 has retired (its max pass overlaps that P.V).
+  static constexpr int kPPairs = HB == 64 ? 1 : 2;
   static constexpr int kOffKV = 0;
   static constexpr int kOffQ = kStages * kStageBytes;
   static constexpr int kOffP = kOffQ + kQBytes;
-  static constexpr int kOffSmall = kOffP + 2 * kPBytes;
+  static constexpr int kOffSmall = kOffP + kPPairs * 2 * kPBytes;
   static constexpr int kTotal = kOffSmall + 4096;
 };
 
@@ -56,21 +57,30 @@ struct SmallSmem {
   uint64_t s_full[2], p_full[2];
   uint64_t pv_done, o_ready, o_free;
   uint32_t tmem_base;
-  uint32_t trig[3];
-  float f[64];        // q_scale * softmax_scale * log2(e)
-  float mref[64];     // reference max (log2 domain)
-  float ps[64];       // reference P scale
-  float mprime[64];   // mref + log2(ps)
-  float fac[64];      // rescale factor of the last reference move
+  float f[64];          // q_scale * softmax_scale * log2(e)
+  float rfin[64];       // per q row: final reference exponent of the request (epilogue)
+  float inv[64];        // per q row: 1 / L
   float lsum[64];
-  int32_t lim[64];    // per q row: first masked token index
-  float red[4][64];
+  int32_t lim[64];      // per q row: first masked token index
+  float red[2][4][64];  // [tile parity][TMEM lane quadrant][q row]: per-warp column maxima / row-sum partials
 };
 static_assert(sizeof(SmallSmem) <= 4096, "SmallSmem too large");
 
 // HB  = q rows per CTA (UMMA N); CPT = S columns (q rows) each softmax thread owns.
-// The softmax group has 4 * HB/CPT warps: 4 TMEM lane quadrants x HB/CPT column slices, so the per-thread work per
-// tile is CPT elements and every SM sub-partition has HB/CPT warps to hide ALU / MUFU / TMEM-load latency.
+// The softmax group has 4 * HB/CPT warps: 4 TMEM lane quadrants x HB/CPT column slices; one thread per (KV token,
+// column slice).
+//
+// Softmax arithmetic (per q row, per 64-token page -- the reference's granularity, splitkv_mla.cu:391-458):
+//   y_j     = s_j * q_scale * k_scale_j * scale_log2 + log2(k_scale_j)       (log2 of the un-normalised P'_j)
+//   ymax    = max_j y_j over the page                    -> the reference's p_scale * 2^m = 2^ymax / 448
+//   code_j  = e4m3(448 * 2^(y_j - ymax))                 -> the reference's P8 codes (:433-440), the page's top = 448
+//   sum     = sum_j 448 * 2^(y_j - ymax) / k_scale_j     -> the reference's cur_sum / p_scale (:426,434)
+// The reference then rescales O and L by exp2(m_old - m_new) * p_old / p_new every page (:442-455); with O in TMEM that
+// is a 128 KB read-modify-write per page.  Here O and L live under a per-row reference exponent R that only moves when
+// a page's ymax exceeds it (then R = ymax + 4 and O is rescaled once), and the page's weight w = 2^(ymax - R) <= 1
+// multiplies the codes instead: code_j * w as an e4m3 pair hi + lo (two P.V products), 8 significant bits -- the
+// result differs from the page-wise recurrence by ~1e-3 (rounding of w*code, fp32 summation order), not by the 2^-4
+// noise of a different e4m3 grid.
 template <int HB, int CPT>
 __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
   using L = SmemLayout<HB>;
@@ -78,7 +88,8 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
   constexpr uint32_t kColS = 0, kColO = 2 * HB;
   constexpr int kCS = HB / CPT;                 // column slices
   constexpr int kSmThreads = 128 * kCS;         // softmax group size
-  static_assert(CPT == 8 || CPT == 16, "CPT must be 8 or 16");
+  constexpr int kPPairs = L::kPPairs;
+  static_assert(CPT % 8 == 0 && CPT <= 32, "CPT must be 8, 16 or 32");
 
   extern __shared__ uint8_t smem_raw[];
   // round up to 1024 B by pointer arithmetic (an integer round trip would demote every access to generic LD / ST)
@@ -115,7 +126,6 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
     mbar_init(&sm.pv_done, 1);
     mbar_init(&sm.o_ready, 1);
     mbar_init(&sm.o_free, kSmThreads);
-    sm.trig[0] = sm.trig[1] = sm.trig[2] = 0;
     fence_mbar_init();
     tma_prefetch_desc(&p.tm_q_nope);
     tma_prefetch_desc(&p.tm_q_rope);
@@ -242,7 +252,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
       ++seg;
     }
   } else if (warp == 2) {
-    // ============================== UMMA issuer: O^T += V^T . P ==============================
+    // ============================== UMMA issuer: O^T += V^T . (P_hi + P_lo) ==============================
     constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
     const uint32_t kv_addr = smem_u32(s_kv), p_addr = smem_u32(s_p);
     const uint64_t dv_sw128 = make_smem_desc(0, 16384, 1024, SWZ_128B);  // MN-major view of the K tile bytes
@@ -260,15 +270,17 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         const uint32_t stage = kv_addr + st * kStageBytes;
         const int tile_start = (sg.start_block + 2 * t) * kPage;
         const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
-        const uint32_t pbuf = p_addr + buf * L::kPBytes;
+        const uint32_t pbuf = p_addr + (kPPairs == 2 ? buf : 0u) * (2 * L::kPBytes);
         if (elect_one()) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
+          for (int hl = 0; hl < 2; ++hl)
 #pragma unroll
-            for (int s = 0; s < 4; ++s)
-              if (s < nk)
-                umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
-                        with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int s = 0; s < 4; ++s)
+                if (s < nk)
+                  umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
+                          with_addr(dp_none, pbuf + hl * L::kPBytes + s * 512), idesc_pv, (t | s | hl) != 0);
           umma_commit(&sm.kv_empty[st]);
           umma_commit(&sm.pv_done);
           if (t == sg.n_tiles - 1) umma_commit(&sm.o_ready);  // one completion per request: the epilogue's gate
@@ -284,9 +296,12 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
     const int cs = (warp - 4) >> 2;             // column slice
     const int cb = cs * CPT;                    // first q column of this thread
     const int tl = quad * 32 + lane;            // token lane within the tile
+    const int page = tl >> 6;                   // which of the tile's two pages this token lane belongs to
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     uint32_t g = 0, o_seg = 0;
-    float lt[CPT];                              // per-lane partial row sums, units of 1/ps relative to mref
+    // per q column of this thread (identical in every thread that owns the column: they are functions of the shared
+    // maxima only): R = reference exponent, lt = this token lane's partial row sum in units of 2^R / 448
+    float R[CPT], lt[CPT];
 
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment(p, b, begin_idx, begin_seqlen, end_idx, end_seqlen, begin_n_split, q_row0, HB);
@@ -296,140 +311,158 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         const int row = q_row0 + st_id;
         const bool vq = st_id < n_valid_q;
         sm.f[st_id] = vq ? __ldg(p.q_scale + (int64_t)b * p.M + row) * p.scale_log2 : 0.f;
-        sm.mref[st_id] = kMInit;
-        sm.ps[st_id] = 1.f;
-        sm.mprime[st_id] = kMInit;
-        sm.lsum[st_id] = 0.f;
         int lim = 0;
         if (vq) lim = p.is_causal ? min(sg.seqlen - mask_len(p.s_q, p.h_q, p.M, row), sg.end_block * kPage) : sg.valid_end;
         sm.lim[st_id] = lim;
       }
       named_bar_sync(1, kSmThreads);
 #pragma unroll
-      for (int q = 0; q < CPT; ++q) lt[q] = 0.f;
+      for (int q = 0; q < CPT; ++q) R[q] = kMInit, lt[q] = 0.f;
       const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
       const bool all_q_valid = n_valid_q == HB && !p.is_causal;
+
+      // this token lane's k scale, fetched one tile ahead (two dependent L2 / HBM round trips otherwise sit between
+      // s_full and the first use)
+      auto fetch_ks = [&](int t) -> float {
+        if (t >= sg.n_tiles) return 1.f;
+        const int token = (sg.start_block + 2 * t) * kPage + tl;
+        if (token >= sg.valid_end) return 1.f;
+        const int pg = __ldg(bt + sg.start_block + 2 * t + page);
+        return __ldg(p.k_scale + (int64_t)pg * kPage + (tl & 63));
+      };
+      float ks_next = fetch_ks(0);
 
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
         const uint32_t buf = g & 1;
         const int tile_start = (sg.start_block + 2 * t) * kPage;
         const int token = tile_start + tl;
         const bool tok_valid = token < sg.valid_end;
-        float ks = 0.f;
-        if (tok_valid) {
-          const int page = __ldg(bt + sg.start_block + 2 * t + (tl >> 6));
-          ks = __ldg(p.k_scale + (int64_t)page * kPage + (tl & 63));
-        }
+        const float ks = ks_next;
+        ks_next = fetch_ks(t + 1);
+        const float lk = log2f(ks), rk = 1.f / ks;
         const bool full_tile = all_q_valid && (tile_start + kTileTokens <= sg.valid_end);
-        if (st_id == 0) sm.trig[(g + 1) % 3] = 0;
 
         mbar_wait(&sm.s_full[buf], (g >> 1) & 1);
         tc_fence_after();
-        float x[CPT];
         const uint32_t s_addr = tmem + kColS + buf * HB + cb + lane_addr;
-        tmem_ld<CPT>(s_addr, x);
-        tmem_wait_ld();
-
-        uint32_t pk[CPT / 4];
-        bool trigger = (t == 0);
-        if (!trigger) {
-          // ---- fast path: reuse the current reference ----
-          float vmax = 0.f;
+        // y = log2 of the un-normalised P' of this token for 8 q columns (S is read from TMEM in both passes: nothing
+        // but R and lt stays live across the barrier)
+        auto load_y8 = [&](int c8, float* y) {
+          tmem_ld<8>(s_addr + c8 * 8, y);
+          tmem_wait_ld();
 #pragma unroll
-          for (int q = 0; q < CPT; ++q) {
-            float arg = fmaf(x[q] * sm.f[cb + q], ks, -sm.mprime[cb + q]);
-            if (!full_tile && !(token < sm.lim[cb + q])) arg = -INFINITY;
-            const float u = ex2_approx(arg);
-            x[q] = u;
-            vmax = fmaxf(vmax, u * ks);
+          for (int q = 0; q < 8; ++q) {
+            const int col = cb + c8 * 8 + q;
+            const float v = fmaf(y[q] * sm.f[col], ks, lk);
+            const bool ok = tok_valid && (full_tile || token < sm.lim[col]);
+            y[q] = ok ? v : -INFINITY;  // a select, not arithmetic: S of a poisoned (NaN) padding row never propagates
           }
+        };
+
+        // ---- pass A: page maxima per q column ----
+        float (*red)[64] = sm.red[g & 1];
 #pragma unroll
-          for (int q = 0; q < CPT; q += 4)
-            pk[q / 4] = cvt_e4m3x4(x[q] * ks, x[q + 1] * ks, x[q + 2] * ks, x[q + 3] * ks);
-          const bool over = vmax > 448.f;
-          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[g % 3] = 1;
-          named_bar_sync(1, kSmThreads);
-          trigger = sm.trig[g % 3] != 0;
-          if (!trigger) {
+        for (int c8 = 0; c8 < CPT / 8; ++c8) {
+          float y[8];
+          load_y8(c8, y);
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) lt[q] += x[q];
+          for (int q = 0; q < 8; ++q) {
+            const int col = cb + c8 * 8 + q;
+            const float wm = warp_max_f32(y[q]);
+            if ((col & 31) == lane) red[quad][col] = wm;
           }
         }
-        if (trigger) {
-          // ---- slow path: move the reference (m_ref, p_scale), rescale O and L ----
-          if (t != 0) {
-            tmem_ld<CPT>(s_addr, x);
-            tmem_wait_ld();
-          }
+        named_bar_sync(1, kSmThreads);
+
+        // ---- reference moves (per q column; every thread that owns the column takes the same decision) ----
+        bool any_move = false;
 #pragma unroll
-          for (int q = 0; q < CPT; ++q) {
-            float z = (x[q] * sm.f[cb + q]) * ks;
-            if (!(token < sm.lim[cb + q])) z = -INFINITY;
-            x[q] = z;
-            const float wm = warp_max_f32(z);
-            if (((cb + q) & 31) == lane) sm.red[quad][cb + q] = wm;
-          }
-          named_bar_sync(1, kSmThreads);
-          float m_old = 0.f, m_new = 0.f;
-          if (st_id < HB) {
-            const float cm = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
-            m_old = sm.mref[st_id];
-            m_new = fmaxf(m_old, cm);
-            sm.mprime[st_id] = m_new;  // temporarily: plain new max, p_scale applied below
-          }
-          named_bar_sync(1, kSmThreads);
-#pragma unroll
-          for (int q = 0; q < CPT; ++q) {
-            const float pp = ex2_approx(x[q] - sm.mprime[cb + q]) * ks;
-            const float wm = warp_max_f32(pp);
-            if (((cb + q) & 31) == lane) sm.red[quad][cb + q] = wm;
-          }
-          named_bar_sync(1, kSmThreads);
-          if (st_id < HB) {
-            float pmax = fmaxf(fmaxf(sm.red[0][st_id], sm.red[1][st_id]), fmaxf(sm.red[2][st_id], sm.red[3][st_id]));
-            pmax = fmaxf(pmax, kPMin);
-            const float ps_new = pmax * (kHeadroom / 448.f);
-            const float ps_old = sm.ps[st_id];
-            sm.fac[st_id] = exp2f(m_old - m_new) * (ps_old / ps_new);
-            sm.mref[st_id] = m_new;
-            sm.ps[st_id] = ps_new;
-            sm.mprime[st_id] = m_new + log2f(ps_new);
-          }
-          named_bar_sync(1, kSmThreads);
+        for (int q = 0; q < CPT; ++q) {
+          const float yb = fmaxf(fmaxf(red[0][cb + q], red[1][cb + q]), fmaxf(red[2][cb + q], red[3][cb + q]));
+          any_move |= yb > R[q];
+        }
+        if (any_move) {  // warp-uniform
           if (t != 0) {
-            // all P.V up to the previous tile must have landed in O before it is rescaled
+            // every P.V up to the previous tile must have landed in O before it is rescaled
             mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
+          }
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              float o[CPT];
-              const uint32_t a = tmem + kColO + j * HB + cb + lane_addr;
-              tmem_ld<CPT>(a, o);
-              tmem_wait_ld();
+          for (int c8 = 0; c8 < CPT / 8; ++c8) {
+            float fac[8];
 #pragma unroll
-              for (int k = 0; k < CPT; ++k) o[k] *= sm.fac[cb + k];
-              tmem_st<CPT>(a, o);
+            for (int q = 0; q < 8; ++q) {
+              const int col = cb + c8 * 8 + q;
+              const float yb = fmaxf(fmaxf(red[0][col], red[1][col]), fmaxf(red[2][col], red[3][col]));
+              const float rn = yb > R[c8 * 8 + q] ? yb + kRefHeadroom : R[c8 * 8 + q];
+              fac[q] = exp2f(R[c8 * 8 + q] - rn);  // 0 on a row's first move (R = -1e30), 1 for rows that stay
+              R[c8 * 8 + q] = rn;
+              lt[c8 * 8 + q] *= fac[q];
             }
-            tmem_wait_st();
+            if (t != 0) {
 #pragma unroll
-            for (int q = 0; q < CPT; ++q) lt[q] *= sm.fac[cb + q];
+              for (int j = 0; j < 4; ++j) {
+                float o[8];
+                const uint32_t a = tmem + kColO + j * HB + cb + c8 * 8 + lane_addr;
+                tmem_ld<8>(a, o);
+                tmem_wait_ld();
+#pragma unroll
+                for (int k = 0; k < 8; ++k) o[k] *= fac[k];
+                tmem_st<8>(a, o);
+              }
+            }
           }
+          if (t != 0) tmem_wait_st();
+        }
+
+        // ---- pass B: page codes, page weight, hi / lo split ----
+        uint32_t hi[CPT / 4], lo[CPT / 4];
 #pragma unroll
-          for (int q = 0; q < CPT; ++q) {
-            const float u = ex2_approx(x[q] - sm.mprime[cb + q]);
-            lt[q] += u;
-            x[q] = u * ks;
+        for (int c8 = 0; c8 < CPT / 8; ++c8) {
+          float y[8];
+          load_y8(c8, y);
+#pragma unroll
+          for (int q = 0; q < 8; q += 2) {
+            float w[2], v[2];
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+              const int col = cb + c8 * 8 + q + e;
+              const float m = page ? fmaxf(red[2][col], red[3][col]) : fmaxf(red[0][col], red[1][col]);
+              const bool live = m > -INFINITY;
+              w[e] = live ? ex2_approx(m - R[c8 * 8 + q + e]) : 0.f;
+              v[e] = ex2_approx(y[q + e] - (live ? m : 0.f) + kLog2Fp8Max);
+            }
+            const uint32_t w_h2 = f32x2_to_f16x2(w[0], w[1]);
+            lt[c8 * 8 + q] = fmaf(f16_lo_to_f32(w_h2), v[0] * rk, lt[c8 * 8 + q]);
+            lt[c8 * 8 + q + 1] = fmaf(f16_hi_to_f32(w_h2), v[1] * rk, lt[c8 * 8 + q + 1]);
+            uint32_t h2, l2;
+            split_hi_lo(cvt_e4m3x2(v[0], v[1]), w_h2, h2, l2);
+            if ((q & 2) == 0) hi[c8 * 2 + q / 4] = h2, lo[c8 * 2 + q / 4] = l2;
+            else hi[c8 * 2 + q / 4] |= h2 << 16, lo[c8 * 2 + q / 4] |= l2 << 16;
           }
-#pragma unroll
-          for (int q = 0; q < CPT; q += 4) pk[q / 4] = cvt_e4m3x4(x[q], x[q + 1], x[q + 2], x[q + 3]);
         }
 
         // ---- publish P (B operand of P.V: [token][q], MN-major, 8x16-byte core matrices) ----
-        // P[buf] (and this KV stage) were last read by P.V of tile g-2, issued by another warp: wait for it to retire
-        mbar_wait(&sm.kv_empty[g % kStages], ((g / kStages) & 1) ^ 1);
-        uint8_t* prow = s_p + buf * L::kPBytes + (cb >> 4) * 2048 + (tl >> 3) * 128 + (tl & 7) * 16 + (cb & 15);
-        if constexpr (CPT == 16) *reinterpret_cast<uint4*>(prow) = make_uint4(pk[0], pk[1], pk[2], pk[3]);
-        else *reinterpret_cast<uint2*>(prow) = make_uint2(pk[0], pk[1]);
+        // The P pair (and this KV stage) was last read by P.V of tile g-2 (two pairs) / g-1 (one pair), issued by
+        // another warp: wait for it to retire
+        if constexpr (kPPairs == 2) {
+          mbar_wait(&sm.kv_empty[g % kStages], ((g / kStages) & 1) ^ 1);
+        } else {
+          if (g > 0) mbar_wait(&sm.pv_done, (g - 1) & 1);
+        }
+        uint8_t* prow = s_p + (kPPairs == 2 ? buf : 0u) * (2 * L::kPBytes) + (cb >> 4) * 2048 + (tl >> 3) * 128 +
+                        (tl & 7) * 16 + (cb & 15);
+        if constexpr (CPT == 8) {
+          *reinterpret_cast<uint2*>(prow) = make_uint2(hi[0], hi[1]);
+          *reinterpret_cast<uint2*>(prow + L::kPBytes) = make_uint2(lo[0], lo[1]);
+        } else {
+#pragma unroll
+          for (int c = 0; c < CPT / 16; ++c) {
+            *reinterpret_cast<uint4*>(prow + c * 2048) = make_uint4(hi[4 * c], hi[4 * c + 1], hi[4 * c + 2], hi[4 * c + 3]);
+            *reinterpret_cast<uint4*>(prow + c * 2048 + L::kPBytes) =
+                make_uint4(lo[4 * c], lo[4 * c + 1], lo[4 * c + 2], lo[4 * c + 3]);
+          }
+        }
         // rows past the end of the sequence feed P.V with P = 0; make sure V there is finite (0 * NaN).
         // Reference: fill_oob_V, splitkv_mla.cu:698-721.
         if (!tok_valid && cs == 0) {
@@ -450,15 +483,22 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
       }
 
       // ---- epilogue of this request: O^T / L -> out (or split partials) ----
+      float (*red)[64] = sm.red[0];
+      named_bar_sync(1, kSmThreads);  // the last tile's readers of red[0] are done
 #pragma unroll
       for (int q = 0; q < CPT; ++q) {
         float v = lt[q];
         for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) sm.red[quad][cb + q] = v;
+        if (lane == 0) red[quad][cb + q] = v;
+        if (tl == 0) sm.rfin[cb + q] = R[q];
       }
       named_bar_sync(1, kSmThreads);
       // fixed summation order: results are bit-reproducible run to run
-      if (st_id < HB) sm.lsum[st_id] = (sm.red[0][st_id] + sm.red[1][st_id]) + (sm.red[2][st_id] + sm.red[3][st_id]);
+      if (st_id < HB) {
+        const float l = (red[0][st_id] + red[1][st_id]) + (red[2][st_id] + red[3][st_id]);
+        sm.lsum[st_id] = l;
+        sm.inv[st_id] = (l == 0.f || l != l) ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
+      }
       named_bar_sync(1, kSmThreads);
       if (sg.n_tiles > 0) {
         // not pv_done: it completes once per tile and a parity wait from here could be two phases behind
@@ -466,11 +506,6 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         tc_fence_after();
       }
       const int64_t out_row0 = (int64_t)b * p.M + q_row0;
-      if (st_id < HB) {
-        const float l = sm.lsum[st_id];
-        sm.fac[st_id] = (l == 0.f || l != l) ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
-      }
-      named_bar_sync(1, kSmThreads);
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         float o[CPT];
@@ -486,7 +521,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         for (int k = 0; k < CPT; ++k) {
           const int q = cb + k;
           if (q < n_valid_q) {
-            const float val = o[k] * sm.fac[q];
+            const float val = o[k] * sm.inv[q];
             if (sg.no_split) p.out[(out_row0 + q) * 512 + d] = __float2bfloat16_rn(val);
             else p.o_accum[((int64_t)sg.split_idx * p.M + q_row0 + q) * 512 + d] = val;
           }
@@ -496,7 +531,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         const int row = q_row0 + st_id;
         const float l = sm.lsum[st_id];
         const bool bad = (l == 0.f || l != l);
-        const float lse2 = log2f(l) + sm.mprime[st_id];
+        const float lse2 = log2f(l) + (sm.rfin[st_id] - kLog2Fp8Max);  // L_true = L * 2^R / 448
         if (sg.no_split) {
           const int s = row / p.h_q, h = row % p.h_q;
           p.lse[((int64_t)b * p.h_q + h) * p.s_q + s] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
@@ -520,11 +555,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
 template <int HB, int CPT>
 static int launch_mla(const MlaParams& prm, int q_blocks, int num_sm_parts, cudaStream_t stream) {
   const int smem = SmemLayout<HB>::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  B200_CUDA(cudaFuncSetAttribute(mla_decode_kernel<HB, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   mla_decode_kernel<HB, CPT><<<dim3(q_blocks, 1, num_sm_parts), 128 + 128 * (HB / CPT), smem, stream>>>(prm);
   B200_CUDA(cudaGetLastError());
   return 0;
@@ -612,8 +643,8 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
   if (M > 64 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else if (HB == 32) rc = launch_mla<32, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else rc = launch_mla<64, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else if (HB == 32) rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else rc = launch_mla<64, 32>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;
   return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);
 }

@@ -17,11 +17,14 @@
 //   every MMA reads at most 6 KB of operands per 64 tensor-core cycles, which is what lets the tensor pipe run near
 //   its issue rate (single-CTA SS MMAs at N <= 128 are operand-bandwidth bound, see b200_umma_rate).
 //
-//   Softmax: a thread owns (q row, 64 token columns = one page).  Two groups of four warps ping-pong over the tiles
-//   (group = tile parity); under the lazy (m_ref, p_scale) reference of mla_decode.cu a tile's P does not depend on
-//   its predecessor unless the reference moves, so the groups only meet at a per-tile hand-off (fin) and a version
-//   counter; a group that computed under a reference that has since moved recomputes.  The pass over S is a compact
-//   16-column loop (TMEM load double-buffered, packed fp32x2 arithmetic, e4m3 codes written straight into the P tile).
+//   Softmax: a thread owns (q row, 64 token columns = one page) -- exactly the reference's (row, page) granularity, so
+//   the page maximum, the page's e4m3 codes and the page sum (mla_decode.cu, comment above mla_decode_kernel) are
+//   thread-local.  O and L live under a per-row reference exponent R that moves only when a page exceeds it; the page
+//   weight 2^(ymax - R) rides on the codes as an e4m3 hi + lo pair (two P tiles, two P.V products per tile).  Two
+//   groups of four warps ping-pong over the tiles (group = tile parity); a tile's P depends on its predecessor only
+//   through R, so the groups meet at a per-tile hand-off (fin) and a version counter; a group that computed under a
+//   reference that has since moved recomputes its second pass.  Both passes over S are compact 16-column loops (TMEM
+//   loads double-buffered, packed fp32x2 / f16x2 arithmetic, codes written straight into the swizzled P tiles).
 //
 //   Warp roles per CTA (384 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
 //   and the k-scale ring; warp 2 = V producer; leader CTA: warp 1 issues every Q.K^T and warp 3 every P.V (two
@@ -29,8 +32,8 @@
 //   warp 1 relays the local P / O hand-offs to the leader; warp 1 also owns the TMEM allocation; warps 4-11 =
 //   softmax / correction / epilogue.
 //   TMEM per CTA: 4 S tiles (4 x 64 columns) + O (2 x 128 columns) = 512 columns.
-//   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, 2 V stages x 32 KB, 4 P tiles x 8 KB (also the
-//   epilogue's staging tile), k-scale ring 4 KB, barriers / row state 5 KB.
+//   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, 2 V stages x 32 KB, 2 P pairs (hi, lo) x 2 x 8 KB
+//   (also the epilogue's staging tile), k-scale ring 4 KB, barriers / row state / log2 and reciprocal scales 6 KB.
 #include <string.h>
 
 #include "mla_common.cuh"
@@ -48,16 +51,15 @@ constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kQBytes;
 constexpr int kOffV = kOffK + kKStages * kKStageBytes;
 constexpr int kOffP = kOffV + kVStages * kVStageBytes;
-constexpr int kPBufs = 4;                            // P tiles: a softmax group writes tile g+2 while P.V of tile g is pending
-constexpr int kOffKs = kOffP + kPBufs * kPBytes;     // k-scale ring: [kKsStages][128] f32; the four P tiles (32 KB) double
-                                                     // as the epilogue's staging tile
+constexpr int kPPairs = 2;                           // P tiles come in (hi, lo) pairs, one pair per softmax group (tile parity)
+constexpr int kOffKs = kOffP + kPPairs * 2 * kPBytes;  // k-scale ring: [kKsStages][128] f32; the four P tiles (32 KB)
+                                                     // double as the epilogue's staging tile
 constexpr int kOffSmall = kOffKs + kKsStages * 512;
 constexpr int kTotal = kOffSmall + 6144;
 constexpr int kSmThreads = 256;                      // softmax group
 constexpr int kSBufs = 4;                            // S tiles in TMEM: Q.K^T may run kSBufs - 1 tiles ahead of P.V
 constexpr uint32_t kColS = 0, kColO = kSBufs * 64, kTmemCols = 512;
 static_assert(kColO + 256 <= kTmemCols, "TMEM budget");
-static_assert(kPBufs == kSBufs, "s_full(g) stands in for p_free of P tile g % kPBufs");
 static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOffKs % 1024 == 0, "swizzle alignment");
 
 struct Small {
@@ -65,16 +67,18 @@ struct Small {
   uint64_t v_land[kVStages], v_empty[kVStages];
   uint64_t ks_full[kKsStages], ks_empty[kKsStages];
   uint64_t q_full, q_empty;
-  uint64_t s_full[kSBufs], p_full[kPBufs], p_free[kPBufs];
+  uint64_t s_full[kSBufs], s_free[kSBufs];     // s_free(g): P.V of tile g retired -> S tile g % kSBufs may be overwritten
+  uint64_t p_full[kPPairs], p_free[kPPairs];   // per P pair (tile parity)
   uint64_t pv_done, o_ready, o_free;
-  uint64_t p_relay[kPBufs], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
+  uint64_t p_relay[kPPairs], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
   uint64_t fin[2];               // tile g (buffer g & 1) is final: published, reference moves done
   uint32_t tmem_base;
   uint32_t version;              // bumped by every reference move
   uint32_t k_issued;             // tiles whose K page this CTA's producer has issued (orders the V re-read behind it)
   uint32_t trig[2][3];
-  float st_mref[64], st_ps[64], st_mprime[64];  // per-row lazy reference: max (log2 domain), P scale, mref + log2(ps)
-  float red1[2][2][64], red2[2][2][64], lred[2][4][64];  // lred: row-sum exchange, double-buffered by request parity
+  float st_ref[64];              // per-row reference exponent R (log2): O and L are in units of 2^R / 448
+  float red1[2][2][64], lred[2][4][64];  // page maxima exchange; lred: row-sum exchange, double-buffered by request parity
+  alignas(16) float lkrk[2][256];  // per softmax group: log2(k_scale) [128] and 1 / k_scale [128] of the tile it works on
 };
 static_assert(sizeof(Small) <= 6144, "Small too large");
 static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
@@ -85,8 +89,12 @@ constexpr int kTraceTiles = 64;
 constexpr int kTraceRoles = 5;
 __device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
 __device__ unsigned long long g_part_cycles[2 * 128 * 4];  // [part < 128][rank]{globaltimer ns at entry, at exit, clock64 at entry, at exit}
+// TR = false (the production instantiation) compiles every trace site out
+template <bool TR>
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
-  if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
+  if constexpr (TR) {
+    if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
+  }
 }
 
 // Register-resident window of one block-table row for the producer warp (warp-uniform use): lane l holds entries
@@ -121,6 +129,7 @@ struct BtWindow {
 };
 
 
+template <bool TR>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     mla_decode_pair_kernel(const __grid_constant__ MlaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -139,8 +148,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
   const int pair_row0 = blockIdx.y * 128;
   const int q_row0 = pair_row0 + 64 * (int)rank;
   const int n_valid_q = max(0, min(64, p.M - q_row0));
-  const bool tr = (p.trace & 1) && part == 0 && blockIdx.y == 0 && lane == 0;
-  if ((p.trace & 1) && tid == 0 && part < 128 && blockIdx.y == 0) {
+  const bool tr = TR && part == 0 && blockIdx.y == 0 && lane == 0;
+  if (TR && tid == 0 && part < 128 && blockIdx.y == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_part_cycles[(part * 2 + rank) * 4] = t;
@@ -170,8 +179,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
     mbar_init(&sm.q_full, 2);
     mbar_init(&sm.q_empty, 1);
-    for (int i = 0; i < kSBufs; ++i) mbar_init(&sm.s_full[i], 1);
-    for (int i = 0; i < kPBufs; ++i) {
+    for (int i = 0; i < kSBufs; ++i) {
+      mbar_init(&sm.s_full[i], 1);
+      mbar_init(&sm.s_free[i], 1);
+    }
+    for (int i = 0; i < kPPairs; ++i) {
       mbar_init(&sm.p_full[i], 5);   // the four warps of the leader's softmax group + the peer's relay
       mbar_init(&sm.p_relay[i], 4);
       mbar_init(&sm.p_free[i], 1);
@@ -256,7 +268,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           }
         }
         uint8_t* stage = s_k + st * kKStageBytes;
-        trace(tr, rank, 0, gt, 0);
+        trace<TR>(tr, rank, 0, gt, 0);
         if (elect_one()) {
           mbar_arrive_expect_tx_cluster(k_full_l[st], exists ? (uint32_t)kKStageBytes : 0u);
           if (exists) {
@@ -387,11 +399,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       pre_cur = nxt_req, pre_nxt = nxt_req2, have_pre = bt_next != nullptr;
       ks_done = ks_next;
     }
-  } else if (warp == 3 && rank == 1 && (p.trace & 1) && part == 0 && blockIdx.y == 0) {
+  } else if (TR && warp == 3 && rank == 1 && part == 0 && blockIdx.y == 0) {
     // diagnostic: when each V stage lands in the non-leader CTA
     for (uint32_t g = 0; g < 40; ++g) {
       mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);
-      trace(lane == 0, rank, 0, g, 3);
+      trace<TR>(lane == 0, rank, 0, g, 3);
     }
   } else if (warp == 2) {
     // ============================== V producer (both CTAs) ==============================
@@ -415,21 +427,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       // these bytes were just streamed through L2 as K by this CTA or its peer
       auto load_v = [&](int t, uint32_t gt) {
         const uint32_t st = gt % kVStages;
-        trace(tr, rank, 0, gt, 1);
+        trace<TR>(tr, rank, 0, gt, 1);
         mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
         // behind this tile's K issue: the same bytes then come out of L2 (or merge with the K fetch in flight) instead
         // of competing with the K and Q loads for HBM at a request's start
-        for (uint32_t spins = 0; !(p.trace & 32) && ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
+        for (uint32_t spins = 0; !(TR && (p.trace & 32)) && ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
           if (spins > B200_WAIT_SPIN_LIMIT) __trap();
           __nanosleep(64);
         }
-        trace(tr, rank, 0, gt, 2);
+        trace<TR>(tr, rank, 0, gt, 2);
         const int blk0 = sg.start_block + 2 * t;
         const int npages = min(2, sg.end_block - blk0);
         const int tok0 = bw.get(blk0) * kPage;
         const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
         uint8_t* stage = s_v + st * kVStageBytes;
-        if (p.trace & 8) {  // diagnostic (wrong results): no V traffic at all
+        if (TR && (p.trace & 8)) {  // diagnostic (wrong results): no V traffic at all
           if (elect_one()) mbar_arrive(&sm.v_land[st]);
           __syncwarp();
           return;
@@ -458,8 +470,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     // warp 1 issues every Q.K^T, warp 3 every P.V: two independent instruction streams into the one in-order tensor
     // pipe, so a Q.K^T waiting for its K page never holds back a P.V whose P is published (and vice versa; a single
     // issuer needs either a fixed interleave or polling, and both cost throughput).  Q.K^T of tile g waits for P.V of
-    // tile g - kSBufs to retire (p_free): S tile g % kSBufs has then been read, P tile g % kPBufs is free, and -- the
-    // pipe being in order -- s_full(g) vouches for both to the softmax warps.
+    // tile g - kSBufs to retire (s_free): S tile g % kSBufs has then been read by its softmax group.
     constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
     constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
     constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
@@ -481,10 +492,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait_cluster(&sm.q_full, seg & 1);
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
           const uint32_t kst = g % kKStages, sb = g % kSBufs;
-          if (g >= (uint32_t)kSBufs) mbar_wait(&sm.p_free[sb], ((g / kSBufs) & 1) ^ 1);  // P.V of tile g - kSBufs retired
+          if (g >= (uint32_t)kSBufs) mbar_wait(&sm.s_free[sb], ((g / kSBufs) & 1) ^ 1);  // P.V of tile g - kSBufs retired
           mbar_wait(&sm.ks_full[g % kKsStages], (g / kKsStages) & 1);  // s_full then vouches for the k scales too
           mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
-          trace(tr, rank, 1, g, 0);
+          trace<TR>(tr, rank, 1, g, 0);
           tc_fence_after();
           const uint32_t stage = k_addr + kst * kKStageBytes;
           const uint32_t d = tmem + kColS + sb * 64;
@@ -504,34 +515,37 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             if (t == sg.n_tiles - 1) umma_commit_pair(&sm.q_empty, 3);  // Q smem reusable once these retire
           }
           __syncwarp();
-          trace(tr, rank, 1, g, 1);
+          trace<TR>(tr, rank, 1, g, 1);
         }
       } else {
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          const uint32_t buf = g % kPBufs, vst = g % kVStages;
-          mbar_wait_cluster(&sm.p_full[buf], (g / kPBufs) & 1);  // P written in both CTAs, V landed in the peer
+          const uint32_t pp = g & 1, vst = g % kVStages;
+          mbar_wait_cluster(&sm.p_full[pp], (g >> 1) & 1);  // P written in both CTAs, V landed in the peer
           mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);        // V landed here
           if (t == 0 && seg > 0) mbar_wait_cluster(&sm.o_free, (seg - 1) & 1);
-          trace(tr, rank, 1, g, 2);
+          trace<TR>(tr, rank, 1, g, 2);
           tc_fence_after();
           const int tile_start = (sg.start_block + 2 * t) * kPage;
           const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
           if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < 2; ++j)
+            for (int hl = 0; hl < 2; ++hl)  // P = P_hi + P_lo
 #pragma unroll
-              for (int s = 0; s < 4; ++s)
-                if (s < nk)
-                  umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + buf * kPBytes + s * 32),
-                               with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
-                               !(t == 0 && s == 0));
+              for (int j = 0; j < 2; ++j)
+#pragma unroll
+                for (int s = 0; s < 4; ++s)
+                  if (s < nk)
+                    umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + (2 * pp + hl) * kPBytes + s * 32),
+                                 with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
+                                 !(t == 0 && s == 0 && hl == 0));
             umma_commit_pair(&sm.v_empty[vst], 3);
-            umma_commit_pair(&sm.p_free[buf], 3);
+            umma_commit_pair(&sm.p_free[pp], 3);
+            umma_commit_pair(&sm.s_free[g % kSBufs], 3);
             umma_commit_pair(&sm.pv_done, 3);
             if (t == sg.n_tiles - 1) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
           }
           __syncwarp();
-          trace(tr, rank, 1, g, 3);
+          trace<TR>(tr, rank, 1, g, 3);
         }
       }
       ++seg;
@@ -543,9 +557,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       // phase completes here -- the stores are then performed in this SM's shared memory -- one remote arrive tells the
       // leader.  A direct remote arrive from the softmax warps would need a cluster-scope release (a cluster-wide
       // membar per tile, measured at a third of their time); with CTA-scope release the arrive overtakes the stores.
-      uint32_t p_full_l[kPBufs];
+      uint32_t p_full_l[kPPairs];
 #pragma unroll
-      for (int i = 0; i < kPBufs; ++i) p_full_l[i] = mapa_u32(smem_u32(&sm.p_full[i]), 0);
+      for (int i = 0; i < kPPairs; ++i) p_full_l[i] = mapa_u32(smem_u32(&sm.p_full[i]), 0);
       const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
       uint32_t g = 0, seg = 0;
       int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
@@ -558,9 +572,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
         if (sg.n_tiles == 0) continue;
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          mbar_wait(&sm.p_relay[g % kPBufs], (g / kPBufs) & 1);
+          mbar_wait(&sm.p_relay[g & 1], (g >> 1) & 1);
           mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);  // the forwarded arrival also vouches for this CTA's V
-          if (elect_one()) mbar_arrive_cluster(p_full_l[g % kPBufs]);
+          if (elect_one()) mbar_arrive_cluster(p_full_l[g & 1]);
           __syncwarp();
         }
         mbar_wait(&sm.o_relay, seg & 1);
@@ -596,11 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     // epilogue and the next request's first tile)
     int cur_seqlen = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);
     float cur_qs = row_valid ? __ldg(p.q_scale + (int64_t)begin_idx * p.M + grow) : 0.f;
-    if (grp == 0 && page == 0) {
-      sm.st_mref[row] = kMInit;
-      sm.st_ps[row] = 1.f;
-      sm.st_mprime[row] = kMInit;
-    }
+    if (grp == 0 && page == 0) sm.st_ref[row] = kMInit;
     named_bar_sync(1, kSmThreads);
     uint32_t rq = 0;  // requests of this part seen so far (parity selects the row-sum exchange buffer)
 
@@ -619,83 +629,43 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       // The row state of this request was reset before the first request (below) or by the group that owns this
       // request's first tile, right after the previous request's last hand-off.  A thread's view starts invalid, so
       // its first tile loads the state (the other group may already have moved the reference).
-      float mprime = kMInit, lsum = 0.f;  // this thread's view of the row reference; lsum is in units of 2^-mprime
+      float rloc = kMInit, lsum = 0.f;  // this thread's view of the row reference R; lsum is in units of 2^rloc / 448
       uint32_t ver = 0xffffffffu;
-
-      // This lane's 64 S columns under the reference `mp`, 16 columns at a time (a compact, not unrolled loop: the
-      // kernel's hot code stays inside the instruction cache): P' = exp2(s f k - mp) k -> e4m3 straight into the P
-      // tile (K-major, 128-byte swizzle; nobody reads it before this group arrives on p_full), row-sum and overflow
-      // contributions.  Packed fp32x2 arithmetic: per element pair 4 FMA-pipe instructions, 2 MUFU.EX2, 1 F2FP.
-      auto tile_pass = [&](uint32_t s_addr, const float* ks_tile, int tile_start, bool need_mask, float mp, uint8_t* prow,
-                           float& acc, float& vmax) {
-        const float2 f2 = make_float2(f, f), nmp2 = make_float2(-mp, -mp), one2 = make_float2(1.f, 1.f);
-        float2 acc2 = make_float2(0.f, 0.f);
-        const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
-        const int nvalid = lim - (tile_start + page * 64);  // columns of this lane below the mask border
-        auto chunk = [&](float* x, int c16) {
-          float kf[16];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 v4 = ksrc[c16 * 4 + i];
-            kf[4 * i] = v4.x, kf[4 * i + 1] = v4.y, kf[4 * i + 2] = v4.z, kf[4 * i + 3] = v4.w;
-          }
-          if (!need_mask) {
-#pragma unroll
-            for (int c = 0; c < 16; c += 2) {
-              const float2 k2 = make_float2(kf[c], kf[c + 1]);
-              const float2 a2 = fma2(make_float2(x[c], x[c + 1]), mul2(f2, k2), nmp2);
-              const float2 u2 = make_float2(ex2_approx(a2.x), ex2_approx(a2.y));
-              acc2 = fma2(u2, one2, acc2);
-              const float2 p2 = mul2(u2, k2);
-              x[c] = p2.x, x[c + 1] = p2.y;
-              vmax = fmaxf(vmax, fmaxf(p2.x, p2.y));
-            }
-          } else {
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-              const bool ok = c16 * 16 + c < nvalid;
-              const float kc = ok ? kf[c] : 0.f;
-              const float arg = ok ? fmaf(x[c], f * kc, -mp) : -INFINITY;
-              const float u = ex2_approx(arg);
-              acc2.x += u;
-              x[c] = u * kc;
-              vmax = fmaxf(vmax, x[c]);
-            }
-          }
-          *reinterpret_cast<uint4*>(prow + (((page * 4 + c16) ^ (row & 7)) << 4)) =
-              make_uint4(cvt_e4m3x4(x[0], x[1], x[2], x[3]), cvt_e4m3x4(x[4], x[5], x[6], x[7]),
-                         cvt_e4m3x4(x[8], x[9], x[10], x[11]), cvt_e4m3x4(x[12], x[13], x[14], x[15]));
-        };
-        // two register sets: the TMEM load of the next 16 columns is in flight while this one is processed
-        float xa[16], xb[16];
-        tmem_ld16(s_addr, reinterpret_cast<uint32_t*>(xa));
-#pragma unroll 1
-        for (int c16 = 0; c16 < 4; c16 += 2) {
-          tmem_wait_ld();
-          tmem_ld16(s_addr + (c16 + 1) * 16, reinterpret_cast<uint32_t*>(xb));
-          chunk(xa, c16);
-          tmem_wait_ld();
-          if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
-          chunk(xb, c16 + 1);
+      // bring this thread's view (rloc, lsum) up to the row's current reference
+      auto sync_view = [&]() {
+        const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
+        if (v_now != ver) {
+          const float r_new = ld_shared_volatile_f32(&sm.st_ref[row]);
+          lsum *= exp2f(rloc - r_new);
+          rloc = r_new;
+          ver = v_now;
         }
-        acc += acc2.x + acc2.y;
       };
-      // max over this lane's 64 columns of the scaled logits z = s f k, and of the k scales of its unmasked columns
-      // (TMEM loads double-buffered, k scales read as float4)
-      auto tile_max = [&](uint32_t s_addr, const float* ks_tile, int tile_start, bool need_mask, float& ksmax) {
+
+      // Pass A over this lane's 64 S columns: ymax = max_j y_j, y_j = s_j f k_j + log2 k_j = log2 of the un-normalised
+      // P'_j (splitkv_mla.cu:400-432 computes the same maximum as max_j exp2(..) k_j).  16 columns at a time, TMEM loads
+      // double-buffered, a compact loop (the kernel's hot code stays inside the instruction cache).
+      auto pass_max = [&](uint32_t s_addr, const float* ks_tile, const float* lk_tile, int tile_start, bool need_mask) {
+        const float2 f2 = make_float2(f, f);
         const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
-        const int nvalid = need_mask ? lim - (tile_start + page * 64) : 64;
-        float r = -INFINITY, km = 0.f;
+        const float4* lsrc = reinterpret_cast<const float4*>(lk_tile + page * 64);
+        const int nvalid = lim - (tile_start + page * 64);  // columns of this lane below the mask border
+        float m0 = -INFINITY, m1 = -INFINITY;
         auto chunk = [&](const float* x, int c16) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 k4 = ksrc[c16 * 4 + i];
-            const float kk[4] = {k4.x, k4.y, k4.z, k4.w};
+            const float4 k4 = ksrc[c16 * 4 + i], l4 = lsrc[c16 * 4 + i];
+            if (!need_mask) {
+              const float2 ya = fma2(make_float2(x[4 * i], x[4 * i + 1]), mul2(f2, make_float2(k4.x, k4.y)), make_float2(l4.x, l4.y));
+              const float2 yb = fma2(make_float2(x[4 * i + 2], x[4 * i + 3]), mul2(f2, make_float2(k4.z, k4.w)), make_float2(l4.z, l4.w));
+              m0 = fmaxf(m0, fmaxf(ya.x, ya.y));
+              m1 = fmaxf(m1, fmaxf(yb.x, yb.y));
+            } else {
+              const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              if (c16 * 16 + 4 * i + j < nvalid) {
-                r = fmaxf(r, x[4 * i + j] * (f * kk[j]));
-                km = fmaxf(km, kk[j]);
+              for (int j = 0; j < 4; ++j) {
+                const float y = fmaf(x[4 * i + j], f * kk[j], ll[j]);
+                if (c16 * 16 + 4 * i + j < nvalid) m0 = fmaxf(m0, y);  // a select: poisoned padding never propagates
               }
             }
           }
@@ -711,136 +681,194 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
           chunk(xb, c16 + 1);
         }
-        ksmax = km;
-        return r;
+        return fmaxf(m0, m1);
+      };
+      // Pass B: the page's codes code_j = e4m3(448 * 2^(y_j - ymax)) (:433-440), the page sum sum_j 448 * 2^(y_j - ymax)
+      // / k_j (:426,434), and code_j * w as an e4m3 pair hi + lo straight into the two P tiles (K-major, 128-byte
+      // swizzle; nobody reads them before this group arrives on p_full).
+      auto pass_codes = [&](uint32_t s_addr, const float* ks_tile, const float* lk_tile, const float* rk_tile, int tile_start,
+                            bool need_mask, float ymax, uint32_t w_h2, uint8_t* prow, float& acc) {
+        const float2 f2 = make_float2(f, f);
+        const float c = (ymax > -INFINITY ? ymax : 0.f) - kLog2Fp8Max;
+        const float2 nc2 = make_float2(-c, -c), one2 = make_float2(1.f, 1.f);
+        float2 acc2 = make_float2(0.f, 0.f);
+        const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
+        const float4* lsrc = reinterpret_cast<const float4*>(lk_tile + page * 64);
+        const float4* rsrc = reinterpret_cast<const float4*>(rk_tile + page * 64);
+        const int nvalid = lim - (tile_start + page * 64);
+        auto chunk = [&](const float* x, int c16) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 k4 = ksrc[c16 * 4 + i], l4 = lsrc[c16 * 4 + i], r4 = rsrc[c16 * 4 + i];
+            float v[4];
+            if (!need_mask) {
+              const float2 ya = fma2(make_float2(x[4 * i], x[4 * i + 1]), mul2(f2, make_float2(k4.x, k4.y)), make_float2(l4.x, l4.y));
+              const float2 yb = fma2(make_float2(x[4 * i + 2], x[4 * i + 3]), mul2(f2, make_float2(k4.z, k4.w)), make_float2(l4.z, l4.w));
+              const float2 aa = fma2(ya, one2, nc2), ab = fma2(yb, one2, nc2);
+              v[0] = ex2_approx(aa.x), v[1] = ex2_approx(aa.y), v[2] = ex2_approx(ab.x), v[3] = ex2_approx(ab.y);
+              acc2 = fma2(make_float2(v[0], v[1]), make_float2(r4.x, r4.y), acc2);
+              acc2 = fma2(make_float2(v[2], v[3]), make_float2(r4.z, r4.w), acc2);
+            } else {
+              const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const bool ok = c16 * 16 + 4 * i + j < nvalid;
+                const float y = fmaf(x[4 * i + j], f * kk[j], ll[j]);
+                v[j] = ok ? ex2_approx(y - c) : 0.f;
+                acc2.x += ok ? v[j] * rr[j] : 0.f;
+              }
+            }
+            uint32_t h0, l0, h1, l1;
+            split_hi_lo(cvt_e4m3x2(v[0], v[1]), w_h2, h0, l0);
+            split_hi_lo(cvt_e4m3x2(v[2], v[3]), w_h2, h1, l1);
+            hi[i] = h0 | (h1 << 16);
+            lo[i] = l0 | (l1 << 16);
+          }
+          const int off = ((page * 4 + c16) ^ (row & 7)) << 4;
+          *reinterpret_cast<uint4*>(prow + off) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(prow + kPBytes + off) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        };
+        // two register sets: the TMEM load of the next 16 columns is in flight while this one is processed
+        float xa[16], xb[16];
+        tmem_ld16(s_addr, reinterpret_cast<uint32_t*>(xa));
+#pragma unroll 1
+        for (int c16 = 0; c16 < 4; c16 += 2) {
+          tmem_wait_ld();
+          tmem_ld16(s_addr + (c16 + 1) * 16, reinterpret_cast<uint32_t*>(xb));
+          chunk(xa, c16);
+          tmem_wait_ld();
+          if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
+          chunk(xb, c16 + 1);
+        }
+        acc = acc2.x + acc2.y;
       };
 
       const int t_first = (int)((grp ^ g0) & 1u);  // this group's first tile of the request
       for (int t = t_first; t < sg.n_tiles; t += 2, ++n_mine) {
         const uint32_t g = g0 + (uint32_t)t;
-        const uint32_t buf = g % kPBufs, vst = g % kVStages, kst = g % kKsStages;
+        const uint32_t vst = g % kVStages, kst = g % kKsStages;
         const int tile_start = (sg.start_block + 2 * t) * kPage;
         const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
         const bool tr_w = tr && quad == 0;
         if (gtid == 0) sm.trig[grp][(n_mine + 1) % 3] = 0;
-        if (t <= 1) trace(tr_w, rank, 3, o_seg, 3);
-        trace(tr_w, rank, 4, g, 3);
+        if (t <= 1) trace<TR>(tr_w, rank, 3, o_seg, 3);
+        trace<TR>(tr_w, rank, 4, g, 3);
 
         // No wait on ks_full: the UMMA issuer saw the tile's k scales land before it issued this tile's Q.K^T, so
         // s_full vouches for them too.
         const float* ks_tile = s_ks + kst * 128;
+        const float* lk_tile = sm.lkrk[grp];
+        const float* rk_tile = sm.lkrk[grp] + 128;
         const uint32_t sb = g % kSBufs;
         const uint32_t s_addr = tmem + kColS + sb * 64 + lane_addr;
-        uint8_t* prow = s_p + buf * kPBytes + row * 128;
+        uint8_t* prow = s_p + (2 * grp) * kPBytes + row * 128;  // this group's P pair: hi tile, lo tile right behind it
         // the first two tiles of a request always see a reference move: wait for the predecessor before computing
         bool fin_waited = false;
         if (t <= 1 && g > 0) {
           mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
           fin_waited = true;
         }
-        // No wait on p_free either: Q.K^T of tile g is issued after P.V of tile g - kSBufs and the tensor pipe retires
-        // in order, so s_full(g) implies that P tile g % kPBufs (kPBufs == kSBufs) is no longer being read.
-        trace(tr_w, rank, 2, g, 0);
+        trace<TR>(tr_w, rank, 2, g, 0);
         mbar_wait(&sm.s_full[sb], (g / kSBufs) & 1);
-        trace(tr_w, rank, 2, g, 1);
+        trace<TR>(tr_w, rank, 2, g, 1);
         tc_fence_after();
 
-        float acc = 0.f;
+        // log2 and reciprocal of the tile's 128 k scales, once per tile for the whole group
+        {
+          const float k = ks_tile[gtid];
+          sm.lkrk[grp][gtid] = log2f(k);
+          sm.lkrk[grp][128 + gtid] = 1.f / k;
+        }
+        named_bar_sync(gbar, 128);
+        const float ymax = pass_max(s_addr, ks_tile, lk_tile, tile_start, need_mask);
+        const bool live = ymax > -INFINITY;
+        trace<TR>(tr_w, rank, 4, g, 0);
+
+        float acc = 0.f, w32 = 0.f;
+        bool p_free_waited = false;
+        // this group's P pair was last read by P.V of tile g - 2
+        auto wait_p_free = [&]() {
+          if (!p_free_waited) {
+            mbar_wait(&sm.p_free[grp], ((g >> 1) & 1) ^ 1);
+            p_free_waited = true;
+          }
+        };
+        auto weighted_pass = [&]() {
+          const float w = live ? ex2_approx(ymax - rloc) : 0.f;
+          const uint32_t w_h2 = f32x2_to_f16x2(w, w);
+          w32 = f16_lo_to_f32(w_h2);  // L carries the weight P.V sees
+          wait_p_free();
+          pass_codes(s_addr, ks_tile, lk_tile, rk_tile, tile_start, need_mask, ymax, w_h2, prow, acc);
+        };
         bool trigger = (t == 0);
         while (!trigger) {
           // ---- fast path: the current reference ----
-          const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
-          if (v_now != ver) {  // the reference moved since this thread last looked: re-base the running sum
-            const float mp_new = ld_shared_volatile_f32(&sm.st_mprime[row]);
-            lsum *= exp2f(mprime - mp_new);
-            mprime = mp_new;
-            ver = v_now;
-          }
-          float vmax = 0.f;
-          acc = 0.f;
-          tile_pass(s_addr, ks_tile, tile_start, need_mask, mprime, prow, acc, vmax);
-          trace(tr_w, rank, 4, g, 0);
+          sync_view();
+          const bool over = __any_sync(0xffffffffu, live && ymax > rloc);  // a row of this warp outgrew its reference
+          if (!over) weighted_pass();
           if (!fin_waited) {
             if (g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);  // tile g-1 is final
             fin_waited = true;
           }
-          trace(tr_w, rank, 4, g, 1);
+          trace<TR>(tr_w, rank, 4, g, 1);
           if (ld_shared_volatile_u32(&sm.version) != ver) continue;  // computed under a reference that has moved
-          const bool over = vmax > 448.f;
-          if (__any_sync(0xffffffffu, over) && lane == 0) sm.trig[grp][n_mine % 3] = 1;
+          if (over && lane == 0) sm.trig[grp][n_mine % 3] = 1;
           named_bar_sync(gbar, 128);
           trigger = sm.trig[grp][n_mine % 3] != 0;
           break;
         }
         if (!trigger) {
-          lsum += acc;
+          lsum = fmaf(w32, acc, lsum);
         } else {
-          // ---- slow path: move the reference (m_ref, p_scale) of every row, rescale O and the running sums ----
+          // ---- slow path: move the reference R of the rows that outgrew it, rescale O and the running sums ----
           if (!fin_waited && g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
-          {
-            const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
-            if (v_now != ver) {
-              const float mp_new = ld_shared_volatile_f32(&sm.st_mprime[row]);
-              lsum *= exp2f(mprime - mp_new);
-              mprime = mp_new;
-              ver = v_now;
-            }
-          }
-          // New reference: m_new = the row's running maximum of the scaled logits; p_scale from an upper bound of
-          // P' = exp2(z - m_new) * k_scale <= max k_scale of the row's unmasked tokens in this tile (one pass over S
-          // instead of two; the bound costs at most the k-scale spread of the tile in e4m3 headroom).
-          float ksmax;
-          sm.red1[grp][page][row] = tile_max(s_addr, ks_tile, tile_start, need_mask, ksmax);
-          sm.red2[grp][page][row] = ksmax;
+          sync_view();
+          sm.red1[grp][page][row] = ymax;
           named_bar_sync(gbar, 128);
-          const float m_old = ld_shared_volatile_f32(&sm.st_mref[row]), ps_old = ld_shared_volatile_f32(&sm.st_ps[row]);
-          const float m_new = fmaxf(m_old, fmaxf(sm.red1[grp][0][row], sm.red1[grp][1][row]));
-          const float pmax = fmaxf(fmaxf(sm.red2[grp][0][row], sm.red2[grp][1][row]), kPMin);
-          const float ps_new = pmax * (kHeadroom / 448.f);
-          const float fac = exp2f(m_old - m_new) * (ps_old / ps_new);
-          const float mp_new = m_new + log2f(ps_new);
+          const float r_old = ld_shared_volatile_f32(&sm.st_ref[row]);  // == rloc
+          const float yb = fmaxf(sm.red1[grp][0][row], sm.red1[grp][1][row]);
+          const float r_new = yb > r_old ? yb + kRefHeadroom : r_old;
+          const float fac = exp2f(r_old - r_new);  // 0 on the row's first move (R = -1e30), 1 if the row stays
           if (t != 0) {
             // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
             // last one issued: tile g is not published yet).  pv_done completes once per tile and Q.K^T runs ahead of
             // P.V: first make sure P.V of tile g-2 has retired (its p_free, at most one phase behind), so that the
             // parity wait on pv_done cannot alias the phase before it.
-            if (g >= 2) mbar_wait(&sm.p_free[(g - 2) % kPBufs], ((g - 2) / kPBufs) & 1);
+            wait_p_free();
             mbar_wait(&sm.pv_done, (g - 1) & 1);
             tc_fence_after();
+            if (__any_sync(0xffffffffu, fac != 1.f)) {
 #pragma unroll 1
-            for (int c8 = 0; c8 < 8; ++c8) {
-              float o[32];
-              const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
-              tmem_ld<32>(a, o);
-              tmem_wait_ld();
+              for (int c8 = 0; c8 < 8; ++c8) {
+                float o[32];
+                const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
+                tmem_ld<32>(a, o);
+                tmem_wait_ld();
 #pragma unroll
-              for (int k = 0; k < 32; ++k) o[k] *= fac;
-              tmem_st<32>(a, o);
+                for (int k = 0; k < 32; ++k) o[k] *= fac;
+                tmem_st<32>(a, o);
+              }
+              tmem_wait_st();
             }
-            tmem_wait_st();
             lsum *= fac;
           }
-          mprime = mp_new;
-          if (page == 0) {
-            sm.st_mref[row] = m_new;
-            sm.st_ps[row] = ps_new;
-            sm.st_mprime[row] = mp_new;
-          }
+          rloc = r_new;
+          if (page == 0) sm.st_ref[row] = r_new;
           tc_fence_before();
           named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
           ver += 1;
           if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
-          float vmax = 0.f;
-          acc = 0.f;
-          tile_pass(s_addr, ks_tile, tile_start, need_mask, mprime, prow, acc, vmax);
-          lsum += acc;
+          weighted_pass();
+          lsum = fmaf(w32, acc, lsum);
+          named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
 
-        trace(tr_w, rank, 2, g, 2);
+        trace<TR>(tr_w, rank, 2, g, 2);
         // ---- publish P ----
-        trace(tr_w, rank, 4, g, 2);
+        trace<TR>(tr_w, rank, 4, g, 2);
         // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
         // Reference: fill_oob_V, splitkv_mla.cu:698-721.
         if (tile_start + kTileTokens > sg.valid_end) {
@@ -861,19 +889,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(rank == 0 ? &sm.p_full[buf] : &sm.p_relay[buf]);
+          mbar_arrive(rank == 0 ? &sm.p_full[grp] : &sm.p_relay[grp]);
           mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the other group may publish tile g+1
         }
-        trace(tr_w, rank, 2, g, 3);
+        trace<TR>(tr_w, rank, 2, g, 3);
       }
       g0 += (uint32_t)sg.n_tiles;
 
       // both groups have published their last tile: bring every thread's running sum to the request's final reference
       named_bar_sync(1, kSmThreads);
       {
-        const float mp_fin = ld_shared_volatile_f32(&sm.st_mprime[row]);
-        lsum *= exp2f(mprime - mp_fin);
-        mprime = mp_fin;
+        const float r_fin = ld_shared_volatile_f32(&sm.st_ref[row]);
+        lsum *= exp2f(rloc - r_fin);
+        rloc = r_fin;
       }
       // ---- epilogue of this request: O / L -> out (or split partials) ----
       // One group writes the request out while the other starts the next request (its first tile always moves the
@@ -885,31 +913,27 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       const bool had_tiles = sg.n_tiles > 0;
       if (grp != egrp) {
         if (b < end_idx) {  // reset the row state for the next request; nobody reads the old one any more
-          if (page == 0) {
-            sm.st_mref[row] = kMInit;
-            sm.st_ps[row] = 1.f;
-            sm.st_mprime[row] = kMInit;
-          }
+          if (page == 0) sm.st_ref[row] = kMInit;
           named_bar_sync(gbar, 128);
         }
       } else {
         const bool tr_e = tr && quad == 0;
-        trace(tr_e, rank, 3, o_seg, 0);
+        trace<TR>(tr_e, rank, 3, o_seg, 0);
         const float l = (sm.lred[rq & 1][0][row] + sm.lred[rq & 1][1][row]) + (sm.lred[rq & 1][2][row] + sm.lred[rq & 1][3][row]);
         const bool bad = (l == 0.f || l != l);
         const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
         if (had_tiles) {
           // (not pv_done: it completes once per tile and a parity wait from here could be phases behind)
           mbar_wait(&sm.o_ready, o_seg & 1);
-          trace(tr_e, rank, 3, o_seg, 1);
+          trace<TR>(tr_e, rank, 3, o_seg, 1);
           tc_fence_after();
         }
         // O -> global through shared memory, so that every global store instruction writes whole 64 / 128-byte
         // segments (a TMEM lane is a q row: storing straight from the tcgen05.ld registers scatters 16-byte pieces
-        // over 32 rows per instruction).  Staging = this group's own two P tiles (its next tiles' buffers: every P.V of
-        // this request has retired, and the other group only writes the other two): one 8 KB half per TMEM lane half
+        // over 32 rows per instruction).  Staging = this group's own P pair (its next tiles' buffers: every P.V of
+        // this request has retired, and the other group only writes its own pair): one 8 KB half per TMEM lane half
         // (= 128-column block of d), [64 rows][32 values], 16-byte chunks XOR-swizzled; eight rounds of 32 columns.
-        uint8_t* stage_mine = s_p + (egrp + 2 * page) * kPBytes;
+        uint8_t* stage_mine = s_p + (2 * egrp + page) * kPBytes;
         const int64_t grow0 = (int64_t)b * p.M + q_row0;
         const int gw = warp & 3;  // warp within the group
         if (p.epi_mode) {
@@ -1026,7 +1050,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             if (sg.no_split) {
               // per instruction: 4 rows x 2 lane halves x 64 B
               const int k = lane & 3, pg = (lane >> 2) & 1, rr = lane >> 3;
-              const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
+              const uint8_t* src = s_p + (2 * egrp + pg) * kPBytes;
   #pragma unroll
               for (int it = 0; it < 4; ++it) {
                 const int r = gw * 16 + it * 4 + rr;
@@ -1036,7 +1060,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             } else {
               // per instruction: 2 rows x 2 lane halves x 128 B
               const int k = lane & 7, pg = (lane >> 3) & 1, rr = lane >> 4;
-              const uint8_t* src = s_p + (egrp + 2 * pg) * kPBytes;
+              const uint8_t* src = s_p + (2 * egrp + pg) * kPBytes;
               float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
   #pragma unroll
               for (int it = 0; it < 8; ++it) {
@@ -1048,9 +1072,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
             named_bar_sync(gbar, 128);  // the staging halves are rewritten by the next round / this group's next P tile
           }
         }
-        if (had_tiles) trace(tr_e, rank, 3, o_seg, 2);
+        if (had_tiles) trace<TR>(tr_e, rank, 3, o_seg, 2);
         if (row_valid && page == 0) {
-          const float lse2 = log2f(l) + mprime;
+          const float lse2 = log2f(l) + (rloc - kLog2Fp8Max);  // L_true = L * 2^R / 448
           if (sg.no_split) {
             const int sq = grow / p.h_q, hh = grow % p.h_q;
             p.lse[((int64_t)b * p.h_q + hh) * p.s_q + sq] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
@@ -1063,7 +1087,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
   }
 
-  if ((p.trace & 1) && tid == 128 && part < 128 && blockIdx.y == 0) {
+  if (TR && tid == 128 && part < 128 && blockIdx.y == 0) {
     unsigned long long t;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
     g_part_cycles[(part * 2 + rank) * 4 + 1] = t;
@@ -1079,13 +1103,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
 int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream) {
   const int smem = pairk::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
   const int q_pairs = (prm.M + 127) / 128;
-  pairk::mla_decode_pair_kernel<<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+  if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, knobs that break results
+    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pairk::mla_decode_pair_kernel<true><<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+  } else {
+    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    pairk::mla_decode_pair_kernel<false><<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+  }
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -432,6 +432,52 @@ __device__ __forceinline__ uint32_t cvt_e4m3x2(float a, float b) {
 __device__ __forceinline__ uint32_t cvt_e4m3x4(float a, float b, float c, float d) {
   return cvt_e4m3x2(a, b) | (cvt_e4m3x2(c, d) << 16);
 }
+// packed e4m3x2 <-> f16x2 and f16x2 arithmetic on raw 32-bit registers (low byte <-> low half)
+__device__ __forceinline__ uint32_t e4m3x2_to_f16x2(uint32_t c2) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.e4m3x2 %0, %1;" : "=r"(r) : "h"((uint16_t)c2));
+  return r;
+}
+__device__ __forceinline__ uint32_t f16x2_to_e4m3x2(uint32_t h2) {
+  uint16_t r;
+  asm("cvt.rn.satfinite.e4m3x2.f16x2 %0, %1;" : "=h"(r) : "r"(h2));
+  return r;
+}
+__device__ __forceinline__ uint32_t f16x2_mul(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("mul.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+__device__ __forceinline__ uint32_t f16x2_sub(uint32_t a, uint32_t b) {
+  uint32_t r;
+  asm("sub.rn.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+  return r;
+}
+// two floats -> f16x2 (low half = a)
+__device__ __forceinline__ uint32_t f32x2_to_f16x2(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.f16x2.f32 %0, %2, %1;" : "=r"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ float f16_lo_to_f32(uint32_t h2) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, lo;\n\t}" : "=f"(r) : "r"(h2));
+  return r;
+}
+__device__ __forceinline__ float f16_hi_to_f32(uint32_t h2) {
+  float r;
+  asm("{\n\t.reg .b16 lo, hi;\n\tmov.b32 {lo, hi}, %1;\n\tcvt.f32.f16 %0, hi;\n\t}" : "=f"(r) : "r"(h2));
+  return r;
+}
+// The P operand of P.V under a per-row reference: the page's own e4m3 codes (the reference kernel's codes, relative to
+// the page's row maximum) times the page weight w <= 1 (f16x2), carried as TWO e4m3 terms hi + lo so that the product
+// keeps 8 significant bits (one e4m3 term alone is a different rounding grid: 2^-4 relative noise).
+__device__ __forceinline__ void split_hi_lo(uint32_t code2, uint32_t w_h2, uint32_t& hi2, uint32_t& lo2) {
+  const uint32_t ph = f16x2_mul(e4m3x2_to_f16x2(code2), w_h2);
+  hi2 = f16x2_to_e4m3x2(ph);
+  lo2 = f16x2_to_e4m3x2(f16x2_sub(ph, e4m3x2_to_f16x2(hi2)));
+}
+
 // packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100)
 __device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
   uint64_t d;

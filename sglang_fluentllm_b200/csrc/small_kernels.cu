@@ -20,39 +20,55 @@ namespace b200 {
 static constexpr float FP8_MAX = 448.0f;
 
 // ------------------------------------------------------------------------------------------------
-// a-4  metadata.  Reference: 3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu:8-75 (one warp; the
-// assignment loop is inherently serial over sm parts, so a single lane runs it after a parallel block count).
+// a-4  metadata.  Reference: 3rdparty/flashmla-fp8/csrc/kernels/get_mla_metadata.cu:8-75 (one warp, a serial walk over
+// the sm parts on lane 0 with every operand fetched from global memory inside the loop).  Same integers here; the block
+// counts and lengths are staged in shared memory by the whole CTA, and the walk -- sequential by construction: where a
+// part ends decides where the next one starts -- runs on one lane out of registers, with the next request's block
+// count loaded one step ahead so that no memory latency sits on the loop-carried chain.
 // ------------------------------------------------------------------------------------------------
-__global__ void mla_metadata_kernel(const int32_t* __restrict__ seqlens, int32_t* __restrict__ meta,
-                                    int32_t* __restrict__ num_splits, int batch, int block_n, int fixed_overhead,
-                                    int num_sm_parts) {
-  extern __shared__ int32_t s_blocks[];  // [batch]
+constexpr int kMetaThreads = 128;
+__global__ void __launch_bounds__(kMetaThreads) mla_metadata_kernel(const int32_t* __restrict__ seqlens,
+                                                                    int32_t* __restrict__ meta,
+                                                                    int32_t* __restrict__ num_splits, int batch,
+                                                                    int block_n, int fixed_overhead, int num_sm_parts) {
+  extern __shared__ int32_t s_meta[];  // [batch] block counts, [batch] lengths, [warps] partial totals
+  int32_t* s_blocks = s_meta;
+  int32_t* s_len = s_meta + batch;
+  int32_t* s_part = s_meta + 2 * batch;
   int total = 0;
-  for (int i = threadIdx.x; i < batch; i += 32) {
-    int nb = (seqlens[i] + block_n - 1) / block_n;
+  for (int i = threadIdx.x; i < batch; i += kMetaThreads) {
+    const int len = seqlens[i];
+    const int nb = (len + block_n - 1) / block_n;
     s_blocks[i] = nb;
+    s_len[i] = len;
     total += nb + fixed_overhead;
   }
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  __syncwarp();
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = total;
+  __syncthreads();
   if (threadIdx.x != 0) return;
-  int payload = max((total + num_sm_parts - 1) / num_sm_parts + fixed_overhead, 2 * fixed_overhead);
+  total = 0;
+#pragma unroll
+  for (int w = 0; w < kMetaThreads / 32; ++w) total += s_part[w];
+  const int payload = max((total + num_sm_parts - 1) / num_sm_parts + fixed_overhead, 2 * fixed_overhead);
   int now_idx = 0, now_block = 0, now_split = 0, cum = 0;
+  int nb = batch > 0 ? s_blocks[0] : 0, nb_next = batch > 1 ? s_blocks[1] : 0;  // requests now_idx, now_idx + 1
+  int last_len = 0;                                                             // length of request now_idx - 1
   num_splits[0] = 0;
   for (int i = 0; i < num_sm_parts; ++i) {
-    int32_t* m = meta + i * 8;
-    m[0] = now_idx;
-    m[1] = now_block * block_n;
-    m[4] = now_split;
+    int4 head = make_int4(now_idx, now_block * block_n, 0, 0);
+    const int begin_split = now_split;
     int remain = payload;
     while (now_idx < batch) {
-      int nb = s_blocks[now_idx];
-      int left = nb - now_block;
+      const int left = nb - now_block;
       if (remain >= left + fixed_overhead) {
         cum += now_split + 1;
         num_splits[now_idx + 1] = cum;
         remain -= left + fixed_overhead;
+        last_len = s_len[now_idx];  // consumed at the end of the part at the earliest
         ++now_idx;
+        nb = nb_next;
+        nb_next = now_idx + 1 < batch ? s_blocks[now_idx + 1] : 0;
         now_block = 0;
         now_split = 0;
       } else {
@@ -64,11 +80,11 @@ __global__ void mla_metadata_kernel(const int32_t* __restrict__ seqlens, int32_t
         break;
       }
     }
-    m[2] = now_block > 0 ? now_idx : now_idx - 1;
-    m[3] = now_block > 0 ? now_block * block_n : (now_idx >= 1 ? seqlens[now_idx - 1] : 0);
-    m[5] = 0;
-    m[6] = 0;
-    m[7] = 0;
+    head.z = now_block > 0 ? now_idx : now_idx - 1;
+    head.w = now_block > 0 ? now_block * block_n : last_len;
+    int4* m = reinterpret_cast<int4*>(meta + i * 8);
+    m[0] = head;
+    m[1] = make_int4(begin_split, 0, 0, 0);
   }
 }
 
@@ -382,15 +398,17 @@ int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_coun
 int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
                           int32_t* num_splits, void* stream) {
   B200_CHECK(cache_seqlens && tile_scheduler_metadata && num_splits, "get_metadata: null pointer");
-  B200_CHECK(batch > 0 && num_sm_parts > 0, "get_metadata: batch=%d num_sm_parts=%d must be positive", batch,
-             num_sm_parts);
-  B200_CHECK(batch * 4 <= 200 * 1024, "get_metadata: batch %d too large", batch);
-  const size_t smem = (size_t)batch * 4;
+  // batch == 0 is an IDLE batch (a data-parallel attention rank with no request, flash_api.cpp:27-63 accepts it): every
+  // part then starts at request 0 >= batch, which the decode kernels read as "no work", and num_splits = [0]
+  B200_CHECK(batch >= 0 && num_sm_parts > 0, "get_metadata: batch=%d num_sm_parts=%d", batch, num_sm_parts);
+  B200_CHECK((reinterpret_cast<uintptr_t>(tile_scheduler_metadata) & 15) == 0, "get_metadata: metadata must be 16-byte aligned");
+  B200_CHECK((size_t)batch * 8 <= 200 * 1024, "get_metadata: batch %d too large", batch);
+  const size_t smem = (size_t)batch * 8 + (kMetaThreads / 32) * 4;
   if (smem > 48 * 1024)
     B200_CUDA(cudaFuncSetAttribute(mla_metadata_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  mla_metadata_kernel<<<1, 32, smem, (cudaStream_t)stream>>>(cache_seqlens, tile_scheduler_metadata, num_splits, batch,
-                                                             B200_MLA_PAGE_SIZE, B200_MLA_FIXED_OVERHEAD_BLOCKS,
-                                                             num_sm_parts);
+  mla_metadata_kernel<<<1, kMetaThreads, smem, (cudaStream_t)stream>>>(cache_seqlens, tile_scheduler_metadata, num_splits,
+                                                                       batch, B200_MLA_PAGE_SIZE,
+                                                                       B200_MLA_FIXED_OVERHEAD_BLOCKS, num_sm_parts);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

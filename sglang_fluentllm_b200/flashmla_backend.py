@@ -5,10 +5,12 @@ pool-side classes the backend reads -- ``MLATokenToKVPool`` in the per-token-FP8
 (mem_cache/memory_pool.py:591-882) and ``KVAllocator`` (mem_cache/allocator.py:19-102).
 
 In the reference the backend is imported only when ``is_sm90_supported()`` (model_executor/attn_initializer.py:25-29)
-and inherits its prefill from FlashInferMLAAttnBackend.  Here the class is self-contained, duck-types ``model_runner``
-/ ``forward_batch`` / ``layer`` (so it can be registered in the reference's AttnInitializer -- see INTEGRATION.md -- or
-driven directly by tests and bench.py) and covers DECODE / IDLE / TARGET_VERIFY / DRAFT_EXTEND.  EXTEND (prefill) is
-outside the hot path and raises.
+and inherits its prefill from FlashInferMLAAttnBackend.  Here the class duck-types ``model_runner`` / ``forward_batch``
+/ ``layer`` (so it can be registered in the reference's AttnInitializer -- see INTEGRATION.md -- or driven directly by
+tests and bench.py), has the reference's constructor, and covers DECODE / IDLE / TARGET_VERIFY / DRAFT_EXTEND itself.
+EXTEND / MIXED (prefill) is outside the hot path: it is delegated to a *prefill backend* -- inside the reference that is
+an instance of its FlashInferMLAAttnBackend, built with the same arguments (``set_prefill_backend_factory``; done by
+``install.patch_attention_initializer`` when that class imports) -- and raises when none is registered.
 """
 from __future__ import annotations
 
@@ -21,6 +23,40 @@ import torch
 from . import flash_mla_fp8
 
 PAGE_SIZE = 64  # flashmla_backend.py:25
+
+# ---- the two things the reference's class takes from its surroundings rather than from its arguments ----------------
+_attention_tp_size_getter = None   # reference: sglang.srt.layers.dp_attention.get_attention_tp_size (flashmla_backend.py:11-13,67-69)
+_prefill_backend_factory = None    # reference: the FlashInferMLAAttnBackend base class (flashmla_backend.py:49,59)
+
+
+def set_attention_tp_size_getter(fn) -> None:
+    """Inject ``get_attention_tp_size`` (tests, bench.py, or an embedding runtime); None restores the default lookup."""
+    global _attention_tp_size_getter
+    _attention_tp_size_getter = fn
+
+
+def get_attention_tp_size() -> int:
+    """The reference resolves heads per rank with dp_attention.get_attention_tp_size() (flashmla_backend.py:67-69), so
+    ``FlashMLABackend(model_runner)`` -- the call attn_initializer.py:395 makes -- must work under TP > 1 without an
+    extra argument: injected getter first, then the reference's own function when sglang is importable, then 1."""
+    if _attention_tp_size_getter is not None:
+        return int(_attention_tp_size_getter())
+    import sys
+    dp = sys.modules.get("sglang.srt.layers.dp_attention")
+    if dp is None:
+        try:
+            import importlib
+            dp = importlib.import_module("sglang.srt.layers.dp_attention")
+        except Exception:
+            return 1
+    return int(dp.get_attention_tp_size())
+
+
+def set_prefill_backend_factory(fn) -> None:
+    """``fn(model_runner, skip_prefill, kv_indptr_buf, q_indptr_decode_buf)`` -> an object with the AttentionBackend
+    methods that serves EXTEND / MIXED batches (the reference's FlashInferMLAAttnBackend); None unregisters."""
+    global _prefill_backend_factory
+    _prefill_backend_factory = fn
 
 
 class ForwardMode(IntEnum):
@@ -228,14 +264,19 @@ class FlashMLADecodeMetadata:
 
 
 class FlashMLABackend(AttentionBackend):
-    """flashmla_backend.py:49-408.  Reads from ``model_runner``: model_config.{scaling, num_attention_heads,
-    kv_lora_rank, qk_nope_head_dim, qk_rope_head_dim, v_head_dim, context_len}, server_args.{speculative_algorithm,
-    speculative_num_draft_tokens}, kv_cache_dtype, kv_cache_quant_method, kv_allocator, dtype; the attention TP size
-    comes from ``attn_tp_size`` (reference: dp_attention.get_attention_tp_size())."""
+    """flashmla_backend.py:49-408, same constructor (:50-57).  Reads from ``model_runner``: model_config.{scaling,
+    num_attention_heads, kv_lora_rank, qk_nope_head_dim, qk_rope_head_dim, v_head_dim, context_len},
+    server_args.{speculative_algorithm, speculative_num_draft_tokens}, kv_cache_dtype, kv_cache_quant_method,
+    kv_allocator, dtype; heads per rank = num_attention_heads // get_attention_tp_size() (:67-69)."""
 
     def __init__(self, model_runner, skip_prefill: bool = False, kv_indptr_buf=None, q_indptr_decode_buf=None,
-                 multi_step_seqlen_incr: int = 0, attn_tp_size: int = 1):
+                 multi_step_seqlen_incr: int = 0):
         cfg, sa = model_runner.model_config, model_runner.server_args
+        attn_tp_size = get_attention_tp_size()
+        # EXTEND / MIXED batches: the reference's base class (:59 super().__init__) -- here a delegate, when registered
+        self.prefill_backend = None
+        if _prefill_backend_factory is not None and not skip_prefill:
+            self.prefill_backend = _prefill_backend_factory(model_runner, skip_prefill, kv_indptr_buf, q_indptr_decode_buf)
         self.softmax_scale = cfg.scaling
         self.draft_token_num = 0 if getattr(sa, "speculative_algorithm", None) is None else sa.speculative_num_draft_tokens
         self.multi_step_seqlen_incr = multi_step_seqlen_incr
@@ -267,6 +308,8 @@ class FlashMLABackend(AttentionBackend):
     # ------------------------------------------------------------------ attention calls
     def _attend(self, q, layer, forward_batch, cache_seqlens):
         bs = forward_batch.batch_size
+        if bs == 0:  # IDLE batch of a data-parallel attention rank: nothing to attend, an empty [0, h * 512] result
+            return q.new_empty((0, layer.tp_q_head_num * layer.v_head_dim))
         k_cache = forward_batch.token_to_kv_pool.get_key_buffer(layer.layer_id)
         assert layer.tp_q_head_num == self.num_q_heads, f"{layer.tp_q_head_num=} != {self.num_q_heads=}"
         reshape_q = q.view(bs, -1, self.num_q_heads, layer.head_dim)
@@ -288,6 +331,8 @@ class FlashMLABackend(AttentionBackend):
     def _attend_quantized(self, q_nope, q_scale, q_rope, layer, forward_batch, cache_seqlens):
         """The attention call on an already quantised Q (flashmla_backend.py:207-224)."""
         bs = forward_batch.batch_size
+        if bs == 0:
+            return q_rope.new_empty((0, layer.tp_q_head_num * layer.v_head_dim))
         mod = self.get_flash_mla_module(q_nope.numel() // (bs * self.kv_lora_rank))
         k_cache_lora, k_scale, k_cache_rope = forward_batch.token_to_kv_pool.get_key_buffer(layer.layer_id)
         q_nope = q_nope.view(bs, -1, self.num_q_heads, self.kv_lora_rank)
@@ -325,8 +370,12 @@ class FlashMLABackend(AttentionBackend):
         """flashmla_backend.py:87-176: TARGET_VERIFY / DRAFT_EXTEND run the decode kernel with s_q = draft tokens."""
         mode = forward_batch.forward_mode
         if not (mode.is_target_verify() or mode.is_draft_extend()):
-            raise NotImplementedError("prefill (EXTEND) is outside the B200 decode hot path; the reference routes it to "
-                                      "FlashInferMLAAttnBackend (flashmla_backend.py:100-104)")
+            # flashmla_backend.py:100-104: prefill of the base and draft models stays on the flashinfer MLA backend
+            if self.prefill_backend is not None:
+                return self.prefill_backend.forward_extend(q, k, v, layer, forward_batch, save_kv_cache, q_pe, k_pe)
+            raise NotImplementedError("prefill (EXTEND) is outside the B200 decode hot path and no prefill backend is "
+                                      "registered (flashmla_backend.set_prefill_backend_factory); the reference routes "
+                                      "it to FlashInferMLAAttnBackend (flashmla_backend.py:100-104)")
         if k is not None:
             assert v is not None
             if save_kv_cache:
@@ -349,7 +398,12 @@ class FlashMLABackend(AttentionBackend):
         return self.get_flash_mla_module(m).get_mla_metadata(lens.to(torch.int32).contiguous(), m, 1)
 
     def init_forward_metadata(self, forward_batch):
-        """flashmla_backend.py:258-290."""
+        """flashmla_backend.py:258-290 (other modes go to the base class, :289-290)."""
+        mode = forward_batch.forward_mode
+        if not (mode.is_decode_or_idle() or mode.is_target_verify() or mode.is_draft_extend()):
+            if self.prefill_backend is not None:
+                return self.prefill_backend.init_forward_metadata(forward_batch)
+            raise RuntimeError(f"Not supported forward mode: {mode} (no prefill backend registered)")
         block_table = self.kv_allocator.req_to_page[forward_batch.req_pool_indices]
         mla_metadata, num_splits = self._metadata(forward_batch.seq_lens, forward_batch.forward_mode)
         self.forward_metadata = FlashMLADecodeMetadata(mla_metadata, num_splits, block_table)
@@ -396,32 +450,49 @@ class FlashMLABackend(AttentionBackend):
 
 
 class FlashMLAMultiStepDecodeBackend:
-    """flashmla_backend.py:411-477: one FlashMLABackend per speculative draft step, step i attending over
-    seq_lens + i."""
+    """flashmla_backend.py:411-477: one FlashMLABackend per speculative draft step, constructed as
+    ``FlashMLAMultiStepDecodeBackend(draft_model_runner, speculative_num_steps)``
+    (speculative/base_spec_worker.py:238-240).  Step i attends over ``seq_lens + i + 1`` (:418: the draft token the
+    step itself just wrote is part of its context); metadata is prepared for the first ``spec_num_steps - 1`` steps
+    (common_template, :424-433).
 
-    def __init__(self, model_runner, topk: int, speculative_num_steps: int, attn_tp_size: int = 1):
-        if topk > 1:
-            raise ValueError("Currently FlashMLA only supports topk=1 for speculative decoding")
-        self.topk, self.speculative_num_steps = topk, speculative_num_steps
-        self.attn_backends = [FlashMLABackend(model_runner, skip_prefill=True, multi_step_seqlen_incr=i,
-                                              attn_tp_size=attn_tp_size) for i in range(speculative_num_steps)]
+    The reference's ``init_cuda_graph_state`` / ``...capture_cuda_graph`` read ``self.speculative_num_steps`` and
+    ``self.topk`` (:444,454), which its ``__init__`` never sets; both names are defined here (topk = 1, the only value
+    the FlashMLA draft path supports) so those methods run."""
+
+    def __init__(self, model_runner, spec_num_steps: int):
+        self.spec_num_steps = self.speculative_num_steps = spec_num_steps
+        self.topk = 1
+        self.attn_backends = [FlashMLABackend(model_runner=model_runner, multi_step_seqlen_incr=i + 1, skip_prefill=True)
+                              for i in range(spec_num_steps)]
+
+    def common_template(self, forward_batch, call_fn):
+        assert forward_batch.spec_info is not None
+        for i in range(self.spec_num_steps - 1):
+            call_fn(i, forward_batch)
 
     def init_forward_metadata(self, forward_batch):
-        for b in self.attn_backends[: self.speculative_num_steps - 1]:
-            b.init_forward_metadata(forward_batch)
+        self.common_template(forward_batch, lambda i, fb: self.attn_backends[i].init_forward_metadata(fb))
 
-    def init_cuda_graph_state(self, max_bs: int):
+    def init_cuda_graph_state(self, max_bs: int, max_num_tokens: Optional[int] = None):
         for b in self.attn_backends:
             b.init_cuda_graph_state(max_bs, block_kv_indices=None)
 
     def init_forward_metadata_capture_cuda_graph(self, forward_batch):
-        for b in self.attn_backends[: self.speculative_num_steps]:
-            b.init_forward_metadata_capture_cuda_graph(forward_batch.batch_size, forward_batch.batch_size,
-                                                       forward_batch.req_pool_indices, forward_batch.seq_lens,
-                                                       ForwardMode.DECODE, forward_batch.spec_info)
+        def call_fn(i, fb):
+            self.attn_backends[i].init_forward_metadata_capture_cuda_graph(
+                fb.batch_size, fb.batch_size * self.topk, fb.req_pool_indices, fb.seq_lens,
+                forward_mode=ForwardMode.DECODE, spec_info=fb.spec_info)
 
-    def init_forward_metadata_replay_cuda_graph(self, forward_batch, bs):
-        for b in self.attn_backends[: self.speculative_num_steps]:
-            b.init_forward_metadata_replay_cuda_graph(bs, forward_batch.req_pool_indices, forward_batch.seq_lens,
-                                                      getattr(forward_batch, "seq_lens_sum", 0), ForwardMode.DECODE,
-                                                      forward_batch.spec_info, seq_lens_cpu=None)
+        self.common_template(forward_batch, call_fn)
+
+    def init_forward_metadata_replay_cuda_graph(self, forward_batch, bs: int):
+        def call_fn(i, fb):
+            self.attn_backends[i].init_forward_metadata_replay_cuda_graph(
+                bs, fb.req_pool_indices, fb.seq_lens, seq_lens_sum=-1, forward_mode=ForwardMode.DECODE,
+                spec_info=fb.spec_info, seq_lens_cpu=None)
+
+        self.common_template(forward_batch, call_fn)
+
+    def get_cuda_graph_seq_len_fill_value(self):
+        return 1

@@ -29,7 +29,7 @@ def build(force: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     text = open(SRC).read()
     cut = text.index("\nusing namespace b200;\n")          # the C-ABI entry points (host launchers) start here
-    unit = "\n".join(["#undef __shared__", "#define __shared__",   # `extern __shared__ int32_t s_blocks[]`
+    unit = "\n".join(["#undef __shared__", "#define __shared__",   # `extern __shared__ int32_t s_meta[]`
                       '#line 1 "%s"' % SRC, text[:cut], '#include "%s"' % os.path.join(HERE, "driver.cpp"), ""])
     cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
     cmd = ["g++", "-std=c++20", "-O1", "-ffp-contract=off", "-fPIC", "-shared", "-pthread", "-w", "-x", "c++", "-",

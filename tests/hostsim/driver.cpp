@@ -3,14 +3,14 @@
 #include "../../oracle/ref_build/shim/ref_shim_impl.inc"
 
 namespace b200 {
-int32_t s_blocks[1 << 20];  // mla_metadata_kernel's dynamic shared memory
+int32_t s_meta[1 << 20];  // mla_metadata_kernel's dynamic shared memory
 }
 using namespace b200;
 
 extern "C" {
 
 int host_mla_get_metadata(const int32_t* seqlens, int batch, int num_sm_parts, int32_t* meta, int32_t* num_splits) {
-  refshim::run_grid(1, 32, [&] {
+  refshim::run_grid(1, kMetaThreads, [&] {
     mla_metadata_kernel(seqlens, meta, num_splits, batch, B200_MLA_PAGE_SIZE, B200_MLA_FIXED_OVERHEAD_BLOCKS, num_sm_parts);
   });
   return 0;

@@ -6,10 +6,11 @@ Tolerances
     bit-exact.
   * block-FP8 GEMM: the reference's criterion, calc_diff < 1e-3 (3rdparty/deep_gemm/tests/test_core.py:71-72), and
     norm-relative < 3e-3 against the fp32 oracle (bf16 output rounding is ~1.7e-3).
-  * MLA decode: lse (no FP8-P involved) to 1e-3; out within the reference's own criterion rel < 5e-2 against fp32
-    attention (tests/test_flash_mla_ckv_fp8_per_token.py:32-39,119-120) -- measured ~2.2e-2, which is the e4m3
-    rounding noise of P on zero-mean V and equals the distance between the reference-faithful page-wise recurrence
-    and fp32 attention (oracle/mla.py); < 3.5e-2 against that faithful restatement.  See DESIGN.md "Numerics".
+  * MLA decode: north_star's 1e-2 relative against the reference-faithful page-wise FP8-P recurrence (oracle/mla.py
+    ::flash_mla_ckv_fp8_per_token, splitkv_mla.cu:377-458) -- measured ~1e-3: the kernels produce the reference's own
+    per-page e4m3 codes of P and carry the page weight as an e4m3 hi + lo pair; lse to 1e-3; and the reference's own
+    criterion rel < 5e-2 against fp32 attention (tests/test_flash_mla_ckv_fp8_per_token.py:32-39,119-120; ~2e-2 is the
+    e4m3 noise of P on zero-mean V, common to the reference and to us).  See DESIGN.md "Numerics".
 """
 import ctypes
 
@@ -271,7 +272,9 @@ def test_mla_decode_vs_oracles(mods, name, b, h, s_q, seqlens, causal):
     assert np.allclose(lse, sl, rtol=1e-3, atol=1e-3)
     assert np.allclose(lse, fl, rtol=1e-3, atol=1e-3)
     assert rel(out, so) < 5e-2          # the reference's own pass criterion
-    assert rel(out, fo) < 3.5e-2        # vs the reference-faithful FP8-P recurrence
+    assert rel(out, fo) < 1e-2, rel(out, fo)   # north_star tolerance vs the reference-faithful FP8-P recurrence
+    frow = np.linalg.norm(out - fo, axis=-1) / np.maximum(np.linalg.norm(fo, axis=-1), 1e-20)
+    assert frow.max() < 2e-2, frow.max()       # and no single (request, head) row far off it
     # per-row check: no single (request, head) row may be wrong while the norm hides it
     row_err = np.linalg.norm(out - so, axis=-1) / np.maximum(np.linalg.norm(so, axis=-1), 1e-20)
     assert row_err.max() < 0.2
@@ -358,6 +361,28 @@ def test_mla_pair_full_size_properties(mods):
         logits = (qn @ kn.t() + qr @ kr.t()) * 576 ** -0.5
         assert np.allclose(lse1[i, :, 0], torch.logsumexp(logits, dim=-1).cpu().numpy(), rtol=1e-3, atol=1e-3)
         assert rel(out1[i, 0], (torch.softmax(logits, -1) @ kn).cpu().numpy()) < 5e-2
+
+
+FULL_SIZE = [
+    ("cfg2-v2lite", 128, 4096, 16, 1, (0, 41, 127)),
+    ("metric-v3", 128, 4096, 128, 1, (0, 77)),
+    ("cfg4-tp8-per-gpu", 256, 8192, 16, 1, (3, 255)),
+    ("cfg5-mtp", 64, 4096, 16, 4, (0, 63)),
+]
+
+
+@pytest.mark.parametrize("name,b,seq,h,s_q,sample", FULL_SIZE, ids=[c[0] for c in FULL_SIZE])
+def test_mla_full_size_vs_faithful_oracle(mods, name, b, seq, h, s_q, sample):
+    """BASELINE.json shapes at full size: sampled requests against the reference-faithful recurrence (with the real
+    scheduler metadata, so split requests go through the fp32 partials and the combine) at north_star's 1e-2."""
+    fm = mods[1]
+    sl = [seq] * b if s_q == 1 else [seq - 7 * (i % 5) for i in range(b)]
+    c = make_case(fm, b, h, s_q, sl, nan_pad=False)
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, s_q > 1)
+    fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=s_q > 1, only_requests=set(sample))
+    for i in sample:
+        assert rel(out[i], fo[i]) < 1e-2, (i, rel(out[i], fo[i]))
+        assert np.allclose(lse[i], fl[i], rtol=1e-3, atol=1e-3)
 
 
 def test_mla_decode_low_noise_input_is_tight(mods):
