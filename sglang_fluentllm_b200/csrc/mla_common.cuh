@@ -39,7 +39,6 @@ struct MlaParams {
   int pf_tiles;  // pair kernel: L2 prefetch distance of the K pages, in 128-token tiles (>= 2)
   int q_pf_tiles;  // pair kernel: the next request's Q is prefetched into L2 this many tiles before the current one ends
   int ks_ahead;  // pair kernel: k scales are loaded this many tiles ahead of the softmax (1 .. kKsAhead)
-  int epi_mode;  // pair kernel epilogue staging: 1 = warp-local (default), 0 = group-wide with 128-thread barriers
   int trace;  // diagnostic: pair kernel records clock64 timestamps of its pipeline events (B200_MLA_TRACE=1)
 };
 

@@ -632,8 +632,6 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.k_lora_base = (const uint8_t*)k_lora;
   prm.k_rope_base = (const uint8_t*)k_rope;
 
-  static const int epi_mode = getenv("B200_MLA_EPI") ? atoi(getenv("B200_MLA_EPI")) : 1;  // pair kernel epilogue staging (A/B knob)
-  prm.epi_mode = epi_mode;
   static const int q_pf = getenv("B200_MLA_QPF") ? atoi(getenv("B200_MLA_QPF")) : 6;
   prm.q_pf_tiles = q_pf < 1 ? 1 : q_pf;
   static const int ks_ahead = getenv("B200_MLA_KSAHEAD") ? atoi(getenv("B200_MLA_KSAHEAD")) : 6;
@@ -641,7 +639,9 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
 
   int rc;
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
-  if (M > 64 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
+  // M above this goes to the CTA-pair kernel (A/B knob; 32 < M <= 64 fills one CTA of the pair)
+  static const int pair_min_m = getenv("B200_MLA_PAIR_MIN_M") ? atoi(getenv("B200_MLA_PAIR_MIN_M")) : 64;
+  if (M > pair_min_m && M > 32 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 32) rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else rc = launch_mla<64, 32>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);

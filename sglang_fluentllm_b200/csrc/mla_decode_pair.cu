@@ -24,39 +24,46 @@
 //   groups of four warps ping-pong over the tiles (group = tile parity); a tile's P depends on its predecessor only
 //   through R, so the groups meet at a per-tile hand-off (fin) and a version counter; a group that computed under a
 //   reference that has since moved recomputes its second pass.  Both passes over S are compact 16-column loops (TMEM
-//   loads double-buffered, packed fp32x2 / f16x2 arithmetic, codes written straight into the swizzled P tiles).
+//   loads double-buffered, packed fp32x2 / f16x2 arithmetic, codes written straight into the swizzled P tiles); the
+//   first pass writes y back over S in TMEM, so the second one neither recomputes it nor needs the mask.
 //
-//   Warp roles per CTA (384 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
+//   Warp roles per CTA (512 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
 //   and the k-scale ring; warp 2 = V producer; leader CTA: warp 1 issues every Q.K^T and warp 3 every P.V (two
 //   independent instruction streams into the in-order tensor pipe; Q.K^T runs up to four tiles ahead), other CTA:
-//   warp 1 relays the local P / O hand-offs to the leader; warp 1 also owns the TMEM allocation; warps 4-11 =
-//   softmax / correction / epilogue.
+//   warp 1 relays the local P / O hand-offs to the leader; warp 1 also owns the TMEM allocation; warps 4-15 = three
+//   softmax / correction / epilogue groups (group = tile index mod 3; each owns one P pair).
 //   TMEM per CTA: 4 S tiles (4 x 64 columns) + O (2 x 128 columns) = 512 columns.
-//   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, 2 V stages x 32 KB, 2 P pairs (hi, lo) x 2 x 8 KB
-//   (also the epilogue's staging tile), k-scale ring 4 KB, barriers / row state / log2 and reciprocal scales 6 KB.
+//   Shared memory per CTA (226 KB): Q 40 KB, 2 K stages x 40 KB, a ring of 3 V units x 16 KB (one unit = one 256-dim
+//   half of the output for the 128 tokens of a tile), 3 P pairs (hi, lo) x 2 x 8 KB (also the epilogue's staging), k-scale
+//   ring 3 KB, barriers / row state / log2 and reciprocal scales 7 KB.
 #include <string.h>
+
+#include <type_traits>
 
 #include "mla_common.cuh"
 
 namespace b200 {
 namespace pairk {
 
-constexpr int kKStages = 2, kVStages = 2;
-constexpr int kKsStages = 8, kKsAhead = 6;  // k-scale ring: 512 B per tile, loaded kKsAhead tiles ahead of the softmax
+constexpr int kKStages = 2;
+constexpr int kVUnits = 3;                  // V ring: unit u = 2 * tile + d-half, slot u % kVUnits
+constexpr int kGroups = 3;                  // softmax groups of four warps; tile g belongs to group g % kGroups
+constexpr int kKsStages = 6, kKsAheadMax = 4;  // k-scale ring: 512 B per tile, loaded ahead of the softmax
 constexpr int kQBytes = 64 * 640;          // 4 nope chunks [64 rows x 128 B] + rope [64 x 128 B]
 constexpr int kKStageBytes = 64 * 640;     // this CTA's page of the tile, same layout
-constexpr int kVStageBytes = 2 * 128 * 128;  // [2 d-halves][128 tokens][128 B]
+constexpr int kVUnitBytes = 128 * 128;       // [128 tokens][128 B]: this CTA's 128 of the 256 output dims of one d-half
 constexpr int kPBytes = 64 * 128;          // [64 q rows][128 tokens] e4m3, K-major SW128
 constexpr int kOffQ = 0;
 constexpr int kOffK = kOffQ + kQBytes;
 constexpr int kOffV = kOffK + kKStages * kKStageBytes;
-constexpr int kOffP = kOffV + kVStages * kVStageBytes;
-constexpr int kPPairs = 2;                           // P tiles come in (hi, lo) pairs, one pair per softmax group (tile parity)
-constexpr int kOffKs = kOffP + kPPairs * 2 * kPBytes;  // k-scale ring: [kKsStages][128] f32; the four P tiles (32 KB)
-                                                     // double as the epilogue's staging tile
+constexpr int kOffP = kOffV + kVUnits * kVUnitBytes;
+constexpr int kPPairs = kGroups;                     // P tiles come in (hi, lo) pairs, one pair per softmax group
+constexpr int kOffKs = kOffP + kPPairs * 2 * kPBytes;  // k-scale ring: [kKsStages][128] f32; a group's P pair (16 KB)
+                                                     // doubles as its epilogue staging tile
 constexpr int kOffSmall = kOffKs + kKsStages * 512;
-constexpr int kTotal = kOffSmall + 6144;
-constexpr int kSmThreads = 256;                      // softmax group
+constexpr int kSmallBytes = 7168;
+constexpr int kTotal = kOffSmall + kSmallBytes;
+constexpr int kSmThreads = 128 * kGroups;            // all softmax groups
 constexpr int kSBufs = 4;                            // S tiles in TMEM: Q.K^T may run kSBufs - 1 tiles ahead of P.V
 constexpr uint32_t kColS = 0, kColO = kSBufs * 64, kTmemCols = 512;
 static_assert(kColO + 256 <= kTmemCols, "TMEM budget");
@@ -64,10 +71,12 @@ static_assert(kOffK % 1024 == 0 && kOffV % 1024 == 0 && kOffP % 1024 == 0 && kOf
 
 struct Small {
   uint64_t k_full[kKStages], k_empty[kKStages];
-  uint64_t v_land[kVStages], v_empty[kVStages];
+  uint64_t v_land[kVUnits], v_empty[kVUnits];
   uint64_t ks_full[kKsStages], ks_empty[kKsStages];
   uint64_t q_full, q_empty;
-  uint64_t s_full[kSBufs], s_free[kSBufs];     // s_free(g): P.V of tile g retired -> S tile g % kSBufs may be overwritten
+  uint64_t s_full[kSBufs], s_free[kSBufs];     // s_free(g): P.V of tile g retired
+  uint64_t s_done[kSBufs];                     // both CTAs' softmax groups are through with S tile g % kSBufs: Q.K^T may overwrite it
+  uint64_t v_peer[kVUnits];                    // leader: the peer CTA's V unit has landed (forwarded by its relay warp)
   uint64_t p_full[kPPairs], p_free[kPPairs];   // per P pair (tile parity)
   uint64_t pv_done, o_ready, o_free;
   uint64_t p_relay[kPPairs], o_relay;  // non-leader CTA: local hand-off points forwarded to the leader by its warp 1
@@ -75,12 +84,12 @@ struct Small {
   uint32_t tmem_base;
   uint32_t version;              // bumped by every reference move
   uint32_t k_issued;             // tiles whose K page this CTA's producer has issued (orders the V re-read behind it)
-  uint32_t trig[2][3];
+  uint32_t trig[kGroups][3];
   float st_ref[64];              // per-row reference exponent R (log2): O and L are in units of 2^R / 448
-  float red1[2][2][64], lred[2][4][64];  // page maxima exchange; lred: row-sum exchange, double-buffered by request parity
-  alignas(16) float lkrk[2][256];  // per softmax group: log2(k_scale) [128] and 1 / k_scale [128] of the tile it works on
+  float lred[2][2 * kGroups][64];  // row-sum exchange, double-buffered by request parity
+  alignas(16) float lkrk[kGroups][256];  // per softmax group: log2(k_scale) [128], 1 / k_scale [128] of the tile it works on
 };
-static_assert(sizeof(Small) <= 6144, "Small too large");
+static_assert(sizeof(Small) <= kSmallBytes, "Small too large");
 static_assert(kTotal + 1024 <= 232448, "over the 227 KB shared-memory limit");
 
 // Pipeline trace of part 0 (diagnostic): [rank][role: 0 producer, 1 mma, 2 softmax warp 4, 3 epilogue (indexed by
@@ -130,7 +139,7 @@ struct BtWindow {
 
 
 template <bool TR>
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
     mla_decode_pair_kernel(const __grid_constant__ MlaParams p) {
   extern __shared__ uint8_t smem_raw[];
   // round up to 1024 B by pointer arithmetic (an integer round trip would demote every access to generic LD / ST)
@@ -169,7 +178,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       mbar_init(&sm.k_full[i], 2);  // one expect_tx arrival per CTA of the pair (leader's copy is the live one)
       mbar_init(&sm.k_empty[i], 1);
     }
-    for (int i = 0; i < kVStages; ++i) {
+    for (int i = 0; i < kVUnits; ++i) {
       mbar_init(&sm.v_land[i], 1);
       mbar_init(&sm.v_empty[i], 1);
     }
@@ -182,7 +191,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     for (int i = 0; i < kSBufs; ++i) {
       mbar_init(&sm.s_full[i], 1);
       mbar_init(&sm.s_free[i], 1);
+      mbar_init(&sm.s_done[i], 5);   // the four warps of the leader's softmax group + the peer's relay
     }
+    for (int i = 0; i < kVUnits; ++i) mbar_init(&sm.v_peer[i], 1);
     for (int i = 0; i < kPPairs; ++i) {
       mbar_init(&sm.p_full[i], 5);   // the four warps of the leader's softmax group + the peer's relay
       mbar_init(&sm.p_relay[i], 4);
@@ -191,9 +202,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     for (int i = 0; i < 2; ++i) mbar_init(&sm.fin[i], 4);
     mbar_init(&sm.pv_done, 1);
     mbar_init(&sm.o_ready, 1);
-    mbar_init(&sm.o_free, 5);   // the four warps of the leader's epilogue group + the peer's relay
-    mbar_init(&sm.o_relay, 4);
-    for (int i = 0; i < 3; ++i) sm.trig[0][i] = sm.trig[1][i] = 0;
+    mbar_init(&sm.o_free, 4 * kGroups + 1);   // the leader's softmax warps (all groups write a request out) + the peer's relay
+    mbar_init(&sm.o_relay, 4 * kGroups);
+    for (int i = 0; i < 3 * kGroups; ++i) (&sm.trig[0][0])[i] = 0;
     sm.version = 0;
     sm.k_issued = 0;
     fence_mbar_init();
@@ -219,7 +230,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 
     uint32_t g = 0, seg_i = 0;
     const int pf = min(p.pf_tiles, 14);  // the block-table window holds 32 entries past the current tile
-    const int ks_ahead = p.ks_ahead;
+    const int ks_ahead = min(p.ks_ahead, kKsAheadMax);
     // Everything a request's first loads depend on is fetched while the previous request runs (its lengths, its split
     // index, the first 64 entries of its block-table row): with no L1, the four dependent L2 round trips otherwise sit
     // between the last K page of one request and the first of the next.
@@ -400,15 +411,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       ks_done = ks_next;
     }
   } else if (TR && warp == 3 && rank == 1 && part == 0 && blockIdx.y == 0) {
-    // diagnostic: when each V stage lands in the non-leader CTA
+    // diagnostic: when the second V unit of each tile lands in the non-leader CTA
     for (uint32_t g = 0; g < 40; ++g) {
-      mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);
+      mbar_wait(&sm.v_land[(2 * g + 1) % kVUnits], ((2 * g + 1) / kVUnits) & 1);
       trace<TR>(lane == 0, rank, 0, g, 3);
     }
   } else if (warp == 2) {
     // ============================== V producer (both CTAs) ==============================
-    // Its own warp: the V stage of tile t frees when P.V of tile t-2 retires, which must not hold back the K stream
-    // (Q.K^T runs ahead of P.V).
+    // Its own warp: a V unit frees when the P.V products that read it retire, which must not hold back the K stream
+    // (Q.K^T runs ahead of P.V).  A unit is one 256-dim half of the output (d-half j) for the 128 tokens of a tile:
+    // unit u = 2 * tile + j lives in slot u % 3, so the ring holds a tile and a half and the second half of tile g + 1
+    // is refilled while P.V of tile g still reads the other half.
     const uint64_t pol_last_use = policy_evict_first();
     uint32_t g = 0;
     int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
@@ -423,42 +436,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       const int32_t* bt = p.block_table + (int64_t)b * p.block_table_stride;
       BtWindow bw;
       bw.init(bt, sg.start_block, sg.end_block, lane);
-      // both pages of tile t, this CTA's two 128-dim output slices (+ the tile's k scales) -> V stage (local barrier);
-      // these bytes were just streamed through L2 as K by this CTA or its peer
+      // both pages of tile t, this CTA's 128-dim slice of d-half j -> V unit (local barrier); these bytes were just
+      // streamed through L2 as K by this CTA or its peer
       auto load_v = [&](int t, uint32_t gt) {
-        const uint32_t st = gt % kVStages;
         trace<TR>(tr, rank, 0, gt, 1);
-        mbar_wait(&sm.v_empty[st], ((gt / kVStages) & 1) ^ 1);
-        // behind this tile's K issue: the same bytes then come out of L2 (or merge with the K fetch in flight) instead
-        // of competing with the K and Q loads for HBM at a request's start
-        for (uint32_t spins = 0; !(TR && (p.trace & 32)) && ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
-          if (spins > B200_WAIT_SPIN_LIMIT) __trap();
-          __nanosleep(64);
-        }
-        trace<TR>(tr, rank, 0, gt, 2);
         const int blk0 = sg.start_block + 2 * t;
         const int npages = min(2, sg.end_block - blk0);
         const int tok0 = bw.get(blk0) * kPage;
         const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
-        uint8_t* stage = s_v + st * kVStageBytes;
-        if (TR && (p.trace & 8)) {  // diagnostic (wrong results): no V traffic at all
-          if (elect_one()) mbar_arrive(&sm.v_land[st]);
-          __syncwarp();
-          return;
-        }
-        if (elect_one()) {
-          mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * (2 * 8192));
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            tma_load_2d_hint(stage + j * 16384, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
-          if (npages > 1) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tma_load_2d_hint(stage + j * 16384 + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1,
-                               pol_last_use);
+#pragma unroll 1
+        for (int j = 0; j < 2; ++j) {
+          const uint32_t u = 2 * gt + (uint32_t)j, st = u % kVUnits;
+          mbar_wait(&sm.v_empty[st], ((u / kVUnits) & 1) ^ 1);
+          if (j == 0) {
+            // behind this tile's K issue: the same bytes then come out of L2 (or merge with the K fetch in flight)
+            // instead of competing with the K and Q loads for HBM at a request's start
+            for (uint32_t spins = 0; !(TR && (p.trace & 32)) && ld_shared_volatile_u32(&sm.k_issued) <= gt; ++spins) {
+              if (spins > B200_WAIT_SPIN_LIMIT) __trap();
+              __nanosleep(64);
+            }
+            trace<TR>(tr, rank, 0, gt, 2);
           }
+          uint8_t* unit = s_v + st * kVUnitBytes;
+          if (TR && (p.trace & 8)) {  // diagnostic (wrong results): no V traffic at all
+            if (elect_one()) mbar_arrive(&sm.v_land[st]);
+            __syncwarp();
+            continue;
+          }
+          if (elect_one()) {
+            mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * 8192);
+            tma_load_2d_hint(unit, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
+            if (npages > 1)
+              tma_load_2d_hint(unit + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1, pol_last_use);
+          }
+          __syncwarp();
         }
-        __syncwarp();
       };
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
         bw.advance_to(sg.start_block + 2 * t, lane);
@@ -469,8 +481,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     // ============================== UMMA issuers (leader CTA) ==============================
     // warp 1 issues every Q.K^T, warp 3 every P.V: two independent instruction streams into the one in-order tensor
     // pipe, so a Q.K^T waiting for its K page never holds back a P.V whose P is published (and vice versa; a single
-    // issuer needs either a fixed interleave or polling, and both cost throughput).  Q.K^T of tile g waits for P.V of
-    // tile g - kSBufs to retire (s_free): S tile g % kSBufs has then been read by its softmax group.
+    // issuer needs either a fixed interleave or polling, and both cost throughput).  Q.K^T of tile g waits until the
+    // softmax groups of both CTAs are through with tile g - kSBufs (s_done: S tile g % kSBufs is dead as soon as its P
+    // is published, long before that P.V retires).
     constexpr uint32_t idesc_qk8 = make_idesc(FMT_E4M3, FMT_E4M3, 0, 0, 128, 128);
     constexpr uint32_t idesc_qk16 = make_idesc(FMT_BF16, FMT_BF16, 0, 0, 128, 128);
     constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 0, 1, 128, 256);
@@ -492,7 +505,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         mbar_wait_cluster(&sm.q_full, seg & 1);
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
           const uint32_t kst = g % kKStages, sb = g % kSBufs;
-          if (g >= (uint32_t)kSBufs) mbar_wait(&sm.s_free[sb], ((g / kSBufs) & 1) ^ 1);  // P.V of tile g - kSBufs retired
+          if (g >= (uint32_t)kSBufs) mbar_wait_cluster(&sm.s_done[sb], ((g / kSBufs) & 1) ^ 1);  // S tile g - kSBufs consumed
           mbar_wait(&sm.ks_full[g % kKsStages], (g / kKsStages) & 1);  // s_full then vouches for the k scales too
           mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
           trace<TR>(tr, rank, 1, g, 0);
@@ -519,26 +532,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
       } else {
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          const uint32_t pp = g & 1, vst = g % kVStages;
-          mbar_wait_cluster(&sm.p_full[pp], (g >> 1) & 1);  // P written in both CTAs, V landed in the peer
-          mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);        // V landed here
+          const uint32_t pp = g % kPPairs;
+          mbar_wait_cluster(&sm.p_full[pp], (g / kPPairs) & 1);  // P written in both CTAs
           if (t == 0 && seg > 0) mbar_wait_cluster(&sm.o_free, (seg - 1) & 1);
           trace<TR>(tr, rank, 1, g, 2);
           tc_fence_after();
           const int tile_start = (sg.start_block + 2 * t) * kPage;
           const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
-          if (elect_one()) {
 #pragma unroll
-            for (int hl = 0; hl < 2; ++hl)  // P = P_hi + P_lo
+          for (int j = 0; j < 2; ++j) {  // d-half by d-half: the first V unit is released while the second is read
+            const uint32_t u = 2 * g + (uint32_t)j, vst = u % kVUnits;
+            mbar_wait(&sm.v_land[vst], (u / kVUnits) & 1);          // V unit landed here
+            mbar_wait_cluster(&sm.v_peer[vst], (u / kVUnits) & 1);  // ... and in the peer
+            tc_fence_after();
+            if (elect_one()) {
 #pragma unroll
-              for (int j = 0; j < 2; ++j)
+              for (int hl = 0; hl < 2; ++hl)  // P = P_hi + P_lo
 #pragma unroll
                 for (int s = 0; s < 4; ++s)
                   if (s < nk)
                     umma_f8_pair(tmem + kColO + j * 128, with_addr(d_kmaj, p_addr + (2 * pp + hl) * kPBytes + s * 32),
-                                 with_addr(d_vmn, v_addr + vst * kVStageBytes + j * 16384 + s * 4096), idesc_pv,
+                                 with_addr(d_vmn, v_addr + vst * kVUnitBytes + s * 4096), idesc_pv,
                                  !(t == 0 && s == 0 && hl == 0));
-            umma_commit_pair(&sm.v_empty[vst], 3);
+              umma_commit_pair(&sm.v_empty[vst], 3);
+            }
+            __syncwarp();
+          }
+          if (elect_one()) {
             umma_commit_pair(&sm.p_free[pp], 3);
             umma_commit_pair(&sm.s_free[g % kSBufs], 3);
             umma_commit_pair(&sm.pv_done, 3);
@@ -561,6 +581,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
 #pragma unroll
       for (int i = 0; i < kPPairs; ++i) p_full_l[i] = mapa_u32(smem_u32(&sm.p_full[i]), 0);
       const uint32_t o_free_l = mapa_u32(smem_u32(&sm.o_free), 0);
+      uint32_t s_done_l[kSBufs], v_peer_l[kVUnits];
+#pragma unroll
+      for (int i = 0; i < kSBufs; ++i) s_done_l[i] = mapa_u32(smem_u32(&sm.s_done[i]), 0);
+#pragma unroll
+      for (int i = 0; i < kVUnits; ++i) v_peer_l[i] = mapa_u32(smem_u32(&sm.v_peer[i]), 0);
       uint32_t g = 0, seg = 0;
       int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
       for (int b = begin_idx; b <= end_idx; ++b) {
@@ -572,9 +597,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
         if (sg.n_tiles == 0) continue;
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
-          mbar_wait(&sm.p_relay[g & 1], (g >> 1) & 1);
-          mbar_wait(&sm.v_land[g % kVStages], (g / kVStages) & 1);  // the forwarded arrival also vouches for this CTA's V
-          if (elect_one()) mbar_arrive_cluster(p_full_l[g & 1]);
+          // per tile: the first V unit (frees early), then this CTA's P (its S tile is dead with it), then the second
+          // V unit (the last to land: its slot frees when P.V of the previous tile's first half retires)
+          const uint32_t u0 = 2 * g, u1 = 2 * g + 1;
+          mbar_wait(&sm.v_land[u0 % kVUnits], (u0 / kVUnits) & 1);
+          if (elect_one()) mbar_arrive_cluster(v_peer_l[u0 % kVUnits]);
+          __syncwarp();
+          mbar_wait(&sm.p_relay[g % kPPairs], (g / kPPairs) & 1);
+          if (elect_one()) {
+            mbar_arrive_cluster(s_done_l[g % kSBufs]);
+            mbar_arrive_cluster(p_full_l[g % kPPairs]);
+          }
+          __syncwarp();
+          mbar_wait(&sm.v_land[u1 % kVUnits], (u1 / kVUnits) & 1);
+          if (elect_one()) mbar_arrive_cluster(v_peer_l[u1 % kVUnits]);
           __syncwarp();
         }
         mbar_wait(&sm.o_relay, seg & 1);
@@ -585,22 +621,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
     }
   } else if (warp >= 4) {
     // ============================== softmax / correction / epilogue (both CTAs) ==============================
-    // Two groups of four warps ping-pong over the tiles: group 0 (warps 4-7) serves the tiles whose S / P buffer is 0,
-    // group 1 (warps 8-11) buffer 1.  A group's per-tile chain (barrier waits, TMEM load, vote, publish) then overlaps
-    // the other group's exponentials instead of idling the SM.  Under the lazy reference a tile's P does not depend
-    // on its predecessor unless a reference move ("trigger") happens, so the groups only meet at a per-tile hand-off
-    // (sm.fin) that orders the moves: tile g is published after tile g-1 is final, and a group that computed under a
-    // reference which has since moved (sm.version) recomputes.
-    const int st_id = tid - 128;              // 0 .. 255 over both groups
-    const int grp = (warp - 4) >> 2;          // S / P buffer (tile parity) this warp serves
+    // Three groups of four warps take the tiles round-robin: group i (warps 4+4i .. 7+4i) serves the tiles with
+    // g % 3 == i and owns P pair i.  A group's per-tile chain (barrier waits, two passes over S, vote, publish) then
+    // overlaps the other groups' arithmetic instead of idling the SM: three softmax warps per scheduler.  A tile's P
+    // depends on its predecessor only through the row reference R, which moves rarely ("trigger"), so the groups only
+    // meet at a per-tile hand-off (sm.fin) that orders the moves: tile g is published after tile g-1 is final, and a
+    // group that computed under a reference which has since moved (sm.version) recomputes its second pass.
+    const int st_id = tid - 128;              // 0 .. 383 over the three groups
+    const int grp = (warp - 4) >> 2;          // which tiles (g % 3) and which P pair this warp serves
     const int gtid = st_id & 127;             // thread within the group
     const uint32_t gbar = 2 + grp;            // the group's named barrier (128 threads)
     const int quad = warp & 3;                // TMEM lane quadrant of this warp
     const int tl = quad * 32 + lane;          // TMEM lane
     const int row = tl & 63;                  // q row within this CTA
     const int page = tl >> 6;                 // lanes 64-127 hold the second half of the N columns = the peer's page
-    const int ch = grp;                       // epilogue only: which 64 of the 128 O columns of each d half
-    const int slot = page * 2 + ch;           // epilogue only: which quarter of the staged row this thread fills
+    const int slot = page * kGroups + grp;    // this thread's slot in the row-sum exchange
     const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
     const bool row_valid = row < n_valid_q;
     const int grow = q_row0 + row;            // row within the request's M rows
@@ -642,33 +677,40 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
       };
 
-      // Pass A over this lane's 64 S columns: ymax = max_j y_j, y_j = s_j f k_j + log2 k_j = log2 of the un-normalised
-      // P'_j (splitkv_mla.cu:400-432 computes the same maximum as max_j exp2(..) k_j).  16 columns at a time, TMEM loads
-      // double-buffered, a compact loop (the kernel's hot code stays inside the instruction cache).
-      auto pass_max = [&](uint32_t s_addr, const float* ks_tile, const float* lk_tile, int tile_start, bool need_mask) {
+      // Pass A over this lane's 64 S columns: y_j = s_j f k_j + log2 k_j = log2 of the un-normalised P'_j, written back
+      // over S in TMEM (masked columns as -inf), and ymax = max_j y_j (splitkv_mla.cu:400-432 computes the same maximum
+      // as max_j exp2(..) k_j).  16 columns at a time, TMEM loads double-buffered, a compact loop (the kernel's hot
+      // code stays inside the instruction cache); the unmasked variant has no branches, so the 16 columns of a chunk
+      // are scheduled as independent chains.
+      auto pass_max = [&](auto mask_tag, uint32_t s_addr, const float* ks_tile, const float* lk_tile, int tile_start) {
+        constexpr bool need_mask = decltype(mask_tag)::value;
         const float2 f2 = make_float2(f, f);
         const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
         const float4* lsrc = reinterpret_cast<const float4*>(lk_tile + page * 64);
         const int nvalid = lim - (tile_start + page * 64);  // columns of this lane below the mask border
         float m0 = -INFINITY, m1 = -INFINITY;
-        auto chunk = [&](const float* x, int c16) {
+        auto chunk = [&](float* x, int c16) {
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 k4 = ksrc[c16 * 4 + i], l4 = lsrc[c16 * 4 + i];
-            if (!need_mask) {
+            if constexpr (!need_mask) {
               const float2 ya = fma2(make_float2(x[4 * i], x[4 * i + 1]), mul2(f2, make_float2(k4.x, k4.y)), make_float2(l4.x, l4.y));
               const float2 yb = fma2(make_float2(x[4 * i + 2], x[4 * i + 3]), mul2(f2, make_float2(k4.z, k4.w)), make_float2(l4.z, l4.w));
               m0 = fmaxf(m0, fmaxf(ya.x, ya.y));
               m1 = fmaxf(m1, fmaxf(yb.x, yb.y));
+              x[4 * i] = ya.x, x[4 * i + 1] = ya.y, x[4 * i + 2] = yb.x, x[4 * i + 3] = yb.y;
             } else {
               const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w};
 #pragma unroll
               for (int j = 0; j < 4; ++j) {
                 const float y = fmaf(x[4 * i + j], f * kk[j], ll[j]);
-                if (c16 * 16 + 4 * i + j < nvalid) m0 = fmaxf(m0, y);  // a select: poisoned padding never propagates
+                // a select: S of a poisoned (NaN) padding row never propagates
+                x[4 * i + j] = (c16 * 16 + 4 * i + j < nvalid) ? y : -INFINITY;
+                m0 = fmaxf(m0, x[4 * i + j]);
               }
             }
           }
+          tmem_st16(s_addr + c16 * 16, reinterpret_cast<const uint32_t*>(x));
         };
         float xa[16], xb[16];
         tmem_ld16(s_addr, reinterpret_cast<uint32_t*>(xa));
@@ -678,50 +720,39 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           tmem_ld16(s_addr + (c16 + 1) * 16, reinterpret_cast<uint32_t*>(xb));
           chunk(xa, c16);
           tmem_wait_ld();
-          if (c16 == 0) tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
+          if (c16 == 0) {
+            tmem_wait_st();  // xa is the source of the store just issued
+            tmem_ld16(s_addr + 32, reinterpret_cast<uint32_t*>(xa));
+          }
           chunk(xb, c16 + 1);
         }
+        tmem_wait_st();
         return fmaxf(m0, m1);
       };
       // Pass B: the page's codes code_j = e4m3(448 * 2^(y_j - ymax)) (:433-440), the page sum sum_j 448 * 2^(y_j - ymax)
       // / k_j (:426,434), and code_j * w as an e4m3 pair hi + lo straight into the two P tiles (K-major, 128-byte
-      // swizzle; nobody reads them before this group arrives on p_full).
-      auto pass_codes = [&](uint32_t s_addr, const float* ks_tile, const float* lk_tile, const float* rk_tile, int tile_start,
-                            bool need_mask, float ymax, uint32_t w_h2, uint8_t* prow, float& acc) {
-        const float2 f2 = make_float2(f, f);
+      // swizzle; nobody reads them before this group arrives on p_full).  y comes back from TMEM; a masked column is
+      // -inf there, i.e. code 0 and no contribution to the sum (its reciprocal scale was forced finite), so one variant
+      // serves masked and unmasked tiles.
+      auto pass_codes = [&](uint32_t s_addr, const float* rk_tile, float ymax, uint32_t w_h2, uint8_t* prow, float& acc) {
         const float c = (ymax > -INFINITY ? ymax : 0.f) - kLog2Fp8Max;
         const float2 nc2 = make_float2(-c, -c), one2 = make_float2(1.f, 1.f);
         float2 acc2 = make_float2(0.f, 0.f);
-        const float4* ksrc = reinterpret_cast<const float4*>(ks_tile + page * 64);
-        const float4* lsrc = reinterpret_cast<const float4*>(lk_tile + page * 64);
         const float4* rsrc = reinterpret_cast<const float4*>(rk_tile + page * 64);
-        const int nvalid = lim - (tile_start + page * 64);
         auto chunk = [&](const float* x, int c16) {
           uint32_t hi[4], lo[4];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
-            const float4 k4 = ksrc[c16 * 4 + i], l4 = lsrc[c16 * 4 + i], r4 = rsrc[c16 * 4 + i];
-            float v[4];
-            if (!need_mask) {
-              const float2 ya = fma2(make_float2(x[4 * i], x[4 * i + 1]), mul2(f2, make_float2(k4.x, k4.y)), make_float2(l4.x, l4.y));
-              const float2 yb = fma2(make_float2(x[4 * i + 2], x[4 * i + 3]), mul2(f2, make_float2(k4.z, k4.w)), make_float2(l4.z, l4.w));
-              const float2 aa = fma2(ya, one2, nc2), ab = fma2(yb, one2, nc2);
-              v[0] = ex2_approx(aa.x), v[1] = ex2_approx(aa.y), v[2] = ex2_approx(ab.x), v[3] = ex2_approx(ab.y);
-              acc2 = fma2(make_float2(v[0], v[1]), make_float2(r4.x, r4.y), acc2);
-              acc2 = fma2(make_float2(v[2], v[3]), make_float2(r4.z, r4.w), acc2);
-            } else {
-              const float kk[4] = {k4.x, k4.y, k4.z, k4.w}, ll[4] = {l4.x, l4.y, l4.z, l4.w}, rr[4] = {r4.x, r4.y, r4.z, r4.w};
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const bool ok = c16 * 16 + 4 * i + j < nvalid;
-                const float y = fmaf(x[4 * i + j], f * kk[j], ll[j]);
-                v[j] = ok ? ex2_approx(y - c) : 0.f;
-                acc2.x += ok ? v[j] * rr[j] : 0.f;
-              }
-            }
+            const float4 r4 = rsrc[c16 * 4 + i];
+            const float2 aa = fma2(make_float2(x[4 * i], x[4 * i + 1]), one2, nc2);
+            const float2 ab = fma2(make_float2(x[4 * i + 2], x[4 * i + 3]), one2, nc2);
+            const float2 va = make_float2(ex2_approx(aa.x), ex2_approx(aa.y));
+            const float2 vb = make_float2(ex2_approx(ab.x), ex2_approx(ab.y));
+            acc2 = fma2(va, make_float2(r4.x, r4.y), acc2);
+            acc2 = fma2(vb, make_float2(r4.z, r4.w), acc2);
             uint32_t h0, l0, h1, l1;
-            split_hi_lo(cvt_e4m3x2(v[0], v[1]), w_h2, h0, l0);
-            split_hi_lo(cvt_e4m3x2(v[2], v[3]), w_h2, h1, l1);
+            split_hi_lo(cvt_e4m3x2(va.x, va.y), w_h2, h0, l0);
+            split_hi_lo(cvt_e4m3x2(vb.x, vb.y), w_h2, h1, l1);
             hi[i] = h0 | (h1 << 16);
             lo[i] = l0 | (l1 << 16);
           }
@@ -744,12 +775,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         acc = acc2.x + acc2.y;
       };
 
-      const int t_first = (int)((grp ^ g0) & 1u);  // this group's first tile of the request
-      for (int t = t_first; t < sg.n_tiles; t += 2, ++n_mine) {
+      const int t_first = (grp + kGroups - (int)(g0 % kGroups)) % kGroups;  // this group's first tile of the request
+      for (int t = t_first; t < sg.n_tiles; t += kGroups, ++n_mine) {
         const uint32_t g = g0 + (uint32_t)t;
-        const uint32_t vst = g % kVStages, kst = g % kKsStages;
+        const uint32_t kst = g % kKsStages;
         const int tile_start = (sg.start_block + 2 * t) * kPage;
-        const bool need_mask = p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end);
+        // warp-uniform: a warp with any row that needs the mask border takes the masked (per-element select) variant
+        const bool need_mask =
+            __any_sync(0xffffffffu, p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end));
         const bool tr_w = tr && quad == 0;
         if (gtid == 0) sm.trig[grp][(n_mine + 1) % 3] = 0;
         if (t <= 1) trace<TR>(tr_w, rank, 3, o_seg, 3);
@@ -763,9 +796,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         const uint32_t sb = g % kSBufs;
         const uint32_t s_addr = tmem + kColS + sb * 64 + lane_addr;
         uint8_t* prow = s_p + (2 * grp) * kPBytes + row * 128;  // this group's P pair: hi tile, lo tile right behind it
-        // the first two tiles of a request always see a reference move: wait for the predecessor before computing
+        // the first tiles of a request always see a reference move: wait for the predecessor before computing
         bool fin_waited = false;
-        if (t <= 1 && g > 0) {
+        if (t < kGroups && g > 0) {
           mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
           fin_waited = true;
         }
@@ -774,23 +807,26 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         trace<TR>(tr_w, rank, 2, g, 1);
         tc_fence_after();
 
-        // log2 and reciprocal of the tile's 128 k scales, once per tile for the whole group
+        // log2 and reciprocal of the tile's 128 k scales, once per tile for the whole group (a token past the end of the
+        // sequence may hold anything: its reciprocal is forced to 0, its logit is masked by pass A)
         {
           const float k = ks_tile[gtid];
-          sm.lkrk[grp][gtid] = log2f(k);
-          sm.lkrk[grp][128 + gtid] = 1.f / k;
+          const bool tok_ok = tile_start + gtid < sg.valid_end;
+          sm.lkrk[grp][gtid] = __log2f(k);
+          sm.lkrk[grp][128 + gtid] = tok_ok ? __frcp_rn(k) : 0.f;
         }
         named_bar_sync(gbar, 128);
-        const float ymax = pass_max(s_addr, ks_tile, lk_tile, tile_start, need_mask);
+        const float ymax = need_mask ? pass_max(std::true_type{}, s_addr, ks_tile, lk_tile, tile_start)
+                                     : pass_max(std::false_type{}, s_addr, ks_tile, lk_tile, tile_start);
         const bool live = ymax > -INFINITY;
         trace<TR>(tr_w, rank, 4, g, 0);
 
         float acc = 0.f, w32 = 0.f;
         bool p_free_waited = false;
-        // this group's P pair was last read by P.V of tile g - 2
+        // this group's P pair was last read by P.V of tile g - 3
         auto wait_p_free = [&]() {
           if (!p_free_waited) {
-            mbar_wait(&sm.p_free[grp], ((g >> 1) & 1) ^ 1);
+            mbar_wait(&sm.p_free[grp], ((g / kPPairs) & 1) ^ 1);
             p_free_waited = true;
           }
         };
@@ -799,14 +835,67 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           const uint32_t w_h2 = f32x2_to_f16x2(w, w);
           w32 = f16_lo_to_f32(w_h2);  // L carries the weight P.V sees
           wait_p_free();
-          pass_codes(s_addr, ks_tile, lk_tile, rk_tile, tile_start, need_mask, ymax, w_h2, prow, acc);
+          pass_codes(s_addr, rk_tile, ymax, w_h2, prow, acc);
         };
-        bool trigger = (t == 0);
-        while (!trigger) {
-          // ---- fast path: the current reference ----
-          sync_view();
-          const bool over = __any_sync(0xffffffffu, live && ymax > rloc);  // a row of this warp outgrew its reference
+        // One code path for the pass over the codes (a single call site keeps the hot loop's footprint inside the
+        // instruction cache): fast path = the current reference; if a row of the group has outgrown it (or on a
+        // request's first tile) the reference moves first ("slow path") and the pass runs under the new one.
+        bool trigger = (t == 0), moved = false;
+        for (;;) {
+          if (!trigger) {
+            sync_view();
+          } else {
+            // ---- slow path: move the reference R of the rows that outgrew it, rescale O and the running sums ----
+            if (!fin_waited && g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            fin_waited = true;
+            sync_view();
+            // the two page maxima of a row meet in the group's own (free) P pair: it is written by the pass below
+            wait_p_free();
+            float* red1 = reinterpret_cast<float*>(s_p + (2 * grp) * kPBytes);  // [2 pages][64 rows]
+            red1[page * 64 + row] = ymax;
+            named_bar_sync(gbar, 128);
+            const float r_old = ld_shared_volatile_f32(&sm.st_ref[row]);  // == rloc
+            const float yb = fmaxf(red1[row], red1[64 + row]);
+            const float r_new = yb > r_old ? yb + kRefHeadroom : r_old;
+            const float fac = exp2f(r_old - r_new);  // 0 on the row's first move (R = -1e30), 1 if the row stays
+            if (t != 0) {
+              // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
+              // last one issued: tile g is not published yet).  pv_done completes once per tile; tile g-1 is final
+              // (fin), so P.V of tile g-2 was issued before it and this parity wait cannot alias an older phase... it
+              // could still be two phases behind if P.V of g-2 has not retired: wait for that one first (s_free).
+              if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
+              mbar_wait(&sm.pv_done, (g - 1) & 1);
+              tc_fence_after();
+              if (__any_sync(0xffffffffu, fac != 1.f)) {
+#pragma unroll 1
+                for (int c8 = 0; c8 < 8; ++c8) {
+                  float o[32];
+                  const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
+                  tmem_ld<32>(a, o);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int k = 0; k < 32; ++k) o[k] *= fac;
+                  tmem_st<32>(a, o);
+                }
+                tmem_wait_st();
+              }
+              lsum *= fac;
+            }
+            rloc = r_new;
+            if (page == 0) sm.st_ref[row] = r_new;
+            tc_fence_before();
+            named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
+            ver += 1;
+            if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
+            moved = true;
+          }
+          const bool over = !moved && __any_sync(0xffffffffu, live && ymax > rloc);  // a row of this warp outgrew its reference
           if (!over) weighted_pass();
+          if (moved) {
+            lsum = fmaf(w32, acc, lsum);
+            named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
+            break;
+          }
           if (!fin_waited) {
             if (g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);  // tile g-1 is final
             fin_waited = true;
@@ -816,52 +905,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
           if (over && lane == 0) sm.trig[grp][n_mine % 3] = 1;
           named_bar_sync(gbar, 128);
           trigger = sm.trig[grp][n_mine % 3] != 0;
-          break;
-        }
-        if (!trigger) {
-          lsum = fmaf(w32, acc, lsum);
-        } else {
-          // ---- slow path: move the reference R of the rows that outgrew it, rescale O and the running sums ----
-          if (!fin_waited && g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
-          sync_view();
-          sm.red1[grp][page][row] = ymax;
-          named_bar_sync(gbar, 128);
-          const float r_old = ld_shared_volatile_f32(&sm.st_ref[row]);  // == rloc
-          const float yb = fmaxf(sm.red1[grp][0][row], sm.red1[grp][1][row]);
-          const float r_new = yb > r_old ? yb + kRefHeadroom : r_old;
-          const float fac = exp2f(r_old - r_new);  // 0 on the row's first move (R = -1e30), 1 if the row stays
-          if (t != 0) {
-            // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
-            // last one issued: tile g is not published yet).  pv_done completes once per tile and Q.K^T runs ahead of
-            // P.V: first make sure P.V of tile g-2 has retired (its p_free, at most one phase behind), so that the
-            // parity wait on pv_done cannot alias the phase before it.
-            wait_p_free();
-            mbar_wait(&sm.pv_done, (g - 1) & 1);
-            tc_fence_after();
-            if (__any_sync(0xffffffffu, fac != 1.f)) {
-#pragma unroll 1
-              for (int c8 = 0; c8 < 8; ++c8) {
-                float o[32];
-                const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
-                tmem_ld<32>(a, o);
-                tmem_wait_ld();
-#pragma unroll
-                for (int k = 0; k < 32; ++k) o[k] *= fac;
-                tmem_st<32>(a, o);
-              }
-              tmem_wait_st();
-            }
-            lsum *= fac;
+          if (!trigger) {
+            lsum = fmaf(w32, acc, lsum);
+            break;
           }
-          rloc = r_new;
-          if (page == 0) sm.st_ref[row] = r_new;
-          tc_fence_before();
-          named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
-          ver += 1;
-          if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
-          weighted_pass();
-          lsum = fmaf(w32, acc, lsum);
-          named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
@@ -872,14 +919,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
         // Reference: fill_oob_V, splitkv_mla.cu:698-721.
         if (tile_start + kTileTokens > sg.valid_end) {
-          mbar_wait(&sm.v_land[vst], (g / kVStages) & 1);
           const int valid_in_tile = sg.valid_end - tile_start;
           const int nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
-          if (gtid >= valid_in_tile && gtid < nk * 32) {
-            uint8_t* stage = s_v + vst * kVStageBytes;
 #pragma unroll
-            for (int j = 0; j < 2; ++j) {
-              uint4* vr = reinterpret_cast<uint4*>(stage + j * 16384 + gtid * 128);
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t u = 2 * g + (uint32_t)j, vst = u % kVUnits;
+            mbar_wait(&sm.v_land[vst], (u / kVUnits) & 1);
+            if (gtid >= valid_in_tile && gtid < nk * 32) {
+              uint4* vr = reinterpret_cast<uint4*>(s_v + vst * kVUnitBytes + gtid * 128);
 #pragma unroll
               for (int k = 0; k < 8; ++k) vr[k] = make_uint4(0, 0, 0, 0);
             }
@@ -889,6 +936,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         tc_fence_before();
         __syncwarp();
         if (lane == 0) {
+          if (rank == 0) mbar_arrive(&sm.s_done[sb]);  // (the peer's share rides on its relay's p_relay hand-off)
           mbar_arrive(rank == 0 ? &sm.p_full[grp] : &sm.p_relay[grp]);
           mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the other group may publish tile g+1
         }
@@ -896,7 +944,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
       }
       g0 += (uint32_t)sg.n_tiles;
 
-      // both groups have published their last tile: bring every thread's running sum to the request's final reference
+      // every group has published its last tile: bring every thread's running sum to the request's final reference
       named_bar_sync(1, kSmThreads);
       {
         const float r_fin = ld_shared_volatile_f32(&sm.st_ref[row]);
@@ -904,22 +952,20 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         rloc = r_fin;
       }
       // ---- epilogue of this request: O / L -> out (or split partials) ----
-      // One group writes the request out while the other starts the next request (its first tile always moves the
-      // reference, ~3k cycles, and the fp32 partial stores drain at ~28 B/clk per SM, ~4.6k cycles): the epilogue group
-      // is the one that does NOT own the next request's first tile (global index g0 now).
-      const int egrp = b < end_idx ? (int)((g0 & 1u) ^ 1u) : 1;
+      // All three groups write the request out, each a third of the O columns (rounds of 32 columns taken round-robin):
+      // a single group needs ~9k cycles for the 128 KB of an fp32 partial, during which its tiles of the next request
+      // wait and the other groups run dry behind it (the tile hand-off is in order).
       sm.lred[rq & 1][slot][row] = lsum;
       named_bar_sync(1, kSmThreads);
       const bool had_tiles = sg.n_tiles > 0;
-      if (grp != egrp) {
-        if (b < end_idx) {  // reset the row state for the next request; nobody reads the old one any more
-          if (page == 0) sm.st_ref[row] = kMInit;
-          named_bar_sync(gbar, 128);
-        }
-      } else {
-        const bool tr_e = tr && quad == 0;
+      // the owner of the next request's first tile (global index g0 now) resets the row state; nobody reads the old one
+      // any more, and the other groups look at it only after that tile is final (fin)
+      if (b < end_idx && grp == (int)(g0 % kGroups) && page == 0) sm.st_ref[row] = kMInit;
+      {
+        const bool tr_e = tr && quad == 0 && grp == 0;
         trace<TR>(tr_e, rank, 3, o_seg, 0);
-        const float l = (sm.lred[rq & 1][0][row] + sm.lred[rq & 1][1][row]) + (sm.lred[rq & 1][2][row] + sm.lred[rq & 1][3][row]);
+        const float* lr = &sm.lred[rq & 1][0][row];  // fixed summation order: results are bit-reproducible run to run
+        const float l = ((lr[0] + lr[64]) + (lr[128] + lr[192])) + (lr[256] + lr[320]);
         const bool bad = (l == 0.f || l != l);
         const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
         if (had_tiles) {
@@ -930,150 +976,75 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(384, 1)
         }
         // O -> global through shared memory, so that every global store instruction writes whole 64 / 128-byte
         // segments (a TMEM lane is a q row: storing straight from the tcgen05.ld registers scatters 16-byte pieces
-        // over 32 rows per instruction).  Staging = this group's own P pair (its next tiles' buffers: every P.V of
-        // this request has retired, and the other group only writes its own pair): one 8 KB half per TMEM lane half
-        // (= 128-column block of d), [64 rows][32 values], 16-byte chunks XOR-swizzled; eight rounds of 32 columns.
-        uint8_t* stage_mine = s_p + (2 * egrp + page) * kPBytes;
+        // over 32 rows per instruction).  Staging = the group's own P pair (every P.V of this request has retired).
+        // Warp-local: a warp's 32 lanes are 32 q rows of one TMEM lane half; it stages its [32 rows][32 columns] block
+        // in a private 4 KB slice and reads it back row-major, so nothing but __syncwarp orders a round and the warps
+        // hide each other's TMEM / shared / store latencies.
+        uint8_t* stage_mine = s_p + (2 * grp + page) * kPBytes;
         const int64_t grow0 = (int64_t)b * p.M + q_row0;
-        const int gw = warp & 3;  // warp within the group
-        if (p.epi_mode) {
-          // Warp-local staging: a warp's 32 lanes are 32 q rows of one TMEM lane half; it stages its [32 rows][32
-          // columns] block in a private 4 KB slice of the group's P tiles and reads it back row-major, so every global
-          // store instruction still writes whole 64 / 128-byte row segments but nothing but __syncwarp orders the
-          // round: the four warps run independently and hide each other's TMEM / shared / store latencies (the
-          // group-wide staging below spends ~900 cycles per round on two 128-thread barriers).
-          uint8_t* wst = stage_mine + (row >> 5) * 4096;
-          const int wrow0 = row & 32;  // first of this warp's 32 rows within the CTA's 64
-          auto flush = [&](const float* o, int r8) {
-            const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3) + 128 * page;
-            if (sg.no_split) {
-              uint8_t* srow = wst + lane * 64;
+        uint8_t* wst = stage_mine + (row >> 5) * 4096;
+        const int wrow0 = row & 32;  // first of this warp's 32 rows within the CTA's 64
+        auto flush = [&](const float* o, int r8) {
+          const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3) + 128 * page;
+          if (sg.no_split) {
+            uint8_t* srow = wst + lane * 64;
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
-                *reinterpret_cast<uint4*>(srow + ((k ^ ((lane >> 1) & 3)) << 4)) =
-                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-              }
-              __syncwarp();
-              const int k = lane & 3, rr = lane >> 2;  // per instruction: 8 rows x 64 B
-#pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int r = it * 8 + rr;
-                const uint4 v = *reinterpret_cast<const uint4*>(wst + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
-                if (wrow0 + r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + wrow0 + r) * 512 + d_base + 8 * k) = v;
-              }
-            } else {
-              uint8_t* srow = wst + lane * 128;
-#pragma unroll
-              for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4*>(srow + ((k ^ (lane & 7)) << 4)) =
-                    make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
-              __syncwarp();
-              const int k = lane & 7, rr = lane >> 3;  // per instruction: 4 rows x 128 B
-              float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0 + wrow0) * 512 + d_base + 4 * k;
-#pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int r = it * 4 + rr;
-                const float4 v = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
-                if (wrow0 + r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512) = v;
-              }
+            for (int k = 0; k < 4; ++k) {
+              __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
+              __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
+              __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
+              __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
+              *reinterpret_cast<uint4*>(srow + ((k ^ ((lane >> 1) & 3)) << 4)) =
+                  make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
+                             *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
             }
-            __syncwarp();  // the slice is rewritten by the next round / this group's next P tile
-          };
-          float oa[32], ob[32];
-          if (had_tiles) {
-            const uint32_t o_addr = tmem + kColO + lane_addr;
-            tmem_ld<32>(o_addr, oa);
+            __syncwarp();
+            const int k = lane & 3, rr = lane >> 2;  // per instruction: 8 rows x 64 B
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+              const int r = it * 8 + rr;
+              const uint4 v = *reinterpret_cast<const uint4*>(wst + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
+              if (wrow0 + r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + wrow0 + r) * 512 + d_base + 8 * k) = v;
+            }
+          } else {
+            uint8_t* srow = wst + lane * 128;
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+              *reinterpret_cast<float4*>(srow + ((k ^ (lane & 7)) << 4)) =
+                  make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
+            __syncwarp();
+            const int k = lane & 7, rr = lane >> 3;  // per instruction: 4 rows x 128 B
+            float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0 + wrow0) * 512 + d_base + 4 * k;
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              const int r = it * 4 + rr;
+              const float4 v = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
+              if (wrow0 + r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512) = v;
+            }
+          }
+          __syncwarp();  // the slice is rewritten by the next round / this group's next P tile
+        };
+        float oa[32];
+        const uint32_t o_addr = tmem + kColO + lane_addr;
 #pragma unroll 1
-            for (int r8 = 0; r8 < 8; r8 += 2) {
-              tmem_wait_ld();
-              tmem_ld<32>(o_addr + (r8 + 1) * 32, ob);
-              flush(oa, r8);
-              tmem_wait_ld();
-              if (r8 + 2 < 8) {
-                tmem_ld<32>(o_addr + (r8 + 2) * 32, oa);
-              } else {  // O has left TMEM: the next request's P.V may overwrite it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
-              }
-              flush(ob, r8 + 1);
+        for (int r8 = grp; r8 < 8; r8 += kGroups) {
+          if (had_tiles) {
+            tmem_ld<32>(o_addr + r8 * 32, oa);
+            tmem_wait_ld();
+            if (r8 + kGroups >= 8) {  // this warp's share of O has left TMEM: the next request's P.V may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) oa[k] = 0.f;
-#pragma unroll 1
-            for (int r8 = 0; r8 < 8; ++r8) flush(oa, r8);
           }
-          named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
-        } else {
-  #pragma unroll 1
-          for (int r8 = 0; r8 < 8; ++r8) {
-            const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3);  // + 128 * page
-            float o[32];
-            if (had_tiles) {
-              tmem_ld<32>(tmem + kColO + r8 * 32 + lane_addr, o);
-              tmem_wait_ld();
-              if (r8 == 7) {  // O is in registers / shared memory: the next request's P.V may overwrite it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
-              }
-            } else {
-  #pragma unroll
-              for (int k = 0; k < 32; ++k) o[k] = 0.f;
-            }
-            if (sg.no_split) {
-              uint8_t* srow = stage_mine + row * 64;
-  #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                __nv_bfloat162 h0 = __floats2bfloat162_rn(o[8 * k] * inv, o[8 * k + 1] * inv);
-                __nv_bfloat162 h1 = __floats2bfloat162_rn(o[8 * k + 2] * inv, o[8 * k + 3] * inv);
-                __nv_bfloat162 h2 = __floats2bfloat162_rn(o[8 * k + 4] * inv, o[8 * k + 5] * inv);
-                __nv_bfloat162 h3 = __floats2bfloat162_rn(o[8 * k + 6] * inv, o[8 * k + 7] * inv);
-                *reinterpret_cast<uint4*>(srow + ((k ^ ((row >> 1) & 3)) << 4)) =
-                    make_uint4(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1),
-                               *reinterpret_cast<uint32_t*>(&h2), *reinterpret_cast<uint32_t*>(&h3));
-              }
-            } else {
-              uint8_t* srow = stage_mine + row * 128;
-  #pragma unroll
-              for (int k = 0; k < 8; ++k)
-                *reinterpret_cast<float4*>(srow + ((k ^ (row & 7)) << 4)) =
-                    make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
-            }
-            named_bar_sync(gbar, 128);
-            if (sg.no_split) {
-              // per instruction: 4 rows x 2 lane halves x 64 B
-              const int k = lane & 3, pg = (lane >> 2) & 1, rr = lane >> 3;
-              const uint8_t* src = s_p + (2 * egrp + pg) * kPBytes;
-  #pragma unroll
-              for (int it = 0; it < 4; ++it) {
-                const int r = gw * 16 + it * 4 + rr;
-                const uint4 v = *reinterpret_cast<const uint4*>(src + r * 64 + ((k ^ ((r >> 1) & 3)) << 4));
-                if (r < n_valid_q) *reinterpret_cast<uint4*>(p.out + (grow0 + r) * 512 + d_base + 128 * pg + 8 * k) = v;
-              }
-            } else {
-              // per instruction: 2 rows x 2 lane halves x 128 B
-              const int k = lane & 7, pg = (lane >> 3) & 1, rr = lane >> 4;
-              const uint8_t* src = s_p + (2 * egrp + pg) * kPBytes;
-              float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0) * 512;
-  #pragma unroll
-              for (int it = 0; it < 8; ++it) {
-                const int r = gw * 16 + it * 2 + rr;
-                const float4 v = *reinterpret_cast<const float4*>(src + r * 128 + ((k ^ (r & 7)) << 4));
-                if (r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512 + d_base + 128 * pg + 4 * k) = v;
-              }
-            }
-            named_bar_sync(gbar, 128);  // the staging halves are rewritten by the next round / this group's next P tile
-          }
+          flush(oa, r8);
         }
+        named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
         if (had_tiles) trace<TR>(tr_e, rank, 3, o_seg, 2);
-        if (row_valid && page == 0) {
+        if (row_valid && page == 0 && grp == 0) {
           const float lse2 = log2f(l) + (rloc - kLog2Fp8Max);  // L_true = L * 2^R / 448
           if (sg.no_split) {
             const int sq = grow / p.h_q, hh = grow % p.h_q;
@@ -1106,10 +1077,10 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream)
   const int q_pairs = (prm.M + 127) / 128;
   if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, knobs that break results
     B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pairk::mla_decode_pair_kernel<true><<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+    pairk::mla_decode_pair_kernel<true><<<dim3(2, q_pairs, num_sm_parts), 128 + pairk::kSmThreads, smem, stream>>>(prm);
   } else {
     B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pairk::mla_decode_pair_kernel<false><<<dim3(2, q_pairs, num_sm_parts), 384, smem, stream>>>(prm);
+    pairk::mla_decode_pair_kernel<false><<<dim3(2, q_pairs, num_sm_parts), 128 + pairk::kSmThreads, smem, stream>>>(prm);
   }
   B200_CUDA(cudaGetLastError());
   return 0;
