@@ -153,6 +153,7 @@ class HotPath:
         import torch
 
         from sglang_fluentllm_b200 import deep_gemm as dg
+        from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
         self.torch, self.dg, self.args, self.dev, self.world = torch, dg, args, dev, world
         from sglang_fluentllm_b200 import tp as tpmod
         self.tpmod = tpmod
@@ -200,8 +201,7 @@ class HotPath:
         self.rope_mod = rope_mod
 
         def weight(n, k):
-            w = (torch.randn(n, k, dtype=torch.bfloat16, device=dev, generator=g) * (k ** -0.5)).contiguous()
-            return dg.per_block_cast_to_fp8(w)
+            return dummy_block_fp8_weight(n, k, dev, g)
 
         self.w_qkv_a = [weight(Q_LORA + KV_LORA + ROPE, HIDDEN) for _ in range(L)]          # replicated
         self.w_q_b = [weight(h * (NOPE_HEAD + ROPE), Q_LORA) for _ in range(L)]              # column-parallel

@@ -580,6 +580,7 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
                                       const int32_t* num_splits, int num_sm_parts, int batch, int s_q, int h_q,
                                       float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
                                       size_t workspace_bytes, int use_pdl, void* stream) {
+  if (batch == 0) return 0;  // IDLE batch (flash_api.cpp accepts batch_size 0): nothing to attend
   B200_CHECK(q_nope && q_rope && q_scale && k_lora && k_rope && k_scale && block_table && cache_seqlens &&
                  tile_scheduler_metadata && num_splits && out && lse && workspace,
              "mla_decode: null pointer argument");
@@ -640,7 +641,7 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   int rc;
   static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
   // M above this goes to the CTA-pair kernel (A/B knob; 32 < M <= 64 fills one CTA of the pair)
-  static const int pair_min_m = getenv("B200_MLA_PAIR_MIN_M") ? atoi(getenv("B200_MLA_PAIR_MIN_M")) : 64;
+  static const int pair_min_m = getenv("B200_MLA_PAIR_MIN_M") ? atoi(getenv("B200_MLA_PAIR_MIN_M")) : 32;
   if (M > pair_min_m && M > 32 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 32) rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);

@@ -399,6 +399,7 @@ extern "C" int b200_mla_decode_bf16(const void* q, const void* k_cache, int64_t 
                                     int num_sm_parts, int batch, int s_q, int h_q, float softmax_scale, int is_causal,
                                     void* out, float* lse, void* workspace, size_t workspace_bytes, int use_pdl,
                                     void* stream) {
+  if (batch == 0) return 0;  // IDLE batch
   B200_CHECK(q && k_cache && block_table && cache_seqlens && tile_scheduler_metadata && num_splits && out && lse &&
                  workspace,
              "mla_decode_bf16: null pointer argument");

@@ -397,7 +397,7 @@ int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_coun
 
 int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
                           int32_t* num_splits, void* stream) {
-  B200_CHECK(cache_seqlens && tile_scheduler_metadata && num_splits, "get_metadata: null pointer");
+  B200_CHECK((cache_seqlens || batch == 0) && tile_scheduler_metadata && num_splits, "get_metadata: null pointer");
   // batch == 0 is an IDLE batch (a data-parallel attention rank with no request, flash_api.cpp:27-63 accepts it): every
   // part then starts at request 0 >= batch, which the decode kernels read as "no work", and num_splits = [0]
   B200_CHECK(batch >= 0 && num_sm_parts > 0, "get_metadata: batch=%d num_sm_parts=%d", batch, num_sm_parts);
@@ -512,6 +512,7 @@ int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cac
 
 int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
                      int batch, int s_q, int h_q, int use_pdl, void* stream) {
+  if (batch == 0) return 0;  // IDLE batch
   B200_CHECK(o_accum && lse_accum && num_splits && out && lse, "combine: null pointer");
   const int M = s_q * h_q;
   const int warps = 8;

@@ -11,21 +11,28 @@ import torch
 from . import _lib
 
 _num_sms = None
-_workspaces = {}  # device index -> split-K scratch (fp32 partial slabs; stream-ordered reuse, no initialisation)
+_workspaces = {}   # (device index, stream handle) -> split-K scratch (fp32 partial slabs; no initialisation needed)
+_retired = []      # outgrown scratch buffers: a captured CUDA graph may still hold their addresses, so they are never freed
 
 
 def _workspace(device: torch.device, nbytes: int):
-    """Per-device split-K scratch.  Grown on demand; growth is not allowed while a CUDA graph is being
-    captured -- the runner's warm-up calls before capture size it (reference: JIT compile happens in warm-up too,
-    python/sglang/srt/model_executor/cuda_graph_runner.py:423-427)."""
+    """Split-K scratch, one buffer per (device, stream): GEMMs running concurrently on several streams (the reference's
+    two-batch overlap, tbo_executor + deep_gemm.set_num_sms) never share slabs.  Grown on demand, except while a CUDA
+    graph is being captured: the buffer's address is baked into the graph, so it must exist -- large enough -- before
+    capture starts; the runner's warm-up runs see to that (cuda_graph_runner.py:423-427; the reference's JIT compile
+    happens in the same warm-up).  Asking for more during capture is an error, not a silent change of tiling."""
     if nbytes == 0:
         return None
-    ws = _workspaces.get(device.index)
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    ws = _workspaces.get(key)
     if ws is None or ws.numel() < nbytes:
         if torch.cuda.is_current_stream_capturing():
-            return None  # fall back to plain tiling for this call rather than allocate inside a capture
+            raise RuntimeError("deep_gemm: split-K workspace of %d bytes requested during CUDA-graph capture; run the same "
+                               "call once on this stream before capturing (warm-up) so the scratch exists" % nbytes)
+        if ws is not None:
+            _retired.append(ws)
         ws = torch.empty(max(nbytes, 64 << 20), dtype=torch.uint8, device=device)
-        _workspaces[device.index] = ws
+        _workspaces[key] = ws
     return ws
 
 
@@ -52,50 +59,22 @@ def get_tma_aligned_size(x: int, element_size: int) -> int:
 
 
 def get_col_major_tma_aligned_tensor(x: torch.Tensor) -> torch.Tensor:
-    """jit_kernels/utils.py:77-107: [m, k/128] scales -> same logical shape, column-major storage with the m stride
-    padded to 16 bytes."""
-    assert x.dim() in (2, 3)
-    remove_dim = False
-    origin_dim = x.dim()
-    if x.dim() == 2:
-        x, remove_dim = x.unsqueeze(0), True
-    b, m, n = x.shape
-    aligned_m = get_tma_aligned_size(m, x.element_size())
-    if (origin_dim == 2 or x.stride(0) == aligned_m * n) and x.stride(1) == 1 and x.stride(2) == aligned_m:
-        return x.squeeze(0) if remove_dim else x
-    aligned_x = torch.transpose(torch.empty((b, n, aligned_m), device=x.device, dtype=x.dtype), 1, 2)
-    aligned_x[:, :m, :] = x
-    aligned_x = aligned_x[:, :m, :]
-    return aligned_x.squeeze(0) if remove_dim else aligned_x
-
-
-def per_token_cast_to_fp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Test-side quantiser of the reference (3rdparty/deep_gemm/tests/test_core.py:9-14)."""
-    assert x.dim() == 2 and x.size(1) % 128 == 0
-    m, n = x.shape
-    x_view = x.view(m, -1, 128)
-    x_amax = x_view.abs().float().amax(dim=2).view(m, -1).clamp(1e-4)
-    return (x_view * (448.0 / x_amax.unsqueeze(2))).to(torch.float8_e4m3fn).view(m, n), (x_amax / 448.0).view(m, -1)
-
-
-def per_block_cast_to_fp8(x: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
-    """Test-side weight quantiser of the reference (tests/test_core.py:17-25)."""
-    assert x.dim() == 2
-    m, n = x.shape
-    x_padded = torch.zeros((ceil_div(m, 128) * 128, ceil_div(n, 128) * 128), dtype=x.dtype, device=x.device)
-    x_padded[:m, :n] = x
-    x_view = x_padded.view(-1, 128, x_padded.size(1) // 128, 128)
-    x_amax = x_view.abs().float().amax(dim=(1, 3), keepdim=True).clamp(1e-4)
-    x_scaled = (x_view * (448.0 / x_amax)).to(torch.float8_e4m3fn)
-    return x_scaled.view_as(x_padded)[:m, :n].contiguous(), (x_amax / 448.0).view(x_view.size(0), x_view.size(2))
-
-
-def calc_diff(x: torch.Tensor, y: torch.Tensor) -> float:
-    """deep_gemm/utils.py:140-144."""
-    x, y = x.double(), y.double()
-    denominator = (x * x + y * y).sum()
-    sim = 2 * (x * y).sum() / denominator
-    return float(1 - sim)
+    """Same contract as the reference helper of this name (jit_kernels/utils.py:77-107): the [m, k/128] (or batched
+    [b, m, k/128]) scale tensor comes back with the same logical shape but column-major storage -- element (i, j) at
+    offset j * m_pad + i -- where m_pad is m rounded up to a 16-byte multiple, which is what a TMA row pitch needs.
+    A tensor that already has that storage is returned as is."""
+    if x.dim() not in (2, 3):
+        raise ValueError("expected a 2-D or 3-D scale tensor, got %d-D" % x.dim())
+    batched = x.dim() == 3
+    xb = x if batched else x[None]
+    nb, m, groups = xb.shape
+    m_pad = get_tma_aligned_size(m, x.element_size())
+    if xb.stride(1) == 1 and xb.stride(2) == m_pad and (nb == 1 or xb.stride(0) == m_pad * groups):
+        return x
+    storage = x.new_empty((nb, groups, m_pad))
+    col_major = storage.permute(0, 2, 1)[:, :m, :]
+    col_major.copy_(xb)
+    return col_major if batched else col_major[0]
 
 
 def gemm_fp8_fp8_bf16_nt(lhs: Tuple[torch.Tensor, torch.Tensor], rhs: Tuple[torch.Tensor, torch.Tensor],

@@ -91,6 +91,17 @@ class Fp8Config:
         return []
 
 
+def dummy_block_fp8_weight(n: int, k: int, device, generator: Optional[torch.Generator] = None, std: Optional[float] = None):
+    """Random-init block-FP8 weight for ``--load-format dummy`` style runs (the reference initialises dummy weights at
+    random instead of reading a checkpoint; an FP8 checkpoint stores e4m3 codes + a 128x128 ``weight_scale_inv``): e4m3
+    codes of N(0, 1) values and one positive scale per block such that the de-quantised weight has standard deviation
+    ``std`` (default k ** -0.5).  Returns (weight e4m3 [n, k], weight_scale_inv f32 [ceil(n/128), ceil(k/128)])."""
+    std = (k ** -0.5) if std is None else std
+    codes = torch.randn(n, k, dtype=torch.float32, device=device, generator=generator).to(torch.float8_e4m3fn)
+    jitter = torch.rand(-(-n // 128), -(-k // 128), dtype=torch.float32, device=device, generator=generator)
+    return codes, (std * (0.75 + 0.5 * jitter)).contiguous()
+
+
 def dense_deep_gemm(A: torch.Tensor, B: torch.Tensor, As: torch.Tensor, Bs: torch.Tensor, block_size: List[int],
                     output_dtype: torch.dtype = torch.float16, use_pdl: bool = True) -> torch.Tensor:
     """dense/gemms/fp8/deep_geem.py:14-56: shape checks, output allocation, ``gemm_fp8_fp8_bf16_nt``."""

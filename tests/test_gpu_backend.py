@@ -10,6 +10,7 @@ import torch
 
 from oracle import fp8 as ofp8
 from oracle import gemm as ogemm
+from helpers import quantize_rhs_128x128
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -182,18 +183,147 @@ def test_backend_target_verify_is_causal_over_draft_tokens():
     all_locs = [torch.cat([ctx_locs[i], new_loc[i * draft:(i + 1) * draft]]) for i in range(bs)]
     ref = _reference(pool, layer, q.view(bs, draft, heads, 576), all_locs, draft, True)
     assert _rel(out.view(bs, draft, heads, 512), ref) < 5e-2
-    with pytest.raises(NotImplementedError):  # prefill stays the reference's
+    with pytest.raises(NotImplementedError):  # prefill stays the reference's (no delegate registered here)
         fbatch.forward_mode = fb.ForwardMode.EXTEND
         backend.forward_extend(q, k_new, k_new, layer, fbatch)
 
 
-def test_multi_step_backend_attends_over_growing_lengths():
+def test_multi_step_backend_matches_reference_signature_and_lengths():
+    """FlashMLAMultiStepDecodeBackend as speculative/base_spec_worker.py:238-240 constructs it --
+    ``(draft_model_runner, speculative_num_steps)`` -- with step i attending over seq_lens + i + 1
+    (flashmla_backend.py:411-422): three draft steps, each writes the K row of its own token and then attends; every
+    step is compared with fp32 attention over ctx + i + 1 rows."""
+    heads, steps = 16, 3
+    fb, mr, alloc, pool, layer = _runner(heads)
+    ms = fb.FlashMLAMultiStepDecodeBackend(mr, steps)
+    assert [b.multi_step_seqlen_incr for b in ms.attn_backends] == [1, 2, 3]
+    assert ms.get_cuda_graph_seq_len_fill_value() == 1
+    with pytest.raises(TypeError):  # the round-1 signature (model_runner, topk, steps) is gone
+        fb.FlashMLAMultiStepDecodeBackend(mr, 1, steps, 1)
+    ctx = [130, 64, 700, 1]
+    bs = len(ctx)
+    ctx_locs = _fill_context(alloc, pool, layer, ctx)
+    seq_lens = torch.tensor(ctx, device=DEV)          # the verified context: constant over the draft steps
+    locs = [l.clone() for l in ctx_locs]
+    torch.manual_seed(11)
+    fbatch = SimpleNamespace(batch_size=bs, seq_lens=seq_lens, req_pool_indices=torch.arange(bs, device=DEV),
+                             out_cache_loc=None, token_to_kv_pool=pool, forward_mode=fb.ForwardMode.DECODE,
+                             spec_info=object())
+    ms.init_forward_metadata(fbatch)                   # common_template: the first steps - 1 backends
+    assert ms.attn_backends[0].forward_metadata is not None and ms.attn_backends[steps - 1].forward_metadata is None
+    ms.attn_backends[steps - 1].init_forward_metadata(fbatch)
+    for i in range(steps):
+        new_loc = torch.cat([alloc.alloc(r, 1, n + i) for r, n in enumerate(ctx)])
+        fbatch.out_cache_loc = new_loc
+        q = torch.randn(bs, heads * 576, dtype=torch.bfloat16, device=DEV)
+        k_new = torch.randn(bs, 1, 576, dtype=torch.bfloat16, device=DEV)
+        out = ms.attn_backends[i].forward_decode(q, k_new, k_new[..., :512], layer, fbatch)
+        locs = [torch.cat([locs[r], new_loc[r:r + 1]]) for r in range(bs)]
+        ref = _reference(pool, layer, q.view(bs, 1, heads, 576), locs, 1, False)   # ctx + i + 1 rows per request
+        assert _rel(out.view(bs, 1, heads, 512), ref) < 5e-2, i
+
+
+def test_backend_resolves_attention_tp_like_the_reference():
+    """attn_initializer.py:395 constructs FlashMLABackend(model_runner) with no TP argument; heads per rank come from
+    get_attention_tp_size() (flashmla_backend.py:67-69).  128 heads at attention-TP 8 -> 16 local heads."""
+    heads, tp = 128, 8
+    fb, mr, alloc, pool, layer = _runner(heads)
+    fb.set_attention_tp_size_getter(lambda: tp)
+    try:
+        backend = fb.FlashMLABackend(mr)
+    finally:
+        fb.set_attention_tp_size_getter(None)
+    assert backend.num_q_heads == backend.num_local_heads == heads // tp
+    local = SimpleNamespace(layer_id=1, tp_q_head_num=heads // tp, head_dim=576, v_head_dim=512, scaling=SCALING)
+    ctx = [200, 65]
+    bs = len(ctx)
+    ctx_locs = _fill_context(alloc, pool, local, ctx)
+    new_loc = torch.cat([alloc.alloc(i, 1, n) for i, n in enumerate(ctx)])
+    fbatch = SimpleNamespace(batch_size=bs, seq_lens=torch.tensor([n + 1 for n in ctx], device=DEV),
+                             req_pool_indices=torch.arange(bs, device=DEV), out_cache_loc=new_loc,
+                             token_to_kv_pool=pool, forward_mode=fb.ForwardMode.DECODE)
+    backend.init_forward_metadata(fbatch)
+    torch.manual_seed(5)
+    q = torch.randn(bs, (heads // tp) * 576, dtype=torch.bfloat16, device=DEV)
+    k_new = torch.randn(bs, 1, 576, dtype=torch.bfloat16, device=DEV)
+    out = backend.forward(q, k_new, k_new[..., :512], local, fbatch)
+    all_locs = [torch.cat([ctx_locs[i], new_loc[i:i + 1]]) for i in range(bs)]
+    ref = _reference(pool, local, q.view(bs, 1, heads // tp, 576), all_locs, 1, False)
+    assert _rel(out.view(bs, 1, heads // tp, 512), ref) < 5e-2
+
+
+def test_backend_draft_extend_and_idle():
+    """DRAFT_EXTEND runs the verify kernel shape (flashmla_backend.py:105-176); an IDLE batch (a data-parallel attention
+    rank without requests: batch_size 0, empty seq_lens) gets metadata and an empty result instead of an error."""
+    heads, draft = 16, 4
+    fb, mr, alloc, pool, layer = _runner(heads, draft_tokens=draft)
+    ctx = [150, 64]
+    bs = len(ctx)
+    ctx_locs = _fill_context(alloc, pool, layer, ctx)
+    backend = fb.FlashMLABackend(mr)
+    new_loc = torch.cat([alloc.alloc(i, draft, n) for i, n in enumerate(ctx)])
+    fbatch = SimpleNamespace(batch_size=bs, seq_lens=torch.tensor(ctx, device=DEV), req_pool_indices=torch.arange(bs, device=DEV),
+                             out_cache_loc=new_loc, token_to_kv_pool=pool, forward_mode=fb.ForwardMode.DRAFT_EXTEND)
+    backend.init_forward_metadata(fbatch)
+    torch.manual_seed(6)
+    q = torch.randn(bs * draft, heads * 576, dtype=torch.bfloat16, device=DEV)
+    k_new = torch.randn(bs * draft, 1, 576, dtype=torch.bfloat16, device=DEV)
+    out = backend.forward(q, k_new, k_new[..., :512], layer, fbatch)
+    all_locs = [torch.cat([ctx_locs[i], new_loc[i * draft:(i + 1) * draft]]) for i in range(bs)]
+    ref = _reference(pool, layer, q.view(bs, draft, heads, 576), all_locs, draft, True)
+    assert _rel(out.view(bs, draft, heads, 512), ref) < 5e-2
+    # IDLE
+    fb2, mr2, alloc2, pool2, layer2 = _runner(heads)
+    idle_backend = fb2.FlashMLABackend(mr2)
+    idle = SimpleNamespace(batch_size=0, seq_lens=torch.empty(0, dtype=torch.int64, device=DEV),
+                           req_pool_indices=torch.empty(0, dtype=torch.int64, device=DEV),
+                           out_cache_loc=torch.empty(0, dtype=torch.int32, device=DEV), token_to_kv_pool=pool2,
+                           forward_mode=fb2.ForwardMode.IDLE)
+    idle_backend.init_forward_metadata(idle)
+    meta = idle_backend.forward_metadata
+    assert meta.num_splits.cpu().tolist() == [0] and meta.block_table.shape[0] == 0
+    assert (meta.flashmla_metadata[:, 0] >= 0).all()          # every part starts at request 0 >= batch: no work
+    out = idle_backend.forward_decode(torch.empty(0, heads * 576, dtype=torch.bfloat16, device=DEV), None, None, layer2, idle)
+    assert out.shape == (0, heads * 512)
+    torch.cuda.synchronize()
+
+
+def test_backend_prefill_is_delegated_when_a_prefill_backend_is_registered():
+    """EXTEND / MIXED go to the reference's FlashInferMLAAttnBackend (flashmla_backend.py:100-104, 289-290): here a
+    registered delegate built with the constructor's arguments; without one the call raises."""
     heads = 16
     fb, mr, alloc, pool, layer = _runner(heads)
-    ms = fb.FlashMLAMultiStepDecodeBackend(mr, topk=1, speculative_num_steps=3)
-    assert [b.multi_step_seqlen_incr for b in ms.attn_backends] == [0, 1, 2]
-    with pytest.raises(ValueError):
-        fb.FlashMLAMultiStepDecodeBackend(mr, topk=2, speculative_num_steps=2)
+    calls = []
+
+    class Prefill:
+        def __init__(self, *a):
+            calls.append(("init", a))
+
+        def init_forward_metadata(self, forward_batch):
+            calls.append(("meta", forward_batch.forward_mode))
+
+        def forward_extend(self, q, k, v, layer, forward_batch, save_kv_cache, q_pe, k_pe):
+            calls.append(("extend", save_kv_cache))
+            return "prefill-result"
+
+    fbatch = SimpleNamespace(batch_size=1, forward_mode=fb.ForwardMode.EXTEND)
+    plain = fb.FlashMLABackend(mr)
+    with pytest.raises(NotImplementedError):
+        plain.forward_extend(None, None, None, layer, fbatch)
+    with pytest.raises(RuntimeError):
+        plain.init_forward_metadata(fbatch)
+    fb.set_prefill_backend_factory(lambda *a: Prefill(*a))
+    try:
+        backend = fb.FlashMLABackend(mr, False, "kv_indptr", "q_indptr")
+        assert fb.FlashMLABackend(mr, skip_prefill=True).prefill_backend is None
+    finally:
+        fb.set_prefill_backend_factory(None)
+    assert calls[0] == ("init", (mr, False, "kv_indptr", "q_indptr"))
+    backend.init_forward_metadata(fbatch)
+    assert backend.forward(None, None, None, layer, fbatch) == "prefill-result"
+    fbatch.forward_mode = fb.ForwardMode.MIXED
+    backend.init_forward_metadata(fbatch)
+    assert [c[0] for c in calls] == ["init", "meta", "extend", "meta"]
 
 
 @pytest.mark.parametrize("m,n,k", [(5, 192, 256), (128, 2112, 1536)])
@@ -206,7 +336,7 @@ def test_fp8_linear_method_apply(m, n, k):
     layer = torch.nn.Module()
     method.create_weights(layer, k, [n], k, n, torch.bfloat16, device=DEV)
     w = (torch.randn(n, k, device=DEV) * k ** -0.5).to(torch.bfloat16)
-    w8, ws = dg.per_block_cast_to_fp8(w)
+    w8, ws = quantize_rhs_128x128(w)
     layer.weight.data.copy_(w8)
     layer.weight_scale_inv.data.copy_(ws)
     method.process_weights_after_loading(layer)

@@ -8,6 +8,7 @@ import torch
 
 from oracle import fp8 as ofp8
 from oracle import gemm as ogemm
+from helpers import quantize_lhs_1x128, quantize_rhs_128x128, similarity_diff
 
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
@@ -34,8 +35,8 @@ def construct_grouped(dg, num_groups, m, k, n, seed):
     y8 = torch.empty_like(y, dtype=torch.float8_e4m3fn)
     ys = torch.empty(num_groups, (n + 127) // 128, k // 128, dtype=torch.float32, device=DEV)
     for g in range(num_groups):
-        x8[g], xs[g] = dg.per_token_cast_to_fp8(x[g])
-        y8[g], ys[g] = dg.per_block_cast_to_fp8(y[g])
+        x8[g], xs[g] = quantize_lhs_1x128(x[g])
+        y8[g], ys[g] = quantize_rhs_128x128(y[g])
     return x, y, x8, xs, y8, ys
 
 
@@ -66,7 +67,7 @@ def test_grouped_contiguous_vs_oracle(dg, num_groups, m, k, n):
             row += 128
         got = out[row:row + m].float().cpu()
         assert rel(got.numpy(), oracle_group(x8[g], xs[g], y8[g], ys[g])) < 3e-3
-        assert dg.calc_diff(got, (x[g].float() @ y[g].float().t()).cpu()) < 1e-3
+        assert similarity_diff(got, (x[g].float() @ y[g].float().t()).cpu()) < 1e-3
         row += m
 
 
@@ -86,7 +87,7 @@ def test_grouped_masked_vs_oracle(dg, num_groups, m, k, n):
             continue
         got = out[g, :mm].float().cpu()
         assert rel(got.numpy(), oracle_group(x8[g, :mm], xs[g, :mm], y8[g], ys[g])) < 3e-3
-        assert dg.calc_diff(got, (x[g, :mm].float() @ y[g].float().t()).cpu()) < 1e-3
+        assert similarity_diff(got, (x[g, :mm].float() @ y[g].float().t()).cpu()) < 1e-3
 
 
 @pytest.mark.parametrize("lens,k,n", [([5], 512, 256), ([130, 0, 1, 127, 64], 512, 256), ([3, 250, 129, 2, 77, 300], 2048, 1792),
@@ -113,7 +114,7 @@ def test_grouped_offset_vs_oracle(dg, lens, k, n):
         got = out[int(off[g]):int(off[g + 1])].float().cpu()
         assert rel(got.numpy(), oracle_group(x8[g, :lens[g]], xs[g, :lens[g]], y8[g], ys[g])) < 3e-3
         if lens[g] >= 16:
-            assert dg.calc_diff(got, (x[g, :lens[g]].float() @ y[g].float().t()).cpu()) < 1e-3
+            assert similarity_diff(got, (x[g, :lens[g]].float() @ y[g].float().t()).cpu()) < 1e-3
 
 
 def test_grouped_layouts_agree(dg):

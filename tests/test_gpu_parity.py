@@ -22,6 +22,7 @@ from oracle import fp8 as ofp8
 from oracle import gemm as ogemm
 from oracle import mla as omla
 from oracle import pool as opool
+from helpers import quantize_lhs_1x128, quantize_rhs_128x128, similarity_diff
 
 pytestmark = pytest.mark.gpu
 
@@ -177,8 +178,8 @@ def test_fp8_gemm_vs_oracle(mods, m, n, k):
     torch.manual_seed(m * 7 + n)
     x = torch.randn(m, k, dtype=torch.bfloat16, device=DEV)
     w = torch.randn(n, k, dtype=torch.bfloat16, device=DEV)
-    a8, a_s = dg.per_token_cast_to_fp8(x)
-    w8, w_s = dg.per_block_cast_to_fp8(w)
+    a8, a_s = quantize_lhs_1x128(x)
+    w8, w_s = quantize_rhs_128x128(w)
     c = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
     for _ in range(2):  # second call checks the self-cleaning split-K workspace
         dg.gemm_fp8_fp8_bf16_nt((a8, dg.get_col_major_tma_aligned_tensor(a_s)), (w8, w_s), c, True)
@@ -187,9 +188,35 @@ def test_fp8_gemm_vs_oracle(mods, m, n, k):
                                       ofp8.e4m3_to_f32(w8.view(torch.uint8).cpu().numpy()), w_s.cpu().numpy())
     got = c.float().cpu().numpy()
     assert rel(got, ref) < 3e-3
-    assert dg.calc_diff(c.float().cpu(), torch.from_numpy(ref)) < 1e-3  # test_core.py:71-72
+    assert similarity_diff(c.float().cpu(), torch.from_numpy(ref)) < 1e-3  # test_core.py:71-72
     # and against the un-quantised product, the reference test's own comparison
-    assert dg.calc_diff(c.float().cpu(), (x.float() @ w.float().t()).cpu()) < 1e-3
+    assert similarity_diff(c.float().cpu(), (x.float() @ w.float().t()).cpu()) < 1e-3
+
+
+@pytest.mark.parametrize("m", [256, 4096])
+@pytest.mark.parametrize("n,k", [(7168, 2048), (4096, 7168)])
+def test_fp8_gemm_baseline_microbench_points(mods, m, n, k):
+    """The BASELINE.json GEMM shapes at the decode batch 256 and at the compute-bound m = 4096: calc_diff < 1e-3 against
+    the oracle's two-level accumulation, evaluated on sampled output rows (the fp32 oracle is a CPU matmul)."""
+    dg = mods[2]
+    torch.manual_seed(m + n)
+    x = torch.randn(m, k, dtype=torch.bfloat16, device=DEV)
+    w = torch.randn(n, k, dtype=torch.bfloat16, device=DEV)
+    a8, a_s = quantize_lhs_1x128(x)
+    w8, w_s = quantize_rhs_128x128(w)
+    c = torch.full((m, n), float("nan"), dtype=torch.bfloat16, device=DEV)
+    dg.gemm_fp8_fp8_bf16_nt((a8, dg.get_col_major_tma_aligned_tensor(a_s)), (w8, w_s), c, True)
+    torch.cuda.synchronize()
+    assert not torch.isnan(c).any()
+    rows = torch.arange(0, m, max(1, m // 96))[:96]          # rows spread over every 128-row tile class
+    ref = ogemm.w8a8_block_fp8_matmul(ofp8.e4m3_to_f32(a8[rows.to(DEV)].view(torch.uint8).cpu().numpy()),
+                                      a_s[rows.to(DEV)].cpu().numpy(),
+                                      ofp8.e4m3_to_f32(w8.view(torch.uint8).cpu().numpy()), w_s.cpu().numpy())
+    got = c[rows.to(DEV)].float().cpu().numpy()
+    assert rel(got, ref) < 3e-3
+    assert similarity_diff(torch.from_numpy(got), torch.from_numpy(ref)) < 1e-3
+    # every row against the un-quantised product on the GPU (the reference test's own comparison)
+    assert similarity_diff(c.float().cpu(), (x.float() @ w.float().t()).cpu()) < 1e-3
 
 
 def test_fp8_gemm_golden(mods, golden_dir):
@@ -383,6 +410,80 @@ def test_mla_full_size_vs_faithful_oracle(mods, name, b, seq, h, s_q, sample):
     for i in sample:
         assert rel(out[i], fo[i]) < 1e-2, (i, rel(out[i], fo[i]))
         assert np.allclose(lse[i], fl[i], rtol=1e-3, atol=1e-3)
+
+
+def test_mla_combine_direct_vs_oracle(mods):
+    """a-5 on its own: b200_mla_combine through the C ABI against oracle.combine_partials (itself within one bf16 ulp of
+    the reference kernel's source run on CPU): requests with 1 (untouched), 2, 3 and 7 splits, -inf partials (a split
+    whose rows saw no token), an all -inf row (lse = +inf, out = 0); <= 1 bf16 ulp on out, lse to 1e-6."""
+    L = mods[0].lib()
+    rng = np.random.default_rng(7)
+    h, s_q, dv = 16, 2, 512
+    M = h * s_q
+    n_splits = [1, 2, 3, 7, 1, 2]
+    b = len(n_splits)
+    ns = np.concatenate([[0], np.cumsum(n_splits)]).astype(np.int32)
+    total = int(ns[-1])
+    o_acc = rng.standard_normal((total, M, dv)).astype(np.float32)
+    lse_acc = (rng.standard_normal((total, M)) * 3).astype(np.float32)
+    lse_acc[ns[2] + 1, :5] = -np.inf          # one split of request 2 empty for 5 rows
+    lse_acc[ns[5]:ns[5] + 2, 3] = -np.inf     # a row of request 5 with no token in any split
+    out0 = rng.standard_normal((b, M, dv)).astype(np.float32)
+    out0 = ofp8.round_to_bf16(out0)
+    lse0 = rng.standard_normal((b, M)).astype(np.float32)
+    want_out, want_lse = out0.copy(), lse0.copy()
+    omla.combine_partials(o_acc, lse_acc, ns, want_out, want_lse)
+    d_o, d_l, d_ns = torch.from_numpy(o_acc).to(DEV), torch.from_numpy(lse_acc).to(DEV), torch.from_numpy(ns).to(DEV)
+    out = torch.from_numpy(out0).to(torch.bfloat16).to(DEV)                    # [b, s_q * h, dv]
+    lse = torch.from_numpy(lse0).to(DEV)                                       # flat [b, M]; (h, s_q) permutation below
+    # the kernel writes lse as [b, h, s_q] (flash_api.cpp:392-394); row m of the partials is (s, hh) = (m // h, m % h)
+    lse_hs = lse.view(b, s_q, h).transpose(1, 2).contiguous()
+    mods[0].check(L.b200_mla_combine(d_o.data_ptr(), d_l.data_ptr(), d_ns.data_ptr(), out.data_ptr(), lse_hs.data_ptr(),
+                                     b, s_q, h, 0, mods[0].current_stream()), "combine")
+    torch.cuda.synchronize()
+    got_out = out.float().cpu().numpy()
+    got_lse = lse_hs.transpose(1, 2).contiguous().view(b, M).cpu().numpy()
+    for i, n in enumerate(n_splits):
+        if n == 1:                               # mla_combine.cu:31-33: single-split requests are not touched
+            assert np.array_equal(got_out[i], out0[i]) and np.array_equal(got_lse[i], lse0[i])
+    ulp = np.abs(got_out - want_out) / np.maximum(np.abs(want_out), 1e-30)
+    assert (ulp <= 2.0 ** -7).all(), ulp.max()   # one bf16 ulp
+    assert np.isposinf(got_lse[5, 3]) and np.isposinf(want_lse[5, 3]) and (got_out[5, 3] == 0).all()
+    fin = np.isfinite(want_lse)
+    assert np.array_equal(fin, np.isfinite(got_lse)) and np.allclose(got_lse[fin], want_lse[fin], rtol=1e-6, atol=1e-6)
+
+
+def test_metadata_idle_batch(mods):
+    """batch_size 0 (an IDLE data-parallel attention rank, flash_api.cpp:27-63 accepts it): num_splits = [0] and no part
+    has work."""
+    fm = mods[1]
+    meta, ns = fm.get_mla_metadata(torch.empty(0, dtype=torch.int32, device=DEV), 16, 1)
+    assert ns.cpu().tolist() == [0] and meta.shape[1] == 8
+    assert (meta[:, 0] >= 0).all() and (meta[:, 2] == -1).all()
+
+
+@pytest.mark.parametrize("h,s_q", [(64, 1), (16, 4), (48, 1)])
+def test_mla_m_le_64_default_routing(mods, h, s_q):
+    """32 < M <= 64 fills one CTA of the pair kernel by default (faster than the single-CTA SwapAB kernel at HB = 64)."""
+    fm = mods[1]
+    c = make_case(fm, 3, h, s_q, [700, 129, 65])
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, s_q > 1)
+    fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=s_q > 1)
+    assert rel(out, fo) < 1e-2 and np.allclose(lse, fl, rtol=1e-3, atol=1e-3)
+
+
+def test_mla_m_le_64_swapab_routing_in_a_subprocess():
+    """The other side of the routing knob (B200_MLA_PAIR_MIN_M=64: SwapAB kernel with HB = 64); the knob is read once per
+    process, hence the subprocess."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, B200_MLA_PAIR_MIN_M="64")
+    here = os.path.dirname(os.path.abspath(__file__))
+    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-k",
+                        "m_le_64_default_routing or ragged-h64 or sq2-causal-h64"], env=env, capture_output=True, text=True,
+                       timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
 
 
 def test_mla_decode_low_noise_input_is_tight(mods):

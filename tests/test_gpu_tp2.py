@@ -1,0 +1,104 @@
+"""Two GPUs, NCCL: the tensor-parallel partition of the attention block (heads / column-parallel q_b_proj / row-parallel
+o_proj + ONE all-reduce, sglang_fluentllm_b200/tp.py) computed with the CUDA kernels must equal the unsharded block to
+bf16 tolerance (reference: python/sglang/srt/layers/linear.py:199,963,1139, flashmla_backend.py:67-75).
+Runs under `gpurun --gpus 2`; skipped on a single-GPU box."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+pytestmark = pytest.mark.gpu
+
+HEADS, D_QK, D_V, Q_LORA, HIDDEN, B, SEQ = 32, 192, 128, 1536, 2048, 24, 700
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _build(dev, plan_rank, plan_size):
+    """Everything is generated from fixed seeds on every rank, so the ranks (and the unsharded run) hold identical
+    weights, pool and inputs."""
+    from sglang_fluentllm_b200 import deep_gemm as dg, flash_mla_fp8 as fm, fp8_kernel as fk, tp
+    from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
+    g = torch.Generator(device=dev).manual_seed(1234)
+    w_q_b = dummy_block_fp8_weight(HEADS * D_QK, Q_LORA, dev, g)
+    w_o = dummy_block_fp8_weight(HIDDEN, HEADS * D_V, dev, g)
+    w_kc = (torch.randn(HEADS, 128, 512, device=dev, generator=g) * 128 ** -0.5).to(torch.bfloat16)   # absorb: q_nope -> latent
+    w_vc = (torch.randn(HEADS, 512, D_V, device=dev, generator=g) * 512 ** -0.5).to(torch.bfloat16)   # latent out -> v head
+    q_a = torch.randn(B, Q_LORA, device=dev, generator=g).to(torch.bfloat16)
+    pages = (SEQ + 63) // 64 + 1
+    n_pages = B * pages + 1
+    kv = torch.randn(n_pages * 64, 1, 576, device=dev, generator=g).to(torch.bfloat16)
+    kl = torch.zeros(n_pages * 64, 1, 512, dtype=torch.uint8, device=dev)
+    ks = torch.zeros(n_pages * 64, 1, 1, dtype=torch.float32, device=dev)
+    kr = torch.zeros(n_pages * 64, 1, 64, dtype=torch.bfloat16, device=dev)
+    fm.quantize_and_cache_k(kv, kl, ks, kr, torch.arange(n_pages * 64, dtype=torch.int32, device=dev), 512)
+    bt = (torch.arange(B * pages, device=dev).reshape(B, pages) + 1).to(torch.int32)
+    sl = torch.full((B,), SEQ, dtype=torch.int32, device=dev)
+    plan = tp.TpPlan(rank=plan_rank, size=plan_size, num_heads=HEADS, qk_head_dim=D_QK, v_head_dim=D_V)
+    h0, h1 = plan.head_range
+
+    def linear(x, ws):
+        w, s = ws
+        xq, xs = fk.sglang_per_token_group_quant_fp8(x.contiguous(), 128, column_major_scales=True, scale_tma_aligned=True)
+        y = torch.empty(x.shape[0], w.shape[0], dtype=torch.bfloat16, device=dev)
+        dg.gemm_fp8_fp8_bf16_nt((xq, xs), (w, s), y, False)
+        return y
+
+    def attention(q):  # [b, h_local, 192] -> [b, h_local, 128] over this rank's heads, full KV pool on every rank
+        hl = q.shape[1]
+        q_lat = torch.einsum("bhd,hdc->bhc", q[..., :128], w_kc[h0:h1])              # w_kc absorb (deepseek_v2.py:840)
+        q_abs = torch.cat([q_lat, q[..., 128:]], dim=-1).unsqueeze(1).contiguous()   # [b, 1, h_local, 576]
+        qn, qs, qr = fm.quantize_ckv_per_token_head(q_abs, 512)
+        meta, ns = fm.get_mla_metadata(sl, hl, 1)
+        o, _ = fm.flash_mla_ckv_fp8_per_token(qn, qr, kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), qs,
+                                              ks.view(n_pages, 64, 1, 1), bt, sl, 512, meta, ns, softmax_scale=192 ** -0.5)
+        return torch.einsum("bhc,hcd->bhd", o[:, 0], w_vc[h0:h1])                     # w_vc absorb (deepseek_v2.py:886)
+
+    return tp.TensorParallelAttentionBlock(plan, w_q_b, w_o, linear, attention), q_a
+
+
+def _worker(rank, world, port, out_path):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cuda", rank)
+        block, q_a = _build(dev, rank, world)
+        y = block.forward(q_a)                      # all-reduced: identical on both ranks
+        torch.cuda.synchronize()
+        gathered = [torch.empty_like(y) for _ in range(world)]
+        dist.all_gather(gathered, y)
+        if rank == 0:
+            assert torch.equal(gathered[0], gathered[1])
+            single, q_a1 = _build(dev, 0, 1)        # the unsharded block on one GPU (no process-group exchange: size 1)
+            single.group = None
+            p = single.plan
+            q = single.linear(q_a1, single.w_q_b)
+            o = single.attention(q.view(B, HEADS, D_QK))
+            ref = single.linear(o.reshape(B, HEADS * D_V), single.w_o)
+            torch.cuda.synchronize()
+            np.savez(out_path, y=y.float().cpu().numpy(), ref=ref.float().cpu().numpy())
+    finally:
+        dist.destroy_process_group()
+
+
+def test_tp2_block_equals_unsharded_block(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    out_path = str(tmp_path / "tp2.npz")
+    mp.spawn(_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    r = np.load(out_path)
+    rel = np.linalg.norm(r["y"] - r["ref"]) / np.linalg.norm(r["ref"])
+    # the sharded run rounds each rank's partial o_proj sums to bf16 before the all-reduce and re-quantises per-rank
+    # activations: bf16-level agreement
+    assert rel < 1e-2, rel

@@ -1,10 +1,14 @@
 """CPU: host-side logic of the Python mirrors (layout helpers, argument checking) -- no GPU needed."""
+import os
+import sys
+
 import numpy as np
 import types
 
 import pytest
 import torch
 
+from helpers import quantize_lhs_1x128, quantize_rhs_128x128, similarity_diff
 from sglang_fluentllm_b200 import deep_gemm as dg
 from sglang_fluentllm_b200 import flash_mla_fp8 as fm
 from sglang_fluentllm_b200 import fp8_kernel as fk
@@ -22,12 +26,12 @@ def test_col_major_tma_aligned_tensor_layout():
 def test_per_token_and_per_block_cast_roundtrip():
     torch.manual_seed(0)
     x = torch.randn(9, 256, dtype=torch.bfloat16)
-    q, s = dg.per_token_cast_to_fp8(x)
+    q, s = quantize_lhs_1x128(x)
     assert q.dtype == torch.float8_e4m3fn and s.shape == (9, 2)
     deq = q.float().view(9, 2, 128) * s.unsqueeze(-1)
     assert (deq.view(9, 256) - x.float()).abs().max() < 0.07 * x.float().abs().max()
     w = torch.randn(130, 256, dtype=torch.bfloat16)
-    wq, ws = dg.per_block_cast_to_fp8(w)
+    wq, ws = quantize_rhs_128x128(w)
     assert wq.shape == (130, 256) and ws.shape == (2, 2)
 
 
@@ -79,10 +83,10 @@ def test_fused_prologue_rejects_cpu_tensors_and_bad_caches():
                                             types.SimpleNamespace(token_to_kv_pool=pool, out_cache_loc=None))
 
 
-def test_calc_diff():
+def test_similarity_diff():
     x = torch.randn(100)
-    assert dg.calc_diff(x, x) < 1e-12
-    assert dg.calc_diff(x, -x) > 1.9
+    assert similarity_diff(x, x) < 1e-12
+    assert similarity_diff(x, -x) > 1.9
 
 
 def test_fp8_config_and_linear_method_mirror_reference_rules():
@@ -130,10 +134,12 @@ def test_install_redirects_the_references_imports():
     import importlib
     import sys
     from sglang_fluentllm_b200 import install as inst
-    for name in ("flash_mla_fp8", "flash_mla_swap", "deep_gemm"):
+    for name in ("flash_mla_fp8", "flash_mla_swap", "deep_gemm", "sglang.srt.layers.attention.flashmla_backend"):
         assert name not in sys.modules
     inst.install()
     try:
+        from sglang_fluentllm_b200 import flashmla_backend as our_backend
+        assert sys.modules["sglang.srt.layers.attention.flashmla_backend"] is our_backend   # base_spec_worker.py:233-240
         import deep_gemm as ref_name_dg
         import flash_mla_fp8 as ref_name_fm
         assert ref_name_fm is fm and ref_name_dg is dg
@@ -155,8 +161,98 @@ def test_install_redirects_the_references_imports():
         inst.uninstall()
         sys.modules.pop("deep_gemm", None)
     assert "flash_mla_fp8" not in sys.modules and "flash_mla_swap" not in sys.modules
+    assert "sglang.srt.layers.attention.flashmla_backend" not in sys.modules
     fake = types.ModuleType("attn_initializer")
     inst.patch_attention_initializer(fake)
     from sglang_fluentllm_b200 import flashmla_backend as fb
     assert fake.FlashMLABackend is fb.FlashMLABackend
     assert fake.FlashMLAMultiStepDecodeBackend is fb.FlashMLAMultiStepDecodeBackend
+
+
+REFERENCE_PY = "/root/reference/python"
+
+
+@pytest.mark.skipif(not os.path.isdir(REFERENCE_PY), reason="the reference tree only exists in the build container")
+def test_backend_metadata_path_on_the_references_own_pool_and_allocator(monkeypatch):
+    """The plug-in reads ``model_runner.kv_allocator.req_to_page`` and ``forward_batch.token_to_kv_pool`` -- here the
+    REFERENCE's KVAllocator (mem_cache/allocator.py) and MLATokenToKVPool (mem_cache/memory_pool.py, per-token FP8
+    layout), imported from /root/reference through the stub hook of tests/golden/make_golden.py and living on the CPU.
+    init_forward_metadata / the CUDA-graph capture + replay protocol must produce the allocator's block table bit for bit
+    and hand the kernel module the lengths the reference hands it (flashmla_backend.py:258-405); the metadata kernel
+    itself is replaced by the oracle (no GPU here), so the integers are the reference scheduler's."""
+    import importlib.util
+    from types import SimpleNamespace
+    from oracle import mla as omla
+    from sglang_fluentllm_b200 import flashmla_backend as fb
+    spec = importlib.util.spec_from_file_location("make_golden", os.path.join(os.path.dirname(__file__), "golden", "make_golden.py"))
+    mg = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mg)
+    finder = mg._Finder()
+    sys.meta_path.insert(0, finder)
+    sys.path.insert(0, REFERENCE_PY)
+    before = set(sys.modules)
+    try:
+        from sglang.srt.mem_cache.allocator import KVAllocator
+        from sglang.srt.mem_cache.memory_pool import MLATokenToKVPool
+        alloc = KVAllocator(size=64 * 64, device="cpu", max_batch_size=8, max_context_len=1024, page_size=64)
+        pool = MLATokenToKVPool(size=64 * 64, model_dtype=torch.bfloat16, dtype=torch.float8_e4m3fn,
+                                quant_method="per_token_head", kv_lora_rank=512, qk_rope_head_dim=64, layer_num=2,
+                                device="cpu", enable_memory_saver=False, max_batch_size=8, max_context_len=1024,
+                                page_size=64, rank=0, enable_alt_stream=False)
+        ctx = {3: 200, 1: 65, 7: 1000}
+        for req, n in ctx.items():
+            assert alloc.alloc(req, n, 0) is not None
+        seen = []
+
+        def oracle_metadata(cache_seqlens, num_heads_per_head_k, num_heads_k):
+            seen.append((cache_seqlens.clone(), num_heads_per_head_k, num_heads_k))
+            meta, ns = omla.get_mla_metadata(cache_seqlens.numpy(), num_heads_per_head_k, num_heads_k, 148)
+            return torch.from_numpy(meta), torch.from_numpy(ns)
+
+        monkeypatch.setattr(fb.flash_mla_fp8, "get_mla_metadata", oracle_metadata)
+        cfg = SimpleNamespace(scaling=192 ** -0.5, num_attention_heads=128, kv_lora_rank=512, qk_nope_head_dim=128,
+                              qk_rope_head_dim=64, v_head_dim=512, context_len=1024)
+        mr = SimpleNamespace(model_config=cfg, server_args=SimpleNamespace(speculative_algorithm=None),
+                             kv_cache_dtype=pool.dtype, kv_cache_quant_method=pool.quant_method, kv_allocator=alloc,
+                             dtype=torch.bfloat16, device="cpu")
+        fb.set_attention_tp_size_getter(lambda: 8)
+        try:
+            backend = fb.FlashMLABackend(mr)
+        finally:
+            fb.set_attention_tp_size_getter(None)
+        assert backend.num_q_heads == 16
+        reqs = torch.tensor([7, 1, 3])
+        seq_lens = torch.tensor([ctx[7] + 1, ctx[1] + 1, ctx[3] + 1])
+        fbatch = SimpleNamespace(batch_size=3, seq_lens=seq_lens, req_pool_indices=reqs, token_to_kv_pool=pool,
+                                 forward_mode=fb.ForwardMode.DECODE)
+        backend.init_forward_metadata(fbatch)
+        md = backend.forward_metadata
+        assert torch.equal(md.block_table, alloc.req_to_page[reqs]) and md.block_table.dtype == torch.int32
+        lens, m, hk = seen[-1]
+        assert lens.dtype == torch.int32 and lens.tolist() == seq_lens.tolist() and (m, hk) == (16, 1)
+        want_meta, want_ns = omla.get_mla_metadata(seq_lens.numpy(), 16, 1, 148)
+        assert np.array_equal(md.flashmla_metadata.numpy(), want_meta) and np.array_equal(md.num_splits.numpy(), want_ns)
+        # the three tensors per layer the kernel call receives are the reference pool's own (views, no copies)
+        k_lora, k_scale, k_rope = pool.get_key_buffer(1)
+        assert k_lora.shape[1:] == (1, 512) and k_scale.shape[1:] == (1, 1) and k_rope.shape[1:] == (1, 64)
+        assert k_lora.view(-1, 64, 1, 512).data_ptr() == k_lora.data_ptr()
+        # CUDA-graph protocol (cuda_graph_runner.py:405-520): static buffers, capture, replay with grown sequences
+        backend.init_cuda_graph_state(max_bs=4)
+        assert backend.cuda_graph_kv_indices.shape == (4, (1024 + 63 + 256) // 64) and int(backend.cuda_graph_kv_indices.min()) == 1
+        backend.init_forward_metadata_capture_cuda_graph(3, 3, reqs, seq_lens, fb.ForwardMode.DECODE, None)
+        static_bt = backend.forward_metadata.block_table
+        assert static_bt.data_ptr() == backend.cuda_graph_kv_indices.data_ptr()
+        assert torch.equal(static_bt[:, : alloc.req_to_page.shape[1]], alloc.req_to_page[reqs])
+        assert alloc.alloc(1, 70, ctx[1]) is not None                 # request 1 grows past a page boundary
+        seq_lens2 = seq_lens + torch.tensor([0, 70, 0])
+        backend.init_forward_metadata_replay_cuda_graph(3, reqs, seq_lens2, int(seq_lens2.sum()), fb.ForwardMode.DECODE, None,
+                                                        seq_lens_cpu=seq_lens2)
+        assert backend.forward_metadata.block_table.data_ptr() == static_bt.data_ptr()   # refreshed in place
+        assert torch.equal(backend.forward_metadata.block_table[:, : alloc.req_to_page.shape[1]], alloc.req_to_page[reqs])
+        assert seen[-1][0].tolist() == seq_lens2.tolist()
+    finally:
+        sys.meta_path.remove(finder)
+        sys.path.remove(REFERENCE_PY)
+        for name in set(sys.modules) - before:
+            if name.split(".")[0] in mg.STUBS or name.split(".")[0] == "sglang":
+                del sys.modules[name]

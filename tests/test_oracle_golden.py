@@ -111,6 +111,20 @@ def test_block_fp8_golden(golden_dir):
     assert np.allclose(c, g["c"], rtol=1e-5, atol=1e-4)
 
 
+def test_test_side_quantisers_match_the_references(golden_dir):
+    """tests/helpers.py stands in for per_token_cast_to_fp8 / per_block_cast_to_fp8 of the reference's GEMM tests
+    (3rdparty/deep_gemm/tests/test_core.py:9-25): bit-equal codes and scales on the golden inputs."""
+    import torch
+    from helpers import quantize_lhs_1x128, quantize_rhs_128x128
+    g = _load(golden_dir, "block_fp8.npz")
+    xq, xs = quantize_lhs_1x128(torch.from_numpy(g["x"]).to(torch.bfloat16))
+    assert np.array_equal(xq.view(torch.uint8).numpy(), g["xq_cast"])
+    assert np.array_equal(xs.numpy().view(np.uint32), g["xs_cast"].view(np.uint32))
+    wq, ws = quantize_rhs_128x128(torch.from_numpy(g["w"]).to(torch.bfloat16))
+    assert np.array_equal(wq.view(torch.uint8).numpy(), g["wq"])
+    assert np.array_equal(ws.numpy().view(np.uint32), g["ws"].view(np.uint32))
+
+
 def test_semantic_vs_faithful_attention_agree():
     """The two attention restatements (plain fp64 softmax vs the reference's page-wise FP8-P recurrence) agree
     within the reference's own criterion (tests/test_flash_mla_ckv_fp8_per_token.py:32-39, rel < 5e-2)."""

@@ -4,7 +4,8 @@ import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-from sglang_fluentllm_b200 import flash_mla_fp8 as fm, deep_gemm as dg, _lib
+from sglang_fluentllm_b200 import flash_mla_fp8 as fm, deep_gemm as dg, fp8_kernel as fk, _lib
+from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
 
 dev = torch.device("cuda:0")
 PEAK = 6555.8
@@ -106,13 +107,9 @@ def bench_gemm(m, n, k, n_rot=None):
     wbytes = n * k
     if n_rot is None:
         n_rot = max(2, min(24, int(3e8 // wbytes) + 2))
-    ws_ = []
-    for _ in range(n_rot):
-        w = torch.randn(n, k, dtype=torch.bfloat16, device=dev)
-        ws_.append(dg.per_block_cast_to_fp8(w))
+    ws_ = [dummy_block_fp8_weight(n, k, dev) for _ in range(n_rot)]
     x = torch.randn(m, k, dtype=torch.bfloat16, device=dev)
-    a8, a_s = dg.per_token_cast_to_fp8(x)
-    a_s = dg.get_col_major_tma_aligned_tensor(a_s)
+    a8, a_s = fk.sglang_per_token_group_quant_fp8(x, 128, column_major_scales=True, scale_tma_aligned=True)
     out = torch.empty(m, n, dtype=torch.bfloat16, device=dev)
 
     def fn(i):
