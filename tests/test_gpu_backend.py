@@ -209,11 +209,14 @@ def test_multi_step_backend_matches_reference_signature_and_lengths():
     fbatch = SimpleNamespace(batch_size=bs, seq_lens=seq_lens, req_pool_indices=torch.arange(bs, device=DEV),
                              out_cache_loc=None, token_to_kv_pool=pool, forward_mode=fb.ForwardMode.DECODE,
                              spec_info=object())
+    # the scheduler reserves the slots of all draft tokens before the draft loop starts (the block table the metadata
+    # snapshots must already hold their pages)
+    draft_locs = [alloc.alloc(r, steps, n) for r, n in enumerate(ctx)]
     ms.init_forward_metadata(fbatch)                   # common_template: the first steps - 1 backends
     assert ms.attn_backends[0].forward_metadata is not None and ms.attn_backends[steps - 1].forward_metadata is None
     ms.attn_backends[steps - 1].init_forward_metadata(fbatch)
     for i in range(steps):
-        new_loc = torch.cat([alloc.alloc(r, 1, n + i) for r, n in enumerate(ctx)])
+        new_loc = torch.stack([draft_locs[r][i] for r in range(bs)])
         fbatch.out_cache_loc = new_loc
         q = torch.randn(bs, heads * 576, dtype=torch.bfloat16, device=DEV)
         k_new = torch.randn(bs, 1, 576, dtype=torch.bfloat16, device=DEV)
