@@ -1,19 +1,21 @@
 #!/usr/bin/env python
 """bench.py -- decode tokens/s of the quantised decode hot path (DeepSeek-V3 MLA, per-token-FP8 KV, bs=128, seq=4K).
 
-One "step" = one decode step of the hot path through all 61 layers for one batch: per layer
-  act-quant + FP8 GEMM (fused_qkv_a_proj shape) -> act-quant + FP8 GEMM (q_b_proj) -> fused prologue (rotary embedding
-  of q_pe / k_pe, q quantiser, quantise-and-cache of the new token's K: one launch) -> paged MLA decode over the FP8 KV
-  pool (+ split-KV combine) -> act-quant + FP8 GEMM (o_proj, row-parallel) -> [all-reduce when tp > 1].
-`--unfused-prologue` runs the reference's sequence instead (quantize_and_cache_k, a copy standing in for rope's write of
-Q's rope columns, quantize_ckv_per_token_head: three launches).
-The bf16 absorb bmm's (w_kc / w_vc) and norms are outside the path and are not run; the latent
-part of the absorbed q is a resident random tensor, its rope part and the o_proj input are slices of the producing
-GEMM / attention outputs, read in place by the strided activation quantiser (no torch copy kernels in the step).
+One "step" = one decode step of the attention block (models/deepseek_v2.py forward_absorb, :796-889) through all 61
+layers for one batch, driven through the plug-in API the reference's model runner uses: per layer
+  Fp8LinearMethod.apply (fused_qkv_a_proj: activation quantiser + block-FP8 GEMM) -> FusedRMSNorm of q_a / kv_a with
+  the q_b_proj input emitted block-quantised -> Fp8LinearMethod.apply (q_b_proj, block_scale supplied) -> w_kc absorb
+  (bf16 torch.bmm, the reference's own op) -> rotary embedding with the fused set_kv_buffer argument (rope of q_pe /
+  k_pe, Q quantiser, quantise-and-cache of the new token's K: one launch) -> FlashMLABackend.forward_decode (paged MLA
+  decode over the FP8 KV pool + split-KV combine) -> w_vc absorb (bmm) -> strided activation quantiser ->
+  Fp8LinearMethod.apply (o_proj, row-parallel) -> [all-reduce when tp > 1].
+The backend is used exactly as cuda_graph_runner.py:405-526 uses it: init_cuda_graph_state, capture-time metadata,
+the layer loop captured in a CUDA graph, and init_forward_metadata_replay_cuda_graph outside the graph before a replay.
 
 tokens/s = batch / step time.  `value` is timed with inputs resident in HBM (CUDA-graph replay of the step);
-`e2e` adds, inside the timed region, the pinned-host -> device copy of the step inputs (hidden states, block table,
-sequence lengths), the per-step metadata kernel and a device -> host read of the step output.
+`e2e` adds, inside the timed region, the pinned-host -> device copies of the step inputs (hidden states, sequence
+lengths, request slots, positions, cache slots, page-table rows), the backend's replay-metadata refresh (block-table
+gather + tile-scheduler kernel) and a device -> host read of the step output.
 
 Multi-GPU (torchrun, one rank per GPU).  Default `--parallelism dp`: one replica of the path per GPU with the per-GPU
 batch fixed at 128 (weak scaling, no data-path collective) -- MLA has a single latent KV head, so under head tensor
@@ -59,14 +61,10 @@ def parse():
                          "column- and row-parallel weights over the GPUs with one all-reduce per layer (strong scaling; "
                          "MLA's single latent KV head makes every rank stream the whole KV pool).  The dp run also "
                          "reports a short tp measurement under \"tp_strong\".")
-    ap.add_argument("--unfused-prologue", action="store_true",
-                    help="run quantize_and_cache_k / rope stand-in copy / quantize_ckv_per_token_head as separate "
-                         "launches instead of the fused prologue kernel (A/B)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for an ncu launch list of the step)")
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--kernel-only", action="store_true", help="time only the MLA decode kernel per layer")
     return ap.parse_args()
 
 
@@ -147,140 +145,183 @@ class ClockSampler:
 # the B200 arm
 # ----------------------------------------------------------------------------------------------------------------
 class HotPath:
-    """All device state of the benchmarked step for one rank."""
+    """The benchmarked step for one rank, built the way the reference's model runner builds it around the plug-in:
+    a KVAllocator + MLATokenToKVPool (per-token-FP8 layout), ONE FlashMLABackend driven through the CUDA-graph protocol
+    of cuda_graph_runner.py:405-526 (init_cuda_graph_state -> ...capture_cuda_graph -> graph capture of the layer loop ->
+    per step ...replay_cuda_graph outside the graph + replay), Fp8LinearMethod.apply for the three block-FP8 linears,
+    FusedRMSNorm for q_a / kv_a, the rotary-embedding prologue with the fused set_kv_buffer argument, and the w_kc / w_vc
+    absorb bmm's (models/deepseek_v2.py:796-889, forward_absorb).  No stand-ins: the step is a runnable attention block."""
 
     def __init__(self, args, rank, world, dev):
         import torch
+        from types import SimpleNamespace
 
-        from sglang_fluentllm_b200 import deep_gemm as dg
-        from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
-        self.torch, self.dg, self.args, self.dev, self.world = torch, dg, args, dev, world
+        from sglang_fluentllm_b200 import flash_mla_fp8 as fm
+        from sglang_fluentllm_b200 import flashmla_backend as fb
+        from sglang_fluentllm_b200 import fp8_kernel as fk
+        from sglang_fluentllm_b200 import fp8_linear as fl
+        from sglang_fluentllm_b200 import layernorm as ln
+        from sglang_fluentllm_b200 import rope as rope_mod
         from sglang_fluentllm_b200 import tp as tpmod
-        self.tpmod = tpmod
+        self.torch, self.args, self.dev, self.world = torch, args, dev, world
+        self.fm, self.fb, self.fk, self.rope_mod, self.tpmod = fm, fb, fk, rope_mod, tpmod
         tp = world if args.parallelism == "tp" else 1
         self.tp = tp
         b, seq, L = args.batch, args.seq, args.layers
         # heads / column-parallel q_b_proj rows / row-parallel o_proj columns of this rank (sglang_fluentllm_b200/tp.py)
         self.plan = tpmod.TpPlan(rank if tp > 1 else 0, tp, args.heads, NOPE_HEAD + ROPE, V_HEAD)
-        self.h = self.plan.heads_per_rank
-        h = self.h
+        self.h = h = self.plan.heads_per_rank
         g = torch.Generator(device=dev)
         g.manual_seed(1234 + rank)
         pages_per_req = (seq + PAGE - 1) // PAGE + 1
         self.n_pages = b * pages_per_req + 1
         slots = self.n_pages * PAGE
-        # paged pool, per-token-FP8 layout (MLATokenToKVPool per_token_head), one triple per layer
-        from sglang_fluentllm_b200 import flash_mla_fp8 as fm
-        self.fm = fm
-        self.k_lora, self.k_scale, self.k_rope = [], [], []
+        scaling = (NOPE_HEAD + ROPE) ** -0.5
+
+        # ---- the plug-in's surroundings: allocator (page table), pool, model-runner facade ----
+        ctx_len = pages_per_req * PAGE
+        self.alloc = fb.KVAllocator(size=slots, device=dev, max_batch_size=b, max_context_len=ctx_len)
+        # page table of a long-running server: every request owns `pages_per_req` shuffled physical pages (page 0 is the
+        # reserved padding page); the host copy is what the scheduler writes through on allocation
+        perm = (torch.randperm(self.n_pages - 1, generator=torch.Generator().manual_seed(7)) + 1).to(torch.int32)
+        self.page_table_host = perm[: b * pages_per_req].reshape(b, pages_per_req).contiguous().pin_memory()
+        self.alloc.req_to_page[:b, :pages_per_req].copy_(self.page_table_host)
+        self.pool = fb.MLATokenToKVPool(size=slots - PAGE, model_dtype=torch.bfloat16, kv_lora_rank=KV_LORA,
+                                        qk_rope_head_dim=ROPE, layer_num=L, device=dev, quant_method="per_token_head")
         tmp = torch.empty(slots, 1, KV_LORA + ROPE, dtype=torch.bfloat16, device=dev)
         idx = torch.arange(slots, dtype=torch.int32, device=dev)
-        for _ in range(L):
+        for l in range(L):  # N(0, 1) context, quantised by the path's own quantiser
             tmp.normal_(generator=g)
-            kl = torch.empty(slots, 1, KV_LORA, dtype=torch.uint8, device=dev)
-            ks = torch.empty(slots, 1, 1, dtype=torch.float32, device=dev)
-            kr = torch.empty(slots, 1, ROPE, dtype=torch.bfloat16, device=dev)
+            kl, ks, kr = self.pool.get_key_buffer(l)
             fm.quantize_and_cache_k(tmp, kl, ks, kr, idx, KV_LORA)
-            self.k_lora.append(kl), self.k_scale.append(ks), self.k_rope.append(kr)
         del tmp
-        # block table: shuffled physical pages (page 0 is the reserved padding page)
-        perm = (torch.randperm(self.n_pages - 1, generator=torch.Generator().manual_seed(7)) + 1).to(torch.int32)
-        self.block_table_host = perm[: b * pages_per_req].reshape(b, pages_per_req).contiguous().pin_memory()
-        self.seqlens_host = torch.full((b,), seq, dtype=torch.int32).pin_memory()
-        self.block_table = self.block_table_host.to(dev)
-        self.seqlens = self.seqlens_host.to(dev)
+        cfg = SimpleNamespace(scaling=scaling, num_attention_heads=args.heads, kv_lora_rank=KV_LORA,
+                              qk_nope_head_dim=NOPE_HEAD, qk_rope_head_dim=ROPE, v_head_dim=KV_LORA, context_len=ctx_len)
+        self.model_runner = SimpleNamespace(model_config=cfg, server_args=SimpleNamespace(speculative_algorithm=None),
+                                            kv_cache_dtype=torch.float8_e4m3fn, kv_cache_quant_method="per_token_head",
+                                            kv_allocator=self.alloc, dtype=torch.bfloat16, device=dev)
+        fb.set_attention_tp_size_getter(lambda: tp)    # what dp_attention.get_attention_tp_size() returns in the reference
+        try:
+            self.backend = fb.FlashMLABackend(self.model_runner)
+        finally:
+            fb.set_attention_tp_size_getter(None)
+        assert self.backend.num_q_heads == h
+        self.backend.init_cuda_graph_state(max_bs=b)
+        self.attn_layers = [SimpleNamespace(layer_id=l, tp_q_head_num=h, head_dim=KV_LORA + ROPE, v_head_dim=KV_LORA,
+                                            scaling=scaling) for l in range(L)]
+
+        # ---- step inputs: host copies (e2e) and the static device tensors the graph reads ----
         last = seq - 1
-        self.out_cache_loc = (self.block_table[:, last // PAGE].to(torch.int64) * PAGE + last % PAGE).to(torch.int32)
-        # rotary embedding inputs of the fused prologue: the new token's position, a cos | sin table of the model's layout
-        # (python/sglang/srt/layers/rotary_embedding.py:791-802)
-        self.positions = torch.full((b,), last, dtype=torch.int64, device=dev)
+        self.hidden_host = torch.randn(b, HIDDEN, dtype=torch.bfloat16).pin_memory()
+        self.seq_lens_host = torch.full((b,), seq, dtype=torch.int32).pin_memory()
+        self.req_pool_host = torch.arange(b, dtype=torch.int64).pin_memory()
+        self.positions_host = torch.full((b,), last, dtype=torch.int64).pin_memory()
+        loc = self.page_table_host[:, last // PAGE].to(torch.int64) * PAGE + last % PAGE
+        self.out_cache_loc_host = loc.to(torch.int32).pin_memory()
+        self.result_host = torch.empty(b, HIDDEN, dtype=torch.bfloat16).pin_memory()
+        self.hidden_in = self.hidden_host.to(dev)
+        self.seq_lens = self.seq_lens_host.to(dev)
+        self.req_pool_indices = self.req_pool_host.to(dev)
+        self.positions = self.positions_host.to(dev)
+        self.out_cache_loc = self.out_cache_loc_host.to(dev)
+        self.fbatch = SimpleNamespace(batch_size=b, seq_lens=self.seq_lens, req_pool_indices=self.req_pool_indices,
+                                      out_cache_loc=self.out_cache_loc, token_to_kv_pool=self.pool,
+                                      forward_mode=fb.ForwardMode.DECODE, spec_info=None)
         inv_freq = 1.0 / (10000.0 ** (torch.arange(0, ROPE, 2, dtype=torch.float32) / ROPE))
         freqs = torch.arange(seq, dtype=torch.float32)[:, None] * inv_freq[None, :]
         self.cos_sin_cache = torch.cat([freqs.cos(), freqs.sin()], dim=-1).contiguous().to(dev)
-        from sglang_fluentllm_b200 import rope as rope_mod
-        self.rope_mod = rope_mod
 
-        def weight(n, k):
-            return dummy_block_fp8_weight(n, k, dev, g)
+        # ---- weights (random init, the reference's --load-format dummy) ----
+        self.method = fl.Fp8LinearMethod(fl.Fp8Config(True, "dynamic", None, [128, 128]), tp_size=tp)
 
-        self.w_qkv_a = [weight(Q_LORA + KV_LORA + ROPE, HIDDEN) for _ in range(L)]          # replicated
-        self.w_q_b = [weight(h * (NOPE_HEAD + ROPE), Q_LORA) for _ in range(L)]              # column-parallel
-        self.w_o = [weight(HIDDEN, h * V_HEAD) for _ in range(L)]                            # row-parallel
-        self.hidden_host = torch.randn(b, HIDDEN, dtype=torch.bfloat16).pin_memory()
-        self.hidden_in = self.hidden_host.to(dev)
-        self.result_host = torch.empty(b, HIDDEN, dtype=torch.bfloat16).pin_memory()
-        # static activations
-        e = lambda *s, dt=torch.bfloat16: torch.empty(*s, dtype=dt, device=dev)
-        self.y_a = e(b, Q_LORA + KV_LORA + ROPE)
-        self.q_full = e(b, h * (NOPE_HEAD + ROPE))
-        self.q_abs = torch.randn(b, 1, h, KV_LORA + ROPE, dtype=torch.bfloat16, device=dev, generator=g)
-        self.attn_o = e(b, h * V_HEAD)
-        self.x = e(b, HIDDEN)
-        self.attn_out = e(b, 1, h, KV_LORA)
-        self.lse = e(b, h, 1, dt=torch.float32)
-        from sglang_fluentllm_b200 import _lib
-        self._lib = _lib
-        L_ = _lib.lib()
-        self.num_sm_parts = L_.b200_mla_num_sm_parts(h, 1, L_.b200_sm_count())
-        self.meta = torch.empty(self.num_sm_parts, 8, dtype=torch.int32, device=dev)
-        self.num_splits = torch.empty(b + 1, dtype=torch.int32, device=dev)
-        self.workspace = torch.empty(L_.b200_mla_workspace_bytes(b, 1, h, self.num_sm_parts), dtype=torch.uint8,
-                                     device=dev)
+        def linear(n, k, n_full, k_full):
+            layer = torch.nn.Module()
+            self.method.create_weights(layer, k, [n], k_full, n_full, torch.bfloat16, device=dev)
+            w, s = fl.dummy_block_fp8_weight(n, k, dev, g)
+            layer.weight.data.copy_(w)
+            layer.weight_scale_inv.data.copy_(s)
+            self.method.process_weights_after_loading(layer)
+            return layer
+
+        qk = NOPE_HEAD + ROPE
+        self.lin_qkv_a = [linear(Q_LORA + KV_LORA + ROPE, HIDDEN, Q_LORA + KV_LORA + ROPE, HIDDEN) for _ in range(L)]  # replicated
+        self.lin_q_b = [linear(h * qk, Q_LORA, args.heads * qk, Q_LORA) for _ in range(L)]             # column-parallel
+        self.lin_o = [linear(HIDDEN, h * V_HEAD, HIDDEN, args.heads * V_HEAD) for _ in range(L)]      # row-parallel
+        self.norms = []
+        for _ in range(L):
+            n = ln.FusedRMSNorm(ln.RMSNorm(Q_LORA, 1e-6, dev), ln.RMSNorm(KV_LORA, 1e-6, dev))
+            n.q_a_norm.weight.data.copy_((torch.rand(Q_LORA, device=dev, generator=g) + 0.5).to(torch.bfloat16))
+            n.kv_a_norm.weight.data.copy_((torch.rand(KV_LORA, device=dev, generator=g) + 0.5).to(torch.bfloat16))
+            self.norms.append(n)
+        bf = lambda *shape, std: (torch.randn(*shape, device=dev, generator=g) * std).to(torch.bfloat16)
+        self.w_kc = [bf(h, NOPE_HEAD, KV_LORA, std=NOPE_HEAD ** -0.5) for _ in range(L)]   # deepseek_v2.py:1629-1633
+        self.w_vc = [bf(h, KV_LORA, V_HEAD, std=KV_LORA ** -0.5) for _ in range(L)]
+        self.q_buf = torch.empty(b, h, KV_LORA + ROPE, dtype=torch.bfloat16, device=dev)  # "Q" of forward_absorb (:829-833)
         self.launches_per_step = 0
-        self.refresh_metadata()
+        self.backend.init_forward_metadata_capture_cuda_graph(b, b, self.req_pool_indices, self.seq_lens,
+                                                              fb.ForwardMode.DECODE, None)
+        # direct-kernel state for the roofline microbenchmark of the dominant kernel
+        self.attn_out = torch.empty(b, 1, h, KV_LORA, dtype=torch.bfloat16, device=dev)
+        self.lse = torch.empty(b, h, 1, dtype=torch.float32, device=dev)
+        from sglang_fluentllm_b200 import _lib
+        L_ = _lib.lib()
+        parts = L_.b200_mla_num_sm_parts(h, 1, L_.b200_sm_count())
+        self.workspace = torch.empty(L_.b200_mla_workspace_bytes(b, 1, h, parts), dtype=torch.uint8, device=dev)
 
-    def refresh_metadata(self):
-        L_ = self._lib.lib()
-        self._lib.check(L_.b200_mla_get_metadata(self.seqlens.data_ptr(), self.args.batch, self.num_sm_parts,
-                                                 self.meta.data_ptr(), self.num_splits.data_ptr(),
-                                                 self._lib.current_stream()), "get_mla_metadata")
+    def host_to_device(self):
+        """The step's inputs from pinned host memory (e2e): hidden states, sequence lengths, request slots, positions,
+        the new tokens' cache slots and the scheduler's page-table rows."""
+        nb = True
+        self.hidden_in.copy_(self.hidden_host, non_blocking=nb)
+        self.seq_lens.copy_(self.seq_lens_host, non_blocking=nb)
+        self.req_pool_indices.copy_(self.req_pool_host, non_blocking=nb)
+        self.positions.copy_(self.positions_host, non_blocking=nb)
+        self.out_cache_loc.copy_(self.out_cache_loc_host, non_blocking=nb)
+        self.alloc.req_to_page[: self.args.batch, : self.page_table_host.shape[1]].copy_(self.page_table_host, non_blocking=nb)
 
-    def linear(self, x, w):
-        from sglang_fluentllm_b200 import fp8_kernel as fk
-        if x.dim() == 2 and x.is_contiguous():
-            xq, xs = fk.sglang_per_token_group_quant_fp8(x, 128, column_major_scales=True, scale_tma_aligned=True)
-        else:  # a slice of the producer's output, quantised in place (no .contiguous() copy)
-            xq, xs = fk.per_token_group_quant_fp8_strided(x)
-        out = self.torch.empty(x.shape[0], w[0].shape[0], dtype=self.torch.bfloat16, device=self.dev)
-        self.dg.gemm_fp8_fp8_bf16_nt((xq, xs), w, out, True)
-        self.launches_per_step += 2
-        return out
+    @property
+    def h2d_bytes(self):
+        ts = (self.hidden_host, self.seq_lens_host, self.req_pool_host, self.positions_host, self.out_cache_loc_host,
+              self.page_table_host)
+        return sum(t.numel() * t.element_size() for t in ts)
+
+    def replay_metadata(self):
+        """cuda_graph_runner.py:505-513: outside the graph, before every replay."""
+        self.backend.init_forward_metadata_replay_cuda_graph(self.args.batch, self.req_pool_indices, self.seq_lens,
+                                                             self.args.batch * self.args.seq, self.fb.ForwardMode.DECODE,
+                                                             None, seq_lens_cpu=None)
 
     def layer(self, l, x):
-        torch, fm = self.torch, self.fm
+        torch = self.torch
         b, h = self.args.batch, self.h
-        y_a = self.linear(x, self.w_qkv_a[l])
-        q_abs = self.q_abs  # absorbed q [b, 1, h, 576]: its latent 512 columns stand in for the w_kc bmm output
-        if self.args.unfused_prologue:
-            k_new = y_a[:, Q_LORA:].unsqueeze(1)  # strided view of the fused projection output: no copy
-            fm.quantize_and_cache_k(k_new, self.k_lora[l], self.k_scale[l], self.k_rope[l], self.out_cache_loc, KV_LORA)
-            q_full = self.linear(y_a[:, :Q_LORA], self.w_q_b[l])
-            # stand-in for rope's write of Q's rope columns: one small strided copy from this step's q_b_proj output
-            q_abs[..., KV_LORA:].copy_(q_full.view(b, 1, h, NOPE_HEAD + ROPE)[..., NOPE_HEAD:])
-            q_nope, q_scale, q_rope = fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
-            self.launches_per_step += 2
-        else:
-            q_full = self.linear(y_a[:, :Q_LORA], self.w_q_b[l])
-            slots = self.n_pages * PAGE
-            arg = self.rope_mod.FusedSetKVBufferArg(
-                value=y_a[:, Q_LORA:Q_LORA + KV_LORA], k_buffer=self.k_rope[l].view(slots, ROPE),
-                v_buffer=self.k_lora[l].view(slots, KV_LORA), scale_buffer=self.k_scale[l].view(slots),
-                cache_loc=self.out_cache_loc)
-            q_nope, q_scale, q_rope = self.rope_mod.fused_rope_quantize_set_kv(
-                self.positions, q_abs[:, 0, :, :KV_LORA], q_full.view(b, h, NOPE_HEAD + ROPE)[..., NOPE_HEAD:],
-                y_a[:, Q_LORA + KV_LORA:], self.cos_sin_cache, False, arg)
-            q_nope, q_scale, q_rope = (q_nope.view(b, 1, h, KV_LORA), q_scale.view(b, 1, h, 1), q_rope.view(b, 1, h, ROPE))
-            self.launches_per_step += 1
-        n_pages = self.n_pages
-        out, _ = fm.flash_mla_ckv_fp8_per_token(
-            q_nope, q_rope, self.k_lora[l].view(n_pages, PAGE, 1, KV_LORA), self.k_rope[l].view(n_pages, PAGE, 1, ROPE),
-            q_scale, self.k_scale[l].view(n_pages, PAGE, 1, 1), self.block_table, self.seqlens, KV_LORA, self.meta,
-            self.num_splits, out=self.attn_out, lse=self.lse, workspace=self.workspace)
-        self.launches_per_step += 2  # decode + combine
-        attn_o = out[:, 0, :, :V_HEAD]  # [b, h, 128] view standing in for the w_vc bmm output, quantised in place
-        y = self.linear(attn_o, self.w_o[l])
+        m = self.method
+        # fused_qkv_a_proj_with_mqa (deepseek_v2.py:796-799): activation quantiser + block-FP8 GEMM
+        qkv = m.apply(self.lin_qkv_a[l], x)
+        # fused q_a / kv_a RMSNorm emitting the q_b_proj input block-quantised (:800-807,816-820)
+        q8, block_scale = self.norms[l].forward_block_quant(qkv, Q_LORA)
+        q = m.apply(self.lin_q_b[l], q8, block_scale=block_scale, output_dtype=torch.bfloat16).view(b, h, NOPE_HEAD + ROPE)
+        q_nope, q_pe = q.split([NOPE_HEAD, ROPE], dim=-1)
+        # w_kc absorb (:829-840): bf16 bmm straight into the latent columns of Q, as the reference does it
+        Q = self.q_buf
+        torch.bmm(q_nope.transpose(0, 1), self.w_kc[l], out=Q[..., :KV_LORA].transpose(0, 1))
+        # rotary embedding with the fused set_kv_buffer argument (:841-857): rope of q_pe / k_pe, Q quantiser and
+        # quantise-and-cache of the new token's K in one launch; returns the quantised Q triple
+        latent_cache = qkv[:, Q_LORA:]
+        arg = self.rope_mod.create_fused_set_kv_buffer_arg(value=latent_cache[:, :KV_LORA], layer=self.attn_layers[l],
+                                                          forward_batch=self.fbatch)
+        triple = self.rope_mod.fused_rope_quantize_set_kv(self.positions, Q[..., :KV_LORA], q_pe, latent_cache[:, KV_LORA:],
+                                                          self.cos_sin_cache, False, arg)
+        # attn_mqa -> AttentionBackend.forward_decode (:872-884), save_kv_cache=False: the prologue cached K already
+        attn = self.backend.forward_decode(triple, None, None, self.attn_layers[l], self.fbatch, save_kv_cache=False)
+        # w_vc absorb (:886-887)
+        attn_bmm = torch.bmm(attn.view(b, h, KV_LORA).transpose(0, 1), self.w_vc[l])            # [h, b, 128]
+        # o_proj (:888): the [b, h, 128] view of the bmm output is quantised in place (no flatten copy)
+        xq, xs = self.fk.per_token_group_quant_fp8_strided(attn_bmm.transpose(0, 1))
+        y = m.apply(self.lin_o[l], xq, block_scale=xs, output_dtype=torch.bfloat16)
         if self.tp > 1:
             self.tpmod.all_reduce_sum(y)  # the path's single exchange: row-parallel partial sums over NVLink
+        # launches: act-quant, GEMM(+reduce), norm+quant, GEMM, bmm, prologue, decode, combine, bmm, act-quant, GEMM
+        self.launches_per_step += 11
         return y
 
     def step(self, x):
@@ -290,14 +331,32 @@ class HotPath:
         return x
 
     def attn_only(self, l):
+        """The dominant kernel alone, through the kernel-module API the backend calls."""
         n_pages = self.n_pages
         if not hasattr(self, "_qq"):
-            self._qq = self.fm.quantize_ckv_per_token_head(self.q_abs, KV_LORA)
+            q_abs = self.torch.randn(self.args.batch, 1, self.h, KV_LORA + ROPE, dtype=self.torch.bfloat16, device=self.dev)
+            self._qq = self.fm.quantize_ckv_per_token_head(q_abs, KV_LORA)
         q_nope, q_scale, q_rope = self._qq
+        kl, ks, kr = self.pool.get_key_buffer(l)
+        md = self.backend.forward_metadata
         self.fm.flash_mla_ckv_fp8_per_token(
-            q_nope, q_rope, self.k_lora[l].view(n_pages, PAGE, 1, KV_LORA), self.k_rope[l].view(n_pages, PAGE, 1, ROPE),
-            q_scale, self.k_scale[l].view(n_pages, PAGE, 1, 1), self.block_table, self.seqlens, KV_LORA, self.meta,
-            self.num_splits, out=self.attn_out, lse=self.lse, workspace=self.workspace)
+            q_nope, q_rope, kl.view(-1, PAGE, 1, KV_LORA), kr.view(-1, PAGE, 1, ROPE), q_scale, ks.view(-1, PAGE, 1, 1),
+            md.block_table[: self.args.batch], self.seq_lens, KV_LORA, md.flashmla_metadata, md.num_splits,
+            out=self.attn_out, lse=self.lse, workspace=self.workspace)
+
+
+def workload_config(args, world, parallelism, heads_per_gpu, cuda_graph=True):
+    """`config` of the JSON line -- the same dictionary for the B200 arm and for `--impl reference`."""
+    n_repl = world if parallelism == "dp" else 1
+    bytes_, _ = mla_bytes_flops(args.batch, args.seq, heads_per_gpu)
+    return {"workload": "DeepSeek-V3 attention block decode (forward_absorb), %d layers: qkv_a / q_b / o_proj "
+                        "block-FP8 GEMMs, q_a / kv_a RMSNorm, w_kc / w_vc absorb, rope + quantise + cache prologue, "
+                        "paged MLA decode over per-token-FP8 KV" % args.layers,
+            "global_batch": args.batch * n_repl, "seq_len": args.seq, "heads_per_gpu": heads_per_gpu,
+            "parallelism": "%s%d" % (parallelism, world), "page_size": PAGE, "cuda_graph": cuda_graph,
+            "api": "FlashMLABackend.forward_decode (CUDA-graph capture/replay protocol) + Fp8LinearMethod.apply + "
+                   "FusedRMSNorm + rotary prologue with fused set_kv_buffer + w_kc / w_vc bmm (torch.bmm, as the reference)",
+            "l2": "inputs larger than L2: %.1f GB of distinct KV + weights streamed per step" % (args.layers * bytes_ / 1e9)}
 
 
 def mla_bytes_flops(b, seq, h, s_q=1):
@@ -374,10 +433,11 @@ def run_b200(args):
                 hp.x_out = hp.step(hp.hidden_in)
 
         def run_e2e_step():
-            hp.hidden_in.copy_(hp.hidden_host, non_blocking=True)
-            hp.block_table.copy_(hp.block_table_host, non_blocking=True)
-            hp.seqlens.copy_(hp.seqlens_host, non_blocking=True)
-            hp.refresh_metadata()
+            # what the model runner does per decode step around the graph (cuda_graph_runner.py:460-526): inputs from
+            # pinned host memory into the static tensors, the backend's replay-metadata refresh (block-table gather +
+            # tile-scheduler kernel), replay, result back to the host
+            hp.host_to_device()
+            hp.replay_metadata()
             run_step()
             hp.result_host.copy_(hp.x_out, non_blocking=True)
 
@@ -431,7 +491,7 @@ def run_b200(args):
     e2e_tokens_per_s = args.batch * n_repl / (ms_e2e / args.steps * 1e-3)
     bytes_, flops = mla_bytes_flops(args.batch, args.seq, hp.h)
     achieved = bytes_ / (attn_ms * 1e-3) / 1e9
-    h2d = hp.hidden_host.numel() * 2 + hp.block_table_host.numel() * 4 + hp.seqlens_host.numel() * 4
+    h2d = hp.h2d_bytes
     d2h = hp.result_host.numel() * 2
     traffic = None
     try:  # DRAM traffic of the dominant kernel from the committed ncu capture of the same shape (profiles/)
@@ -445,14 +505,7 @@ def run_b200(args):
         "ms_per_step": round(ms_step, 4), "higher_is_better": True,
         "scaling": "weak" if args.parallelism == "dp" else "strong", "vs_baseline": None, "dtype": "fp8_e4m3",
         "data": "synthetic (random-init weights, N(0,1) KV quantised by the path's own quantiser, constant seq len)",
-        "config": {"workload": "DeepSeek-V3 attention block decode, %d layers: qkv_a/q_b/o_proj block-FP8 GEMMs + "
-                               "paged MLA decode over per-token-FP8 KV" % args.layers,
-                   "global_batch": args.batch * n_repl, "seq_len": args.seq, "heads_per_gpu": hp.h,
-                   "parallelism": "%s%d" % (args.parallelism, world), "page_size": PAGE,
-                   "cuda_graph": graph is not None,
-                   "prologue": "unfused (3 launches)" if args.unfused_prologue else "fused rope + q quantiser + K cache",
-                   "l2": "inputs larger than L2: %.1f GB of distinct KV + weights streamed per step" % (
-                       args.layers * (bytes_ + 0) / 1e9)},
+        "config": workload_config(args, world, args.parallelism, hp.h, graph is not None),
         "e2e": {"value": round(e2e_tokens_per_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
         "gpu_launches": launches * args.steps,
@@ -524,11 +577,11 @@ def cpu_baseline(args, budget_s=20.0):
     from oracle import native_cpu
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 4
-    t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=2)
-    while t_attn * 4 < budget_s / 3 and sample_b < args.batch:
-        sample_b *= 2
-        t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=2)
+    sample_b = min(32, args.batch)  # at least a quarter of the batch; doubled while the budget allows
+    t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1)
+    while t_attn * 4 < budget_s / 2 and sample_b < args.batch:
+        sample_b = min(2 * sample_b, args.batch)
+        t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1)
     t_gemm = native_cpu.time_block_fp8_linears(min(args.batch, 32), args.heads, repeats=1) * (args.batch / min(args.batch, 32))
     per_layer = t_attn * (args.batch / sample_b) + t_gemm
     value = args.batch / (per_layer * args.layers)
@@ -553,8 +606,10 @@ def run_reference(args):
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.batch / v * 1e3, 3),
             "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "strong", "vs_baseline": None,
             "dtype": "bf16/f32 (CPU)",
-            "data": "synthetic", "config": {"workload": "same step as the b200 arm, reference CPU path (port)",
-                                            "global_batch": args.batch, "seq_len": args.seq},
+            "data": "synthetic (same shapes as the B200 arm; the CPU path runs on a bf16 pool: torch-native attention "
+                    "cannot read the per-token-FP8 layout)",
+            "config": workload_config(args, max(1, args.gpus), "dp" if args.gpus > 1 else "tp",
+                                      args.heads, True),
             "cpu_baseline": base,
             "e2e": {"value": v, "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)

@@ -142,6 +142,18 @@ int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* sc
 int b200_act_quant_1x128_strided(const void* x, int64_t x_row_stride, int64_t x_group_stride, int64_t m, int64_t k,
                                  void* q, float* scales, int64_t scale_stride, float eps, void* stream);
 
+/* RMSNorm of the fused qkv_a projection output (q_a columns [0, q_dim), kv_a columns [q_dim, q_dim + 512) of each row)
+ * with the 1x128 activation quantiser of the q_b_proj input fused in.  Replaces FusedRMSNorm.forward
+ * (python/sglang/srt/layers/layernorm.py:276-303 -> flashinfer _rmsnorm_fused_parallel,
+ * 3rdparty/flashinfer/include/flashinfer/norm.cuh:474-630) and the fuse_block_quant_fp8 epilogue of its allgather-fused
+ * form (layernorm.py:305-330), called at python/sglang/srt/models/deepseek_v2.py:796-820.
+ *   qkv bf16 [m][row_stride]: kv_a is normalised in place; q_a is written normalised to q_out bf16 [m][q_out_stride]
+ *   (may be NULL) and / or quantised to q8 e4m3 [m][q_dim] + q_scales f32 [q_dim/128][scale_stride] (may be NULL), the
+ *   same bits b200_act_quant_1x128 produces from q_out.  q_dim: multiple of 512, <= 3584; kv_dim must be 512. */
+int b200_qk_rmsnorm_quant(void* qkv, int64_t m, int64_t row_stride, int q_dim, int kv_dim, const void* q_weight,
+                          const void* kv_weight, float eps, void* q_out, int64_t q_out_stride, void* q8, float* q_scales,
+                          int64_t scale_stride, float quant_eps, void* stream);
+
 /* Block-scaled W8A8 FP8 GEMM, out[m][n] = bf16( sum_kb a_scales[kb][i] * b_scales[n/128][kb] * (A_kb . B_kb^T) ).
  * Replaces deep_gemm.gemm_fp8_fp8_bf16_nt (3rdparty/deep_gemm/deep_gemm/jit_kernels/gemm.py:145-226 ->
  * include/deep_gemm/fp8_gemm.cuh:60-399,409-827); same argument order as the JIT'd

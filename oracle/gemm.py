@@ -52,3 +52,18 @@ def per_token_group_quant_fp8(x_f32, group_size: int = 128, eps: float = 1e-10):
     s = (amax / FP8_MAX).astype(np.float32)
     q = np.clip((xg / s[..., None]).astype(np.float32), -FP8_MAX, FP8_MAX)
     return f32_to_e4m3(q).reshape(m, k), s
+
+
+def fused_qk_rmsnorm(qkv, q_dim: int, kv_dim: int, q_weight, kv_weight, eps: float):
+    """f-2: FusedRMSNorm.forward (python/sglang/srt/layers/layernorm.py:276-303 -> flashinfer norm.cuh:474-630):
+    out = bf16(float(x) * rsqrt(mean(x^2) + eps) * float(w)) for the q_a columns [0, q_dim) and the kv_a columns
+    [q_dim, q_dim + kv_dim) of every row, evaluated in float64 and rounded once (the kernel's fp32 evaluation may differ
+    by one bf16 ulp).  Returns (q_a normalised [m, q_dim], kv_a normalised [m, kv_dim]) as float32 holding bf16 values."""
+    from .fp8 import round_to_bf16
+    x = np.asarray(qkv, dtype=np.float64)
+    outs = []
+    for lo, hi, w in ((0, q_dim, q_weight), (q_dim, q_dim + kv_dim, kv_weight)):
+        part = x[:, lo:hi]
+        rcp = 1.0 / np.sqrt((part * part).mean(axis=1, keepdims=True) + eps)
+        outs.append(round_to_bf16((part * rcp * np.asarray(w, dtype=np.float64)[None, :]).astype(np.float32)))
+    return outs[0], outs[1]

@@ -39,6 +39,7 @@ _SIGNATURES = {
     "b200_mla_combine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
     "b200_act_quant_1x128": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),
     "b200_act_quant_1x128_strided": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),
+    "b200_qk_rmsnorm_quant": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, c_float, _P, c_int64, _P, _P, c_int64, c_float, _P]),
     "b200_fp8_gemm_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
     "b200_fp8_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, c_int, _P]),
     "b200_fp8_gemm_grouped_row_tiles": (c_int, [c_int, c_int, c_int]),

@@ -379,6 +379,98 @@ __global__ void __launch_bounds__(256)
   *reinterpret_cast<uint2*>(q + g * 128 + sub * 8) = pk;
 }
 
+// ------------------------------------------------------------------------------------------------
+// f-2  RMSNorm of the two halves of the fused qkv_a projection output, with the 1x128 activation quantiser of the
+// q_b_proj input fused in.  Reference: FusedRMSNorm.forward (python/sglang/srt/layers/layernorm.py:276-303 ->
+// flashinfer _rmsnorm_fused_parallel, 3rdparty/flashinfer/include/flashinfer/norm.cuh:474-630: out = bf16(float(x) *
+// rsqrt(mean(x^2) + eps) * float(w))) called at models/deepseek_v2.py:816-820 (q_a -> a contiguous buffer, kv_a in
+// place), and the block-quant epilogue of forward_with_allgather_fusion (fuse_block_quant_fp8, layernorm.py:305-330;
+// block_scale plumbing deepseek_v2.py:796-807).  One CTA per token: warp w < q_dim / 512 owns columns [512 w, 512 w +
+// 512) of q_a (four quantiser groups, 8 lanes x 16 values each), the last warp owns the 512 columns of kv_a.  The
+// quantised codes are computed from the bf16-rounded normalised values with the arithmetic of act_quant_1x128_kernel,
+// so they are bit-identical to quantising the bf16 output in a second launch.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    qk_rmsnorm_quant_kernel(__nv_bfloat16* __restrict__ qkv, int64_t row_stride, int q_dim, const __nv_bfloat16* __restrict__ q_weight,
+                            const __nv_bfloat16* __restrict__ kv_weight, float eps, __nv_bfloat16* __restrict__ q_out,
+                            int64_t q_out_stride, uint8_t* __restrict__ q8, float* __restrict__ q_scales,
+                            int64_t scale_stride, float quant_eps) {
+  extern __shared__ float s_norm[];  // [warps] partial sums of squares
+  pdl_launch_dependents();
+  pdl_wait_prior_grid();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_warps = q_dim / 512;
+  const bool is_kv = warp == q_warps;
+  const int64_t row = blockIdx.x;
+  __nv_bfloat16* src = qkv + row * row_stride + (is_kv ? q_dim : warp * 512) + lane * 16;
+  const __nv_bfloat16* wsrc = (is_kv ? kv_weight : q_weight + warp * 512) + lane * 16;
+  float v[16], w[16];
+  {
+    const uint4 r0 = *reinterpret_cast<const uint4*>(src), r1 = *reinterpret_cast<const uint4*>(src + 8);
+    const uint4 w0 = __ldg(reinterpret_cast<const uint4*>(wsrc)), w1 = __ldg(reinterpret_cast<const uint4*>(wsrc + 8));
+    const uint32_t rr[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+    const uint32_t ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[2 * j] = __uint_as_float(rr[j] << 16), v[2 * j + 1] = __uint_as_float(rr[j] & 0xFFFF0000u);
+      w[2 * j] = __uint_as_float(ww[j] << 16), w[2 * j + 1] = __uint_as_float(ww[j] & 0xFFFF0000u);
+    }
+  }
+  float ss = 0.f;
+#pragma unroll
+  for (int j = 0; j < 16; ++j) ss = __fmaf_rn(v[j], v[j], ss);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ss += __shfl_xor_sync(0xffffffffu, ss, o);
+  if (lane == 0) s_norm[warp] = ss;
+  __syncthreads();
+  float total = 0.f;
+  if (is_kv) {
+    total = s_norm[q_warps];
+  } else {
+    for (int i = 0; i < q_warps; ++i) total += s_norm[i];  // fixed order
+  }
+  const float rcp = rsqrtf(__fadd_rn(__fdiv_rn(total, is_kv ? 512.f : (float)q_dim), eps));
+  uint32_t packed[8];
+  float o[16];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const __nv_bfloat162 h = __floats2bfloat162_rn(__fmul_rn(__fmul_rn(v[2 * j], rcp), w[2 * j]),
+                                                    __fmul_rn(__fmul_rn(v[2 * j + 1], rcp), w[2 * j + 1]));
+    packed[j] = *reinterpret_cast<const uint32_t*>(&h);
+    o[2 * j] = __uint_as_float(packed[j] << 16), o[2 * j + 1] = __uint_as_float(packed[j] & 0xFFFF0000u);
+  }
+  if (is_kv) {  // kv_a: normalised in place (the k_nope columns the fused prologue quantises into the pool)
+    *reinterpret_cast<uint4*>(src) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(src + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+    return;
+  }
+  const int col0 = warp * 512 + lane * 16;
+  if (q_out != nullptr) {
+    __nv_bfloat16* dst = q_out + row * q_out_stride + col0;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+    *reinterpret_cast<uint4*>(dst + 8) = make_uint4(packed[4], packed[5], packed[6], packed[7]);
+  }
+  if (q8 != nullptr) {  // 1x128 groups = 8 lanes x 16 values; arithmetic of act_quant_1x128_kernel
+    float amax = quant_eps;
+#pragma unroll
+    for (int j = 0; j < 16; ++j) amax = fmaxf(amax, fabsf(o[j]));
+#pragma unroll
+    for (int d = 4; d > 0; d >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, d, 8));
+    const float sc = __fdiv_rn(amax, FP8_MAX);
+    const int group = col0 >> 7;
+    if ((lane & 7) == 0) q_scales[group * scale_stride + row] = sc;
+    float qv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) qv[j] = fminf(fmaxf(__fdiv_rn(o[j], sc), -FP8_MAX), FP8_MAX);
+    uint4 pk;
+    pk.x = cvt_e4m3x4(qv[0], qv[1], qv[2], qv[3]);
+    pk.y = cvt_e4m3x4(qv[4], qv[5], qv[6], qv[7]);
+    pk.z = cvt_e4m3x4(qv[8], qv[9], qv[10], qv[11]);
+    pk.w = cvt_e4m3x4(qv[12], qv[13], qv[14], qv[15]);
+    *reinterpret_cast<uint4*>(q8 + row * q_dim + col0) = pk;
+  }
+}
+
 }  // namespace b200
 
 using namespace b200;
@@ -550,6 +642,24 @@ int b200_act_quant_1x128_strided(const void* x, int64_t x_row_stride, int64_t x_
   return launch_kernel(act_quant_1x128_kernel, dim3((unsigned)((groups + groups_per_block - 1) / groups_per_block)),
                        dim3(groups_per_block * 16), 0, (cudaStream_t)stream, pdl_default(), (const __nv_bfloat16*)x,
                        x_row_stride, x_group_stride, (uint8_t*)q, scales, groups, (int)(k / 128), scale_stride, eps);
+}
+
+int b200_qk_rmsnorm_quant(void* qkv, int64_t m, int64_t row_stride, int q_dim, int kv_dim, const void* q_weight,
+                          const void* kv_weight, float eps, void* q_out, int64_t q_out_stride, void* q8, float* q_scales,
+                          int64_t scale_stride, float quant_eps, void* stream) {
+  B200_CHECK(qkv && q_weight && kv_weight, "qk_rmsnorm_quant: null pointer");
+  B200_CHECK(kv_dim == 512 && q_dim > 0 && q_dim % 512 == 0 && q_dim <= 7 * 512,
+             "qk_rmsnorm_quant: q_dim=%d (multiple of 512, <= 3584) kv_dim=%d (512) not supported", q_dim, kv_dim);
+  B200_CHECK(q_out || q8, "qk_rmsnorm_quant: neither a bf16 nor a quantised q output was given");
+  B200_CHECK(!q8 || q_scales, "qk_rmsnorm_quant: quantised output needs a scale buffer");
+  B200_CHECK(row_stride % 8 == 0 && (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (!q_out || q_out_stride % 8 == 0),
+             "qk_rmsnorm_quant: rows must be 16-byte aligned");
+  if (m == 0) return 0;
+  const int warps = q_dim / 512 + 1;
+  return launch_kernel(qk_rmsnorm_quant_kernel, dim3((unsigned)m), dim3(warps * 32), warps * sizeof(float),
+                       (cudaStream_t)stream, pdl_default(), (__nv_bfloat16*)qkv, row_stride, q_dim,
+                       (const __nv_bfloat16*)q_weight, (const __nv_bfloat16*)kv_weight, eps, (__nv_bfloat16*)q_out,
+                       q_out_stride, (uint8_t*)q8, q_scales, scale_stride, quant_eps);
 }
 
 }  // extern "C"

@@ -4,6 +4,7 @@
 
 namespace b200 {
 int32_t s_meta[1 << 20];  // mla_metadata_kernel's dynamic shared memory
+float s_norm[64];         // qk_rmsnorm_quant_kernel's
 }
 using namespace b200;
 

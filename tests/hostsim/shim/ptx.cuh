@@ -19,3 +19,6 @@ inline float warp_max_f32(float v) {
   return v;
 }
 }  // namespace b200
+
+// rsqrt.approx stand-in for the host build (qk_rmsnorm_quant_kernel)
+inline float rsqrtf(float x) { return 1.0f / std::sqrt(x); }
