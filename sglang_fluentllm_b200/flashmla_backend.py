@@ -359,7 +359,10 @@ class FlashMLABackend(AttentionBackend):
             assert v is not None
             if save_kv_cache:
                 forward_batch.token_to_kv_pool.set_kv_buffer(layer, forward_batch.out_cache_loc, k, v)
-        cache_seqlens = forward_batch.seq_lens + self.multi_step_seqlen_incr
+        # flashmla_backend.py:202: seq_lens + multi_step_seqlen_incr (no elementwise launch per layer when the increment
+        # is zero, i.e. outside the speculative draft loop)
+        incr = self.multi_step_seqlen_incr
+        cache_seqlens = forward_batch.seq_lens + incr if incr else forward_batch.seq_lens
         if isinstance(q, (tuple, list)):
             if self.cache_quant_method != "per_token_head":
                 raise RuntimeError("a pre-quantised q needs the per_token_head KV pool")
