@@ -19,7 +19,7 @@
 //   Warp roles (1 CTA/SM): warp 0 = TMA producer, warp 1 = UMMA issuer for Q.K^T, warp 2 = UMMA issuer for P.V,
 //   warp 3 idle, warps 4.. = softmax / correction / epilogue (4 TMEM lane quadrants x HB/CPT column slices; one
 //   thread per (KV token, column slice)).
-//   TMEM: S double-buffered (2 x HB columns) + O (4 x HB columns).  P.V is issued twice per tile (hi and lo term of P).
+//   TMEM: S double-buffered (2 x HB columns) + O (4 d-chunks x [hi | lo] = 8 x HB columns).
 //
 //   Softmax: the reference's page-wise FP8 codes of P under a lazily moved per-row reference (see the comment above
 //   mla_decode_kernel); the row sum L is kept per token-lane in registers and reduced once per request.
@@ -41,9 +41,9 @@ template <int HB>
 struct SmemLayout {
   static constexpr int kQBytes = HB * 640;           // 4 nope chunks [HB x 128 B] + rope [HB x 128 B]
   static constexpr int kPBytes = HB * kTileTokens;   // [HB/16 chunks][16 groups][8 tokens][16 q]
-  // P buffers: (hi, lo) pairs.  Two pairs (tile parity) when they fit; HB = 64 has room for one pair, and the softmax
-  // of tile g then writes P once P.V of tile g-1 has retired (its max pass overlaps that P.V).
-  static constexpr int kPPairs = HB == 64 ? 1 : 2;
+  // P buffers: (hi, lo) pairs by tile parity; the lo tile sits right behind the hi tile, so the pair is ONE B operand
+  // of 2 * HB columns
+  static constexpr int kPPairs = 2;
   static constexpr int kOffKV = 0;
   static constexpr int kOffQ = kStages * kStageBytes;
   static constexpr int kOffP = kOffQ + kQBytes;
@@ -78,17 +78,19 @@ static_assert(sizeof(SmallSmem) <= 4096, "SmallSmem too large");
 // The reference then rescales O and L by exp2(m_old - m_new) * p_old / p_new every page (:442-455); with O in TMEM that
 // is a 128 KB read-modify-write per page.  Here O and L live under a per-row reference exponent R that only moves when
 // a page's ymax exceeds it (then R = ymax + 4 and O is rescaled once), and the page's weight w = 2^(ymax - R) <= 1
-// multiplies the codes instead: code_j * w as an e4m3 pair hi + lo (two P.V products), 8 significant bits -- the
-// result differs from the page-wise recurrence by ~1e-3 (rounding of w*code, fp32 summation order), not by the 2^-4
-// noise of a different e4m3 grid.
+// multiplies the codes instead: code_j * w as an e4m3 pair hi + lo, 8 significant bits -- the result differs from the
+// page-wise recurrence by ~1e-3 (rounding of w*code, fp32 summation order), not by the 2^-4 noise of a different e4m3
+// grid.  Under SwapAB P is the B operand and HB is small, so hi and lo ride in ONE product: B = [P_hi | P_lo] with
+// N = 2 HB columns, O^T = [O_hi | O_lo] in TMEM, added in the epilogue -- P.V issues as many UMMAs (and reads V^T from
+// shared memory as often) as with a single P tile.
 template <int HB, int CPT>
 __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(const __grid_constant__ MlaParams p) {
   using L = SmemLayout<HB>;
-  constexpr uint32_t kTmemCols = HB == 64 ? 512 : (HB == 32 ? 256 : 128);
-  constexpr uint32_t kColS = 0, kColO = 2 * HB;
+  static_assert(HB == 16 || HB == 32, "HB must be 16 or 32 (larger M runs on the CTA-pair kernel)");
+  constexpr uint32_t kTmemCols = HB == 32 ? 512 : 256;
+  constexpr uint32_t kColS = 0, kColO = 2 * HB;  // S: 2 x HB columns; O: 4 d-chunks x [hi HB | lo HB] columns
   constexpr int kCS = HB / CPT;                 // column slices
   constexpr int kSmThreads = 128 * kCS;         // softmax group size
-  constexpr int kPPairs = L::kPPairs;
   static_assert(CPT % 8 == 0 && CPT <= 32, "CPT must be 8, 16 or 32");
 
   extern __shared__ uint8_t smem_raw[];
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
     }
   } else if (warp == 2) {
     // ============================== UMMA issuer: O^T += V^T . (P_hi + P_lo) ==============================
-    constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, HB);
+    constexpr uint32_t idesc_pv = make_idesc(FMT_E4M3, FMT_E4M3, 1, 1, 128, 2 * HB);  // N = [P_hi | P_lo]
     const uint32_t kv_addr = smem_u32(s_kv), p_addr = smem_u32(s_p);
     const uint64_t dv_sw128 = make_smem_desc(0, 16384, 1024, SWZ_128B);  // MN-major view of the K tile bytes
     const uint64_t dp_none = make_smem_desc(0, 128, 2048, SWZ_NONE);     // P: 8x16-B core matrices
@@ -270,17 +272,15 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         const uint32_t stage = kv_addr + st * kStageBytes;
         const int tile_start = (sg.start_block + 2 * t) * kPage;
         const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
-        const uint32_t pbuf = p_addr + (kPPairs == 2 ? buf : 0u) * (2 * L::kPBytes);
+        const uint32_t pbuf = p_addr + buf * (2 * L::kPBytes);
         if (elect_one()) {
 #pragma unroll
-          for (int hl = 0; hl < 2; ++hl)
+          for (int j = 0; j < 4; ++j)
 #pragma unroll
-            for (int j = 0; j < 4; ++j)
-#pragma unroll
-              for (int s = 0; s < 4; ++s)
-                if (s < nk)
-                  umma_f8(tmem + kColO + j * HB, with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
-                          with_addr(dp_none, pbuf + hl * L::kPBytes + s * 512), idesc_pv, (t | s | hl) != 0);
+            for (int s = 0; s < 4; ++s)
+              if (s < nk)
+                umma_f8(tmem + kColO + j * (2 * HB), with_addr(dv_sw128, stage + j * kNopeChunkBytes + s * 4096),
+                        with_addr(dp_none, pbuf + s * 512), idesc_pv, (t | s) != 0);
           umma_commit(&sm.kv_empty[st]);
           umma_commit(&sm.pv_done);
           if (t == sg.n_tiles - 1) umma_commit(&sm.o_ready);  // one completion per request: the epilogue's gate
@@ -401,7 +401,7 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
             }
             if (t != 0) {
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
+              for (int j = 0; j < 8; ++j) {  // 4 d-chunks x (hi, lo)
                 float o[8];
                 const uint32_t a = tmem + kColO + j * HB + cb + c8 * 8 + lane_addr;
                 tmem_ld<8>(a, o);
@@ -445,13 +445,8 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
         // ---- publish P (B operand of P.V: [token][q], MN-major, 8x16-byte core matrices) ----
         // The P pair (and this KV stage) was last read by P.V of tile g-2 (two pairs) / g-1 (one pair), issued by
         // another warp: wait for it to retire
-        if constexpr (kPPairs == 2) {
-          mbar_wait(&sm.kv_empty[g % kStages], ((g / kStages) & 1) ^ 1);
-        } else {
-          if (g > 0) mbar_wait(&sm.pv_done, (g - 1) & 1);
-        }
-        uint8_t* prow = s_p + (kPPairs == 2 ? buf : 0u) * (2 * L::kPBytes) + (cb >> 4) * 2048 + (tl >> 3) * 128 +
-                        (tl & 7) * 16 + (cb & 15);
+        mbar_wait(&sm.kv_empty[g % kStages], ((g / kStages) & 1) ^ 1);
+        uint8_t* prow = s_p + buf * (2 * L::kPBytes) + (cb >> 4) * 2048 + (tl >> 3) * 128 + (tl & 7) * 16 + (cb & 15);
         if constexpr (CPT == 8) {
           *reinterpret_cast<uint2*>(prow) = make_uint2(hi[0], hi[1]);
           *reinterpret_cast<uint2*>(prow + L::kPBytes) = make_uint2(lo[0], lo[1]);
@@ -510,8 +505,12 @@ __global__ void __launch_bounds__(128 + 128 * (HB / CPT), 1) mla_decode_kernel(c
       for (int j = 0; j < 4; ++j) {
         float o[CPT];
         if (sg.n_tiles > 0) {
-          tmem_ld<CPT>(tmem + kColO + j * HB + cb + lane_addr, o);
+          float ol[CPT];
+          tmem_ld<CPT>(tmem + kColO + j * (2 * HB) + cb + lane_addr, o);
+          tmem_ld<CPT>(tmem + kColO + j * (2 * HB) + HB + cb + lane_addr, ol);
           tmem_wait_ld();
+#pragma unroll
+          for (int k = 0; k < CPT; ++k) o[k] += ol[k];  // O = O_hi + O_lo
         } else {
 #pragma unroll
           for (int k = 0; k < CPT; ++k) o[k] = 0.f;
@@ -639,13 +638,11 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   prm.ks_ahead = ks_ahead < 1 ? 1 : (ks_ahead > 6 ? 6 : ks_ahead);
 
   int rc;
-  static const bool force_swap = getenv("B200_MLA_FORCE_SWAPAB") != nullptr;  // diagnostic: single-CTA kernel for every M
-  // M above this goes to the CTA-pair kernel (A/B knob; 32 < M <= 64 fills one CTA of the pair)
-  static const int pair_min_m = getenv("B200_MLA_PAIR_MIN_M") ? atoi(getenv("B200_MLA_PAIR_MIN_M")) : 32;
-  if (M > pair_min_m && M > 32 && !force_swap) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
+  // M <= 32: single-CTA SwapAB kernel (KV tokens on UMMA M, q rows on N); above: the CTA-pair kernel (32 < M <= 64 fills
+  // one CTA of the pair -- measured faster than a 64-column SwapAB tile)
+  if (M > 32) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
   else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else if (HB == 32) rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
-  else rc = launch_mla<64, 32>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  else rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;
   return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);
 }

@@ -472,20 +472,6 @@ def test_mla_m_le_64_default_routing(mods, h, s_q):
     assert rel(out, fo) < 1e-2 and np.allclose(lse, fl, rtol=1e-3, atol=1e-3)
 
 
-def test_mla_m_le_64_swapab_routing_in_a_subprocess():
-    """The other side of the routing knob (B200_MLA_PAIR_MIN_M=64: SwapAB kernel with HB = 64); the knob is read once per
-    process, hence the subprocess."""
-    import os
-    import subprocess
-    import sys
-    env = dict(os.environ, B200_MLA_PAIR_MIN_M="64")
-    here = os.path.dirname(os.path.abspath(__file__))
-    r = subprocess.run([sys.executable, "-m", "pytest", "-q", "-x", os.path.join(here, "test_gpu_parity.py"), "-m", "gpu", "-k",
-                        "m_le_64_default_routing or ragged-h64 or sq2-causal-h64"], env=env, capture_output=True, text=True,
-                       timeout=600)
-    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
-
-
 def test_mla_decode_low_noise_input_is_tight(mods):
     """With a constant-sign V the e4m3 rounding of P averages out: the kernel must agree with fp32 attention to well
     under 1e-2 -- isolates real bugs from quantisation noise."""
