@@ -183,20 +183,6 @@ int b200_fp8_gemm_grouped_nt(const void* a, const float* a_scales, int64_t a_sca
                              const float* b_scales, void* out, const int32_t* group_layout, int mode, int num_groups,
                              int m, int n, int k, int use_pdl, void* stream);
 
-/* Hardware self-test of the hand-built UMMA shared-memory / instruction descriptors (csrc/umma_lab.cu).
- * Writes max|got-expected|/max|expected| of one operand-layout variant to *rel_err. */
-int b200_umma_selftest(int variant, int n, float* rel_err);
-
-/* Issue-rate probe for the same operand layouts: average SM cycles per tcgen05.mma (M=128, N=n, K=32 B). */
-int b200_umma_rate(int variant, int n, int iters, float* cycles_per_mma);
-
-/* CTA-pair (cta_group::2) lab: raw TMEM dump [2][128][256] of one M=128 MMA chain; host pointers (diagnostic). */
-int b200_umma_pair_lab(int b_mode, int n, const void* a, const void* b, float* out);
-
-/* Issue-rate probe for cta_group::2 MMAs (M = 128 over a CTA pair): average SM cycles per tcgen05.mma.
- * mode 0/1/2 = Q.K^T fp8 / P.V / Q.K^T bf16 operand forms at N = n, mode 3 = the MLA tile mix (28 MMAs per tile). */
-int b200_umma_pair_rate(int mode, int n, int iters, float* cycles_per_mma);
-
 /* Diagnostic: clock64 pipeline trace of the last CTA-pair MLA launch made with B200_MLA_TRACE set. */
 int b200_mla_read_trace(unsigned long long* out, int n);
 /* Diagnostic: per (part, CTA rank) globaltimer ns at entry / at the end of the softmax warps' work, same launch. */

@@ -44,14 +44,37 @@ _SIGNATURES = {
     "b200_fp8_gemm_nt": (c_int, [_P, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, _P, c_size_t, c_int, _P]),
     "b200_fp8_gemm_grouped_row_tiles": (c_int, [c_int, c_int, c_int]),
     "b200_fp8_gemm_grouped_nt": (c_int, [_P, _P, c_int64, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int, _P]),
-    "b200_umma_selftest": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
-    "b200_umma_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
-    "b200_umma_pair_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
-    "b200_umma_pair_lab": (c_int, [c_int, c_int, _P, _P, _P]),
     "b200_mla_read_trace": (c_int, [_P, c_int]),
     "b200_mla_read_part_times": (c_int, [_P, c_int]),
 }
 EXPORTED_SYMBOLS = tuple(_SIGNATURES)
+
+# test-only hardware probes (include/b200_lab.h, _C/libb200lab.so): never loaded by the product modules
+LAB_LIB_PATH = os.path.join(_HERE, "_C", "libb200lab.so")
+_LAB_SIGNATURES = {
+    "b200_lab_last_error": (c_char_p, []),
+    "b200_umma_selftest": (c_int, [c_int, c_int, ctypes.POINTER(c_float)]),
+    "b200_umma_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
+    "b200_umma_pair_rate": (c_int, [c_int, c_int, c_int, ctypes.POINTER(c_float)]),
+    "b200_umma_pair_lab": (c_int, [c_int, c_int, _P, _P, _P]),
+}
+LAB_EXPORTED_SYMBOLS = tuple(_LAB_SIGNATURES)
+_lab = None
+
+
+def lab() -> ctypes.CDLL:
+    """The probe library (tests / tools only)."""
+    global _lab
+    if _lab is None:
+        if not os.path.exists(LAB_LIB_PATH):
+            raise RuntimeError("sglang_fluentllm_b200: %s not found -- run `python __graft_entry__.py`" % LAB_LIB_PATH)
+        handle = ctypes.CDLL(LAB_LIB_PATH)
+        for name, (res, args) in _LAB_SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lab = handle
+    return _lab
 
 _lib = None
 

@@ -17,6 +17,7 @@
 
 #include <vector>
 
+#include "b200_lab.h"
 #include "host_utils.h"
 #include "ptx.cuh"
 
@@ -592,3 +593,5 @@ extern "C" int b200_umma_pair_rate(int mode, int n, int iters, float* cycles_per
   *cycles_per_mma = (float)c / ((float)iters * per_iter);
   return 0;
 }
+
+extern "C" const char* b200_lab_last_error(void) { return b200::get_last_error(); }

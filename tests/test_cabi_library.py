@@ -8,8 +8,8 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "b200_decode.h")).read()
+def _declared_symbols(header="b200_decode.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b200_[a-z0-9_]+)\s*\(", text)))
 
@@ -39,6 +39,20 @@ def test_python_binding_covers_every_symbol(built_lib):
     from sglang_fluentllm_b200 import _lib
     assert sorted(_lib.EXPORTED_SYMBOLS) == _declared_symbols()
     _lib.lib()  # sets restype/argtypes for all of them; raises if one is missing
+
+
+def test_probe_library_is_separate_from_the_product(built_lib):
+    """The UMMA descriptor / issue-rate probes live in their own test-only library (include/b200_lab.h): the product
+    library exports none of them and the probe library exports all of them."""
+    import __graft_entry__ as ge
+    from sglang_fluentllm_b200 import _lib
+    lab_syms = _declared_symbols("b200_lab.h")
+    assert "b200_umma_selftest" in lab_syms and sorted(_lib.LAB_EXPORTED_SYMBOLS) == lab_syms
+    product, lab = ctypes.CDLL(built_lib), ctypes.CDLL(ge.LAB_LIB)
+    for s in lab_syms:
+        assert hasattr(lab, s), "missing export: %s" % s
+        assert not hasattr(product, s), "probe symbol %s leaked into the product library" % s
+    _lib.lab()
 
 
 def test_pure_host_entry_points(built_lib):

@@ -35,11 +35,11 @@ def test_umma_bf16_mn_major_two_chunk_descriptor():
     """P.V operand forms of the bf16 kernel: A = V^T MN-major SW128 spanning two 64-dim chunks (LBO = chunk stride),
     B = thread-written bf16 P[q][tok] K-major SW128 in two 64-token chunks."""
     from sglang_fluentllm_b200 import _lib
-    L = _lib.lib()
+    L = _lib.lab()  # the probe library (include/b200_lab.h)
     for n in (16, 32, 64):
         err = ctypes.c_float(-1)
         rc = L.b200_umma_selftest(5, n, ctypes.byref(err))
-        assert rc == 0, L.b200_last_error()
+        assert rc == 0, L.b200_lab_last_error()
         assert err.value < 1e-5, "variant 5 n=%d rel_err=%g" % (n, err.value)
 
 

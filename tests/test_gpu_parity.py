@@ -44,12 +44,12 @@ def rel(a, b):
 # ------------------------------------------------------------------------------------------------------------------
 def test_umma_descriptor_selftest(mods):
     """The hand-built UMMA smem/instruction descriptors of every operand layout the kernels use."""
-    L = mods[0].lib()
+    L = mods[0].lab()  # the probe library (include/b200_lab.h), not the product
     for variant in (0, 1, 3):  # K-major fp8, K-major bf16, MN-major V^T x thread-written P
         for n in (16, 64):
             err = ctypes.c_float(-1)
             rc = L.b200_umma_selftest(variant, n, ctypes.byref(err))
-            assert rc == 0, L.b200_last_error()
+            assert rc == 0, L.b200_lab_last_error()
             assert err.value < 1e-5, "variant %d n=%d rel_err=%g" % (variant, n, err.value)
 
 
