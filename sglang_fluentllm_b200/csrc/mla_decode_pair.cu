@@ -787,12 +787,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         const uint32_t sb = g % kSBufs;
         const uint32_t s_addr = tmem + kColS + sb * 64 + lane_addr;
         uint8_t* prow = s_p + (2 * grp) * kPBytes + row * 128;  // this group's P pair: hi tile, lo tile right behind it
-        // the first tiles of a request always see a reference move: wait for the predecessor before computing
-        bool fin_waited = false;
-        if (t < kGroups && g > 0) {
-          mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
-          fin_waited = true;
-        }
+        bool fin_waited = false, fin_arrived = false;
         trace<TR>(tr_w, rank, 2, g, 0);
         mbar_wait(&sm.s_full[sb], (g / kSBufs) & 1);
         trace<TR>(tr_w, rank, 2, g, 1);
@@ -811,6 +806,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
                                      : pass_max(std::false_type{}, s_addr, ks_tile, lk_tile, tile_start);
         const bool live = ymax > -INFINITY;
         trace<TR>(tr_w, rank, 4, g, 0);
+        // the first tiles of a request always see a reference move (the first tile makes one): their weighted pass
+        // waits for the predecessor's reference instead of running ahead of it (the max pass above did overlap it)
+        if (t < kGroups && g > 0) {
+          mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
+          fin_waited = true;
+        }
 
         float acc = 0.f, w32 = 0.f;
         bool p_free_waited = false;
@@ -877,7 +878,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             tc_fence_before();
             named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
             ver += 1;
-            if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other group with this warp's arrival on sm.fin
+            if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other groups with the arrival on sm.fin
+            // The reference is final for this tile and O is rescaled: the next tile may run its weighted pass while this
+            // one runs its own (what orders them further -- P.V issue order, pv_done before a rescale -- does not hang
+            // on fin).  The version store above is ordered before the arrival of gtid 0's warp by this barrier.
+            named_bar_sync(gbar, 128);
+            if (lane == 0) mbar_arrive(&sm.fin[g & 1]);
+            fin_arrived = true;
             moved = true;
           }
           const bool over = !moved && __any_sync(0xffffffffu, live && ymax > rloc);  // a row of this warp outgrew its reference
@@ -929,7 +936,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         if (lane == 0) {
           if (rank == 0) mbar_arrive(&sm.s_done[sb]);  // (the peer's share rides on its relay's p_relay hand-off)
           mbar_arrive(rank == 0 ? &sm.p_full[grp] : &sm.p_relay[grp]);
-          mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the other group may publish tile g+1
+          if (!fin_arrived) mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the next tile may publish
         }
         trace<TR>(tr_w, rank, 2, g, 3);
       }
