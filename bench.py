@@ -493,12 +493,13 @@ def run_b200(args):
     achieved = bytes_ / (attn_ms * 1e-3) / 1e9
     h2d = hp.h2d_bytes
     d2h = hp.result_host.numel() * 2
-    traffic = None
+    traffic = traffic_source = None
     try:  # DRAM traffic of the dominant kernel from the committed ncu capture of the same shape (profiles/)
         key = "mla_decode_pair_kernel b=%d seq=%d h=%d s_q=1" % (args.batch, args.seq, hp.h)
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]["traffic_bytes"]
+        entry = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))[key]
+        traffic, traffic_source = entry["traffic_bytes"], entry["source"]
     except Exception:
-        traffic = None
+        traffic, traffic_source = None, None
     line = {
         "metric": METRIC, "value": round(tokens_per_s, 2),
         "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
@@ -511,7 +512,8 @@ def run_b200(args):
         "gpu_launches": launches * args.steps,
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
-                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "peak_source": peak_src,
+                     "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_source,
+                     "peak_source": peak_src,
                      "kernel": "mla_decode_kernel (+combine), per layer, L2-cold", "kernel_ms": round(attn_ms, 4),
                      "algorithmic_bytes": bytes_, "tflops": round(flops / (attn_ms * 1e-3) / 1e12, 1)},
     }
