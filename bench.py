@@ -504,7 +504,8 @@ def run_b200(args):
         "metric": METRIC, "value": round(tokens_per_s, 2),
         "unit": "tokens/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": round(ms_step, 4), "higher_is_better": True,
-        "scaling": "weak" if args.parallelism == "dp" else "strong", "vs_baseline": None, "dtype": "fp8_e4m3",
+        "scaling": "strong" if (args.parallelism == "tp" and world > 1) else "weak", "vs_baseline": None,
+        "dtype": "fp8_e4m3",
         "data": "synthetic (random-init weights, N(0,1) KV quantised by the path's own quantiser, constant seq len)",
         "config": workload_config(args, world, args.parallelism, hp.h, graph is not None),
         "e2e": {"value": round(e2e_tokens_per_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
@@ -606,7 +607,7 @@ def run_reference(args):
     base["value"] = v
     line = {"impl": "reference", "metric": METRIC, "value": v, "unit": "tokens/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(args.batch / v * 1e3, 3),
-            "higher_is_better": True, "scaling": "weak" if args.gpus > 1 else "strong", "vs_baseline": None,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16/f32 (CPU)",
             "data": "synthetic (same shapes as the B200 arm; the CPU path runs on a bf16 pool: torch-native attention "
                     "cannot read the per-token-FP8 layout)",
