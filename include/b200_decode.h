@@ -103,14 +103,20 @@ size_t b200_mla_workspace_bytes(int batch, int s_q, int h_q, int num_sm_parts);
  *   block_table int32 [b][block_table_stride]   cache_seqlens int32 [b]
  *   tile_scheduler_metadata / num_splits from b200_mla_get_metadata (num_sm_parts rows)
  *   out bf16 [b][s_q][h_q][512]      lse f32 [b][h_q][s_q]
- *   workspace >= b200_mla_workspace_bytes(...) */
+ *   workspace >= b200_mla_workspace_bytes(...)
+ *   merge_state: NULL, or int32 [b200_mla_merge_state_ints(batch, s_q, h_q)] that is ZERO when the call starts and is
+ *   not shared with a call running concurrently on another stream.  With it, the kernel for s_q * h_q > 32 merges the
+ *   requests the scheduler cut over several parts itself (the part that finishes last adds the others' partials) and
+ *   no combine kernel is launched; the kernel leaves the buffer zero again, so one buffer zeroed once serves every
+ *   later call on the stream.  NULL: partials + b200_mla_combine, as the reference. */
+size_t b200_mla_merge_state_ints(int batch, int s_q, int h_q);
 int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, const float* q_scale, const void* k_lora,
                                       const void* k_rope, const float* k_scale, int64_t num_pages,
                                       const int32_t* block_table, int64_t block_table_stride,
                                       const int32_t* cache_seqlens, const int32_t* tile_scheduler_metadata,
                                       const int32_t* num_splits, int num_sm_parts, int batch, int s_q, int h_q,
                                       float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
-                                      size_t workspace_bytes, int use_pdl, void* stream);
+                                      size_t workspace_bytes, int32_t* merge_state, int use_pdl, void* stream);
 
 /* Paged MLA decode attention over a bf16 KV cache (split-KV + combine), no quantisation anywhere.
  * Replaces flash_mla_fp8.flash_mla_with_kvcache / flash_mla_swap.flash_mla_with_kvcache

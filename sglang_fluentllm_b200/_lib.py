@@ -26,10 +26,11 @@ _SIGNATURES = {
     ),
     "b200_mla_dequantize_indexed": (c_int, [_P, _P, _P, _P, c_int64, c_int64, _P, _P, _P]),
     "b200_mla_workspace_bytes": (c_size_t, [c_int, c_int, c_int, c_int]),
+    "b200_mla_merge_state_ints": (c_size_t, [c_int, c_int, c_int]),
     "b200_mla_decode_ckv_fp8_per_token": (
         c_int,
         [_P, _P, _P, _P, _P, _P, c_int64, _P, c_int64, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_int, _P, _P,
-         _P, c_size_t, c_int, _P],
+         _P, c_size_t, _P, c_int, _P],
     ),
     "b200_mla_decode_bf16": (
         c_int,

@@ -30,6 +30,8 @@ struct MlaParams {
   float* lse;
   float* o_accum;
   float* lse_accum;
+  int* merge_state;  // pair kernel: per (request, q block, CTA) {ticket, done} counters, zero between launches; null =
+                     // split requests are left to the combine kernel
   int batch, s_q, h_q, M;
   float scale_log2;
   int is_causal;

@@ -566,6 +566,12 @@ using namespace b200;
 
 extern "C" {
 
+size_t b200_mla_merge_state_ints(int batch, int s_q, int h_q) {
+  // {ticket, done} per (request, 128-row q block, CTA of the pair)
+  if (batch <= 0 || s_q <= 0 || h_q <= 0) return 0;
+  return (size_t)batch * ((s_q * h_q + 127) / 128) * 4;
+}
+
 size_t b200_mla_workspace_bytes(int batch, int s_q, int h_q, int num_sm_parts) {
   const size_t M = (size_t)s_q * h_q;
   const size_t splits = (size_t)batch + num_sm_parts;
@@ -578,7 +584,7 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
                                       const int32_t* cache_seqlens, const int32_t* tile_scheduler_metadata,
                                       const int32_t* num_splits, int num_sm_parts, int batch, int s_q, int h_q,
                                       float softmax_scale, int is_causal, void* out, float* lse, void* workspace,
-                                      size_t workspace_bytes, int use_pdl, void* stream) {
+                                      size_t workspace_bytes, int32_t* merge_state, int use_pdl, void* stream) {
   if (batch == 0) return 0;  // IDLE batch (flash_api.cpp accepts batch_size 0): nothing to attend
   B200_CHECK(q_nope && q_rope && q_scale && k_lora && k_rope && k_scale && block_table && cache_seqlens &&
                  tile_scheduler_metadata && num_splits && out && lse && workspace,
@@ -640,8 +646,16 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
   int rc;
   // M <= 32: single-CTA SwapAB kernel (KV tokens on UMMA M, q rows on N); above: the CTA-pair kernel (32 < M <= 64 fills
   // one CTA of the pair -- measured faster than a 64-column SwapAB tile)
-  if (M > 32) rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
-  else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
+  if (M > 32) {
+    // with a merge-state buffer the pair kernel merges cut requests itself (the part that finishes last): no combine
+    static const int no_merge = getenv("B200_MLA_NO_MERGE") ? atoi(getenv("B200_MLA_NO_MERGE")) : 0;  // A/B knob
+    // (only when the whole grid is resident at once: with two waves of parts -- 32 < M <= 64 -- the tails of the merging
+    // parts cost more than the combine launch, measured)
+    const bool one_wave = 2 * ((M + 127) / 128) * num_sm_parts <= device_sm_count();
+    prm.merge_state = (no_merge || !one_wave) ? nullptr : reinterpret_cast<int*>(merge_state);
+    rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
+    if (rc || prm.merge_state) return rc;
+  } else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;
   return b200_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, use_pdl, stream);

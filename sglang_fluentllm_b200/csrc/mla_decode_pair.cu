@@ -85,6 +85,7 @@ struct Small {
   uint32_t version;              // bumped by every reference move
   uint32_t k_issued;             // tiles whose K page this CTA's producer has issued (orders the V re-read behind it)
   uint32_t trig[kGroups][3];
+  int merge_ticket;              // split request: how many of its parts had reached their epilogue before this one
   float st_ref[64];              // per-row reference exponent R (log2): O and L are in units of 2^R / 448
   float lred[2][2 * kGroups][64];  // row-sum exchange, double-buffered by request parity
   alignas(16) float lkrk[kGroups][256];  // per softmax group: log2(k_scale) [128], 1 / k_scale [128] of the tile it works on
@@ -954,8 +955,33 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       // a single group needs ~9k cycles for the 128 KB of an fp32 partial, during which its tiles of the next request
       // wait and the other groups run dry behind it (the tile hand-off is in order).
       sm.lred[rq & 1][slot][row] = lsum;
+      // A request cut over several parts is merged by whichever of its parts reaches its epilogue last (no combine
+      // launch): every part takes a ticket here; all but the last write their fp32 partial and count themselves done,
+      // the last one waits for that count (its peers are already in their epilogues), merges in split order and
+      // leaves both counters at zero for the next launch.
+      const bool mrg = !sg.no_split && p.merge_state != nullptr;
+      int* mstate = nullptr;
+      if (mrg) {
+        mstate = p.merge_state + ((((int64_t)b * gridDim.y + blockIdx.y) * 2 + rank) << 1);
+        if (st_id == 0) sm.merge_ticket = atomicAdd(mstate, 1);
+      }
       named_bar_sync(1, kSmThreads);
       const bool had_tiles = sg.n_tiles > 0;
+      int sp0 = 0, n_sp = 1;
+      bool i_merge = false;
+      if (mrg) {
+        sp0 = sg.split_idx - (b == begin_idx ? begin_n_split : 0);
+        n_sp = (b < end_idx ? cur_ns : __ldg(p.num_splits + b + 1)) - sp0;
+        i_merge = sm.merge_ticket == n_sp - 1;
+        if (i_merge) {
+          // the other parts' partials were written long ago (a request's later parts run first) and have left L2 since:
+          // start them on their way back now, while the last P.V of this part drains
+          for (int i = 0; i < n_sp && i < 4; ++i) {
+            if (sp0 + i == sg.split_idx) continue;
+            if (st_id < n_valid_q) bulk_prefetch_l2(p.o_accum + ((int64_t)(sp0 + i) * p.M + q_row0 + st_id) * 512, 2048);
+          }
+        }
+      }
       // the owner of the next request's first tile (global index g0 now) resets the row state; nobody reads the old one
       // any more, and the other groups look at it only after that tile is final (fin)
       if (b < end_idx && grp == (int)(g0 % kGroups) && page == 0) sm.st_ref[row] = kMInit;
@@ -966,7 +992,38 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         const float l = ((lr[0] + lr[64]) + (lr[128] + lr[192])) + (lr[256] + lr[320]);
         const bool bad = (l == 0.f || l != l);
         const float inv = bad ? 1.f : 1.f / l;  // splitkv_mla.cu:1464-1466
-        if (had_tiles) {
+        // merge: [row] the request's lse, [64 + row] this part's (log2), in the row-sum buffer of the other parity
+        float* mg = &sm.lred[(rq & 1) ^ 1][0][0];
+        if (i_merge) {
+          if (st_id == 0) {  // the other parts of this request are in their epilogues already: a short wait
+            uint32_t spins = 0;
+            while (ld_acquire_gpu_s32(mstate + 1) < n_sp - 1) {
+              __nanosleep(64);
+              if (++spins > (1u << 22)) __trap();  // a lost partial: fail loudly instead of hanging the device
+            }
+          }
+          named_bar_sync(1, kSmThreads);
+          if (grp == 0 && page == 0) {
+            const float own = bad ? -INFINITY : log2f(l) + (rloc - kLog2Fp8Max);
+            float glse = 0.f;
+            if (row_valid) {  // the combine kernel's arithmetic (mla_combine.cu:72-110), splits in index order
+              const float* la = p.lse_accum + (int64_t)sp0 * p.M + grow;
+              const int own_i = sg.split_idx - sp0;
+              float mx = -INFINITY;
+              for (int i = 0; i < n_sp; ++i) mx = fmaxf(mx, i == own_i ? own : __ldcg(la + (int64_t)i * p.M));
+              if (mx == -INFINITY) mx = 0.f;
+              float sum = 0.f;
+              for (int i = 0; i < n_sp; ++i) sum += exp2f((i == own_i ? own : __ldcg(la + (int64_t)i * p.M)) - mx);
+              glse = (sum == 0.f || sum != sum) ? INFINITY : log2f(sum) + mx;
+              const int sq = grow / p.h_q, hh = grow % p.h_q;
+              p.lse[((int64_t)b * p.h_q + hh) * p.s_q + sq] = glse * 0.6931471805599453f;
+            }
+            mg[row] = glse;
+            mg[64 + row] = own;
+          }
+          named_bar_sync(1, kSmThreads);
+        }
+        if (had_tiles) {  // (the merge's lse exchange above ran while the last P.V drained)
           // (not pv_done: it completes once per tile and a parity wait from here could be phases behind)
           mbar_wait(&sm.o_ready, o_seg & 1);
           trace<TR>(tr_e, rank, 3, o_seg, 1);
@@ -982,9 +1039,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         const int64_t grow0 = (int64_t)b * p.M + q_row0;
         uint8_t* wst = stage_mine + (row >> 5) * 4096;
         const int wrow0 = row & 32;  // first of this warp's 32 rows within the CTA's 64
-        auto flush = [&](const float* o, int r8) {
+        auto flush = [&](const float* o, int r8, bool as_bf16, float inv) {
           const int d_base = 256 * (r8 >> 2) + 32 * (r8 & 3) + 128 * page;
-          if (sg.no_split) {
+          if (as_bf16) {
             uint8_t* srow = wst + lane * 64;
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
@@ -1012,12 +1069,58 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
                   make_float4(o[4 * k] * inv, o[4 * k + 1] * inv, o[4 * k + 2] * inv, o[4 * k + 3] * inv);
             __syncwarp();
             const int k = lane & 7, rr = lane >> 3;  // per instruction: 4 rows x 128 B
-            float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0 + wrow0) * 512 + d_base + 4 * k;
+            if (!i_merge) {
+              float* dst0 = p.o_accum + ((int64_t)sg.split_idx * p.M + q_row0 + wrow0) * 512 + d_base + 4 * k;
 #pragma unroll
-            for (int it = 0; it < 8; ++it) {
-              const int r = it * 4 + rr;
-              const float4 v = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
-              if (wrow0 + r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512) = v;
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rr;
+                const float4 v = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
+                if (wrow0 + r < n_valid_q) *reinterpret_cast<float4*>(dst0 + (int64_t)r * 512) = v;
+              }
+            } else {
+              // merge (mla_combine.cu:112-150): out = sum_i 2^(lse_i - lse) O_i over the request's splits in index order;
+              // this part's O_i from the staging tile at its turn, the others' from their fp32 partials, 4 rows x 128 B
+              // per load instruction and the 8 loads of a split in flight together
+              float4 acc[8];
+#pragma unroll
+              for (int it = 0; it < 8; ++it) acc[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+              const int own_i = sg.split_idx - sp0;
+#pragma unroll 1
+              for (int i = 0; i < n_sp; ++i) {
+                float4 x[8];
+                float li[8];
+                if (i == own_i) {
+#pragma unroll
+                  for (int it = 0; it < 8; ++it) {
+                    const int r = it * 4 + rr;
+                    x[it] = *reinterpret_cast<const float4*>(wst + r * 128 + ((k ^ (r & 7)) << 4));
+                    li[it] = mg[64 + wrow0 + r];
+                  }
+                } else {
+                  const int64_t prow0 = (int64_t)(sp0 + i) * p.M + q_row0 + wrow0;
+#pragma unroll
+                  for (int it = 0; it < 8; ++it) {
+                    const int r = min(it * 4 + rr, n_valid_q - 1 - wrow0);  // rows past the request: a valid address, unused
+                    x[it] = __ldcg(reinterpret_cast<const float4*>(p.o_accum + (prow0 + r) * 512 + d_base + 4 * k));
+                    li[it] = __ldcg(p.lse_accum + prow0 + r);
+                  }
+                }
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                  const float w = exp2f(li[it] - mg[wrow0 + it * 4 + rr]);
+                  if (w == 0.f || w != w) continue;  // empty split: its partial may hold anything
+                  acc[it].x = fmaf(w, x[it].x, acc[it].x), acc[it].y = fmaf(w, x[it].y, acc[it].y);
+                  acc[it].z = fmaf(w, x[it].z, acc[it].z), acc[it].w = fmaf(w, x[it].w, acc[it].w);
+                }
+              }
+#pragma unroll
+              for (int it = 0; it < 8; ++it) {
+                const int r = it * 4 + rr;
+                __nv_bfloat162 h0 = __floats2bfloat162_rn(acc[it].x, acc[it].y), h1 = __floats2bfloat162_rn(acc[it].z, acc[it].w);
+                if (wrow0 + r < n_valid_q)
+                  *reinterpret_cast<uint2*>(p.out + (grow0 + wrow0 + r) * 512 + d_base + 4 * k) =
+                      make_uint2(*reinterpret_cast<uint32_t*>(&h0), *reinterpret_cast<uint32_t*>(&h1));
+              }
             }
           }
           __syncwarp();  // the slice is rewritten by the next round / this group's next P tile
@@ -1038,7 +1141,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
 #pragma unroll
             for (int k = 0; k < 32; ++k) oa[k] = 0.f;
           }
-          flush(oa, r8);
+          flush(oa, r8, sg.no_split, inv);
         }
         named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
         if (had_tiles) trace<TR>(tr_e, rank, 3, o_seg, 2);
@@ -1047,8 +1150,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (sg.no_split) {
             const int sq = grow / p.h_q, hh = grow % p.h_q;
             p.lse[((int64_t)b * p.h_q + hh) * p.s_q + sq] = bad ? INFINITY : lse2 * 0.6931471805599453f;  // :1484
-          } else {
+          } else if (!i_merge) {
             p.lse_accum[(int64_t)sg.split_idx * p.M + grow] = bad ? -INFINITY : lse2;                    // :1506
+          }
+        }
+        if (mrg) {
+          if (!i_merge) __threadfence();  // this thread's share of the partial, before the count below
+          named_bar_sync(1, kSmThreads);  // (also: mg and merge_ticket are free for the next request)
+          if (st_id == 0) {
+            if (i_merge) {
+              mstate[0] = 0, mstate[1] = 0;
+            } else {
+              atomicAdd(mstate + 1, 1);
+            }
           }
         }
       }

@@ -472,6 +472,12 @@ __device__ __forceinline__ float f16_hi_to_f32(uint32_t h2) {
 // The P operand of P.V under a per-row reference: the page's own e4m3 codes (the reference kernel's codes, relative to
 // the page's row maximum) times the page weight w <= 1 (f16x2), carried as TWO e4m3 terms hi + lo so that the product
 // keeps 8 significant bits (one e4m3 term alone is a different rounding grid: 2^-4 relative noise).
+__device__ __forceinline__ int ld_acquire_gpu_s32(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 __device__ __forceinline__ void split_hi_lo(uint32_t code2, uint32_t w_h2, uint32_t& hi2, uint32_t& lo2) {
   const uint32_t ph = f16x2_mul(e4m3x2_to_f16x2(code2), w_h2);
   hi2 = f16x2_to_e4m3x2(ph);

@@ -4,7 +4,7 @@ input), backed by the sm_100a C-ABI library instead of the sm_90a pybind extensi
 """
 from __future__ import annotations
 
-from typing import Optional, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import torch
 
@@ -42,6 +42,36 @@ def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
     return meta, num_splits
 
 
+_merge_states: Dict[Tuple[int, int], torch.Tensor] = {}
+_merge_retired: List[torch.Tensor] = []  # outgrown buffers: a captured graph may still point at them
+
+
+def merge_state_ints(batch: int, s_q: int, h_q: int) -> int:
+    """Entries of the int32 ``merge_state`` scratch of flash_mla_ckv_fp8_per_token."""
+    return int(_lib.lib().b200_mla_merge_state_ints(batch, s_q, h_q))
+
+
+def new_merge_state(batch: int, s_q: int, h_q: int, device) -> torch.Tensor:
+    """A zeroed merge-state buffer for a caller that owns its own (one per concurrently running call)."""
+    return torch.zeros(max(1, merge_state_ints(batch, s_q, h_q)), dtype=torch.int32, device=device)
+
+
+def _default_merge_state(dev: torch.device, n_ints: int) -> Optional[torch.Tensor]:
+    key = (dev.index if dev.index is not None else torch.cuda.current_device(), torch.cuda.current_stream(dev).cuda_stream)
+    buf = _merge_states.get(key)
+    if buf is not None and buf.numel() >= n_ints:
+        return buf
+    if torch.cuda.is_current_stream_capturing():
+        # a buffer zeroed inside the capture would only be zero after the first replay: leave this call on the
+        # partials + combine path (correct, one more launch) rather than guess
+        return None
+    if buf is not None:
+        _merge_retired.append(buf)
+    buf = torch.zeros(max(n_ints, 1 << 14), dtype=torch.int32, device=dev)
+    _merge_states[key] = buf
+    return buf
+
+
 def flash_mla_ckv_fp8_per_token(
     q_nope: torch.Tensor,
     q_rope: torch.Tensor,
@@ -60,8 +90,15 @@ def flash_mla_ckv_fp8_per_token(
     lse: Optional[torch.Tensor] = None,
     workspace: Optional[torch.Tensor] = None,
     use_pdl: bool = True,
+    merge_state=None,
 ) -> Tuple[torch.Tensor, torch.Tensor]:
     """flash_mla_interface.py:68-120 -> csrc/flash_api.cpp:216-397.
+
+    ``merge_state``: int32 scratch (``merge_state_ints(b, s_q, h_q)`` entries, zero) with which the kernel for
+    s_q * h_q > 32 merges requests cut over several parts itself instead of leaving them to a combine launch (see
+    include/b200_decode.h).  Default: one zeroed buffer per (device, stream), kept by this module; a caller that runs
+    the op on several streams at once or captures it into a graph before the first eager call passes its own;
+    ``False`` keeps the reference's two launches (fp32 partials + combine).
 
     q_nope (b, s_q, h_q, 512) fp8/uint8; q_rope (b, s_q, h_q, 64) bf16; q_scale (b, s_q, h_q, 1) f32;
     k_cache_lora (num_blocks, 64, 1, 512) fp8/uint8; k_cache_rope (num_blocks, 64, 1, 64) bf16;
@@ -115,13 +152,23 @@ def flash_mla_ckv_fp8_per_token(
         if workspace is None:
             workspace = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
         _require(workspace.numel() * workspace.element_size() >= ws_bytes, "workspace too small")
+        n_ms = L.b200_mla_merge_state_ints(b, s_q, h_q)
+        if merge_state is False:
+            merge_state = None
+        elif merge_state is None:
+            merge_state = _default_merge_state(dev, n_ms)
+        else:
+            _cuda(merge_state, "merge_state")
+            _require(merge_state.dtype == torch.int32 and merge_state.is_contiguous() and merge_state.numel() >= n_ms,
+                     "merge_state must be contiguous int32 with at least %d entries" % n_ms)
         _lib.check(
             L.b200_mla_decode_ckv_fp8_per_token(
                 q_nope.data_ptr(), q_rope.data_ptr(), q_scale.data_ptr(), k_cache_lora.data_ptr(),
                 k_cache_rope.data_ptr(), k_scale.data_ptr(), num_blocks, block_table.data_ptr(), block_table.stride(0),
                 cache_seqlens.data_ptr(), tile_scheduler_metadata.data_ptr(), num_splits.data_ptr(), num_sm_parts, b,
                 s_q, h_q, float(softmax_scale), int(bool(causal)), out.data_ptr(), lse.data_ptr(),
-                workspace.data_ptr(), workspace.numel() * workspace.element_size(), int(bool(use_pdl)),
+                workspace.data_ptr(), workspace.numel() * workspace.element_size(),
+                merge_state.data_ptr() if merge_state is not None else None, int(bool(use_pdl)),
                 _lib.current_stream()),
             "flash_mla_ckv_fp8_per_token")
     return out, lse

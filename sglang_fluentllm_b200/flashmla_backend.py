@@ -338,6 +338,9 @@ class FlashMLABackend(AttentionBackend):
         q_nope = q_nope.view(bs, -1, self.num_q_heads, self.kv_lora_rank)
         q_rope = q_rope.view(bs, -1, self.num_q_heads, self.qk_rope_head_dim)
         q_scale = q_scale.view(bs, -1, self.num_q_heads, 1)
+        ms = getattr(self, "_merge_state", None)
+        if ms is not None and ms.numel() < bs * ((q_nope.shape[1] * self.num_q_heads + 127) // 128) * 4:
+            ms = None  # larger than the graph state was sized for: the module's per-stream default
         o, _ = mod.flash_mla_ckv_fp8_per_token(
             q_nope=q_nope, q_rope=q_rope,
             k_cache_lora=k_cache_lora.view(-1, PAGE_SIZE, 1, self.kv_lora_rank),
@@ -348,7 +351,7 @@ class FlashMLABackend(AttentionBackend):
             head_dim_v=self.kv_lora_rank,
             tile_scheduler_metadata=self.forward_metadata.flashmla_metadata,
             num_splits=self.forward_metadata.num_splits,
-            softmax_scale=layer.scaling, causal=True)
+            softmax_scale=layer.scaling, causal=True, merge_state=ms)
         return o.view(-1, layer.tp_q_head_num * layer.v_head_dim)
 
     def forward_decode(self, q, k, v, layer, forward_batch, save_kv_cache=True, **kwargs):
@@ -422,6 +425,8 @@ class FlashMLABackend(AttentionBackend):
         ones = torch.ones(max_bs, dtype=torch.int32, device=block_kv_indices.device)
         self.cuda_graph_mla_metadata, self.cuda_graph_num_splits = self.get_flash_mla_module(m).get_mla_metadata(ones, m, 1)
         self.cuda_graph_kv_indices = block_kv_indices
+        # the graph's own zeroed merge-state scratch (flash_mla_ckv_fp8_per_token merges cut requests in the kernel)
+        self._merge_state = flash_mla_fp8.new_merge_state(max_bs, 1, m, block_kv_indices.device)
 
     def init_forward_metadata_capture_cuda_graph(self, bs, num_tokens, req_pool_indices, seq_lens, forward_mode,
                                                  spec_info=None):

@@ -332,6 +332,35 @@ def test_mla_pair_split_long_sequences(mods):
     assert row_err.max() < 0.2
 
 
+@pytest.mark.parametrize("b,h,s_q,seqlens,causal", [
+    (2, 128, 1, [9000, 4100], False),        # every part boundary inside a request: up to ~50 parts per request
+    (40, 128, 1, [700 + 37 * i for i in range(40)], False),  # most requests cut in two, some whole
+    (3, 128, 2, [3000, 130, 1500], True),    # M = 256: two q blocks per request, causal border
+    (5, 96, 1, [1, 64, 2000, 700, 5000], False),  # half-filled second CTA, a one-token request
+])
+def test_mla_pair_in_kernel_merge_equals_combine(mods, b, h, s_q, seqlens, causal):
+    """Requests cut over several scheduler parts: the pair kernel's own merge (the part that finishes last adds the
+    others' fp32 partials in split order, mla_combine.cu:72-153) against the partials + combine-kernel path on the same
+    inputs -- same arithmetic in the same order, so at most an ulp of the bf16 output apart; the counters are zero
+    again afterwards (the buffer serves the next call as is), and the call is repeatable on it."""
+    fm = mods[1]
+    c = make_case(fm, b, h, s_q, seqlens, nan_pad=False)
+    sl = c["sl"].to(DEV)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    assert (np.diff(ns.cpu().numpy()) > 1).any(), "expected at least one split request"
+    a = (c["qn"], c["qr"], c["kl"], c["kr"], c["qs"], c["ks"], c["bt"].to(DEV), sl, 512, meta, ns)
+    ms = fm.new_merge_state(b, s_q, h, DEV)
+    o_c, l_c = fm.flash_mla_ckv_fp8_per_token(*a, causal=causal, merge_state=False)
+    for _ in range(3):
+        o_m, l_m = fm.flash_mla_ckv_fp8_per_token(*a, causal=causal, merge_state=ms)
+        torch.cuda.synchronize()
+        assert int(ms.abs().max()) == 0, "merge counters not back at zero"
+        assert torch.equal(l_m, l_c) or float((l_m - l_c).abs().max()) < 1e-6
+        d = (o_m.float() - o_c.float()).abs()
+        assert float((d / o_c.float().abs().clamp_min(1e-3)).max()) < 2 ** -7, float(d.max())
+        assert float((d > 0).float().mean()) < 1e-3  # and nearly everywhere the same bits
+
+
 @pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])
 def test_mla_reference_moves_under_growing_logits(mods, h, s_q):
     """Keys whose norm grows along the sequence make the row maximum (and k_scale) climb tile after tile, so the lazy
