@@ -45,6 +45,11 @@ int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_coun
  *   num_splits               int32 [batch + 1]        prefix sums of the per-request split counts */
 int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
                           int32_t* num_splits, void* stream);
+/* The same scheduler with the per-request fixed cost as a parameter (get_mla_metadata.cu:16 fixes it at 5 blocks of 64
+ * tokens, the cost of a request boundary on the reference's sm_90 kernel; here a boundary costs 12-24 blocks' worth of
+ * time).  Same output format; any positive value gives a valid schedule for the decode kernels. */
+int b200_mla_get_metadata_ex(const int32_t* cache_seqlens, int batch, int num_sm_parts, int fixed_overhead_blocks,
+                             int32_t* tile_scheduler_metadata, int32_t* num_splits, void* stream);
 
 /* Per-(token, head) FP8 quantiser for q.  Replaces flash_mla_fp8.quantize_ckv_per_token_head
  * (csrc/flash_api.cpp:399-460, cache_kernels.cu:27-122).

@@ -46,7 +46,8 @@ def num_sm_parts_for(num_heads_per_head_k: int, num_heads_k: int, sm_count: int)
     return sm_count // num_heads_k // ceil_div(num_heads_per_head_k, BLOCK_SIZE_M)
 
 
-def get_mla_metadata(seqlens_k, num_heads_per_head_k: int, num_heads_k: int, sm_count: int):
+def get_mla_metadata(seqlens_k, num_heads_per_head_k: int, num_heads_k: int, sm_count: int,
+                     fixed_overhead_blocks: int = FIXED_OVERHEAD_NUM_BLOCKS):
     """Integer tile scheduler.  csrc/kernels/get_mla_metadata.cu:8-75 (kernel body),
     csrc/flash_api.cpp:27-63 (num_sm_parts, output shapes).
 
@@ -57,7 +58,7 @@ def get_mla_metadata(seqlens_k, num_heads_per_head_k: int, num_heads_k: int, sm_
     seqlens_k = np.asarray(seqlens_k, dtype=np.int64)
     batch_size = int(seqlens_k.shape[0])
     block_size_n = PAGE_BLOCK_SIZE
-    fixed = FIXED_OVERHEAD_NUM_BLOCKS
+    fixed = int(fixed_overhead_blocks)  # the reference's constant unless a test sweeps the product's extension
     num_sm_parts = num_sm_parts_for(num_heads_per_head_k, num_heads_k, sm_count)
 
     num_blocks = [ceil_div(int(s), block_size_n) for s in seqlens_k]

@@ -17,6 +17,7 @@ _SIGNATURES = {
     "b200_sm_count": (c_int, []),
     "b200_mla_num_sm_parts": (c_int, [c_int, c_int, c_int]),
     "b200_mla_get_metadata": (c_int, [_P, c_int, c_int, _P, _P, _P]),
+    "b200_mla_get_metadata_ex": (c_int, [_P, c_int, c_int, c_int, _P, _P, _P]),
     "b200_mla_quantize_q": (c_int, [_P, c_int64, c_int, c_int, _P, _P, _P, _P]),
     "b200_mla_quantize_and_cache_k": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, _P, _P, _P]),
     "b200_mla_rope_quantize_fused": (

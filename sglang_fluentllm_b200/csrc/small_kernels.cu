@@ -7,6 +7,7 @@
 // All are byte/elementwise streaming kernels: 128-bit coalesced loads/stores, one warp per row, no shared-memory
 // staging needed (no reuse).  Arithmetic is IEEE fp32 (explicit _rn intrinsics, no FMA contraction) so e4m3 codes
 // and scale bits are bit-exact against the numpy oracle.
+#include <cstdlib>
 #include <cuda_bf16.h>
 #include <cuda_fp8.h>
 #include <math.h>
@@ -489,18 +490,26 @@ int b200_mla_num_sm_parts(int num_heads_per_head_k, int num_heads_k, int sm_coun
 
 int b200_mla_get_metadata(const int32_t* cache_seqlens, int batch, int num_sm_parts, int32_t* tile_scheduler_metadata,
                           int32_t* num_splits, void* stream) {
+  return b200_mla_get_metadata_ex(cache_seqlens, batch, num_sm_parts, B200_MLA_FIXED_OVERHEAD_BLOCKS,
+                                  tile_scheduler_metadata, num_splits, stream);
+}
+
+int b200_mla_get_metadata_ex(const int32_t* cache_seqlens, int batch, int num_sm_parts, int fixed_overhead_blocks,
+                             int32_t* tile_scheduler_metadata, int32_t* num_splits, void* stream) {
   B200_CHECK((cache_seqlens || batch == 0) && tile_scheduler_metadata && num_splits, "get_metadata: null pointer");
   // batch == 0 is an IDLE batch (a data-parallel attention rank with no request, flash_api.cpp:27-63 accepts it): every
   // part then starts at request 0 >= batch, which the decode kernels read as "no work", and num_splits = [0]
   B200_CHECK(batch >= 0 && num_sm_parts > 0, "get_metadata: batch=%d num_sm_parts=%d", batch, num_sm_parts);
+  B200_CHECK(fixed_overhead_blocks > 0 && fixed_overhead_blocks <= 1024, "get_metadata: fixed_overhead_blocks=%d",
+             fixed_overhead_blocks);
   B200_CHECK((reinterpret_cast<uintptr_t>(tile_scheduler_metadata) & 15) == 0, "get_metadata: metadata must be 16-byte aligned");
   B200_CHECK((size_t)batch * 8 <= 200 * 1024, "get_metadata: batch %d too large", batch);
   const size_t smem = (size_t)batch * 8 + (kMetaThreads / 32) * 4;
   if (smem > 48 * 1024)
     B200_CUDA(cudaFuncSetAttribute(mla_metadata_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   mla_metadata_kernel<<<1, kMetaThreads, smem, (cudaStream_t)stream>>>(cache_seqlens, tile_scheduler_metadata, num_splits,
-                                                                       batch, B200_MLA_PAGE_SIZE,
-                                                                       B200_MLA_FIXED_OVERHEAD_BLOCKS, num_sm_parts);
+                                                                       batch, B200_MLA_PAGE_SIZE, fixed_overhead_blocks,
+                                                                       num_sm_parts);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -23,13 +23,31 @@ def _cuda(t: torch.Tensor, name: str) -> None:
     _require(t.is_cuda, "%s must be on CUDA device" % name)  # flash_api.cpp:23 CHECK_DEVICE
 
 
+REFERENCE_OVERHEAD_BLOCKS = 5  # get_mla_metadata.cu:16 fixed_overhead_num_blocks
+
+
+def tuned_overhead_blocks(num_q_rows: int) -> int:
+    """The scheduler's per-request fixed cost (in 64-token blocks) that balances the parts on B200: a request boundary
+    costs the CTA-pair kernel (more than 64 q rows) about 24 blocks' worth of time and the narrower kernels about 12
+    (measured; the reference's 5 is the sm_90 kernel's).  B200_MLA_SCHED_OVERHEAD overrides (sweeps)."""
+    import os
+    env = os.environ.get("B200_MLA_SCHED_OVERHEAD")
+    if env:
+        return int(env)
+    return 24 if num_q_rows > 64 else 12
+
+
 def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
-                     num_heads_k: int) -> Tuple[torch.Tensor, torch.Tensor]:
+                     num_heads_k: int, fixed_overhead_blocks: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """flash_mla_interface.py:8-23 -> csrc/flash_api.cpp:27-63.
-    Returns (tile_scheduler_metadata int32 [num_sm_parts, 8], num_splits int32 [batch + 1])."""
+    Returns (tile_scheduler_metadata int32 [num_sm_parts, 8], num_splits int32 [batch + 1]).
+    ``fixed_overhead_blocks`` (extension): the scheduler's per-request fixed cost; default = the reference's constant,
+    i.e. the reference's schedule bit for bit; ``tuned_overhead_blocks(M)`` is what the B200 backend passes."""
     _cuda(cache_seqlens, "seqlens_k")
     _require(cache_seqlens.dtype == torch.int32, "seqlens_k must have dtype int32")
     _require(cache_seqlens.is_contiguous(), "seqlens_k must be contiguous")
+    if fixed_overhead_blocks is None:
+        fixed_overhead_blocks = REFERENCE_OVERHEAD_BLOCKS
     L = _lib.lib()
     with torch.cuda.device(cache_seqlens.device):
         num_sm_parts = L.b200_mla_num_sm_parts(num_heads_per_head_k, num_heads_k, L.b200_sm_count())
@@ -37,8 +55,9 @@ def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
         batch = cache_seqlens.numel()
         meta = torch.empty(num_sm_parts, TILE_SCHEDULER_METADATA_SIZE, dtype=torch.int32, device=cache_seqlens.device)
         num_splits = torch.empty(batch + 1, dtype=torch.int32, device=cache_seqlens.device)
-        _lib.check(L.b200_mla_get_metadata(cache_seqlens.data_ptr(), batch, num_sm_parts, meta.data_ptr(),
-                                           num_splits.data_ptr(), _lib.current_stream()), "get_mla_metadata")
+        _lib.check(L.b200_mla_get_metadata_ex(cache_seqlens.data_ptr(), batch, num_sm_parts, int(fixed_overhead_blocks),
+                                              meta.data_ptr(), num_splits.data_ptr(), _lib.current_stream()),
+                   "get_mla_metadata")
     return meta, num_splits
 
 

@@ -401,7 +401,10 @@ class FlashMLABackend(AttentionBackend):
             lens, m = seq_lens + self.draft_token_num, self.draft_token_num * self.num_q_heads
         else:
             raise RuntimeError(f"Not supported forward mode: {forward_mode}")
-        return self.get_flash_mla_module(m).get_mla_metadata(lens.to(torch.int32).contiguous(), m, 1)
+        # the scheduler's per-request cost tuned for this kernel (the reference's constant models its sm_90 kernel)
+        mod = self.get_flash_mla_module(m)
+        return mod.get_mla_metadata(lens.to(torch.int32).contiguous(), m, 1,
+                                    fixed_overhead_blocks=mod.tuned_overhead_blocks(m))
 
     def init_forward_metadata(self, forward_batch):
         """flashmla_backend.py:258-290 (other modes go to the base class, :289-290)."""
@@ -423,7 +426,9 @@ class FlashMLABackend(AttentionBackend):
                                           dtype=torch.int32, device=self.device)
         m = (self.draft_token_num or 1) * self.num_q_heads
         ones = torch.ones(max_bs, dtype=torch.int32, device=block_kv_indices.device)
-        self.cuda_graph_mla_metadata, self.cuda_graph_num_splits = self.get_flash_mla_module(m).get_mla_metadata(ones, m, 1)
+        mod = self.get_flash_mla_module(m)
+        self.cuda_graph_mla_metadata, self.cuda_graph_num_splits = mod.get_mla_metadata(
+            ones, m, 1, fixed_overhead_blocks=mod.tuned_overhead_blocks(m))
         self.cuda_graph_kv_indices = block_kv_indices
         # the graph's own zeroed merge-state scratch (flash_mla_ckv_fp8_per_token merges cut requests in the kernel)
         self._merge_state = flash_mla_fp8.new_merge_state(max_bs, 1, m, block_kv_indices.device)

@@ -62,6 +62,12 @@ def test_metadata_bit_exact(mods, batch, hpk):
     om, ons = omla.get_mla_metadata(seqlens, hpk, 1, _lib.lib().b200_sm_count())
     assert np.array_equal(meta.cpu().numpy()[:, :5], om[:, :5])
     assert np.array_equal(ns.cpu().numpy(), ons)
+    # the scheduler with the per-request cost the B200 backend passes (an extension; same algorithm, same format)
+    for ovh in (fm.tuned_overhead_blocks(hpk), 3, 40):
+        meta, ns = fm.get_mla_metadata(torch.from_numpy(seqlens).to(DEV), hpk, 1, fixed_overhead_blocks=ovh)
+        om, ons = omla.get_mla_metadata(seqlens, hpk, 1, _lib.lib().b200_sm_count(), fixed_overhead_blocks=ovh)
+        assert np.array_equal(meta.cpu().numpy()[:, :5], om[:, :5]), ovh
+        assert np.array_equal(ns.cpu().numpy(), ons), ovh
 
 
 def test_quantize_q_bit_exact(mods):
@@ -257,9 +263,9 @@ def make_case(fm, b, h, s_q, seqlens, seed=0, shuffle=True, nan_pad=True):
                 ks=ks.view(n_pages, 64, 1, 1), bt=block_table, sl=seqlens)
 
 
-def run_mla(fm, c, h, s_q, causal):
+def run_mla(fm, c, h, s_q, causal, overhead=None):
     sl = c["sl"].to(DEV)
-    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1, fixed_overhead_blocks=overhead)
     out, lse = fm.flash_mla_ckv_fp8_per_token(c["qn"], c["qr"], c["kl"], c["kr"], c["qs"], c["ks"], c["bt"].to(DEV), sl,
                                               512, meta, ns, causal=causal)
     torch.cuda.synchronize()
@@ -288,11 +294,15 @@ MLA_CASES = [
 ]
 
 
+@pytest.mark.parametrize("schedule", ["reference", "tuned"])
 @pytest.mark.parametrize("name,b,h,s_q,seqlens,causal", MLA_CASES, ids=[c[0] for c in MLA_CASES])
-def test_mla_decode_vs_oracles(mods, name, b, h, s_q, seqlens, causal):
+def test_mla_decode_vs_oracles(mods, name, b, h, s_q, seqlens, causal, schedule):
+    """Under the reference's tile schedule (the default of get_mla_metadata) and under the one the B200 backend asks
+    for (tuned_overhead_blocks): the faithful oracle follows whichever metadata it is given."""
     fm = mods[1]
     c = make_case(fm, b, h, s_q, seqlens)
-    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, causal)
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, causal,
+                                       overhead=None if schedule == "reference" else fm.tuned_overhead_blocks(h * s_q))
     assert not np.isnan(out).any(), "NaN leaked from the poisoned padding rows"
     so, sl = omla.flash_mla_ckv_fp8_semantic(*args, causal=causal)
     fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=causal)

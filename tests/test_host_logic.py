@@ -204,9 +204,10 @@ def test_backend_metadata_path_on_the_references_own_pool_and_allocator(monkeypa
             assert alloc.alloc(req, n, 0) is not None
         seen = []
 
-        def oracle_metadata(cache_seqlens, num_heads_per_head_k, num_heads_k):
+        def oracle_metadata(cache_seqlens, num_heads_per_head_k, num_heads_k, fixed_overhead_blocks=5):
             seen.append((cache_seqlens.clone(), num_heads_per_head_k, num_heads_k))
-            meta, ns = omla.get_mla_metadata(cache_seqlens.numpy(), num_heads_per_head_k, num_heads_k, 148)
+            meta, ns = omla.get_mla_metadata(cache_seqlens.numpy(), num_heads_per_head_k, num_heads_k, 148,
+                                             fixed_overhead_blocks=fixed_overhead_blocks)
             return torch.from_numpy(meta), torch.from_numpy(ns)
 
         monkeypatch.setattr(fb.flash_mla_fp8, "get_mla_metadata", oracle_metadata)
@@ -230,7 +231,9 @@ def test_backend_metadata_path_on_the_references_own_pool_and_allocator(monkeypa
         assert torch.equal(md.block_table, alloc.req_to_page[reqs]) and md.block_table.dtype == torch.int32
         lens, m, hk = seen[-1]
         assert lens.dtype == torch.int32 and lens.tolist() == seq_lens.tolist() and (m, hk) == (16, 1)
-        want_meta, want_ns = omla.get_mla_metadata(seq_lens.numpy(), 16, 1, 148)
+        # (the backend asks for the schedule with the per-request cost tuned for the B200 kernels)
+        want_meta, want_ns = omla.get_mla_metadata(seq_lens.numpy(), 16, 1, 148,
+                                                   fixed_overhead_blocks=fm.tuned_overhead_blocks(16))
         assert np.array_equal(md.flashmla_metadata.numpy(), want_meta) and np.array_equal(md.num_splits.numpy(), want_ns)
         # the three tensors per layer the kernel call receives are the reference pool's own (views, no copies)
         k_lora, k_scale, k_rope = pool.get_key_buffer(1)

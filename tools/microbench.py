@@ -7,6 +7,9 @@ import torch
 from sglang_fluentllm_b200 import flash_mla_fp8 as fm, deep_gemm as dg, fp8_kernel as fk, _lib
 from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
 
+# the tile schedule the backend runs (per-request cost tuned for B200); a tree without the extension keeps the reference's
+SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m)} if hasattr(fm, "tuned_overhead_blocks") else {})
+
 dev = torch.device("cuda:0")
 PEAK = 6555.8
 
@@ -55,7 +58,7 @@ def bench_mla(b, seq, h, s_q=1, n_rot=None):
     qn, qs, qr = fm.quantize_ckv_per_token_head(q, 512)
     bt = (torch.randperm(n_pages - 1)[: b * pages_per].reshape(b, pages_per) + 1).to(torch.int32).to(dev)
     sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
-    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1, **SCHED(s_q * h))
     L = _lib.lib()
     out = torch.empty(b, s_q, h, 512, dtype=torch.bfloat16, device=dev)
     lse = torch.empty(b, h, s_q, dtype=torch.float32, device=dev)
@@ -84,7 +87,7 @@ def bench_mla_bf16(b, seq, h, s_q=1):
     q = torch.randn(b, s_q, h, 576, dtype=torch.bfloat16, device=dev)
     bt = (torch.randperm(n_pages - 1)[: b * pages_per].reshape(b, pages_per) + 1).to(torch.int32).to(dev)
     sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
-    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1, **SCHED(s_q * h))
     L = _lib.lib()
     out = torch.empty(b, s_q, h, 512, dtype=torch.bfloat16, device=dev)
     lse = torch.empty(b, h, s_q, dtype=torch.float32, device=dev)
