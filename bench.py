@@ -61,6 +61,9 @@ def parse():
                          "column- and row-parallel weights over the GPUs with one all-reduce per layer (strong scaling; "
                          "MLA's single latent KV head makes every rank stream the whole KV pool).  The dp run also "
                          "reports a short tp measurement under \"tp_strong\".")
+    ap.add_argument("--timeline", default=None, metavar="FILE",
+                    help="diagnostic: replay the captured step under the CUPTI activity profiler and write per-kernel "
+                         "durations and the idle gaps between consecutive kernels to FILE (not a bench value)")
     ap.add_argument("--profile-step", action="store_true",
                     help="run ONE eager step between cudaProfilerStart/Stop and exit (for an ncu launch list of the step)")
     ap.add_argument("--no-graph", action="store_true")
@@ -320,7 +323,8 @@ class HotPath:
         y = m.apply(self.lin_o[l], xq, block_scale=xs, output_dtype=torch.bfloat16)
         if self.tp > 1:
             self.tpmod.all_reduce_sum(y)  # the path's single exchange: row-parallel partial sums over NVLink
-        # launches: act-quant, GEMM(+reduce), norm+quant, GEMM, bmm, prologue, decode, combine, bmm, act-quant, GEMM
+        # launches: act-quant, GEMM, norm+quant, GEMM, bmm, prologue, decode (merges cut requests itself), bmm, act-quant,
+        # GEMM + split-K reduce
         self.launches_per_step += 11
         return y
 
@@ -342,7 +346,7 @@ class HotPath:
         self.fm.flash_mla_ckv_fp8_per_token(
             q_nope, q_rope, kl.view(-1, PAGE, 1, KV_LORA), kr.view(-1, PAGE, 1, ROPE), q_scale, ks.view(-1, PAGE, 1, 1),
             md.block_table[: self.args.batch], self.seq_lens, KV_LORA, md.flashmla_metadata, md.num_splits,
-            out=self.attn_out, lse=self.lse, workspace=self.workspace)
+            softmax_scale=self.attn_layers[l].scaling, out=self.attn_out, lse=self.lse, workspace=self.workspace)
 
 
 def workload_config(args, world, parallelism, heads_per_gpu, cuda_graph=True):
@@ -455,6 +459,9 @@ def run_b200(args):
         for _ in range(max(args.warmup, 3)):
             run_step()
         log("warm-up replays done")
+        if args.timeline:
+            write_timeline(args.timeline, run_step, stream, args.layers)
+            return
         sampler = ClockSampler(local_rank)
         sampler.start()
         ms = timed(run_step, args.steps)
@@ -572,6 +579,46 @@ def run_b200(args):
 # ----------------------------------------------------------------------------------------------------------------
 # CPU baseline / reference arm
 # ----------------------------------------------------------------------------------------------------------------
+def write_timeline(path, run_step, stream, layers):
+    """Per-kernel durations and inter-kernel gaps of one replayed step (CUPTI activity records)."""
+    import torch
+    from torch.profiler import ProfilerActivity, profile
+    with profile(activities=[ProfilerActivity.CUDA]) as prof:
+        run_step()
+        stream.synchronize()
+    evs = []
+    for e in prof.events():
+        if getattr(e, "device_type", None) is not None and "CUDA" in str(e.device_type):
+            evs.append((e.time_range.start, e.time_range.end, e.name))
+    evs.sort()
+    per = {}
+    busy = 0.0
+    gaps = []
+    for i, (t0, t1, name) in enumerate(evs):
+        d = per.setdefault(name, [0, 0.0, 0.0])  # count, total duration, total gap in front of it
+        d[0] += 1
+        d[1] += t1 - t0
+        busy += t1 - t0
+        if i:
+            g = t0 - evs[i - 1][1]
+            d[2] += g
+            gaps.append(g)
+    span = evs[-1][1] - evs[0][0] if evs else 0.0
+    with open(path, "w") as f:
+        f.write("one replayed step: %d device activities, span %.1f us, busy %.1f us, idle between kernels %.1f us (%.1f %%)\n"
+                % (len(evs), span, busy, span - busy, 100.0 * (span - busy) / max(span, 1e-9)))
+        f.write("%6s %10s %10s %10s  %s\n" % ("count", "avg us", "total us", "gap before", "kernel"))
+        for name, (n, tot, gap) in sorted(per.items(), key=lambda kv: -kv[1][1]):
+            f.write("%6d %10.2f %10.1f %10.2f  %s\n" % (n, tot / n, tot, gap / n, name[:110]))
+        per_layer = len(evs) // max(layers, 1)
+        if per_layer and len(evs) >= 3 * per_layer:
+            f.write("layer 2 in launch order (start relative to the layer's first kernel, duration, gap before):\n")
+            base = evs[2 * per_layer][0]
+            for i in range(2 * per_layer, 3 * per_layer):
+                t0, t1, name = evs[i]
+                f.write("  %9.2f %8.2f %7.2f  %s\n" % (t0 - base, t1 - t0, t0 - evs[i - 1][1], name[:100]))
+
+
 def cpu_baseline(args, budget_s=20.0):
     """The reference's CPU path for this step (torch-native SDPA decode loop over a bf16 pool + native block-FP8
     matmul), ported in oracle/native_cpu.py, on a bounded sample: `sample_b` requests of one layer."""

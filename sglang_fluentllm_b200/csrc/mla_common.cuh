@@ -15,7 +15,12 @@ static constexpr int kTileTokens = 128;
 static constexpr int kPage = B200_MLA_PAGE_SIZE;
 static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
 static constexpr float kLog2Fp8Max = 8.807354922057604f;      // log2(448): a page's largest P' maps to the e4m3 maximum (splitkv_mla.cu:433)
-static constexpr float kRefHeadroom = 4.0f;                   // log2: a moved row reference leaves 2^4 of growth before the next move
+// log2 of the growth a moved row reference leaves before the next move.  A move drains the P.V pipeline and rescales O
+// in TMEM (2-3 tiles' worth of time), and with attention logits of spread sigma = 2.5 (log2 units: DeepSeek's 192^-0.5
+// scaling on unit-variance q, k) a headroom of 4 sent 23 % of the tiles down that path, 7 sends 0.1 % (sigma = 4: 62 % /
+// 14 %).  The price is e4m3 range: page weights down to 2^-7 leave the lo term of small codes subnormal; simulated
+// distance to the faithful oracle 1.0-1.9e-3 instead of 0.7-1.0e-3 (tools/sim_hilo.py), 2.6e-3 at 8, 8e-3 at 10.
+static constexpr float kRefHeadroom = 7.0f;
 
 struct MlaParams {
   CUtensorMap tm_q_nope, tm_q_rope, tm_k_nope, tm_k_rope;

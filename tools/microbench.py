@@ -8,6 +8,9 @@ from sglang_fluentllm_b200 import flash_mla_fp8 as fm, deep_gemm as dg, fp8_kern
 from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
 
 # the tile schedule the backend runs (per-request cost tuned for B200); a tree without the extension keeps the reference's
+# softmax scale of the model (DeepSeek-V3: qk_head_dim ** -0.5 = 192 ** -0.5; on unit-variance q and k that is a logit
+# spread of 2.5 in log2 units, which decides how often a row reference moves); B200_MB_SCALE overrides
+SM_SCALE = float(os.environ.get("B200_MB_SCALE", 192 ** -0.5))
 SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m)} if hasattr(fm, "tuned_overhead_blocks") else {})
 
 dev = torch.device("cuda:0")
@@ -66,8 +69,8 @@ def bench_mla(b, seq, h, s_q=1, n_rot=None):
 
     def fn(i):
         kl, kr, ks = pools[i % n_rot]
-        fm.flash_mla_ckv_fp8_per_token(qn, qr, kl, kr, qs, ks, bt, sl, 512, meta, ns, causal=s_q > 1, out=out, lse=lse,
-                                       workspace=ws)
+        fm.flash_mla_ckv_fp8_per_token(qn, qr, kl, kr, qs, ks, bt, sl, 512, meta, ns, softmax_scale=SM_SCALE,
+                                       causal=s_q > 1, out=out, lse=lse, workspace=ws)
 
     us = time_graph(fn, n_rot)
     S, M = b * seq, h * s_q
