@@ -92,6 +92,6 @@ __device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_id
 }
 
 // CTA-pair kernel for 64 < M (mla_decode_pair.cu); the Q tensor maps must use 64-row boxes.
-int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream);
+int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream_t stream);
 
 }  // namespace b200

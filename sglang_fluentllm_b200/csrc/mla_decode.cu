@@ -653,7 +653,7 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
     // parts cost more than the combine launch, measured)
     const bool one_wave = 2 * ((M + 127) / 128) * num_sm_parts <= device_sm_count();
     prm.merge_state = (no_merge || !one_wave) ? nullptr : reinterpret_cast<int*>(merge_state);
-    rc = launch_mla_pair(prm, num_sm_parts, (cudaStream_t)stream);
+    rc = launch_mla_pair(prm, num_sm_parts, use_pdl != 0 && pdl_default(), (cudaStream_t)stream);
     if (rc || prm.merge_state) return rc;
   } else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);

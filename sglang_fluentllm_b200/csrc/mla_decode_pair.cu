@@ -166,14 +166,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
     g_part_cycles[(part * 2 + rank) * 4 + 2] = clock64();
   }
 
-  const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
-  const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
-            end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
-  // the split-KV combine kernel behind this one is launched with programmatic stream serialization: its CTAs may be
-  // scheduled as soon as SMs drain (its griddepcontrol.wait orders the reads of the partials)
-  pdl_launch_dependents();
-  if (begin_idx >= p.batch) return;  // splitkv_mla.cu:1226 (both CTAs of the pair take the same exit)
-
+  // Launched as a programmatic dependent of the kernel in front of it (the prologue that writes q and the new K rows):
+  // everything up to griddepcontrol.wait touches no global data and overlaps that kernel's tail.
   if (tid == 0) {
     for (int i = 0; i < kKStages; ++i) {
       mbar_init(&sm.k_full[i], 2);  // one expect_tx arrival per CTA of the pair (leader's copy is the live one)
@@ -221,6 +215,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
   cluster_sync_all();  // the peer's barriers are initialised before anything is credited to them
   tc_fence_after();
   const uint32_t tmem = sm.tmem_base;
+
+  pdl_wait_prior_grid();
+  const int32_t* meta = p.meta + part * B200_MLA_METADATA_INTS;
+  const int begin_idx = __ldg(meta + 0), begin_seqlen = __ldg(meta + 1), end_idx = __ldg(meta + 2),
+            end_seqlen = __ldg(meta + 3), begin_n_split = __ldg(meta + 4);
+  // a kernel behind this one that is launched with programmatic stream serialization may be scheduled as SMs drain
+  // (its own griddepcontrol.wait orders its reads)
+  pdl_launch_dependents();
+  if (begin_idx >= p.batch) {  // splitkv_mla.cu:1226 (both CTAs of the pair take the same exit)
+    tc_fence_before();
+    __syncthreads();
+    cluster_sync_all();
+    if (warp == 1) tmem_dealloc_pair(tmem, kTmemCols);
+    return;
+  }
 
   if (warp == 0) {
     // ============================== TMA producer (both CTAs) ==============================
@@ -809,9 +818,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         trace<TR>(tr_w, rank, 4, g, 0);
         // the first tiles of a request always see a reference move (the first tile makes one): their weighted pass
         // waits for the predecessor's reference instead of running ahead of it (the max pass above did overlap it)
-        if (t < kGroups && g > 0) {
+        // (the third tile only needs the first tile's reference, not its predecessor's publish: fin of tile g - 2 shares
+        // this tile's barrier slot and stays complete until this group arrives on it; a move by tile g - 1 in between is
+        // caught by the version check like anywhere else)
+        if (t == 1 && g > 0) {
           mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
           fin_waited = true;
+        } else if (t == 2) {
+          mbar_wait(&sm.fin[g & 1], ((g - 2) >> 1) & 1);
         }
 
         float acc = 0.f, w32 = 0.f;
@@ -1184,18 +1198,16 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
 
 }  // namespace pairk
 
-int launch_mla_pair(const MlaParams& prm, int num_sm_parts, cudaStream_t stream) {
+int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream_t stream) {
   const int smem = pairk::kTotal + 1024;
   const int q_pairs = (prm.M + 127) / 128;
+  const dim3 grid(2, q_pairs, num_sm_parts), block(128 + pairk::kSmThreads);
   if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, knobs that break results
     B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pairk::mla_decode_pair_kernel<true><<<dim3(2, q_pairs, num_sm_parts), 128 + pairk::kSmThreads, smem, stream>>>(prm);
-  } else {
-    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    pairk::mla_decode_pair_kernel<false><<<dim3(2, q_pairs, num_sm_parts), 128 + pairk::kSmThreads, smem, stream>>>(prm);
+    return launch_kernel(pairk::mla_decode_pair_kernel<true>, grid, block, smem, stream, pdl, prm);
   }
-  B200_CUDA(cudaGetLastError());
-  return 0;
+  B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+  return launch_kernel(pairk::mla_decode_pair_kernel<false>, grid, block, smem, stream, pdl, prm);
 }
 
 }  // namespace b200
