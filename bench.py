@@ -535,6 +535,11 @@ def run_b200(args):
         targs.parallelism = "tp"
         hp_tp = HotPath(targs, rank, world, dev)
         torch.cuda.synchronize()
+        # the all-reduce: this repo's two-shot kernel over NVLink peer memory (csrc/p2p_comm.cu); B200_TP_NCCL=1 keeps
+        # torch.distributed's NCCL call for A/B
+        use_p2p = not os.environ.get("B200_TP_NCCL")
+        if use_p2p:
+            hp_tp.tpmod.enable_p2p_all_reduce(None, dev, args.batch * HIDDEN * 2)
         with torch.cuda.stream(stream):
             for _ in range(2):
                 hp_tp.step(hp_tp.hidden_in)
@@ -555,7 +560,9 @@ def run_b200(args):
             ms_tp = hp_tp.tpmod.max_over_ranks_ms(e0.elapsed_time(e1), dev) / args.steps
         tp_strong = {"value": round(args.batch / (ms_tp * 1e-3), 2), "unit": "tokens/s", "ms_per_step": round(ms_tp, 4),
                      "global_batch": args.batch, "heads_per_gpu": hp_tp.h, "scaling": "strong",
-                     "collective": "1 NCCL all-reduce [b, 7168] bf16 per layer on the row-parallel o_proj output"}
+                     "collective": ("1 all-reduce [b, 7168] bf16 per layer on the row-parallel o_proj output: "
+                                    + ("two-shot kernel over NVLink peer memory (csrc/p2p_comm.cu)" if use_p2p else "NCCL")),
+                     "nvlink_bytes_per_step_per_gpu": int(2 * (world - 1) / world * args.batch * HIDDEN * 2 * args.layers)}
         g_tp = hp_tp = None
         log("tp_strong done")
     if tp_strong is not None:

@@ -139,6 +139,38 @@ int b200_mla_decode_bf16(const void* q, const void* k_cache, int64_t num_pages, 
 int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
                      int batch, int s_q, int h_q, int use_pdl, void* stream);
 
+/* ---- one-box collectives over NVLink peer memory (csrc/p2p_comm.cu) -------------------------------------------------
+ * Replace, for the exchanges either side of the attention block: tensor_model_parallel_all_reduce behind the
+ * row-parallel o_proj (python/sglang/srt/layers/linear.py:1139) and the uneven token reduce-scatter / all-gather of the
+ * attention-TP group (distributed/decoder_comm_manager.py:42-89; sm_90 implementation:
+ * distributed/device_communicators/custom_triton_rsag/triton_rsag.py:97-300).
+ * Every rank allocates one communication buffer (buf_bytes, the same on every rank) and one flag pad
+ * (b200_comm_flag_bytes) with b200_comm_alloc, exports both (64-byte CUDA IPC handles), and opens its peers' (same
+ * node).  bufs / flags: HOST arrays [world] of the device pointers as mapped in this process (own entries = own
+ * allocations).  A call is collective: every rank of the group launches it with the same sizes (`blocks` is reserved:
+ * pass 0) on its own operand `in`; the kernel stages the operand in HALF of the buffer (the halves alternate per call, which is
+ * what lets a call end without a barrier), so an operand may take at most buf_bytes / 2.  bf16, 16-byte granularity;
+ * sums in rank order in fp32 (every rank gets the same bits).  The pads carry the call counters: only these entry
+ * points may touch them, and a call that trapped (a peer never arrived) leaves the group unusable. */
+size_t b200_comm_flag_bytes(void);
+int b200_comm_alloc(size_t bytes, void** ptr);
+int b200_comm_free(void* ptr);
+int b200_comm_ipc_export(void* ptr, void* handle64);
+int b200_comm_ipc_open(const void* handle64, void** ptr);
+int b200_comm_ipc_close(void* ptr);
+/* out[numel] = sum over ranks of in[numel] (two ranks: one pass over the peer's operand; more: two-shot). */
+int b200_comm_all_reduce_bf16(void* const* bufs, void* const* flags, size_t buf_bytes, int rank, int world, const void* in,
+                              int64_t numel, void* out, int blocks, void* stream);
+/* row_offsets: HOST int64 [world + 1], first row of every rank's share.  in [row_offsets[world]][hidden] on every
+ * rank, out [rows of this rank][hidden]. */
+int b200_comm_reduce_scatter_bf16(void* const* bufs, void* const* flags, size_t buf_bytes, int rank, int world,
+                                  const int64_t* row_offsets, const void* in, int64_t hidden, void* out, int blocks,
+                                  void* stream);
+/* in [rows of this rank][hidden], out [row_offsets[world]][hidden] = every rank's rows in rank order. */
+int b200_comm_all_gather_bf16(void* const* bufs, void* const* flags, size_t buf_bytes, int rank, int world,
+                              const int64_t* row_offsets, const void* in, int64_t hidden, void* out, int blocks,
+                              void* stream);
+
 /* 1x128 activation quantiser, column-major TMA-aligned scales.  Replaces sgl_per_token_group_quant_fp8
  * (3rdparty/flashinfer/csrc/sgl_fp8_quantization.cu:357-520; python wrapper
  * python/sglang/srt/layers/dense/gemms/fp8/fp8_kernel.py:430-463).

@@ -39,6 +39,15 @@ _SIGNATURES = {
          c_int, _P],
     ),
     "b200_mla_combine": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, _P]),
+    "b200_comm_flag_bytes": (c_size_t, []),
+    "b200_comm_alloc": (c_int, [c_size_t, _P]),
+    "b200_comm_free": (c_int, [_P]),
+    "b200_comm_ipc_export": (c_int, [_P, _P]),
+    "b200_comm_ipc_open": (c_int, [_P, _P]),
+    "b200_comm_ipc_close": (c_int, [_P]),
+    "b200_comm_all_reduce_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, c_int64, _P, c_int, _P]),
+    "b200_comm_reduce_scatter_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, _P, c_int64, _P, c_int, _P]),
+    "b200_comm_all_gather_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, _P, c_int64, _P, c_int, _P]),
     "b200_act_quant_1x128": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),
     "b200_act_quant_1x128_strided": (c_int, [_P, c_int64, c_int64, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),
     "b200_qk_rmsnorm_quant": (c_int, [_P, c_int64, c_int64, c_int, c_int, _P, _P, c_float, _P, c_int64, _P, _P, c_int64, c_float, _P]),

@@ -79,10 +79,35 @@ def shard_row_parallel(weight: torch.Tensor, scale: torch.Tensor, cols: slice):
     return weight[:, cols].contiguous(), scale[:, cols.start // BLOCK: cols.stop // BLOCK].contiguous()
 
 
+_p2p = None  # comm.P2PGroup of the tensor-parallel group once enable_p2p_all_reduce() has run
+
+
+def enable_p2p_all_reduce(group, device, max_bytes: int):
+    """Route the block's all-reduce through this repo's NVLink peer-memory kernel (csrc/p2p_comm.cu) instead of NCCL:
+    collective (every rank of ``group`` calls it once, before any graph capture).  Returns the comm.P2PGroup."""
+    global _p2p
+    from . import comm
+    _p2p = comm.P2PGroup(group if group is not None else dist.group.WORLD, device, max_bytes)
+    return _p2p
+
+
+def disable_p2p_all_reduce() -> None:
+    global _p2p
+    if _p2p is not None:
+        _p2p.close()
+    _p2p = None
+
+
 def all_reduce_sum(t: torch.Tensor, group=None) -> torch.Tensor:
-    """The path's single exchange.  In place; a no-op without a process group (tp = 1)."""
+    """The path's single exchange.  In place; a no-op without a process group (tp = 1).  CUDA bf16 tensors that fit the
+    peer-memory buffer go through the P2P kernel when it is enabled, everything else through torch.distributed (NCCL on
+    the GPU box, gloo in the CPU tests)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+        if (_p2p is not None and t.is_cuda and t.dtype == torch.bfloat16 and t.is_contiguous() and t.numel() % 8 == 0
+                and t.numel() * 2 <= _p2p.max_operand_bytes):
+            _p2p.all_reduce(t)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
     return t
 
 

@@ -102,3 +102,99 @@ def test_tp2_block_equals_unsharded_block(tmp_path):
     # the sharded run rounds each rank's partial o_proj sums to bf16 before the all-reduce and re-quantises per-rank
     # activations: bf16-level agreement
     assert rel < 1e-2, rel
+
+
+def _p2p_worker(rank, world, port, out_path):
+    """The peer-memory collectives of csrc/p2p_comm.cu against torch.distributed (NCCL) on the same tensors."""
+    import time
+    import torch.distributed as dist
+    from sglang_fluentllm_b200 import comm
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ.setdefault("B200_COMM_SPIN_LIMIT", str(1 << 22))  # a lost signal fails within seconds here
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world)
+    try:
+        dev = torch.device("cuda", rank)
+        hidden = 7168
+        rsag = comm.RSAG(dist.group.WORLD, rank, max_tokens=256, hidden_size=hidden, device=dev)
+        p2p = rsag.p2p
+        g = torch.Generator(device=dev).manual_seed(7 + rank)
+        res = {}
+        # all-reduce, 128 x 7168 (the o_proj output of the metric shape) and a small ragged size; repeated (flag reuse)
+        for shape in ((128, hidden), (3, 8), (37, 1024)):
+            for it in range(3):
+                x = torch.randn(*shape, device=dev, generator=g).to(torch.bfloat16)
+                want = x.float().clone()
+                dist.all_reduce(want)
+                got = p2p.all_reduce(x.clone())
+                torch.cuda.synchronize()
+                # NCCL sums in fp32 here (the float copy): the kernel's bf16 rounding of one fp32 sum must match it
+                assert torch.equal(got, want.to(torch.bfloat16)), (shape, it)
+        # uneven reduce-scatter / all-gather, incl. a rank without rows
+        for tokens in ([130, 126], [5, 0], [0, 3], [1, 1]):
+            total = sum(tokens)
+            x = torch.randn(total, hidden, device=dev, generator=g).to(torch.bfloat16)
+            want = x.float().clone()
+            dist.all_reduce(want)
+            want = want.to(torch.bfloat16)
+            mine, off = rsag.reduce_scatter(x, token_list_in_group=tokens)
+            assert off == sum(tokens[:rank]) and mine.shape[0] == tokens[rank]
+            assert torch.equal(mine, want[off: off + tokens[rank]]), tokens
+            back = rsag.all_gather(mine, token_list_in_group=tokens)
+            torch.cuda.synchronize()
+            assert torch.equal(back, want), tokens
+        mine, off = rsag.reduce_scatter(torch.ones(7, hidden, device=dev, dtype=torch.bfloat16), 7)   # tp_num_tokens form
+        assert (mine.shape[0], off) == ((4, 0) if rank == 0 else (3, 4)) and float(mine.float().min()) == 2.0
+        # the all-reduce inside a CUDA graph, replayed (the flag pads return to zero after every call)
+        x = torch.randn(128, hidden, device=dev, generator=g).to(torch.bfloat16)
+        y = torch.empty_like(x)
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            p2p.all_reduce(x, out=y)
+            s.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, stream=s):
+                p2p.all_reduce(x, out=y)
+            want = x.float().clone()
+        dist.all_reduce(want)
+        for _ in range(5):
+            y.zero_()
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(y, want.to(torch.bfloat16))
+        # timing, 1.84 MB: NCCL against the peer-memory kernel (graph replays, device-timed)
+        def timed(fn, n=50):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            dist.barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) * 1e3 / n
+        res["nccl_us"] = timed(lambda: dist.all_reduce(x))
+        res["p2p_us"] = timed(lambda: p2p.all_reduce(x, out=y))
+        res["p2p_graph_us"] = timed(graph.replay)
+        if rank == 0:
+            import json
+            json.dump(res, open(out_path, "w"))
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_p2p_collectives_match_nccl(tmp_path):
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    out_path = str(tmp_path / "p2p.json")
+    mp.spawn(_p2p_worker, args=(2, _free_port(), out_path), nprocs=2, join=True)
+    import json
+    r = json.load(open(out_path))
+    print("all-reduce of 128 x 7168 bf16 on 2 GPUs: NCCL %.1f us, peer-memory kernel %.1f us (in a graph %.1f us)" % (
+        r["nccl_us"], r["p2p_us"], r["p2p_graph_us"]))
+    os.makedirs("gpurun_out", exist_ok=True)
+    json.dump(r, open("gpurun_out/p2p_all_reduce_2gpu.json", "w"))
