@@ -561,7 +561,9 @@ def run_b200(args):
         tp_strong = {"value": round(args.batch / (ms_tp * 1e-3), 2), "unit": "tokens/s", "ms_per_step": round(ms_tp, 4),
                      "global_batch": args.batch, "heads_per_gpu": hp_tp.h, "scaling": "strong",
                      "collective": ("1 all-reduce [b, 7168] bf16 per layer on the row-parallel o_proj output: "
-                                    + ("two-shot kernel over NVLink peer memory (csrc/p2p_comm.cu)" if use_p2p else "NCCL")),
+                                    + (("this repo's kernel over NVLink (csrc/p2p_comm.cu): "
+                                        + ("in-switch reduction (multimem)" if getattr(hp_tp.tpmod._p2p, "_nvls", None)
+                                           and world > 2 else "peer loads")) if use_p2p else "NCCL")),
                      "nvlink_bytes_per_step_per_gpu": int(2 * (world - 1) / world * args.batch * HIDDEN * 2 * args.layers)}
         g_tp = hp_tp = None
         log("tp_strong done")

@@ -161,6 +161,11 @@ int b200_comm_ipc_close(void* ptr);
 /* out[numel] = sum over ranks of in[numel] (two ranks: one pass over the peer's operand; more: two-shot). */
 int b200_comm_all_reduce_bf16(void* const* bufs, void* const* flags, size_t buf_bytes, int rank, int world, const void* in,
                               int64_t numel, void* out, int blocks, void* stream);
+/* The same sum through the switch (NVLS).  multicast_ptr / local_ptr: the multicast and the local mapping of ONE
+ * symmetric buffer of buf_bytes per rank bound to a multicast object spanning the group (e.g. what
+ * torch.distributed._symmetric_memory's rendezvous returns); flags: the pads of this library as above. */
+int b200_comm_all_reduce_nvls_bf16(void* multicast_ptr, void* local_ptr, void* const* flags, size_t buf_bytes, int rank,
+                                   int world, const void* in, int64_t numel, void* out, int blocks, void* stream);
 /* row_offsets: HOST int64 [world + 1], first row of every rank's share.  in [row_offsets[world]][hidden] on every
  * rank, out [rows of this rank][hidden]. */
 int b200_comm_reduce_scatter_bf16(void* const* bufs, void* const* flags, size_t buf_bytes, int rank, int world,

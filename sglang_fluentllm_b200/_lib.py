@@ -46,6 +46,7 @@ _SIGNATURES = {
     "b200_comm_ipc_open": (c_int, [_P, _P]),
     "b200_comm_ipc_close": (c_int, [_P]),
     "b200_comm_all_reduce_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, c_int64, _P, c_int, _P]),
+    "b200_comm_all_reduce_nvls_bf16": (c_int, [_P, _P, _P, c_size_t, c_int, c_int, _P, c_int64, _P, c_int, _P]),
     "b200_comm_reduce_scatter_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, _P, c_int64, _P, c_int, _P]),
     "b200_comm_all_gather_bf16": (c_int, [_P, _P, c_size_t, c_int, c_int, _P, _P, c_int64, _P, c_int, _P]),
     "b200_act_quant_1x128": (c_int, [_P, c_int64, c_int64, _P, _P, c_int64, c_float, _P]),

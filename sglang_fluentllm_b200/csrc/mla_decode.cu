@@ -77,7 +77,7 @@ static_assert(sizeof(SmallSmem) <= 4096, "SmallSmem too large");
 //   sum     = sum_j 448 * 2^(y_j - ymax) / k_scale_j     -> the reference's cur_sum / p_scale (:426,434)
 // The reference then rescales O and L by exp2(m_old - m_new) * p_old / p_new every page (:442-455); with O in TMEM that
 // is a 128 KB read-modify-write per page.  Here O and L live under a per-row reference exponent R that only moves when
-// a page's ymax exceeds it (then R = ymax + 4 and O is rescaled once), and the page's weight w = 2^(ymax - R) <= 1
+// a page's ymax exceeds it (then R = ymax + kRefHeadroom and O is rescaled once), and the page's weight w = 2^(ymax - R) <= 1
 // multiplies the codes instead: code_j * w as an e4m3 pair hi + lo, 8 significant bits -- the result differs from the
 // page-wise recurrence by ~1e-3 (rounding of w*code, fp32 summation order), not by the 2^-4 noise of a different e4m3
 // grid.  Under SwapAB P is the B operand and HB is small, so hi and lo ride in ONE product: B = [P_hi | P_lo] with

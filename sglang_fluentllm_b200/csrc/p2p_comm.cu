@@ -186,6 +186,51 @@ __global__ void __launch_bounds__(kThreads) all_reduce_kernel(const __grid_const
   finish_call(p, rank, epoch);
 }
 
+// All-reduce through the switch (NVLS): `mc` is a multicast address that maps the same symmetric buffer on every rank.
+// Rank r asks the switch for the sum of slice r over all ranks (multimem.ld_reduce: one response per 16 bytes instead of
+// one per rank) and broadcasts it back into every rank's buffer (multimem.st); after a second meeting every rank copies
+// the result out of its own buffer.  Per rank 2 / w of the message crosses its link.
+__device__ __forceinline__ uint4 multimem_ld_reduce_bf16(const uint4* mc) {
+  uint4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.acc::f32.v4.bf16x2 {%0, %1, %2, %3}, [%4];"
+               : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+               : "l"(mc)
+               : "memory");
+  return v;
+}
+__device__ __forceinline__ void multimem_st_bf16(uint4* mc, const uint4& v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.bf16x2 [%0], {%1, %2, %3, %4};" ::"l"(mc), "r"(v.x), "r"(v.y), "r"(v.z),
+               "r"(v.w)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(kThreads) all_reduce_nvls_kernel(const __grid_constant__ Peers p, int rank, int world,
+                                                                   uint4* __restrict__ mc, uint4* __restrict__ local,
+                                                                   const uint4* __restrict__ in, int64_t units,
+                                                                   uint4* __restrict__ out) {
+  const int epoch = call_epoch(p, rank);
+  const int64_t base = ((epoch / kMeets) & 1) * p.half_units;
+  const int64_t stride = (int64_t)gridDim.x * kThreads;
+  copy_range(in, local + base, first_unit(0), units, stride);
+  meet_peers(p, rank, world, 0, epoch);
+  {
+    const int64_t per = (units + world - 1) / world;
+    const int64_t lo = rank * per, hi = min(lo + per, units);
+    for (int64_t u = first_unit(lo); u < hi; u += kUnroll * stride) {
+      uint4 v[kUnroll];
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (u + j * stride < hi) v[j] = multimem_ld_reduce_bf16(mc + base + u + j * stride);
+#pragma unroll
+      for (int j = 0; j < kUnroll; ++j)
+        if (u + j * stride < hi) multimem_st_bf16(mc + base + u + j * stride, v[j]);
+    }
+  }
+  meet_peers(p, rank, world, 1, epoch);
+  copy_range(local + base, out, first_unit(0), units, stride);
+  finish_call(p, rank, epoch);
+}
+
 // Uneven reduce-scatter over rows: out[rows of this rank] = sum over ranks of their operands' same rows.
 __global__ void __launch_bounds__(kThreads) reduce_scatter_kernel(const __grid_constant__ Peers p, int rank, int world,
                                                                   const uint4* __restrict__ in, int64_t units_per_row,
@@ -301,9 +346,28 @@ int b200_comm_all_reduce_bf16(void* const* bufs, void* const* flags, size_t buf_
              (long long)numel * 2, buf_bytes);
   // two ranks: one pass over the peer's operand; more: reduce a slice each, then collect
   static const int force = getenv("B200_COMM_ONE_SHOT") ? atoi(getenv("B200_COMM_ONE_SHOT")) : -1;
-  const int one_shot = force >= 0 ? force : (world <= 2);
+  // measured on 8 GPUs: one pass 36 us, two-shot 41-47 us for 1.8 MB (a meeting costs more than the extra traffic)
+  const int one_shot = force >= 0 ? force : ((int64_t)(world - 1) * numel * 2 <= (16ll << 20));
   all_reduce_kernel<<<pick_blocks(one_shot ? units : (units + world - 1) / world, blocks), kThreads, 0, (cudaStream_t)stream>>>(
       p, rank, world, (const uint4*)in, units, (uint4*)out, one_shot);
+  B200_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int b200_comm_all_reduce_nvls_bf16(void* multicast_ptr, void* local_ptr, void* const* flags, size_t buf_bytes, int rank,
+                                   int world, const void* in, int64_t numel, void* out, int blocks, void* stream) {
+  Peers p;
+  void* none[kMaxWorld] = {};
+  for (int r = 0; r < world && r < kMaxWorld; ++r) none[r] = local_ptr;  // (the peers' buffers are reached through the switch)
+  if (fill_peers(p, none, flags, buf_bytes, rank, world, nullptr)) return 1;
+  B200_CHECK(multicast_ptr && local_ptr && ((uintptr_t)multicast_ptr & 15) == 0, "comm_all_reduce_nvls: no multicast mapping");
+  B200_CHECK(in && out && numel > 0 && numel % 8 == 0 && ((uintptr_t)out & 15) == 0 && ((uintptr_t)in & 15) == 0,
+             "comm_all_reduce_nvls: numel %lld must be a positive multiple of 8, in / out 16-byte aligned", (long long)numel);
+  const int64_t units = numel / 8;
+  B200_CHECK(units <= p.half_units, "comm_all_reduce_nvls: %lld bytes do not fit half of the %zu-byte symmetric buffer",
+             (long long)numel * 2, buf_bytes);
+  all_reduce_nvls_kernel<<<pick_blocks(units, blocks), kThreads, 0, (cudaStream_t)stream>>>(
+      p, rank, world, (uint4*)multicast_ptr, (uint4*)local_ptr, (const uint4*)in, units, (uint4*)out);
   B200_CUDA(cudaGetLastError());
   return 0;
 }

@@ -88,6 +88,8 @@ def enable_p2p_all_reduce(group, device, max_bytes: int):
     global _p2p
     from . import comm
     _p2p = comm.P2PGroup(group if group is not None else dist.group.WORLD, device, max_bytes)
+    if _p2p.world > 2:
+        _p2p.enable_nvls()  # in-switch reduction where the box has it (falls back to peer loads, reason in nvls_error)
     return _p2p
 
 
