@@ -13,7 +13,8 @@ q = torch.randn(b, 1, h, 576, dtype=torch.bfloat16, device=dev)
 qn, qs, qr = fm.quantize_ckv_per_token_head(q, 512)
 bt = (torch.randperm(n_pages - 1)[: b * pp].reshape(b, pp) + 1).to(torch.int32).to(dev)
 sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
-meta, ns = fm.get_mla_metadata(sl, h, 1)
+meta, ns = fm.get_mla_metadata(sl, h, 1, fixed_overhead_blocks=fm.tuned_overhead_blocks(h))  # the backend's schedule
 for _ in range(4):
-    fm.flash_mla_ckv_fp8_per_token(qn, qr, kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), qs, ks.view(n_pages, 64, 1, 1), bt, sl, 512, meta, ns)
+    fm.flash_mla_ckv_fp8_per_token(qn, qr, kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), qs, ks.view(n_pages, 64, 1, 1), bt, sl, 512, meta, ns,
+                                   softmax_scale=192 ** -0.5)  # the model's scale (logit spread 2.5 bits)
 torch.cuda.synchronize()
