@@ -633,20 +633,26 @@ def cpu_baseline(args, budget_s=20.0):
     matmul), ported in oracle/native_cpu.py, on a bounded sample: `sample_b` requests of one layer."""
     import torch
 
-    from oracle import native_cpu
+    from oracle import native_cpu, ref_import
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
+    # the reference's own functions where /root/reference exists (the build container), their port elsewhere (GPU box)
+    ref = ref_import.reference_cpu_path()
+    decode, matmul, quant = ref if ref is not None else (None, None, None)
     sample_b = min(32, args.batch)  # at least a quarter of the batch; doubled while the budget allows
-    t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1)
+    t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1, decode=decode)
     while t_attn * 4 < budget_s / 2 and sample_b < args.batch:
         sample_b = min(2 * sample_b, args.batch)
-        t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1)
-    t_gemm = native_cpu.time_block_fp8_linears(min(args.batch, 32), args.heads, repeats=1) * (args.batch / min(args.batch, 32))
+        t_attn = native_cpu.time_decode_attention(sample_b, args.seq, args.heads, repeats=1, decode=decode)
+    t_gemm = native_cpu.time_block_fp8_linears(min(args.batch, 32), args.heads, repeats=1, matmul=matmul,
+                                               quant=quant) * (args.batch / min(args.batch, 32))
     per_layer = t_attn * (args.batch / sample_b) + t_gemm
     value = args.batch / (per_layer * args.layers)
-    return {"value": round(value, 3), "unit": "tokens/s", "cores": cores, "kind": "port",
-            "sample": "1 layer: torch-native SDPA decode for %d of %d requests (seq %d, %d heads, bf16 pool) + native "
+    return {"value": round(value, 3), "unit": "tokens/s", "cores": cores, "kind": "reference" if ref is not None else "port",
+            "sample": "1 layer: torch-native SDPA decode (%s) for %d of %d requests (seq %d, %d heads, bf16 pool) + native "
                       "block-FP8 matmuls for %d rows; scaled to %d requests x %d layers" % (
+                          "TorchNativeAttnBackend._run_sdpa_forward_decode, the reference's own source"
+                          if ref is not None else "port of TorchNativeAttnBackend._run_sdpa_forward_decode",
                           sample_b, args.batch, args.seq, args.heads, min(args.batch, 32), args.batch, args.layers)}
 
 

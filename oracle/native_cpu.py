@@ -9,7 +9,8 @@ ONLY -- never on the product path).
   * block-FP8 linear: native_w8a8_block_fp8_matmul (python/sglang/test/test_block_fp8.py:89-141) with
     native_per_token_group_quant_fp8 (:15-40).
 The reference package itself is not importable without stubs, and /root/reference does not exist on
-the GPU box, so this is a port ("kind": "port" in bench.py).
+the GPU box, so there this port is what is timed ("kind": "port" in bench.py); where the tree exists, bench.py times the
+reference's own functions through oracle/ref_import.py ("kind": "reference") with the same driver below.
 """
 from __future__ import annotations
 
@@ -74,8 +75,10 @@ def native_w8a8_block_fp8_matmul(A, B, As, Bs, block_size=(128, 128), output_dty
     return C.to(output_dtype)
 
 
-def time_decode_attention(b, seq, heads, repeats=2):
-    """Seconds for one layer of decode attention over `b` requests (median of `repeats` after one warm-up)."""
+def time_decode_attention(b, seq, heads, repeats=2, decode=None):
+    """Seconds for one layer of decode attention over `b` requests (median of `repeats` after one warm-up).  `decode`:
+    the loop to time (default: the port above; bench.py passes the reference's own method where it can import it)."""
+    decode = decode or run_sdpa_forward_decode
     g = torch.Generator().manual_seed(0)
     total = b * seq
     k_cache = torch.randn(total + 64, 1, 576, dtype=torch.bfloat16, generator=g)
@@ -88,14 +91,16 @@ def time_decode_attention(b, seq, heads, repeats=2):
     ts = []
     for i in range(repeats + 1):
         t0 = time.perf_counter()
-        run_sdpa_forward_decode(q, out, k_cache, v_cache, req_to_token, pool_idx, seq_lens, scaling=576 ** -0.5,
-                                enable_gqa=True)
+        decode(q, out, k_cache, v_cache, req_to_token, pool_idx, seq_lens, scaling=576 ** -0.5, enable_gqa=True)
         ts.append(time.perf_counter() - t0)
     return sorted(ts[1:])[len(ts[1:]) // 2]
 
 
-def time_block_fp8_linears(m, heads, repeats=1):
-    """Seconds for the three block-FP8 linears of one attention block (qkv_a, q_b, o_proj shapes) on `m` rows."""
+def time_block_fp8_linears(m, heads, repeats=1, matmul=None, quant=None):
+    """Seconds for the three block-FP8 linears of one attention block (qkv_a, q_b, o_proj shapes) on `m` rows.
+    `matmul` / `quant`: the functions to time (default: the ports above)."""
+    matmul = matmul or native_w8a8_block_fp8_matmul
+    quant = quant or native_per_token_group_quant_fp8
     g = torch.Generator().manual_seed(1)
     shapes = [(1536 + 576, 7168), (heads * 192, 1536), (7168, heads * 128)]
     ws = []
@@ -108,7 +113,7 @@ def time_block_fp8_linears(m, heads, repeats=1):
         t0 = time.perf_counter()
         for (n, k), (wq, w_s) in zip(shapes, ws):
             x = torch.randn(m, k, dtype=torch.bfloat16, generator=g)
-            xq, xs = native_per_token_group_quant_fp8(x, 128)
-            native_w8a8_block_fp8_matmul(xq, wq, xs, w_s)
+            xq, xs = quant(x, 128)
+            matmul(xq, wq, xs, w_s, [128, 128], torch.bfloat16)
         ts.append(time.perf_counter() - t0)
     return sorted(ts[1:])[len(ts[1:]) // 2]

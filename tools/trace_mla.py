@@ -21,10 +21,10 @@ if os.environ.get("SHARED_PAGES"):  # diagnostic: every request walks the same f
     n_sh = int(os.environ["SHARED_PAGES"])
     bt = ((torch.arange(b * pp).reshape(b, pp) % n_sh) + 1).to(torch.int32).to(dev)
 sl = torch.full((b,), seq, dtype=torch.int32, device=dev)
-meta, ns = fm.get_mla_metadata(sl, h, 1)
+meta, ns = fm.get_mla_metadata(sl, h, 1, fixed_overhead_blocks=fm.tuned_overhead_blocks(h))
 outs = []
 for _ in range(5):
-    o, l = fm.flash_mla_ckv_fp8_per_token(qn, qr, kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), qs, ks.view(n_pages, 64, 1, 1), bt, sl, 512, meta, ns)
+    o, l = fm.flash_mla_ckv_fp8_per_token(qn, qr, kl.view(n_pages, 64, 1, 512), kr.view(n_pages, 64, 1, 64), qs, ks.view(n_pages, 64, 1, 1), bt, sl, 512, meta, ns, softmax_scale=192 ** -0.5)
     torch.cuda.synchronize()
     outs.append((o.float().cpu().numpy(), l.cpu().numpy()))
 for i in range(1, len(outs)):
