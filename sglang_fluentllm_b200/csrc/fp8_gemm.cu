@@ -210,11 +210,11 @@ __global__ void __launch_bounds__(64 + 128 * (BT / CPT), 1) fp8_gemm_kernel(cons
 // ------------------------------------------------------------------------------------------------------------------
 template <int BN>
 struct GemmTokMSmem {
-  static constexpr int kStages = BN == 256 ? 4 : (BN == 128 ? 6 : 8);
+  static constexpr int kStages = BN == 256 ? 4 : (BN == 192 ? 5 : (BN == 128 ? 6 : 8));
   static constexpr int kABytes = 128 * 128;   // token tile
   static constexpr int kWBytes = BN * 128;    // weight tile
   static constexpr int kStageBytes = kABytes + kWBytes + 1024;  // + 128 activation scales
-  static constexpr int kWBlocks = BN > 128 ? BN / 128 : 1;      // 128-row weight scale blocks a tile touches
+  static constexpr int kWBlocks = BN > 128 ? (BN + 127) / 128 : 1;  // 128-row weight scale blocks a tile touches
   static constexpr int kOffWScale = kStages * kStageBytes + 1024;  // [kWBlocks][<= 128 k-blocks] floats
   static constexpr int kTotal = kOffWScale + 1024;
   static_assert(kStages * kStageBytes >= 128 * BN * 4, "the epilogue stages the fp32 tile in the pipeline buffers");
@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
   using S = GemmTokMSmem<BN>;
   constexpr int kStages = S::kStages;
   constexpr int CPT = 64, kPromo = 2 * BN;  // 4 lane quadrants x BN / 64 column slices
-  constexpr uint32_t kTmemCols = 2 * BN;
+  constexpr uint32_t kTmemCols = 2 * BN > 256 ? 512 : 2 * BN;  // (an allocation is a power of two)
   constexpr int kWBlocks = S::kWBlocks;
 
   extern __shared__ uint8_t smem_raw[];
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
       }
       named_bar_sync(1, kPromo);
     }
-    const float* my_wscale = s_wscale + (cb / 128) * num_kb;
+    const float* my_wscale = s_wscale + (nblk - n0 / 128) * num_kb;  // (a 192-row tile may start in the middle of a block)
     float2 acc[CPT / 2];
 #pragma unroll
     for (int j = 0; j < CPT / 2; ++j) acc[j] = make_float2(0.f, 0.f);
@@ -405,6 +405,7 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
     named_bar_sync(1, kPromo);
     const int pw = warp - 2;                           // promotion warp
     constexpr int kRowsPerWarp = 128 / (kPromo / 32);  // rows each warp writes out
+    constexpr bool kEvenRows = 128 % (kPromo / 32) == 0;
     if (p.splits == 1) {
       constexpr int kChunks = BN / 8;  // 16-byte chunks per bf16 row
       uint8_t* srow = smem + row * (BN * 2);
@@ -420,9 +421,10 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
       }
       named_bar_sync(1, kPromo);
 #pragma unroll
-      for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
-        const int idx = it * 32 + lane;
-        const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
+      for (int it = 0; it < 128 * kChunks / kPromo; ++it) {
+        // BN = 192: twelve promotion warps do not divide the 128 rows; chunks are dealt round-robin over all of them
+        const int idx = kEvenRows ? it * 32 + lane : it * kPromo + (tid - 64);
+        const int r = kEvenRows ? pw * kRowsPerWarp + idx / kChunks : idx / kChunks, c = idx % kChunks;
         const uint4 v = *reinterpret_cast<const uint4*>(smem + r * (BN * 2) + ((c ^ (r & 7)) << 4));
         if (m0 + r >= m_begin && m0 + r < m_end && n0 + c * 8 < p.n)
           *reinterpret_cast<uint4*>(p.out + (int64_t)(m0 + r) * p.n + n0 + c * 8) = v;
@@ -438,9 +440,9 @@ __global__ void __launch_bounds__(64 + 2 * BN, 1) fp8_gemm_tokm_kernel(const __g
         named_bar_sync(1, kPromo);
         float* slab = p.ws + ((int64_t)blockIdx.z * p.m + m0) * p.n + n0;
 #pragma unroll
-        for (int it = 0; it < kRowsPerWarp * kChunks / 32; ++it) {
-          const int idx = it * 32 + lane;
-          const int r = pw * kRowsPerWarp + idx / kChunks, c = idx % kChunks;
+        for (int it = 0; it < 128 * kChunks / kPromo; ++it) {
+          const int idx = kEvenRows ? it * 32 + lane : it * kPromo + (tid - 64);
+          const int r = kEvenRows ? pw * kRowsPerWarp + idx / kChunks : idx / kChunks, c = idx % kChunks;
           const float4 v = *reinterpret_cast<const float4*>(smem + r * (BN * 4) + ((c ^ (r & 7)) << 4));
           if (m0 + r < p.m && n0 + c * 4 < p.n) *reinterpret_cast<float4*>(slab + (int64_t)r * p.n + c * 4) = v;
         }
@@ -624,8 +626,11 @@ static GemmConfig pick_config(int m, int n, int k, int sm_count) {
   const int num_kb = k / 128;
   GemmConfig best = {256, 1};
   double best_cost = 1e30;
-  for (int bn = 256; bn >= 64; bn >>= 1) {
+  static const int kBn[4] = {256, 192, 128, 64};
+  for (int bi = 0; bi < 4; ++bi) {
+    const int bn = kBn[bi];
     if (force_bn && bn != force_bn) continue;
+    if (bn == 192 && n % 192 != 0) continue;  // 192-row tiles only where they tile n exactly (q_b_proj: 24576 = 128 x 192)
     const int tiles = ((n + bn - 1) / bn) * ((m + 127) / 128);
     int splits = force_splits ? force_splits : splits_for(tiles, k, sm_count);
     if (splits > num_kb) splits = num_kb;
@@ -700,12 +705,14 @@ int b200_fp8_gemm_nt(const void* a, const float* a_scales, int64_t a_scale_strid
     rc = -1;
     if (prm.splits >= 2 && prm.splits <= 8 && !no_kc) {
       if (gc.bn == 256) rc = launch_gemm_tokm<256, true>(prm, use_pdl, st);
+      else if (gc.bn == 192) rc = launch_gemm_tokm<192, true>(prm, use_pdl, st);
       else if (gc.bn == 128) rc = launch_gemm_tokm<128, true>(prm, use_pdl, st);
       else rc = launch_gemm_tokm<64, true>(prm, use_pdl, st);
       reduced_in_cluster = rc == 0;
     }
     if (rc == -1) {  // no split, more than 8 splits, or the clusters do not all fit at once
       if (gc.bn == 256) rc = launch_gemm_tokm<256, false>(prm, use_pdl, st);
+      else if (gc.bn == 192) rc = launch_gemm_tokm<192, false>(prm, use_pdl, st);
       else if (gc.bn == 128) rc = launch_gemm_tokm<128, false>(prm, use_pdl, st);
       else rc = launch_gemm_tokm<64, false>(prm, use_pdl, st);
     }

@@ -175,7 +175,10 @@ def test_act_quant_golden(mods, golden_dir):
 
 
 GEMM_SHAPES = [(16, 128, 128), (1, 64, 128), (32, 256, 512), (100, 192, 256), (300, 256, 384), (128, 2112, 7168),
-               (128, 7168, 2048), (64, 4096, 7168), (7, 2112, 7168), (128, 24576, 1536)]
+               (128, 7168, 2048), (64, 4096, 7168), (7, 2112, 7168), (128, 24576, 1536),
+               # n a multiple of 192: the 192-row weight tile (tiles that start in the middle of a 128-row scale block),
+               # with and without split-K (`B200_GEMM_BN=192 pytest -k gemm` forces it on every shape it fits)
+               (128, 3072, 1536), (200, 768, 2048), (130, 1920, 7168), (128, 384, 16384)]
 
 
 @pytest.mark.parametrize("m,n,k", GEMM_SHAPES)
