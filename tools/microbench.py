@@ -128,6 +128,9 @@ def bench_gemm(m, n, k, n_rot=None):
 
 
 what = sys.argv[1:] or ["mla", "gemm"]
+if what and what[0] == "gemm1":  # one shape: python tools/microbench.py gemm1 M N K  (with B200_GEMM_BN / B200_GEMM_SPLITS)
+    bench_gemm(int(what[1]), int(what[2]), int(what[3]))
+    what = []
 if "mla128" in what:
     bench_mla(128, 4096, 128)
     bench_mla(64, 4096, 128, s_q=2)
