@@ -14,6 +14,12 @@ namespace b200 {
 static constexpr int kTileTokens = 128;
 static constexpr int kPage = B200_MLA_PAGE_SIZE;
 static constexpr float kMInit = -1e30f;                       // splitkv_mla.cu:16 (MAX_INIT_VAL_SM)
+// Batches smaller than the number of scheduler parts (long sequences cut over dozens of parts): a request cut into
+// more than this many pieces keeps the fp32 partials + combine path -- a single CTA merging them would serialise what
+// the combine kernel spreads over the device (measured at b = 1, seq 32K: 79 us against 43.5 us).  Batches of at least
+// one request per part (where a request is in two, rarely three pieces) merge everything in the kernel and launch no
+// combine at all (an empty combine launch costs 3.5 us at the metric shape).
+static constexpr int kMaxKernelMerge = 3;
 static constexpr float kLog2Fp8Max = 8.807354922057604f;      // log2(448): a page's largest P' maps to the e4m3 maximum (splitkv_mla.cu:433)
 // log2 of the growth a moved row reference leaves before the next move.  A move drains the P.V pipeline and rescales O
 // in TMEM (2-3 tiles' worth of time), and with attention logits of spread sigma = 2.5 (log2 units: DeepSeek's 192^-0.5
@@ -37,6 +43,7 @@ struct MlaParams {
   float* lse_accum;
   int* merge_state;  // pair kernel: per (request, q block, CTA) {ticket, done} counters, zero between launches; null =
                      // split requests are left to the combine kernel
+  int merge_limit;   // pair kernel: requests cut into more pieces than this are left to the combine kernel
   int batch, s_q, h_q, M;
   float scale_log2;
   int is_causal;
@@ -95,3 +102,7 @@ __device__ __forceinline__ Segment make_segment(const MlaParams& p, int batch_id
 int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream_t stream);
 
 }  // namespace b200
+
+// Split-KV combine launch (small_kernels.cu); requests cut into at most `merged_up_to` pieces are skipped.
+int launch_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
+                       int batch, int s_q, int h_q, int merged_up_to, int use_pdl, void* stream);

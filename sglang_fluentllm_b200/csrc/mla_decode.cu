@@ -653,8 +653,14 @@ int b200_mla_decode_ckv_fp8_per_token(const void* q_nope, const void* q_rope, co
     // parts cost more than the combine launch, measured)
     const bool one_wave = 2 * ((M + 127) / 128) * num_sm_parts <= device_sm_count();
     prm.merge_state = (no_merge || !one_wave) ? nullptr : reinterpret_cast<int*>(merge_state);
+    // at least one request per part: everything is merged in the kernel, no combine launch (mla_common.cuh)
+    const bool all_in_kernel = batch >= num_sm_parts;
+    prm.merge_limit = all_in_kernel ? 0x7fffffff : kMaxKernelMerge;
     rc = launch_mla_pair(prm, num_sm_parts, use_pdl != 0 && pdl_default(), (cudaStream_t)stream);
-    if (rc || prm.merge_state) return rc;
+    if (rc || (prm.merge_state && all_in_kernel)) return rc;
+    if (prm.merge_state)  // what is left for the combine kernel: requests in more than kMaxKernelMerge pieces
+      return launch_mla_combine(prm.o_accum, prm.lse_accum, num_splits, out, lse, batch, s_q, h_q, kMaxKernelMerge, use_pdl,
+                                stream);
   } else if (HB == 16) rc = launch_mla<16, 8>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   else rc = launch_mla<32, 16>(prm, q_blocks, num_sm_parts, (cudaStream_t)stream);
   if (rc) return rc;

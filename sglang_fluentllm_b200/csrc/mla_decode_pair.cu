@@ -654,6 +654,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
     // per-request scalars, fetched one request ahead (three dependent L2 round trips otherwise sit between a request's
     // epilogue and the next request's first tile)
     int cur_seqlen = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);
+    const int ns_end = __ldg(p.num_splits + end_idx + 1);  // end of the last request's split range (merge decision)
     float cur_qs = row_valid ? __ldg(p.q_scale + (int64_t)begin_idx * p.M + grow) : 0.f;
     if (grp == 0 && page == 0) sm.st_ref[row] = kMInit;
     named_bar_sync(1, kSmThreads);
@@ -973,7 +974,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       // launch): every part takes a ticket here; all but the last write their fp32 partial and count themselves done,
       // the last one waits for that count (its peers are already in their epilogues), merges in split order and
       // leaves both counters at zero for the next launch.
-      const bool mrg = !sg.no_split && p.merge_state != nullptr;
+      int sp0 = 0, n_sp = 1;
+      if (!sg.no_split) {
+        sp0 = sg.split_idx - (b == begin_idx ? begin_n_split : 0);
+        n_sp = (b < end_idx ? cur_ns : ns_end) - sp0;
+      }
+      // (small batches: requests in more than kMaxKernelMerge pieces are left to the combine kernel, see mla_common.cuh)
+      const bool mrg = !sg.no_split && p.merge_state != nullptr && n_sp <= p.merge_limit;
       int* mstate = nullptr;
       if (mrg) {
         mstate = p.merge_state + ((((int64_t)b * gridDim.y + blockIdx.y) * 2 + rank) << 1);
@@ -981,11 +988,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       }
       named_bar_sync(1, kSmThreads);
       const bool had_tiles = sg.n_tiles > 0;
-      int sp0 = 0, n_sp = 1;
       bool i_merge = false;
       if (mrg) {
-        sp0 = sg.split_idx - (b == begin_idx ? begin_n_split : 0);
-        n_sp = (b < end_idx ? cur_ns : __ldg(p.num_splits + b + 1)) - sp0;
         i_merge = sm.merge_ticket == n_sp - 1;
         if (i_merge) {
           // the other parts' partials were written long ago (a request's later parts run first) and have left L2 since:

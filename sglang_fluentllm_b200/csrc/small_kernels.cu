@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     mla_combine_kernel(const float* __restrict__ o_accum, const float* __restrict__ lse_accum,
                        const int32_t* __restrict__ num_splits_ptr, __nv_bfloat16* __restrict__ out,
-                       float* __restrict__ lse_out, int batch, int M, int h_q, int s_q) {
+                       float* __restrict__ lse_out, int batch, int M, int h_q, int s_q, int merged_up_to) {
   pdl_wait_prior_grid();
   const int b = blockIdx.x;
   const int row = blockIdx.y * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -297,7 +297,9 @@ __global__ void __launch_bounds__(256)
   if (row >= M) return;
   const int s0 = num_splits_ptr[b], s1 = num_splits_ptr[b + 1];
   const int n = s1 - s0;
-  if (n <= 1) return;  // the decode kernel wrote the final result itself
+  // the decode kernel wrote the final result itself: an uncut request, or (pair kernel with a merge-state buffer) one
+  // cut into at most `merged_up_to` pieces, which the part that finished last has merged
+  if (n <= 1 || n <= merged_up_to) return;
   float max_lse = -INFINITY;
   for (int i = lane; i < n; i += 32) max_lse = fmaxf(max_lse, lse_accum[(size_t)(s0 + i) * M + row]);
   max_lse = warp_max_f32(max_lse);
@@ -476,6 +478,28 @@ __global__ void __launch_bounds__(256)
 
 using namespace b200;
 
+// Split-KV combine launch; requests cut into at most `merged_up_to` pieces are skipped (merged by the decode kernel).
+int launch_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
+                       int batch, int s_q, int h_q, int merged_up_to, int use_pdl, void* stream) {
+  if (batch == 0) return 0;  // IDLE batch
+  B200_CHECK(o_accum && lse_accum && num_splits && out && lse, "combine: null pointer");
+  const int M = s_q * h_q;
+  const int warps = 8;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(batch, (M + warps - 1) / warps, 1);
+  cfg.blockDim = dim3(warps * 32, 1, 1);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl ? 1 : 0;
+  B200_CUDA(cudaLaunchKernelEx(&cfg, mla_combine_kernel, o_accum, lse_accum, num_splits, (__nv_bfloat16*)out, lse, batch,
+                               M, h_q, s_q, merged_up_to));
+  return 0;
+}
+
 extern "C" {
 
 const char* b200_last_error(void) { return get_last_error(); }
@@ -613,23 +637,7 @@ int b200_mla_dequantize_indexed(const void* k_lora_cache, const void* k_rope_cac
 
 int b200_mla_combine(const float* o_accum, const float* lse_accum, const int32_t* num_splits, void* out, float* lse,
                      int batch, int s_q, int h_q, int use_pdl, void* stream) {
-  if (batch == 0) return 0;  // IDLE batch
-  B200_CHECK(o_accum && lse_accum && num_splits && out && lse, "combine: null pointer");
-  const int M = s_q * h_q;
-  const int warps = 8;
-  cudaLaunchConfig_t cfg;
-  memset(&cfg, 0, sizeof(cfg));
-  cfg.gridDim = dim3(batch, (M + warps - 1) / warps, 1);
-  cfg.blockDim = dim3(warps * 32, 1, 1);
-  cfg.stream = (cudaStream_t)stream;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = use_pdl ? 1 : 0;
-  B200_CUDA(cudaLaunchKernelEx(&cfg, mla_combine_kernel, o_accum, lse_accum, num_splits, (__nv_bfloat16*)out, lse, batch,
-                               M, h_q, s_q));
-  return 0;
+  return launch_mla_combine(o_accum, lse_accum, num_splits, out, lse, batch, s_q, h_q, 0, use_pdl, stream);
 }
 
 int b200_act_quant_1x128(const void* x, int64_t m, int64_t k, void* q, float* scales, int64_t scale_stride, float eps,

@@ -49,7 +49,7 @@ int host_mla_combine(const float* o_accum, const float* lse_accum, const int32_t
                      int batch, int s_q, int h_q) {
   const int M = s_q * h_q;
   refshim::run_grid((unsigned)batch, 256, [&] {
-    mla_combine_kernel(o_accum, lse_accum, num_splits, reinterpret_cast<__nv_bfloat16*>(out), lse, batch, M, h_q, s_q);
+    mla_combine_kernel(o_accum, lse_accum, num_splits, reinterpret_cast<__nv_bfloat16*>(out), lse, batch, M, h_q, s_q, 0);
   }, (unsigned)((M + 7) / 8));
   return 0;
 }

@@ -350,6 +350,9 @@ def test_mla_pair_split_long_sequences(mods):
     (40, 128, 1, [700 + 37 * i for i in range(40)], False),  # most requests cut in two, some whole
     (3, 128, 2, [3000, 130, 1500], True),    # M = 256: two q blocks per request, causal border
     (5, 96, 1, [1, 64, 2000, 700, 5000], False),  # half-filled second CTA, a one-token request
+    # at least one request per scheduler part: everything is merged in the kernel, however many pieces (here one long
+    # request over dozens of parts among short ones); below that, pieces beyond three go to the combine kernel
+    (80, 128, 1, [20000] + [100 + 3 * i for i in range(79)], False),
 ])
 def test_mla_pair_in_kernel_merge_equals_combine(mods, b, h, s_q, seqlens, causal):
     """Requests cut over several scheduler parts: the pair kernel's own merge (the part that finishes last adds the
