@@ -99,10 +99,21 @@ constexpr int kTraceTiles = 64;
 constexpr int kTraceRoles = 5;
 __device__ unsigned long long g_trace[2 * kTraceRoles * kTraceTiles * 4];
 __device__ unsigned long long g_part_cycles[2 * 128 * 4];  // [part < 128][rank]{globaltimer ns at entry, at exit, clock64 at entry, at exit}
+// "Chaos" mode of the diagnostic instantiation (B200_MLA_TRACE bit 2): every trace site -- 20 of them over the producer,
+// the MMA issuers, the softmax passes, the hand-offs and the epilogue -- delays its warp by a pseudo-random 0-4 us, so
+// warps, groups and the two CTAs of a pair drift against each other by whole tiles.  The protocol must not care: the
+// results have to stay bit-identical (tests/test_gpu_parity.py::test_mla_pair_is_timing_independent).
+__device__ int g_chaos;
 // TR = false (the production instantiation) compiles every trace site out
 template <bool TR>
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
   if constexpr (TR) {
+    if (g_chaos) {  // (the same delay for the whole warp: the trace sites are warp-converged code in front of aligned barriers)
+      const uint32_t c = __shfl_sync(0xffffffffu, (uint32_t)clock64(), 0);
+      uint32_t h = c * 2654435761u ^ ((threadIdx.x >> 5) * 40503u + blockIdx.z * 9176u + role * 131u + ev * 31u + g);
+      h ^= h >> 13, h *= 0x5bd1e995u, h ^= h >> 15;
+      if ((h & 3u) == 0) __nanosleep((h >> 4) & 0xfffu);
+    }
     if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
   }
 }
@@ -420,8 +431,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       pre_cur = nxt_req, pre_nxt = nxt_req2, have_pre = bt_next != nullptr;
       ks_done = ks_next;
     }
-  } else if (TR && warp == 3 && rank == 1 && part == 0 && blockIdx.y == 0) {
-    // diagnostic: when the second V unit of each tile lands in the non-leader CTA
+  } else if (TR && (p.trace & 64) && warp == 3 && rank == 1 && part == 0 && blockIdx.y == 0) {
+    // diagnostic (B200_MLA_TRACE bit 6, tools/trace_mla.py; needs at least 40 tiles in part 0 -- a passive observer of
+    // barrier parities must not fall behind): when the second V unit of each tile lands in the non-leader CTA
     for (uint32_t g = 0; g < 40; ++g) {
       mbar_wait(&sm.v_land[(2 * g + 1) % kVUnits], ((2 * g + 1) / kVUnits) & 1);
       trace<TR>(lane == 0, rank, 0, g, 3);
@@ -450,6 +462,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       // streamed through L2 as K by this CTA or its peer
       auto load_v = [&](int t, uint32_t gt) {
         trace<TR>(tr, rank, 0, gt, 1);
+        B200_BEACON(1, gt);
         const int blk0 = sg.start_block + 2 * t;
         const int npages = min(2, sg.end_block - blk0);
         const int tok0 = bw.get(blk0) * kPage;
@@ -519,6 +532,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           mbar_wait(&sm.ks_full[g % kKsStages], (g / kKsStages) & 1);  // s_full then vouches for the k scales too
           mbar_wait_cluster(&sm.k_full[kst], (g / kKStages) & 1);
           trace<TR>(tr, rank, 1, g, 0);
+          B200_BEACON(2, g);
           tc_fence_after();
           const uint32_t stage = k_addr + kst * kKStageBytes;
           const uint32_t d = tmem + kColS + sb * 64;
@@ -546,6 +560,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           mbar_wait_cluster(&sm.p_full[pp], (g / kPPairs) & 1);  // P written in both CTAs
           if (t == 0 && seg > 0) mbar_wait_cluster(&sm.o_free, (seg - 1) & 1);
           trace<TR>(tr, rank, 1, g, 2);
+          B200_BEACON(3, g);
           tc_fence_after();
           const int tile_start = (sg.start_block + 2 * t) * kPage;
           const int nk = (min(kTileTokens, sg.valid_end - tile_start) + 31) / 32;
@@ -613,6 +628,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           mbar_wait(&sm.v_land[u0 % kVUnits], (u0 / kVUnits) & 1);
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u0 % kVUnits]);
           __syncwarp();
+          B200_BEACON(4, g);
           mbar_wait(&sm.p_relay[g % kPPairs], (g / kPPairs) & 1);
           if (elect_one()) {
             mbar_arrive_cluster(s_done_l[g % kSBufs]);
@@ -623,6 +639,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u1 % kVUnits]);
           __syncwarp();
         }
+        B200_BEACON(4, 1000 + seg);
         mbar_wait(&sm.o_relay, seg & 1);
         if (elect_one()) mbar_arrive_cluster(o_free_l);
         __syncwarp();
@@ -679,7 +696,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       uint32_t ver = 0xffffffffu;
       // bring this thread's view (rloc, lsum) up to the row's current reference
       auto sync_view = [&]() {
-        const uint32_t v_now = ld_shared_volatile_u32(&sm.version);
+        // (lane 0's reading for the whole warp: what the warp does next -- recompute or not, the warp-wide votes -- must
+        // not depend on one load instruction handing every lane the same value, e.g. under an instrumenting tool)
+        const uint32_t v_now = __shfl_sync(0xffffffffu, ld_shared_volatile_u32(&sm.version), 0);
         if (v_now != ver) {
           const float r_new = ld_shared_volatile_f32(&sm.st_ref[row]);
           lsum *= exp2f(rloc - r_new);
@@ -787,6 +806,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             __any_sync(0xffffffffu, p.is_causal || !row_valid || (tile_start + kTileTokens > sg.valid_end));
         const bool tr_w = tr && quad == 0;
         if (gtid == 0) sm.trig[grp][(n_mine + 1) % 3] = 0;
+        if (gtid == 0) B200_BEACON(5 + grp, g), B200_BEACON(8 + grp, 0), B200_BEACON(11, b);
         if (t <= 1) trace<TR>(tr_w, rank, 3, o_seg, 3);
         trace<TR>(tr_w, rank, 4, g, 3);
 
@@ -817,6 +837,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
                                      : pass_max(std::false_type{}, s_addr, ks_tile, lk_tile, tile_start);
         const bool live = ymax > -INFINITY;
         trace<TR>(tr_w, rank, 4, g, 0);
+        if (gtid == 0) B200_BEACON(8 + grp, 1);
         // the first tiles of a request always see a reference move (the first tile makes one): their weighted pass
         // waits for the predecessor's reference instead of running ahead of it (the max pass above did overlap it)
         // (the third tile only needs the first tile's reference, not its predecessor's publish: fin of tile g - 2 shares
@@ -850,15 +871,18 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         // request's first tile) the reference moves first ("slow path") and the pass runs under the new one.
         bool trigger = (t == 0), moved = false;
         for (;;) {
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 11 + 100 * g);
           if (!trigger) {
             sync_view();
           } else {
             // ---- slow path: move the reference R of the rows that outgrew it, rescale O and the running sums ----
             if (!fin_waited && g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);
+            if (gtid == 0) B200_BEACON(8 + grp, 2);
             fin_waited = true;
             sync_view();
             // the two page maxima of a row meet in the group's own (free) P pair: it is written by the pass below
             wait_p_free();
+            if (lane == 0) B200_BEACON(16 + (warp - 4), 21 + 100 * g);
             float* red1 = reinterpret_cast<float*>(s_p + (2 * grp) * kPBytes);  // [2 pages][64 rows]
             red1[page * 64 + row] = ymax;
             named_bar_sync(gbar, 128);
@@ -871,7 +895,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
               // last one issued: tile g is not published yet).  pv_done completes once per tile; tile g-1 is final
               // (fin), so P.V of tile g-2 was issued before it and this parity wait cannot alias an older phase... it
               // could still be two phases behind if P.V of g-2 has not retired: wait for that one first (s_free).
+              if (lane == 0) B200_BEACON(16 + (warp - 4), 22 + 100 * g);
               if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
+              if (lane == 0) B200_BEACON(16 + (warp - 4), 23 + 100 * g);
               mbar_wait(&sm.pv_done, (g - 1) & 1);
               tc_fence_after();
               if (__any_sync(0xffffffffu, fac != 1.f)) {
@@ -889,6 +915,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
               }
               lsum *= fac;
             }
+            if (lane == 0) B200_BEACON(16 + (warp - 4), 24 + 100 * g);
             rloc = r_new;
             if (page == 0) sm.st_ref[row] = r_new;
             tc_fence_before();
@@ -899,23 +926,29 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             // one runs its own (what orders them further -- P.V issue order, pv_done before a rescale -- does not hang
             // on fin).  The version store above is ordered before the arrival of gtid 0's warp by this barrier.
             named_bar_sync(gbar, 128);
+            if (lane == 0) B200_BEACON(16 + (warp - 4), 25 + 100 * g);
             if (lane == 0) mbar_arrive(&sm.fin[g & 1]);
             fin_arrived = true;
             moved = true;
           }
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 12 + 100 * g);
           const bool over = !moved && __any_sync(0xffffffffu, live && ymax > rloc);  // a row of this warp outgrew its reference
           if (!over) weighted_pass();
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 13 + 100 * g);
           if (moved) {
             lsum = fmaf(w32, acc, lsum);
             named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
             break;
           }
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 14 + 100 * g);
           if (!fin_waited) {
             if (g > 0) mbar_wait(&sm.fin[(g - 1) & 1], ((g - 1) >> 1) & 1);  // tile g-1 is final
             fin_waited = true;
           }
           trace<TR>(tr_w, rank, 4, g, 1);
-          if (ld_shared_volatile_u32(&sm.version) != ver) continue;  // computed under a reference that has moved
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 15 + 100 * g);
+          if (__shfl_sync(0xffffffffu, ld_shared_volatile_u32(&sm.version), 0) != ver) continue;  // computed under a reference that has moved
+          if (lane == 0) B200_BEACON(16 + (warp - 4), 16 + 100 * g);
           if (over && lane == 0) sm.trig[grp][n_mine % 3] = 1;
           named_bar_sync(gbar, 128);
           trigger = sm.trig[grp][n_mine % 3] != 0;
@@ -928,6 +961,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         if (lane == 0) mbar_arrive(&sm.ks_empty[kst]);
 
         trace<TR>(tr_w, rank, 2, g, 2);
+        if (gtid == 0) B200_BEACON(8 + grp, 3);
         // ---- publish P ----
         trace<TR>(tr_w, rank, 4, g, 2);
         // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
@@ -955,8 +989,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (!fin_arrived) mbar_arrive(&sm.fin[g & 1]);  // tile g is final: the next tile may publish
         }
         trace<TR>(tr_w, rank, 2, g, 3);
+        if (gtid == 0) B200_BEACON(8 + grp, 4);
       }
       g0 += (uint32_t)sg.n_tiles;
+      if (gtid == 0) B200_BEACON(8 + grp, 5), B200_BEACON(11, b);
 
       // every group has published its last tile: bring every thread's running sum to the request's final reference
       named_bar_sync(1, kSmThreads);
@@ -1014,6 +1050,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         float* mg = &sm.lred[(rq & 1) ^ 1][0][0];
         if (i_merge) {
           if (st_id == 0) {  // the other parts of this request are in their epilogues already: a short wait
+            B200_BEACON(12, 100 + n_sp);
             uint32_t spins = 0;
             while (ld_acquire_gpu_s32(mstate + 1) < n_sp - 1) {
               __nanosleep(64);
@@ -1042,6 +1079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           named_bar_sync(1, kSmThreads);
         }
         if (had_tiles) {  // (the merge's lse exchange above ran while the last P.V drained)
+          if (gtid == 0) B200_BEACON(8 + grp, 7);
           // (not pv_done: it completes once per tile and a parity wait from here could be phases behind)
           mbar_wait(&sm.o_ready, o_seg & 1);
           trace<TR>(tr_e, rank, 3, o_seg, 1);
@@ -1162,6 +1200,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           flush(oa, r8, sg.no_split, inv);
         }
         named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
+        if (gtid == 0) B200_BEACON(8 + grp, 8);
         if (had_tiles) trace<TR>(tr_e, rank, 3, o_seg, 2);
         if (row_valid && page == 0 && grp == 0) {
           const float lse2 = log2f(l) + (rloc - kLog2Fp8Max);  // L_true = L * 2^R / 448
@@ -1206,7 +1245,9 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream
   const int smem = pairk::kTotal + 1024;
   const int q_pairs = (prm.M + 127) / 128;
   const dim3 grid(2, q_pairs, num_sm_parts), block(128 + pairk::kSmThreads);
-  if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, knobs that break results
+  if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, bit 2 = random delays
+    const int chaos = (prm.trace & 4) ? 1 : 0;
+    B200_CUDA(cudaMemcpyToSymbolAsync(pairk::g_chaos, &chaos, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return launch_kernel(pairk::mla_decode_pair_kernel<true>, grid, block, smem, stream, pdl, prm);
   }
@@ -1227,3 +1268,21 @@ extern "C" int b200_mla_read_trace(unsigned long long* out, int n) {
   B200_CUDA(cudaMemcpyFromSymbol(out, b200::pairk::g_trace, sizeof(unsigned long long) * (n < total ? n : total)));
   return 0;
 }
+
+#ifdef B200_WAIT_DEBUG
+#include <cstddef>
+#include <cstdio>
+// debug build only: where the first abandoned wait is recorded (pinned host memory, 8 unsigned)
+extern "C" int b200_debug_set_record(unsigned* pinned) {
+  cudaMemcpyToSymbol(b200::g_wait_host, &pinned, sizeof(pinned));
+  unsigned z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  cudaMemcpyToSymbol(b200::g_wait_dead, z, sizeof(z));
+  using S = b200::pairk::Small;
+#define OFF(f) printf("  %-10s %zu\n", #f, offsetof(S, f))
+  OFF(k_full); OFF(k_empty); OFF(v_land); OFF(v_empty); OFF(ks_full); OFF(ks_empty); OFF(q_full); OFF(q_empty);
+  OFF(s_full); OFF(s_free); OFF(s_done); OFF(v_peer); OFF(p_full); OFF(p_free); OFF(pv_done); OFF(o_ready); OFF(o_free);
+  OFF(p_relay); OFF(o_relay); OFF(fin); OFF(tmem_base);
+  printf("  Small at dynamic shared offset %d (+ alignment), CTA window 0x1000000 per rank\n", b200::pairk::kOffSmall);
+  return 0;
+}
+#endif

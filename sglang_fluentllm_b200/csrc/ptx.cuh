@@ -8,6 +8,9 @@
 
 namespace b200 {
 
+#ifndef B200_WAIT_DEBUG
+#define B200_BEACON(i, v) ((void)0)
+#endif
 #ifndef B200_WAIT_SPIN_LIMIT
 #define B200_WAIT_SPIN_LIMIT (1u << 26)
 #endif
@@ -69,10 +72,35 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+#ifdef B200_WAIT_DEBUG
+// debug build only: the first wait that gives up is recorded (and abandoned, so that the kernel ends and the record can
+// be read) instead of trapping: {flag, shared address of the barrier, parity, thread, block x | y << 8 | z << 16}
+static __device__ unsigned g_wait_dead[8];
+static __device__ unsigned* g_wait_host;  // pinned host memory (survives the trap): set by b200_debug_set_record
+static __device__ unsigned g_beacon[160][2][32];  // progress beacons of the pair kernel's roles, per (part, rank)
+#define B200_BEACON(i, v) (g_beacon[blockIdx.z < 160 ? blockIdx.z : 159][blockIdx.x & 1][i] = (unsigned)(v))
+__device__ __forceinline__ void wait_gave_up(uint64_t* bar, uint32_t parity, unsigned kind) {
+  if (atomicCAS(&g_wait_dead[0], 0u, kind) == 0u && g_wait_host) {
+    volatile unsigned* h = g_wait_host;
+    h[1] = (unsigned)__cvta_generic_to_shared(bar), h[2] = parity, h[3] = threadIdx.x;
+    h[4] = blockIdx.x | (blockIdx.y << 8) | (blockIdx.z << 16);
+    for (int r = 0; r < 2; ++r)
+      for (int i = 0; i < 32; ++i) h[8 + r * 32 + i] = g_beacon[blockIdx.z < 160 ? blockIdx.z : 159][r][i];
+    h[0] = kind;
+    __threadfence_system();
+  }
+  __nanosleep(1000000);
+  __trap();
+}
+#endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
+#ifdef B200_WAIT_DEBUG
+    if (++spins > (1u << 18)) wait_gave_up(bar, parity, 1u);
+#else
     if (++spins > B200_WAIT_SPIN_LIMIT) __trap();
+#endif
   }
 }
 
@@ -359,7 +387,11 @@ __device__ __forceinline__ bool mbar_test_wait_cluster(uint64_t* bar, uint32_t p
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait_cluster(bar, parity)) {
+#ifdef B200_WAIT_DEBUG
+    if (++spins > (1u << 18)) wait_gave_up(bar, parity, 2u);
+#else
     if (++spins > B200_WAIT_SPIN_LIMIT) __trap();
+#endif
   }
 }
 // TMA load into this CTA's shared memory whose completion bytes are credited to a barrier in either CTA of the pair

@@ -14,6 +14,8 @@ Tolerances
 """
 import ctypes
 
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -375,6 +377,32 @@ def test_mla_pair_in_kernel_merge_equals_combine(mods, b, h, s_q, seqlens, causa
         d = (o_m.float() - o_c.float()).abs()
         assert float((d / o_c.float().abs().clamp_min(1e-3)).max()) < 2 ** -7, float(d.max())
         assert float((d > 0).float().mean()) < 1e-3  # and nearly everywhere the same bits
+
+
+def test_mla_pair_is_timing_independent(tmp_path):
+    """The CTA-pair kernel's hand-offs (row-reference moves, tile order, P / S / V rings, cluster relays, in-kernel
+    merge) must not depend on who is fast: the diagnostic instantiation with a pseudo-random 0-4 us delay at each of its
+    20 trace sites (B200_MLA_TRACE=5: warps, softmax groups and the two CTAs drift by whole tiles) has to reproduce the
+    production instantiation's output bit for bit, run after run, under both tile schedules."""
+    import subprocess
+    import sys
+    helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chaos_case.py")
+    outs = {}
+    for name, env_extra, repeats in (("plain", {}, 1), ("chaos", {"B200_MLA_TRACE": "5"}, 4)):
+        env = dict(os.environ)
+        env.pop("B200_MLA_TRACE", None)
+        env.update(env_extra)
+        path = str(tmp_path / (name + ".npz"))
+        r = subprocess.run([sys.executable, helper, path, str(repeats)], env=env, capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0, r.stderr[-3000:]
+        outs[name] = np.load(path)
+    plain, chaos = outs["plain"], outs["chaos"]
+    n = 0
+    for key in chaos.files:
+        base = key.rsplit("_", 1)[0] + "_0"
+        assert np.array_equal(chaos[key], plain[base]), "%s differs from the undisturbed run" % key
+        n += 1
+    assert n >= 5 * 2 * 4 * 2
 
 
 @pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])

@@ -1,7 +1,7 @@
-"""Pipeline timeline of the CTA-pair MLA kernel (part 0): run with B200_MLA_TRACE=1.
-Usage: B200_MLA_TRACE=1 python tools/trace_mla.py [H B SEQ]; also checks run-to-run determinism."""
+"""Pipeline timeline of the CTA-pair MLA kernel (part 0): run with B200_MLA_TRACE=65 (the default here).
+Usage: python tools/trace_mla.py [H B SEQ]; also checks run-to-run determinism."""
 import os, sys
-os.environ.setdefault("B200_MLA_TRACE", "1")
+os.environ.setdefault("B200_MLA_TRACE", "65")  # bit 0: timestamps, bit 6: the V-landing observer (big shapes only)
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import torch
