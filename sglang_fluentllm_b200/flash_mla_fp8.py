@@ -37,12 +37,24 @@ def tuned_overhead_blocks(num_q_rows: int) -> int:
     return 24 if num_q_rows > 64 else 12
 
 
+def tuned_num_sm_parts(num_q_rows: int) -> Optional[int]:
+    """Scheduler parts for the kernel that will run, where that differs from the reference's rule (one part per SM and
+    64 q rows, flash_api.cpp:41-43): 33-64 q rows run on CTA pairs, so half as many parts (one wave instead of two waves
+    of short parts); None = the reference's rule."""
+    if 32 < num_q_rows <= 64:
+        return max(1, int(_lib.lib().b200_sm_count()) // 2)
+    return None
+
+
 def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
-                     num_heads_k: int, fixed_overhead_blocks: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
+                     num_heads_k: int, fixed_overhead_blocks: Optional[int] = None,
+                     num_sm_parts: Optional[int] = None) -> Tuple[torch.Tensor, torch.Tensor]:
     """flash_mla_interface.py:8-23 -> csrc/flash_api.cpp:27-63.
     Returns (tile_scheduler_metadata int32 [num_sm_parts, 8], num_splits int32 [batch + 1]).
     ``fixed_overhead_blocks`` (extension): the scheduler's per-request fixed cost; default = the reference's constant,
-    i.e. the reference's schedule bit for bit; ``tuned_overhead_blocks(M)`` is what the B200 backend passes."""
+    i.e. the reference's schedule bit for bit; ``tuned_overhead_blocks(M)`` is what the B200 backend passes.
+    ``num_sm_parts`` (extension): number of parts; default = the reference's rule, ``tuned_num_sm_parts(M)`` is the
+    backend's."""
     _cuda(cache_seqlens, "seqlens_k")
     _require(cache_seqlens.dtype == torch.int32, "seqlens_k must have dtype int32")
     _require(cache_seqlens.is_contiguous(), "seqlens_k must be contiguous")
@@ -50,7 +62,8 @@ def get_mla_metadata(cache_seqlens: torch.Tensor, num_heads_per_head_k: int,
         fixed_overhead_blocks = REFERENCE_OVERHEAD_BLOCKS
     L = _lib.lib()
     with torch.cuda.device(cache_seqlens.device):
-        num_sm_parts = L.b200_mla_num_sm_parts(num_heads_per_head_k, num_heads_k, L.b200_sm_count())
+        if num_sm_parts is None:
+            num_sm_parts = L.b200_mla_num_sm_parts(num_heads_per_head_k, num_heads_k, L.b200_sm_count())
         _require(num_sm_parts > 0, "get_mla_metadata: no SM parts for num_heads_per_head_k=%d" % num_heads_per_head_k)
         batch = cache_seqlens.numel()
         meta = torch.empty(num_sm_parts, TILE_SCHEDULER_METADATA_SIZE, dtype=torch.int32, device=cache_seqlens.device)

@@ -404,7 +404,8 @@ class FlashMLABackend(AttentionBackend):
         # the scheduler's per-request cost tuned for this kernel (the reference's constant models its sm_90 kernel)
         mod = self.get_flash_mla_module(m)
         return mod.get_mla_metadata(lens.to(torch.int32).contiguous(), m, 1,
-                                    fixed_overhead_blocks=mod.tuned_overhead_blocks(m))
+                                    fixed_overhead_blocks=mod.tuned_overhead_blocks(m),
+                                    num_sm_parts=mod.tuned_num_sm_parts(m))
 
     def init_forward_metadata(self, forward_batch):
         """flashmla_backend.py:258-290 (other modes go to the base class, :289-290)."""
@@ -428,7 +429,7 @@ class FlashMLABackend(AttentionBackend):
         ones = torch.ones(max_bs, dtype=torch.int32, device=block_kv_indices.device)
         mod = self.get_flash_mla_module(m)
         self.cuda_graph_mla_metadata, self.cuda_graph_num_splits = mod.get_mla_metadata(
-            ones, m, 1, fixed_overhead_blocks=mod.tuned_overhead_blocks(m))
+            ones, m, 1, fixed_overhead_blocks=mod.tuned_overhead_blocks(m), num_sm_parts=mod.tuned_num_sm_parts(m))
         self.cuda_graph_kv_indices = block_kv_indices
         # the graph's own zeroed merge-state scratch (flash_mla_ckv_fp8_per_token merges cut requests in the kernel)
         self._merge_state = flash_mla_fp8.new_merge_state(max_bs, 1, m, block_kv_indices.device)

@@ -70,6 +70,15 @@ def test_metadata_bit_exact(mods, batch, hpk):
         om, ons = omla.get_mla_metadata(seqlens, hpk, 1, _lib.lib().b200_sm_count(), fixed_overhead_blocks=ovh)
         assert np.array_equal(meta.cpu().numpy()[:, :5], om[:, :5]), ovh
         assert np.array_equal(ns.cpu().numpy(), ons), ovh
+    # ... and with the number of parts the backend asks for (33-64 q rows run on CTA pairs: half as many parts): the
+    # oracle gets there through an SM count that gives the same number under the reference's rule
+    parts = fm.tuned_num_sm_parts(hpk)
+    if parts is not None:
+        ovh = fm.tuned_overhead_blocks(hpk)
+        meta, ns = fm.get_mla_metadata(torch.from_numpy(seqlens).to(DEV), hpk, 1, fixed_overhead_blocks=ovh, num_sm_parts=parts)
+        assert meta.shape[0] == parts
+        om, ons = omla.get_mla_metadata(seqlens, hpk, 1, parts * ((hpk + 63) // 64), fixed_overhead_blocks=ovh)
+        assert np.array_equal(meta.cpu().numpy()[:, :5], om[:, :5]) and np.array_equal(ns.cpu().numpy(), ons)
 
 
 def test_quantize_q_bit_exact(mods):
@@ -268,9 +277,9 @@ def make_case(fm, b, h, s_q, seqlens, seed=0, shuffle=True, nan_pad=True):
                 ks=ks.view(n_pages, 64, 1, 1), bt=block_table, sl=seqlens)
 
 
-def run_mla(fm, c, h, s_q, causal, overhead=None):
+def run_mla(fm, c, h, s_q, causal, overhead=None, parts=None):
     sl = c["sl"].to(DEV)
-    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1, fixed_overhead_blocks=overhead)
+    meta, ns = fm.get_mla_metadata(sl, s_q * h, 1, fixed_overhead_blocks=overhead, num_sm_parts=parts)
     out, lse = fm.flash_mla_ckv_fp8_per_token(c["qn"], c["qr"], c["kl"], c["kr"], c["qs"], c["ks"], c["bt"].to(DEV), sl,
                                               512, meta, ns, causal=causal)
     torch.cuda.synchronize()
@@ -306,8 +315,9 @@ def test_mla_decode_vs_oracles(mods, name, b, h, s_q, seqlens, causal, schedule)
     for (tuned_overhead_blocks): the faithful oracle follows whichever metadata it is given."""
     fm = mods[1]
     c = make_case(fm, b, h, s_q, seqlens)
-    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, causal,
-                                       overhead=None if schedule == "reference" else fm.tuned_overhead_blocks(h * s_q))
+    tuned = schedule != "reference"
+    out, lse, args, meta, ns = run_mla(fm, c, h, s_q, causal, overhead=fm.tuned_overhead_blocks(h * s_q) if tuned else None,
+                                       parts=fm.tuned_num_sm_parts(h * s_q) if tuned else None)
     assert not np.isnan(out).any(), "NaN leaked from the poisoned padding rows"
     so, sl = omla.flash_mla_ckv_fp8_semantic(*args, causal=causal)
     fo, fl = omla.flash_mla_ckv_fp8_per_token(*args, meta, ns, causal=causal)
@@ -402,7 +412,7 @@ def test_mla_pair_is_timing_independent(tmp_path):
         base = key.rsplit("_", 1)[0] + "_0"
         assert np.array_equal(chaos[key], plain[base]), "%s differs from the undisturbed run" % key
         n += 1
-    assert n >= 5 * 2 * 4 * 2
+    assert n >= 6 * 2 * 4 * 2
 
 
 @pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])

@@ -204,8 +204,9 @@ def test_backend_metadata_path_on_the_references_own_pool_and_allocator(monkeypa
             assert alloc.alloc(req, n, 0) is not None
         seen = []
 
-        def oracle_metadata(cache_seqlens, num_heads_per_head_k, num_heads_k, fixed_overhead_blocks=5):
+        def oracle_metadata(cache_seqlens, num_heads_per_head_k, num_heads_k, fixed_overhead_blocks=5, num_sm_parts=None):
             seen.append((cache_seqlens.clone(), num_heads_per_head_k, num_heads_k))
+            assert num_sm_parts is None  # 16 q rows: the reference's rule
             meta, ns = omla.get_mla_metadata(cache_seqlens.numpy(), num_heads_per_head_k, num_heads_k, 148,
                                              fixed_overhead_blocks=fixed_overhead_blocks)
             return torch.from_numpy(meta), torch.from_numpy(ns)

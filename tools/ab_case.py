@@ -23,7 +23,7 @@ if root != HERE:  # load this repo's oracle under its own name even when another
 from oracle import mla as omla
 
 # the tile schedule the backend runs (per-request cost tuned for B200); a tree without the extension keeps the reference's
-SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m)} if hasattr(fm, "tuned_overhead_blocks") else {})
+SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m), **({"num_sm_parts": fm.tuned_num_sm_parts(m)} if hasattr(fm, "tuned_num_sm_parts") and not os.environ.get("B200_REF_PARTS") else {})} if hasattr(fm, "tuned_overhead_blocks") else {})
 
 dev = torch.device("cuda:0")
 

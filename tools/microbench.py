@@ -11,7 +11,7 @@ from sglang_fluentllm_b200.fp8_linear import dummy_block_fp8_weight
 # softmax scale of the model (DeepSeek-V3: qk_head_dim ** -0.5 = 192 ** -0.5; on unit-variance q and k that is a logit
 # spread of 2.5 in log2 units, which decides how often a row reference moves); B200_MB_SCALE overrides
 SM_SCALE = float(os.environ.get("B200_MB_SCALE", 192 ** -0.5))
-SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m)} if hasattr(fm, "tuned_overhead_blocks") else {})
+SCHED = lambda m: ({"fixed_overhead_blocks": fm.tuned_overhead_blocks(m), **({"num_sm_parts": fm.tuned_num_sm_parts(m)} if hasattr(fm, "tuned_num_sm_parts") and not os.environ.get("B200_REF_PARTS") else {})} if hasattr(fm, "tuned_overhead_blocks") else {})
 
 dev = torch.device("cuda:0")
 PEAK = 6555.8
