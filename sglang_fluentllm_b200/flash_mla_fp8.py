@@ -28,13 +28,13 @@ REFERENCE_OVERHEAD_BLOCKS = 5  # get_mla_metadata.cu:16 fixed_overhead_num_block
 
 def tuned_overhead_blocks(num_q_rows: int) -> int:
     """The scheduler's per-request fixed cost (in 64-token blocks) that balances the parts on B200: a request boundary
-    costs the CTA-pair kernel (more than 64 q rows) about 24 blocks' worth of time and the narrower kernels about 12
+    costs the CTA-pair kernel (more than 32 q rows) about 24 blocks' worth of time and the SwapAB kernel about 12
     (measured; the reference's 5 is the sm_90 kernel's).  B200_MLA_SCHED_OVERHEAD overrides (sweeps)."""
     import os
     env = os.environ.get("B200_MLA_SCHED_OVERHEAD")
     if env:
         return int(env)
-    return 24 if num_q_rows > 64 else 12
+    return 24 if num_q_rows > 32 else 12
 
 
 def tuned_num_sm_parts(num_q_rows: int) -> Optional[int]:
