@@ -261,6 +261,7 @@ class HotPath:
         self.w_vc = [bf(h, KV_LORA, V_HEAD, std=KV_LORA ** -0.5) for _ in range(L)]
         self.q_buf = torch.empty(b, h, KV_LORA + ROPE, dtype=torch.bfloat16, device=dev)  # "Q" of forward_absorb (:829-833)
         self.launches_per_step = 0
+        self.library_launches_per_step = 0
         self.backend.init_forward_metadata_capture_cuda_graph(b, b, self.req_pool_indices, self.seq_lens,
                                                               fb.ForwardMode.DECODE, None)
         # direct-kernel state for the roofline microbenchmark of the dominant kernel
@@ -325,11 +326,13 @@ class HotPath:
             self.tpmod.all_reduce_sum(y)  # the path's single exchange: row-parallel partial sums over NVLink
         # launches: act-quant, GEMM, norm+quant, GEMM, bmm, prologue, decode (merges cut requests itself), bmm, act-quant,
         # GEMM + split-K reduce
-        self.launches_per_step += 11
+        self.launches_per_step += 9     # this repo's kernels
+        self.library_launches_per_step += 2   # the two cuBLAS bmm's
         return y
 
     def step(self, x):
         self.launches_per_step = 0
+        self.library_launches_per_step = 0
         for l in range(self.args.layers):
             x = self.layer(l, x)
         return x
@@ -517,7 +520,8 @@ def run_b200(args):
         "config": workload_config(args, world, args.parallelism, hp.h, graph is not None),
         "e2e": {"value": round(e2e_tokens_per_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
-        "gpu_launches": launches * args.steps,
+        "gpu_launches": launches * args.steps,  # this repo's kernels only
+        "library_launches": hp.library_launches_per_step * args.steps,  # cuBLAS bf16 bmm (w_kc / w_vc absorb, as the reference)
         "clocks": clocks,
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_source,
