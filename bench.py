@@ -526,7 +526,7 @@ def run_b200(args):
         "roofline": {"bound": "hbm", "achieved": round(achieved, 1), "peak": hbm_peak, "unit": "GB/s",
                      "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_source,
                      "peak_source": peak_src,
-                     "kernel": "mla_decode_kernel (+combine), per layer, L2-cold", "kernel_ms": round(attn_ms, 4),
+                     "kernel": "mla_decode_pair_kernel (merges cut requests itself; + combine launch where the backend needs one), per layer, L2-cold, model softmax scale", "kernel_ms": round(attn_ms, 4),
                      "algorithmic_bytes": bytes_, "tflops": round(flops / (attn_ms * 1e-3) / 1e12, 1)},
     }
     tp_strong = None
