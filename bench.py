@@ -543,7 +543,16 @@ def run_b200(args):
         # torch.distributed's NCCL call for A/B
         use_p2p = not os.environ.get("B200_TP_NCCL")
         if use_p2p:
-            hp_tp.tpmod.enable_p2p_all_reduce(None, dev, args.batch * HIDDEN * 2)
+            try:
+                hp_tp.tpmod.enable_p2p_all_reduce(None, dev, args.batch * HIDDEN * 2)
+                ok = torch.ones(1, device=dev)
+            except Exception as e:  # no peer access / IPC on this box: say so and time the NCCL form
+                log("peer-memory all-reduce unavailable (%s: %s): tp_strong uses NCCL" % (type(e).__name__, e))
+                ok = torch.zeros(1, device=dev)
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)  # every rank or none
+            if float(ok.item()) == 0.0:
+                use_p2p = False
+                hp_tp.tpmod._p2p = None
         with torch.cuda.stream(stream):
             for _ in range(2):
                 hp_tp.step(hp_tp.hidden_in)
