@@ -41,6 +41,10 @@ def tuned_num_sm_parts(num_q_rows: int) -> Optional[int]:
     """Scheduler parts for the kernel that will run, where that differs from the reference's rule (one part per SM and
     64 q rows, flash_api.cpp:41-43): 33-64 q rows run on CTA pairs, so half as many parts (one wave instead of two waves
     of short parts); None = the reference's rule."""
+    import os
+    env = os.environ.get("B200_MLA_PARTS")  # sweeps
+    if env:
+        return int(env)
     if 32 < num_q_rows <= 64:
         return max(1, int(_lib.lib().b200_sm_count()) // 2)
     return None
