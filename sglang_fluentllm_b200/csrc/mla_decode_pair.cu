@@ -869,8 +869,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         // One code path for the pass over the codes (a single call site keeps the hot loop's footprint inside the
         // instruction cache): fast path = the current reference; if a row of the group has outgrown it (or on a
         // request's first tile) the reference moves first ("slow path") and the pass runs under the new one.
-        bool trigger = (t == 0), moved = false, rescale_pending = false;
-        float rescale_fac = 1.f;
+        bool trigger = (t == 0), moved = false;
         for (;;) {
           if (lane == 0) B200_BEACON(16 + (warp - 4), 11 + 100 * g);
           if (!trigger) {
@@ -891,22 +890,41 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             const float yb = fmaxf(red1[row], red1[64 + row]);
             const float r_new = yb > r_old ? yb + kRefHeadroom : r_old;
             const float fac = exp2f(r_old - r_new);  // 0 on the row's first move (R = -1e30), 1 if the row stays
-            // O is rescaled further down, behind this tile's weighted pass (which only needs the new reference): the
-            // drain of the P.V products in flight -- a move's main cost -- then overlaps that pass instead of preceding it
-            rescale_fac = fac;
-            rescale_pending = t != 0;
-            if (t != 0) lsum *= fac;
+            if (t != 0) {
+              // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
+              // last one issued: tile g is not published yet).  pv_done completes once per tile; tile g-1 is final
+              // (fin), so P.V of tile g-2 was issued before it and this parity wait cannot alias an older phase... it
+              // could still be two phases behind if P.V of g-2 has not retired: wait for that one first (s_free).
+              if (lane == 0) B200_BEACON(16 + (warp - 4), 22 + 100 * g);
+              if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
+              if (lane == 0) B200_BEACON(16 + (warp - 4), 23 + 100 * g);
+              mbar_wait(&sm.pv_done, (g - 1) & 1);
+              tc_fence_after();
+              if (__any_sync(0xffffffffu, fac != 1.f)) {
+#pragma unroll 1
+                for (int c8 = 0; c8 < 8; ++c8) {
+                  float o[32];
+                  const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
+                  tmem_ld<32>(a, o);
+                  tmem_wait_ld();
+#pragma unroll
+                  for (int k = 0; k < 32; ++k) o[k] *= fac;
+                  tmem_st<32>(a, o);
+                }
+                tmem_wait_st();
+              }
+              lsum *= fac;
+            }
             if (lane == 0) B200_BEACON(16 + (warp - 4), 24 + 100 * g);
             rloc = r_new;
             if (page == 0) sm.st_ref[row] = r_new;
-            named_bar_sync(gbar, 128);  // the new row state is written by the whole group
+            tc_fence_before();
+            named_bar_sync(gbar, 128);  // O rescaled and the new row state written by the whole group
             ver += 1;
             if (gtid == 0) st_shared_volatile_u32(&sm.version, ver);  // reaches the other groups with the arrival on sm.fin
-            // The reference is final for this tile: the next tiles may run their weighted passes (and publish) while this
-            // one runs its own and rescales O.  What orders the rest does not hang on fin: P.V is issued in tile order, so
-            // nothing of a later tile reaches O before this tile's P.V, which waits for this tile's publish, which follows
-            // the rescale; and a later tile that moves the reference again waits for this tile's P.V (pv_done) before it
-            // touches O.  The version store above is ordered before the arrival of gtid 0's warp by this barrier.
+            // The reference is final for this tile and O is rescaled: the next tile may run its weighted pass while this
+            // one runs its own (what orders them further -- P.V issue order, pv_done before a rescale -- does not hang
+            // on fin).  The version store above is ordered before the arrival of gtid 0's warp by this barrier.
             named_bar_sync(gbar, 128);
             if (lane == 0) B200_BEACON(16 + (warp - 4), 25 + 100 * g);
             if (lane == 0) mbar_arrive(&sm.fin[g & 1]);
@@ -918,29 +936,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (!over) weighted_pass();
           if (lane == 0) B200_BEACON(16 + (warp - 4), 13 + 100 * g);
           if (moved) {
-            if (rescale_pending) {
-              // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
-              // last one that can be in flight: tile g is not published yet and P.V is issued in tile order).  pv_done
-              // completes once per tile; it could still be two phases behind if P.V of g-2 has not retired: wait for
-              // that one first (s_free).
-              if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
-              mbar_wait(&sm.pv_done, (g - 1) & 1);
-              tc_fence_after();
-              if (__any_sync(0xffffffffu, rescale_fac != 1.f)) {
-#pragma unroll 1
-                for (int c8 = 0; c8 < 8; ++c8) {
-                  float o[32];
-                  const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
-                  tmem_ld<32>(a, o);
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int k = 0; k < 32; ++k) o[k] *= rescale_fac;
-                  tmem_st<32>(a, o);
-                }
-                tmem_wait_st();
-              }
-              tc_fence_before();  // (the publish below arrives on p_full behind this: P.V of this tile sees the rescaled O)
-            }
             lsum = fmaf(w32, acc, lsum);
             named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
             break;

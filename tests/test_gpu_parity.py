@@ -412,7 +412,7 @@ def test_mla_pair_is_timing_independent(tmp_path):
         base = key.rsplit("_", 1)[0] + "_0"
         assert np.array_equal(chaos[key], plain[base]), "%s differs from the undisturbed run" % key
         n += 1
-    assert n >= 6 * 2 * 4 * 2
+    assert n >= 7 * 2 * 4 * 2
 
 
 @pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])
