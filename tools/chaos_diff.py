@@ -1,3 +1,5 @@
+"""Which outputs differ between an undisturbed run and runs with random warp delays (tests/chaos_case.py under
+B200_MLA_TRACE=5)?  Prints the tensors, how many elements and which (request, head) rows differ.  Usage: python tools/chaos_diff.py"""
 import os, sys, subprocess, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 helper = os.path.join(ROOT, "tests", "chaos_case.py")
