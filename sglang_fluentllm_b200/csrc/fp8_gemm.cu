@@ -540,11 +540,8 @@ static int launch_splitk_reduce(const GemmParams& prm, cudaStream_t stream) {
 template <int BN, bool KC, bool GROUPED = false>
 static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmTokMSmem<BN>::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN, KC, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  // per device and context, so not cached per process (a process may drive several GPUs)
+  B200_CUDA(cudaFuncSetAttribute(fp8_gemm_tokm_kernel<BN, KC, GROUPED>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((prm.n + BN - 1) / BN, prm.tiles_y ? prm.tiles_y : (prm.m + 127) / 128, prm.splits);
@@ -584,11 +581,8 @@ static int launch_gemm_tokm(const GemmParams& prm, int use_pdl, cudaStream_t str
 template <int BT, int CPT>
 static int launch_gemm(const GemmParams& prm, int use_pdl, cudaStream_t stream) {
   const int smem = GemmSmem<BT>::kTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(fp8_gemm_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  // per device and context, so not cached per process (a process may drive several GPUs)
+  B200_CUDA(cudaFuncSetAttribute(fp8_gemm_kernel<BT, CPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3((prm.n + 127) / 128, (prm.m + BT - 1) / BT, prm.splits);

@@ -439,11 +439,8 @@ extern "C" int b200_mla_decode_bf16(const void* q, const void* k_cache, int64_t 
   prm.is_causal = is_causal;
 
   const int smem = bf16kv::kSmemTotal + 1024;
-  static bool configured = false;
-  if (!configured) {
-    B200_CUDA(cudaFuncSetAttribute(bf16kv::mla_decode_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    configured = true;
-  }
+  // per device and context, so not cached per process (a process may drive several GPUs)
+  B200_CUDA(cudaFuncSetAttribute(bf16kv::mla_decode_bf16_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
   if (int rc = launch_kernel(bf16kv::mla_decode_bf16_kernel, dim3(q_blocks, 1, num_sm_parts), dim3(bf16kv::kThreads), smem,
                              (cudaStream_t)stream, use_pdl != 0, prm))
     return rc;
