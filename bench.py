@@ -527,7 +527,13 @@ def run_b200(args):
                      "frac": round(achieved / hbm_peak, 4), "traffic": traffic, "traffic_source": traffic_source,
                      "peak_source": peak_src,
                      "kernel": "mla_decode_pair_kernel (merges cut requests itself; + combine launch where the backend needs one), per layer, L2-cold, model softmax scale", "kernel_ms": round(attn_ms, 4),
-                     "algorithmic_bytes": bytes_, "tflops": round(flops / (attn_ms * 1e-3) / 1e12, 1)},
+                     "algorithmic_bytes": bytes_, "tflops": round(flops / (attn_ms * 1e-3) / 1e12, 1),
+                     # the second roofline (informational): the page-wise P arithmetic issues P.V twice (hi + lo weights,
+                     # DESIGN 3.1), so the tensor pipe executes 2 S M (576 + 2 * 512) flops; peaks = torch._scaled_mm
+                     # 8192^3 on this pool (profiles/r2h_gemm_compare.txt: burst / sustained under the power cap)
+                     "tensor": {"executed_tflops": round(flops * 1600 / 1088 / (attn_ms * 1e-3) / 1e12, 1),
+                                "fp8_peak_burst": 3107.0, "fp8_peak_sustained": 2612.0,
+                                "frac_of_sustained": round(flops * 1600 / 1088 / (attn_ms * 1e-3) / 1e12 / 2612.0, 4)}},
     }
     tp_strong = None
     if world > 1 and args.parallelism == "dp":

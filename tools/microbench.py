@@ -131,6 +131,11 @@ what = sys.argv[1:] or ["mla", "gemm"]
 if what and what[0] == "gemm1":  # one shape: python tools/microbench.py gemm1 M N K  (with B200_GEMM_BN / B200_GEMM_SPLITS)
     bench_gemm(int(what[1]), int(what[2]), int(what[3]))
     what = []
+if what and what[0] == "mla1":  # shapes: python tools/microbench.py mla1 B,SEQ,H[,SQ] ...
+    for a in what[1:]:
+        v = [int(x) for x in a.split(",")]
+        bench_mla(v[0], v[1], v[2], s_q=v[3] if len(v) > 3 else 1)
+    what = []
 if "mla128" in what:
     bench_mla(128, 4096, 128)
     bench_mla(64, 4096, 128, s_q=2)
