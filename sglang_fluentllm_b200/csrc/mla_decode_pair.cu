@@ -103,12 +103,16 @@ __device__ unsigned long long g_part_cycles[2 * 128 * 4];  // [part < 128][rank]
 // the MMA issuers, the softmax passes, the hand-offs and the epilogue -- delays its warp by a pseudo-random 0-4 us, so
 // warps, groups and the two CTAs of a pair drift against each other by whole tiles.  The protocol must not care: the
 // results have to stay bit-identical (tests/test_gpu_parity.py::test_mla_pair_is_timing_independent).
-__device__ int g_chaos;
+__constant__ int g_chaos;  // (constant bank: a trace site must not cost an L2 round trip)
 // TR = false (the production instantiation) compiles every trace site out
 template <bool TR>
 __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t g, int ev) {
   if constexpr (TR) {
-    if (g_chaos) {  // (the same delay for the whole warp: the trace sites are warp-converged code in front of aligned barriers)
+    // one bit per site: 4 * role + event for the pipeline's sites, 20-25 for the request-boundary detail sites (role 3,
+    // index >= 8), so that a perturbation that changes results can be pinned to the hand-off it disturbs
+    // (B200_MLA_CHAOS_SITES)
+    const int site_bit = (role == 3 && g >= 8u) ? (g >= 16u ? 24 + ev : 20 + ev) : 4 * role + ev;
+    if ((g_chaos >> site_bit) & 1) {  // (the same delay for the whole warp: the trace sites are warp-converged code in front of aligned barriers)
       const uint32_t c = __shfl_sync(0xffffffffu, (uint32_t)clock64(), 0);
       uint32_t h = c * 2654435761u ^ ((threadIdx.x >> 5) * 40503u + blockIdx.z * 9176u + role * 131u + ev * 31u + g);
       h ^= h >> 13, h *= 0x5bd1e995u, h ^= h >> 15;
@@ -116,6 +120,23 @@ __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t
     }
     if (on && g < (uint32_t)kTraceTiles) g_trace[((rank * kTraceRoles + role) * kTraceTiles + g) * 4 + ev] = clock64();
   }
+}
+
+// Token rows past the end of a request meet P = 0 in P.V: make V there finite (0 * NaN).  Reference: fill_oob_V,
+// splitkv_mla.cu:698-721.  Called by the warp that has just seen the unit land and hands it to P.V -- the P.V issuer for
+// the leader's units, the relay warp for the peer's -- i.e. by warps that wait for every unit in order.  (The softmax
+// groups used to do this in front of their publish.  They run up to three tiles ahead of P.V, though: with unit u - 3 of
+// the same slot still in flight, their parity wait for unit u returned on the slot's older phase and the zeros went
+// into the rows of unit u - 3 under its TMA -- found by the timing-perturbation test with delays in the V producer.)
+// At most 31 rows: one per lane.  Rows [valid_in_tile, nk * 32) of [128 tokens][128 B].
+__device__ __forceinline__ void zero_v_rows_past_end(uint8_t* unit, int valid_in_tile, int nk, int lane) {
+  const int r = valid_in_tile + lane;
+  if (r < nk * 32) {
+    uint4* vr = reinterpret_cast<uint4*>(unit + r * 128);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) vr[k] = make_uint4(0, 0, 0, 0);
+  }
+  fence_proxy_async_smem();
 }
 
 // Register-resident window of one block-table row for the producer warp (warp-uniform use): lane l holds entries
@@ -558,7 +579,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         for (int t = 0; t < sg.n_tiles; ++t, ++g) {
           const uint32_t pp = g % kPPairs;
           mbar_wait_cluster(&sm.p_full[pp], (g / kPPairs) & 1);  // P written in both CTAs
+          if (t == 0) trace<TR>(tr, rank, 3, 16 + seg, 0);
           if (t == 0 && seg > 0) mbar_wait_cluster(&sm.o_free, (seg - 1) & 1);
+          if (t == 0) trace<TR>(tr, rank, 3, 16 + seg, 1);
           trace<TR>(tr, rank, 1, g, 2);
           B200_BEACON(3, g);
           tc_fence_after();
@@ -568,7 +591,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           for (int j = 0; j < 2; ++j) {  // d-half by d-half: the first V unit is released while the second is read
             const uint32_t u = 2 * g + (uint32_t)j, vst = u % kVUnits;
             mbar_wait(&sm.v_land[vst], (u / kVUnits) & 1);          // V unit landed here
-            mbar_wait_cluster(&sm.v_peer[vst], (u / kVUnits) & 1);  // ... and in the peer
+            if (tile_start + kTileTokens > sg.valid_end) {
+              zero_v_rows_past_end(s_v + vst * kVUnitBytes, sg.valid_end - tile_start, nk, lane);
+              __syncwarp();
+            }
+            mbar_wait_cluster(&sm.v_peer[vst], (u / kVUnits) & 1);  // ... and in the peer (rows past the end zeroed)
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -625,7 +652,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           // per tile: the first V unit (frees early), then this CTA's P (its S tile is dead with it), then the second
           // V unit (the last to land: its slot frees when P.V of the previous tile's first half retires)
           const uint32_t u0 = 2 * g, u1 = 2 * g + 1;
+          const int tile_start = (sg.start_block + 2 * t) * kPage;
+          const bool past_end = tile_start + kTileTokens > sg.valid_end;
+          const int valid_in_tile = sg.valid_end - tile_start, nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
+          // this warp's own stores go out in front of the remote arrive (CTA-scope release): cluster fence
+          auto zero_past_end = [&](uint32_t u) {
+            zero_v_rows_past_end(s_v + (u % kVUnits) * kVUnitBytes, valid_in_tile, nk, lane);
+            asm volatile("fence.acq_rel.cluster;" ::: "memory");
+            __syncwarp();
+          };
           mbar_wait(&sm.v_land[u0 % kVUnits], (u0 / kVUnits) & 1);
+          if (past_end) zero_past_end(u0);
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u0 % kVUnits]);
           __syncwarp();
           B200_BEACON(4, g);
@@ -636,6 +673,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           }
           __syncwarp();
           mbar_wait(&sm.v_land[u1 % kVUnits], (u1 / kVUnits) & 1);
+          if (past_end) zero_past_end(u1);
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u1 % kVUnits]);
           __syncwarp();
         }
@@ -810,8 +848,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         if (t <= 1) trace<TR>(tr_w, rank, 3, o_seg, 3);
         trace<TR>(tr_w, rank, 4, g, 3);
 
-        // No wait on ks_full: the UMMA issuer saw the tile's k scales land before it issued this tile's Q.K^T, so
-        // s_full vouches for them too.
+        // The leader's UMMA issuer saw ITS copy of the tile's k scales land before it issued this tile's Q.K^T, so in the
+        // leader s_full vouches for them.  The peer CTA loads its own copy, and nothing there stands between that load
+        // and the reads below: it waits on its own barrier (found by the timing-perturbation test: a late copy gave the
+        // peer's 64 rows a tile computed with some of the slot's previous scales).  The slot is this group's own
+        // (g + 6 = g mod 3), so the parity cannot alias.
         const float* ks_tile = s_ks + kst * 128;
         const float* lk_tile = sm.lkrk[grp];
         const float* rk_tile = sm.lkrk[grp] + 128;
@@ -821,6 +862,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         bool fin_waited = false, fin_arrived = false;
         trace<TR>(tr_w, rank, 2, g, 0);
         mbar_wait(&sm.s_full[sb], (g / kSBufs) & 1);
+        if (rank != 0) mbar_wait(&sm.ks_full[kst], (g / kKsStages) & 1);
         trace<TR>(tr_w, rank, 2, g, 1);
         tc_fence_after();
 
@@ -964,22 +1006,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         if (gtid == 0) B200_BEACON(8 + grp, 3);
         // ---- publish P ----
         trace<TR>(tr_w, rank, 4, g, 2);
-        // token rows past the end of the sequence meet P = 0 in P.V; make V there finite (0 * NaN).
-        // Reference: fill_oob_V, splitkv_mla.cu:698-721.
-        if (tile_start + kTileTokens > sg.valid_end) {
-          const int valid_in_tile = sg.valid_end - tile_start;
-          const int nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
-#pragma unroll
-          for (int j = 0; j < 2; ++j) {
-            const uint32_t u = 2 * g + (uint32_t)j, vst = u % kVUnits;
-            mbar_wait(&sm.v_land[vst], (u / kVUnits) & 1);
-            if (gtid >= valid_in_tile && gtid < nk * 32) {
-              uint4* vr = reinterpret_cast<uint4*>(s_v + vst * kVUnitBytes + gtid * 128);
-#pragma unroll
-              for (int k = 0; k < 8; ++k) vr[k] = make_uint4(0, 0, 0, 0);
-            }
-          }
-        }
+        // (token rows past the end of the sequence are zeroed in the V units by the warps that hand the units to P.V)
         fence_proxy_async_smem();
         tc_fence_before();
         __syncwarp();
@@ -1188,17 +1215,21 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (had_tiles) {
             tmem_ld<32>(o_addr + r8 * 32, oa);
             tmem_wait_ld();
+            if (r8 == grp) trace<TR>(tr_e, rank, 3, 8 + o_seg, 0);
             if (r8 + kGroups >= 8) {  // this warp's share of O has left TMEM: the next request's P.V may overwrite it
               tc_fence_before();
               __syncwarp();
               if (lane == 0) mbar_arrive(rank == 0 ? &sm.o_free : &sm.o_relay);
+              trace<TR>(tr_e, rank, 3, 8 + o_seg, 2);
             }
           } else {
 #pragma unroll
             for (int k = 0; k < 32; ++k) oa[k] = 0.f;
           }
           flush(oa, r8, sg.no_split, inv);
+          if (r8 == grp) trace<TR>(tr_e, rank, 3, 8 + o_seg, 1);
         }
+        trace<TR>(tr_e, rank, 3, 8 + o_seg, 3);
         named_bar_sync(gbar, 128);  // the slices are this group's next P tiles (written per q row across warps)
         if (gtid == 0) B200_BEACON(8 + grp, 8);
         if (had_tiles) trace<TR>(tr_e, rank, 3, o_seg, 2);
@@ -1246,7 +1277,8 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream
   const int q_pairs = (prm.M + 127) / 128;
   const dim3 grid(2, q_pairs, num_sm_parts), block(128 + pairk::kSmThreads);
   if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, bit 2 = random delays
-    const int chaos = (prm.trace & 4) ? 1 : 0;
+    static const int sites = getenv("B200_MLA_CHAOS_SITES") ? atoi(getenv("B200_MLA_CHAOS_SITES")) : 0x3ffffff;
+    const int chaos = (prm.trace & 4) ? sites : 0;
     B200_CUDA(cudaMemcpyToSymbolAsync(pairk::g_chaos, &chaos, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
     B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     return launch_kernel(pairk::mla_decode_pair_kernel<true>, grid, block, smem, stream, pdl, prm);

@@ -392,13 +392,13 @@ def test_mla_pair_in_kernel_merge_equals_combine(mods, b, h, s_q, seqlens, causa
 def test_mla_pair_is_timing_independent(tmp_path):
     """The CTA-pair kernel's hand-offs (row-reference moves, tile order, P / S / V rings, cluster relays, in-kernel
     merge) must not depend on who is fast: the diagnostic instantiation with a pseudo-random 0-4 us delay at each of its
-    20 trace sites (B200_MLA_TRACE=5: warps, softmax groups and the two CTAs drift by whole tiles) has to reproduce the
+    26 trace sites (B200_MLA_TRACE=5: warps, softmax groups and the two CTAs drift by whole tiles) has to reproduce the
     production instantiation's output bit for bit, run after run, under both tile schedules."""
     import subprocess
     import sys
     helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chaos_case.py")
     outs = {}
-    for name, env_extra, repeats in (("plain", {}, 1), ("chaos", {"B200_MLA_TRACE": "5"}, 4)):
+    for name, env_extra, repeats in (("plain", {}, 1), ("chaos", {"B200_MLA_TRACE": "5"}, 10)):
         env = dict(os.environ)
         env.pop("B200_MLA_TRACE", None)
         env.update(env_extra)

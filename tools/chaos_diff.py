@@ -6,7 +6,7 @@ helper = os.path.join(ROOT, "tests", "chaos_case.py")
 env = dict(os.environ); env.pop("B200_MLA_TRACE", None)
 subprocess.run([sys.executable, helper, "/tmp/plain.npz", "1"], env=env, check=True, capture_output=True)
 env["B200_MLA_TRACE"] = "5"
-subprocess.run([sys.executable, helper, "/tmp/chaos.npz", "12"], env=env, check=True, capture_output=True)
+subprocess.run([sys.executable, helper, "/tmp/chaos.npz", sys.argv[1] if len(sys.argv) > 1 else "12"], env=env, check=True, capture_output=True)
 p, c = np.load("/tmp/plain.npz"), np.load("/tmp/chaos.npz")
 for key in c.files:
     base = key.rsplit("_", 1)[0] + "_0"

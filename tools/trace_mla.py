@@ -81,6 +81,11 @@ for rank in range(2):
     for sgi in range(4):
         e = tr[rank, 3, sgi, :] - t0
         print(" %7d | %9d %8d %8d | %8d" % (sgi, e[0], e[1], e[2], e[3]))
+    print(" request | epilogue detail (group 0, warp 0): first O chunk in registers  first chunk stored  last chunk read (O released)  last chunk stored | P.V issuer: first P of the request complete  O free")
+    for sgi in range(4):
+        e = tr[rank, 3, 8 + sgi, :] - t0
+        m = tr[rank, 3, 16 + sgi, :] - t0
+        print(" %7d | %9d %8d %8d %8d | %9d %8d" % (sgi, e[0], e[1], e[2], e[3], m[0], m[1]))
 
 pt = np.zeros(2 * 128 * 4, dtype=np.uint64)
 _lib.check(L.b200_mla_read_part_times(pt.ctypes.data, pt.size), "read_part_times")
