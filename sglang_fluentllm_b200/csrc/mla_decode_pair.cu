@@ -76,6 +76,7 @@ struct Small {
   uint64_t q_full, q_empty;
   uint64_t s_full[kSBufs], s_free[kSBufs];     // s_free(g): P.V of tile g retired
   uint64_t s_done[kSBufs];                     // both CTAs' softmax groups are through with S tile g % kSBufs: Q.K^T may overwrite it
+  uint64_t v_aux[2];                           // landing barrier of a request's last units while their rows past the end are zeroed
   uint64_t v_peer[kVUnits];                    // leader: the peer CTA's V unit has landed (forwarded by its relay warp)
   uint64_t p_full[kPPairs], p_free[kPPairs];   // per P pair (tile parity)
   uint64_t pv_done, o_ready, o_free;
@@ -123,12 +124,13 @@ __device__ __forceinline__ void trace(bool on, uint32_t rank, int role, uint32_t
 }
 
 // Token rows past the end of a request meet P = 0 in P.V: make V there finite (0 * NaN).  Reference: fill_oob_V,
-// splitkv_mla.cu:698-721.  Called by the warp that has just seen the unit land and hands it to P.V -- the P.V issuer for
-// the leader's units, the relay warp for the peer's -- i.e. by warps that wait for every unit in order.  (The softmax
-// groups used to do this in front of their publish.  They run up to three tiles ahead of P.V, though: with unit u - 3 of
-// the same slot still in flight, their parity wait for unit u returned on the slot's older phase and the zeros went
-// into the rows of unit u - 3 under its TMA -- found by the timing-perturbation test with delays in the V producer.)
-// At most 31 rows: one per lane.  Rows [valid_in_tile, nk * 32) of [128 tokens][128 B].
+// splitkv_mla.cu:698-721.  Called by the V producer warp of each CTA, the one warp that sees every unit of its ring in
+// order: a unit with such rows lands on an auxiliary barrier, the producer zeroes the rows and only then completes the
+// unit's phase of v_land, so the consumers (P.V issuer, relay) see a finished unit and know nothing of this.  (The
+// softmax groups used to do it in front of their publish.  They run up to three tiles ahead of P.V, though: with unit
+// u - 3 of the same slot still in flight, their parity wait for unit u returned on the slot's older phase and the zeros
+// went into the rows of unit u - 3 under its TMA -- found by the timing-perturbation test with delays in the V
+// producer.)  At most 31 rows, one per lane: rows [valid_in_tile, nk * 32) of [128 tokens][128 B].
 __device__ __forceinline__ void zero_v_rows_past_end(uint8_t* unit, int valid_in_tile, int nk, int lane) {
   const int r = valid_in_tile + lane;
   if (r < nk * 32) {
@@ -221,6 +223,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
       mbar_init(&sm.s_done[i], 5);   // the four warps of the leader's softmax group + the peer's relay
     }
     for (int i = 0; i < kVUnits; ++i) mbar_init(&sm.v_peer[i], 1);
+    for (int i = 0; i < 2; ++i) mbar_init(&sm.v_aux[i], 1);
     for (int i = 0; i < kPPairs; ++i) {
       mbar_init(&sm.p_full[i], 5);   // the four warps of the leader's softmax group + the peer's relay
       mbar_init(&sm.p_relay[i], 4);
@@ -466,7 +469,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
     // unit u = 2 * tile + j lives in slot u % 3, so the ring holds a tile and a half and the second half of tile g + 1
     // is refilled while P.V of tile g still reads the other half.
     const uint64_t pol_last_use = policy_evict_first();
-    uint32_t g = 0;
+    uint32_t g = 0, n_tails = 0;  // n_tails: units pairs that went through v_aux (its phase count)
     int cur_sl = __ldg(p.seqlens + begin_idx), cur_ns = __ldg(p.num_splits + begin_idx);  // fetched one request ahead
     for (int b = begin_idx; b <= end_idx; ++b) {
       const Segment sg = make_segment_from(p, b, cur_sl, cur_ns, begin_idx, begin_seqlen, end_idx, end_seqlen,
@@ -488,6 +491,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
         const int npages = min(2, sg.end_block - blk0);
         const int tok0 = bw.get(blk0) * kPage;
         const int tok1 = npages > 1 ? bw.get(blk0 + 1) * kPage : 0;
+        // rows past the request's end inside the 32-token blocks P.V reads (only a request's last tile has any)
+        const int valid_in_tile = sg.valid_end - (sg.start_block + 2 * t) * kPage;
+        const int nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
+        const bool zero_tail = valid_in_tile < nk * 32 && !(TR && (p.trace & 8));
 #pragma unroll 1
         for (int j = 0; j < 2; ++j) {
           const uint32_t u = 2 * gt + (uint32_t)j, st = u % kVUnits;
@@ -508,12 +515,24 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             continue;
           }
           if (elect_one()) {
-            mbar_arrive_expect_tx(&sm.v_land[st], (uint32_t)npages * 8192);
-            tma_load_2d_hint(unit, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok0, pol_last_use);
-            if (npages > 1)
-              tma_load_2d_hint(unit + 8192, &p.tm_k_nope, &sm.v_land[st], 256 * j + 128 * (int)rank, tok1, pol_last_use);
+            uint64_t* land = zero_tail ? &sm.v_aux[j] : &sm.v_land[st];
+            mbar_arrive_expect_tx(land, (uint32_t)npages * 8192);
+            tma_load_2d_hint(unit, &p.tm_k_nope, land, 256 * j + 128 * (int)rank, tok0, pol_last_use);
+            if (npages > 1) tma_load_2d_hint(unit + 8192, &p.tm_k_nope, land, 256 * j + 128 * (int)rank, tok1, pol_last_use);
           }
           __syncwarp();
+        }
+        if (zero_tail) {  // (the next unit's slot frees no earlier than P.V of this tile's predecessor: nothing waits on this)
+#pragma unroll 1
+          for (int j = 0; j < 2; ++j) {
+            const uint32_t u = 2 * gt + (uint32_t)j, st = u % kVUnits;
+            mbar_wait(&sm.v_aux[j], n_tails & 1);
+            zero_v_rows_past_end(s_v + st * kVUnitBytes, valid_in_tile, nk, lane);
+            __syncwarp();
+            if (elect_one()) mbar_arrive(&sm.v_land[st]);  // the unit's phase of v_land: landed and finished
+            __syncwarp();
+          }
+          ++n_tails;
         }
       };
       for (int t = 0; t < sg.n_tiles; ++t, ++g) {
@@ -591,11 +610,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           for (int j = 0; j < 2; ++j) {  // d-half by d-half: the first V unit is released while the second is read
             const uint32_t u = 2 * g + (uint32_t)j, vst = u % kVUnits;
             mbar_wait(&sm.v_land[vst], (u / kVUnits) & 1);          // V unit landed here
-            if (tile_start + kTileTokens > sg.valid_end) {
-              zero_v_rows_past_end(s_v + vst * kVUnitBytes, sg.valid_end - tile_start, nk, lane);
-              __syncwarp();
-            }
-            mbar_wait_cluster(&sm.v_peer[vst], (u / kVUnits) & 1);  // ... and in the peer (rows past the end zeroed)
+            mbar_wait_cluster(&sm.v_peer[vst], (u / kVUnits) & 1);  // ... and in the peer
             tc_fence_after();
             if (elect_one()) {
 #pragma unroll
@@ -652,17 +667,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           // per tile: the first V unit (frees early), then this CTA's P (its S tile is dead with it), then the second
           // V unit (the last to land: its slot frees when P.V of the previous tile's first half retires)
           const uint32_t u0 = 2 * g, u1 = 2 * g + 1;
-          const int tile_start = (sg.start_block + 2 * t) * kPage;
-          const bool past_end = tile_start + kTileTokens > sg.valid_end;
-          const int valid_in_tile = sg.valid_end - tile_start, nk = (min(kTileTokens, valid_in_tile) + 31) / 32;
-          // this warp's own stores go out in front of the remote arrive (CTA-scope release): cluster fence
-          auto zero_past_end = [&](uint32_t u) {
-            zero_v_rows_past_end(s_v + (u % kVUnits) * kVUnitBytes, valid_in_tile, nk, lane);
-            asm volatile("fence.acq_rel.cluster;" ::: "memory");
-            __syncwarp();
-          };
           mbar_wait(&sm.v_land[u0 % kVUnits], (u0 / kVUnits) & 1);
-          if (past_end) zero_past_end(u0);
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u0 % kVUnits]);
           __syncwarp();
           B200_BEACON(4, g);
@@ -673,7 +678,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           }
           __syncwarp();
           mbar_wait(&sm.v_land[u1 % kVUnits], (u1 / kVUnits) & 1);
-          if (past_end) zero_past_end(u1);
           if (elect_one()) mbar_arrive_cluster(v_peer_l[u1 % kVUnits]);
           __syncwarp();
         }
