@@ -141,6 +141,21 @@ __device__ __forceinline__ void zero_v_rows_past_end(uint8_t* unit, int valid_in
   fence_proxy_async_smem();
 }
 
+// O *= fac for this thread's TMEM lane (256 columns): a row reference moved
+__device__ __forceinline__ void rescale_o(uint32_t lane_base, float fac) {
+#pragma unroll 1
+  for (int c8 = 0; c8 < 8; ++c8) {
+    float o[32];
+    const uint32_t a = lane_base + c8 * 32;
+    tmem_ld<32>(a, o);
+    tmem_wait_ld();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) o[k] *= fac;
+    tmem_st<32>(a, o);
+  }
+  tmem_wait_st();
+}
+
 // Register-resident window of one block-table row for the producer warp (warp-uniform use): lane l holds entries
 // base + l and base + 32 + l.  With ~230 KB of shared memory per CTA there is no L1 left, so every __ldg of the block
 // table is an L2 round trip (300-600 cycles under load); three of them per tile in the producer's dependency chain were
@@ -173,7 +188,7 @@ struct BtWindow {
 };
 
 
-template <bool TR>
+template <bool TR, bool DEFER>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
     mla_decode_pair_kernel(const __grid_constant__ MlaParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -932,32 +947,36 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             float* red1 = reinterpret_cast<float*>(s_p + (2 * grp) * kPBytes);  // [2 pages][64 rows]
             red1[page * 64 + row] = ymax;
             named_bar_sync(gbar, 128);
-            const float r_old = ld_shared_volatile_f32(&sm.st_ref[row]);  // == rloc
+            // (== sm.st_ref[row] as of sync_view above: moves are serialised by fin.  Not read from shared memory here: the
+            // row's other thread -- the lane of the second page, in another warp -- writes r_new below, and in the
+            // deferred form nothing long stands between this line and that store: single rows came out wrong under the
+            // timing-perturbation test until this read was gone)
+            const float r_old = rloc;
             const float yb = fmaxf(red1[row], red1[64 + row]);
             const float r_new = yb > r_old ? yb + kRefHeadroom : r_old;
             const float fac = exp2f(r_old - r_new);  // 0 on the row's first move (R = -1e30), 1 if the row stays
-            if (t != 0) {
-              // every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the
-              // last one issued: tile g is not published yet).  pv_done completes once per tile; tile g-1 is final
-              // (fin), so P.V of tile g-2 was issued before it and this parity wait cannot alias an older phase... it
-              // could still be two phases behind if P.V of g-2 has not retired: wait for that one first (s_free).
+            // Every P.V up to the previous tile must have landed in O before it is rescaled (P.V of tile g-1 is the last
+            // one that can be in flight: tile g is not published yet and P.V is issued in tile order).  pv_done completes
+            // once per tile; the parity wait could still be two phases behind if P.V of g-2 has not retired: wait for
+            // that one first (s_free).
+            auto drain_and_rescale = [&](float f_o) {
               if (lane == 0) B200_BEACON(16 + (warp - 4), 22 + 100 * g);
               if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
               if (lane == 0) B200_BEACON(16 + (warp - 4), 23 + 100 * g);
               mbar_wait(&sm.pv_done, (g - 1) & 1);
               tc_fence_after();
-              if (__any_sync(0xffffffffu, fac != 1.f)) {
-#pragma unroll 1
-                for (int c8 = 0; c8 < 8; ++c8) {
-                  float o[32];
-                  const uint32_t a = tmem + kColO + c8 * 32 + lane_addr;
-                  tmem_ld<32>(a, o);
-                  tmem_wait_ld();
-#pragma unroll
-                  for (int k = 0; k < 32; ++k) o[k] *= fac;
-                  tmem_st<32>(a, o);
-                }
-                tmem_wait_st();
+              if (__any_sync(0xffffffffu, f_o != 1.f)) rescale_o(tmem + kColO + lane_addr, f_o);
+            };
+            if (t != 0) {
+              if constexpr (!DEFER) {
+                drain_and_rescale(fac);
+              } else {
+                // DEFER: O is rescaled further down, behind this tile's weighted pass (which only needs the new
+                // reference): the drain of the P.V products in flight -- a move's main cost -- then overlaps that pass.
+                // The factor waits in shared memory, not in a register across the pass: the slot is where this thread's
+                // row sum goes at the request's end; until then nobody reads it (the epilogue that read this buffer last,
+                // two requests back, and a merge of the previous request are behind that request's barriers).
+                sm.lred[rq & 1][slot][row] = fac;
               }
               lsum *= fac;
             }
@@ -971,6 +990,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
             // The reference is final for this tile and O is rescaled: the next tile may run its weighted pass while this
             // one runs its own (what orders them further -- P.V issue order, pv_done before a rescale -- does not hang
             // on fin).  The version store above is ordered before the arrival of gtid 0's warp by this barrier.
+            // (DEFER: O is not rescaled yet.  Nothing of a later tile reaches O before this tile's P.V -- P.V is issued in
+            // tile order and waits for this tile's publish, which follows the rescale below -- and a later tile that moves
+            // the reference again waits for this tile's P.V, pv_done, before it touches O.)
             named_bar_sync(gbar, 128);
             if (lane == 0) B200_BEACON(16 + (warp - 4), 25 + 100 * g);
             if (lane == 0) mbar_arrive(&sm.fin[g & 1]);
@@ -982,6 +1004,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           if (!over) weighted_pass();
           if (lane == 0) B200_BEACON(16 + (warp - 4), 13 + 100 * g);
           if (moved) {
+            if constexpr (DEFER) {
+              if (t != 0) {
+                const float f_o = sm.lred[rq & 1][slot][row];
+                // (same waits, same order as the undeferred form: see drain_and_rescale in the slow path)
+                if (g >= 2) mbar_wait(&sm.s_free[(g - 2) % kSBufs], ((g - 2) / kSBufs) & 1);
+                mbar_wait(&sm.pv_done, (g - 1) & 1);
+                tc_fence_after();
+                if (__any_sync(0xffffffffu, f_o != 1.f)) rescale_o(tmem + kColO + lane_addr, f_o);
+                tc_fence_before();  // (the publish below arrives on p_full behind this: P.V of this tile sees the rescaled O)
+              }
+            }
             lsum = fmaf(w32, acc, lsum);
             named_bar_sync(gbar, 128);  // lkrk is rewritten at this group's next tile
             break;
@@ -1280,15 +1313,21 @@ int launch_mla_pair(const MlaParams& prm, int num_sm_parts, bool pdl, cudaStream
   const int smem = pairk::kTotal + 1024;
   const int q_pairs = (prm.M + 127) / 128;
   const dim3 grid(2, q_pairs, num_sm_parts), block(128 + pairk::kSmThreads);
+  // B200_MLA_DEFER_RESCALE=1: the instantiation that rescales O behind a moving tile's weighted pass.  On logits whose
+  // row maxima keep growing (spread of 4-6 bits: 14-40 % of the tiles move a reference) it is 10-19 % faster; on the
+  // bench's logits (0.1 % of the tiles) it measures 2 % slower, so it is not the default.
+  static const bool defer = getenv("B200_MLA_DEFER_RESCALE") && atoi(getenv("B200_MLA_DEFER_RESCALE")) != 0;
+  auto launch = [&](auto* kernel) {
+    B200_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    return launch_kernel(kernel, grid, block, smem, stream, pdl, prm);
+  };
   if (prm.trace & 1) {  // diagnostic instantiation (B200_MLA_TRACE): pipeline timestamps, bit 2 = random delays
     static const int sites = getenv("B200_MLA_CHAOS_SITES") ? atoi(getenv("B200_MLA_CHAOS_SITES")) : 0x3ffffff;
     const int chaos = (prm.trace & 4) ? sites : 0;
     B200_CUDA(cudaMemcpyToSymbolAsync(pairk::g_chaos, &chaos, sizeof(int), 0, cudaMemcpyHostToDevice, stream));
-    B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-    return launch_kernel(pairk::mla_decode_pair_kernel<true>, grid, block, smem, stream, pdl, prm);
+    return defer ? launch(pairk::mla_decode_pair_kernel<true, true>) : launch(pairk::mla_decode_pair_kernel<true, false>);
   }
-  B200_CUDA(cudaFuncSetAttribute(pairk::mla_decode_pair_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
-  return launch_kernel(pairk::mla_decode_pair_kernel<false>, grid, block, smem, stream, pdl, prm);
+  return defer ? launch(pairk::mla_decode_pair_kernel<false, true>) : launch(pairk::mla_decode_pair_kernel<false, false>);
 }
 
 }  // namespace b200

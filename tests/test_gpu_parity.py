@@ -393,26 +393,33 @@ def test_mla_pair_is_timing_independent(tmp_path):
     """The CTA-pair kernel's hand-offs (row-reference moves, tile order, P / S / V rings, cluster relays, in-kernel
     merge) must not depend on who is fast: the diagnostic instantiation with a pseudo-random 0-4 us delay at each of its
     26 trace sites (B200_MLA_TRACE=5: warps, softmax groups and the two CTAs drift by whole tiles) has to reproduce the
-    production instantiation's output bit for bit, run after run, under both tile schedules."""
+    production instantiation's output bit for bit, run after run, under both tile schedules.  The same for the
+    instantiation that rescales O behind a moving tile's weighted pass (B200_MLA_DEFER_RESCALE=1): undisturbed and
+    disturbed it has to give the default instantiation's bits (the arithmetic is the same, only its place in time
+    differs)."""
     import subprocess
     import sys
     helper = os.path.join(os.path.dirname(os.path.abspath(__file__)), "chaos_case.py")
     outs = {}
-    for name, env_extra, repeats in (("plain", {}, 1), ("chaos", {"B200_MLA_TRACE": "5"}, 10)):
+    runs = (("plain", {}, 1), ("chaos", {"B200_MLA_TRACE": "5"}, 10), ("defer", {"B200_MLA_DEFER_RESCALE": "1"}, 1),
+            ("defer_chaos", {"B200_MLA_DEFER_RESCALE": "1", "B200_MLA_TRACE": "5"}, 8))
+    for name, env_extra, repeats in runs:
         env = dict(os.environ)
-        env.pop("B200_MLA_TRACE", None)
+        for k in ("B200_MLA_TRACE", "B200_MLA_DEFER_RESCALE", "B200_MLA_CHAOS_SITES"):
+            env.pop(k, None)
         env.update(env_extra)
         path = str(tmp_path / (name + ".npz"))
         r = subprocess.run([sys.executable, helper, path, str(repeats)], env=env, capture_output=True, text=True, timeout=600)
         assert r.returncode == 0, r.stderr[-3000:]
         outs[name] = np.load(path)
-    plain, chaos = outs["plain"], outs["chaos"]
+    plain = outs["plain"]
     n = 0
-    for key in chaos.files:
-        base = key.rsplit("_", 1)[0] + "_0"
-        assert np.array_equal(chaos[key], plain[base]), "%s differs from the undisturbed run" % key
-        n += 1
-    assert n >= 7 * 2 * 4 * 2
+    for name in ("chaos", "defer", "defer_chaos"):
+        for key in outs[name].files:
+            base = key.rsplit("_", 1)[0] + "_0"
+            assert np.array_equal(outs[name][key], plain[base]), "%s (%s) differs from the undisturbed run" % (key, name)
+            n += 1
+    assert n >= 7 * 2 * (10 + 1 + 8) * 2
 
 
 @pytest.mark.parametrize("h,s_q", [(128, 1), (16, 1)])

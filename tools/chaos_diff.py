@@ -3,7 +3,7 @@ B200_MLA_TRACE=5)?  Prints the tensors, how many elements and which (request, he
 import os, sys, subprocess, numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 helper = os.path.join(ROOT, "tests", "chaos_case.py")
-env = dict(os.environ); env.pop("B200_MLA_TRACE", None)
+env = dict(os.environ); env.pop("B200_MLA_TRACE", None)  # (B200_MLA_DEFER_RESCALE=1 in the environment tests that instantiation)
 subprocess.run([sys.executable, helper, "/tmp/plain.npz", "1"], env=env, check=True, capture_output=True)
 env["B200_MLA_TRACE"] = "5"
 subprocess.run([sys.executable, helper, "/tmp/chaos.npz", sys.argv[1] if len(sys.argv) > 1 else "12"], env=env, check=True, capture_output=True)
