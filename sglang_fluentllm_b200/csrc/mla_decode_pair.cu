@@ -642,8 +642,11 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(128 + kSmThreads, 1)
           }
           if (elect_one()) {
             umma_commit_pair(&sm.p_free[pp], 3);
-            umma_commit_pair(&sm.s_free[g % kSBufs], 3);
+            // pv_done in front of s_free: a reference move waits for s_free of tile g - 2 to know that pv_done is at most
+            // one phase behind its own parity wait; with the two arrivals in this order, seeing the former implies the
+            // latter
             umma_commit_pair(&sm.pv_done, 3);
+            umma_commit_pair(&sm.s_free[g % kSBufs], 3);
             if (t == sg.n_tiles - 1) umma_commit_pair(&sm.o_ready, 3);  // one completion per request: the epilogue's gate
           }
           __syncwarp();
