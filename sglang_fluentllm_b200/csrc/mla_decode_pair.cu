@@ -20,15 +20,16 @@
 //   Softmax: a thread owns (q row, 64 token columns = one page) -- exactly the reference's (row, page) granularity, so
 //   the page maximum, the page's e4m3 codes and the page sum (mla_decode.cu, comment above mla_decode_kernel) are
 //   thread-local.  O and L live under a per-row reference exponent R that moves only when a page exceeds it; the page
-//   weight 2^(ymax - R) rides on the codes as an e4m3 hi + lo pair (two P tiles, two P.V products per tile).  Two
-//   groups of four warps ping-pong over the tiles (group = tile parity); a tile's P depends on its predecessor only
+//   weight 2^(ymax - R) rides on the codes as an e4m3 hi + lo pair (two P tiles, two P.V products per tile).  Three
+//   groups of four warps take the tiles round-robin (group = tile index mod 3); a tile's P depends on its predecessor only
 //   through R, so the groups meet at a per-tile hand-off (fin) and a version counter; a group that computed under a
 //   reference that has since moved recomputes its second pass.  Both passes over S are compact 16-column loops (TMEM
 //   loads double-buffered, packed fp32x2 / f16x2 arithmetic, codes written straight into the swizzled P tiles); the
 //   first pass writes y back over S in TMEM, so the second one neither recomputes it nor needs the mask.
 //
 //   Warp roles per CTA (512 threads): warp 0 = TMA producer for Q, K pages (-> leader barrier via cta_group::2 TMA)
-//   and the k-scale ring; warp 2 = V producer; leader CTA: warp 1 issues every Q.K^T and warp 3 every P.V (two
+//   and the k-scale ring; warp 2 = V producer (it also zeroes the token rows past a request's end before it completes
+//   the unit's landing barrier); leader CTA: warp 1 issues every Q.K^T and warp 3 every P.V (two
 //   independent instruction streams into the in-order tensor pipe; Q.K^T runs up to four tiles ahead), other CTA:
 //   warp 1 relays the local P / O hand-offs to the leader; warp 1 also owns the TMEM allocation; warps 4-15 = three
 //   softmax / correction / epilogue groups (group = tile index mod 3; each owns one P pair).
