@@ -219,3 +219,32 @@ def test_two_step_wait_deadlocks():
 def test_producer_side_zero_fill_is_timing_independent(form):
     finished, misplaced, zeroed_ok = sweep(form)
     assert finished == 300 and not misplaced and zeroed_ok == 300
+
+
+# ---- the row reference's two lanes ("Deferred rescale") -------------------------------------------
+def _move_outcome(rng, read_from_shared, deferred):
+    """One reference move of one q row: its two threads (the lanes of the tile's two pages, in different warps) leave the
+    group barrier, take r_old, compute the same r_new, and the page-0 thread stores it.  Returns the rescale factors the
+    two threads apply (they must agree)."""
+    st_ref, r_new = 1.0, 5.0                     # shared row state; both threads have synced their view: rloc == st_ref
+    view = {0: st_ref, 1: st_ref}
+    t_read = {0: rng.uniform(0, 60), 1: rng.uniform(0, 60)}              # cycles after the barrier: warps drift
+    # page 0's store follows its read: behind the drain + rescale of O (~1000 cycles) in the undeferred order, at once
+    # in the deferred one
+    t_store = t_read[0] + (10 if deferred else 1000)
+    fac = {}
+    for page in (0, 1):
+        r_old = (r_new if (read_from_shared and page == 1 and t_read[1] > t_store) else st_ref) if read_from_shared else view[page]
+        fac[page] = 2.0 ** (r_old - (r_new if r_new > r_old else r_old))
+    return fac[0], fac[1]
+
+
+def test_row_reference_is_taken_from_the_threads_own_view():
+    rng = random.Random(0)
+    # re-reading shared memory: the deferred order lets the partner's store overtake the read in some schedules (the
+    # partner then sees "no move" and skips its half of the row); the undeferred order hid it behind the rescale
+    bad_deferred = sum(a != b for a, b in (_move_outcome(rng, True, True) for _ in range(2000)))
+    bad_undeferred = sum(a != b for a, b in (_move_outcome(rng, True, False) for _ in range(2000)))
+    assert bad_deferred > 0 and bad_undeferred == 0
+    # the shipped form (both instantiations): r_old is the thread's own synced view
+    assert all(a == b for a, b in (_move_outcome(rng, False, d) for d in (True, False) for _ in range(2000)))
